@@ -1,0 +1,210 @@
+/* drfe — B200-native RGB-D feature front end: the C ABI.
+ *
+ * This header is the drop-in boundary for DR-SLAM's per-frame feature front end
+ * (the work Frame::Frame spawns before Tracking::Track, reference src/Frame.cc:124-134):
+ *
+ *   Planar_SLAM::ORBextractor::operator()(image, mask, keypoints, descriptors)
+ *        reference include/ORBextractor.h:51-61, src/ORBextractor.cc:1043-1105
+ *   CAPE::process(cloud, nr_planes, nr_cylinders, seg_output, planes, cylinders)
+ *        reference src/CAPE/CAPE.h:47-48, src/CAPE/CAPE.cpp:47-457
+ *   PlaneDetection_CAPE::runPlaneDetection()  (depth -> organized cloud -> CAPE)
+ *        reference src/PlaneExtractor.cpp:111-191
+ *
+ * Plain C, POD only (no OpenCV / Eigen / torch types).  Every function returns an
+ * int status: 0 = DRFE_OK, negative = error (drfe_last_error() has the text).  There
+ * is NO CPU fallback: if no CUDA device is usable every create call fails loudly.
+ *
+ * Threading: a handle may be driven from any host thread, one call at a time per
+ * handle (the reference calls its extractors from a fresh std::thread each frame,
+ * Frame.cc:124-127).  Each handle owns a non-blocking CUDA stream; nothing runs on the
+ * legacy default stream.
+ *
+ * The header-only C++ adapters in dr-slam_b200/host/ re-create the reference's class
+ * signatures on top of these entry points; INTEGRATION.md shows the binding a DR-SLAM
+ * maintainer would add.
+ */
+#ifndef DRFE_H_
+#define DRFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRFE_OK 0
+#define DRFE_ERR_ARG (-1)      /* bad argument (null, size mismatch, unsupported config) */
+#define DRFE_ERR_CUDA (-2)     /* CUDA runtime error or no usable device                 */
+#define DRFE_ERR_CAPACITY (-3) /* a device-side buffer overflowed (result incomplete)     */
+#define DRFE_ERR_STATE (-4)    /* call order violated (e.g. download before enqueue)      */
+
+#define DRFE_MEM_HOST 0   /* pointer is host memory (pinned => the copy is asynchronous) */
+#define DRFE_MEM_DEVICE 1 /* pointer is device memory on the handle's device             */
+
+#define DRFE_MAX_LEVELS 16
+
+/* Same layout as cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave,
+ * class_id.  ORBextractor fills class_id = -1, size = int(31*scale[octave]), angle in
+ * degrees [0,360) (ORBextractor.cc:837-847, :77-104). */
+typedef struct drfe_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} drfe_keypoint;
+
+/* Constructor arguments of ORBextractor (ORBextractor.h:51-52). */
+typedef struct drfe_orb_params {
+  int32_t nfeatures;
+  float scale_factor;
+  int32_t nlevels;
+  int32_t ini_th_fast;
+  int32_t min_th_fast;
+} drfe_orb_params;
+
+/* Mirror of the public data members of PlaneSeg (src/CAPE/PlaneSeg.h:15-28). */
+typedef struct drfe_plane {
+  int32_t nr_pts, min_nr_pts;
+  double x_acc, y_acc, z_acc, xx_acc, yy_acc, zz_acc, xy_acc, xz_acc, yz_acc;
+  float score, MSE;
+  int32_t planar;
+  double mean[3], normal[3], d;
+} drfe_plane;
+
+/* Mirror of what CAPE::process copies out per cylinder (CAPE.cpp:434-445). */
+typedef struct drfe_cylinder {
+  float radius;
+  double center[3];
+  double axis[3];
+} drfe_cylinder;
+
+/* Constructor arguments of CAPE (CAPE.h:47) + camera intrinsics used by the wrapper
+ * (PlaneExtractor.cpp:117-127). */
+typedef struct drfe_cape_params {
+  int32_t depth_height, depth_width;
+  int32_t cell_width, cell_height;
+  int32_t cylinder_detection;
+  float min_cos_angle_4_merge; /* reference default 0.97814; DR-SLAM passes cos(pi/12) */
+  float max_merge_dist;        /* reference default 900;     DR-SLAM passes Plane.MAX_MERGE_DIST */
+} drfe_cape_params;
+
+typedef struct drfe_orb drfe_orb;
+typedef struct drfe_cape drfe_cape;
+
+/* ------------------------------------------------------------------ general */
+const char* drfe_last_error(void);   /* thread-local text of the last failure            */
+const char* drfe_version(void);
+int drfe_device_count(int* count);   /* number of CUDA devices visible                    */
+/* total number of drfe kernel launches issued by this process (bench "gpu_launches") */
+int64_t drfe_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ ORB
+ * One handle = one ORBextractor instance bound to a device, an image size and a maximum
+ * frame batch (frames of a batch are independent; batch=1 reproduces operator()). */
+int drfe_orb_create(const drfe_orb_params* params, int width, int height, int max_batch,
+                    int device, drfe_orb** out);
+int drfe_orb_destroy(drfe_orb* h);
+
+/* Getters mirroring ORBextractor::GetLevels / GetScaleFactor(s) / GetInverseScaleFactors /
+ * GetScaleSigmaSquares / GetInverseScaleSigmaSquares (ORBextractor.h:63-83); arrays hold
+ * nlevels floats. */
+int drfe_orb_get_levels(const drfe_orb* h);
+float drfe_orb_get_scale_factor(const drfe_orb* h);
+int drfe_orb_get_scale_factors(const drfe_orb* h, float* scale, float* inv_scale,
+                               float* sigma2, float* inv_sigma2);
+int drfe_orb_features_per_level(const drfe_orb* h, int level); /* mnFeaturesPerLevel */
+/* upper bound on keypoints one frame can return (>= nfeatures; the quadtree may overshoot
+ * each level's quota by up to 3, ORBextractor.cc:730) */
+int drfe_orb_max_keypoints(const drfe_orb* h);
+
+/* operator()(image, mask, keypoints, descriptors) for ONE 8-bit gray frame in host memory.
+ * `mask` is ignored by the reference (ORBextractor.h:58) and has no parameter here.
+ * gray == NULL or w/h == 0 mirrors the reference's silent return on an empty image
+ * (ORBextractor.cc:1046): *n is left untouched and DRFE_OK is returned.
+ * desc receives 32 bytes per keypoint, row-aligned with kps. */
+int drfe_orb_extract(drfe_orb* h, const uint8_t* gray, int width, int height, size_t row_stride,
+                     drfe_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* Batched, asynchronous form.  enqueue: (copy nframes images, H2D if mem_kind is host,) and
+ * launch the whole pipeline on the handle's stream; returns without waiting.
+ * download: wait, then copy results to host: kps[f*cap_per_frame + i], desc[(f*cap+i)*32],
+ * counts[f].  Any of kps/desc may be NULL to skip that copy. */
+int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride,
+                     size_t frame_stride, int mem_kind);
+int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_per_frame,
+                      int* counts);
+int drfe_orb_sync(drfe_orb* h);
+void* drfe_orb_stream(drfe_orb* h); /* the handle's cudaStream_t */
+
+/* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
+ * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
+ * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */
+int drfe_orb_level_size(const drfe_orb* h, int level, int* width, int* height);
+int drfe_orb_get_pyramid(drfe_orb* h, int frame, int level, int bordered, uint8_t* dst);
+int drfe_orb_get_blurred(drfe_orb* h, int frame, int level, uint8_t* dst);
+/* FAST candidates of one level: xyr[3*i..] = x, y (region coords, origin (16,16)) and
+ * response, in no particular order (compare as a set); returns the count in *n. */
+int drfe_orb_get_candidates(drfe_orb* h, int frame, int level, float* xyr, int cap, int* n);
+/* quadtree-retained keypoints of one level in the reference's list order (level
+ * coordinates, angle filled, not yet scaled to level 0). */
+int drfe_orb_get_level_keypoints(drfe_orb* h, int frame, int level, drfe_keypoint* dst, int cap,
+                                 int* n);
+/* device time of the last enqueue, split by stage (ms); names[i] are static strings.
+ * Only meaningful after drfe_orb_set_profiling(h, 1). */
+int drfe_orb_set_profiling(drfe_orb* h, int on);
+int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, int* nstages);
+
+/* ------------------------------------------------------------------ CAPE
+ * One handle = one CAPE instance (CAPE.h:47) for a fixed depth size, on one device, able
+ * to process up to max_batch independent frames per call. */
+int drfe_cape_create(const drfe_cape_params* params, int max_batch, int device, drfe_cape** out);
+int drfe_cape_destroy(drfe_cape* h);
+
+/* CAPE::process on cell-major organized clouds (the layout organizePointCloudByCell
+ * produces, PlaneExtractor.cpp:80-99): per frame 3*H*W floats, column-major N x 3
+ * (all X, then all Y, then all Z), point index = cell_id*cell_w*cell_h + local_r*cell_w +
+ * local_c. */
+int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_t frame_stride,
+                            int mem_kind);
+/* PlaneDetection_CAPE::runPlaneDetection: depth (float, same unit the thresholds are
+ * meant in) -> cloud in double -> float, cell-major scatter, then CAPE::process. */
+int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_t row_stride,
+                            size_t frame_stride, int mem_kind, float fx, float fy, float cx,
+                            float cy);
+/* wait + copy out.  seg_out: nframes * H*W labels (0 = none, 1..n planes, 51.. cylinders),
+ * fully written (the reference only writes labelled pixels of a caller-zeroed image).
+ * planes[f*plane_cap + i]; cylinders may be NULL when cylinder detection is off. */
+int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int plane_cap,
+                       int* nr_planes, drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders);
+int drfe_cape_sync(drfe_cape* h);
+void* drfe_cape_stream(drfe_cape* h);
+
+/* Single-frame conveniences with the reference's argument meaning. */
+int drfe_cape_process(drfe_cape* h, const float* cloud_cellmajor, uint8_t* seg_out,
+                      drfe_plane* planes, int plane_cap, int* nr_planes, drfe_cylinder* cylinders,
+                      int cyl_cap, int* nr_cylinders);
+int drfe_cape_process_depth(drfe_cape* h, const float* depth, size_t row_stride, float fx, float fy,
+                            float cx, float cy, uint8_t* seg_out, drfe_plane* planes, int plane_cap,
+                            int* nr_planes, drfe_cylinder* cylinders, int cyl_cap,
+                            int* nr_cylinders);
+
+/* intermediates for parity tests, copied to host */
+int drfe_cape_num_cells(const drfe_cape* h, int* cells_x, int* cells_y);
+int drfe_cape_get_cloud(drfe_cape* h, int frame, float* cloud_cellmajor);
+/* per-cell PlaneSeg after stage 1 (CAPE.cpp:62-80): cells[cell_id] */
+int drfe_cape_get_cells(drfe_cape* h, int frame, drfe_plane* cells);
+/* grid_plane_seg_map after region growing + the eroded map used for painting */
+int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t* eroded_map);
+int drfe_cape_set_profiling(drfe_cape* h, int on);
+int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages);
+
+/* ------------------------------------------------------------------ synthetic input
+ * Deterministic procedural RGB-D frame (textured Manhattan corridor / room) used by the
+ * tests and bench: gray u8 (w*h) and depth f32 metres (w*h), seed selects the camera pose.
+ * Host-only helper, no GPU involved.  scene: 0 = corridor, 1 = room, 2 = room + pillars. */
+int drfe_synth_frame(int width, int height, int scene, uint32_t seed, float depth_unit_scale,
+                     uint8_t* gray, float* depth, float* fx, float* fy, float* cx, float* cy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRFE_H_ */

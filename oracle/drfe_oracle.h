@@ -1,0 +1,51 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY (see header of orb_oracle.cpp / cape_oracle.cpp).
+ * C entry points of the CPU restatement; loaded through ctypes by tests/, smoke() and
+ * bench.py's cpu_baseline / --impl reference legs.  Never linked into libdrfe.so. */
+#ifndef DRFE_ORACLE_H_
+#define DRFE_ORACLE_H_
+#include "../include/drfe.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- ORB (orb_oracle.cpp) ---- */
+void* orc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+void orc_orb_destroy(void* h);
+int orc_orb_run(void* h, const uint8_t* gray, int w, int hgt, int stride);
+int orc_orb_features_per_level(void* h, int level);
+float orc_orb_scale_factor(void* h, int level);
+int orc_orb_umax(void* h, int v);
+int orc_orb_level_size(void* h, int level, int* w, int* hgt);
+int orc_orb_get_level(void* h, int level, int bordered, uint8_t* dst);
+int orc_orb_get_blurred(void* h, int level, uint8_t* dst);
+int orc_orb_get_candidates(void* h, int level, float* xyr, int cap);
+int orc_orb_get_level_keypoints(void* h, int level, drfe_keypoint* dst, int cap);
+int orc_orb_level_tie(void* h, int level);
+int orc_orb_get_result(void* h, drfe_keypoint* kps, uint8_t* desc, int cap);
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
+void orc_border101_u8(const uint8_t* src, int w, int h, int b, uint8_t* dst);
+int orc_fast9_nms(const uint8_t* img, int stride, int w, int h, int threshold, float* xyr, int cap);
+void orc_gaussian7_u8(const uint8_t* src, int w, int h, uint8_t* dst);
+float orc_fast_atan2(float y, float x);
+int orc_distribute_quadtree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N,
+                            float* out_xyr, int cap, int* tie);
+
+/* ---- CAPE (cape_oracle.cpp) ---- */
+void* orc_cape_create(int depth_height, int depth_width, int cell_width, int cell_height,
+                      int cylinder_detection, float min_cos_angle_4_merge, float max_merge_dist);
+void orc_cape_destroy(void* h);
+/* PlaneDetection_CAPE::runPlaneDetection cloud + organize (PlaneExtractor.cpp:112-152) */
+void orc_cape_depth_to_cloud(void* h, const float* depth, int row_stride, float fx, float fy,
+                             float cx, float cy, float* cloud_cellmajor);
+/* CAPE::process; seg_out must be zeroed by the caller like the reference */
+int orc_cape_process(void* h, const float* cloud_cellmajor, uint8_t* seg_out, drfe_plane* planes,
+                     int plane_cap, int* nr_planes, drfe_cylinder* cyls, int cyl_cap,
+                     int* nr_cylinders);
+int orc_cape_get_cells(void* h, drfe_plane* cells);
+int orc_cape_get_grid_maps(void* h, int32_t* plane_map, uint8_t* eroded_map);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,257 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/libdrfe_oracle.so (the CPU restatement of the reference's ORB +
+CAPE front end, see orb_oracle.cpp / cape_oracle.cpp).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product (dr-slam_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdrfe_oracle.so")
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+class Plane(C.Structure):
+    _fields_ = [("nr_pts", C.c_int32), ("min_nr_pts", C.c_int32),
+                ("x_acc", C.c_double), ("y_acc", C.c_double), ("z_acc", C.c_double),
+                ("xx_acc", C.c_double), ("yy_acc", C.c_double), ("zz_acc", C.c_double),
+                ("xy_acc", C.c_double), ("xz_acc", C.c_double), ("yz_acc", C.c_double),
+                ("score", C.c_float), ("MSE", C.c_float), ("planar", C.c_int32),
+                ("mean", C.c_double * 3), ("normal", C.c_double * 3), ("d", C.c_double)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+PLANE_DTYPE = np.dtype([("nr_pts", "<i4"), ("min_nr_pts", "<i4"),
+                        ("x_acc", "<f8"), ("y_acc", "<f8"), ("z_acc", "<f8"),
+                        ("xx_acc", "<f8"), ("yy_acc", "<f8"), ("zz_acc", "<f8"),
+                        ("xy_acc", "<f8"), ("xz_acc", "<f8"), ("yz_acc", "<f8"),
+                        ("score", "<f4"), ("MSE", "<f4"), ("planar", "<i4"),
+                        ("mean", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8")], align=True)
+assert KP_DTYPE.itemsize == 28 and PLANE_DTYPE.itemsize == C.sizeof(Plane)
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, f32p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.orc_orb_create.restype = C.c_void_p
+        L.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_orb_destroy.argtypes = [C.c_void_p]
+        L.orc_orb_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_orb_features_per_level.argtypes = [C.c_void_p, C.c_int]
+        L.orc_orb_scale_factor.argtypes = [C.c_void_p, C.c_int]
+        L.orc_orb_scale_factor.restype = C.c_float
+        L.orc_orb_umax.argtypes = [C.c_void_p, C.c_int]
+        L.orc_orb_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+        L.orc_orb_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_orb_get_blurred.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_orb_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_orb_get_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_orb_level_tie.argtypes = [C.c_void_p, C.c_int]
+        L.orc_orb_get_result.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_border101_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_fast9_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_gaussian7_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_distribute_quadtree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_void_p, C.c_int, i32p]
+        L.orc_cape_create.restype = C.c_void_p
+        L.orc_cape_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.orc_cape_destroy.argtypes = [C.c_void_p]
+        L.orc_cape_depth_to_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                              C.c_float, C.c_float, C.c_void_p]
+        L.orc_cape_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, i32p,
+                                       C.c_void_p, C.c_int, i32p]
+        L.orc_cape_get_cells.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_cape_get_grid_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OrbOracle:
+    """CPU restatement of Planar_SLAM::ORBextractor (ORBextractor.cc:410-1132)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = self.L.orc_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_orb_destroy(self.h)
+            self.h = None
+
+    def features_per_level(self):
+        return [self.L.orc_orb_features_per_level(self.h, l) for l in range(self.nlevels)]
+
+    def scale_factors(self):
+        return [self.L.orc_orb_scale_factor(self.h, l) for l in range(self.nlevels)]
+
+    def umax(self):
+        return [self.L.orc_orb_umax(self.h, v) for v in range(16)]
+
+    def run(self, gray):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        self._gray = gray
+        return self.L.orc_orb_run(self.h, _p(gray), gray.shape[1], gray.shape[0], gray.strides[0])
+
+    def level_size(self, level):
+        w, h = C.c_int32(), C.c_int32()
+        self.L.orc_orb_level_size(self.h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, level, bordered=False):
+        w, h = self.level_size(level)
+        if bordered:
+            w, h = w + 38, h + 38
+        out = np.empty((h, w), np.uint8)
+        self.L.orc_orb_get_level(self.h, level, int(bordered), _p(out))
+        return out
+
+    def blurred(self, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        n = self.L.orc_orb_get_blurred(self.h, level, _p(out))
+        return out if n else None
+
+    def candidates(self, level):
+        cap = 1 << 17
+        buf = np.empty((cap, 3), np.float32)
+        n = self.L.orc_orb_get_candidates(self.h, level, _p(buf), cap)
+        assert n <= cap
+        return buf[:n].copy()
+
+    def level_keypoints(self, level):
+        cap = self.nfeatures * 4 + 64
+        buf = np.empty(cap, KP_DTYPE)
+        n = self.L.orc_orb_get_level_keypoints(self.h, level, _p(buf), cap)
+        return buf[:n].copy()
+
+    def level_tie(self, level):
+        return self.L.orc_orb_level_tie(self.h, level)
+
+    def result(self):
+        cap = self.nfeatures * 4 + 64
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = self.L.orc_orb_get_result(self.h, _p(kps), _p(desc), cap)
+        return kps[:n].copy(), desc[:n].copy()
+
+    def extract(self, gray):
+        self.run(gray)
+        return self.result()
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def border101(src, b):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((src.shape[0] + 2 * b, src.shape[1] + 2 * b), np.uint8)
+    lib().orc_border101_u8(_p(src), src.shape[1], src.shape[0], b, _p(dst))
+    return dst
+
+
+def fast9_nms(img, threshold):
+    """cv::FAST(img, threshold, nonmax=True) restatement -> (n,3) [x, y, response]."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    cap = img.shape[0] * img.shape[1] // 4 + 16
+    buf = np.empty((cap, 3), np.float32)
+    n = lib().orc_fast9_nms(_p(img), img.strides[0], img.shape[1], img.shape[0], threshold, _p(buf), cap)
+    return buf[:n].copy()
+
+
+def gaussian7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7_u8(_p(src), src.shape[1], src.shape[0], _p(dst))
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def distribute_quadtree(xyr, min_x, max_x, min_y, max_y, n_want):
+    xyr = np.ascontiguousarray(xyr, np.float32)
+    out = np.empty((len(xyr) + 8, 3), np.float32)
+    tie = C.c_int32(0)
+    n = lib().orc_distribute_quadtree(_p(xyr), len(xyr), min_x, max_x, min_y, max_y, n_want, _p(out),
+                                      len(out), C.byref(tie))
+    return out[:n].copy(), tie.value
+
+
+class CapeOracle:
+    """CPU restatement of CAPE (CAPE.cpp) + the DR-SLAM wrapper (PlaneExtractor.cpp:111-191)."""
+
+    def __init__(self, height=480, width=640, cell_w=20, cell_h=20, cylinder=False,
+                 min_cos=float(np.float32(np.cos(np.pi / 12))), max_merge_dist=50.0):
+        self.L = lib()
+        self.H, self.W, self.cw, self.ch = height, width, cell_w, cell_h
+        self.ncx, self.ncy = width // cell_w, height // cell_h
+        self.h = self.L.orc_cape_create(height, width, cell_w, cell_h, int(cylinder), min_cos, max_merge_dist)
+        if not self.h:
+            raise NotImplementedError("oracle: cylinder detection is not restated")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_cape_destroy(self.h)
+            self.h = None
+
+    def depth_to_cloud(self, depth, fx, fy, cx, cy):
+        depth = np.ascontiguousarray(depth, np.float32)
+        cloud = np.zeros(3 * self.H * self.W, np.float32)
+        self.L.orc_cape_depth_to_cloud(self.h, _p(depth), depth.strides[0] // 4, fx, fy, cx, cy, _p(cloud))
+        return cloud
+
+    def process(self, cloud, plane_cap=256):
+        cloud = np.ascontiguousarray(cloud, np.float32)
+        seg = np.zeros((self.H, self.W), np.uint8)
+        planes = np.zeros(plane_cap, PLANE_DTYPE)
+        npl, ncy = C.c_int32(0), C.c_int32(0)
+        self.L.orc_cape_process(self.h, _p(cloud), _p(seg), _p(planes), plane_cap, C.byref(npl), None, 0,
+                                C.byref(ncy))
+        return seg, planes[:npl.value].copy()
+
+    def cells(self):
+        out = np.zeros(self.ncx * self.ncy, PLANE_DTYPE)
+        self.L.orc_cape_get_cells(self.h, _p(out))
+        return out
+
+    def grid_maps(self):
+        pm = np.zeros((self.ncy, self.ncx), np.int32)
+        em = np.zeros((self.ncy, self.ncx), np.uint8)
+        self.L.orc_cape_get_grid_maps(self.h, _p(pm), _p(em))
+        return pm, em
