@@ -1,0 +1,38 @@
+// drfe C ABI: process-wide pieces (error text, version, launch counter).
+#include <cuda_runtime.h>
+
+#include "drfe_internal.h"
+
+namespace drfe {
+
+static thread_local char t_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace drfe
+
+extern "C" {
+
+const char* drfe_last_error(void) { return drfe::t_err; }
+const char* drfe_version(void) { return "drfe 0.1 (sm_100a)"; }
+int64_t drfe_kernel_launch_count(void) { return (int64_t)drfe::g_launches.load(); }
+int drfe_device_count(int* count) {
+  if (!count) return DRFE_ERR_ARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    drfe::set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return DRFE_ERR_CUDA;
+  }
+  *count = n;
+  return DRFE_OK;
+}
+
+}  // extern "C"

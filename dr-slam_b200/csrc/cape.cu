@@ -1,0 +1,881 @@
+// drfe CAPE plane extraction for sm_100a — the work of PlaneDetection_CAPE::runPlaneDetection
+// (reference src/PlaneExtractor.cpp:111-191) and CAPE::process (src/CAPE/CAPE.cpp:47-457),
+// batched over independent frames.  Built with --fmad=false: every float/double operation
+// is individually rounded exactly like the CPU oracle.
+//
+// Kernels:
+//   k_cape_cells   half-warp per grid cell: depth -> XYZ (double math, PlaneExtractor.cpp:
+//                  117-127) -> cell-major cloud, the 9 float moment sums in the declared
+//                  16-lane tree, missing-data / depth-jump tests and fitPlane with a 3x3
+//                  Jacobi eigen-solve in registers (PlaneSeg.cpp:8-142)
+//   k_cape_grid    one CTA per frame: normal histogram, seeded region growing as frontier
+//                  propagation, plane merging, erode/dilate cell masks (CAPE.cpp:82-291)
+//   k_cape_refine  one warp per cell: per-pixel boundary refinement + seg_output in image
+//                  layout (CAPE.cpp:294-319, 395-432)
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "drfe_internal.h"
+
+namespace drfe {
+
+static const int kMaxPlanes = 255;       // labels are uchar (CAPE.cpp:286)
+static const int kHistBins = 20;
+
+struct CapeDev {
+  int H, W, cw, ch, ncx, ncy, ncells, npc, B;
+  float min_cos, max_merge_dist;
+  float fx, fy, cx, cy;
+  const float* depth; long long depth_rs, depth_fs;   // input depth (may be null: cloud given)
+  float* cloud;                 // [B][3][H*W] cell-major
+  drfe_plane* cells;            // [B][ncells]
+  float* tols;                  // [B][ncells]
+  int* plane_map;               // [B][ncells]
+  uint8_t* eroded_map;          // [B][ncells]
+  uint32_t* border_bits;        // [B][ncells][8]  bit p set: cell is in mask_diff of final plane p (1-based)
+  drfe_plane* segs;             // [B][kMaxPlanes+1] scratch: plane_segments
+  drfe_plane* planes;           // [B][kMaxPlanes]   plane_segments_final
+  float4* plane_eq;             // [B][kMaxPlanes+1] (nx,ny,nz,d) float of final planes (1-based)
+  float* plane_maxd;            // [B][kMaxPlanes+1] 9*MSE
+  int* nplanes;                 // [B]
+  uint8_t* seg;                 // [B][H*W]
+  int* status;
+};
+
+// ---- 3x3 symmetric eigen-solve (cyclic Jacobi).  Mirrors eig3_sym() of the oracle
+// operation for operation; only + - * / sqrt fabs, no FMA.
+__device__ void eig3_sym(const double in[6], double w[3], double v[3][3]) {
+  double a[3][3] = {{in[0], in[1], in[2]}, {in[1], in[3], in[4]}, {in[2], in[4], in[5]}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    if (a[0][1] == 0.0 && a[0][2] == 0.0 && a[1][2] == 0.0) break;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int p = (k == 2) ? 1 : 0, q = (k == 0) ? 1 : 2, r = (k == 0) ? 2 : ((k == 1) ? 1 : 0);
+      const double apq = a[p][q];
+      if (apq == 0.0) continue;
+      const double app = a[p][p], aqq = a[q][q];
+      const double g = 100.0 * fabs(apq);
+      if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
+        a[p][q] = a[q][p] = 0.0;
+        continue;
+      }
+      const double h = aqq - app;
+      double t;
+      if (fabs(h) + g == fabs(h)) {
+        t = apq / h;
+      } else {
+        const double theta = 0.5 * h / apq;
+        t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+        if (theta < 0.0) t = -t;
+      }
+      const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+      a[p][p] = app - t * apq;
+      a[q][q] = aqq + t * apq;
+      a[p][q] = a[q][p] = 0.0;
+      const double arp = a[r][p], arq = a[r][q];
+      a[r][p] = a[p][r] = c * arp - s * arq;
+      a[r][q] = a[q][r] = s * arp + c * arq;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const double vp = v[m][p], vq = v[m][q];
+        v[m][p] = c * vp - s * vq;
+        v[m][q] = s * vp + c * vq;
+      }
+    }
+  }
+  int i0 = 0, i1 = 1, i2 = 2;
+  const double d[3] = {a[0][0], a[1][1], a[2][2]};
+  if (d[i1] < d[i0]) { int t = i0; i0 = i1; i1 = t; }
+  if (d[i2] < d[i1]) { int t = i1; i1 = i2; i2 = t; }
+  if (d[i1] < d[i0]) { int t = i0; i0 = i1; i1 = t; }
+  double vv[3][3];
+  const int idx[3] = {i0, i1, i2};
+  for (int i = 0; i < 3; ++i) {
+    w[i] = d[idx[i]];
+    for (int m = 0; m < 3; ++m) vv[m][i] = v[m][idx[i]];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int m = 0; m < 3; ++m) v[m][i] = vv[m][i];
+}
+
+// PlaneSeg::fitPlane (PlaneSeg.cpp:111-142)
+__device__ void fit_plane(drfe_plane& s) {
+  const double n = (double)s.nr_pts;
+  s.mean[0] = s.x_acc / n; s.mean[1] = s.y_acc / n; s.mean[2] = s.z_acc / n;
+  const double cov[6] = {s.xx_acc - s.x_acc * s.x_acc / n, s.xy_acc - s.x_acc * s.y_acc / n,
+                         s.xz_acc - s.x_acc * s.z_acc / n, s.yy_acc - s.y_acc * s.y_acc / n,
+                         s.yz_acc - s.y_acc * s.z_acc / n, s.zz_acc - s.z_acc * s.z_acc / n};
+  double w[3], v[3][3];
+  eig3_sym(cov, w, v);
+  const double v0 = v[0][0], v1 = v[1][0], v2 = v[2][0];
+  double d = -(v0 * s.mean[0] + v1 * s.mean[1] + v2 * s.mean[2]);
+  if (d > 0) { s.normal[0] = v0; s.normal[1] = v1; s.normal[2] = v2; }
+  else { s.normal[0] = -v0; s.normal[1] = -v1; s.normal[2] = -v2; d = -d; }
+  s.d = d;
+  s.MSE = (float)(w[0] / n);
+  s.score = (float)(w[1] / w[0]);
+}
+
+__device__ __forceinline__ void expand_seg(drfe_plane& a, const drfe_plane& b) {
+  a.x_acc += b.x_acc; a.y_acc += b.y_acc; a.z_acc += b.z_acc;
+  a.xx_acc += b.xx_acc; a.yy_acc += b.yy_acc; a.zz_acc += b.zz_acc;
+  a.xy_acc += b.xy_acc; a.xz_acc += b.xz_acc; a.yz_acc += b.yz_acc;
+  a.nr_pts += b.nr_pts;
+}
+
+// ------------------------------------------------------------------ cells
+// 16 lanes per cell.  Lane l owns the declared accumulator l of each of the 9 sums:
+// elements l, l+16, l+32, ... in ascending order (Eigen's two-packet AVX redux, App. B.1),
+// then lanes l and l+8 are added, then the 8 -> 4 -> 2 -> 1 halving tree.
+__device__ __forceinline__ float tree16(float v, int n, int body, const float* tail_vals, unsigned mask, int lane16,
+                                        float extra8) {
+  // p8 = lane[l] + lane[l+8]
+  float p = v + __shfl_down_sync(mask, v, 8, 16);
+  if (n - body >= 8) p = p + extra8;                      // one more aligned packet (lanes 0..7)
+  p = p + __shfl_down_sync(mask, p, 4, 16);
+  p = p + __shfl_down_sync(mask, p, 2, 16);
+  p = p + __shfl_down_sync(mask, p, 1, 16);
+  (void)tail_vals; (void)lane16;
+  return p;  // valid in lane 0 of the group
+}
+
+__global__ void __launch_bounds__(128) k_cape_cells(const CapeDev* __restrict__ Pp, int nframes) {
+  const CapeDev& P = *Pp;
+  const int gid = (blockIdx.x * 128 + threadIdx.x) >> 4;   // global cell index over the batch
+  const int l = threadIdx.x & 15;
+  const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+  if (gid >= nframes * P.ncells) return;                    // whole 16-lane groups exit together
+  const int f = gid / P.ncells, cell = gid - f * P.ncells;
+  const int npc = P.npc, cw = P.cw;
+  const long long N = (long long)P.H * P.W;
+  float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+  float* CY = CX + N;
+  float* CZ = CY + N;
+  const int body = (npc / 16) * 16;
+  const int full8 = (npc - body >= 8) ? body + 8 : body;
+  float ax = 0, ay = 0, az = 0, axx = 0, ayy = 0, azz = 0, axy = 0, axz = 0, ayz = 0;
+  float ex = 0, ey = 0, ez = 0, exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;  // extra packet
+  int cnt = 0;
+  const float* dsrc = nullptr;
+  const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
+  if (P.depth) dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;
+  for (int i = l; i < npc; i += 16) {
+    float x, y, z;
+    if (dsrc) {
+      const int lr = i / cw, lc = i - lr * cw;
+      const float dz = __ldg(dsrc + (long long)lr * P.depth_rs + lc);
+      const double zd = (double)dz;
+      const double xd = ((double)(cc * cw + lc) - (double)P.cx) * zd / (double)P.fx;
+      const double yd = ((double)(cr * P.ch + lr) - (double)P.cy) * zd / (double)P.fy;
+      x = (float)xd; y = (float)yd; z = (float)zd;
+      CX[i] = x; CY[i] = y; CZ[i] = z;
+    } else {
+      x = CX[i]; y = CY[i]; z = CZ[i];
+    }
+    cnt += (z > 0.f);
+    if (i < body) {
+      if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
+      else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
+             axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
+    } else if (i < full8) {
+      ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) cnt += __shfl_down_sync(mask, cnt, o, 16);
+  // the extra packet sits in lanes body%16.. of the iteration; bring values to lanes 0..7
+  // (body is a multiple of 16, so element body+j is handled by lane j: already in place)
+  float sx = tree16(ax, npc, body, nullptr, mask, l, ex), sy = tree16(ay, npc, body, nullptr, mask, l, ey),
+        sz = tree16(az, npc, body, nullptr, mask, l, ez), sxx = tree16(axx, npc, body, nullptr, mask, l, exx),
+        syy = tree16(ayy, npc, body, nullptr, mask, l, eyy), szz = tree16(azz, npc, body, nullptr, mask, l, ezz),
+        sxy = tree16(axy, npc, body, nullptr, mask, l, exy), sxz = tree16(axz, npc, body, nullptr, mask, l, exz),
+        syz = tree16(ayz, npc, body, nullptr, mask, l, eyz);
+  __syncwarp(mask);
+  if (l != 0) return;
+  // scalar tail (Eigen's unaligned end), sequential
+  for (int i = full8; i < npc; ++i) {
+    const float x = CX[i], y = CY[i], z = CZ[i];
+    sx = sx + x; sy = sy + y; sz = sz + z; sxx = sxx + x * x; syy = syy + y * y; szz = szz + z * z;
+    sxy = sxy + x * y; sxz = sxz + x * z; syz = syz + y * z;
+  }
+  drfe_plane s;
+  memset(&s, 0, sizeof(s));                        // zero-filled PlaneSeg storage (App. B.2)
+  s.min_nr_pts = npc / 2;
+  s.nr_pts = cnt;
+  s.planar = 1;
+  float tol = 0.f;
+  const int chh = npc / cw;
+  if (s.nr_pts < s.min_nr_pts) s.planar = 0;
+  if (s.planar) {  // horizontal then vertical depth-jump scan through the middle (PlaneSeg.cpp:36-76)
+    int jumps = 0;
+    int i = cw * (chh / 2), j = i + cw;
+    float z_last = fmaxf(CZ[i], CZ[i + 1]);
+    ++i;
+    while (i < j) {
+      const float z = CZ[i];
+      if (z > 0 && (double)fabsf(z - z_last) < 100.0) z_last = z;
+      else if (z > 0) ++jumps;
+      ++i;
+    }
+    if (jumps > 1) s.planar = 0;
+  }
+  if (s.planar) {
+    int jumps = 0;
+    int i = cw / 2, j = npc - i;
+    float z_last = fmaxf(CZ[i], CZ[i + cw]);
+    i += cw;
+    while (i < j) {
+      const float z = CZ[i];
+      if (z > 0 && (double)fabsf(z - z_last) < 100.0) z_last = z;
+      else if (z > 0) ++jumps;
+      i += cw;
+    }
+    if (jumps > 1) s.planar = 0;
+  }
+  if (s.planar) {
+    s.x_acc = sx; s.y_acc = sy; s.z_acc = sz; s.xx_acc = sxx; s.yy_acc = syy; s.zz_acc = szz;
+    s.xy_acc = sxy; s.xz_acc = sxz; s.yz_acc = syz;
+    fit_plane(s);
+    const double lim = 0.000001425 * s.mean[2] * s.mean[2] + 10.0;   // Params.h:6-7
+    if ((double)s.MSE > lim * lim) s.planar = 0;
+    if (s.planar) {  // cell_distance_tols (CAPE.cpp:69-73)
+      const float dx = CX[npc - 1] - CX[0], dy = CY[npc - 1] - CY[0], dz = CZ[npc - 1] - CZ[0];
+      const float diam = sqrtf(dx * dx + dy * dy + dz * dz);
+      const float sin_merge = (float)sqrt(1.0 - (double)P.min_cos * (double)P.min_cos);
+      const float t = fminf(fmaxf(diam * sin_merge, 20.0f), P.max_merge_dist);
+      tol = t * t;
+    }
+  }
+  P.cells[(long long)f * P.ncells + cell] = s;
+  P.tols[(long long)f * P.ncells + cell] = tol;
+}
+
+// ------------------------------------------------------------------ grid stage
+struct CellS {            // per-cell data kept in shared memory by k_cape_grid
+  double n[3], m[3], d;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict__ Pp) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const CapeDev& P = *Pp;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nc = P.ncells, ncx = P.ncx, ncy = P.ncy;
+  CellS* cs = reinterpret_cast<CellS*>(smem);
+  float* tol = reinterpret_cast<float*>(cs + nc);
+  float* mse = tol + nc;
+  int* bin = reinterpret_cast<int*>(mse + nc);      // histogram bin per cell (-1 = removed / non planar)
+  int* pmap = bin + nc;                              // grid_plane_seg_map
+  int* list = pmap + nc;                             // ordered cell list scratch
+  int* hist = list + nc;                             // [400]
+  uint32_t* assoc = reinterpret_cast<uint32_t*>(hist + kHistBins * kHistBins);  // [256][8] bit matrix
+  uint8_t* unassigned = reinterpret_cast<uint8_t*>(assoc + 256 * 8);
+  uint8_t* act = unassigned + nc;
+  uint8_t* mask = act + nc;
+  uint8_t* er = mask + nc;
+  uint8_t* di = er + nc;
+  __shared__ unsigned long long s_best;
+  __shared__ int s_cnt, s_seed, s_changed, s_any, s_np, s_nfinal, s_warp[THREADS / 32];
+  __shared__ int merge[kMaxPlanes + 1];
+  __shared__ double s_acc[9];
+  __shared__ int s_accn;
+
+  const drfe_plane* cells = P.cells + (long long)f * nc;
+  drfe_plane* segs = P.segs + (long long)f * (kMaxPlanes + 1);
+  for (int i = tid; i < kHistBins * kHistBins; i += THREADS) hist[i] = 0;
+  for (int i = tid; i < 256 * 8; i += THREADS) assoc[i] = 0;
+  if (tid == 0) { s_np = 0; s_nfinal = 0; }
+  __syncthreads();
+  // ---- spherical-coordinate histogram (CAPE.cpp:82-101, Histogram.cpp:15-43)
+  int my_remaining = 0;
+  for (int c = tid; c < nc; c += THREADS) {
+    const drfe_plane& g = cells[c];
+    cs[c].n[0] = g.normal[0]; cs[c].n[1] = g.normal[1]; cs[c].n[2] = g.normal[2];
+    cs[c].m[0] = g.mean[0]; cs[c].m[1] = g.mean[1]; cs[c].m[2] = g.mean[2];
+    cs[c].d = g.d;
+    tol[c] = P.tols[(long long)f * nc + c];
+    mse[c] = g.MSE;
+    pmap[c] = 0;
+    int b = -1;
+    if (g.planar) {
+      const double nx = g.normal[0], ny = g.normal[1], nz = g.normal[2];
+      const double pn = sqrt(nx * nx + ny * ny);
+      const double polar = acos(-nz);
+      const int xq = (int)((kHistBins - 1) * (polar - 0.0) / (3.14 - 0.0));
+      int yq = 0;
+      if (xq > 0) yq = (int)((kHistBins - 1) * (atan2(nx / pn, ny / pn) - (-3.14)) / (3.14 - (-3.14)));
+      b = yq * kHistBins + xq;
+      atomicAdd(&hist[b], 1);
+      ++my_remaining;
+    }
+    bin[c] = b;
+    unassigned[c] = g.planar ? 1 : 0;
+  }
+  // block sum of remaining planar cells
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_remaining += __shfl_down_sync(0xFFFFFFFFu, my_remaining, o);
+  if (lane == 0) s_warp[wid] = my_remaining;
+  __syncthreads();
+  int remaining = 0;
+  for (int w = 0; w < THREADS / 32; ++w) remaining += s_warp[w];
+  __syncthreads();
+
+  // ---- seeded region growing (CAPE.cpp:114-218)
+  while (remaining > 0) {
+    if (tid == 0) { s_best = 0ull; s_cnt = 0; }
+    __syncthreads();
+    // most frequent bin, first maximum wins (Histogram.cpp:49-55)
+    for (int b = tid; b < kHistBins * kHistBins; b += THREADS)
+      if (hist[b] > 0) atomicMax(&s_best, ((unsigned long long)hist[b] << 32) | (unsigned)(0xFFFF - b));
+    __syncthreads();
+    if (s_best == 0ull) break;
+    const int best_bin = 0xFFFF - (int)(s_best & 0xFFFFu);
+    const int ncand = (int)(s_best >> 32);
+    if (ncand < 5) break;                                  // Checkpoint 1 (:120)
+    // ordered candidate list (ascending cell id), built by warp 0
+    if (wid == 0) {
+      int base = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        const bool is = c < nc && bin[c] == best_bin;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
+        if (is) list[base + __popc(bal & ((1u << lane) - 1))] = c;
+        base += __popc(bal);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        // seed = candidate with the smallest MSE, with the reference's stray index (:125-132):
+        // the running minimum is refreshed from Grid[i] (loop counter), not Grid[candidate].
+        int seed = list[0];
+        float min_mse = (float)2147483647;
+        for (int i = 0; i < ncand; ++i) {
+          const int c = list[i];
+          if (mse[c] < min_mse) { seed = c; min_mse = mse[i]; }
+        }
+        s_seed = seed;
+      }
+    }
+    for (int c = tid; c < nc; c += THREADS) act[c] = 0;
+    __syncthreads();
+    const int seed = s_seed;
+    // RegionGrowing (:485-506) == closure of "cell passes against an activated 4-neighbour's
+    // plane"; the seed is tested against its own plane.
+    if (tid == 0) {
+      const CellS& a = cs[seed];
+      const double dist = a.n[0] * a.m[0] + a.n[1] * a.m[1] + a.n[2] * a.m[2] + a.d;
+      const bool ok = unassigned[seed] && !(a.n[0] * a.n[0] + a.n[1] * a.n[1] + a.n[2] * a.n[2] < (double)P.min_cos ||
+                                            dist * dist > (double)tol[seed]);
+      act[seed] = ok ? 1 : 0;
+      s_changed = ok ? 1 : 0;
+    }
+    __syncthreads();
+    while (s_changed) {
+      __syncthreads();
+      if (tid == 0) s_changed = 0;
+      __syncthreads();
+      for (int c = tid; c < nc; c += THREADS) {
+        if (!unassigned[c] || act[c]) continue;
+        const int y = c / ncx, x = c - y * ncx;
+        const CellS& b = cs[c];
+        bool ok = false;
+#pragma unroll
+        for (int k = 0; k < 4 && !ok; ++k) {
+          int p;
+          if (k == 0) { if (x + 1 >= ncx) continue; p = c + 1; }        // reached from its left neighbour's "right"
+          else if (k == 1) { if (x == 0) continue; p = c - 1; }
+          else if (k == 2) { if (y + 1 >= ncy) continue; p = c + ncx; }
+          else { if (y == 0) continue; p = c - ncx; }
+          if (!act[p]) continue;
+          const CellS& a = cs[p];
+          const double dist = a.n[0] * b.m[0] + a.n[1] * b.m[1] + a.n[2] * b.m[2] + a.d;
+          ok = !(a.n[0] * b.n[0] + a.n[1] * b.n[1] + a.n[2] * b.n[2] < (double)P.min_cos || dist * dist > (double)tol[c]);
+        }
+        if (ok) { act[c] = 1; s_changed = 1; }
+      }
+      __syncthreads();
+    }
+    // ---- merge activated cells in ascending order (:144-153); ordered list by warp 0
+    if (wid == 0) {
+      int base = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        const bool is = c < nc && act[c];
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
+        if (is) list[base + __popc(bal & ((1u << lane) - 1))] = c;
+        base += __popc(bal);
+      }
+      if (lane == 0) s_cnt = base;
+    }
+    __syncthreads();
+    const int nact = s_cnt;
+    if (tid < 10) {
+      // new_ps = *Grid[seed] then expandSegment(Grid[i]) for every activated i (seed included twice)
+      const drfe_plane& sd = cells[seed];
+      if (tid < 9) {
+        const double* base0 = &sd.x_acc;
+        double acc = base0[tid];
+        for (int i = 0; i < nact; ++i) acc += (&cells[list[i]].x_acc)[tid];
+        s_acc[tid] = acc;
+      } else {
+        int acc = sd.nr_pts;
+        for (int i = 0; i < nact; ++i) acc += cells[list[i]].nr_pts;
+        s_accn = acc;
+      }
+    }
+    for (int i = tid; i < nact; i += THREADS) {
+      const int c = list[i];
+      atomicSub(&hist[bin[c]], 1);       // H.removePoint
+      bin[c] = -1;
+      unassigned[c] = 0;
+    }
+    remaining -= nact;
+    __syncthreads();
+    if (nact < 4) continue;                                // Checkpoint 2 (:157)
+    if (tid == 0) {
+      drfe_plane ps = cells[seed];
+      ps.x_acc = s_acc[0]; ps.y_acc = s_acc[1]; ps.z_acc = s_acc[2]; ps.xx_acc = s_acc[3]; ps.yy_acc = s_acc[4];
+      ps.zz_acc = s_acc[5]; ps.xy_acc = s_acc[6]; ps.xz_acc = s_acc[7]; ps.yz_acc = s_acc[8];
+      ps.nr_pts = s_accn;
+      fit_plane(ps);
+      s_any = 0;
+      if (ps.score > 100) {                                // it is a plane (:163)
+        if (s_np < kMaxPlanes) { segs[s_np] = ps; s_np = s_np + 1; s_any = s_np; }
+        else atomicOr(P.status, 1);
+      }
+    }
+    __syncthreads();
+    const int label = s_any;
+    if (label > 0)
+      for (int i = tid; i < nact; i += THREADS) pmap[list[i]] = label;
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
+  const int np = s_np;
+  for (int c = tid; c < nc; c += THREADS) {
+    const int r = c / ncx, x = c - r * ncx;
+    if (r >= ncy - 1 || x >= ncx - 1) continue;
+    const int v = pmap[c];
+    if (v <= 0) continue;
+    const int right = pmap[c + 1], below = pmap[c + ncx];
+    if (right > 0 && v != right) atomicOr(&assoc[(v - 1) * 8 + ((right - 1) >> 5)], 1u << ((right - 1) & 31));
+    if (below > 0 && v != below) atomicOr(&assoc[(v - 1) * 8 + ((below - 1) >> 5)], 1u << ((below - 1) & 31));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    auto get = [&](int r, int c) { return (assoc[r * 8 + (c >> 5)] >> (c & 31)) & 1u; };
+    for (int i = 0; i < np; ++i) merge[i] = i;
+    for (int r = 0; r < np; ++r) {
+      const int pid = merge[r];
+      bool expanded = false;
+      for (int c = r + 1; c < np; ++c) {
+        if (!(get(r, c) || get(c, r))) continue;
+        const drfe_plane& A = segs[pid];
+        const drfe_plane& Cc = segs[c];
+        const double cosang = A.normal[0] * Cc.normal[0] + A.normal[1] * Cc.normal[1] + A.normal[2] * Cc.normal[2];
+        // sic: the x term uses plane r, the others plane_id (:238-240)
+        const double dd = segs[r].normal[0] * Cc.mean[0] + A.normal[1] * Cc.mean[1] + A.normal[2] * Cc.mean[2] + A.d;
+        if (cosang > (double)P.min_cos && dd * dd < (double)P.max_merge_dist) {
+          expand_seg(segs[pid], segs[c]);
+          merge[c] = pid;
+          expanded = true;
+        }
+      }
+      if (expanded) fit_plane(segs[pid]);
+    }
+  }
+  __syncthreads();
+  // ---- per final plane: cell mask, erode (cross), dilate (square) (CAPE.cpp:254-291)
+  uint8_t* eroded_map = P.eroded_map + (long long)f * nc;
+  uint32_t* bbits = P.border_bits + (long long)f * nc * 8;
+  for (int c = tid; c < nc; c += THREADS) {
+    eroded_map[c] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bbits[c * 8 + k] = 0;
+  }
+  for (int i = 0; i < np; ++i) {
+    if (merge[i] != i) continue;
+    if (tid == 0) s_any = 0;
+    for (int c = tid; c < nc; c += THREADS) {
+      const int v = pmap[c];
+      mask[c] = (v > i && merge[v - 1] == i) ? 1 : 0;        // j >= i with merge label i
+    }
+    __syncthreads();
+    for (int c = tid; c < nc; c += THREADS) {
+      const int r = c / ncx, x = c - r * ncx;
+      int e = mask[c];
+      if (x > 0) e &= mask[c - 1];
+      if (x + 1 < ncx) e &= mask[c + 1];
+      if (r > 0) e &= mask[c - ncx];
+      if (r + 1 < ncy) e &= mask[c + ncx];
+      er[c] = (uint8_t)e;
+      if (e) s_any = 1;
+      int dmax = 0;
+      for (int dr = -1; dr <= 1; ++dr)
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int rr = r + dr, xx = x + dc;
+          if (rr < 0 || rr >= ncy || xx < 0 || xx >= ncx) continue;
+          dmax |= mask[rr * ncx + xx];
+        }
+      di[c] = (uint8_t)dmax;
+    }
+    __syncthreads();
+    const bool keep = s_any != 0;                          // completely eroded planes are ignored (:275)
+    __syncthreads();
+    if (!keep) continue;
+    const int plane_nr = s_nfinal + 1;
+    __syncthreads();
+    if (tid == 0) {
+      const drfe_plane& ps = segs[i];
+      P.planes[(long long)f * kMaxPlanes + s_nfinal] = ps;
+      P.plane_eq[(long long)f * (kMaxPlanes + 1) + plane_nr] =
+          make_float4((float)ps.normal[0], (float)ps.normal[1], (float)ps.normal[2], (float)ps.d);
+      P.plane_maxd[(long long)f * (kMaxPlanes + 1) + plane_nr] = 9 * ps.MSE;
+      s_nfinal = plane_nr;
+    }
+    for (int c = tid; c < nc; c += THREADS) {
+      if (er[c]) eroded_map[c] = (uint8_t)plane_nr;
+      if (di[c] && !er[c]) bbits[c * 8 + (plane_nr >> 5)] |= 1u << (plane_nr & 31);
+    }
+    __syncthreads();
+  }
+  int* plane_map = P.plane_map + (long long)f * nc;
+  for (int c = tid; c < nc; c += THREADS) plane_map[c] = pmap[c];
+  if (tid == 0) P.nplanes[f] = s_nfinal;
+}
+
+// ------------------------------------------------------------------ refinement + output
+// One warp per cell.  Label per pixel = argmin over final planes (in order) of the squared
+// float distance, subject to < 9*MSE, strict '<' against the running minimum which starts at
+// the bit pattern memset(...,100,...) leaves (0x64646464, CAPE.cpp:60).  Cells inside an
+// eroded mask are painted whole (:410-412).
+__global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__ Pp, int nframes) {
+  const CapeDev& P = *Pp;
+  const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= nframes * P.ncells) return;
+  const int f = gw / P.ncells, cell = gw - f * P.ncells;
+  const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
+  const int npc = P.npc, cw = P.cw;
+  const long long N = (long long)P.H * P.W;
+  uint8_t* out = P.seg + (long long)f * N + (long long)(cr * P.ch) * P.W + cc * cw;
+  const int er = P.eroded_map[(long long)f * P.ncells + cell];
+  const uint32_t* bb = P.border_bits + ((long long)f * P.ncells + cell) * 8;
+  uint32_t bits[8];
+  uint32_t anyb = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { bits[k] = bb[k]; anyb |= bits[k]; }
+  if (er > 0 || anyb == 0) {
+    for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)er; }
+    return;
+  }
+  const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+  const float* CY = CX + N;
+  const float* CZ = CY + N;
+  const float4* eq = P.plane_eq + (long long)f * (kMaxPlanes + 1);
+  const float* maxd = P.plane_maxd + (long long)f * (kMaxPlanes + 1);
+  for (int i = lane; i < npc; i += 32) {
+    const float x = CX[i], y = CY[i], z = CZ[i];
+    float best = __uint_as_float(0x64646464u);
+    int lab = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t b = bits[k];
+      while (b) {
+        const int p = k * 32 + __ffs(b) - 1;
+        b &= b - 1;
+        const float4 e = eq[p];
+        const float v = x * e.x + y * e.y + z * e.z + e.w;
+        const float dist = v * v;
+        if (dist < maxd[p] && dist < best) { best = dist; lab = p; }
+      }
+    }
+    const int lr = i / cw, lc = i - lr * cw;
+    out[(long long)lr * P.W + lc] = (uint8_t)lab;
+  }
+}
+
+__global__ void k_cape_clear_margin(const CapeDev* __restrict__ Pp, int nframes) {
+  // pixels outside the last full cell row/column are never labelled
+  const CapeDev& P = *Pp;
+  const long long N = (long long)P.H * P.W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * nframes) return;
+  const int p = (int)(idx % N);
+  const int r = p / P.W, c = p - r * P.W;
+  if (r >= P.ncy * P.ch || c >= P.ncx * P.cw) P.seg[idx] = 0;
+}
+
+}  // namespace drfe
+
+// ====================================================================== host side
+using namespace drfe;
+
+struct drfe_cape {
+  int device = 0, max_batch = 0;
+  drfe_cape_params prm{};
+  CapeDev hd{};
+  CapeDev* dd = nullptr;
+  cudaStream_t stream = nullptr;
+  float* d_depth = nullptr;   // staging for host depth
+  size_t grid_smem = 0;
+  int last_frames = 0;
+  bool pending = false, margin = false;
+  StageTimer timer;
+  std::vector<void*> allocs;
+};
+
+template <typename T>
+static int cape_alloc(drfe_cape* h, T** p, size_t count) {
+  void* q = nullptr;
+  DRFE_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return DRFE_OK;
+}
+
+extern "C" {
+
+int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe_cape** out) {
+  if (!pr || !out) { set_error("drfe_cape_create: null argument"); return DRFE_ERR_ARG; }
+  *out = nullptr;
+  if (pr->depth_height < 1 || pr->depth_width < 1 || pr->cell_width < 2 || pr->cell_height < 2 || max_batch < 1 ||
+      pr->cell_width * pr->cell_height < 16 || pr->depth_width / pr->cell_width < 2 || pr->depth_height / pr->cell_height < 2) {
+    set_error("drfe_cape_create: invalid parameters");
+    return DRFE_ERR_ARG;
+  }
+  if (pr->cylinder_detection) {
+    set_error("drfe_cape_create: cylinder detection is not implemented yet");
+    return DRFE_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("drfe_cape_create: no CUDA device available (there is no CPU fallback)");
+    return DRFE_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("drfe_cape_create: bad device %d", device); return DRFE_ERR_ARG; }
+  DeviceScope ds(device);
+  if (!ds.ok) { set_error("cudaSetDevice(%d) failed", device); return DRFE_ERR_CUDA; }
+  drfe_cape* h = new drfe_cape();
+  h->device = device; h->max_batch = max_batch; h->prm = *pr;
+  CapeDev& D = h->hd;
+  memset(&D, 0, sizeof(D));
+  D.H = pr->depth_height; D.W = pr->depth_width; D.cw = pr->cell_width; D.ch = pr->cell_height;
+  D.ncx = D.W / D.cw; D.ncy = D.H / D.ch; D.ncells = D.ncx * D.ncy; D.npc = D.cw * D.ch; D.B = max_batch;
+  D.min_cos = pr->min_cos_angle_4_merge; D.max_merge_dist = pr->max_merge_dist;
+  h->margin = (D.ncx * D.cw != D.W) || (D.ncy * D.ch != D.H);
+  const size_t N = (size_t)D.H * D.W, B = max_batch, nc = D.ncells;
+  int rc = DRFE_OK;
+  auto fail = [&](int code) { drfe_cape_destroy(h); return code; };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(DRFE_ERR_CUDA); }
+  rc |= cape_alloc(h, &D.cloud, 3 * N * B);
+  rc |= cape_alloc(h, &D.cells, nc * B);
+  rc |= cape_alloc(h, &D.tols, nc * B);
+  rc |= cape_alloc(h, &D.plane_map, nc * B);
+  rc |= cape_alloc(h, &D.eroded_map, nc * B);
+  rc |= cape_alloc(h, &D.border_bits, nc * B * 8);
+  rc |= cape_alloc(h, &D.segs, (size_t)(kMaxPlanes + 1) * B);
+  rc |= cape_alloc(h, &D.planes, (size_t)kMaxPlanes * B);
+  rc |= cape_alloc(h, &D.plane_eq, (size_t)(kMaxPlanes + 1) * B);
+  rc |= cape_alloc(h, &D.plane_maxd, (size_t)(kMaxPlanes + 1) * B);
+  rc |= cape_alloc(h, &D.nplanes, B);
+  rc |= cape_alloc(h, &D.seg, N * B);
+  rc |= cape_alloc(h, &D.status, 1);
+  rc |= cape_alloc(h, &h->d_depth, N * B);
+  rc |= cape_alloc(h, &h->dd, 1);
+  if (rc) return fail(DRFE_ERR_CUDA);
+  if (cudaMemset(D.status, 0, sizeof(int)) != cudaSuccess || cudaMemset(D.cloud, 0, 3 * N * B * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMemset failed"); return fail(DRFE_ERR_CUDA);
+  }
+  h->grid_smem = nc * (sizeof(CellS) + 4 + 4 + 4 + 4 + 4 + 5) + kHistBins * kHistBins * 4 + 256 * 8 * 4 + 64;
+  if (h->grid_smem > 200 * 1024) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
+  if (cudaFuncSetAttribute(k_cape_grid<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
+    set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
+  }
+  if (h->timer.create()) return fail(DRFE_ERR_CUDA);
+  *out = h;
+  return DRFE_OK;
+}
+
+int drfe_cape_destroy(drfe_cape* h) {
+  if (!h) return DRFE_OK;
+  DeviceScope ds(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  h->timer.destroy();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DRFE_OK;
+}
+
+void* drfe_cape_stream(drfe_cape* h) { return h ? (void*)h->stream : nullptr; }
+int drfe_cape_num_cells(const drfe_cape* h, int* cx, int* cy) {
+  if (!h) return DRFE_ERR_ARG;
+  if (cx) *cx = h->hd.ncx;
+  if (cy) *cy = h->hd.ncy;
+  return DRFE_OK;
+}
+int drfe_cape_set_profiling(drfe_cape* h, int on) { if (!h) return DRFE_ERR_ARG; h->timer.enabled = on != 0; return DRFE_OK; }
+int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages) {
+  if (!h || !ms || !nstages) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  return h->timer.read(ms, names, cap, nstages);
+}
+
+static int cape_run(drfe_cape* h, int nframes) {
+  cudaStream_t st = h->stream;
+  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
+  const int ncell_total = nframes * h->hd.ncells;
+  DRFE_LAUNCH(k_cape_cells, (ncell_total * 16 + 127) / 128, 128, 0, st, h->dd, nframes);
+  h->timer.mark("cells", st);
+  DRFE_LAUNCH(k_cape_grid<256>, nframes, 256, h->grid_smem, st, h->dd);
+  h->timer.mark("grid", st);
+  if (h->margin) {
+    const long long tot = (long long)h->hd.H * h->hd.W * nframes;
+    DRFE_LAUNCH(k_cape_clear_margin, (unsigned)((tot + 255) / 256), 256, 0, st, h->dd, nframes);
+  }
+  DRFE_LAUNCH(k_cape_refine, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, nframes);
+  h->timer.mark("refine", st);
+  h->last_frames = nframes;
+  h->pending = true;
+  return DRFE_OK;
+}
+
+int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_t frame_stride, int mem_kind) {
+  if (!h || !cloud) { set_error("drfe_cape_enqueue_cloud: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_enqueue_cloud: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  const size_t N3 = (size_t)3 * h->hd.H * h->hd.W;
+  if (frame_stride < N3 && nframes > 1) { set_error("drfe_cape_enqueue_cloud: frame_stride too small"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  cudaStream_t st = h->stream;
+  h->timer.begin(st);
+  const cudaMemcpyKind kind = mem_kind == DRFE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  if (mem_kind != DRFE_MEM_HOST && mem_kind != DRFE_MEM_DEVICE) { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
+  if (frame_stride == N3 || nframes == 1)
+    DRFE_CUDA(cudaMemcpyAsync(h->hd.cloud, cloud, N3 * nframes * sizeof(float), kind, st));
+  else
+    DRFE_CUDA(cudaMemcpy2DAsync(h->hd.cloud, N3 * sizeof(float), cloud, frame_stride * sizeof(float), N3 * sizeof(float), nframes, kind, st));
+  h->timer.mark("copy_in", st);
+  h->hd.depth = nullptr;
+  return cape_run(h, nframes);
+}
+
+int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_t row_stride, size_t frame_stride,
+                            int mem_kind, float fx, float fy, float cx, float cy) {
+  if (!h || !depth) { set_error("drfe_cape_enqueue_depth: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_enqueue_depth: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  const int W = h->hd.W, H = h->hd.H;
+  if (row_stride < (size_t)W) { set_error("drfe_cape_enqueue_depth: row_stride < width"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  cudaStream_t st = h->stream;
+  h->timer.begin(st);
+  if (mem_kind == DRFE_MEM_HOST) {
+    if (row_stride == (size_t)W && (frame_stride == (size_t)W * H || nframes == 1))
+      DRFE_CUDA(cudaMemcpyAsync(h->d_depth, depth, (size_t)nframes * W * H * sizeof(float), cudaMemcpyHostToDevice, st));
+    else
+      for (int f = 0; f < nframes; ++f)
+        DRFE_CUDA(cudaMemcpy2DAsync(h->d_depth + (size_t)f * W * H, W * sizeof(float), depth + f * frame_stride,
+                                    row_stride * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice, st));
+    h->hd.depth = h->d_depth; h->hd.depth_rs = W; h->hd.depth_fs = (long long)W * H;
+    h->timer.mark("h2d", st);
+  } else if (mem_kind == DRFE_MEM_DEVICE) {
+    h->hd.depth = depth; h->hd.depth_rs = (long long)row_stride; h->hd.depth_fs = (long long)frame_stride;
+  } else { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
+  h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy;
+  return cape_run(h, nframes);
+}
+
+int drfe_cape_sync(drfe_cape* h) {
+  if (!h) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  return DRFE_OK;
+}
+
+int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
+                       drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders) {
+  (void)cylinders; (void)cyl_cap;
+  if (!h || !nr_planes) { set_error("drfe_cape_download: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_cape_download: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  const size_t N = (size_t)h->hd.H * h->hd.W;
+  int status = 0;
+  DRFE_CUDA(cudaMemcpyAsync(nr_planes, h->hd.nplanes, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaMemcpyAsync(&status, h->hd.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (seg_out) DRFE_CUDA(cudaMemcpyAsync(seg_out, h->hd.seg, N * nf, cudaMemcpyDeviceToHost, st));
+  if (planes && plane_cap > 0) {
+    const size_t w = (size_t)std::min(plane_cap, kMaxPlanes) * sizeof(drfe_plane);
+    DRFE_CUDA(cudaMemcpy2DAsync(planes, (size_t)plane_cap * sizeof(drfe_plane), h->hd.planes, (size_t)kMaxPlanes * sizeof(drfe_plane),
+                                w, nf, cudaMemcpyDeviceToHost, st));
+  }
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  if (nr_cylinders) for (int f = 0; f < nf; ++f) nr_cylinders[f] = 0;
+  if (status) {
+    cudaMemsetAsync(h->hd.status, 0, sizeof(int), st);
+    set_error("CAPE: more than %d planes in a frame", kMaxPlanes);
+    return DRFE_ERR_CAPACITY;
+  }
+  if (planes)
+    for (int f = 0; f < nf; ++f)
+      if (nr_planes[f] > plane_cap) { set_error("drfe_cape_download: frame %d has %d planes, plane_cap is %d", f, nr_planes[f], plane_cap); return DRFE_ERR_CAPACITY; }
+  return DRFE_OK;
+}
+
+int drfe_cape_process(drfe_cape* h, const float* cloud, uint8_t* seg_out, drfe_plane* planes, int plane_cap,
+                      int* nr_planes, drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders) {
+  if (!h) { set_error("null handle"); return DRFE_ERR_ARG; }
+  int rc = drfe_cape_enqueue_cloud(h, 1, cloud, (size_t)3 * h->hd.H * h->hd.W, DRFE_MEM_HOST);
+  if (rc) return rc;
+  return drfe_cape_download(h, seg_out, planes, plane_cap, nr_planes, cylinders, cyl_cap, nr_cylinders);
+}
+
+int drfe_cape_process_depth(drfe_cape* h, const float* depth, size_t row_stride, float fx, float fy, float cx, float cy,
+                            uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
+                            drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders) {
+  if (!h) { set_error("null handle"); return DRFE_ERR_ARG; }
+  int rc = drfe_cape_enqueue_depth(h, 1, depth, row_stride, row_stride * h->hd.H, DRFE_MEM_HOST, fx, fy, cx, cy);
+  if (rc) return rc;
+  return drfe_cape_download(h, seg_out, planes, plane_cap, nr_planes, cylinders, cyl_cap, nr_cylinders);
+}
+
+static int cape_frame_ok(drfe_cape* h, int frame) {
+  if (!h) { set_error("null handle"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("nothing enqueued"); return DRFE_ERR_STATE; }
+  if (frame < 0 || frame >= h->last_frames) { set_error("bad frame"); return DRFE_ERR_ARG; }
+  return DRFE_OK;
+}
+
+int drfe_cape_get_cloud(drfe_cape* h, int frame, float* cloud) {
+  int rc = cape_frame_ok(h, frame);
+  if (rc) return rc;
+  DeviceScope ds(h->device);
+  const size_t N3 = (size_t)3 * h->hd.H * h->hd.W;
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  DRFE_CUDA(cudaMemcpy(cloud, h->hd.cloud + N3 * frame, N3 * sizeof(float), cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+int drfe_cape_get_cells(drfe_cape* h, int frame, drfe_plane* cells) {
+  int rc = cape_frame_ok(h, frame);
+  if (rc) return rc;
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  DRFE_CUDA(cudaMemcpy(cells, h->hd.cells + (size_t)h->hd.ncells * frame, (size_t)h->hd.ncells * sizeof(drfe_plane), cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t* eroded_map) {
+  int rc = cape_frame_ok(h, frame);
+  if (rc) return rc;
+  DeviceScope ds(h->device);
+  const size_t nc = h->hd.ncells;
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  if (plane_map) DRFE_CUDA(cudaMemcpy(plane_map, h->hd.plane_map + nc * frame, nc * sizeof(int), cudaMemcpyDeviceToHost));
+  if (eroded_map) DRFE_CUDA(cudaMemcpy(eroded_map, h->hd.eroded_map + nc * frame, nc, cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1139 @@
+// drfe ORB front end for sm_100a: ComputePyramid, per-cell FAST-9 + quadtree distribution,
+// IC_Angle, 7x7 Gaussian and steered rBRIEF — the work of
+// Planar_SLAM::ORBextractor::operator() (reference src/ORBextractor.cc:1043-1105),
+// batched over independent frames.  All arithmetic is integer / fixed point except
+// fastAtan2 and the descriptor steering, which use explicit round-to-nearest float ops
+// (no FMA contraction) so results match the CPU oracle bit for bit.
+//
+// Kernels (one launch each per batch unless noted):
+//   k_pyr_level0   gray -> level 0 + 19 px reflect-101 frame   (ORBextractor.cc:1125-1129)
+//   k_pyr_resize   level l-1 -> level l, OpenCV fixed-point INTER_LINEAR + frame; one
+//                  launch per level because level l reads level l-1   (:1118-1123)
+//   k_fast_cells   one CTA per 30 px grid cell: FAST-9/16 score for every pixel with packed
+//                  s16x2 min/max, per-cell NMS, iniThFAST -> minThFAST fallback (:789-829)
+//   k_quadtree     one CTA per (frame, level): DistributeOctTree replayed with prefix scans,
+//                  order-free (node membership is geometric; ties resolved by the
+//                  reference's candidate order encoded in a key)           (:539-763)
+//   k_blur         separable 8.8 fixed-point Gaussian 7x7, sigma 2          (:1085-1086)
+//   k_orient_describe  one warp per keypoint: IC_Angle (:77-104) + rBRIEF-256 (:107-147)
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "drfe_internal.h"
+
+namespace drfe {
+
+static const int kEdge = 19;     // EDGE_THRESHOLD (ORBextractor.cc:74)
+static const int kXOff = 32;     // byte offset of ROI column 0 inside a bordered row
+static const int kHalfPatch = 15;
+
+__constant__ int8_t c_pattern[1024];
+__constant__ int c_umax[16];
+static const int8_t h_pattern[1024] = {
+#include "../../include/drfe_orb_pattern.inc"
+};
+
+struct LevelDev {
+  int w, h, pitch, rows;            // bordered buffer: rows x pitch bytes, ROI at (kEdge, kXOff)
+  long long img_off, img_fstride;   // bytes
+  int bpitch;
+  long long blur_off, blur_fstride;
+  int regW, regH, nCols, nRows, wCell, hCell;
+  int nfeat, nIni;
+  float hX;
+  int root_x[5];                    // root boundaries int(hX*i), i = 0..nIni (nIni <= 4)
+  int cand_cap;
+  long long cand_off;               // element offset inside one frame's candidate arena
+  int node_cap;
+  int kp_off;                       // offset inside one frame's per-level keypoint arena
+  float scale, size;
+  long long xtab_off, ytab_off;     // element offsets into the resize tables (level >= 1)
+};
+
+struct CellDev { short level, x0, y0, ww, wh, pad; };
+struct TileDev { short level, tx, ty, pad; };
+
+struct OrbDev {
+  int nlevels, B, ini_th, min_th;
+  LevelDev lv[DRFE_MAX_LEVELS];
+  uint8_t* pyr;
+  uint8_t* blur;
+  const uint2* rtab;                // resize tables {idx0 | idx1<<16, c0 | c1<<16}
+  const CellDev* cells;
+  const TileDev* tiles;
+  uint32_t* cand;                   // [B][cand_total] packed x | y<<12 | q<<24 (region coords)
+  long long cand_fstride;
+  int* cand_cnt;                    // [B][nlevels]
+  uint16_t* node_of;                // [B][cand_total] scratch for the quadtree
+  uint32_t* lkp;                    // [B][lkp_total] packed x | y<<12 | q<<24 (level coords)
+  int lkp_fstride;
+  int* lkp_cnt;                     // [B][nlevels]
+  drfe_keypoint* out_kp;            // [B][kp_cap]
+  uint8_t* out_desc;                // [B][kp_cap][32]
+  int* out_cnt;                     // [B]
+  int kp_cap;
+  int* status;                      // bit 0: candidate overflow, bit 1: node overflow
+  int fast_tp, fast_rows, fast_list_cap;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+__device__ __forceinline__ uint8_t* roi_ptr(const OrbDev& P, const LevelDev& L, int f) {
+  return P.pyr + L.img_off + (long long)f * L.img_fstride + (long long)kEdge * L.pitch + kXOff;
+}
+
+// ------------------------------------------------------------------ K1 pyramid
+// Each thread writes 4 horizontally adjacent bytes (one aligned uchar4) of the bordered
+// level image; border positions are reflected to their interior source coordinate and
+// recomputed (identical bytes to copyMakeBorder, no second pass).
+__global__ void __launch_bounds__(256) k_pyr_level0(const OrbDev* __restrict__ Pp,
+                                                     const uint8_t* __restrict__ src,
+                                                     long long row_stride, long long frame_stride) {
+  const OrbDev& P = *Pp;
+  const LevelDev& L = P.lv[0];
+  const int groups = (L.w + 40 + 3) >> 2;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (g >= groups || by >= L.rows) return;
+  const uint8_t* s = src + (long long)f * frame_stride + (long long)reflect101(by - kEdge, L.h) * row_stride;
+  const int bx = 4 * g - 20;
+  uchar4 o;
+  o.x = __ldg(s + reflect101(bx, L.w));
+  o.y = __ldg(s + reflect101(bx + 1, L.w));
+  o.z = __ldg(s + reflect101(bx + 2, L.w));
+  o.w = __ldg(s + reflect101(bx + 3, L.w));
+  uint8_t* d = P.pyr + L.img_off + (long long)f * L.img_fstride + (long long)by * L.pitch + (kXOff - 20) + 4 * g;
+  *reinterpret_cast<uchar4*>(d) = o;
+}
+
+// cv::resize INTER_LINEAR 8UC1: 11-bit coefficient fixed point.
+__global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ Pp, int level) {
+  const OrbDev& P = *Pp;
+  const LevelDev& L = P.lv[level];
+  const LevelDev& S = P.lv[level - 1];
+  const int groups = (L.w + 40 + 3) >> 2;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y * blockDim.y + threadIdx.y;
+  const int f = blockIdx.z;
+  if (g >= groups || by >= L.rows) return;
+  const uint2 ty = __ldg(P.rtab + L.ytab_off + reflect101(by - kEdge, L.h));
+  const uint8_t* sroi = roi_ptr(P, S, f);
+  const uint8_t* s0 = sroi + (long long)(ty.x & 0xFFFF) * S.pitch;
+  const uint8_t* s1 = sroi + (long long)(ty.x >> 16) * S.pitch;
+  const int b0 = (int)(ty.y & 0xFFFF), b1 = (int)(ty.y >> 16);
+  const int bx = 4 * g - 20;
+  uint8_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint2 tx = __ldg(P.rtab + L.xtab_off + reflect101(bx + k, L.w));
+    const int i0 = tx.x & 0xFFFF, i1 = tx.x >> 16;
+    const int c0 = (int)(tx.y & 0xFFFF), c1 = (int)(tx.y >> 16);
+    const int r0 = s0[i0] * c0 + s0[i1] * c1;
+    const int r1 = s1[i0] * c0 + s1[i1] * c1;
+    o[k] = (uint8_t)((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2);
+  }
+  uint8_t* d = P.pyr + L.img_off + (long long)f * L.img_fstride + (long long)by * L.pitch + (kXOff - 20) + 4 * g;
+  *reinterpret_cast<uchar4*>(d) = make_uchar4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------ K2 FAST
+// Threshold-free FAST-9/16 score for two pixels packed as s16x2 (values biased by +256):
+// Q = max over the 16 nine-pixel arcs of max(min(d), -max(d)), d = v - ring; the OpenCV
+// response is Q - 1 and "corner at threshold t" <=> Q - 1 >= t.
+__device__ __forceinline__ void fast_q_pair(const uint32_t (&d)[16], int& q_lo, int& q_hi) {
+  uint32_t mn3[16], mx3[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mn3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    mx3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  }
+  uint32_t best_mn = 0x00000000u, best_mx = 0x7FFF7FFFu;  // max of mins, min of maxes
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t a = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+    const uint32_t b = __vimin3_s16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
+    best_mn = __vimax3_s16x2(best_mn, a, b);
+    const uint32_t c = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+    const uint32_t e = __vimax3_s16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
+    best_mx = __vimin3_s16x2(best_mx, c, e);
+  }
+  // un-bias: d' = d + 256
+  const int mn_lo = (int)(best_mn & 0xFFFF) - 256, mn_hi = (int)(best_mn >> 16) - 256;
+  const int mx_lo = 256 - (int)(best_mx & 0xFFFF), mx_hi = 256 - (int)(best_mx >> 16);
+  q_lo = max(mn_lo, mx_lo) - 1;
+  q_hi = max(mn_hi, mx_hi) - 1;
+}
+
+// ring offsets (dx,dy), k = 0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
+// (-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)  
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fast_cells(const OrbDev* __restrict__ Pp) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const OrbDev& P = *Pp;
+  const CellDev cell = P.cells[blockIdx.x];
+  const int f = blockIdx.y;
+  const LevelDev& L = P.lv[cell.level];
+  const int tp = P.fast_tp, ww = cell.ww, wh = cell.wh;
+  uint8_t* tile = smem;                                  // wh x tp pixels (+1 guard row)
+  uint8_t* score = smem + (size_t)tp * (P.fast_rows + 1);   // same shape
+  uint32_t* list = reinterpret_cast<uint32_t*>(score + (size_t)tp * (P.fast_rows + 1));
+  __shared__ int s_n, s_n_ini, s_base, s_emit;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_n = 0; s_n_ini = 0; s_emit = 0; }
+
+  const uint8_t* src = roi_ptr(P, L, f) + (long long)cell.y0 * L.pitch + cell.x0;
+  const int tw4 = tp >> 2;
+  // window -> smem; columns >= ww and the guard row are zero
+  for (int idx = tid; idx < (wh + 1) * tp; idx += THREADS) {
+    const int r = idx / tp, c = idx - r * tp;
+    tile[idx] = (r < wh && c < ww) ? __ldg(src + (long long)r * L.pitch + c) : 0;
+  }
+  for (int idx = tid; idx < (wh + 1) * tw4; idx += THREADS) reinterpret_cast<uint32_t*>(score)[idx] = 0;
+  __syncthreads();
+
+  const int iw = ww - 6, ih = wh - 6;
+  const int groups = (iw + 3) >> 2;
+  const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+  for (int task = tid; task < ih * groups; task += THREADS) {
+    const int ry = task / groups, g = task - ry * groups;
+    // rows y-3..y+3 (window rows ry..ry+6), bytes 4g..4g+11
+    uint32_t w[7][3];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const uint32_t* p = tile32 + (ry + r) * tw4 + g;
+      w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2];
+    }
+    // 4 adjacent bytes starting at byte offset o (0..8) of row r
+    auto quad = [&](int r, int o) -> uint32_t {
+      return (o & 3) == 0 ? w[r][o >> 2] : __funnelshift_r(w[r][o >> 2], w[r][(o >> 2) + 1], 8 * (o & 3));
+    };
+    const uint32_t vq = quad(3, 3);                         // centres of the 4 pixels
+    const uint32_t v_even = (vq & 0x00FF00FFu) + 0x01000100u;        // pixels 0,2 (+256 bias)
+    const uint32_t v_odd = ((vq >> 8) & 0x00FF00FFu) + 0x01000100u;  // pixels 1,3
+    uint32_t de[16], dod[16];
+#define DRFE_RING(k, dx, dy)                                   \
+  {                                                            \
+    const uint32_t rq = quad(3 + (dy), 3 + (dx));              \
+    de[k] = v_even - (rq & 0x00FF00FFu);                       \
+    dod[k] = v_odd - ((rq >> 8) & 0x00FF00FFu);                \
+  }
+    DRFE_RING(0, 0, 3) DRFE_RING(1, 1, 3) DRFE_RING(2, 2, 2) DRFE_RING(3, 3, 1)
+    DRFE_RING(4, 3, 0) DRFE_RING(5, 3, -1) DRFE_RING(6, 2, -2) DRFE_RING(7, 1, -3)
+    DRFE_RING(8, 0, -3) DRFE_RING(9, -1, -3) DRFE_RING(10, -2, -2) DRFE_RING(11, -3, -1)
+    DRFE_RING(12, -3, 0) DRFE_RING(13, -3, 1) DRFE_RING(14, -2, 2) DRFE_RING(15, -1, 3)
+#undef DRFE_RING
+    int q0, q1, q2, q3;
+    fast_q_pair(de, q0, q2);
+    fast_q_pair(dod, q1, q3);
+    const int x = 3 + 4 * g;  // window column of pixel 0
+    const int minq = P.min_th;
+    uint32_t packed = 0;
+    if (q0 >= minq) packed |= (uint32_t)q0;
+    if (q1 >= minq && x + 1 < ww - 3) packed |= (uint32_t)q1 << 8;
+    if (q2 >= minq && x + 2 < ww - 3) packed |= (uint32_t)q2 << 16;
+    if (q3 >= minq && x + 3 < ww - 3) packed |= (uint32_t)q3 << 24;
+    if (packed) {
+      // score tile is byte addressed at (ry+3, x): x = 4g+3 is not word aligned
+      uint8_t* sp = score + (ry + 3) * tp + x;
+      if (packed & 0xFF) sp[0] = (uint8_t)packed;
+      if (packed & 0xFF00) sp[1] = (uint8_t)(packed >> 8);
+      if (packed & 0xFF0000) sp[2] = (uint8_t)(packed >> 16);
+      if (packed >> 24) sp[3] = (uint8_t)(packed >> 24);
+    }
+  }
+  __syncthreads();
+  // per-cell non-maximum suppression: strict maximum over the 8 neighbours (zeros outside
+  // the cell's interior band, so no suppression across cell edges)
+  for (int idx = tid; idx < ih * iw; idx += THREADS) {
+    const int ry = idx / iw, rx = idx - ry * iw;
+    const uint8_t* sp = score + (ry + 3) * tp + rx + 3;
+    const int s = sp[0];
+    if (s == 0) continue;
+    if (s > sp[-1] && s > sp[1] && s > sp[-tp - 1] && s > sp[-tp] && s > sp[-tp + 1] && s > sp[tp - 1] &&
+        s > sp[tp] && s > sp[tp + 1]) {
+      const int slot = atomicAdd(&s_n, 1);
+      if (s >= P.ini_th) atomicAdd(&s_n_ini, 1);
+      if (slot < P.fast_list_cap) list[slot] = (uint32_t)(rx + 3) | ((uint32_t)(ry + 3) << 12) | ((uint32_t)s << 24);
+    }
+  }
+  __syncthreads();
+  const int n = min(s_n, P.fast_list_cap);
+  const bool use_ini = s_n_ini > 0;        // FAST(iniThFAST) found something -> no fallback
+  const int total = use_ini ? s_n_ini : n;
+  int* cnt = P.cand_cnt + f * P.nlevels + cell.level;
+  if (tid == 0 && total > 0) s_base = atomicAdd(cnt, total);
+  __syncthreads();
+  if (total == 0) return;
+  uint32_t* out = P.cand + (long long)f * P.cand_fstride + L.cand_off;
+  const int ox = cell.x0 - (kEdge - 3), oy = cell.y0 - (kEdge - 3);  // window origin in region coords
+  for (int i = tid; i < n; i += THREADS) {
+    const uint32_t e = list[i];
+    const int q = e >> 24;
+    if (use_ini && q < P.ini_th) continue;
+    const int pos = s_base + atomicAdd(&s_emit, 1);
+    if (pos < L.cand_cap)
+      out[pos] = (uint32_t)((e & 0xFFF) + ox) | ((uint32_t)(((e >> 12) & 0xFFF) + oy) << 12) | ((uint32_t)q << 24);
+    else
+      atomicOr(P.status, 1);
+  }
+}
+
+// ------------------------------------------------------------------ K3 quadtree
+// In-place exclusive scan of a[0..n) by the whole block; returns the total to every thread.
+template <int THREADS>
+__device__ int block_excl_scan(int* a, int n, int* warp_tot) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunk = (n + THREADS - 1) / THREADS;
+  const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int wI = 0; wI < THREADS / 32; ++wI) {
+    const int t = warp_tot[wI];
+    if (wI < wid) base += t;
+    total += t;
+  }
+  int run = base + inc - sum;
+  for (int i = lo; i < hi; ++i) { const int v = a[i]; a[i] = run; run += v; }
+  __syncthreads();
+  return total;
+}
+
+struct QBox { short x0, y0, x1, y1; };
+
+__device__ __forceinline__ void child_mid(const QBox& b, int& mx, int& my) {
+  // halfX = ceil(float(x1-x0)/2) (ORBextractor.cc:483-484); exact in integers for |w| < 2^24
+  const int wdt = b.x1 - b.x0, hgt = b.y1 - b.y0;
+  const int hx = (wdt >= 0) ? (wdt + 1) / 2 : -((-wdt) / 2);
+  const int hy = (hgt >= 0) ? (hgt + 1) / 2 : -((-hgt) / 2);
+  mx = b.x0 + hx; my = b.y0 + hy;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__ Pp) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const OrbDev& P = *Pp;
+  const int level = blockIdx.x, f = blockIdx.y;
+  const LevelDev& L = P.lv[level];
+  const int NC = L.node_cap, N = L.nfeat;
+  const int tid = threadIdx.x;
+  // ---- shared layout
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(smem);
+  QBox* boxA = reinterpret_cast<QBox*>(best + NC);
+  QBox* boxB = boxA + NC;
+  int* cntA = reinterpret_cast<int*>(boxB + NC);
+  int* cntB = cntA + NC;
+  int* ccnt = cntB + NC;        // [NC*4] children counts of split candidates
+  int* a_rank = ccnt + 4 * NC;  // per pos: rank among candidates or -1
+  int* a_order = a_rank + NC;   // rank -> pos
+  int* a_off = a_order + NC;    // per rank: creation offset
+  int* a_keep = a_off + NC;     // per pos: index among kept nodes
+  int* a_tmp = a_keep + NC;
+  unsigned short* remap = reinterpret_cast<unsigned short*>(a_tmp + NC);  // [NC*4]
+  unsigned short* remap_keep = remap + 4 * NC;                            // [NC]
+  __shared__ int warp_tot[THREADS / 32];
+  __shared__ int s_nsplit, s_expand;
+
+  const int n = min(P.cand_cnt[f * P.nlevels + level], L.cand_cap);
+  const uint32_t* keys = P.cand + (long long)f * P.cand_fstride + L.cand_off;
+  uint16_t* node_of = P.node_of + (long long)f * P.cand_fstride + L.cand_off;
+  int* out_cnt = P.lkp_cnt + f * P.nlevels + level;
+  if (n == 0) { if (tid == 0) *out_cnt = 0; return; }
+
+  QBox* box = boxA; QBox* nbox = boxB;
+  int* cnt = cntA; int* ncnt = cntB;
+
+  // ---- roots (ORBextractor.cc:543-592): key -> root by int(x / hX); empty roots dropped
+  for (int i = tid; i < NC; i += THREADS) { cnt[i] = 0; }
+  __syncthreads();
+  for (int k = tid; k < n; k += THREADS) {
+    const int x = keys[k] & 0xFFF;
+    int r = (int)__fdiv_rn((float)x, L.hX);
+    r = min(r, L.nIni - 1);
+    node_of[k] = (uint16_t)r;
+    atomicAdd(&cnt[r], 1);
+  }
+  __syncthreads();
+  int S = 0;
+  {
+    // compact non-empty roots (nIni <= 4: done redundantly by every thread)
+    int newpos[4];
+    for (int i = 0; i < L.nIni; ++i) { newpos[i] = S; if (cnt[i] > 0) ++S; }
+    int c[4];
+    for (int i = 0; i < L.nIni; ++i) c[i] = cnt[i];
+    __syncthreads();
+    if (tid == 0)
+      for (int i = 0; i < L.nIni; ++i)
+        if (c[i] > 0) {
+          cnt[newpos[i]] = c[i];
+          box[newpos[i]] = QBox{(short)L.root_x[i], 0, (short)L.root_x[i + 1], (short)L.regH};
+        }
+    for (int k = tid; k < n; k += THREADS) node_of[k] = (uint16_t)newpos[node_of[k]];
+    __syncthreads();
+  }
+
+  bool fine = false;
+  int Cprev = 0;
+  for (int iter = 0; iter < 64; ++iter) {
+    const int prevS = S;
+    // 1. split candidates: coarse = every multi-key node; fine = multi-key nodes created by
+    //    the previous pass (they sit at the list front)
+    for (int p = tid; p < S; p += THREADS) {
+      const bool cand = cnt[p] > 1 && (!fine || p < Cprev);
+      a_tmp[p] = cand ? 1 : 0;
+      ccnt[4 * p] = ccnt[4 * p + 1] = ccnt[4 * p + 2] = ccnt[4 * p + 3] = 0;
+    }
+    if (tid == 0) { s_nsplit = 0x7FFFFFFF; s_expand = 0; }
+    __syncthreads();
+    // compact index of candidates in list order
+    for (int p = tid; p < S; p += THREADS) a_rank[p] = a_tmp[p];
+    __syncthreads();
+    const int V = block_excl_scan<THREADS>(a_rank, S, warp_tot);   // a_rank[p] = compact idx
+    if (V == 0) break;                                             // nothing to split: size unchanged
+    // 2. classify the keys of candidate nodes into their 4 children (DivideNode :515-531)
+    for (int k = tid; k < n; k += THREADS) {
+      const int nd = node_of[k] & 0x3FFF;
+      if (!a_tmp[nd]) continue;
+      const uint32_t e = keys[k];
+      const int x = e & 0xFFF, y = (e >> 12) & 0xFFF;
+      int mx, my;
+      child_mid(box[nd], mx, my);
+      const int c = (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
+      atomicAdd(&ccnt[4 * nd + c], 1);
+      node_of[k] = (uint16_t)(nd | (c << 14));
+    }
+    // 3. split order.  coarse: list order.  fine: sort by (nKeys, creation seq) ascending and
+    //    walk from the back (:684-686) == (nKeys desc, list position asc).
+    for (int p = tid; p < S; p += THREADS)
+      if (a_tmp[p]) a_order[a_rank[p]] = p;       // compact list (coarse: final order)
+    __syncthreads();
+    if (fine) {
+      for (int i = tid; i < V; i += THREADS) a_off[i] = a_order[i];  // stash compact list
+      __syncthreads();
+      for (int i = tid; i < V; i += THREADS) {
+        const int p = a_off[i], cp = cnt[p];
+        int r = 0;
+        for (int j = 0; j < V; ++j) {
+          const int pj = a_off[j], cj = cnt[pj];
+          r += (cj > cp) || (cj == cp && pj < p);
+        }
+        a_keep[i] = r;                                            // rank of compact entry i
+      }
+      __syncthreads();
+      for (int i = tid; i < V; i += THREADS) { a_order[a_keep[i]] = a_off[i]; }
+      __syncthreads();
+      for (int r = tid; r < V; r += THREADS) a_rank[a_order[r]] = r;
+      __syncthreads();
+      // stop splitting as soon as the list reaches N nodes (:730-731)
+      for (int r = tid; r < V; r += THREADS) {
+        const int p = a_order[r];
+        const int nch = (ccnt[4 * p] > 0) + (ccnt[4 * p + 1] > 0) + (ccnt[4 * p + 2] > 0) + (ccnt[4 * p + 3] > 0);
+        a_off[r] = nch - 1;
+      }
+      __syncthreads();
+      // inclusive gains
+      {
+        // exclusive scan then add own gain
+        for (int r = tid; r < V; r += THREADS) a_keep[r] = a_off[r];
+        __syncthreads();
+        block_excl_scan<THREADS>(a_keep, V, warp_tot);
+        for (int r = tid; r < V; r += THREADS)
+          if (S + a_keep[r] + a_off[r] >= N) atomicMin(&s_nsplit, r + 1);
+        __syncthreads();
+      }
+    }
+    const int nsplit = min(s_nsplit, V);
+    // 4. creation offsets in split order
+    for (int r = tid; r < V; r += THREADS) {
+      const int p = a_order[r];
+      const int nch = (ccnt[4 * p] > 0) + (ccnt[4 * p + 1] > 0) + (ccnt[4 * p + 2] > 0) + (ccnt[4 * p + 3] > 0);
+      a_off[r] = (r < nsplit) ? nch : 0;
+    }
+    for (int p = tid; p < S; p += THREADS) a_keep[p] = (a_tmp[p] && a_rank[p] < nsplit) ? 0 : 1;
+    __syncthreads();
+    const int C = block_excl_scan<THREADS>(a_off, V, warp_tot);
+    const int K = block_excl_scan<THREADS>(a_keep, S, warp_tot);
+    const int newS = C + K;
+    if (newS > NC) { if (tid == 0) atomicOr(P.status, 2); break; }
+    // 5. build the new list: children are pushed to the front one by one (n1..n4, :636-673),
+    //    so the list starts with the created nodes in reverse creation order, followed by
+    //    the surviving nodes in their old order.
+    for (int r = tid; r < nsplit; r += THREADS) {
+      const int p = a_order[r];
+      const QBox b = box[p];
+      int mx, my;
+      child_mid(b, mx, my);
+      int ci = a_off[r], nexp = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cc = ccnt[4 * p + c];
+        if (cc == 0) continue;
+        const int np = C - 1 - ci;
+        ++ci;
+        QBox nb;
+        nb.x0 = (c & 1) ? (short)mx : b.x0; nb.x1 = (c & 1) ? b.x1 : (short)mx;
+        nb.y0 = (c & 2) ? (short)my : b.y0; nb.y1 = (c & 2) ? b.y1 : (short)my;
+        nbox[np] = nb; ncnt[np] = cc;
+        remap[4 * p + c] = (unsigned short)np;
+        nexp += (cc > 1);
+      }
+      if (nexp) atomicAdd(&s_expand, nexp);
+    }
+    for (int p = tid; p < S; p += THREADS) {
+      if (a_tmp[p] && a_rank[p] < nsplit) continue;
+      const int np = C + a_keep[p];
+      nbox[np] = box[p]; ncnt[np] = cnt[p];
+      remap_keep[p] = (unsigned short)np;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += THREADS) {
+      const int v = node_of[k], nd = v & 0x3FFF;
+      node_of[k] = (a_tmp[nd] && a_rank[nd] < nsplit) ? remap[4 * nd + (v >> 14)] : remap_keep[nd];
+    }
+    const int nexpand = s_expand;
+    __syncthreads();
+    { QBox* t = box; box = nbox; nbox = t; int* u = cnt; cnt = ncnt; ncnt = u; }
+    S = newS; Cprev = C;
+    // 6. termination (:677-681, :735-736)
+    if (S >= N || S == prevS) break;
+    if (!fine && S + 3 * nexpand > N) fine = true;
+  }
+  __syncthreads();
+  // ---- keep the best key per node: max response, first in the reference's candidate order
+  // (cell row-major, then pixel row-major) on ties (:741-760).
+  for (int p = tid; p < S; p += THREADS) best[p] = 0ull;
+  __syncthreads();
+  for (int k = tid; k < n; k += THREADS) {
+    const uint32_t e = keys[k];
+    const int x = e & 0xFFF, y = (e >> 12) & 0xFFF;
+    const unsigned cellid = (unsigned)(((y - 3) / L.hCell) * L.nCols + (x - 3) / L.wCell);
+    const unsigned long long ord = ((unsigned long long)cellid << 24) | ((unsigned long long)y << 12) | x;
+    const unsigned long long val = ((unsigned long long)(e >> 24) << 40) | (0xFFFFFFFFFFull - ord);
+    atomicMax(&best[node_of[k] & 0x3FFF], val);
+  }
+  __syncthreads();
+  uint32_t* out = P.lkp + (long long)f * P.lkp_fstride + L.kp_off;
+  for (int p = tid; p < S; p += THREADS) {
+    const unsigned long long v = best[p];
+    const unsigned long long ord = 0xFFFFFFFFFFull - (v & 0xFFFFFFFFFFull);
+    const uint32_t x = (uint32_t)(ord & 0xFFF) + (kEdge - 3), y = (uint32_t)((ord >> 12) & 0xFFF) + (kEdge - 3);
+    out[p] = x | (y << 12) | ((uint32_t)(v >> 40) << 24);
+  }
+  if (tid == 0) *out_cnt = S;
+}
+
+// ------------------------------------------------------------------ K5 Gaussian
+// 7x7 sigma=2 separable, 8.8 fixed point {18,34,48,56,48,34,18}, rounding (v + 2^15) >> 16
+// (SURVEY App. A.5).  Reads the bordered level image, whose 19 px reflect-101 frame is
+// exactly the BORDER_REFLECT_101 extension GaussianBlur applies to the cloned level.
+static const int kBlurTW = 64, kBlurTH = 32;
+__global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp) {
+  __shared__ __align__(16) uint8_t s_in[(kBlurTH + 6) * (kBlurTW + 8)];
+  __shared__ __align__(16) uint16_t s_mid[(kBlurTH + 6) * kBlurTW];
+  const OrbDev& P = *Pp;
+  const TileDev t = P.tiles[blockIdx.x];
+  const int f = blockIdx.y;
+  const LevelDev& L = P.lv[t.level];
+  if (P.lkp_cnt[f * P.nlevels + t.level] == 0) return;  // reference skips levels without keypoints (:1081)
+  const int x0 = t.tx * kBlurTW, y0 = t.ty * kBlurTH;
+  const uint8_t* src = roi_ptr(P, L, f) + (long long)(y0 - 3) * L.pitch + (x0 - 3);
+  const int tid = threadIdx.x;
+  const int IW = kBlurTW + 8;  // smem input pitch (only TW+6 columns are used)
+  const int cols = min(kBlurTW, L.w - x0), rows = min(kBlurTH, L.h - y0);
+  for (int idx = tid; idx < (rows + 6) * (cols + 6); idx += 256) {
+    const int r = idx / (cols + 6), c = idx - r * (cols + 6);
+    s_in[r * IW + c] = __ldg(src + (long long)r * L.pitch + c);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (rows + 6) * cols; idx += 256) {
+    const int r = idx / cols, c = idx - r * cols;
+    const uint8_t* p = s_in + r * IW + c;
+    s_mid[r * kBlurTW + c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+  }
+  __syncthreads();
+  uint8_t* dst = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)y0 * L.bpitch + x0;
+  for (int idx = tid; idx < rows * cols; idx += 256) {
+    const int r = idx / cols, c = idx - r * cols;
+    const uint16_t* p = s_mid + r * kBlurTW + c;
+    const uint32_t v = 18u * (p[0] + p[6 * kBlurTW]) + 34u * (p[kBlurTW] + p[5 * kBlurTW]) +
+                       48u * (p[2 * kBlurTW] + p[4 * kBlurTW]) + 56u * p[3 * kBlurTW];
+    dst[(long long)r * L.bpitch + c] = (uint8_t)min((v + 32768u) >> 16, 255u);
+  }
+}
+
+// ------------------------------------------------------------------ K4+K6 orientation + descriptor
+// cv::fastAtan2 (degrees), plain float32 with explicit rounding of every op
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float s = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s,
+              p7 = -0.04432655554792128f * s;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+static const int kDescWarps = 8;
+__global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp) {
+  const OrbDev& P = *Pp;
+  const int level = blockIdx.y, f = blockIdx.z;
+  const LevelDev& L = P.lv[level];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int* cnts = P.lkp_cnt + f * P.nlevels;
+  const int nk = cnts[level];
+  const int i = blockIdx.x * kDescWarps + wid;
+  if (blockIdx.x == 0 && level == 0 && threadIdx.x == 0) {
+    int tot = 0;
+    for (int l = 0; l < P.nlevels; ++l) tot += cnts[l];
+    P.out_cnt[f] = min(tot, P.kp_cap);
+  }
+  if (i >= nk) return;
+  int base = 0;
+  for (int l = 0; l < level; ++l) base += cnts[l];
+  const uint32_t e = P.lkp[(long long)f * P.lkp_fstride + L.kp_off + i];
+  const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;   // cvRound of integral coords
+  // ---- IC_Angle: moments over the radius-15 disc, lanes across u, loop over rows v
+  const uint8_t* img = roi_ptr(P, L, f) + (long long)cy * L.pitch + cx;
+  int m10 = 0, m01 = 0;
+  const int u = lane - kHalfPatch;
+  if (lane < 31) {
+    const int au = abs(u);
+#pragma unroll 1
+    for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+      if (au <= c_umax[abs(v)]) {
+        const int val = img[(long long)v * L.pitch + u];
+        m10 += u * val;
+        m01 += v * val;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_down_sync(0xFFFFFFFFu, m10, o);
+    m01 += __shfl_down_sync(0xFFFFFFFFu, m01, o);
+  }
+  float angle = 0.f, a = 0.f, b = 0.f;
+  if (lane == 0) {
+    angle = fast_atan2_deg((float)m01, (float)m10);
+    const float rad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+    a = (float)cos((double)rad);   // correctly rounded cosf/sinf
+    b = (float)sin((double)rad);
+  }
+  angle = __shfl_sync(0xFFFFFFFFu, angle, 0);
+  a = __shfl_sync(0xFFFFFFFFu, a, 0);
+  b = __shfl_sync(0xFFFFFFFFu, b, 0);
+  // ---- rBRIEF: lane j computes descriptor byte j (8 tests)
+  const uint8_t* bl = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)cy * L.bpitch + cx;
+  const int8_t* pat = c_pattern + lane * 32;
+  int val = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1];
+    const float x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = bl[(long long)r0 * L.bpitch + c0], t1 = bl[(long long)r1 * L.bpitch + c1];
+    val |= (t0 < t1) << j;
+  }
+  const int o = base + i;
+  if (o >= P.kp_cap) return;
+  P.out_desc[((long long)f * P.kp_cap + o) * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    drfe_keypoint kp;
+    // pt *= mvScaleFactor[level] for level > 0 (ORBextractor.cc:1095-1101)
+    kp.x = level ? __fmul_rn((float)cx, L.scale) : (float)cx;
+    kp.y = level ? __fmul_rn((float)cy, L.scale) : (float)cy;
+    kp.size = L.size;
+    kp.angle = angle;
+    kp.response = (float)resp;
+    kp.octave = level;
+    kp.class_id = -1;
+    P.out_kp[(long long)f * P.kp_cap + o] = kp;
+  }
+}
+
+__global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int nframes) {
+  const OrbDev& P = *Pp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nframes * P.nlevels) { P.cand_cnt[i] = 0; P.lkp_cnt[i] = 0; }
+  if (i < nframes) P.out_cnt[i] = 0;
+}
+
+}  // namespace drfe
+
+// ====================================================================== host side
+using namespace drfe;
+
+struct drfe_orb {
+  int device = 0, width = 0, height = 0, max_batch = 0;
+  drfe_orb_params prm{};
+  double scaleFactorD = 1.2;
+  std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+  std::vector<int> per_level;
+  OrbDev hd{};                 // host copy of the device descriptor
+  OrbDev* dd = nullptr;        // device copy
+  cudaStream_t stream = nullptr;
+  uint8_t* d_gray = nullptr;   // staging for host inputs [B][H][W]
+  void* d_rtab = nullptr; void* d_cells = nullptr; void* d_tiles = nullptr;
+  int ncells = 0, ntiles = 0, max_node_cap = 0, max_lkp = 0;
+  size_t fast_smem = 0, quad_smem = 0;
+  int last_frames = 0;
+  bool pending = false;
+  StageTimer timer;
+  std::vector<void*> allocs;
+};
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+static void make_resize_tab(int ssize, int dsize, std::vector<uint2>& out) {
+  // OpenCV resize.cpp (INTER_LINEAR, 8U): scale = 1/(dsize/ssize); fx = (dx+0.5)*scale-0.5 (float)
+  const double scale = 1.0 / ((double)dsize / ssize);
+  for (int d = 0; d < dsize; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    const int c0 = cv_round_f((1.f - f) * 2048.f), c1 = cv_round_f(f * 2048.f);
+    const int s1 = std::min(s + 1, ssize - 1);
+    out.push_back(make_uint2((unsigned)s | ((unsigned)s1 << 16), (unsigned)c0 | ((unsigned)c1 << 16)));
+  }
+}
+
+template <typename T>
+static int dev_alloc(drfe_orb* h, T** p, size_t count) {
+  void* q = nullptr;
+  DRFE_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return DRFE_OK;
+}
+
+static int orb_build(drfe_orb* h) {
+  const drfe_orb_params& pr = h->prm;
+  const int nl = pr.nlevels;
+  // ---- ORBextractor::ORBextractor (ORBextractor.cc:410-446)
+  h->scaleFactorD = (double)pr.scale_factor;
+  h->scale.assign(nl, 1.f); h->sigma2.assign(nl, 1.f);
+  for (int i = 1; i < nl; ++i) {
+    h->scale[i] = (float)(h->scale[i - 1] * h->scaleFactorD);
+    h->sigma2[i] = h->scale[i] * h->scale[i];
+  }
+  h->inv_scale.resize(nl); h->inv_sigma2.resize(nl);
+  for (int i = 0; i < nl; ++i) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+  h->per_level.resize(nl);
+  {
+    const float factor = (float)(1.0f / h->scaleFactorD);
+    float want = pr.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; ++l) { h->per_level[l] = cv_round_f(want); sum += h->per_level[l]; want *= factor; }
+    h->per_level[nl - 1] = std::max(pr.nfeatures - sum, 0);
+  }
+  int umax[16];
+  {
+    const int vmax = (int)floor(kHalfPatch * sqrt(2.f) / 2 + 1), vmin = (int)ceil(kHalfPatch * sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) umax[v] = (int)lrint(sqrt((double)kHalfPatch * kHalfPatch - v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+      while (umax[v0] == umax[v0 + 1]) ++v0;
+      umax[v] = v0; ++v0;
+    }
+  }
+  // ---- per-level geometry (ComputePyramid :1111-1113, ComputeKeyPointsOctTree :773-787)
+  OrbDev& D = h->hd;
+  memset(&D, 0, sizeof(D));
+  D.nlevels = nl; D.B = h->max_batch; D.ini_th = pr.ini_th_fast; D.min_th = pr.min_th_fast;
+  std::vector<uint2> rtab;
+  std::vector<CellDev> cells;
+  std::vector<TileDev> tiles;
+  long long img_total = 0, blur_total = 0, cand_total = 0;
+  int lkp_total = 0, kp_cap = 0, max_ww = 0, max_wh = 0;
+  for (int l = 0; l < nl; ++l) {
+    LevelDev& L = D.lv[l];
+    L.w = cv_round_f((float)h->width * h->inv_scale[l]);
+    L.h = cv_round_f((float)h->height * h->inv_scale[l]);
+    L.pitch = (kXOff + L.w + 32 + 127) / 128 * 128;
+    L.rows = L.h + 2 * kEdge;
+    L.img_fstride = (long long)L.pitch * (L.rows + 1);
+    L.img_off = img_total;
+    img_total += L.img_fstride * h->max_batch;
+    L.bpitch = (L.w + 127) / 128 * 128;
+    L.blur_fstride = (long long)L.bpitch * L.h;
+    L.blur_off = blur_total;
+    blur_total += L.blur_fstride * h->max_batch;
+    L.regW = L.w - 2 * (kEdge - 3); L.regH = L.h - 2 * (kEdge - 3);
+    if (L.regW < 30 || L.regH < 30) { set_error("level %d (%dx%d) is too small for the 30 px FAST grid", l, L.w, L.h); return DRFE_ERR_ARG; }
+    const float width = (float)L.regW, height = (float)L.regH;
+    L.nCols = (int)(width / 30.f); L.nRows = (int)(height / 30.f);
+    L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
+    L.nfeat = h->per_level[l];
+    L.nIni = (int)roundf(width / height);
+    if (L.nIni < 1 || L.nIni > 4) { set_error("unsupported aspect ratio (quadtree roots = %d)", L.nIni); return DRFE_ERR_ARG; }
+    L.hX = width / L.nIni;
+    for (int i = 0; i <= L.nIni; ++i) L.root_x[i] = (int)(L.hX * (float)i);
+    L.cand_cap = std::min(1 << 16, std::max(1024, (L.regW * L.regH) / 24));
+    L.cand_off = cand_total; cand_total += L.cand_cap;
+    L.node_cap = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
+    if (L.node_cap > 0x3FFF) { set_error("nfeatures too large"); return DRFE_ERR_ARG; }
+    h->max_node_cap = std::max(h->max_node_cap, L.node_cap);
+    L.kp_off = lkp_total; lkp_total += L.node_cap;
+    kp_cap += L.node_cap;
+    L.scale = h->scale[l];
+    L.size = (float)(int)(31 * h->scale[l]);
+    if (l > 0) {
+      L.xtab_off = (long long)rtab.size(); make_resize_tab(D.lv[l - 1].w, L.w, rtab);
+      L.ytab_off = (long long)rtab.size(); make_resize_tab(D.lv[l - 1].h, L.h, rtab);
+    }
+    const int minB = kEdge - 3, maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+    for (int i = 0; i < L.nRows; ++i) {
+      const int iniY = minB + i * L.hCell;
+      int maxY = iniY + L.hCell + 6;
+      if (iniY >= maxBY - 3) continue;
+      if (maxY > maxBY) maxY = maxBY;
+      for (int j = 0; j < L.nCols; ++j) {
+        const int iniX = minB + j * L.wCell;
+        int maxX = iniX + L.wCell + 6;
+        if (iniX >= maxBX - 6) continue;
+        if (maxX > maxBX) maxX = maxBX;
+        if (maxX - iniX < 7 || maxY - iniY < 7) continue;  // FAST finds nothing in < 7 px
+        cells.push_back(CellDev{(short)l, (short)iniX, (short)iniY, (short)(maxX - iniX), (short)(maxY - iniY), 0});
+        max_ww = std::max(max_ww, maxX - iniX); max_wh = std::max(max_wh, maxY - iniY);
+      }
+    }
+    for (int ty = 0; ty < (L.h + kBlurTH - 1) / kBlurTH; ++ty)
+      for (int tx = 0; tx < (L.w + kBlurTW - 1) / kBlurTW; ++tx) tiles.push_back(TileDev{(short)l, (short)tx, (short)ty, 0});
+    if (L.w > 4000 || L.h > 4000) { set_error("image too large (12-bit packed coordinates)"); return DRFE_ERR_ARG; }
+  }
+  h->ncells = (int)cells.size(); h->ntiles = (int)tiles.size();
+  D.cand_fstride = cand_total; D.lkp_fstride = lkp_total; D.kp_cap = kp_cap; h->max_lkp = 0;
+  for (int l = 0; l < nl; ++l) h->max_lkp = std::max(h->max_lkp, D.lv[l].node_cap);
+  D.fast_tp = (max_ww + 8 + 3) / 4 * 4 + 4;     // word loads read up to 4g+11 <= ww+8
+  D.fast_rows = max_wh;
+  D.fast_list_cap = ((max_ww - 5) / 2 + 1) * ((max_wh - 5) / 2 + 1);
+  h->fast_smem = (size_t)2 * D.fast_tp * (D.fast_rows + 1) + (size_t)D.fast_list_cap * 4;
+  const int NC = h->max_node_cap;
+  h->quad_smem = (size_t)NC * (8 + 8 + 8 + 4 + 4 + 16 + 5 * 4 + 8 + 2) + 64;
+
+  // ---- device memory
+  const int B = h->max_batch;
+  DRFE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (dev_alloc(h, &D.pyr, (size_t)img_total + 256)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.blur, (size_t)blur_total + 256)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.cand, (size_t)cand_total * B)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.node_of, (size_t)cand_total * B)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.cand_cnt, (size_t)B * nl)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.lkp, (size_t)lkp_total * B)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.lkp_cnt, (size_t)B * nl)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.out_kp, (size_t)kp_cap * B)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.out_desc, (size_t)kp_cap * B * 32)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.out_cnt, (size_t)B)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &D.status, 1)) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &h->d_gray, (size_t)B * h->width * h->height)) return DRFE_ERR_CUDA;
+  uint2* d_rtab; CellDev* d_cells; TileDev* d_tiles;
+  if (dev_alloc(h, &d_rtab, rtab.size())) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &d_cells, cells.size())) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &d_tiles, tiles.size())) return DRFE_ERR_CUDA;
+  DRFE_CUDA(cudaMemcpy(d_rtab, rtab.data(), rtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  DRFE_CUDA(cudaMemcpy(d_cells, cells.data(), cells.size() * sizeof(CellDev), cudaMemcpyHostToDevice));
+  DRFE_CUDA(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice));
+  D.rtab = d_rtab; D.cells = d_cells; D.tiles = d_tiles;
+  DRFE_CUDA(cudaMemset(D.pyr, 0, (size_t)img_total + 256));
+  DRFE_CUDA(cudaMemset(D.status, 0, sizeof(int)));
+  if (dev_alloc(h, &h->dd, 1)) return DRFE_ERR_CUDA;
+  DRFE_CUDA(cudaMemcpy(h->dd, &D, sizeof(D), cudaMemcpyHostToDevice));
+  DRFE_CUDA(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+  DRFE_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+  DRFE_CUDA(cudaFuncSetAttribute(k_fast_cells<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
+  DRFE_CUDA(cudaFuncSetAttribute(k_quadtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->quad_smem));
+  if (h->timer.create()) return DRFE_ERR_CUDA;
+  return DRFE_OK;
+}
+
+extern "C" {
+
+int drfe_orb_create(const drfe_orb_params* params, int width, int height, int max_batch, int device,
+                    drfe_orb** out) {
+  if (!params || !out) { set_error("drfe_orb_create: null argument"); return DRFE_ERR_ARG; }
+  *out = nullptr;
+  if (params->nlevels < 1 || params->nlevels > DRFE_MAX_LEVELS || params->nfeatures < 1 ||
+      !(params->scale_factor > 1.0f) || params->min_th_fast < 1 || params->ini_th_fast < params->min_th_fast ||
+      params->ini_th_fast > 254 || max_batch < 1 || width < 64 || height < 64) {
+    set_error("drfe_orb_create: invalid parameters");
+    return DRFE_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("drfe_orb_create: no CUDA device available (there is no CPU fallback)");
+    return DRFE_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("drfe_orb_create: bad device %d", device); return DRFE_ERR_ARG; }
+  DeviceScope ds(device);
+  if (!ds.ok) { set_error("cudaSetDevice(%d) failed", device); return DRFE_ERR_CUDA; }
+  drfe_orb* h = new drfe_orb();
+  h->device = device; h->width = width; h->height = height; h->max_batch = max_batch; h->prm = *params;
+  const int rc = orb_build(h);
+  if (rc != DRFE_OK) { drfe_orb_destroy(h); return rc; }
+  *out = h;
+  return DRFE_OK;
+}
+
+int drfe_orb_destroy(drfe_orb* h) {
+  if (!h) return DRFE_OK;
+  DeviceScope ds(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  h->timer.destroy();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DRFE_OK;
+}
+
+int drfe_orb_get_levels(const drfe_orb* h) { return h ? h->prm.nlevels : 0; }
+float drfe_orb_get_scale_factor(const drfe_orb* h) { return h ? (float)h->scaleFactorD : 0.f; }
+int drfe_orb_get_scale_factors(const drfe_orb* h, float* s, float* is, float* s2, float* is2) {
+  if (!h) return DRFE_ERR_ARG;
+  for (int i = 0; i < h->prm.nlevels; ++i) {
+    if (s) s[i] = h->scale[i];
+    if (is) is[i] = h->inv_scale[i];
+    if (s2) s2[i] = h->sigma2[i];
+    if (is2) is2[i] = h->inv_sigma2[i];
+  }
+  return DRFE_OK;
+}
+int drfe_orb_features_per_level(const drfe_orb* h, int level) {
+  return (h && level >= 0 && level < h->prm.nlevels) ? h->per_level[level] : DRFE_ERR_ARG;
+}
+int drfe_orb_max_keypoints(const drfe_orb* h) { return h ? h->hd.kp_cap : 0; }
+void* drfe_orb_stream(drfe_orb* h) { return h ? (void*)h->stream : nullptr; }
+int drfe_orb_level_size(const drfe_orb* h, int level, int* w, int* hgt) {
+  if (!h || level < 0 || level >= h->prm.nlevels) { set_error("bad level"); return DRFE_ERR_ARG; }
+  if (w) *w = h->hd.lv[level].w;
+  if (hgt) *hgt = h->hd.lv[level].h;
+  return DRFE_OK;
+}
+int drfe_orb_set_profiling(drfe_orb* h, int on) { if (!h) return DRFE_ERR_ARG; h->timer.enabled = on != 0; return DRFE_OK; }
+int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, int* nstages) {
+  if (!h || !ms || !nstages) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  return h->timer.read(ms, names, cap, nstages);
+}
+
+int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride, size_t frame_stride,
+                     int mem_kind) {
+  if (!h || !gray) { set_error("drfe_orb_enqueue: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_orb_enqueue: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  if (row_stride < (size_t)h->width) { set_error("drfe_orb_enqueue: row_stride < width"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const OrbDev& D = h->hd;
+  const uint8_t* src = gray;
+  long long rs = (long long)row_stride, fs = (long long)frame_stride;
+  h->timer.begin(st);
+  if (mem_kind == DRFE_MEM_HOST) {
+    if (row_stride == (size_t)h->width && (frame_stride == (size_t)h->width * h->height || nframes == 1)) {
+      DRFE_CUDA(cudaMemcpyAsync(h->d_gray, gray, (size_t)nframes * h->width * h->height, cudaMemcpyHostToDevice, st));
+    } else {
+      for (int f = 0; f < nframes; ++f)
+        DRFE_CUDA(cudaMemcpy2DAsync(h->d_gray + (size_t)f * h->width * h->height, h->width, gray + f * frame_stride,
+                                    row_stride, h->width, h->height, cudaMemcpyHostToDevice, st));
+    }
+    src = h->d_gray; rs = h->width; fs = (long long)h->width * h->height;
+    h->timer.mark("h2d", st);
+  } else if (mem_kind != DRFE_MEM_DEVICE) {
+    set_error("drfe_orb_enqueue: bad mem_kind"); return DRFE_ERR_ARG;
+  }
+  const int nl = D.nlevels;
+  DRFE_LAUNCH(k_zero_counts, (nframes * nl + 255) / 256, 256, 0, st, h->dd, nframes);
+  {
+    const LevelDev& L = D.lv[0];
+    dim3 blk(64, 4), grd(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, nframes);
+    DRFE_LAUNCH(k_pyr_level0, grd, blk, 0, st, h->dd, src, rs, fs);
+  }
+  for (int l = 1; l < nl; ++l) {
+    const LevelDev& L = D.lv[l];
+    dim3 blk(64, 4), grd(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, nframes);
+    DRFE_LAUNCH(k_pyr_resize, grd, blk, 0, st, h->dd, l);
+  }
+  h->timer.mark("pyramid", st);
+  DRFE_LAUNCH(k_fast_cells<128>, dim3(h->ncells, nframes), 128, h->fast_smem, st, h->dd);
+  h->timer.mark("fast", st);
+  DRFE_LAUNCH(k_quadtree<256>, dim3(nl, nframes), 256, h->quad_smem, st, h->dd);
+  h->timer.mark("quadtree", st);
+  DRFE_LAUNCH(k_blur, dim3(h->ntiles, nframes), 256, 0, st, h->dd);
+  h->timer.mark("blur", st);
+  DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kDescWarps - 1) / kDescWarps, nl, nframes), kDescWarps * 32, 0, st, h->dd);
+  h->timer.mark("orient_describe", st);
+  h->last_frames = nframes;
+  h->pending = true;
+  return DRFE_OK;
+}
+
+int drfe_orb_sync(drfe_orb* h) {
+  if (!h) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  return DRFE_OK;
+}
+
+static int orb_check_status(drfe_orb* h) {
+  int st = 0;
+  DRFE_CUDA(cudaMemcpyAsync(&st, h->hd.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  if (st) {
+    DRFE_CUDA(cudaMemsetAsync(h->hd.status, 0, sizeof(int), h->stream));
+    set_error("device buffer overflow (status %d: 1 = FAST candidates, 2 = quadtree nodes)", st);
+    return DRFE_ERR_CAPACITY;
+  }
+  return DRFE_OK;
+}
+
+int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_per_frame, int* counts) {
+  if (!h || !counts) { set_error("drfe_orb_download: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_orb_download: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames, cap = h->hd.kp_cap;
+  DRFE_CUDA(cudaMemcpyAsync(counts, h->hd.out_cnt, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (kps) {
+    if (cap_per_frame >= cap)
+      DRFE_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap_per_frame * sizeof(drfe_keypoint), h->hd.out_kp, (size_t)cap * sizeof(drfe_keypoint),
+                                  (size_t)cap * sizeof(drfe_keypoint), nf, cudaMemcpyDeviceToHost, st));
+    else
+      DRFE_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap_per_frame * sizeof(drfe_keypoint), h->hd.out_kp, (size_t)cap * sizeof(drfe_keypoint),
+                                  (size_t)cap_per_frame * sizeof(drfe_keypoint), nf, cudaMemcpyDeviceToHost, st));
+  }
+  if (desc) {
+    const size_t wbytes = (size_t)std::min(cap, cap_per_frame) * 32;
+    DRFE_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap_per_frame * 32, h->hd.out_desc, (size_t)cap * 32, wbytes, nf,
+                                cudaMemcpyDeviceToHost, st));
+  }
+  const int rc = orb_check_status(h);
+  if (rc != DRFE_OK) return rc;
+  for (int f = 0; f < nf; ++f)
+    if (counts[f] > cap_per_frame && (kps || desc)) {
+      set_error("drfe_orb_download: frame %d has %d keypoints, cap_per_frame is %d", f, counts[f], cap_per_frame);
+      return DRFE_ERR_CAPACITY;
+    }
+  return DRFE_OK;
+}
+
+int drfe_orb_extract(drfe_orb* h, const uint8_t* gray, int width, int height, size_t row_stride, drfe_keypoint* kps,
+                     uint8_t* desc, int cap, int* n) {
+  if (!h) { set_error("drfe_orb_extract: null handle"); return DRFE_ERR_ARG; }
+  if (!gray || width == 0 || height == 0) return DRFE_OK;  // empty image: silent return (ORBextractor.cc:1046)
+  if (width != h->width || height != h->height) { set_error("drfe_orb_extract: image is %dx%d, handle was created for %dx%d", width, height, h->width, h->height); return DRFE_ERR_ARG; }
+  if (!n) { set_error("drfe_orb_extract: null count pointer"); return DRFE_ERR_ARG; }
+  int rc = drfe_orb_enqueue(h, 1, gray, row_stride, row_stride * height, DRFE_MEM_HOST);
+  if (rc != DRFE_OK) return rc;
+  return drfe_orb_download(h, kps, desc, cap, n);
+}
+
+// ---------------------------------------------------------------- intermediates
+static int orb_frame_level_ok(drfe_orb* h, int frame, int level) {
+  if (!h) { set_error("null handle"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("nothing enqueued"); return DRFE_ERR_STATE; }
+  if (frame < 0 || frame >= h->last_frames || level < 0 || level >= h->prm.nlevels) { set_error("bad frame/level"); return DRFE_ERR_ARG; }
+  return DRFE_OK;
+}
+
+int drfe_orb_get_pyramid(drfe_orb* h, int frame, int level, int bordered, uint8_t* dst) {
+  int rc = orb_frame_level_ok(h, frame, level);
+  if (rc) return rc;
+  if (!dst) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  const LevelDev& L = h->hd.lv[level];
+  const uint8_t* base = h->hd.pyr + L.img_off + (long long)frame * L.img_fstride;
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  if (bordered)
+    DRFE_CUDA(cudaMemcpy2D(dst, L.w + 2 * kEdge, base + (kXOff - kEdge), L.pitch, L.w + 2 * kEdge, L.rows, cudaMemcpyDeviceToHost));
+  else
+    DRFE_CUDA(cudaMemcpy2D(dst, L.w, base + (long long)kEdge * L.pitch + kXOff, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+
+int drfe_orb_get_blurred(drfe_orb* h, int frame, int level, uint8_t* dst) {
+  int rc = orb_frame_level_ok(h, frame, level);
+  if (rc) return rc;
+  if (!dst) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  const LevelDev& L = h->hd.lv[level];
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  DRFE_CUDA(cudaMemcpy2D(dst, L.w, h->hd.blur + L.blur_off + (long long)frame * L.blur_fstride, L.bpitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+
+int drfe_orb_get_candidates(drfe_orb* h, int frame, int level, float* xyr, int cap, int* n) {
+  int rc = orb_frame_level_ok(h, frame, level);
+  if (rc) return rc;
+  if (!n) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  const LevelDev& L = h->hd.lv[level];
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  int cnt = 0;
+  DRFE_CUDA(cudaMemcpy(&cnt, h->hd.cand_cnt + frame * h->prm.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = cnt;
+  const int m = std::min(std::min(cnt, cap), L.cand_cap);
+  if (xyr && m > 0) {
+    std::vector<uint32_t> tmp(m);
+    DRFE_CUDA(cudaMemcpy(tmp.data(), h->hd.cand + (long long)frame * h->hd.cand_fstride + L.cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; ++i) {
+      xyr[3 * i] = (float)(tmp[i] & 0xFFF); xyr[3 * i + 1] = (float)((tmp[i] >> 12) & 0xFFF); xyr[3 * i + 2] = (float)(tmp[i] >> 24);
+    }
+  }
+  if (cnt > L.cand_cap) { set_error("candidate buffer overflow on level %d (%d > %d)", level, cnt, L.cand_cap); return DRFE_ERR_CAPACITY; }
+  return DRFE_OK;
+}
+
+int drfe_orb_get_level_keypoints(drfe_orb* h, int frame, int level, drfe_keypoint* dst, int cap, int* n) {
+  int rc = orb_frame_level_ok(h, frame, level);
+  if (rc) return rc;
+  if (!n) return DRFE_ERR_ARG;
+  DeviceScope ds(h->device);
+  const int nl = h->prm.nlevels, kcap = h->hd.kp_cap;
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  std::vector<int> cnts(nl);
+  DRFE_CUDA(cudaMemcpy(cnts.data(), h->hd.lkp_cnt + frame * nl, nl * sizeof(int), cudaMemcpyDeviceToHost));
+  int base = 0;
+  for (int l = 0; l < level; ++l) base += cnts[l];
+  const int cnt = cnts[level];
+  *n = cnt;
+  const int m = std::min(cnt, cap);
+  if (dst && m > 0) {
+    DRFE_CUDA(cudaMemcpy(dst, h->hd.out_kp + (long long)frame * kcap + base, (size_t)m * sizeof(drfe_keypoint), cudaMemcpyDeviceToHost));
+    // out_kp holds level-0-scaled coordinates; undo with the exact packed level coordinates
+    std::vector<uint32_t> pk(m);
+    DRFE_CUDA(cudaMemcpy(pk.data(), h->hd.lkp + (long long)frame * h->hd.lkp_fstride + h->hd.lv[level].kp_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; ++i) { dst[i].x = (float)(pk[i] & 0xFFF); dst[i].y = (float)((pk[i] >> 12) & 0xFFF); }
+  }
+  return DRFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+"""ctypes binding of libdrfe.so (the C ABI in include/drfe.h) plus thin Python mirrors of the
+reference's operator interfaces, used by the tests and bench:
+
+    ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)(image, mask)
+        -> Planar_SLAM::ORBextractor::operator()  (reference include/ORBextractor.h:51-61)
+    CAPE(depth_height, depth_width, cell_width, cell_height, cylinder_detection,
+         min_cos_angle_4_merge, max_merge_dist).process(cloud_array)
+        -> CAPE::process  (reference src/CAPE/CAPE.h:47-48)
+    PlaneDetectionCAPE  -> PlaneDetection_CAPE::readDepthImage / runPlaneDetection
+        (reference include/PlaneExtractor.h:84-115)
+
+There is no CPU fallback: if libdrfe.so is missing or no CUDA device is usable these raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdrfe.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+PLANE_DTYPE = np.dtype([("nr_pts", "<i4"), ("min_nr_pts", "<i4"),
+                        ("x_acc", "<f8"), ("y_acc", "<f8"), ("z_acc", "<f8"),
+                        ("xx_acc", "<f8"), ("yy_acc", "<f8"), ("zz_acc", "<f8"),
+                        ("xy_acc", "<f8"), ("xz_acc", "<f8"), ("yz_acc", "<f8"),
+                        ("score", "<f4"), ("MSE", "<f4"), ("planar", "<i4"),
+                        ("mean", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8")], align=True)
+CYL_DTYPE = np.dtype([("radius", "<f4"), ("center", "<f8", (3,)), ("axis", "<f8", (3,))], align=True)
+
+MEM_HOST, MEM_DEVICE = 0, 1
+OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class CapeParams(C.Structure):
+    _fields_ = [("depth_height", C.c_int32), ("depth_width", C.c_int32), ("cell_width", C.c_int32),
+                ("cell_height", C.c_int32), ("cylinder_detection", C.c_int32),
+                ("min_cos_angle_4_merge", C.c_float), ("max_merge_dist", C.c_float)]
+
+
+class DrfeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("drfe error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/drfe.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "drfe_last_error", "drfe_version", "drfe_device_count", "drfe_kernel_launch_count",
+    "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
+    "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
+    "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
+    "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
+    "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
+    "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
+    "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
+    "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
+    "drfe_cape_get_grid_maps", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libdrfe.so (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libdrfe.so not found at %s — run __graft_entry__.build() "
+                          "(make -C dr-slam_b200/csrc); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)
+    L.drfe_last_error.restype = C.c_char_p
+    L.drfe_version.restype = C.c_char_p
+    L.drfe_device_count.argtypes = [i32p]
+    L.drfe_kernel_launch_count.restype = C.c_int64
+    L.drfe_orb_create.argtypes = [C.POINTER(OrbParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.drfe_orb_destroy.argtypes = [vp]
+    L.drfe_orb_get_levels.argtypes = [vp]
+    L.drfe_orb_get_scale_factor.argtypes = [vp]
+    L.drfe_orb_get_scale_factor.restype = C.c_float
+    L.drfe_orb_get_scale_factors.argtypes = [vp, vp, vp, vp, vp]
+    L.drfe_orb_features_per_level.argtypes = [vp, C.c_int]
+    L.drfe_orb_max_keypoints.argtypes = [vp]
+    L.drfe_orb_extract.argtypes = [vp, vp, C.c_int, C.c_int, sz, vp, vp, C.c_int, i32p]
+    L.drfe_orb_enqueue.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int]
+    L.drfe_orb_download.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.drfe_orb_sync.argtypes = [vp]
+    L.drfe_orb_stream.argtypes = [vp]
+    L.drfe_orb_stream.restype = vp
+    L.drfe_orb_level_size.argtypes = [vp, C.c_int, i32p, i32p]
+    L.drfe_orb_get_pyramid.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.drfe_orb_get_blurred.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.drfe_orb_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, i32p]
+    L.drfe_orb_get_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, i32p]
+    L.drfe_orb_set_profiling.argtypes = [vp, C.c_int]
+    L.drfe_orb_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
+    L.drfe_cape_create.argtypes = [C.POINTER(CapeParams), C.c_int, C.c_int, C.POINTER(vp)]
+    L.drfe_cape_destroy.argtypes = [vp]
+    L.drfe_cape_enqueue_cloud.argtypes = [vp, C.c_int, vp, sz, C.c_int]
+    L.drfe_cape_enqueue_depth.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.drfe_cape_download.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp]
+    L.drfe_cape_sync.argtypes = [vp]
+    L.drfe_cape_stream.argtypes = [vp]
+    L.drfe_cape_stream.restype = vp
+    L.drfe_cape_process.argtypes = [vp, vp, vp, vp, C.c_int, i32p, vp, C.c_int, i32p]
+    L.drfe_cape_process_depth.argtypes = [vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, C.c_int,
+                                          i32p, vp, C.c_int, i32p]
+    L.drfe_cape_num_cells.argtypes = [vp, i32p, i32p]
+    L.drfe_cape_get_cloud.argtypes = [vp, C.c_int, vp]
+    L.drfe_cape_get_cells.argtypes = [vp, C.c_int, vp]
+    L.drfe_cape_get_grid_maps.argtypes = [vp, C.c_int, vp, vp]
+    L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
+    L.drfe_cape_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
+    L.drfe_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_float, vp, vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise DrfeError(rc, lib().drfe_last_error().decode())
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    n = C.c_int32(0)
+    lib().drfe_device_count(C.byref(n))
+    return n.value
+
+
+def kernel_launch_count():
+    return int(lib().drfe_kernel_launch_count())
+
+
+def synth_frame(width=640, height=480, scene=0, seed=20260000, depth_unit_scale=1.0):
+    """Deterministic procedural RGB-D frame -> (gray u8 HxW, depth f32 HxW, (fx, fy, cx, cy))."""
+    gray = np.empty((height, width), np.uint8)
+    depth = np.empty((height, width), np.float32)
+    K = [C.c_float() for _ in range(4)]
+    _check(lib().drfe_synth_frame(width, height, scene, seed, depth_unit_scale, _ptr(gray), _ptr(depth),
+                                  *[C.cast(C.byref(k), C.c_void_p) for k in K]))
+    return gray, depth, tuple(k.value for k in K)
+
+
+def _stage_times(fn, h):
+    ms = (C.c_float * 16)()
+    names = (C.c_char_p * 16)()
+    n = C.c_int32(0)
+    _check(fn(h, C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), 16, C.byref(n)))
+    return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+
+class ORBextractor:
+    """Planar_SLAM::ORBextractor with its constructor arguments (ORBextractor.h:51-52).  The image
+    size and the maximum frame batch are fixed per instance (device buffers are preallocated)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
+                 width=640, height=480, max_batch=1, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.width, self.height, self.max_batch, self.nlevels = width, height, max_batch, nlevels
+        prm = OrbParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        _check(self.L.drfe_orb_create(C.byref(prm), width, height, max_batch, device, C.byref(self.h)))
+        self.cap = self.L.drfe_orb_max_keypoints(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drfe_orb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- getters (ORBextractor.h:63-83)
+    def GetLevels(self):
+        return self.L.drfe_orb_get_levels(self.h)
+
+    def GetScaleFactor(self):
+        return self.L.drfe_orb_get_scale_factor(self.h)
+
+    def _factors(self):
+        a = [np.empty(self.nlevels, np.float32) for _ in range(4)]
+        _check(self.L.drfe_orb_get_scale_factors(self.h, *[_ptr(x) for x in a]))
+        return a
+
+    def GetScaleFactors(self):
+        return self._factors()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._factors()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._factors()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._factors()[3]
+
+    def features_per_level(self):
+        return [self.L.drfe_orb_features_per_level(self.h, l) for l in range(self.nlevels)]
+
+    # ---- operator()
+    def __call__(self, image, mask=None):
+        """operator()(image, mask, keypoints, descriptors): mask is ignored (ORBextractor.h:58).
+        An empty image returns (None, None) — the reference returns without touching its outputs."""
+        if image is None or image.size == 0:
+            return None, None
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise AssertionError("image.type() == CV_8UC1")   # reference asserts (ORBextractor.cc:1050)
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kps = np.empty(self.cap, KP_DTYPE)
+        desc = np.empty((self.cap, 32), np.uint8)
+        n = C.c_int32(0)
+        _check(self.L.drfe_orb_extract(self.h, _ptr(image), image.shape[1], image.shape[0], image.strides[0],
+                                       _ptr(kps), _ptr(desc), self.cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    # ---- batched
+    def enqueue(self, gray, mem_kind=MEM_HOST, nframes=None, row_stride=None, frame_stride=None):
+        """gray: (B,H,W) uint8 numpy array (host) or a raw device pointer (int) with explicit strides."""
+        if isinstance(gray, np.ndarray):
+            assert gray.dtype == np.uint8 and gray.ndim == 3 and gray.strides[2] == 1
+            nframes, row_stride, frame_stride = gray.shape[0], gray.strides[1], gray.strides[0]
+            self._keep = gray
+        _check(self.L.drfe_orb_enqueue(self.h, nframes, _ptr(gray), row_stride, frame_stride, mem_kind))
+        self._nframes = nframes
+
+    def download(self, kps=None, desc=None, counts=None):
+        nf = self._nframes
+        kps = np.empty((nf, self.cap), KP_DTYPE) if kps is None else kps
+        desc = np.empty((nf, self.cap, 32), np.uint8) if desc is None else desc
+        counts = np.empty(nf, np.int32) if counts is None else counts
+        _check(self.L.drfe_orb_download(self.h, _ptr(kps), _ptr(desc), self.cap, _ptr(counts)))
+        return kps, desc, counts
+
+    def sync(self):
+        _check(self.L.drfe_orb_sync(self.h))
+
+    def stream(self):
+        return self.L.drfe_orb_stream(self.h)
+
+    def set_profiling(self, on=True):
+        _check(self.L.drfe_orb_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        return _stage_times(self.L.drfe_orb_stage_times, self.h)
+
+    # ---- intermediates (mvImagePyramid etc.)
+    def level_size(self, level):
+        w, h = C.c_int32(), C.c_int32()
+        _check(self.L.drfe_orb_level_size(self.h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def pyramid(self, frame, level, bordered=False):
+        w, h = self.level_size(level)
+        if bordered:
+            w, h = w + 38, h + 38
+        out = np.empty((h, w), np.uint8)
+        _check(self.L.drfe_orb_get_pyramid(self.h, frame, level, int(bordered), _ptr(out)))
+        return out
+
+    def blurred(self, frame, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        _check(self.L.drfe_orb_get_blurred(self.h, frame, level, _ptr(out)))
+        return out
+
+    def candidates(self, frame, level):
+        cap = 1 << 16
+        buf = np.empty((cap, 3), np.float32)
+        n = C.c_int32(0)
+        _check(self.L.drfe_orb_get_candidates(self.h, frame, level, _ptr(buf), cap, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def level_keypoints(self, frame, level):
+        buf = np.empty(self.cap, KP_DTYPE)
+        n = C.c_int32(0)
+        _check(self.L.drfe_orb_get_level_keypoints(self.h, frame, level, _ptr(buf), self.cap, C.byref(n)))
+        return buf[:n.value].copy()
+
+
+class CAPE:
+    """CAPE with its constructor arguments (CAPE.h:47)."""
+
+    def __init__(self, depth_height, depth_width, cell_width, cell_height, cylinder_detection=False,
+                 min_cos_angle_4_merge=0.97814, max_merge_dist=900.0, max_batch=1, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.H, self.W, self.cw, self.ch, self.max_batch = depth_height, depth_width, cell_width, cell_height, max_batch
+        prm = CapeParams(depth_height, depth_width, cell_width, cell_height, int(cylinder_detection),
+                         min_cos_angle_4_merge, max_merge_dist)
+        _check(self.L.drfe_cape_create(C.byref(prm), max_batch, device, C.byref(self.h)))
+        cx, cy = C.c_int32(), C.c_int32()
+        self.L.drfe_cape_num_cells(self.h, C.byref(cx), C.byref(cy))
+        self.ncx, self.ncy = cx.value, cy.value
+        self.plane_cap = 255
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drfe_cape_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def process(self, cloud_array, seg_output=None):
+        """process(cloud_array, nr_planes, nr_cylinders, seg_output, plane_segments_final,
+        cylinder_segments_final) -> (nr_planes, nr_cylinders, seg_output, planes, cylinders).
+        cloud_array: cell-major N x 3 column-major float32 (flat 3*N: all X, all Y, all Z).
+        Like the reference only labelled pixels of a passed-in seg_output are overwritten."""
+        cloud = np.ascontiguousarray(cloud_array, np.float32).reshape(-1)
+        assert cloud.size == 3 * self.H * self.W
+        seg = np.empty((self.H, self.W), np.uint8)
+        planes = np.zeros(self.plane_cap, PLANE_DTYPE)
+        npl, ncyl = C.c_int32(0), C.c_int32(0)
+        _check(self.L.drfe_cape_process(self.h, _ptr(cloud), _ptr(seg), _ptr(planes), self.plane_cap, C.byref(npl),
+                                        None, 0, C.byref(ncyl)))
+        if seg_output is not None:
+            seg_output[seg > 0] = seg[seg > 0]
+            seg = seg_output
+        return npl.value, ncyl.value, seg, planes[:npl.value].copy(), []
+
+    def process_depth(self, depth, fx, fy, cx, cy):
+        depth = np.ascontiguousarray(depth, np.float32)
+        seg = np.empty((self.H, self.W), np.uint8)
+        planes = np.zeros(self.plane_cap, PLANE_DTYPE)
+        npl, ncyl = C.c_int32(0), C.c_int32(0)
+        _check(self.L.drfe_cape_process_depth(self.h, _ptr(depth), depth.strides[0] // 4, fx, fy, cx, cy, _ptr(seg),
+                                              _ptr(planes), self.plane_cap, C.byref(npl), None, 0, C.byref(ncyl)))
+        return npl.value, ncyl.value, seg, planes[:npl.value].copy(), []
+
+    # ---- batched
+    def enqueue_depth(self, depth, fx, fy, cx, cy, mem_kind=MEM_HOST, nframes=None, row_stride=None, frame_stride=None):
+        if isinstance(depth, np.ndarray):
+            assert depth.dtype == np.float32 and depth.ndim == 3 and depth.strides[2] == 4
+            nframes, row_stride, frame_stride = depth.shape[0], depth.strides[1] // 4, depth.strides[0] // 4
+            self._keep = depth
+        _check(self.L.drfe_cape_enqueue_depth(self.h, nframes, _ptr(depth), row_stride, frame_stride, mem_kind,
+                                              fx, fy, cx, cy))
+        self._nframes = nframes
+
+    def enqueue_cloud(self, cloud, mem_kind=MEM_HOST, nframes=None, frame_stride=None):
+        if isinstance(cloud, np.ndarray):
+            assert cloud.dtype == np.float32 and cloud.ndim == 2
+            nframes, frame_stride = cloud.shape[0], cloud.strides[0] // 4
+            self._keep = cloud
+        _check(self.L.drfe_cape_enqueue_cloud(self.h, nframes, _ptr(cloud), frame_stride, mem_kind))
+        self._nframes = nframes
+
+    def download(self, seg=None, planes=None, nplanes=None):
+        nf = self._nframes
+        seg = np.empty((nf, self.H, self.W), np.uint8) if seg is None else seg
+        planes = np.zeros((nf, self.plane_cap), PLANE_DTYPE) if planes is None else planes
+        nplanes = np.empty(nf, np.int32) if nplanes is None else nplanes
+        ncyl = np.empty(nf, np.int32)
+        _check(self.L.drfe_cape_download(self.h, _ptr(seg), _ptr(planes), planes.shape[1], _ptr(nplanes), None, 0,
+                                         _ptr(ncyl)))
+        return seg, planes, nplanes
+
+    def sync(self):
+        _check(self.L.drfe_cape_sync(self.h))
+
+    def stream(self):
+        return self.L.drfe_cape_stream(self.h)
+
+    def set_profiling(self, on=True):
+        _check(self.L.drfe_cape_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        return _stage_times(self.L.drfe_cape_stage_times, self.h)
+
+    # ---- intermediates
+    def cloud(self, frame=0):
+        out = np.empty(3 * self.H * self.W, np.float32)
+        _check(self.L.drfe_cape_get_cloud(self.h, frame, _ptr(out)))
+        return out
+
+    def cells(self, frame=0):
+        out = np.zeros(self.ncx * self.ncy, PLANE_DTYPE)
+        _check(self.L.drfe_cape_get_cells(self.h, frame, _ptr(out)))
+        return out
+
+    def grid_maps(self, frame=0):
+        pm = np.zeros((self.ncy, self.ncx), np.int32)
+        em = np.zeros((self.ncy, self.ncx), np.uint8)
+        _check(self.L.drfe_cape_get_grid_maps(self.h, frame, _ptr(pm), _ptr(em)))
+        return pm, em
+
+
+class PlaneDetectionCAPE:
+    """PlaneDetection_CAPE (PlaneExtractor.h:84-115): readDepthImage + runPlaneDetection with
+    the public result fields nr_planes, nr_cylinders, seg_output, plane_params."""
+
+    def __init__(self, PATCH_SIZE=20, MAX_MERGE_DIST=50.0, cylinder_detection=False, device=0):
+        self.PATCH_SIZE, self.MAX_MERGE_DIST, self.cylinder_detection = PATCH_SIZE, MAX_MERGE_DIST, cylinder_detection
+        self.COS_ANGLE_MAX = float(np.float32(np.cos(np.pi / 12)))   # PlaneExtractor.h:111
+        self.device = device
+        self._cape = None
+        self.depth_img = None
+
+    def readDepthImage(self, depthImg, K):
+        if depthImg is None or depthImg.size == 0 or depthImg.dtype != np.float32:
+            return False          # reference prints a warning and returns false (PlaneExtractor.cpp:104-107)
+        self.depth_img, self.K_ = depthImg, np.asarray(K, np.float32)
+        return True
+
+    def runPlaneDetection(self):
+        H, W = self.depth_img.shape
+        if self._cape is None or (self._cape.H, self._cape.W) != (H, W):
+            self._cape = CAPE(H, W, self.PATCH_SIZE, self.PATCH_SIZE, self.cylinder_detection, self.COS_ANGLE_MAX,
+                              self.MAX_MERGE_DIST, device=self.device)
+        K = self.K_
+        (self.nr_planes, self.nr_cylinders, self.seg_output, self.plane_params,
+         self.cylinder_params) = self._cape.process_depth(self.depth_img, float(K[0, 0]), float(K[1, 1]),
+                                                          float(K[0, 2]), float(K[1, 2]))

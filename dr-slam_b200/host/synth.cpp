@@ -179,7 +179,7 @@ extern "C" int drfe_synth_frame(int width, int height, int scene, uint32_t seed,
     for (int u = 0; u < width; ++u) {
       const float xn = ((float)u - pcx) / f, yn = ((float)v - pcy) / f;
       V3 d = right * xn + down * yn + fwd;  // camera-frame z component is exactly 1 => depth z = t
-      Hit best, h;
+      Hit best{}, h{};
       hit_box(room, pos, d, true, best);
       for (const Box& b : boxes)
         if (hit_box(b, pos, d, false, h) && h.t < best.t) best = h;
