@@ -35,4 +35,33 @@ int drfe_device_count(int* count) {
   return DRFE_OK;
 }
 
+
+// ---- device timers for callers that drive several handles (bench): CUDA events on the
+// handles' own streams.
+int drfe_event_create(void** ev) {
+  if (!ev) return DRFE_ERR_ARG;
+  cudaEvent_t e;
+  DRFE_CUDA(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return DRFE_OK;
+}
+int drfe_event_destroy(void* ev) {
+  if (ev) DRFE_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return DRFE_OK;
+}
+int drfe_event_record(void* ev, void* stream) {
+  DRFE_CUDA(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream));
+  return DRFE_OK;
+}
+int drfe_stream_wait_event(void* stream, void* ev) {
+  DRFE_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+  return DRFE_OK;
+}
+int drfe_event_elapsed_ms(void* start, void* stop, float* ms) {
+  if (!ms) return DRFE_ERR_ARG;
+  DRFE_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  DRFE_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return DRFE_OK;
+}
+
 }  // extern "C"

@@ -718,7 +718,7 @@ int drfe_cape_num_cells(const drfe_cape* h, int* cx, int* cy) {
   if (cy) *cy = h->hd.ncy;
   return DRFE_OK;
 }
-int drfe_cape_set_profiling(drfe_cape* h, int on) { if (!h) return DRFE_ERR_ARG; h->timer.enabled = on != 0; return DRFE_OK; }
+int drfe_cape_set_profiling(drfe_cape* h, int on) { if (!h) return DRFE_ERR_ARG; h->timer.reset(on != 0); return DRFE_OK; }
 int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages) {
   if (!h || !ms || !nstages) return DRFE_ERR_ARG;
   DeviceScope ds(h->device);

@@ -52,43 +52,60 @@ struct DeviceScope {
   }
 };
 
-// per-stage device timers (cudaEvent pairs on the handle's stream)
+// per-stage device timers: cudaEvent pairs on the handle's stream, kept for the last
+// kSlots enqueues so a bench can read per-kernel averages AFTER its timed region without
+// synchronising inside it.
 struct StageTimer {
-  static const int kMax = 16;
-  cudaEvent_t ev[kMax + 1];
+  static const int kMax = 12, kSlots = 64;
+  cudaEvent_t ev[kSlots][kMax + 1];
   const char* names[kMax];
-  int n = 0;
-  bool enabled = false, created = false, valid = false;
+  int n = 0, slot = -1, filled = 0;
+  bool enabled = false, created = false;
   int create() {
-    for (int i = 0; i <= kMax; ++i) DRFE_CUDA(cudaEventCreate(&ev[i]));
+    for (int s = 0; s < kSlots; ++s)
+      for (int i = 0; i <= kMax; ++i) DRFE_CUDA(cudaEventCreate(&ev[s][i]));
     created = true;
     return DRFE_OK;
   }
   void destroy() {
     if (created)
-      for (int i = 0; i <= kMax; ++i) cudaEventDestroy(ev[i]);
+      for (int s = 0; s < kSlots; ++s)
+        for (int i = 0; i <= kMax; ++i) cudaEventDestroy(ev[s][i]);
     created = false;
   }
+  void reset(bool on) { enabled = on; slot = -1; filled = 0; n = 0; }
   void begin(cudaStream_t s) {
-    n = 0; valid = false;
-    if (enabled) cudaEventRecord(ev[0], s);
+    if (!enabled) return;
+    slot = (slot + 1) % kSlots;
+    if (filled < kSlots) ++filled;
+    n = 0;
+    cudaEventRecord(ev[slot][0], s);
   }
   void mark(const char* name, cudaStream_t s) {
-    if (!enabled || n >= kMax) return;
+    if (!enabled || slot < 0 || n >= kMax) return;
     names[n] = name;
-    cudaEventRecord(ev[n + 1], s);
+    cudaEventRecord(ev[slot][n + 1], s);
     ++n;
-    valid = true;
   }
+  // average over the recorded enqueues (all must have run the same stage sequence)
   int read(float* ms, const char** out_names, int cap, int* nstages) {
     *nstages = 0;
-    if (!enabled || !valid) return DRFE_OK;
-    DRFE_CUDA(cudaEventSynchronize(ev[n]));
-    for (int i = 0; i < n && i < cap; ++i) {
-      DRFE_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    if (!enabled || filled == 0) return DRFE_OK;
+    const int m = n < cap ? n : cap;
+    for (int i = 0; i < m; ++i) ms[i] = 0.f;
+    for (int s = 0; s < filled; ++s) {
+      DRFE_CUDA(cudaEventSynchronize(ev[s][n]));
+      for (int i = 0; i < m; ++i) {
+        float t = 0.f;
+        DRFE_CUDA(cudaEventElapsedTime(&t, ev[s][i], ev[s][i + 1]));
+        ms[i] += t;
+      }
+    }
+    for (int i = 0; i < m; ++i) {
+      ms[i] /= (float)filled;
       if (out_names) out_names[i] = names[i];
     }
-    *nstages = n < cap ? n : cap;
+    *nstages = m;
     return DRFE_OK;
   }
 };

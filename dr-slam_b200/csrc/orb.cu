@@ -938,7 +938,7 @@ int drfe_orb_level_size(const drfe_orb* h, int level, int* w, int* hgt) {
   if (hgt) *hgt = h->hd.lv[level].h;
   return DRFE_OK;
 }
-int drfe_orb_set_profiling(drfe_orb* h, int on) { if (!h) return DRFE_ERR_ARG; h->timer.enabled = on != 0; return DRFE_OK; }
+int drfe_orb_set_profiling(drfe_orb* h, int on) { if (!h) return DRFE_ERR_ARG; h->timer.reset(on != 0); return DRFE_OK; }
 int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, int* nstages) {
   if (!h || !ms || !nstages) return DRFE_ERR_ARG;
   DeviceScope ds(h->device);

@@ -53,6 +53,8 @@ class DrfeError(RuntimeError):
 # every symbol include/drfe.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "drfe_last_error", "drfe_version", "drfe_device_count", "drfe_kernel_launch_count",
+    "drfe_event_create", "drfe_event_destroy", "drfe_event_record", "drfe_stream_wait_event",
+    "drfe_event_elapsed_ms",
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
@@ -81,6 +83,11 @@ def lib():
     L.drfe_version.restype = C.c_char_p
     L.drfe_device_count.argtypes = [i32p]
     L.drfe_kernel_launch_count.restype = C.c_int64
+    L.drfe_event_create.argtypes = [C.POINTER(vp)]
+    L.drfe_event_destroy.argtypes = [vp]
+    L.drfe_event_record.argtypes = [vp, vp]
+    L.drfe_stream_wait_event.argtypes = [vp, vp]
+    L.drfe_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.drfe_orb_create.argtypes = [C.POINTER(OrbParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.drfe_orb_destroy.argtypes = [vp]
     L.drfe_orb_get_levels.argtypes = [vp]
@@ -155,6 +162,31 @@ def synth_frame(width=640, height=480, scene=0, seed=20260000, depth_unit_scale=
     _check(lib().drfe_synth_frame(width, height, scene, seed, depth_unit_scale, _ptr(gray), _ptr(depth),
                                   *[C.cast(C.byref(k), C.c_void_p) for k in K]))
     return gray, depth, tuple(k.value for k in K)
+
+
+class Event:
+    """CUDA event on a handle stream (device-side timing)."""
+
+    def __init__(self):
+        self.e = C.c_void_p()
+        _check(lib().drfe_event_create(C.byref(self.e)))
+
+    def record(self, stream):
+        _check(lib().drfe_event_record(self.e, stream))
+
+    def elapsed_ms(self, stop):
+        ms = C.c_float(0)
+        _check(lib().drfe_event_elapsed_ms(self.e, stop.e, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        if getattr(self, "e", None):
+            lib().drfe_event_destroy(self.e)
+            self.e = None
+
+
+def stream_wait_event(stream, event):
+    _check(lib().drfe_stream_wait_event(stream, event.e))
 
 
 def _stage_times(fn, h):

@@ -97,6 +97,14 @@ int drfe_device_count(int* count);   /* number of CUDA devices visible          
 /* total number of drfe kernel launches issued by this process (bench "gpu_launches") */
 int64_t drfe_kernel_launch_count(void);
 
+/* CUDA-event timers on handle streams (for benches driving several handles): events are
+ * opaque; `stream` is what drfe_orb_stream / drfe_cape_stream return. */
+int drfe_event_create(void** ev);
+int drfe_event_destroy(void* ev);
+int drfe_event_record(void* ev, void* stream);
+int drfe_stream_wait_event(void* stream, void* ev);
+int drfe_event_elapsed_ms(void* start, void* stop, float* ms); /* waits for `stop` */
+
 /* ------------------------------------------------------------------ ORB
  * One handle = one ORBextractor instance bound to a device, an image size and a maximum
  * frame batch (frames of a batch are independent; batch=1 reproduces operator()). */
@@ -148,8 +156,9 @@ int drfe_orb_get_candidates(drfe_orb* h, int frame, int level, float* xyr, int c
  * coordinates, angle filled, not yet scaled to level 0). */
 int drfe_orb_get_level_keypoints(drfe_orb* h, int frame, int level, drfe_keypoint* dst, int cap,
                                  int* n);
-/* device time of the last enqueue, split by stage (ms); names[i] are static strings.
- * Only meaningful after drfe_orb_set_profiling(h, 1). */
+/* per-stage device time (ms) averaged over the enqueues (at most the last 64) issued since
+ * drfe_orb_set_profiling(h, 1); names[i] are static strings.  Reading waits for the stream;
+ * recording itself never synchronises. */
 int drfe_orb_set_profiling(drfe_orb* h, int on);
 int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, int* nstages);
 

@@ -1,0 +1,75 @@
+"""GPU: BASELINE-size batches (256 frames of 640x480) checked through size-independent
+properties plus oracle spot checks: every frame of a batch gives exactly what the same frame
+gives alone (frames are independent: no cross-frame state), results do not depend on the
+position inside the batch or on how the batch is sharded, keypoints respect the reference's
+geometric invariants."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+MC = float(np.float32(np.cos(np.pi / 12)))
+B = 256
+
+
+@pytest.fixture(scope="module")
+def sequence(drfe):
+    data = [drfe.synth_frame(640, 480, (i // 64) % 3, 20260000 + i) for i in range(B)]
+    return np.stack([d[0] for d in data]), np.stack([d[1] for d in data]), data[0][2]
+
+
+def test_orb_full_batch(drfe, orc, sequence):
+    gray, _, _ = sequence
+    ex = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=B)
+    ex.enqueue(gray)
+    kps, desc, counts = ex.download()
+    assert counts.min() >= 1000 and counts.max() <= ex.cap        # >= nfeatures on textured frames, <= N + overshoot
+    scale = ex.GetScaleFactors()
+    for f in range(B):
+        k = kps[f, :counts[f]]
+        lx, ly = k["x"] / scale[k["octave"]], k["y"] / scale[k["octave"]]
+        lw = np.array([ex.level_size(l)[0] for l in range(8)])[k["octave"]]
+        lh = np.array([ex.level_size(l)[1] for l in range(8)])[k["octave"]]
+        assert np.all(lx > 18.99) and np.all(ly > 18.99) and np.all(lx < lw - 18.99) and np.all(ly < lh - 18.99)   # EDGE_THRESHOLD
+        assert np.all(np.diff(k["octave"]) >= 0)                                   # levels ascending (:1076-1104)
+        assert np.all((k["angle"] >= 0) & (k["angle"] < 360)) and np.all(k["response"] >= 7)
+    # sharding invariance: the same frames in two half batches at different positions
+    ex2 = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=B // 2)
+    for half in range(2):
+        sl = slice(half * B // 2, (half + 1) * B // 2)
+        ex2.enqueue(gray[sl][::-1].copy())                         # reversed order inside the shard
+        k2, d2, c2 = ex2.download()
+        assert np.array_equal(c2[::-1], counts[sl])
+        for j in (0, 17, B // 2 - 1):
+            f = sl.start + (B // 2 - 1 - j)
+            assert k2[j, :c2[j]].tobytes() == kps[f, :counts[f]].tobytes() and np.array_equal(d2[j, :c2[j]], desc[f, :counts[f]])
+    # oracle spot checks
+    o = orc.OrbOracle(1000)
+    for f in (0, 100, 255):
+        rk, rd = o.extract(gray[f])
+        assert counts[f] == len(rk)
+        for n in ("x", "y", "response", "octave", "angle"):
+            assert np.array_equal(kps[f, :counts[f]][n], rk[n]), n
+        ham = np.unpackbits(desc[f, :counts[f]] ^ rd, axis=1).sum(1)
+        assert (ham == 0).mean() >= 0.995 and ham.max() <= 8
+
+
+def test_cape_full_batch(drfe, orc, sequence):
+    _, depth, K = sequence
+    cp = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0, max_batch=B)
+    cp.enqueue_depth(depth, *K)
+    seg, planes, npl = cp.download()
+    assert npl.min() >= 1 and seg.max() <= npl.max()
+    for f in range(B):
+        assert seg[f].max() <= npl[f]
+        n = planes[f, :npl[f]]["normal"]
+        assert np.allclose((n ** 2).sum(1), 1, atol=1e-9) and np.all(planes[f, :npl[f]]["d"] > 0)   # d > 0 orientation rule
+    cp2 = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0, max_batch=64)
+    cp2.enqueue_depth(depth[100:164], *K)
+    s2, p2, n2 = cp2.download()
+    assert np.array_equal(s2, seg[100:164]) and np.array_equal(n2, npl[100:164])
+    o = orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
+    for f in (0, 77, 255):
+        oseg, oplanes = o.process(o.depth_to_cloud(depth[f], *K))
+        assert np.array_equal(seg[f], oseg) and npl[f] == len(oplanes)
+        assert np.allclose(planes[f, :npl[f]]["normal"], oplanes["normal"], atol=1e-5, rtol=0)
+        assert np.allclose(planes[f, :npl[f]]["d"], oplanes["d"], atol=1e-5, rtol=1e-9)

@@ -1,0 +1,147 @@
+"""GPU: the CUDA CAPE path through the C ABI against the CPU oracle and golden fixtures.
+Bars (BASELINE.json north_star): cell segmentation and seg_output bit-exact, plane normals
+and offsets within 1e-5 (here they are bit-identical to the oracle, which runs the same
+Jacobi eigen-solve; the golden fixtures use LAPACK, hence the 1e-9 tolerance there)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+MC = float(np.float32(np.cos(np.pi / 12)))
+TOL = 1e-5
+
+
+def compare_with_oracle(cp, o, depth, K, f=0, exact=True):
+    cloud = o.depth_to_cloud(depth, *K)
+    oseg, oplanes = o.process(cloud)
+    assert np.array_equal(cp.cloud(f), cloud), "organized cloud"
+    cg, co = cp.cells(f), o.cells()
+    for n in ("nr_pts", "planar", "x_acc", "y_acc", "z_acc", "xx_acc", "yy_acc", "zz_acc", "xy_acc", "xz_acc", "yz_acc"):
+        assert np.array_equal(cg[n], co[n]), "cell %s" % n
+    assert np.allclose(cg["normal"], co["normal"], atol=TOL, rtol=0) and np.allclose(cg["d"], co["d"], atol=TOL, rtol=1e-9)
+    if exact:
+        for n in ("normal", "d", "mean", "MSE", "score"):
+            assert np.array_equal(cg[n], co[n]), "cell %s (same Jacobi sequence)" % n
+    pm, em = cp.grid_maps(f)
+    opm, oem = o.grid_maps()
+    assert np.array_equal(pm, opm), "grid_plane_seg_map"
+    assert np.array_equal(em, oem), "eroded map"
+    return oseg, oplanes
+
+
+def check_planes(planes, oplanes):
+    assert len(planes) == len(oplanes)
+    assert np.array_equal(planes["nr_pts"], oplanes["nr_pts"])
+    assert np.allclose(planes["normal"], oplanes["normal"], atol=TOL, rtol=0)
+    assert np.allclose(planes["d"], oplanes["d"], atol=TOL, rtol=1e-9)
+    assert np.allclose(planes["MSE"], oplanes["MSE"], rtol=1e-5) and np.allclose(planes["score"], oplanes["score"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("w,h,scene,seed,unit,cell,mmd", [
+    (640, 480, 0, 20260000, 1.0, 20, 50.0),        # DR-SLAM feeds metres (Frame.cc:113-115)
+    (640, 480, 1, 20260077, 1.0, 20, 50.0),
+    (640, 480, 0, 20260100, 1000.0, 20, 50.0),     # CAPE's native millimetres
+    (640, 480, 2, 20260100, 1000.0, 20, 900.0),    # reference default max_merge_dist
+    (640, 480, 1, 20260012, 1000.0, 10, 50.0),     # Realsense.yaml PATCH_SIZE 10 (100-point cells: scalar tail path)
+    (1280, 720, 2, 20260140, 1000.0, 20, 50.0),    # configs[4] geometry
+])
+def test_cape_parity(drfe, orc, w, h, scene, seed, unit, cell, mmd):
+    _, depth, K = drfe.synth_frame(w, h, scene, seed, unit)
+    cp = drfe.CAPE(h, w, cell, cell, False, MC, mmd)
+    npl, ncyl, seg, planes, cyl = cp.process_depth(depth, *K)
+    o = orc.CapeOracle(h, w, cell, cell, False, MC, mmd)
+    oseg, oplanes = compare_with_oracle(cp, o, depth, K)
+    assert ncyl == 0 and npl == len(oplanes)
+    assert np.array_equal(seg, oseg), "seg_output: %d px differ" % (seg != oseg).sum()
+    check_planes(planes, oplanes)
+    cp.close()
+
+
+def test_process_cloud_entry_equals_depth_entry(drfe, orc):
+    """CAPE::process(cloud_array, ...) boundary: same result as the fused depth entry."""
+    _, depth, K = drfe.synth_frame(640, 480, 1, 20260055, 1000.0)
+    o = orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
+    cloud = o.depth_to_cloud(depth, *K)
+    cp = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0)
+    a = cp.process(cloud)
+    b = cp.process_depth(depth, *K)
+    assert a[0] == b[0] and np.array_equal(a[2], b[2]) and a[3].tobytes() == b[3].tobytes()
+    oseg, oplanes = o.process(cloud)
+    assert np.array_equal(a[2], oseg)
+    pre = np.full((480, 640), 9, np.uint8)                      # reference only writes labelled pixels
+    out = cp.process(cloud, seg_output=pre)[2]
+    assert np.array_equal(out[oseg > 0], oseg[oseg > 0]) and np.all(out[oseg == 0] == 9)
+
+
+@pytest.mark.parametrize("name", ["cape_640x480_corridor_m.npz", "cape_640x480_room_mm.npz",
+                                  "cape_320x240_room_mm_cell10.npz"])
+def test_cape_matches_golden(drfe, name):
+    g = load_golden(name)
+    depth = g["depth_q"].astype(np.float32) * np.float32(1.0 / 5000.0) * g["unit"]
+    h, w = depth.shape
+    cell = int(g["cell"])
+    cp = drfe.CAPE(h, w, cell, cell, False, float(g["min_cos"]), float(g["max_merge"]))
+    npl, _, seg, planes, _ = cp.process_depth(depth, *[float(v) for v in g["K"]])
+    cells = cp.cells()
+    assert np.array_equal(cells["planar"].astype(np.uint8), g["cell_planar"])
+    sums = np.stack([cells[f] for f in ("x_acc", "y_acc", "z_acc", "xx_acc", "yy_acc", "zz_acc", "xy_acc", "xz_acc", "yz_acc")], 1)
+    assert np.array_equal(sums, g["cell_sums"])
+    pm, em = cp.grid_maps()
+    assert np.array_equal(pm, g["plane_map"]) and np.array_equal(em, g["eroded_map"])
+    assert np.array_equal(seg, g["seg"])
+    assert npl == len(g["plane_d"])
+    assert np.allclose(planes["normal"], g["plane_normal"], atol=TOL, rtol=0)
+    assert np.allclose(planes["d"], g["plane_d"], atol=TOL, rtol=1e-9)
+
+
+def test_empty_depth_gives_no_planes(drfe, orc):
+    cp = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0)
+    npl, ncyl, seg, planes, _ = cp.process_depth(np.zeros((480, 640), np.float32), 525.0, 525.0, 319.5, 239.5)
+    assert npl == 0 and ncyl == 0 and not seg.any() and len(planes) == 0
+    assert not cp.cells()["planar"].any()
+
+
+def test_single_wall_one_plane(drfe, orc):
+    """A fronto-parallel wall in millimetres: one plane, normal (0,0,-1), d = depth."""
+    depth = np.full((480, 640), 2000.0, np.float32)
+    depth += np.random.default_rng(3).normal(0, 2.0, depth.shape).astype(np.float32)
+    K = (525.0, 525.0, 319.5, 239.5)
+    cp = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0)
+    npl, _, seg, planes, _ = cp.process_depth(depth, *K)
+    o = orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
+    oseg, oplanes = compare_with_oracle(cp, o, depth, K)
+    assert npl == 1 and np.array_equal(seg, oseg)
+    assert abs(planes["normal"][0][2] + 1) < 1e-3 and abs(planes["d"][0] - 2000) < 2
+    check_planes(planes, oplanes)
+
+
+def test_batch_equals_single_and_oracle(drfe, orc):
+    sel = [(0, 20260001), (1, 20260002), (2, 20260003), (0, 20260200)]
+    data = [drfe.synth_frame(640, 480, s, seed, 1000.0) for s, seed in sel]
+    depth = np.stack([d[1] for d in data])
+    K = data[0][2]
+    cpb = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0, max_batch=4)
+    cpb.enqueue_depth(depth, *K)
+    seg, planes, npl = cpb.download()
+    cp1 = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0)
+    o = orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
+    for f in range(4):
+        r = cp1.process_depth(depth[f], *K)
+        assert r[0] == npl[f] and np.array_equal(r[2], seg[f]) and r[3].tobytes() == planes[f, :npl[f]].tobytes()
+        oseg, oplanes = o.process(o.depth_to_cloud(depth[f], *K))
+        assert np.array_equal(seg[f], oseg)
+        check_planes(planes[f, :npl[f]], oplanes)
+
+
+def test_plane_detection_wrapper(drfe, orc):
+    """PlaneDetection_CAPE::readDepthImage / runPlaneDetection (PlaneExtractor.cpp:101-191)."""
+    _, depth, K = drfe.synth_frame(640, 480, 1, 20260090)
+    pd = drfe.PlaneDetectionCAPE(PATCH_SIZE=20, MAX_MERGE_DIST=50.0)
+    assert not pd.readDepthImage(depth.astype(np.float64), np.eye(3))     # wrong depth type -> false
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+    assert pd.readDepthImage(depth, Km)
+    pd.runPlaneDetection()
+    o = orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
+    oseg, oplanes = o.process(o.depth_to_cloud(depth, *K))
+    assert pd.nr_planes == len(oplanes) and pd.nr_cylinders == 0 and np.array_equal(pd.seg_output, oseg)
