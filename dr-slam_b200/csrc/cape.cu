@@ -42,6 +42,7 @@ struct CapeDev {
   int* nplanes;                 // [B]
   uint8_t* seg;                 // [B][H*W]
   int* status;
+  void* cs_spill;               // [B][ncells] CellS in global memory when the grid does not fit in smem
 };
 
 // ---- 3x3 symmetric eigen-solve (cyclic Jacobi).  Mirrors eig3_sym() of the oracle
@@ -265,8 +266,10 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   const CapeDev& P = *Pp;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nc = P.ncells, ncx = P.ncx, ncy = P.ncy;
-  CellS* cs = reinterpret_cast<CellS*>(smem);
-  float* tol = reinterpret_cast<float*>(cs + nc);
+  // per-cell plane parameters live in shared memory unless the grid is too large for it
+  // (e.g. 10 px cells at 640x480 = 3072 cells), in which case they stay L2-resident
+  CellS* cs = P.cs_spill ? reinterpret_cast<CellS*>(P.cs_spill) + (long long)f * nc : reinterpret_cast<CellS*>(smem);
+  float* tol = P.cs_spill ? reinterpret_cast<float*>(smem) : reinterpret_cast<float*>(cs + nc);
   float* mse = tol + nc;
   int* bin = reinterpret_cast<int*>(mse + nc);      // histogram bin per cell (-1 = removed / non planar)
   int* pmap = bin + nc;                              // grid_plane_seg_map
@@ -690,7 +693,14 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   if (cudaMemset(D.status, 0, sizeof(int)) != cudaSuccess || cudaMemset(D.cloud, 0, 3 * N * B * sizeof(float)) != cudaSuccess) {
     set_error("cudaMemset failed"); return fail(DRFE_ERR_CUDA);
   }
-  h->grid_smem = nc * (sizeof(CellS) + 4 + 4 + 4 + 4 + 4 + 5) + kHistBins * kHistBins * 4 + 256 * 8 * 4 + 64;
+  const size_t grid_fixed = kHistBins * kHistBins * 4 + 256 * 8 * 4 + 64;
+  h->grid_smem = nc * (sizeof(CellS) + 4 + 4 + 4 + 4 + 4 + 5) + grid_fixed;
+  if (h->grid_smem > 160 * 1024) {
+    h->grid_smem = nc * (4 + 4 + 4 + 4 + 4 + 5) + grid_fixed;
+    CellS* spill = nullptr;
+    if (cape_alloc(h, &spill, nc * B)) return fail(DRFE_ERR_CUDA);
+    D.cs_spill = spill;
+  }
   if (h->grid_smem > 200 * 1024) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
   if (cudaFuncSetAttribute(k_cape_grid<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
     set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
