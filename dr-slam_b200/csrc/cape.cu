@@ -24,6 +24,7 @@ namespace drfe {
 static const int kMaxPlanes = 255;       // labels are uchar (CAPE.cpp:286)
 static const int kHistBins = 20;
 
+struct CellSums;
 struct CapeDev {
   int H, W, cw, ch, ncx, ncy, ncells, npc, B;
   float min_cos, max_merge_dist;
@@ -42,6 +43,7 @@ struct CapeDev {
   int* nplanes;                 // [B]
   uint8_t* seg;                 // [B][H*W]
   int* status;
+  struct CellSums* sums;        // [B][ncells] per-cell moment sums (k_cape_sums -> k_cape_fit)
   void* cs_spill;               // [B][ncells] CellS in global memory when the grid does not fit in smem
 };
 
@@ -129,73 +131,121 @@ __device__ __forceinline__ void expand_seg(drfe_plane& a, const drfe_plane& b) {
 }
 
 // ------------------------------------------------------------------ cells
-// 16 lanes per cell.  Lane l owns the declared accumulator l of each of the 9 sums:
+// k_cape_sums: 16 lanes per cell.  Lane l owns the declared accumulator l of each of the 9 sums:
 // elements l, l+16, l+32, ... in ascending order (Eigen's two-packet AVX redux, App. B.1),
-// then lanes l and l+8 are added, then the 8 -> 4 -> 2 -> 1 halving tree.
-__device__ __forceinline__ float tree16(float v, int n, int body, const float* tail_vals, unsigned mask, int lane16,
-                                        float extra8) {
-  // p8 = lane[l] + lane[l+8]
-  float p = v + __shfl_down_sync(mask, v, 8, 16);
-  if (n - body >= 8) p = p + extra8;                      // one more aligned packet (lanes 0..7)
+// then lanes l and l+8 are added, then the 8 -> 4 -> 2 -> 1 halving tree.  The depth values
+// of a chunk are loaded before any of them is used so the loads overlap; z is kept in shared
+// memory for the two depth-jump scans (PlaneSeg.cpp:36-76), which two lanes run side by side.
+// Output per cell: 9 float sums, the valid-point count and the planarity flags so far
+// (CellSums); k_cape_fit turns that into the PlaneSeg with one thread per cell.
+struct CellSums { float s[9]; int cnt; int planar; int pad; };
+
+__device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, float extra8) {
+  float p = v + __shfl_down_sync(mask, v, 8, 16);        // lane[l] + lane[l+8]
+  if (has_extra) p = p + extra8;                           // one more aligned packet (lanes 0..7)
   p = p + __shfl_down_sync(mask, p, 4, 16);
   p = p + __shfl_down_sync(mask, p, 2, 16);
   p = p + __shfl_down_sync(mask, p, 1, 16);
-  (void)tail_vals; (void)lane16;
   return p;  // valid in lane 0 of the group
 }
 
-__global__ void __launch_bounds__(128) k_cape_cells(const CapeDev* __restrict__ Pp, int nframes) {
+static const int kSumsThreads = 128, kSumsChunk = 8;
+template <bool FROM_DEPTH>
+__global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __restrict__ Pp, int nframes) {
+  extern __shared__ __align__(16) float s_zall[];           // [8 groups][npc]
   const CapeDev& P = *Pp;
-  const int gid = (blockIdx.x * 128 + threadIdx.x) >> 4;   // global cell index over the batch
+  const int gid = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;   // global cell index over the batch
   const int l = threadIdx.x & 15;
   const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
   if (gid >= nframes * P.ncells) return;                    // whole 16-lane groups exit together
   const int f = gid / P.ncells, cell = gid - f * P.ncells;
   const int npc = P.npc, cw = P.cw;
+  float* s_z = s_zall + (threadIdx.x >> 4) * npc;
   const long long N = (long long)P.H * P.W;
-  float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
-  float* CY = CX + N;
-  float* CZ = CY + N;
+  float* __restrict__ CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+  float* __restrict__ CY = CX + N;
+  float* __restrict__ CZ = CY + N;
   const int body = (npc / 16) * 16;
-  const int full8 = (npc - body >= 8) ? body + 8 : body;
+  const bool has_extra = npc - body >= 8;
+  const int full8 = has_extra ? body + 8 : body;
   float ax = 0, ay = 0, az = 0, axx = 0, ayy = 0, azz = 0, axy = 0, axz = 0, ayz = 0;
   float ex = 0, ey = 0, ez = 0, exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;  // extra packet
   int cnt = 0;
-  const float* dsrc = nullptr;
   const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
-  if (P.depth) dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;
-  for (int i = l; i < npc; i += 16) {
-    float x, y, z;
-    if (dsrc) {
-      const int lr = i / cw, lc = i - lr * cw;
-      const float dz = __ldg(dsrc + (long long)lr * P.depth_rs + lc);
-      const double zd = (double)dz;
-      const double xd = ((double)(cc * cw + lc) - (double)P.cx) * zd / (double)P.fx;
-      const double yd = ((double)(cr * P.ch + lr) - (double)P.cy) * zd / (double)P.fy;
-      x = (float)xd; y = (float)yd; z = (float)zd;
-      CX[i] = x; CY[i] = y; CZ[i] = z;
-    } else {
-      x = CX[i]; y = CY[i]; z = CZ[i];
+  const float* __restrict__ dsrc = nullptr;
+  if (FROM_DEPTH) dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;
+  const double fx = (double)P.fx, fy = (double)P.fy, pcx = (double)P.cx, pcy = (double)P.cy;
+  int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
+  for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
+    float vz[kSumsChunk], vx[kSumsChunk], vy[kSumsChunk];
+    {
+      int r2 = lr, c2 = lc;
+#pragma unroll
+      for (int u = 0; u < kSumsChunk; ++u) {
+        const int i = i0 + 16 * u;
+        vz[u] = 0.f; vx[u] = 0.f; vy[u] = 0.f;
+        if (i < npc) {
+          if (FROM_DEPTH) vz[u] = __ldg(dsrc + (long long)r2 * P.depth_rs + c2);
+          else { vx[u] = CX[i]; vy[u] = CY[i]; vz[u] = CZ[i]; }
+        }
+        c2 += 16;
+        while (c2 >= cw) { c2 -= cw; ++r2; }
+      }
     }
-    cnt += (z > 0.f);
-    if (i < body) {
-      if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
-      else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
-             axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
-    } else if (i < full8) {
-      ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
+#pragma unroll
+    for (int u = 0; u < kSumsChunk; ++u) {
+      const int i = i0 + 16 * u;
+      if (i < npc) {
+        float x, y, z;
+        if (FROM_DEPTH) {
+          // PlaneExtractor.cpp:117-127: all in double, stored as float
+          const double zd = (double)vz[u];
+          const double xd = ((double)(cc * cw + lc) - pcx) * zd / fx;
+          const double yd = ((double)(cr * P.ch + lr) - pcy) * zd / fy;
+          x = (float)xd; y = (float)yd; z = (float)zd;
+          CX[i] = x; CY[i] = y; CZ[i] = z;
+        } else {
+          x = vx[u]; y = vy[u]; z = vz[u];
+        }
+        s_z[i] = z;
+        cnt += (z > 0.f);
+        if (i < body) {
+          if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
+          else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
+                 axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
+        } else if (i < full8) {
+          ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
+        }
+      }
+      lc += 16;
+      while (lc >= cw) { lc -= cw; ++lr; }
     }
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) cnt += __shfl_down_sync(mask, cnt, o, 16);
-  // the extra packet sits in lanes body%16.. of the iteration; bring values to lanes 0..7
-  // (body is a multiple of 16, so element body+j is handled by lane j: already in place)
-  float sx = tree16(ax, npc, body, nullptr, mask, l, ex), sy = tree16(ay, npc, body, nullptr, mask, l, ey),
-        sz = tree16(az, npc, body, nullptr, mask, l, ez), sxx = tree16(axx, npc, body, nullptr, mask, l, exx),
-        syy = tree16(ayy, npc, body, nullptr, mask, l, eyy), szz = tree16(azz, npc, body, nullptr, mask, l, ezz),
-        sxy = tree16(axy, npc, body, nullptr, mask, l, exy), sxz = tree16(axz, npc, body, nullptr, mask, l, exz),
-        syz = tree16(ayz, npc, body, nullptr, mask, l, eyz);
-  __syncwarp(mask);
+  // (body is a multiple of 16, so element body+j was handled by lane j: the extra packet is in place)
+  float sx = tree16(ax, has_extra, mask, ex), sy = tree16(ay, has_extra, mask, ey), sz = tree16(az, has_extra, mask, ez),
+        sxx = tree16(axx, has_extra, mask, exx), syy = tree16(ayy, has_extra, mask, eyy),
+        szz = tree16(azz, has_extra, mask, ezz), sxy = tree16(axy, has_extra, mask, exy),
+        sxz = tree16(axz, has_extra, mask, exz), syz = tree16(ayz, has_extra, mask, eyz);
+  __syncwarp(mask);                                         // s_z and the cloud are complete
+  // depth-jump scans through the middle row (lane 0) and the middle column (lane 1)
+  int jumps = 0;
+  if (l < 2) {
+    const int chh = npc / cw;
+    int i, j, step;
+    float z_last;
+    if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_last = fmaxf(s_z[i], s_z[i + 1]); }
+    else { i = cw / 2; j = npc - i; step = cw; z_last = fmaxf(s_z[i], s_z[i + cw]); }
+    i += step;
+    while (i < j) {
+      const float z = s_z[i];
+      if (z > 0 && (double)fabsf(z - z_last) < 100.0) z_last = z;
+      else if (z > 0) ++jumps;
+      i += step;
+    }
+  }
+  const int jumps_v = __shfl_down_sync(mask, jumps, 1, 16);
   if (l != 0) return;
   // scalar tail (Eigen's unaligned end), sequential
   for (int i = full8; i < npc; ++i) {
@@ -203,47 +253,48 @@ __global__ void __launch_bounds__(128) k_cape_cells(const CapeDev* __restrict__ 
     sx = sx + x; sy = sy + y; sz = sz + z; sxx = sxx + x * x; syy = syy + y * y; szz = szz + z * z;
     sxy = sxy + x * y; sxz = sxz + x * z; syz = syz + y * z;
   }
+  CellSums o;
+  o.s[0] = sx; o.s[1] = sy; o.s[2] = sz; o.s[3] = sxx; o.s[4] = syy; o.s[5] = szz; o.s[6] = sxy; o.s[7] = sxz; o.s[8] = syz;
+  o.cnt = cnt;
+  o.planar = (cnt >= npc / 2 && jumps <= 1 && jumps_v <= 1) ? 1 : 0;
+  o.pad = 0;
+  float4* dst = reinterpret_cast<float4*>(P.sums + (long long)gid);
+  const float4* srcv = reinterpret_cast<const float4*>(&o);
+  dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2];
+}
+
+// k_cape_fit: one thread per cell — the rest of PlaneSeg::PlaneSeg (PlaneSeg.cpp:78-94): sums
+// widened to double, fitPlane, the depth-dependent MSE test, and the cell's merge tolerance
+// (CAPE.cpp:69-73).
+__global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp, int nframes) {
+  const CapeDev& P = *Pp;
+  const int gid = blockIdx.x * 128 + threadIdx.x;
+  if (gid >= nframes * P.ncells) return;
+  const int f = gid / P.ncells, cell = gid - f * P.ncells;
+  const int npc = P.npc;
+  CellSums in;
+  {
+    const float4* srcv = reinterpret_cast<const float4*>(P.sums + (long long)gid);
+    float4* d = reinterpret_cast<float4*>(&in);
+    d[0] = srcv[0]; d[1] = srcv[1]; d[2] = srcv[2];
+  }
   drfe_plane s;
   memset(&s, 0, sizeof(s));                        // zero-filled PlaneSeg storage (App. B.2)
   s.min_nr_pts = npc / 2;
-  s.nr_pts = cnt;
-  s.planar = 1;
+  s.nr_pts = in.cnt;
+  s.planar = in.planar;
   float tol = 0.f;
-  const int chh = npc / cw;
-  if (s.nr_pts < s.min_nr_pts) s.planar = 0;
-  if (s.planar) {  // horizontal then vertical depth-jump scan through the middle (PlaneSeg.cpp:36-76)
-    int jumps = 0;
-    int i = cw * (chh / 2), j = i + cw;
-    float z_last = fmaxf(CZ[i], CZ[i + 1]);
-    ++i;
-    while (i < j) {
-      const float z = CZ[i];
-      if (z > 0 && (double)fabsf(z - z_last) < 100.0) z_last = z;
-      else if (z > 0) ++jumps;
-      ++i;
-    }
-    if (jumps > 1) s.planar = 0;
-  }
   if (s.planar) {
-    int jumps = 0;
-    int i = cw / 2, j = npc - i;
-    float z_last = fmaxf(CZ[i], CZ[i + cw]);
-    i += cw;
-    while (i < j) {
-      const float z = CZ[i];
-      if (z > 0 && (double)fabsf(z - z_last) < 100.0) z_last = z;
-      else if (z > 0) ++jumps;
-      i += cw;
-    }
-    if (jumps > 1) s.planar = 0;
-  }
-  if (s.planar) {
-    s.x_acc = sx; s.y_acc = sy; s.z_acc = sz; s.xx_acc = sxx; s.yy_acc = syy; s.zz_acc = szz;
-    s.xy_acc = sxy; s.xz_acc = sxz; s.yz_acc = syz;
+    s.x_acc = in.s[0]; s.y_acc = in.s[1]; s.z_acc = in.s[2]; s.xx_acc = in.s[3]; s.yy_acc = in.s[4]; s.zz_acc = in.s[5];
+    s.xy_acc = in.s[6]; s.xz_acc = in.s[7]; s.yz_acc = in.s[8];
     fit_plane(s);
     const double lim = 0.000001425 * s.mean[2] * s.mean[2] + 10.0;   // Params.h:6-7
     if ((double)s.MSE > lim * lim) s.planar = 0;
     if (s.planar) {  // cell_distance_tols (CAPE.cpp:69-73)
+      const long long N = (long long)P.H * P.W;
+      const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+      const float* CY = CX + N;
+      const float* CZ = CY + N;
       const float dx = CX[npc - 1] - CX[0], dy = CY[npc - 1] - CY[0], dz = CZ[npc - 1] - CZ[0];
       const float diam = sqrtf(dx * dx + dy * dy + dz * dz);
       const float sin_merge = (float)sqrt(1.0 - (double)P.min_cos * (double)P.min_cos);
@@ -251,8 +302,8 @@ __global__ void __launch_bounds__(128) k_cape_cells(const CapeDev* __restrict__ 
       tol = t * t;
     }
   }
-  P.cells[(long long)f * P.ncells + cell] = s;
-  P.tols[(long long)f * P.ncells + cell] = tol;
+  P.cells[gid] = s;
+  P.tols[gid] = tol;
 }
 
 // ------------------------------------------------------------------ grid stage
@@ -677,6 +728,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.cloud, 3 * N * B);
   rc |= cape_alloc(h, &D.cells, nc * B);
   rc |= cape_alloc(h, &D.tols, nc * B);
+  rc |= cape_alloc(h, &D.sums, nc * B);
   rc |= cape_alloc(h, &D.plane_map, nc * B);
   rc |= cape_alloc(h, &D.eroded_map, nc * B);
   rc |= cape_alloc(h, &D.border_bits, nc * B * 8);
@@ -704,6 +756,14 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   if (h->grid_smem > 200 * 1024) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
   if (cudaFuncSetAttribute(k_cape_grid<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
     set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
+  }
+  {
+    const size_t sums_smem = (size_t)(kSumsThreads / 16) * D.npc * sizeof(float);
+    if (sums_smem > 200 * 1024) { set_error("drfe_cape_create: cells of %d points are too large", D.npc); return fail(DRFE_ERR_ARG); }
+    if (cudaFuncSetAttribute(k_cape_sums<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_cape_sums<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
+    }
   }
   if (h->timer.create()) return fail(DRFE_ERR_CUDA);
   *out = h;
@@ -739,8 +799,12 @@ static int cape_run(drfe_cape* h, int nframes) {
   cudaStream_t st = h->stream;
   DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
   const int ncell_total = nframes * h->hd.ncells;
-  DRFE_LAUNCH(k_cape_cells, (ncell_total * 16 + 127) / 128, 128, 0, st, h->dd, nframes);
+  const size_t sums_smem = (size_t)(kSumsThreads / 16) * h->hd.npc * sizeof(float);
+  if (h->hd.depth) DRFE_LAUNCH(k_cape_sums<true>, (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads, kSumsThreads, sums_smem, st, h->dd, nframes);
+  else DRFE_LAUNCH(k_cape_sums<false>, (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads, kSumsThreads, sums_smem, st, h->dd, nframes);
   h->timer.mark("cells", st);
+  DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, nframes);
+  h->timer.mark("fit", st);
   DRFE_LAUNCH(k_cape_grid<256>, nframes, 256, h->grid_smem, st, h->dd);
   h->timer.mark("grid", st);
   if (h->margin) {

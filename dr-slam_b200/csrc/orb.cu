@@ -9,8 +9,9 @@
 //   k_pyr_level0   gray -> level 0 + 19 px reflect-101 frame   (ORBextractor.cc:1125-1129)
 //   k_pyr_resize   level l-1 -> level l, OpenCV fixed-point INTER_LINEAR + frame; one
 //                  launch per level because level l reads level l-1   (:1118-1123)
-//   k_fast_cells   one CTA per 30 px grid cell: FAST-9/16 score for every pixel with packed
-//                  s16x2 min/max, per-cell NMS, iniThFAST -> minThFAST fallback (:789-829)
+//   k_fast_strips  one CTA per row of 30 px grid cells: rows staged in smem by TMA bulk copies,
+//                  FAST-9/16 score for every pixel with packed u16x2 min/max (VIMNMX3), per-cell
+//                  NMS, iniThFAST -> minThFAST fallback                      (:789-829)
 //   k_quadtree     one CTA per (frame, level): DistributeOctTree replayed with prefix scans,
 //                  order-free (node membership is geometric; ties resolved by the
 //                  reference's candidate order encoded in a key)           (:539-763)
@@ -30,7 +31,7 @@ static const int kEdge = 19;     // EDGE_THRESHOLD (ORBextractor.cc:74)
 static const int kXOff = 32;     // byte offset of ROI column 0 inside a bordered row
 static const int kHalfPatch = 15;
 
-__constant__ int8_t c_pattern[1024];
+__constant__ __align__(16) int8_t c_pattern[1024];
 __constant__ int c_umax[16];
 static const int8_t h_pattern[1024] = {
 #include "../../include/drfe_orb_pattern.inc"
@@ -43,6 +44,9 @@ struct LevelDev {
   long long blur_off, blur_fstride;
   int regW, regH, nCols, nRows, wCell, hCell;
   int nfeat, nIni;
+  int blur_nq;                      // 4-pixel columns of the blur kernel, ceil(w/4)
+  uint32_t blur_magic;              // ceil(2^32 / blur_nq)
+  uint32_t quads_magic;             // ceil(2^32 / quads), quads = ceil((w-38)/4): task -> row by __umulhi
   float hX;
   int root_x[5];                    // root boundaries int(hX*i), i = 0..nIni (nIni <= 4)
   int cand_cap;
@@ -53,8 +57,8 @@ struct LevelDev {
   long long xtab_off, ytab_off;     // element offsets into the resize tables (level >= 1)
 };
 
-struct CellDev { short level, x0, y0, ww, wh, pad; };
-struct TileDev { short level, tx, ty, pad; };
+struct StripDev { short level, y0, nrows, pad; };   // FAST strip: interior rows [y0, y0+nrows) of one cell row
+static const int kMaxStripCells = 160;
 
 struct OrbDev {
   int nlevels, B, ini_th, min_th;
@@ -62,8 +66,7 @@ struct OrbDev {
   uint8_t* pyr;
   uint8_t* blur;
   const uint2* rtab;                // resize tables {idx0 | idx1<<16, c0 | c1<<16}
-  const CellDev* cells;
-  const TileDev* tiles;
+  const StripDev* strips;
   uint32_t* cand;                   // [B][cand_total] packed x | y<<12 | q<<24 (region coords)
   long long cand_fstride;
   int* cand_cnt;                    // [B][nlevels]
@@ -76,7 +79,8 @@ struct OrbDev {
   int* out_cnt;                     // [B]
   int kp_cap;
   int* status;                      // bit 0: candidate overflow, bit 1: node overflow
-  int fast_tp, fast_rows, fast_list_cap;
+  int fast_tp, fast_rows;
+  int blur_blk_off[DRFE_MAX_LEVELS + 1];   // first k_blur block of each level
 };
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -144,144 +148,228 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ P
 }
 
 // ------------------------------------------------------------------ K2 FAST
-// Threshold-free FAST-9/16 score for two pixels packed as s16x2 (values biased by +256):
-// Q = max over the 16 nine-pixel arcs of max(min(d), -max(d)), d = v - ring; the OpenCV
-// response is Q - 1 and "corner at threshold t" <=> Q - 1 >= t.
-__device__ __forceinline__ void fast_q_pair(const uint32_t (&d)[16], int& q_lo, int& q_hi) {
+// Threshold-free FAST-9/16 score.  With ring values r[0..15] around centre v,
+//   A = min over the 16 nine-pixel arcs of max(r over the arc)
+//   B = max over the 16 nine-pixel arcs of min(r over the arc)
+//   q = max(v - A, B - v) - 1          (= OpenCV's cornerScore; corner at threshold t <=> q >= t)
+// Two pixels are processed per 32-bit register as u16x2 (VIMNMX3.U16x2 on sm_100a).
+// Returns (q + 257) per half, i.e. always positive.
+__device__ __forceinline__ uint32_t fast_q_pair(const uint32_t (&r)[16], uint32_t v) {
   uint32_t mn3[16], mx3[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    mn3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    mx3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
   }
-  uint32_t best_mn = 0x00000000u, best_mx = 0x7FFF7FFFu;  // max of mins, min of maxes
+  uint32_t B = 0x00000000u, A = 0x7FFF7FFFu;
 #pragma unroll
   for (int k = 0; k < 16; k += 2) {
-    const uint32_t a = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
-    const uint32_t b = __vimin3_s16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
-    best_mn = __vimax3_s16x2(best_mn, a, b);
-    const uint32_t c = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
-    const uint32_t e = __vimax3_s16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
-    best_mx = __vimin3_s16x2(best_mx, c, e);
+    const uint32_t a = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+    const uint32_t b = __vimin3_u16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
+    B = __vimax3_u16x2(B, a, b);
+    const uint32_t c = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+    const uint32_t e = __vimax3_u16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
+    A = __vimin3_u16x2(A, c, e);
   }
-  // un-bias: d' = d + 256
-  const int mn_lo = (int)(best_mn & 0xFFFF) - 256, mn_hi = (int)(best_mn >> 16) - 256;
-  const int mx_lo = 256 - (int)(best_mx & 0xFFFF), mx_hi = 256 - (int)(best_mx >> 16);
-  q_lo = max(mn_lo, mx_lo) - 1;
-  q_hi = max(mn_hi, mx_hi) - 1;
+  // halves never borrow: v + 256 - A >= 1 and B + 256 - v >= 1
+  const uint32_t t1 = v + 0x01000100u - A, t2 = B + 0x01000100u - v;
+  return __vmaxu2(t1, t2);
+}
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ring offsets (dx,dy), k = 0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
 // (-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)  
+//
+// One CTA per (cell row of one level, frame).  The cells' interior bands tile the region
+// [19, w-19) x [19, h-19) exactly (App. A.3b), so a strip = the interior rows of one cell row
+// over the full width; pixel -> cell is (x-19)/wCell.  Stages:
+//   1. rows Y0-3 .. Y1+2 of the level image -> smem by TMA bulk copies (one per row)
+//   2. score e = max(q + 1 - minTh, 0) for every interior pixel, 4 pixels per task
+//   3. per-cell NMS (neighbours in another cell count as 0) -> survivor list in smem, and a
+//      per-cell count of survivors with q >= iniTh
+//   4. emit survivors with q >= iniTh, or all of them for cells where FAST(iniTh) found
+//      nothing (the minThFAST fallback, ORBextractor.cc:812-816), in arbitrary order (the
+//      quadtree orders by a key)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_fast_cells(const OrbDev* __restrict__ Pp) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
-  const CellDev cell = P.cells[blockIdx.x];
+  const StripDev strip = P.strips[blockIdx.x];
   const int f = blockIdx.y;
-  const LevelDev& L = P.lv[cell.level];
-  const int tp = P.fast_tp, ww = cell.ww, wh = cell.wh;
-  uint8_t* tile = smem;                                  // wh x tp pixels (+1 guard row)
-  uint8_t* score = smem + (size_t)tp * (P.fast_rows + 1);   // same shape
-  uint32_t* list = reinterpret_cast<uint32_t*>(score + (size_t)tp * (P.fast_rows + 1));
-  __shared__ int s_n, s_n_ini, s_base, s_emit;
+  const LevelDev& L = P.lv[strip.level];
+  const int TP = P.fast_tp;                  // smem row pitch (multiple of 16)
+  const int nrows = strip.nrows;             // interior rows of this strip
+  uint8_t* tile = smem;                      // (nrows + 6) x TP: level rows Y0-3.., ROI columns 0..
+  uint8_t* score = smem + (size_t)TP * (P.fast_rows + 6);   // (nrows + 2) x TP with zero guards
+  uint32_t* list = reinterpret_cast<uint32_t*>(tile);       // survivors (aliases the tile after stage 2)
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_n, s_ini[kMaxStripCells];
+  uint4* s_mask = reinterpret_cast<uint4*>(score + (size_t)TP * (P.fast_rows + 2));   // [quads]
   const int tid = threadIdx.x;
-  if (tid == 0) { s_n = 0; s_n_ini = 0; s_emit = 0; }
-
-  const uint8_t* src = roi_ptr(P, L, f) + (long long)cell.y0 * L.pitch + cell.x0;
-  const int tw4 = tp >> 2;
-  // window -> smem; columns >= ww and the guard row are zero
-  for (int idx = tid; idx < (wh + 1) * tp; idx += THREADS) {
-    const int r = idx / tp, c = idx - r * tp;
-    tile[idx] = (r < wh && c < ww) ? __ldg(src + (long long)r * L.pitch + c) : 0;
-  }
-  for (int idx = tid; idx < (wh + 1) * tw4; idx += THREADS) reinterpret_cast<uint32_t*>(score)[idx] = 0;
+  if (tid == 0) { s_n = 0; mbar_init(&s_bar, 1); }
+  for (int i = tid; i < kMaxStripCells; i += THREADS) s_ini[i] = 0;
   __syncthreads();
-
-  const int iw = ww - 6, ih = wh - 6;
-  const int groups = (iw + 3) >> 2;
+  // ---- 1. TMA: one bulk copy per image row
+  {
+    const uint32_t row_bytes = (uint32_t)((L.w + 15) & ~15);
+    const uint8_t* src = roi_ptr(P, L, f) + (long long)(strip.y0 - 3) * L.pitch;
+    if (tid == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nrows + 6));
+    for (int r = tid; r < nrows + 6; r += THREADS) bulk_g2s(tile + (size_t)r * TP, src + (long long)r * L.pitch, row_bytes, &s_bar);
+  }
+  // ---- 2. scores.  Score map: (nrows + 2) x TP4 words, one word = 4 pixels; word column 0 and
+  // quads + 1 and rows 0 and nrows + 1 are zero guards (neighbours outside the strip belong to
+  // other cells and count as 0).
+  const int iw = L.w - 2 * kEdge;            // interior width
+  const int quads = (iw + 3) >> 2;
+  const int TP4 = TP >> 2;
+  const int wCell = L.wCell;
   const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
-  for (int task = tid; task < ih * groups; task += THREADS) {
-    const int ry = task / groups, g = task - ry * groups;
-    // rows y-3..y+3 (window rows ry..ry+6), bytes 4g..4g+11
+  uint32_t* score32 = reinterpret_cast<uint32_t*>(score);
+  for (int i = tid; i < TP4; i += THREADS) { score32[i] = 0; score32[(nrows + 1) * TP4 + i] = 0; }
+  for (int i = tid; i < nrows; i += THREADS) { score32[(i + 1) * TP4] = 0; score32[(i + 1) * TP4 + quads + 1] = 0; }
+  // per-quad cell-boundary masks as u16x2 {left even, left odd, right even, right odd}: a pixel
+  // in the first (last) column of its cell has no left (right) neighbours
+  for (int g = tid; g < quads; g += THREADS) {
+    uint32_t ml = 0, mr = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = 4 * g + k;
+      if (x % wCell != 0) ml |= 0xFFu << (8 * k);
+      if ((x + 1) % wCell != 0) mr |= 0xFFu << (8 * k);
+    }
+    s_mask[g] = make_uint4(__byte_perm(ml, 0, 0x4240), __byte_perm(ml, 0, 0x4341), __byte_perm(mr, 0, 0x4240),
+                           __byte_perm(mr, 0, 0x4341));
+  }
+  const uint32_t kmin = (uint32_t)(256 + P.min_th) * 0x00010001u;
+  const int ntask = nrows * quads;
+  mbar_wait(&s_bar, 0);                      // the strip's rows have landed
+  for (int task = tid; task < ntask; task += THREADS) {
+    const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+    const int g = task - ry * quads;
+    // window rows ry..ry+6 (level rows y-3..y+3), bytes 16+4g .. 16+4g+11 (level columns x-3..x+8)
     uint32_t w[7][3];
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
-      const uint32_t* p = tile32 + (ry + r) * tw4 + g;
+      const uint32_t* p = tile32 + (ry + r) * TP4 + 4 + g;
       w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2];
     }
     // 4 adjacent bytes starting at byte offset o (0..8) of row r
     auto quad = [&](int r, int o) -> uint32_t {
       return (o & 3) == 0 ? w[r][o >> 2] : __funnelshift_r(w[r][o >> 2], w[r][(o >> 2) + 1], 8 * (o & 3));
     };
-    const uint32_t vq = quad(3, 3);                         // centres of the 4 pixels
-    const uint32_t v_even = (vq & 0x00FF00FFu) + 0x01000100u;        // pixels 0,2 (+256 bias)
-    const uint32_t v_odd = ((vq >> 8) & 0x00FF00FFu) + 0x01000100u;  // pixels 1,3
-    uint32_t de[16], dod[16];
+    const uint32_t vq = quad(3, 3);                          // centres of the 4 pixels
+    const uint32_t v_even = __byte_perm(vq, 0, 0x4240);      // pixels 0,2 as u16x2
+    const uint32_t v_odd = __byte_perm(vq, 0, 0x4341);       // pixels 1,3
+    uint32_t re[16], ro[16];
 #define DRFE_RING(k, dx, dy)                                   \
   {                                                            \
     const uint32_t rq = quad(3 + (dy), 3 + (dx));              \
-    de[k] = v_even - (rq & 0x00FF00FFu);                       \
-    dod[k] = v_odd - ((rq >> 8) & 0x00FF00FFu);                \
+    re[k] = __byte_perm(rq, 0, 0x4240);                        \
+    ro[k] = __byte_perm(rq, 0, 0x4341);                        \
   }
     DRFE_RING(0, 0, 3) DRFE_RING(1, 1, 3) DRFE_RING(2, 2, 2) DRFE_RING(3, 3, 1)
     DRFE_RING(4, 3, 0) DRFE_RING(5, 3, -1) DRFE_RING(6, 2, -2) DRFE_RING(7, 1, -3)
     DRFE_RING(8, 0, -3) DRFE_RING(9, -1, -3) DRFE_RING(10, -2, -2) DRFE_RING(11, -3, -1)
     DRFE_RING(12, -3, 0) DRFE_RING(13, -3, 1) DRFE_RING(14, -2, 2) DRFE_RING(15, -1, 3)
 #undef DRFE_RING
-    int q0, q1, q2, q3;
-    fast_q_pair(de, q0, q2);
-    fast_q_pair(dod, q1, q3);
-    const int x = 3 + 4 * g;  // window column of pixel 0
-    const int minq = P.min_th;
-    uint32_t packed = 0;
-    if (q0 >= minq) packed |= (uint32_t)q0;
-    if (q1 >= minq && x + 1 < ww - 3) packed |= (uint32_t)q1 << 8;
-    if (q2 >= minq && x + 2 < ww - 3) packed |= (uint32_t)q2 << 16;
-    if (q3 >= minq && x + 3 < ww - 3) packed |= (uint32_t)q3 << 24;
-    if (packed) {
-      // score tile is byte addressed at (ry+3, x): x = 4g+3 is not word aligned
-      uint8_t* sp = score + (ry + 3) * tp + x;
-      if (packed & 0xFF) sp[0] = (uint8_t)packed;
-      if (packed & 0xFF00) sp[1] = (uint8_t)(packed >> 8);
-      if (packed & 0xFF0000) sp[2] = (uint8_t)(packed >> 16);
-      if (packed >> 24) sp[3] = (uint8_t)(packed >> 24);
-    }
+    // e = max(q + 257, 256 + minTh) - (256 + minTh) = max(q + 1 - minTh, 0) per half (< 256)
+    const uint32_t ee = __vmaxu2(fast_q_pair(re, v_even), kmin) - kmin;
+    const uint32_t eo = __vmaxu2(fast_q_pair(ro, v_odd), kmin) - kmin;
+    uint32_t packed = ee | (eo << 8);                        // bytes: pixel 0,1,2,3
+    const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
+    if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
+    score32[(ry + 1) * TP4 + g + 1] = packed;
   }
   __syncthreads();
-  // per-cell non-maximum suppression: strict maximum over the 8 neighbours (zeros outside
-  // the cell's interior band, so no suppression across cell edges)
-  for (int idx = tid; idx < ih * iw; idx += THREADS) {
-    const int ry = idx / iw, rx = idx - ry * iw;
-    const uint8_t* sp = score + (ry + 3) * tp + rx + 3;
-    const int s = sp[0];
-    if (s == 0) continue;
-    if (s > sp[-1] && s > sp[1] && s > sp[-tp - 1] && s > sp[-tp] && s > sp[-tp + 1] && s > sp[tp - 1] &&
-        s > sp[tp] && s > sp[tp + 1]) {
+  // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free
+  // on u16x2 pairs (the score map is dense at minThFAST on textured frames)
+  const int e_ini = P.ini_th + 1 - P.min_th;
+  const int list_cap = (TP * (P.fast_rows + 6)) >> 2;
+  for (int task = tid; task < ntask; task += THREADS) {
+    const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+    const int g = task - ry * quads;
+    const uint32_t* sp = score32 + (ry + 1) * TP4 + g + 1;
+    const uint32_t c0 = sp[0];
+    if (c0 == 0) continue;
+    const uint32_t u0 = sp[-TP4 - 1], u1 = sp[-TP4], u2 = sp[-TP4 + 1];
+    const uint32_t m0 = sp[-1], m2 = sp[1];
+    const uint32_t d0 = sp[TP4 - 1], d1 = sp[TP4], d2 = sp[TP4 + 1];
+    const uint4 mk = s_mask[g];
+    // byte k of L* = pixel k-1, of R* = pixel k+1
+    const uint32_t Lu = __funnelshift_r(u0, u1, 24), Ru = __funnelshift_r(u1, u2, 8);
+    const uint32_t Lm = __funnelshift_r(m0, c0, 24), Rm = __funnelshift_r(c0, m2, 8);
+    const uint32_t Ld = __funnelshift_r(d0, d1, 24), Rd = __funnelshift_r(d1, d2, 8);
+    uint32_t t[2];
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      const uint32_t sel = par ? 0x4341u : 0x4240u;
+      const uint32_t lmax = __vimax3_u16x2(__byte_perm(Lu, 0, sel), __byte_perm(Lm, 0, sel), __byte_perm(Ld, 0, sel)) & (par ? mk.y : mk.x);
+      const uint32_t rmax = __vimax3_u16x2(__byte_perm(Ru, 0, sel), __byte_perm(Rm, 0, sel), __byte_perm(Rd, 0, sel)) & (par ? mk.w : mk.z);
+      const uint32_t nb = __vimax3_u16x2(lmax, rmax, __vmaxu2(__byte_perm(u1, 0, sel), __byte_perm(d1, 0, sel)));
+      const uint32_t c = __byte_perm(c0, 0, sel);
+      t[par] = c - __vminu2(c, nb);                          // per half: > 0 <=> strict maximum
+    }
+    if ((t[0] | t[1]) == 0) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (((t[k & 1] >> (16 * (k >> 1))) & 0xFFFF) == 0) continue;
+      const int e = (c0 >> (8 * k)) & 0xFF;
+      const int x = 4 * g + k;
       const int slot = atomicAdd(&s_n, 1);
-      if (s >= P.ini_th) atomicAdd(&s_n_ini, 1);
-      if (slot < P.fast_list_cap) list[slot] = (uint32_t)(rx + 3) | ((uint32_t)(ry + 3) << 12) | ((uint32_t)s << 24);
+      if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | ((uint32_t)e << 24);
+      else atomicOr(P.status, 1);
+      if (e >= e_ini) atomicAdd(&s_ini[x / wCell], 1);
     }
   }
   __syncthreads();
-  const int n = min(s_n, P.fast_list_cap);
-  const bool use_ini = s_n_ini > 0;        // FAST(iniThFAST) found something -> no fallback
-  const int total = use_ini ? s_n_ini : n;
-  int* cnt = P.cand_cnt + f * P.nlevels + cell.level;
-  if (tid == 0 && total > 0) s_base = atomicAdd(cnt, total);
-  __syncthreads();
-  if (total == 0) return;
+  // ---- 4. emit (region coordinates: origin (16,16) => interior x + 3)
+  const int n = min(s_n, list_cap);
+  int* cnt = P.cand_cnt + f * P.nlevels + strip.level;
   uint32_t* out = P.cand + (long long)f * P.cand_fstride + L.cand_off;
-  const int ox = cell.x0 - (kEdge - 3), oy = cell.y0 - (kEdge - 3);  // window origin in region coords
-  for (int i = tid; i < n; i += THREADS) {
-    const uint32_t e = list[i];
-    const int q = e >> 24;
-    if (use_ini && q < P.ini_th) continue;
-    const int pos = s_base + atomicAdd(&s_emit, 1);
-    if (pos < L.cand_cap)
-      out[pos] = (uint32_t)((e & 0xFFF) + ox) | ((uint32_t)(((e >> 12) & 0xFFF) + oy) << 12) | ((uint32_t)q << 24);
-    else
-      atomicOr(P.status, 1);
+  const int oy = strip.y0 - kEdge + 3;
+  const int lane = tid & 31;
+  for (int i0 = tid - lane; i0 < n; i0 += THREADS) {
+    const int i = i0 + lane;
+    uint32_t ent = 0;
+    bool keep = false;
+    if (i < n) {
+      ent = list[i];
+      const int e = ent >> 24;
+      keep = e >= e_ini || s_ini[(int)(ent & 0xFFF) / wCell] == 0;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (bal == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cnt, __popc(bal));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (keep) {
+      const int pos = base + __popc(bal & ((1u << lane) - 1));
+      const uint32_t q = (ent >> 24) + P.min_th - 1;
+      if (pos < L.cand_cap)
+        out[pos] = ((ent & 0xFFF) + 3) | ((((ent >> 12) & 0xFFF) + oy) << 12) | (q << 24);
+      else
+        atomicOr(P.status, 1);
+    }
   }
 }
 
@@ -327,7 +415,7 @@ __device__ __forceinline__ void child_mid(const QBox& b, int& mx, int& my) {
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__ Pp) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const int level = blockIdx.x, f = blockIdx.y;
   const LevelDev& L = P.lv[level];
@@ -542,38 +630,53 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
 // 7x7 sigma=2 separable, 8.8 fixed point {18,34,48,56,48,34,18}, rounding (v + 2^15) >> 16
 // (SURVEY App. A.5).  Reads the bordered level image, whose 19 px reflect-101 frame is
 // exactly the BORDER_REFLECT_101 extension GaussianBlur applies to the cloned level.
-static const int kBlurTW = 64, kBlurTH = 32;
+// One thread = a 4-pixel-wide column of kBlurRows output rows: per input row three aligned
+// words, the horizontal pass as two u8 dot products (IDP.4A) per pixel, the vertical pass over
+// a 7-row register window.  No shared memory: neighbouring threads hit the same L1 lines.
+static const int kBlurRows = 16;
+__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int (&h)[4]) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(row);
+  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);     // columns x-4 .. x+7
+  const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);    // taps -3..0
+  const uint32_t k1 = 48u | (34u << 8) | (18u << 16);                  // taps +1..+3
+  h[0] = __dp4a(__funnelshift_r(b, c, 8), k1, __dp4a(__funnelshift_r(a, b, 8), k0, 0u));
+  h[1] = __dp4a(__funnelshift_r(b, c, 16), k1, __dp4a(__funnelshift_r(a, b, 16), k0, 0u));
+  h[2] = __dp4a(__funnelshift_r(b, c, 24), k1, __dp4a(__funnelshift_r(a, b, 24), k0, 0u));
+  h[3] = __dp4a(c, k1, __dp4a(b, k0, 0u));
+}
+
 __global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp) {
-  __shared__ __align__(16) uint8_t s_in[(kBlurTH + 6) * (kBlurTW + 8)];
-  __shared__ __align__(16) uint16_t s_mid[(kBlurTH + 6) * kBlurTW];
   const OrbDev& P = *Pp;
-  const TileDev t = P.tiles[blockIdx.x];
+  int level = 0;
+  while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blur_blk_off[level + 1]) ++level;
+  const LevelDev& L = P.lv[level];
   const int f = blockIdx.y;
-  const LevelDev& L = P.lv[t.level];
-  if (P.lkp_cnt[f * P.nlevels + t.level] == 0) return;  // reference skips levels without keypoints (:1081)
-  const int x0 = t.tx * kBlurTW, y0 = t.ty * kBlurTH;
-  const uint8_t* src = roi_ptr(P, L, f) + (long long)(y0 - 3) * L.pitch + (x0 - 3);
-  const int tid = threadIdx.x;
-  const int IW = kBlurTW + 8;  // smem input pitch (only TW+6 columns are used)
-  const int cols = min(kBlurTW, L.w - x0), rows = min(kBlurTH, L.h - y0);
-  for (int idx = tid; idx < (rows + 6) * (cols + 6); idx += 256) {
-    const int r = idx / (cols + 6), c = idx - r * (cols + 6);
-    s_in[r * IW + c] = __ldg(src + (long long)r * L.pitch + c);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < (rows + 6) * cols; idx += 256) {
-    const int r = idx / cols, c = idx - r * cols;
-    const uint8_t* p = s_in + r * IW + c;
-    s_mid[r * kBlurTW + c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-  }
-  __syncthreads();
-  uint8_t* dst = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)y0 * L.bpitch + x0;
-  for (int idx = tid; idx < rows * cols; idx += 256) {
-    const int r = idx / cols, c = idx - r * cols;
-    const uint16_t* p = s_mid + r * kBlurTW + c;
-    const uint32_t v = 18u * (p[0] + p[6 * kBlurTW]) + 34u * (p[kBlurTW] + p[5 * kBlurTW]) +
-                       48u * (p[2 * kBlurTW] + p[4 * kBlurTW]) + 56u * p[3 * kBlurTW];
-    dst[(long long)r * L.bpitch + c] = (uint8_t)min((v + 32768u) >> 16, 255u);
+  if (P.lkp_cnt[f * P.nlevels + level] == 0) return;  // reference skips levels without keypoints (:1081)
+  // flattened (row group, 4-pixel column) index, columns fastest
+  const int t = ((int)blockIdx.x - P.blur_blk_off[level]) * 256 + threadIdx.x;
+  const int rg = (int)__umulhi((uint32_t)t, L.blur_magic);
+  const int q = t - rg * L.blur_nq;
+  const int y0 = rg * kBlurRows;
+  if (y0 >= L.h) return;
+  const int nrows = min(kBlurRows, L.h - y0);
+  const uint8_t* src = roi_ptr(P, L, f) + (long long)(y0 - 3) * L.pitch + 4 * q - 4;
+  uint8_t* dst = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)y0 * L.bpitch + 4 * q;
+  int h[7][4];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) blur_hrow(src + (long long)r * L.pitch, h[r]);
+#pragma unroll
+  for (int r = 0; r < kBlurRows; ++r) {
+    if (r < nrows) {
+      blur_hrow(src + (long long)(r + 6) * L.pitch, h[(r + 6) % 7]);
+      uint32_t o = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = 18 * (h[r % 7][j] + h[(r + 6) % 7][j]) + 34 * (h[(r + 1) % 7][j] + h[(r + 5) % 7][j]) +
+                      48 * (h[(r + 2) % 7][j] + h[(r + 4) % 7][j]) + 56 * h[(r + 3) % 7][j] + 32768;
+        o |= (uint32_t)(v >> 16) << (8 * j);                            // <= 255 by construction
+      }
+      *reinterpret_cast<uint32_t*>(dst + (long long)r * L.bpitch) = o;
+    }
   }
 }
 
@@ -601,37 +704,50 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 static const int kDescWarps = 8;
 __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp) {
+  // rBRIEF pattern in shared memory, one word (x0,y0,x1,y1 as int8) per test, laid out so
+  // that lane j's t-th test sits at word t*32 + j (conflict-free); constant memory would
+  // serialise the lane-divergent index
+  __shared__ uint32_t s_pat[256];
   const OrbDev& P = *Pp;
   const int level = blockIdx.y, f = blockIdx.z;
   const LevelDev& L = P.lv[level];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int* cnts = P.lkp_cnt + f * P.nlevels;
   const int nk = cnts[level];
-  const int i = blockIdx.x * kDescWarps + wid;
   if (blockIdx.x == 0 && level == 0 && threadIdx.x == 0) {
     int tot = 0;
     for (int l = 0; l < P.nlevels; ++l) tot += cnts[l];
     P.out_cnt[f] = min(tot, P.kp_cap);
   }
+  if ((int)blockIdx.x * kDescWarps >= nk) return;           // whole CTA idle
+  {
+    const int t = threadIdx.x;                                // test index = 8*byte + bit
+    s_pat[(t & 7) * 32 + (t >> 3)] = reinterpret_cast<const uint32_t*>(c_pattern)[t];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kDescWarps + wid;
   if (i >= nk) return;
   int base = 0;
   for (int l = 0; l < level; ++l) base += cnts[l];
   const uint32_t e = P.lkp[(long long)f * P.lkp_fstride + L.kp_off + i];
   const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;   // cvRound of integral coords
-  // ---- IC_Angle: moments over the radius-15 disc, lanes across u, loop over rows v
+  // ---- IC_Angle: moments over the radius-15 disc.  Lane l owns column u = l - 15; the disc is
+  // symmetric (|u| <= umax[|v|] <=> |v| <= umax[|u|]), so the lane's row range is a constant.
   const uint8_t* img = roi_ptr(P, L, f) + (long long)cy * L.pitch + cx;
   int m10 = 0, m01 = 0;
   const int u = lane - kHalfPatch;
-  if (lane < 31) {
-    const int au = abs(u);
-#pragma unroll 1
+  const int vmax = (lane < 31) ? c_umax[abs(u)] : -1;
+  {
+    int sum = 0;
+#pragma unroll
     for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-      if (au <= c_umax[abs(v)]) {
-        const int val = img[(long long)v * L.pitch + u];
-        m10 += u * val;
+      if (abs(v) <= vmax) {
+        const int val = img[v * L.pitch + u];
+        sum += val;
         m01 += v * val;
       }
     }
+    m10 = u * sum;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -650,17 +766,17 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   b = __shfl_sync(0xFFFFFFFFu, b, 0);
   // ---- rBRIEF: lane j computes descriptor byte j (8 tests)
   const uint8_t* bl = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)cy * L.bpitch + cx;
-  const int8_t* pat = c_pattern + lane * 32;
   int val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1];
-    const float x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+    const uint32_t pw = s_pat[j * 32 + lane];
+    const float x0 = (float)(int8_t)(pw & 0xFF), y0 = (float)(int8_t)((pw >> 8) & 0xFF);
+    const float x1 = (float)(int8_t)((pw >> 16) & 0xFF), y1 = (float)(int8_t)(pw >> 24);
     const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
     const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = bl[(long long)r0 * L.bpitch + c0], t1 = bl[(long long)r1 * L.bpitch + c1];
+    const int t0 = bl[r0 * L.bpitch + c0], t1 = bl[r1 * L.bpitch + c1];
     val |= (t0 < t1) << j;
   }
   const int o = base + i;
@@ -702,8 +818,8 @@ struct drfe_orb {
   OrbDev* dd = nullptr;        // device copy
   cudaStream_t stream = nullptr;
   uint8_t* d_gray = nullptr;   // staging for host inputs [B][H][W]
-  void* d_rtab = nullptr; void* d_cells = nullptr; void* d_tiles = nullptr;
-  int ncells = 0, ntiles = 0, max_node_cap = 0, max_lkp = 0;
+  void* d_rtab = nullptr; void* d_strips = nullptr;
+  int nstrips = 0, blur_blocks = 0, max_node_cap = 0, max_lkp = 0;
   size_t fast_smem = 0, quad_smem = 0;
   int last_frames = 0;
   bool pending = false;
@@ -771,10 +887,9 @@ static int orb_build(drfe_orb* h) {
   memset(&D, 0, sizeof(D));
   D.nlevels = nl; D.B = h->max_batch; D.ini_th = pr.ini_th_fast; D.min_th = pr.min_th_fast;
   std::vector<uint2> rtab;
-  std::vector<CellDev> cells;
-  std::vector<TileDev> tiles;
+  std::vector<StripDev> strips;
   long long img_total = 0, blur_total = 0, cand_total = 0;
-  int lkp_total = 0, kp_cap = 0, max_ww = 0, max_wh = 0;
+  int lkp_total = 0, kp_cap = 0, max_strip_rows = 0;
   for (int l = 0; l < nl; ++l) {
     LevelDev& L = D.lv[l];
     L.w = cv_round_f((float)h->width * h->inv_scale[l]);
@@ -811,33 +926,34 @@ static int orb_build(drfe_orb* h) {
       L.xtab_off = (long long)rtab.size(); make_resize_tab(D.lv[l - 1].w, L.w, rtab);
       L.ytab_off = (long long)rtab.size(); make_resize_tab(D.lv[l - 1].h, L.h, rtab);
     }
-    const int minB = kEdge - 3, maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+    // FAST strips: the interior rows [19 + i*hCell, min(19 + (i+1)*hCell, h-19)) of cell row i.
+    // Cell (i, j) of the reference's grid (:789-829) evaluates FAST exactly on the pixels
+    // [19 + j*wCell, ..) x [19 + i*hCell, ..) clipped to [19, w-19) x [19, h-19) (App. A.3b).
+    if (L.nCols > kMaxStripCells) { set_error("image too wide (%d FAST cell columns)", L.nCols); return DRFE_ERR_ARG; }
     for (int i = 0; i < L.nRows; ++i) {
-      const int iniY = minB + i * L.hCell;
-      int maxY = iniY + L.hCell + 6;
-      if (iniY >= maxBY - 3) continue;
-      if (maxY > maxBY) maxY = maxBY;
-      for (int j = 0; j < L.nCols; ++j) {
-        const int iniX = minB + j * L.wCell;
-        int maxX = iniX + L.wCell + 6;
-        if (iniX >= maxBX - 6) continue;
-        if (maxX > maxBX) maxX = maxBX;
-        if (maxX - iniX < 7 || maxY - iniY < 7) continue;  // FAST finds nothing in < 7 px
-        cells.push_back(CellDev{(short)l, (short)iniX, (short)iniY, (short)(maxX - iniX), (short)(maxY - iniY), 0});
-        max_ww = std::max(max_ww, maxX - iniX); max_wh = std::max(max_wh, maxY - iniY);
-      }
+      const int y0 = kEdge + i * L.hCell, y1 = std::min(y0 + L.hCell, L.h - kEdge);
+      if (y1 <= y0) continue;
+      strips.push_back(StripDev{(short)l, (short)y0, (short)(y1 - y0), 0});
+      max_strip_rows = std::max(max_strip_rows, y1 - y0);
     }
-    for (int ty = 0; ty < (L.h + kBlurTH - 1) / kBlurTH; ++ty)
-      for (int tx = 0; tx < (L.w + kBlurTW - 1) / kBlurTW; ++tx) tiles.push_back(TileDev{(short)l, (short)tx, (short)ty, 0});
+    {
+      const unsigned quads = (unsigned)((L.w - 2 * kEdge + 3) / 4);
+      L.quads_magic = (uint32_t)(((1ull << 32) + quads - 1) / quads);
+    }
+    L.blur_nq = (L.w + 3) / 4;
+    L.blur_magic = (uint32_t)(((1ull << 32) + L.blur_nq - 1) / L.blur_nq);
+    D.blur_blk_off[l] = h->blur_blocks;
+    h->blur_blocks += (L.blur_nq * ((L.h + kBlurRows - 1) / kBlurRows) + 255) / 256;
+    D.blur_blk_off[l + 1] = h->blur_blocks;
     if (L.w > 4000 || L.h > 4000) { set_error("image too large (12-bit packed coordinates)"); return DRFE_ERR_ARG; }
   }
-  h->ncells = (int)cells.size(); h->ntiles = (int)tiles.size();
+  h->nstrips = (int)strips.size();
   D.cand_fstride = cand_total; D.lkp_fstride = lkp_total; D.kp_cap = kp_cap; h->max_lkp = 0;
   for (int l = 0; l < nl; ++l) h->max_lkp = std::max(h->max_lkp, D.lv[l].node_cap);
-  D.fast_tp = (max_ww + 8 + 3) / 4 * 4 + 4;     // word loads read up to 4g+11 <= ww+8
-  D.fast_rows = max_wh;
-  D.fast_list_cap = ((max_ww - 5) / 2 + 1) * ((max_wh - 5) / 2 + 1);
-  h->fast_smem = (size_t)2 * D.fast_tp * (D.fast_rows + 1) + (size_t)D.fast_list_cap * 4;
+  D.fast_tp = (D.lv[0].w + 15) / 16 * 16;         // smem row pitch of a FAST strip (TMA rows are 16 B multiples)
+  D.fast_rows = max_strip_rows;
+  h->fast_smem = (size_t)D.fast_tp * (D.fast_rows + 6) + (size_t)D.fast_tp * (D.fast_rows + 2) + (size_t)D.fast_tp * 4;
+  if (h->fast_smem > 220 * 1024) { set_error("image too wide for the FAST strip kernel (%zu B of shared memory)", h->fast_smem); return DRFE_ERR_ARG; }
   const int NC = h->max_node_cap;
   h->quad_smem = (size_t)NC * (8 + 8 + 8 + 4 + 4 + 16 + 5 * 4 + 8 + 2) + 64;
 
@@ -856,21 +972,19 @@ static int orb_build(drfe_orb* h) {
   if (dev_alloc(h, &D.out_cnt, (size_t)B)) return DRFE_ERR_CUDA;
   if (dev_alloc(h, &D.status, 1)) return DRFE_ERR_CUDA;
   if (dev_alloc(h, &h->d_gray, (size_t)B * h->width * h->height)) return DRFE_ERR_CUDA;
-  uint2* d_rtab; CellDev* d_cells; TileDev* d_tiles;
+  uint2* d_rtab; StripDev* d_strips;
   if (dev_alloc(h, &d_rtab, rtab.size())) return DRFE_ERR_CUDA;
-  if (dev_alloc(h, &d_cells, cells.size())) return DRFE_ERR_CUDA;
-  if (dev_alloc(h, &d_tiles, tiles.size())) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &d_strips, strips.size())) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(d_rtab, rtab.data(), rtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-  DRFE_CUDA(cudaMemcpy(d_cells, cells.data(), cells.size() * sizeof(CellDev), cudaMemcpyHostToDevice));
-  DRFE_CUDA(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice));
-  D.rtab = d_rtab; D.cells = d_cells; D.tiles = d_tiles;
+  DRFE_CUDA(cudaMemcpy(d_strips, strips.data(), strips.size() * sizeof(StripDev), cudaMemcpyHostToDevice));
+  D.rtab = d_rtab; D.strips = d_strips;
   DRFE_CUDA(cudaMemset(D.pyr, 0, (size_t)img_total + 256));
   DRFE_CUDA(cudaMemset(D.status, 0, sizeof(int)));
   if (dev_alloc(h, &h->dd, 1)) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(h->dd, &D, sizeof(D), cudaMemcpyHostToDevice));
   DRFE_CUDA(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
   DRFE_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
-  DRFE_CUDA(cudaFuncSetAttribute(k_fast_cells<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
+  DRFE_CUDA(cudaFuncSetAttribute(k_fast_strips<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
   DRFE_CUDA(cudaFuncSetAttribute(k_quadtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->quad_smem));
   if (h->timer.create()) return DRFE_ERR_CUDA;
   return DRFE_OK;
@@ -983,11 +1097,11 @@ int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_s
     DRFE_LAUNCH(k_pyr_resize, grd, blk, 0, st, h->dd, l);
   }
   h->timer.mark("pyramid", st);
-  DRFE_LAUNCH(k_fast_cells<128>, dim3(h->ncells, nframes), 128, h->fast_smem, st, h->dd);
+  DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, nframes), 256, h->fast_smem, st, h->dd);
   h->timer.mark("fast", st);
   DRFE_LAUNCH(k_quadtree<256>, dim3(nl, nframes), 256, h->quad_smem, st, h->dd);
   h->timer.mark("quadtree", st);
-  DRFE_LAUNCH(k_blur, dim3(h->ntiles, nframes), 256, 0, st, h->dd);
+  DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, nframes), 256, 0, st, h->dd);
   h->timer.mark("blur", st);
   DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kDescWarps - 1) / kDescWarps, nl, nframes), kDescWarps * 32, 0, st, h->dd);
   h->timer.mark("orient_describe", st);
