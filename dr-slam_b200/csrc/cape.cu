@@ -35,7 +35,8 @@ struct CapeDev {
   float* tols;                  // [B][ncells]
   int* plane_map;               // [B][ncells]
   uint8_t* eroded_map;          // [B][ncells]
-  uint32_t* border_bits;        // [B][ncells][8]  bit p set: cell is in mask_diff of final plane p (1-based)
+  uint32_t* border_vec;         // [B][kMaxPlanes+1][ceil(ncells/32)] bit c of row p: cell c is in mask_diff of final plane p (1-based)
+  int grid_sums_smem;           // k_cape_grid keeps the cells' moment sums in shared memory
   drfe_plane* segs;             // [B][kMaxPlanes+1] scratch: plane_segments
   drfe_plane* planes;           // [B][kMaxPlanes]   plane_segments_final
   float4* plane_eq;             // [B][kMaxPlanes+1] (nx,ny,nz,d) float of final planes (1-based)
@@ -44,7 +45,6 @@ struct CapeDev {
   uint8_t* seg;                 // [B][H*W]
   int* status;
   struct CellSums* sums;        // [B][ncells] per-cell moment sums (k_cape_sums -> k_cape_fit)
-  void* cs_spill;               // [B][ncells] CellS in global memory when the grid does not fit in smem
 };
 
 // ---- 3x3 symmetric eigen-solve (cyclic Jacobi).  Mirrors eig3_sym() of the oracle
@@ -307,205 +307,257 @@ __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp
 }
 
 // ------------------------------------------------------------------ grid stage
-struct CellS {            // per-cell data kept in shared memory by k_cape_grid
-  double n[3], m[3], d;
-};
+// CAPE::process between the per-cell fits and the per-pixel refinement (CAPE.cpp:82-291), one
+// CTA per frame.  The cell grid is handled as bit vectors (bit c = cell c, 32 cells per word):
+//  * RegionGrowing's acceptance test of cell c against an activated 4-neighbour p
+//    (CAPE.cpp:485-506) depends only on the pair (p, c), so the four directed edge masks
+//    FL/FR/FU/FD are computed once per frame; growing a region is then reachability over those
+//    masks: A |= ((A<<1)&FL | (A>>1)&FR | (A<<ncx)&FU | (A>>ncx)&FD) & U until A stops changing —
+//    the same set the recursion activates (order-free), done by one warp on a few words.
+//  * erode (3x3 cross) / dilate (3x3 square) of the per-plane cell masks (:270, :282) are
+//    shifts and ANDs / ORs of the mask vector.
+// The seed loop itself is sequential and runs on warp 0; the other warps join for the
+// per-cell set-up and the per-plane mask stage.
+__device__ __forceinline__ uint32_t bv_get(const uint32_t* V, int nw, int w) { return (w >= 0 && w < nw) ? V[w] : 0u; }
+// word w of V shifted up by k cells (bit c of the result = bit c-k of V), zeros shifted in
+__device__ __forceinline__ uint32_t bv_shl(const uint32_t* V, int nw, int w, int k) {
+  const int q = k >> 5, r = k & 31;
+  const uint32_t lo = bv_get(V, nw, w - q);
+  return r ? ((lo << r) | (bv_get(V, nw, w - q - 1) >> (32 - r))) : lo;
+}
+// word w of V shifted down by k cells (bit c of the result = bit c+k of V)
+__device__ __forceinline__ uint32_t bv_shr(const uint32_t* V, int nw, int w, int k) {
+  const int q = k >> 5, r = k & 31;
+  const uint32_t hi = bv_get(V, nw, w + q);
+  return r ? ((hi >> r) | (bv_get(V, nw, w + q + 1) << (32 - r))) : hi;
+}
+
+enum { BV_FL = 0, BV_FR, BV_FU, BV_FD, BV_U, BV_A, BV_B, BV_M, BV_H, BV_C0, BV_CL, BV_R0, BV_RL, BV_VALID, BV_COUNT };
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict__ Pp) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CapeDev& P = *Pp;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nc = P.ncells, ncx = P.ncx, ncy = P.ncy;
-  // per-cell plane parameters live in shared memory unless the grid is too large for it
-  // (e.g. 10 px cells at 640x480 = 3072 cells), in which case they stay L2-resident
-  CellS* cs = P.cs_spill ? reinterpret_cast<CellS*>(P.cs_spill) + (long long)f * nc : reinterpret_cast<CellS*>(smem);
-  float* tol = P.cs_spill ? reinterpret_cast<float*>(smem) : reinterpret_cast<float*>(cs + nc);
-  float* mse = tol + nc;
-  int* bin = reinterpret_cast<int*>(mse + nc);      // histogram bin per cell (-1 = removed / non planar)
-  int* pmap = bin + nc;                              // grid_plane_seg_map
-  int* list = pmap + nc;                             // ordered cell list scratch
-  int* hist = list + nc;                             // [400]
-  uint32_t* assoc = reinterpret_cast<uint32_t*>(hist + kHistBins * kHistBins);  // [256][8] bit matrix
-  uint8_t* unassigned = reinterpret_cast<uint8_t*>(assoc + 256 * 8);
-  uint8_t* act = unassigned + nc;
-  uint8_t* mask = act + nc;
-  uint8_t* er = mask + nc;
-  uint8_t* di = er + nc;
-  __shared__ unsigned long long s_best;
-  __shared__ int s_cnt, s_seed, s_changed, s_any, s_np, s_nfinal, s_warp[THREADS / 32];
+  const int nc = P.ncells, ncx = P.ncx, ncy = P.ncy, nw = (nc + 31) >> 5;
+  // ---- shared layout
+  uint32_t* bv = reinterpret_cast<uint32_t*>(smem);               // [BV_COUNT][nw]
+  int* hist = reinterpret_cast<int*>(bv + BV_COUNT * nw);         // [400]
+  uint32_t* assoc = reinterpret_cast<uint32_t*>(hist + kHistBins * kHistBins);   // [256][8] plane adjacency bits
+  int* list = reinterpret_cast<int*>(assoc + 256 * 8);            // [nc] candidate cells of the chosen bin
+  int* npts = list + nc;                                          // [nc] nr_pts of each cell
+  float* mse = reinterpret_cast<float*>(npts + nc);               // [nc]
+  float* sums = mse + nc;                                         // [nc][9] cell moment sums (floats, exact) if they fit
+  short* bin = reinterpret_cast<short*>(sums + (P.grid_sums_smem ? 9 * nc : 0));   // [nc] histogram bin (-1: none)
+  uint8_t* pmap = reinterpret_cast<uint8_t*>(bin + nc);           // [nc] grid_plane_seg_map (labels 1..255)
   __shared__ int merge[kMaxPlanes + 1];
   __shared__ double s_acc[9];
-  __shared__ int s_accn;
+  __shared__ int s_np, s_accn;
+  uint32_t* FL = bv + BV_FL * nw; uint32_t* FR = bv + BV_FR * nw; uint32_t* FU = bv + BV_FU * nw; uint32_t* FD = bv + BV_FD * nw;
+  uint32_t* U = bv + BV_U * nw; uint32_t* A = bv + BV_A * nw; uint32_t* Bv = bv + BV_B * nw;
+  uint32_t* M = bv + BV_M * nw; uint32_t* Hh = bv + BV_H * nw;
+  uint32_t* C0 = bv + BV_C0 * nw; uint32_t* CL = bv + BV_CL * nw; uint32_t* R0 = bv + BV_R0 * nw; uint32_t* RL = bv + BV_RL * nw;
+  uint32_t* VALID = bv + BV_VALID * nw;
 
   const drfe_plane* cells = P.cells + (long long)f * nc;
+  const float* tols = P.tols + (long long)f * nc;
   drfe_plane* segs = P.segs + (long long)f * (kMaxPlanes + 1);
   for (int i = tid; i < kHistBins * kHistBins; i += THREADS) hist[i] = 0;
   for (int i = tid; i < 256 * 8; i += THREADS) assoc[i] = 0;
-  if (tid == 0) { s_np = 0; s_nfinal = 0; }
+  if (tid == 0) s_np = 0;
   __syncthreads();
-  // ---- spherical-coordinate histogram (CAPE.cpp:82-101, Histogram.cpp:15-43)
-  int my_remaining = 0;
-  for (int c = tid; c < nc; c += THREADS) {
-    const drfe_plane& g = cells[c];
-    cs[c].n[0] = g.normal[0]; cs[c].n[1] = g.normal[1]; cs[c].n[2] = g.normal[2];
-    cs[c].m[0] = g.mean[0]; cs[c].m[1] = g.mean[1]; cs[c].m[2] = g.mean[2];
-    cs[c].d = g.d;
-    tol[c] = P.tols[(long long)f * nc + c];
-    mse[c] = g.MSE;
-    pmap[c] = 0;
-    int b = -1;
-    if (g.planar) {
-      const double nx = g.normal[0], ny = g.normal[1], nz = g.normal[2];
-      const double pn = sqrt(nx * nx + ny * ny);
-      const double polar = acos(-nz);
-      const int xq = (int)((kHistBins - 1) * (polar - 0.0) / (3.14 - 0.0));
-      int yq = 0;
-      if (xq > 0) yq = (int)((kHistBins - 1) * (atan2(nx / pn, ny / pn) - (-3.14)) / (3.14 - (-3.14)));
-      b = yq * kHistBins + xq;
-      atomicAdd(&hist[b], 1);
-      ++my_remaining;
-    }
-    bin[c] = b;
-    unassigned[c] = g.planar ? 1 : 0;
-  }
-  // block sum of remaining planar cells
+  // ---- per-cell set-up: histogram bin (CAPE.cpp:82-101, Histogram.cpp:15-43), edge masks
+  const double min_cos = (double)P.min_cos;
+  for (int c0 = wid * 32; c0 < nw * 32; c0 += THREADS) {
+    const int c = c0 + lane;
+    const bool valid = c < nc;
+    bool planar = false, fl = false, fr = false, fu = false, fd = false;
+    int y = 0, x = 0;
+    if (valid) {
+      y = c / ncx; x = c - y * ncx;
+      const drfe_plane& g = cells[c];
+      planar = g.planar != 0;
+      mse[c] = g.MSE;
+      npts[c] = g.nr_pts;
+      pmap[c] = 0;
+      if (P.grid_sums_smem) {
+        const double* sp = &g.x_acc;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) my_remaining += __shfl_down_sync(0xFFFFFFFFu, my_remaining, o);
-  if (lane == 0) s_warp[wid] = my_remaining;
-  __syncthreads();
-  int remaining = 0;
-  for (int w = 0; w < THREADS / 32; ++w) remaining += s_warp[w];
+        for (int k = 0; k < 9; ++k) sums[c * 9 + k] = (float)sp[k];     // exact: the sums are floats widened to double
+      }
+      int b = -1;
+      if (planar) {
+        const double nx = g.normal[0], ny = g.normal[1], nz = g.normal[2];
+        const double mx = g.mean[0], my = g.mean[1], mz = g.mean[2];
+        const double pn = sqrt(nx * nx + ny * ny);
+        const double polar = acos(-nz);
+        const int xq = (int)((kHistBins - 1) * (polar - 0.0) / (3.14 - 0.0));
+        int yq = 0;
+        if (xq > 0) yq = (int)((kHistBins - 1) * (atan2(nx / pn, ny / pn) - (-3.14)) / (3.14 - (-3.14)));
+        b = yq * kHistBins + xq;
+        atomicAdd(&hist[b], 1);
+        // can this cell be activated from neighbour p (RegionGrowing called with p's normal and d)?
+        const double tol = (double)tols[c];
+        auto edge = [&](int p) -> bool {
+          const drfe_plane& a = cells[p];
+          const double dist = a.normal[0] * mx + a.normal[1] * my + a.normal[2] * mz + a.d;
+          return !(a.normal[0] * nx + a.normal[1] * ny + a.normal[2] * nz < min_cos || dist * dist > tol);
+        };
+        if (x > 0) fl = edge(c - 1);
+        if (x + 1 < ncx) fr = edge(c + 1);
+        if (y > 0) fu = edge(c - ncx);
+        if (y + 1 < ncy) fd = edge(c + ncx);
+      }
+      bin[c] = (short)b;
+    }
+    const int w = c0 >> 5;
+    const unsigned b_fl = __ballot_sync(0xFFFFFFFFu, fl), b_fr = __ballot_sync(0xFFFFFFFFu, fr),
+                   b_fu = __ballot_sync(0xFFFFFFFFu, fu), b_fd = __ballot_sync(0xFFFFFFFFu, fd),
+                   b_u = __ballot_sync(0xFFFFFFFFu, planar), b_v = __ballot_sync(0xFFFFFFFFu, valid),
+                   b_c0 = __ballot_sync(0xFFFFFFFFu, valid && x == 0), b_cl = __ballot_sync(0xFFFFFFFFu, valid && x == ncx - 1),
+                   b_r0 = __ballot_sync(0xFFFFFFFFu, valid && y == 0), b_rl = __ballot_sync(0xFFFFFFFFu, valid && y == ncy - 1);
+    if (lane == 0) {
+      FL[w] = b_fl; FR[w] = b_fr; FU[w] = b_fu; FD[w] = b_fd; U[w] = b_u; VALID[w] = b_v;
+      C0[w] = b_c0; CL[w] = b_cl; R0[w] = b_r0; RL[w] = b_rl; A[w] = 0; Bv[w] = 0;
+    }
+  }
   __syncthreads();
 
-  // ---- seeded region growing (CAPE.cpp:114-218)
-  while (remaining > 0) {
-    if (tid == 0) { s_best = 0ull; s_cnt = 0; }
-    __syncthreads();
-    // most frequent bin, first maximum wins (Histogram.cpp:49-55)
-    for (int b = tid; b < kHistBins * kHistBins; b += THREADS)
-      if (hist[b] > 0) atomicMax(&s_best, ((unsigned long long)hist[b] << 32) | (unsigned)(0xFFFF - b));
-    __syncthreads();
-    if (s_best == 0ull) break;
-    const int best_bin = 0xFFFF - (int)(s_best & 0xFFFFu);
-    const int ncand = (int)(s_best >> 32);
-    if (ncand < 5) break;                                  // Checkpoint 1 (:120)
-    // ordered candidate list (ascending cell id), built by warp 0
-    if (wid == 0) {
-      int base = 0;
-      for (int c0 = 0; c0 < nc; c0 += 32) {
-        const int c = c0 + lane;
-        const bool is = c < nc && bin[c] == best_bin;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
-        if (is) list[base + __popc(bal & ((1u << lane) - 1))] = c;
-        base += __popc(bal);
+  // ---- seeded region growing (CAPE.cpp:114-218), warp 0
+  if (wid == 0) {
+    int remaining = 0;
+    for (int w = lane; w < nw; w += 32) remaining += __popc(U[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) remaining += __shfl_xor_sync(0xFFFFFFFFu, remaining, o);
+    int np = 0;
+    for (int guard = 0; remaining > 0 && guard <= nc; ++guard) {
+      // most frequent bin, first maximum wins (Histogram.cpp:49-55)
+      unsigned best = 0;
+      for (int b = lane; b < kHistBins * kHistBins; b += 32) {
+        const int hcnt = hist[b];
+        if (hcnt > 0) best = max(best, ((unsigned)hcnt << 16) | (unsigned)(0xFFFF - b));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+      if (best == 0) break;
+      const int best_bin = 0xFFFF - (int)(best & 0xFFFFu);
+      const int ncand = (int)(best >> 16);
+      if (ncand < 5) break;                                  // Checkpoint 1 (:120)
+      // candidate cells in ascending order
+      {
+        int base = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          const int c = c0 + lane;
+          const bool is = c < nc && bin[c] == best_bin;
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
+          if (is) list[base + __popc(bal & ((1u << lane) - 1))] = c;
+          base += __popc(bal);
+        }
       }
       __syncwarp();
+      // seed = candidate with the smallest MSE, with the reference's stray index (:125-132):
+      // the running minimum is refreshed from Grid[i] (loop counter), not Grid[candidate].
+      int seed = 0;
       if (lane == 0) {
-        // seed = candidate with the smallest MSE, with the reference's stray index (:125-132):
-        // the running minimum is refreshed from Grid[i] (loop counter), not Grid[candidate].
-        int seed = list[0];
+        seed = list[0];
         float min_mse = (float)2147483647;
+#pragma unroll 4
         for (int i = 0; i < ncand; ++i) {
           const int c = list[i];
           if (mse[c] < min_mse) { seed = c; min_mse = mse[i]; }
         }
-        s_seed = seed;
       }
-    }
-    for (int c = tid; c < nc; c += THREADS) act[c] = 0;
-    __syncthreads();
-    const int seed = s_seed;
-    // RegionGrowing (:485-506) == closure of "cell passes against an activated 4-neighbour's
-    // plane"; the seed is tested against its own plane.
-    if (tid == 0) {
-      const CellS& a = cs[seed];
-      const double dist = a.n[0] * a.m[0] + a.n[1] * a.m[1] + a.n[2] * a.m[2] + a.d;
-      const bool ok = unassigned[seed] && !(a.n[0] * a.n[0] + a.n[1] * a.n[1] + a.n[2] * a.n[2] < (double)P.min_cos ||
-                                            dist * dist > (double)tol[seed]);
-      act[seed] = ok ? 1 : 0;
-      s_changed = ok ? 1 : 0;
-    }
-    __syncthreads();
-    while (s_changed) {
-      __syncthreads();
-      if (tid == 0) s_changed = 0;
-      __syncthreads();
-      for (int c = tid; c < nc; c += THREADS) {
-        if (!unassigned[c] || act[c]) continue;
-        const int y = c / ncx, x = c - y * ncx;
-        const CellS& b = cs[c];
-        bool ok = false;
-#pragma unroll
-        for (int k = 0; k < 4 && !ok; ++k) {
-          int p;
-          if (k == 0) { if (x + 1 >= ncx) continue; p = c + 1; }        // reached from its left neighbour's "right"
-          else if (k == 1) { if (x == 0) continue; p = c - 1; }
-          else if (k == 2) { if (y + 1 >= ncy) continue; p = c + ncx; }
-          else { if (y == 0) continue; p = c - ncx; }
-          if (!act[p]) continue;
-          const CellS& a = cs[p];
-          const double dist = a.n[0] * b.m[0] + a.n[1] * b.m[1] + a.n[2] * b.m[2] + a.d;
-          ok = !(a.n[0] * b.n[0] + a.n[1] * b.n[1] + a.n[2] * b.n[2] < (double)P.min_cos || dist * dist > (double)tol[c]);
-        }
-        if (ok) { act[c] = 1; s_changed = 1; }
-      }
-      __syncthreads();
-    }
-    // ---- merge activated cells in ascending order (:144-153); ordered list by warp 0
-    if (wid == 0) {
-      int base = 0;
-      for (int c0 = 0; c0 < nc; c0 += 32) {
-        const int c = c0 + lane;
-        const bool is = c < nc && act[c];
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
-        if (is) list[base + __popc(bal & ((1u << lane) - 1))] = c;
-        base += __popc(bal);
-      }
-      if (lane == 0) s_cnt = base;
-    }
-    __syncthreads();
-    const int nact = s_cnt;
-    if (tid < 10) {
-      // new_ps = *Grid[seed] then expandSegment(Grid[i]) for every activated i (seed included twice)
+      seed = __shfl_sync(0xFFFFFFFFu, seed, 0);
+      // RegionGrowing from the seed with its own plane (:142)
       const drfe_plane& sd = cells[seed];
-      if (tid < 9) {
-        const double* base0 = &sd.x_acc;
-        double acc = base0[tid];
-        for (int i = 0; i < nact; ++i) acc += (&cells[list[i]].x_acc)[tid];
-        s_acc[tid] = acc;
-      } else {
+      bool seed_ok;
+      {
+        const double dist = sd.normal[0] * sd.mean[0] + sd.normal[1] * sd.mean[1] + sd.normal[2] * sd.mean[2] + sd.d;
+        seed_ok = ((U[seed >> 5] >> (seed & 31)) & 1u) &&
+                  !(sd.normal[0] * sd.normal[0] + sd.normal[1] * sd.normal[1] + sd.normal[2] * sd.normal[2] < min_cos ||
+                    dist * dist > (double)tols[seed]);
+      }
+      if (!seed_ok) { if (lane == 0) atomicOr(P.status, 2); break; }   // the reference would never terminate here
+      uint32_t* cur = A; uint32_t* nxt = Bv;
+      for (int w = lane; w < nw; w += 32) cur[w] = (w == (seed >> 5)) ? (1u << (seed & 31)) : 0u;
+      __syncwarp();
+      for (;;) {
+        bool changed = false;
+        for (int w = lane; w < nw; w += 32) {
+          const uint32_t a = cur[w], u = U[w], l = FL[w], r = FR[w];
+          uint32_t a2 = a | (((bv_shl(cur, nw, w, 1) & l) | (bv_shr(cur, nw, w, 1) & r) | (bv_shl(cur, nw, w, ncx) & FU[w]) |
+                              (bv_shr(cur, nw, w, ncx) & FD[w])) & u);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) a2 |= (((a2 << 1) & l) | ((a2 >> 1) & r)) & u;   // in-word row closure
+          nxt[w] = a2;
+          changed |= (a2 != a);
+        }
+        __syncwarp();
+        { uint32_t* t = cur; cur = nxt; nxt = t; }
+        if (!__any_sync(0xFFFFFFFFu, changed)) break;
+      }
+      // ---- accumulate: new_ps = *Grid[seed], then expandSegment(Grid[i]) for every activated i in
+      // ascending order (the seed is counted twice, :134,146-149); lanes 0..8 own one sum each
+      int nact = 0;
+      for (int w = lane; w < nw; w += 32) nact += __popc(cur[w]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nact += __shfl_xor_sync(0xFFFFFFFFu, nact, o);
+      if (lane < 9) {
+        double acc = (&sd.x_acc)[lane];
+        for (int w = 0; w < nw; ++w) {
+          uint32_t bits = cur[w];
+          while (bits) {
+            const int c = (w << 5) + __ffs(bits) - 1;
+            bits &= bits - 1;
+            acc += P.grid_sums_smem ? (double)sums[c * 9 + lane] : (&cells[c].x_acc)[lane];
+          }
+        }
+        s_acc[lane] = acc;
+      } else if (lane == 9) {
         int acc = sd.nr_pts;
-        for (int i = 0; i < nact; ++i) acc += cells[list[i]].nr_pts;
+        for (int w = 0; w < nw; ++w) {
+          uint32_t bits = cur[w];
+          while (bits) { const int c = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; acc += npts[c]; }
+        }
         s_accn = acc;
       }
-    }
-    for (int i = tid; i < nact; i += THREADS) {
-      const int c = list[i];
-      atomicSub(&hist[bin[c]], 1);       // H.removePoint
-      bin[c] = -1;
-      unassigned[c] = 0;
-    }
-    remaining -= nact;
-    __syncthreads();
-    if (nact < 4) continue;                                // Checkpoint 2 (:157)
-    if (tid == 0) {
-      drfe_plane ps = cells[seed];
-      ps.x_acc = s_acc[0]; ps.y_acc = s_acc[1]; ps.z_acc = s_acc[2]; ps.xx_acc = s_acc[3]; ps.yy_acc = s_acc[4];
-      ps.zz_acc = s_acc[5]; ps.xy_acc = s_acc[6]; ps.xz_acc = s_acc[7]; ps.yz_acc = s_acc[8];
-      ps.nr_pts = s_accn;
-      fit_plane(ps);
-      s_any = 0;
-      if (ps.score > 100) {                                // it is a plane (:163)
-        if (s_np < kMaxPlanes) { segs[s_np] = ps; s_np = s_np + 1; s_any = s_np; }
-        else atomicOr(P.status, 1);
+      // remove the activated cells from the histogram and the unassigned mask (:150-153)
+      for (int w = lane; w < nw; w += 32) {
+        uint32_t bits = cur[w];
+        U[w] &= ~bits;
+        while (bits) {
+          const int c = (w << 5) + __ffs(bits) - 1;
+          bits &= bits - 1;
+          atomicSub(&hist[bin[c]], 1);
+          bin[c] = -1;
+        }
       }
+      remaining -= nact;
+      __syncwarp();
+      if (nact < 4) continue;                                // Checkpoint 2 (:157)
+      int label = 0;
+      if (lane == 0) {
+        drfe_plane ps = sd;
+        ps.x_acc = s_acc[0]; ps.y_acc = s_acc[1]; ps.z_acc = s_acc[2]; ps.xx_acc = s_acc[3]; ps.yy_acc = s_acc[4];
+        ps.zz_acc = s_acc[5]; ps.xy_acc = s_acc[6]; ps.xz_acc = s_acc[7]; ps.yz_acc = s_acc[8];
+        ps.nr_pts = s_accn;
+        fit_plane(ps);
+        if (ps.score > 100) {                                // it is a plane (:163)
+          if (np < kMaxPlanes) { segs[np] = ps; label = np + 1; }
+          else atomicOr(P.status, 1);
+        }
+      }
+      label = __shfl_sync(0xFFFFFFFFu, label, 0);
+      if (label > 0) {
+        np = label;
+        for (int w = lane; w < nw; w += 32) {
+          uint32_t bits = cur[w];
+          while (bits) { const int c = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; pmap[c] = (uint8_t)label; }
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    const int label = s_any;
-    if (label > 0)
-      for (int i = tid; i < nact; i += THREADS) pmap[list[i]] = label;
-    __syncthreads();
+    if (lane == 0) s_np = np;
   }
   __syncthreads();
   // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
@@ -528,11 +580,11 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
       bool expanded = false;
       for (int c = r + 1; c < np; ++c) {
         if (!(get(r, c) || get(c, r))) continue;
-        const drfe_plane& A = segs[pid];
+        const drfe_plane& Ap = segs[pid];
         const drfe_plane& Cc = segs[c];
-        const double cosang = A.normal[0] * Cc.normal[0] + A.normal[1] * Cc.normal[1] + A.normal[2] * Cc.normal[2];
+        const double cosang = Ap.normal[0] * Cc.normal[0] + Ap.normal[1] * Cc.normal[1] + Ap.normal[2] * Cc.normal[2];
         // sic: the x term uses plane r, the others plane_id (:238-240)
-        const double dd = segs[r].normal[0] * Cc.mean[0] + A.normal[1] * Cc.mean[1] + A.normal[2] * Cc.mean[2] + A.d;
+        const double dd = segs[r].normal[0] * Cc.mean[0] + Ap.normal[1] * Cc.mean[1] + Ap.normal[2] * Cc.mean[2] + Ap.d;
         if (cosang > (double)P.min_cos && dd * dd < (double)P.max_merge_dist) {
           expand_seg(segs[pid], segs[c]);
           merge[c] = pid;
@@ -545,61 +597,54 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   __syncthreads();
   // ---- per final plane: cell mask, erode (cross), dilate (square) (CAPE.cpp:254-291)
   uint8_t* eroded_map = P.eroded_map + (long long)f * nc;
-  uint32_t* bbits = P.border_bits + (long long)f * nc * 8;
-  for (int c = tid; c < nc; c += THREADS) {
-    eroded_map[c] = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) bbits[c * 8 + k] = 0;
-  }
+  uint32_t* border = P.border_vec + (long long)f * (kMaxPlanes + 1) * nw;
+  for (int c = tid; c < nc; c += THREADS) eroded_map[c] = 0;
+  int nfinal = 0;
   for (int i = 0; i < np; ++i) {
     if (merge[i] != i) continue;
-    if (tid == 0) s_any = 0;
-    for (int c = tid; c < nc; c += THREADS) {
-      const int v = pmap[c];
-      mask[c] = (v > i && merge[v - 1] == i) ? 1 : 0;        // j >= i with merge label i
+    for (int w = tid; w < nw; w += THREADS) {
+      uint32_t m = 0;
+      const int cend = min(32, nc - (w << 5));
+      for (int b = 0; b < cend; ++b) {
+        const int v = pmap[(w << 5) + b];
+        if (v > i && merge[v - 1] == i) m |= 1u << b;          // j >= i with merge label i
+      }
+      M[w] = m;
     }
     __syncthreads();
-    for (int c = tid; c < nc; c += THREADS) {
-      const int r = c / ncx, x = c - r * ncx;
-      int e = mask[c];
-      if (x > 0) e &= mask[c - 1];
-      if (x + 1 < ncx) e &= mask[c + 1];
-      if (r > 0) e &= mask[c - ncx];
-      if (r + 1 < ncy) e &= mask[c + ncx];
-      er[c] = (uint8_t)e;
-      if (e) s_any = 1;
-      int dmax = 0;
-      for (int dr = -1; dr <= 1; ++dr)
-        for (int dc = -1; dc <= 1; ++dc) {
-          const int rr = r + dr, xx = x + dc;
-          if (rr < 0 || rr >= ncy || xx < 0 || xx >= ncx) continue;
-          dmax |= mask[rr * ncx + xx];
-        }
-      di[c] = (uint8_t)dmax;
+    int any = 0;
+    uint32_t er_w[4];                                          // this thread's words of the eroded mask
+    for (int w = tid, k = 0; w < nw; w += THREADS, ++k) {
+      const uint32_t m = M[w];
+      const uint32_t l1 = bv_shl(M, nw, w, 1), r1 = bv_shr(M, nw, w, 1);
+      const uint32_t e = m & (l1 | C0[w]) & (r1 | CL[w]) & (bv_shl(M, nw, w, ncx) | R0[w]) & (bv_shr(M, nw, w, ncx) | RL[w]);
+      Hh[w] = m | (l1 & ~C0[w]) | (r1 & ~CL[w]);
+      if (k < 4) er_w[k] = e;
+      any |= (e != 0);
     }
-    __syncthreads();
-    const bool keep = s_any != 0;                          // completely eroded planes are ignored (:275)
-    __syncthreads();
-    if (!keep) continue;
-    const int plane_nr = s_nfinal + 1;
-    __syncthreads();
-    if (tid == 0) {
-      const drfe_plane& ps = segs[i];
-      P.planes[(long long)f * kMaxPlanes + s_nfinal] = ps;
-      P.plane_eq[(long long)f * (kMaxPlanes + 1) + plane_nr] =
-          make_float4((float)ps.normal[0], (float)ps.normal[1], (float)ps.normal[2], (float)ps.d);
-      P.plane_maxd[(long long)f * (kMaxPlanes + 1) + plane_nr] = 9 * ps.MSE;
-      s_nfinal = plane_nr;
-    }
-    for (int c = tid; c < nc; c += THREADS) {
-      if (er[c]) eroded_map[c] = (uint8_t)plane_nr;
-      if (di[c] && !er[c]) bbits[c * 8 + (plane_nr >> 5)] |= 1u << (plane_nr & 31);
+    const int keep = __syncthreads_or(any);                    // completely eroded planes are ignored (:275)
+    if (keep) {
+      const int plane_nr = ++nfinal;
+      if (tid == 0) {
+        const drfe_plane& ps = segs[i];
+        P.planes[(long long)f * kMaxPlanes + plane_nr - 1] = ps;
+        P.plane_eq[(long long)f * (kMaxPlanes + 1) + plane_nr] =
+            make_float4((float)ps.normal[0], (float)ps.normal[1], (float)ps.normal[2], (float)ps.d);
+        P.plane_maxd[(long long)f * (kMaxPlanes + 1) + plane_nr] = 9 * ps.MSE;
+      }
+      for (int w = tid, k = 0; w < nw; w += THREADS, ++k) {
+        const uint32_t e = er_w[k & 3];
+        const uint32_t d = (Hh[w] | bv_shl(Hh, nw, w, ncx) | bv_shr(Hh, nw, w, ncx)) & VALID[w];
+        border[(long long)plane_nr * nw + w] = d & ~e;         // mask_diff = dilated - eroded (:284)
+        uint32_t bits = e;
+        while (bits) { const int c = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; eroded_map[c] = (uint8_t)plane_nr; }
+      }
     }
     __syncthreads();
   }
   int* plane_map = P.plane_map + (long long)f * nc;
   for (int c = tid; c < nc; c += THREADS) plane_map[c] = pmap[c];
-  if (tid == 0) P.nplanes[f] = s_nfinal;
+  if (tid == 0) P.nplanes[f] = nfinal;
 }
 
 // ------------------------------------------------------------------ refinement + output
@@ -617,11 +662,25 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
   const long long N = (long long)P.H * P.W;
   uint8_t* out = P.seg + (long long)f * N + (long long)(cr * P.ch) * P.W + cc * cw;
   const int er = P.eroded_map[(long long)f * P.ncells + cell];
-  const uint32_t* bb = P.border_bits + ((long long)f * P.ncells + cell) * 8;
+  // planes whose dilated-minus-eroded mask contains this cell (bit p of bits[] = final plane p)
+  const int nw = (P.ncells + 31) >> 5, npl = P.nplanes[f];
+  const uint32_t* bvec = P.border_vec + (long long)f * (kMaxPlanes + 1) * nw + (cell >> 5);
   uint32_t bits[8];
   uint32_t anyb = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { bits[k] = bb[k]; anyb |= bits[k]; }
+  for (int k = 0; k < 8; ++k) bits[k] = 0;
+  for (int p0 = 1; p0 <= npl; p0 += 32) {
+    const int p = p0 + lane;
+    const bool in = p <= npl && ((bvec[(long long)p * nw] >> (cell & 31)) & 1u);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);     // bit j = plane p0 + j
+    // planes p0 .. p0+31 straddle words (p0 >> 5) and (p0 >> 5) + 1 of bits[] (p0 = 1 mod 32)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k == (p0 >> 5)) bits[k] |= bal << 1;
+      if (k == (p0 >> 5) + 1) bits[k] |= bal >> 31;
+    }
+    anyb |= bal;
+  }
   if (er > 0 || anyb == 0) {
     for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)er; }
     return;
@@ -731,7 +790,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.sums, nc * B);
   rc |= cape_alloc(h, &D.plane_map, nc * B);
   rc |= cape_alloc(h, &D.eroded_map, nc * B);
-  rc |= cape_alloc(h, &D.border_bits, nc * B * 8);
+  rc |= cape_alloc(h, &D.border_vec, (size_t)(kMaxPlanes + 1) * ((nc + 31) / 32) * B);
   rc |= cape_alloc(h, &D.segs, (size_t)(kMaxPlanes + 1) * B);
   rc |= cape_alloc(h, &D.planes, (size_t)kMaxPlanes * B);
   rc |= cape_alloc(h, &D.plane_eq, (size_t)(kMaxPlanes + 1) * B);
@@ -745,16 +804,14 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   if (cudaMemset(D.status, 0, sizeof(int)) != cudaSuccess || cudaMemset(D.cloud, 0, 3 * N * B * sizeof(float)) != cudaSuccess) {
     set_error("cudaMemset failed"); return fail(DRFE_ERR_CUDA);
   }
-  const size_t grid_fixed = kHistBins * kHistBins * 4 + 256 * 8 * 4 + 64;
-  h->grid_smem = nc * (sizeof(CellS) + 4 + 4 + 4 + 4 + 4 + 5) + grid_fixed;
-  if (h->grid_smem > 160 * 1024) {
-    h->grid_smem = nc * (4 + 4 + 4 + 4 + 4 + 5) + grid_fixed;
-    CellS* spill = nullptr;
-    if (cape_alloc(h, &spill, nc * B)) return fail(DRFE_ERR_CUDA);
-    D.cs_spill = spill;
+  {
+    const size_t nw = (nc + 31) / 32;
+    const size_t base = (size_t)BV_COUNT * nw * 4 + kHistBins * kHistBins * 4 + 256 * 8 * 4 + nc * (4 + 4 + 4 + 2 + 1) + 64;
+    D.grid_sums_smem = (base + nc * 36 <= 160 * 1024) ? 1 : 0;
+    h->grid_smem = base + (D.grid_sums_smem ? nc * 36 : 0);
+    if (h->grid_smem > 200 * 1024 || nw > 4 * 128) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
   }
-  if (h->grid_smem > 200 * 1024) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
-  if (cudaFuncSetAttribute(k_cape_grid<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_cape_grid<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
     set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
   }
   {
@@ -805,7 +862,7 @@ static int cape_run(drfe_cape* h, int nframes) {
   h->timer.mark("cells", st);
   DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, nframes);
   h->timer.mark("fit", st);
-  DRFE_LAUNCH(k_cape_grid<256>, nframes, 256, h->grid_smem, st, h->dd);
+  DRFE_LAUNCH(k_cape_grid<128>, nframes, 128, h->grid_smem, st, h->dd);
   h->timer.mark("grid", st);
   if (h->margin) {
     const long long tot = (long long)h->hd.H * h->hd.W * nframes;
