@@ -149,6 +149,19 @@ __device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, 
   return p;  // valid in lane 0 of the group
 }
 
+// (float)(t / den) without the fp64 division: q' = t * RN(1/den) is within 2 ulps of the
+// correctly rounded quotient q, so float(q') == float(q) unless a float rounding midpoint
+// (double mantissa bits 28..0 == 0x10000000) lies within a few ulps of q', or the result is
+// outside the float normal range — those rare cases take the exact division.
+__device__ __forceinline__ float div_to_float(double t, double den, double rden) {
+  const double q = t * rden;
+  const uint32_t lo = (uint32_t)__double2loint(q), ex = ((uint32_t)__double2hiint(q) >> 20) & 0x7FFu;
+  const bool near_mid = ((lo & 0x1FFFFFFFu) - 0x0FFFFFFCu) <= 8u;
+  const bool odd_range = (ex - 898u > 251u) && q != 0.0;
+  if (near_mid || odd_range) return (float)(t / den);
+  return (float)q;
+}
+
 static const int kSumsThreads = 128, kSumsChunk = 8;
 template <bool FROM_DEPTH>
 __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __restrict__ Pp, int nframes) {
@@ -175,6 +188,7 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
   const float* __restrict__ dsrc = nullptr;
   if (FROM_DEPTH) dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;
   const double fx = (double)P.fx, fy = (double)P.fy, pcx = (double)P.cx, pcy = (double)P.cy;
+  const double rfx = 1.0 / fx, rfy = 1.0 / fy;
   int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
   for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
     float vz[kSumsChunk], vx[kSumsChunk], vy[kSumsChunk];
@@ -200,9 +214,9 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
         if (FROM_DEPTH) {
           // PlaneExtractor.cpp:117-127: all in double, stored as float
           const double zd = (double)vz[u];
-          const double xd = ((double)(cc * cw + lc) - pcx) * zd / fx;
-          const double yd = ((double)(cr * P.ch + lr) - pcy) * zd / fy;
-          x = (float)xd; y = (float)yd; z = (float)zd;
+          x = div_to_float(((double)(cc * cw + lc) - pcx) * zd, fx, rfx);
+          y = div_to_float(((double)(cr * P.ch + lr) - pcy) * zd, fy, rfy);
+          z = vz[u];
           CX[i] = x; CY[i] = y; CZ[i] = z;
         } else {
           x = vx[u]; y = vy[u]; z = vz[u];

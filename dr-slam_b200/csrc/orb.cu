@@ -55,8 +55,10 @@ struct LevelDev {
   int kp_off;                       // offset inside one frame's per-level keypoint arena
   float scale, size;
   long long xtab_off, ytab_off;     // element offsets into the resize tables (level >= 1)
+  int ptile_off, ptile_cnt, ptile_gx;   // this level's k_pyr_resize tiles inside OrbDev::ptiles
 };
 
+struct PyrTile;
 struct StripDev { short level, y0, nrows, pad; };   // FAST strip: interior rows [y0, y0+nrows) of one cell row
 static const int kMaxStripCells = 160;
 
@@ -67,6 +69,8 @@ struct OrbDev {
   uint8_t* blur;
   const uint2* rtab;                // resize tables {idx0 | idx1<<16, c0 | c1<<16}
   const StripDev* strips;
+  const struct PyrTile* ptiles;     // k_pyr_resize tiles of all levels
+  int pyr_src_bytes;                // smem bytes reserved for a tile's source window
   uint32_t* cand;                   // [B][cand_total] packed x | y<<12 | q<<24 (region coords)
   long long cand_fstride;
   int* cand_cnt;                    // [B][nlevels]
@@ -118,33 +122,75 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const OrbDev* __restrict__ P
 }
 
 // cv::resize INTER_LINEAR 8UC1: 11-bit coefficient fixed point.
+// One CTA = a 128 x 32 tile of the bordered destination level (border pixels are computed
+// like any other pixel, from their reflected coordinate).  The source window of the tile is
+// staged in shared memory with coalesced word loads; the horizontal pass runs once per
+// source row (thread = 4 fixed destination columns, its 4 table entries live in registers)
+// and leaves T >> 4 as u16 in shared memory; the vertical pass combines two such rows per
+// destination row.  One launch per level: level l reads level l-1.
+static const int kPyrTW = 128, kPyrTH = 32;
+struct PyrTile { short g0, by0, sx0, sw4, sy0, nsy, pad0, pad1; };   // first 4-px group, first bordered row, source window
+
 __global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ Pp, int level) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[level];
   const LevelDev& S = P.lv[level - 1];
+  const PyrTile t = P.ptiles[L.ptile_off + blockIdx.x];
+  const int f = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int SW = t.sw4 * 4;                                   // source window pitch (bytes)
+  uint8_t* s_src = smem;                                      // [nsy][SW]
+  uint2* s_T = reinterpret_cast<uint2*>(smem + P.pyr_src_bytes);   // [nsy][32] 4 x u16 per thread column
+  // ---- source window -> smem
+  {
+    const uint8_t* src = roi_ptr(P, S, f) + (long long)t.sy0 * S.pitch + t.sx0;   // sx0 is a multiple of 4
+    const int nwords = t.nsy * t.sw4;
+    uint32_t* d = reinterpret_cast<uint32_t*>(s_src);
+    for (int i = threadIdx.x; i < nwords; i += 256) {
+      const int r = i / t.sw4, c = i - r * t.sw4;
+      d[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (long long)r * S.pitch) + c);
+    }
+  }
+  // ---- this thread's 4 destination columns
   const int groups = (L.w + 40 + 3) >> 2;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y * blockDim.y + threadIdx.y;
-  const int f = blockIdx.z;
-  if (g >= groups || by >= L.rows) return;
-  const uint2 ty = __ldg(P.rtab + L.ytab_off + reflect101(by - kEdge, L.h));
-  const uint8_t* sroi = roi_ptr(P, S, f);
-  const uint8_t* s0 = sroi + (long long)(ty.x & 0xFFFF) * S.pitch;
-  const uint8_t* s1 = sroi + (long long)(ty.x >> 16) * S.pitch;
-  const int b0 = (int)(ty.y & 0xFFFF), b1 = (int)(ty.y >> 16);
-  const int bx = 4 * g - 20;
-  uint8_t o[4];
+  const int g = t.g0 + tx;
+  const bool col_ok = g < groups;
+  int i0[4], i1[4], c0[4], c1[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const uint2 tx = __ldg(P.rtab + L.xtab_off + reflect101(bx + k, L.w));
-    const int i0 = tx.x & 0xFFFF, i1 = tx.x >> 16;
-    const int c0 = (int)(tx.y & 0xFFFF), c1 = (int)(tx.y >> 16);
-    const int r0 = s0[i0] * c0 + s0[i1] * c1;
-    const int r1 = s1[i0] * c0 + s1[i1] * c1;
-    o[k] = (uint8_t)((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2);
+    const uint2 e = __ldg(P.rtab + L.xtab_off + reflect101(4 * g - 20 + k, L.w));
+    i0[k] = (int)(e.x & 0xFFFF) - t.sx0; i1[k] = (int)(e.x >> 16) - t.sx0;
+    c0[k] = (int)(e.y & 0xFFFF); c1[k] = (int)(e.y >> 16);
+    if (!col_ok) { i0[k] = 0; i1[k] = 0; }
   }
-  uint8_t* d = P.pyr + L.img_off + (long long)f * L.img_fstride + (long long)by * L.pitch + (kXOff - 20) + 4 * g;
-  *reinterpret_cast<uchar4*>(d) = make_uchar4(o[0], o[1], o[2], o[3]);
+  __syncthreads();
+  // ---- horizontal pass: one source row at a time
+  for (int r = ty; r < t.nsy; r += 8) {
+    const uint8_t* row = s_src + r * SW;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (uint32_t)(row[i0[k]] * c0[k] + row[i1[k]] * c1[k]) >> 4;
+    s_T[r * 32 + tx] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+  }
+  __syncthreads();
+  // ---- vertical pass
+  if (!col_ok) return;
+  uint8_t* dbase = P.pyr + L.img_off + (long long)f * L.img_fstride + (kXOff - 20) + 4 * g;
+#pragma unroll
+  for (int rr = 0; rr < kPyrTH / 8; ++rr) {
+    const int by = t.by0 + ty + 8 * rr;
+    if (by >= L.rows) break;
+    const uint2 e = __ldg(P.rtab + L.ytab_off + reflect101(by - kEdge, L.h));
+    const int r0 = (int)(e.x & 0xFFFF) - t.sy0, r1 = (int)(e.x >> 16) - t.sy0;
+    const int b0 = (int)(e.y & 0xFFFF), b1 = (int)(e.y >> 16);
+    const uint2 T0 = s_T[r0 * 32 + tx], T1 = s_T[r1 * 32 + tx];
+    const uint32_t o0 = (((b0 * (int)(T0.x & 0xFFFF)) >> 16) + ((b1 * (int)(T1.x & 0xFFFF)) >> 16) + 2) >> 2;
+    const uint32_t o1 = (((b0 * (int)(T0.x >> 16)) >> 16) + ((b1 * (int)(T1.x >> 16)) >> 16) + 2) >> 2;
+    const uint32_t o2 = (((b0 * (int)(T0.y & 0xFFFF)) >> 16) + ((b1 * (int)(T1.y & 0xFFFF)) >> 16) + 2) >> 2;
+    const uint32_t o3 = (((b0 * (int)(T0.y >> 16)) >> 16) + ((b1 * (int)(T1.y >> 16)) >> 16) + 2) >> 2;
+    *reinterpret_cast<uint32_t*>(dbase + (long long)by * L.pitch) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+  }
 }
 
 // ------------------------------------------------------------------ K2 FAST
@@ -703,11 +749,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 static const int kDescWarps = 8;
+static const int kPatchRows = 2 * kEdge + 1, kPatchW4 = 11;   // 39 rows x 44 bytes (39 columns + alignment slack)
 __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp) {
   // rBRIEF pattern in shared memory, one word (x0,y0,x1,y1 as int8) per test, laid out so
   // that lane j's t-th test sits at word t*32 + j (conflict-free); constant memory would
   // serialise the lane-divergent index
   __shared__ uint32_t s_pat[256];
+  __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchW4];
   const OrbDev& P = *Pp;
   const int level = blockIdx.y, f = blockIdx.z;
   const LevelDev& L = P.lv[level];
@@ -739,13 +787,15 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   const int vmax = (lane < 31) ? c_umax[abs(u)] : -1;
   {
     int sum = 0;
+    const uint8_t* ip = img + u - kHalfPatch * L.pitch;
 #pragma unroll
     for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
       if (abs(v) <= vmax) {
-        const int val = img[v * L.pitch + u];
+        const int val = *ip;
         sum += val;
         m01 += v * val;
       }
+      ip += L.pitch;
     }
     m10 = u * sum;
   }
@@ -764,8 +814,24 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   angle = __shfl_sync(0xFFFFFFFFu, angle, 0);
   a = __shfl_sync(0xFFFFFFFFu, a, 0);
   b = __shfl_sync(0xFFFFFFFFu, b, 0);
-  // ---- rBRIEF: lane j computes descriptor byte j (8 tests)
-  const uint8_t* bl = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)cy * L.bpitch + cx;
+  // ---- rBRIEF: lane j computes descriptor byte j (8 tests).  The 39x39 blurred patch around
+  // the keypoint (|rotated pattern coordinate| <= 18 < EDGE_THRESHOLD) is staged in shared
+  // memory with aligned word loads; the 512 steered samples are then shared-memory gathers.
+  uint32_t* patch = s_patch[wid];
+  const int xb = (cx - kEdge) & ~3, ox = (cx - kEdge) - xb;
+  {
+    const uint8_t* bsrc = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)(cy - kEdge) * L.bpitch + xb;
+#pragma unroll
+    for (int k = 0; k < (kPatchRows * kPatchW4 + 31) / 32; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < kPatchRows * kPatchW4) {
+        const int r = idx / kPatchW4, wc = idx - r * kPatchW4;
+        patch[idx] = __ldg(reinterpret_cast<const uint32_t*>(bsrc + r * L.bpitch) + wc);
+      }
+    }
+  }
+  __syncwarp();
+  const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch) + kEdge * (kPatchW4 * 4) + ox + kEdge;   // patch centre
   int val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -776,7 +842,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
     const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = bl[r0 * L.bpitch + c0], t1 = bl[r1 * L.bpitch + c1];
+    const int t0 = pc[r0 * (kPatchW4 * 4) + c0], t1 = pc[r1 * (kPatchW4 * 4) + c1];
     val |= (t0 < t1) << j;
   }
   const int o = base + i;
@@ -820,7 +886,7 @@ struct drfe_orb {
   uint8_t* d_gray = nullptr;   // staging for host inputs [B][H][W]
   void* d_rtab = nullptr; void* d_strips = nullptr;
   int nstrips = 0, blur_blocks = 0, max_node_cap = 0, max_lkp = 0;
-  size_t fast_smem = 0, quad_smem = 0;
+  size_t fast_smem = 0, quad_smem = 0, pyr_smem = 0;
   int last_frames = 0;
   bool pending = false;
   StageTimer timer;
@@ -887,6 +953,8 @@ static int orb_build(drfe_orb* h) {
   memset(&D, 0, sizeof(D));
   D.nlevels = nl; D.B = h->max_batch; D.ini_th = pr.ini_th_fast; D.min_th = pr.min_th_fast;
   std::vector<uint2> rtab;
+  std::vector<PyrTile> ptiles;
+  int max_pyr_src = 0, max_pyr_nsy = 0;
   std::vector<StripDev> strips;
   long long img_total = 0, blur_total = 0, cand_total = 0;
   int lkp_total = 0, kp_cap = 0, max_strip_rows = 0;
@@ -925,6 +993,30 @@ static int orb_build(drfe_orb* h) {
     if (l > 0) {
       L.xtab_off = (long long)rtab.size(); make_resize_tab(D.lv[l - 1].w, L.w, rtab);
       L.ytab_off = (long long)rtab.size(); make_resize_tab(D.lv[l - 1].h, L.h, rtab);
+      // k_pyr_resize tiles and their source windows
+      const int groups = (L.w + 40 + 3) / 4;
+      L.ptile_off = (int)ptiles.size();
+      L.ptile_gx = (groups + 31) / 32;
+      auto refl = [](int i, int n) { if (i < 0) i = -i; if (i >= n) i = 2 * (n - 1) - i; return i; };
+      for (int by0 = 0; by0 < L.rows; by0 += kPyrTH)
+        for (int g0 = 0; g0 < groups; g0 += kPyrTW / 4) {
+          int sx0 = 1 << 30, sx1 = -1, sy0 = 1 << 30, sy1 = -1;
+          for (int g = g0; g < std::min(g0 + kPyrTW / 4, groups); ++g)
+            for (int k = 0; k < 4; ++k) {
+              const uint2 e = rtab[L.xtab_off + refl(4 * g - 20 + k, L.w)];
+              sx0 = std::min(sx0, (int)(e.x & 0xFFFF)); sx1 = std::max(sx1, (int)(e.x >> 16));
+            }
+          for (int by = by0; by < std::min(by0 + kPyrTH, L.rows); ++by) {
+            const uint2 e = rtab[L.ytab_off + refl(by - kEdge, L.h)];
+            sy0 = std::min(sy0, (int)(e.x & 0xFFFF)); sy1 = std::max(sy1, (int)(e.x >> 16));
+          }
+          sx0 &= ~3;
+          const int sw4 = (sx1 - sx0) / 4 + 1, nsy = sy1 - sy0 + 1;
+          ptiles.push_back(PyrTile{(short)g0, (short)by0, (short)sx0, (short)sw4, (short)sy0, (short)nsy, 0, 0});
+          max_pyr_src = std::max(max_pyr_src, sw4 * 4 * nsy);
+          max_pyr_nsy = std::max(max_pyr_nsy, nsy);
+        }
+      L.ptile_cnt = (int)ptiles.size() - L.ptile_off;
     }
     // FAST strips: the interior rows [19 + i*hCell, min(19 + (i+1)*hCell, h-19)) of cell row i.
     // Cell (i, j) of the reference's grid (:789-829) evaluates FAST exactly on the pixels
@@ -972,8 +1064,13 @@ static int orb_build(drfe_orb* h) {
   if (dev_alloc(h, &D.out_cnt, (size_t)B)) return DRFE_ERR_CUDA;
   if (dev_alloc(h, &D.status, 1)) return DRFE_ERR_CUDA;
   if (dev_alloc(h, &h->d_gray, (size_t)B * h->width * h->height)) return DRFE_ERR_CUDA;
-  uint2* d_rtab; StripDev* d_strips;
+  uint2* d_rtab; StripDev* d_strips; PyrTile* d_ptiles;
   if (dev_alloc(h, &d_rtab, rtab.size())) return DRFE_ERR_CUDA;
+  if (dev_alloc(h, &d_ptiles, ptiles.size())) return DRFE_ERR_CUDA;
+  DRFE_CUDA(cudaMemcpy(d_ptiles, ptiles.data(), ptiles.size() * sizeof(PyrTile), cudaMemcpyHostToDevice));
+  D.ptiles = d_ptiles;
+  D.pyr_src_bytes = (max_pyr_src + 15) / 16 * 16;
+  h->pyr_smem = (size_t)D.pyr_src_bytes + (size_t)max_pyr_nsy * 32 * sizeof(uint2);
   if (dev_alloc(h, &d_strips, strips.size())) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(d_rtab, rtab.data(), rtab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
   DRFE_CUDA(cudaMemcpy(d_strips, strips.data(), strips.size() * sizeof(StripDev), cudaMemcpyHostToDevice));
@@ -1093,8 +1190,7 @@ int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_s
   }
   for (int l = 1; l < nl; ++l) {
     const LevelDev& L = D.lv[l];
-    dim3 blk(64, 4), grd(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, nframes);
-    DRFE_LAUNCH(k_pyr_resize, grd, blk, 0, st, h->dd, l);
+    DRFE_LAUNCH(k_pyr_resize, dim3(L.ptile_cnt, nframes), 256, h->pyr_smem, st, h->dd, l);
   }
   h->timer.mark("pyramid", st);
   DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, nframes), 256, h->fast_smem, st, h->dd);
