@@ -36,6 +36,7 @@ struct CapeDev {
   int* plane_map;               // [B][ncells]
   uint8_t* eroded_map;          // [B][ncells]
   uint32_t* border_vec;         // [B][kMaxPlanes+1][ceil(ncells/32)] bit c of row p: cell c is in mask_diff of final plane p (1-based)
+  long long* dbg;               // [B][16] k_cape_grid counters/cycles (diagnostics, may be null)
   int grid_sums_smem;           // k_cape_grid keeps the cells' moment sums in shared memory
   drfe_plane* segs;             // [B][kMaxPlanes+1] scratch: plane_segments
   drfe_plane* planes;           // [B][kMaxPlanes]   plane_segments_final
@@ -153,12 +154,13 @@ __device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, 
 // correctly rounded quotient q, so float(q') == float(q) unless a float rounding midpoint
 // (double mantissa bits 28..0 == 0x10000000) lies within a few ulps of q', or the result is
 // outside the float normal range — those rare cases take the exact division.
+__device__ __noinline__ float div_exact_to_float(double t, double den) { return (float)(t / den); }
 __device__ __forceinline__ float div_to_float(double t, double den, double rden) {
   const double q = t * rden;
   const uint32_t lo = (uint32_t)__double2loint(q), ex = ((uint32_t)__double2hiint(q) >> 20) & 0x7FFu;
   const bool near_mid = ((lo & 0x1FFFFFFFu) - 0x0FFFFFFCu) <= 8u;
   const bool odd_range = (ex - 898u > 251u) && q != 0.0;
-  if (near_mid || odd_range) return (float)(t / den);
+  if (near_mid || odd_range) return div_exact_to_float(t, den);   // rare: kept out of line
   return (float)q;
 }
 
@@ -169,7 +171,9 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
   const CapeDev& P = *Pp;
   const int gid = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;   // global cell index over the batch
   const int l = threadIdx.x & 15;
-  const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+  // full-warp mask: both 16-lane groups of a warp run the same shuffles (width 16); a group that
+  // exited above is simply absent.  (A per-group runtime mask makes the compiler serialise them.)
+  const unsigned mask = 0xFFFFFFFFu;
   if (gid >= nframes * P.ncells) return;                    // whole 16-lane groups exit together
   const int f = gid / P.ncells, cell = gid - f * P.ncells;
   const int npc = P.npc, cw = P.cw;
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
   const double fx = (double)P.fx, fy = (double)P.fy, pcx = (double)P.cx, pcy = (double)P.cy;
   const double rfx = 1.0 / fx, rfy = 1.0 / fy;
   int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
+  const int step_r = 16 / cw, step_c = 16 - step_r * cw;    // element i + 16
   for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
     float vz[kSumsChunk], vx[kSumsChunk], vy[kSumsChunk];
     {
@@ -202,8 +207,8 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
           if (FROM_DEPTH) vz[u] = __ldg(dsrc + (long long)r2 * P.depth_rs + c2);
           else { vx[u] = CX[i]; vy[u] = CY[i]; vz[u] = CZ[i]; }
         }
-        c2 += 16;
-        while (c2 >= cw) { c2 -= cw; ++r2; }
+        c2 += step_c; r2 += step_r;
+        if (c2 >= cw) { c2 -= cw; ++r2; }
       }
     }
 #pragma unroll
@@ -231,8 +236,8 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
           ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
         }
       }
-      lc += 16;
-      while (lc >= cw) { lc -= cw; ++lr; }
+      lc += step_c; lr += step_r;
+      if (lc >= cw) { lc -= cw; ++lr; }
     }
   }
 #pragma unroll
@@ -438,7 +443,10 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   __syncthreads();
 
   // ---- seeded region growing (CAPE.cpp:114-218), warp 0
+  long long t_setup = clock64();
   if (wid == 0) {
+    long long c_arg = 0, c_scan = 0, c_bfs = 0, c_acc = 0, c_fit = 0, n_seeds = 0, n_bfs = 0, s_ncand = 0, s_nact = 0, tt = clock64();
+#define DRFE_TICK(acc) { const long long now = clock64(); acc += now - tt; tt = now; }
     int remaining = 0;
     for (int w = lane; w < nw; w += 32) remaining += __popc(U[w]);
 #pragma unroll
@@ -469,6 +477,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
         }
       }
       __syncwarp();
+      DRFE_TICK(c_arg) ++n_seeds; s_ncand += ncand;
       // seed = candidate with the smallest MSE, with the reference's stray index (:125-132):
       // the running minimum is refreshed from Grid[i] (loop counter), not Grid[candidate].
       int seed = 0;
@@ -482,6 +491,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
         }
       }
       seed = __shfl_sync(0xFFFFFFFFu, seed, 0);
+      DRFE_TICK(c_scan)
       // RegionGrowing from the seed with its own plane (:142)
       const drfe_plane& sd = cells[seed];
       bool seed_ok;
@@ -508,8 +518,10 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
         }
         __syncwarp();
         { uint32_t* t = cur; cur = nxt; nxt = t; }
+        ++n_bfs;
         if (!__any_sync(0xFFFFFFFFu, changed)) break;
       }
+      DRFE_TICK(c_bfs)
       // ---- accumulate: new_ps = *Grid[seed], then expandSegment(Grid[i]) for every activated i in
       // ascending order (the seed is counted twice, :134,146-149); lanes 0..8 own one sum each
       int nact = 0;
@@ -548,6 +560,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
       }
       remaining -= nact;
       __syncwarp();
+      DRFE_TICK(c_acc) s_nact += nact;
       if (nact < 4) continue;                                // Checkpoint 2 (:157)
       int label = 0;
       if (lane == 0) {
@@ -570,8 +583,15 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
         }
       }
       __syncwarp();
+      DRFE_TICK(c_fit)
     }
     if (lane == 0) s_np = np;
+    if (lane == 0 && P.dbg) {
+      long long* d = P.dbg + (long long)f * 16;
+      d[0] = n_seeds; d[1] = n_bfs; d[2] = s_ncand; d[3] = s_nact; d[4] = c_arg; d[5] = c_scan; d[6] = c_bfs; d[7] = c_acc; d[8] = c_fit;
+      d[9] = t_setup;
+    }
+#undef DRFE_TICK
   }
   __syncthreads();
   // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
@@ -659,6 +679,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   int* plane_map = P.plane_map + (long long)f * nc;
   for (int c = tid; c < nc; c += THREADS) plane_map[c] = pmap[c];
   if (tid == 0) P.nplanes[f] = nfinal;
+  if (tid == 0 && P.dbg) { long long* d = P.dbg + (long long)f * 16; d[10] = clock64(); }
 }
 
 // ------------------------------------------------------------------ refinement + output
@@ -802,6 +823,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.cells, nc * B);
   rc |= cape_alloc(h, &D.tols, nc * B);
   rc |= cape_alloc(h, &D.sums, nc * B);
+  rc |= cape_alloc(h, &D.dbg, 16 * B);
   rc |= cape_alloc(h, &D.plane_map, nc * B);
   rc |= cape_alloc(h, &D.eroded_map, nc * B);
   rc |= cape_alloc(h, &D.border_vec, (size_t)(kMaxPlanes + 1) * ((nc + 31) / 32) * B);
@@ -1010,6 +1032,14 @@ int drfe_cape_get_cells(drfe_cape* h, int frame, drfe_plane* cells) {
   DeviceScope ds(h->device);
   DRFE_CUDA(cudaStreamSynchronize(h->stream));
   DRFE_CUDA(cudaMemcpy(cells, h->hd.cells + (size_t)h->hd.ncells * frame, (size_t)h->hd.ncells * sizeof(drfe_plane), cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16) {
+  int rc = cape_frame_ok(h, frame);
+  if (rc) return rc;
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  DRFE_CUDA(cudaMemcpy(out16, h->hd.dbg + 16 * frame, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return DRFE_OK;
 }
 int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t* eroded_map) {

@@ -46,6 +46,7 @@ struct LevelDev {
   int nfeat, nIni;
   int blur_nq;                      // 4-pixel columns of the blur kernel, ceil(w/4)
   uint32_t blur_magic;              // ceil(2^32 / blur_nq)
+  uint32_t wcell_magic;             // ceil(2^32 / wCell): interior x -> cell column by __umulhi
   uint32_t quads_magic;             // ceil(2^32 / quads), quads = ceil((w-38)/4): task -> row by __umulhi
   float hX;
   int root_x[5];                    // root boundaries int(hX*i), i = 0..nIni (nIni <= 4)
@@ -351,12 +352,18 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   // on u16x2 pairs (the score map is dense at minThFAST on textured frames)
   const int e_ini = P.ini_th + 1 - P.min_th;
   const int list_cap = (TP * (P.fast_rows + 6)) >> 2;
-  for (int task = tid; task < ntask; task += THREADS) {
+  const int lane = tid & 31;
+  for (int task0 = tid - lane; task0 < ntask; task0 += THREADS) {
+    const int task = task0 + lane;
+    uint32_t surv = 0, sc0 = 0;
+    int sry = 0, sg = 0;
+    if (task < ntask) {
     const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
     const int g = task - ry * quads;
+    sry = ry; sg = g;
     const uint32_t* sp = score32 + (ry + 1) * TP4 + g + 1;
     const uint32_t c0 = sp[0];
-    if (c0 == 0) continue;
+    if (c0 != 0) {
     const uint32_t u0 = sp[-TP4 - 1], u1 = sp[-TP4], u2 = sp[-TP4 + 1];
     const uint32_t m0 = sp[-1], m2 = sp[1];
     const uint32_t d0 = sp[TP4 - 1], d1 = sp[TP4], d2 = sp[TP4 + 1];
@@ -375,25 +382,40 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       const uint32_t c = __byte_perm(c0, 0, sel);
       t[par] = c - __vminu2(c, nb);                          // per half: > 0 <=> strict maximum
     }
-    if ((t[0] | t[1]) == 0) continue;
+    // pack the 4 survivor flags; appended below by the whole warp
+    surv = ((t[0] & 0xFFFFu) ? 1u : 0u) | ((t[1] & 0xFFFFu) ? 2u : 0u) | ((t[0] >> 16) ? 4u : 0u) | ((t[1] >> 16) ? 8u : 0u);
+    sc0 = c0;
+    }  // c0 != 0
+    }  // task < ntask
+    // warp-aggregated append: one shared-memory atomic per warp and pixel slot
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (((t[k & 1] >> (16 * (k >> 1))) & 0xFFFF) == 0) continue;
-      const int e = (c0 >> (8 * k)) & 0xFF;
-      const int x = 4 * g + k;
-      const int slot = atomicAdd(&s_n, 1);
-      if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | ((uint32_t)e << 24);
-      else atomicOr(P.status, 1);
-      if (e >= e_ini) atomicAdd(&s_ini[x / wCell], 1);
+      const bool on = (surv >> k) & 1u;
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, on);
+      if (bal == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (on) {
+        const int slot = base + __popc(bal & ((1u << lane) - 1));
+        const uint32_t e = (sc0 >> (8 * k)) & 0xFF;
+        if (slot < list_cap) list[slot] = (uint32_t)(4 * sg + k) | ((uint32_t)sry << 12) | (e << 24);
+        else atomicOr(P.status, 1);
+      }
     }
   }
   __syncthreads();
-  // ---- 4. emit (region coordinates: origin (16,16) => interior x + 3)
+  // per-cell count of survivors at iniThFAST (does FAST(iniThFAST) find anything in the cell?)
   const int n = min(s_n, list_cap);
+  for (int i = tid; i < n; i += THREADS) {
+    const uint32_t ent = list[i];
+    if ((int)(ent >> 24) >= e_ini) atomicAdd(&s_ini[__umulhi(ent & 0xFFFu, L.wcell_magic)], 1);
+  }
+  __syncthreads();
+  // ---- 4. emit (region coordinates: origin (16,16) => interior x + 3)
   int* cnt = P.cand_cnt + f * P.nlevels + strip.level;
   uint32_t* out = P.cand + (long long)f * P.cand_fstride + L.cand_off;
   const int oy = strip.y0 - kEdge + 3;
-  const int lane = tid & 31;
   for (int i0 = tid - lane; i0 < n; i0 += THREADS) {
     const int i = i0 + lane;
     uint32_t ent = 0;
@@ -401,7 +423,7 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     if (i < n) {
       ent = list[i];
       const int e = ent >> 24;
-      keep = e >= e_ini || s_ini[(int)(ent & 0xFFF) / wCell] == 0;
+      keep = e >= e_ini || s_ini[__umulhi(ent & 0xFFFu, L.wcell_magic)] == 0;
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
     if (bal == 0) continue;
@@ -1031,6 +1053,7 @@ static int orb_build(drfe_orb* h) {
     {
       const unsigned quads = (unsigned)((L.w - 2 * kEdge + 3) / 4);
       L.quads_magic = (uint32_t)(((1ull << 32) + quads - 1) / quads);
+      L.wcell_magic = (uint32_t)(((1ull << 32) + L.wCell - 1) / L.wCell);
     }
     L.blur_nq = (L.w + 3) / 4;
     L.blur_magic = (uint32_t)(((1ull << 32) + L.blur_nq - 1) / L.blur_nq);

@@ -63,7 +63,7 @@ SYMBOLS = [
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
-    "drfe_cape_get_grid_maps", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
+    "drfe_cape_get_grid_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def lib():
     L.drfe_cape_get_cloud.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_get_cells.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_get_grid_maps.argtypes = [vp, C.c_int, vp, vp]
+    L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
     L.drfe_cape_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
     L.drfe_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_float, vp, vp, vp, vp, vp, vp]
@@ -407,6 +408,11 @@ class CAPE:
 
     def stream(self):
         return self.L.drfe_cape_stream(self.h)
+
+    def debug_counters(self, frame=0):
+        out = np.zeros(16, np.int64)
+        _check(self.L.drfe_cape_debug_counters(self.h, frame, _ptr(out)))
+        return out
 
     def set_profiling(self, on=True):
         _check(self.L.drfe_cape_set_profiling(self.h, int(on)))

@@ -203,6 +203,10 @@ int drfe_cape_get_cloud(drfe_cape* h, int frame, float* cloud_cellmajor);
 int drfe_cape_get_cells(drfe_cape* h, int frame, drfe_plane* cells);
 /* grid_plane_seg_map after region growing + the eroded map used for painting */
 int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t* eroded_map);
+/* diagnostics of the grid stage of one frame: [0] seeds, [1] growth sweeps, [2] sum of candidates,
+ * [3] sum of activated cells, [4..8] cycles in bin search+list / seed scan / growth / accumulate /
+ * fit+label, [9] clock after set-up, [10] clock at the end */
+int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16);
 int drfe_cape_set_profiling(drfe_cape* h, int on);
 int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages);
 

@@ -15,7 +15,7 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    lines, cur_file, hdr = [], None, None
+    agg, cur_file, hdr = {}, None, None
     tot_s = tot_i = 0
     for r in rows:
         if not r:
@@ -29,10 +29,16 @@ def main():
                 s, i = int(r[6] or 0), int(r[7] or 0)
             except ValueError:
                 continue
-            lines.append((s, i, cur_file, int(r[0]), r[1].strip()))
+            key = (cur_file, int(r[0]))
+            if key in agg:
+                agg[key][0] += s
+                agg[key][1] += i
+            else:
+                agg[key] = [s, i, r[1].strip()]
             tot_s += s
             tot_i += i
-    print("kernel %s: %d samples, %d warp instructions (first matching launch(es))" % (kern, tot_s, tot_i))
+    print("kernel %s: %d samples, %d warp instructions (all matching launches summed)" % (kern, tot_s, tot_i))
+    lines = [(v[0], v[1], k[0], k[1], v[2]) for k, v in agg.items()]
     for s, i, f, ln, src in sorted(lines, reverse=True)[:top]:
         print("%5.1f%% smp %5.1f%% inst  %s:%-4d %s" % (100.0 * s / max(tot_s, 1), 100.0 * i / max(tot_i, 1), f, ln, src[:110]))
 

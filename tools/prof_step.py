@@ -61,6 +61,10 @@ def main():
         cape.sync()
         res.update(dict(cape.stage_times()))
         print("planes/frame: mean %.2f" % cape.download()[2].mean())
+        dbg = np.stack([cape.debug_counters(i) for i in range(min(B, 32))])
+        names = ["seeds", "sweeps", "sum_ncand", "sum_nact", "cyc_argmax_list", "cyc_scan", "cyc_grow", "cyc_accum", "cyc_fit"]
+        print("grid stage per frame (mean over %d frames): " % len(dbg) + ", ".join("%s %.0f" % (n, dbg[:, i].mean()) for i, n in enumerate(names)) +
+              ", cyc_tail %.0f" % (dbg[:, 10] - dbg[:, 9] - dbg[:, 4:9].sum(1)).mean())
     tot = sum(res.values())
     print("stage ms per %d-frame batch (serialised): " % B + ", ".join("%s %.3f" % kv for kv in res.items()) +
           " | total %.3f ms => %.0f frames/s" % (tot, B / tot * 1e3))
