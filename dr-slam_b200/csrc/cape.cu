@@ -36,6 +36,9 @@ struct CapeDev {
   int* plane_map;               // [B][ncells]
   uint8_t* eroded_map;          // [B][ncells]
   uint32_t* border_vec;         // [B][kMaxPlanes+1][ceil(ncells/32)] bit c of row p: cell c is in mask_diff of final plane p (1-based)
+  double* jobacc;               // [B][max_jobs][10] accumulated sums + point count of each grown region
+  drfe_plane* jobseg;           // [B][max_jobs] fitted region of each job
+  int max_jobs;                 // regions of >= 4 cells a frame can have: ncells/4 + 1
   long long* dbg;               // [B][16] k_cape_grid counters/cycles (diagnostics, may be null)
   int grid_sums_smem;           // k_cape_grid keeps the cells' moment sums in shared memory
   drfe_plane* segs;             // [B][kMaxPlanes+1] scratch: plane_segments
@@ -368,10 +371,12 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   float* mse = reinterpret_cast<float*>(npts + nc);               // [nc]
   float* sums = mse + nc;                                         // [nc][9] cell moment sums (floats, exact) if they fit
   short* bin = reinterpret_cast<short*>(sums + (P.grid_sums_smem ? 9 * nc : 0));   // [nc] histogram bin (-1: none)
-  uint8_t* pmap = reinterpret_cast<uint8_t*>(bin + nc);           // [nc] grid_plane_seg_map (labels 1..255)
+  unsigned short* jobid = reinterpret_cast<unsigned short*>(bin + nc);   // [nc] job of each grown cell (0xFFFF: none)
+  short* job_seed = reinterpret_cast<short*>(jobid + nc);         // [max_jobs] seed cell of each job
+  uint8_t* pmap = reinterpret_cast<uint8_t*>(job_seed + P.max_jobs);   // [nc] grid_plane_seg_map (labels 1..255)
+  uint8_t* job_label = pmap + nc;                                 // [max_jobs] 0 / plane label of the job
   __shared__ int merge[kMaxPlanes + 1];
-  __shared__ double s_acc[9];
-  __shared__ int s_np, s_accn;
+  __shared__ int s_np, s_njobs;
   uint32_t* FL = bv + BV_FL * nw; uint32_t* FR = bv + BV_FR * nw; uint32_t* FU = bv + BV_FU * nw; uint32_t* FD = bv + BV_FD * nw;
   uint32_t* U = bv + BV_U * nw; uint32_t* A = bv + BV_A * nw; uint32_t* Bv = bv + BV_B * nw;
   uint32_t* M = bv + BV_M * nw; uint32_t* Hh = bv + BV_H * nw;
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   drfe_plane* segs = P.segs + (long long)f * (kMaxPlanes + 1);
   for (int i = tid; i < kHistBins * kHistBins; i += THREADS) hist[i] = 0;
   for (int i = tid; i < 256 * 8; i += THREADS) assoc[i] = 0;
-  if (tid == 0) s_np = 0;
+  if (tid == 0) { s_np = 0; s_njobs = 0; }
   __syncthreads();
   // ---- per-cell set-up: histogram bin (CAPE.cpp:82-101, Histogram.cpp:15-43), edge masks
   const double min_cos = (double)P.min_cos;
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
       mse[c] = g.MSE;
       npts[c] = g.nr_pts;
       pmap[c] = 0;
+      jobid[c] = 0xFFFF;
       if (P.grid_sums_smem) {
         const double* sp = &g.x_acc;
 #pragma unroll
@@ -442,16 +448,24 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   }
   __syncthreads();
 
-  // ---- seeded region growing (CAPE.cpp:114-218), warp 0
+  // ---- seeded region growing (CAPE.cpp:114-218).  Warp 0 runs the sequential part: pick the
+  // seed, grow the region, take its cells out of the histogram.  What happens to a grown region
+  // afterwards (accumulate its cells' sums, fit, score > 100 ?) does not influence the following
+  // seeds, so it is recorded as a "job" (jobid[c] = job of cell c) and all jobs are
+  // accumulated and fitted in parallel after the loop; labels are then handed out in job order.
   long long t_setup = clock64();
   if (wid == 0) {
-    long long c_arg = 0, c_scan = 0, c_bfs = 0, c_acc = 0, c_fit = 0, n_seeds = 0, n_bfs = 0, s_ncand = 0, s_nact = 0, tt = clock64();
+    long long c_arg = 0, c_scan = 0, c_bfs = 0, c_acc = 0, n_seeds = 0, n_bfs = 0, s_ncand = 0, s_nact = 0, tt = clock64();
 #define DRFE_TICK(acc) { const long long now = clock64(); acc += now - tt; tt = now; }
     int remaining = 0;
     for (int w = lane; w < nw; w += 32) remaining += __popc(U[w]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) remaining += __shfl_xor_sync(0xFFFFFFFFu, remaining, o);
-    int np = 0;
+    int njobs = 0;
+    const bool one_word = nw <= 32;          // the whole grid fits one word per lane: grow in registers
+    const int qsh = ncx >> 5, rsh = ncx & 31;
+    const uint32_t r_fl = (one_word && lane < nw) ? FL[lane] : 0u, r_fr = (one_word && lane < nw) ? FR[lane] : 0u,
+                   r_fu = (one_word && lane < nw) ? FU[lane] : 0u, r_fd = (one_word && lane < nw) ? FD[lane] : 0u;
     for (int guard = 0; remaining > 0 && guard <= nc; ++guard) {
       // most frequent bin, first maximum wins (Histogram.cpp:49-55)
       unsigned best = 0;
@@ -480,12 +494,23 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
       DRFE_TICK(c_arg) ++n_seeds; s_ncand += ncand;
       // seed = candidate with the smallest MSE, with the reference's stray index (:125-132):
       // the running minimum is refreshed from Grid[i] (loop counter), not Grid[candidate].
+      // Both MSE values of a step are independent of the running state, so they are fetched
+      // ahead (4 steps at a time); only the compare/select is sequential.
       int seed = 0;
       if (lane == 0) {
         seed = list[0];
         float min_mse = (float)2147483647;
-#pragma unroll 4
-        for (int i = 0; i < ncand; ++i) {
+        int i = 0;
+        for (; i + 4 <= ncand; i += 4) {
+          const int c0 = list[i], c1 = list[i + 1], c2 = list[i + 2], c3 = list[i + 3];
+          const float a0 = mse[c0], a1 = mse[c1], a2 = mse[c2], a3 = mse[c3];
+          const float b0 = mse[i], b1 = mse[i + 1], b2 = mse[i + 2], b3 = mse[i + 3];
+          if (a0 < min_mse) { seed = c0; min_mse = b0; }
+          if (a1 < min_mse) { seed = c1; min_mse = b1; }
+          if (a2 < min_mse) { seed = c2; min_mse = b2; }
+          if (a3 < min_mse) { seed = c3; min_mse = b3; }
+        }
+        for (; i < ncand; ++i) {
           const int c = list[i];
           if (mse[c] < min_mse) { seed = c; min_mse = mse[i]; }
         }
@@ -502,52 +527,64 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
                     dist * dist > (double)tols[seed]);
       }
       if (!seed_ok) { if (lane == 0) atomicOr(P.status, 2); break; }   // the reference would never terminate here
-      uint32_t* cur = A; uint32_t* nxt = Bv;
-      for (int w = lane; w < nw; w += 32) cur[w] = (w == (seed >> 5)) ? (1u << (seed & 31)) : 0u;
-      __syncwarp();
-      for (;;) {
-        bool changed = false;
-        for (int w = lane; w < nw; w += 32) {
-          const uint32_t a = cur[w], u = U[w], l = FL[w], r = FR[w];
-          uint32_t a2 = a | (((bv_shl(cur, nw, w, 1) & l) | (bv_shr(cur, nw, w, 1) & r) | (bv_shl(cur, nw, w, ncx) & FU[w]) |
-                              (bv_shr(cur, nw, w, ncx) & FD[w])) & u);
+      uint32_t* cur = A;
+      if (one_word) {
+        // one word per lane: neighbours' words by shuffle, everything else in registers
+        const uint32_t u = lane < nw ? U[lane] : 0u;
+        uint32_t a = (lane == (seed >> 5)) ? (1u << (seed & 31)) : 0u;
+        for (;;) {
+          const uint32_t up1 = __shfl_up_sync(0xFFFFFFFFu, a, 1), dn1 = __shfl_down_sync(0xFFFFFFFFu, a, 1);
+          const uint32_t p1 = lane >= 1 ? up1 : 0u, n1 = lane + 1 < 32 ? dn1 : 0u;
+          // A << ncx and A >> ncx, word granularity qsh, bit granularity rsh
+          uint32_t sl = __shfl_up_sync(0xFFFFFFFFu, a, qsh), sl2 = __shfl_up_sync(0xFFFFFFFFu, a, qsh + 1);
+          uint32_t sr = __shfl_down_sync(0xFFFFFFFFu, a, qsh), sr2 = __shfl_down_sync(0xFFFFFFFFu, a, qsh + 1);
+          if (lane < qsh) sl = 0u;
+          if (lane < qsh + 1) sl2 = 0u;
+          if (lane + qsh >= 32) sr = 0u;
+          if (lane + qsh + 1 >= 32) sr2 = 0u;
+          if (qsh == 0) { sl = a; sr = a; }
+          const uint32_t shl_n = rsh ? ((sl << rsh) | (sl2 >> (32 - rsh))) : sl;
+          const uint32_t shr_n = rsh ? ((sr >> rsh) | (sr2 << (32 - rsh))) : sr;
+          uint32_t a2 = a | (((((a << 1) | (p1 >> 31)) & r_fl) | (((a >> 1) | (n1 << 31)) & r_fr) | (shl_n & r_fu) | (shr_n & r_fd)) & u);
 #pragma unroll
-          for (int it = 0; it < 4; ++it) a2 |= (((a2 << 1) & l) | ((a2 >> 1) & r)) & u;   // in-word row closure
-          nxt[w] = a2;
-          changed |= (a2 != a);
+          for (int it = 0; it < 4; ++it) a2 |= (((a2 << 1) & r_fl) | ((a2 >> 1) & r_fr)) & u;   // in-word row closure
+          const bool changed = a2 != a;
+          a = a2;
+          ++n_bfs;
+          if (!__any_sync(0xFFFFFFFFu, changed)) break;
         }
+        if (lane < nw) cur[lane] = a;
         __syncwarp();
-        { uint32_t* t = cur; cur = nxt; nxt = t; }
-        ++n_bfs;
-        if (!__any_sync(0xFFFFFFFFu, changed)) break;
+      } else {
+        uint32_t* nxt = Bv;
+        for (int w = lane; w < nw; w += 32) cur[w] = (w == (seed >> 5)) ? (1u << (seed & 31)) : 0u;
+        __syncwarp();
+        for (;;) {
+          bool changed = false;
+          for (int w = lane; w < nw; w += 32) {
+            const uint32_t a = cur[w], u = U[w], l = FL[w], r = FR[w];
+            uint32_t a2 = a | (((bv_shl(cur, nw, w, 1) & l) | (bv_shr(cur, nw, w, 1) & r) | (bv_shl(cur, nw, w, ncx) & FU[w]) |
+                                (bv_shr(cur, nw, w, ncx) & FD[w])) & u);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) a2 |= (((a2 << 1) & l) | ((a2 >> 1) & r)) & u;   // in-word row closure
+            nxt[w] = a2;
+            changed |= (a2 != a);
+          }
+          __syncwarp();
+          { uint32_t* t = cur; cur = nxt; nxt = t; }
+          ++n_bfs;
+          if (!__any_sync(0xFFFFFFFFu, changed)) break;
+        }
       }
       DRFE_TICK(c_bfs)
-      // ---- accumulate: new_ps = *Grid[seed], then expandSegment(Grid[i]) for every activated i in
-      // ascending order (the seed is counted twice, :134,146-149); lanes 0..8 own one sum each
       int nact = 0;
       for (int w = lane; w < nw; w += 32) nact += __popc(cur[w]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) nact += __shfl_xor_sync(0xFFFFFFFFu, nact, o);
-      if (lane < 9) {
-        double acc = (&sd.x_acc)[lane];
-        for (int w = 0; w < nw; ++w) {
-          uint32_t bits = cur[w];
-          while (bits) {
-            const int c = (w << 5) + __ffs(bits) - 1;
-            bits &= bits - 1;
-            acc += P.grid_sums_smem ? (double)sums[c * 9 + lane] : (&cells[c].x_acc)[lane];
-          }
-        }
-        s_acc[lane] = acc;
-      } else if (lane == 9) {
-        int acc = sd.nr_pts;
-        for (int w = 0; w < nw; ++w) {
-          uint32_t bits = cur[w];
-          while (bits) { const int c = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; acc += npts[c]; }
-        }
-        s_accn = acc;
-      }
-      // remove the activated cells from the histogram and the unassigned mask (:150-153)
+      // remove the activated cells from the histogram and the unassigned mask (:150-153); regions
+      // of at least 4 cells (Checkpoint 2, :157) become a job
+      const bool is_job = nact >= 4;
+      if (is_job && njobs >= P.max_jobs) { if (lane == 0) atomicOr(P.status, 4); break; }
       for (int w = lane; w < nw; w += 32) {
         uint32_t bits = cur[w];
         U[w] &= ~bits;
@@ -556,42 +593,71 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
           bits &= bits - 1;
           atomicSub(&hist[bin[c]], 1);
           bin[c] = -1;
+          if (is_job) jobid[c] = (unsigned short)njobs;
         }
       }
+      if (is_job) { if (lane == 0) job_seed[njobs] = seed; ++njobs; }
       remaining -= nact;
       __syncwarp();
       DRFE_TICK(c_acc) s_nact += nact;
-      if (nact < 4) continue;                                // Checkpoint 2 (:157)
-      int label = 0;
-      if (lane == 0) {
-        drfe_plane ps = sd;
-        ps.x_acc = s_acc[0]; ps.y_acc = s_acc[1]; ps.z_acc = s_acc[2]; ps.xx_acc = s_acc[3]; ps.yy_acc = s_acc[4];
-        ps.zz_acc = s_acc[5]; ps.xy_acc = s_acc[6]; ps.xz_acc = s_acc[7]; ps.yz_acc = s_acc[8];
-        ps.nr_pts = s_accn;
-        fit_plane(ps);
-        if (ps.score > 100) {                                // it is a plane (:163)
-          if (np < kMaxPlanes) { segs[np] = ps; label = np + 1; }
-          else atomicOr(P.status, 1);
-        }
-      }
-      label = __shfl_sync(0xFFFFFFFFu, label, 0);
-      if (label > 0) {
-        np = label;
-        for (int w = lane; w < nw; w += 32) {
-          uint32_t bits = cur[w];
-          while (bits) { const int c = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; pmap[c] = (uint8_t)label; }
-        }
-      }
-      __syncwarp();
-      DRFE_TICK(c_fit)
     }
-    if (lane == 0) s_np = np;
+    if (lane == 0) s_njobs = njobs;
     if (lane == 0 && P.dbg) {
       long long* d = P.dbg + (long long)f * 16;
-      d[0] = n_seeds; d[1] = n_bfs; d[2] = s_ncand; d[3] = s_nact; d[4] = c_arg; d[5] = c_scan; d[6] = c_bfs; d[7] = c_acc; d[8] = c_fit;
-      d[9] = t_setup;
+      d[0] = n_seeds; d[1] = n_bfs; d[2] = s_ncand; d[3] = s_nact; d[4] = c_arg; d[5] = c_scan; d[6] = c_bfs; d[7] = c_acc; d[8] = 0;
+      d[9] = t_setup; d[11] = clock64();
     }
 #undef DRFE_TICK
+  }
+  __syncthreads();
+  // ---- jobs: new_ps = *Grid[seed], then expandSegment(Grid[i]) for every activated i in ascending
+  // order (the seed is counted twice, :134,146-149).  One thread per (job, sum).
+  const int njobs = s_njobs;
+  double* jobacc = P.jobacc + (long long)f * P.max_jobs * 10;
+  drfe_plane* jobseg = P.jobseg + (long long)f * P.max_jobs;
+  const bool sums_smem = P.grid_sums_smem != 0;
+  for (int t = tid; t < njobs * 10; t += THREADS) {
+    const int j = t / 10, k = t - j * 10;
+    const drfe_plane& sd = cells[job_seed[j]];
+    if (k < 9) {
+      double acc = (&sd.x_acc)[k];
+      for (int c = 0; c < nc; ++c)
+        if (jobid[c] == j) acc += sums_smem ? (double)sums[c * 9 + k] : (&cells[c].x_acc)[k];
+      jobacc[j * 10 + k] = acc;
+    } else {
+      int acc = sd.nr_pts;
+      for (int c = 0; c < nc; ++c)
+        if (jobid[c] == j) acc += npts[c];
+      jobacc[j * 10 + 9] = (double)acc;
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < njobs; j += THREADS) {
+    drfe_plane ps = cells[job_seed[j]];
+    const double* a = jobacc + j * 10;
+    ps.x_acc = a[0]; ps.y_acc = a[1]; ps.z_acc = a[2]; ps.xx_acc = a[3]; ps.yy_acc = a[4];
+    ps.zz_acc = a[5]; ps.xy_acc = a[6]; ps.xz_acc = a[7]; ps.yz_acc = a[8];
+    ps.nr_pts = (int)a[9];
+    fit_plane(ps);
+    jobseg[j] = ps;
+    job_label[j] = ps.score > 100 ? 1 : 0;                   // it is a plane (:163)
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int np = 0;
+    for (int j = 0; j < njobs; ++j) {
+      if (!job_label[j]) continue;
+      if (np < kMaxPlanes) job_label[j] = (uint8_t)(++np);
+      else { job_label[j] = 0; atomicOr(P.status, 1); }
+    }
+    s_np = np;
+  }
+  __syncthreads();
+  for (int j = tid; j < njobs; j += THREADS)
+    if (job_label[j]) segs[job_label[j] - 1] = jobseg[j];
+  for (int c = tid; c < nc; c += THREADS) {
+    const int j = jobid[c];
+    pmap[c] = (j == 0xFFFF) ? 0 : job_label[j];
   }
   __syncthreads();
   // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
@@ -824,6 +890,9 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.tols, nc * B);
   rc |= cape_alloc(h, &D.sums, nc * B);
   rc |= cape_alloc(h, &D.dbg, 16 * B);
+  D.max_jobs = (int)nc / 4 + 1;
+  rc |= cape_alloc(h, &D.jobacc, (size_t)D.max_jobs * 10 * B);
+  rc |= cape_alloc(h, &D.jobseg, (size_t)D.max_jobs * B);
   rc |= cape_alloc(h, &D.plane_map, nc * B);
   rc |= cape_alloc(h, &D.eroded_map, nc * B);
   rc |= cape_alloc(h, &D.border_vec, (size_t)(kMaxPlanes + 1) * ((nc + 31) / 32) * B);
@@ -842,7 +911,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   }
   {
     const size_t nw = (nc + 31) / 32;
-    const size_t base = (size_t)BV_COUNT * nw * 4 + kHistBins * kHistBins * 4 + 256 * 8 * 4 + nc * (4 + 4 + 4 + 2 + 1) + 64;
+    const size_t base = (size_t)BV_COUNT * nw * 4 + kHistBins * kHistBins * 4 + 256 * 8 * 4 + nc * (4 + 4 + 4 + 2 + 2 + 1) + (nc / 4 + 1) * 3 + 64;
     D.grid_sums_smem = (base + nc * 36 <= 160 * 1024) ? 1 : 0;
     h->grid_smem = base + (D.grid_sums_smem ? nc * 36 : 0);
     if (h->grid_smem > 200 * 1024 || nw > 4 * 128) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
