@@ -67,6 +67,7 @@ def algorithmic_bytes():
         "blur": 2 * P,                          # blur read + write
         "orient_describe": 749 * N + 512 * N + 60 * N,
         "cells": 4 * WH + 12 * WH + 12 * WH,    # depth read, cloud write, PlaneSeg read (fused in one kernel)
+        "fit": 768 * (48 + 156),                # per-cell sums in, PlaneSeg + tolerance out
         "grid": 0,
         "refine": WH,                           # seg_output write (border-cell re-reads are data dependent)
         "total": WH + P + P_src + P + 2 * P + 1321 * N + 29 * WH,
@@ -216,7 +217,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     threads = max(1, (os.cpu_count() or 8) // max(1, world))
-    gray, depth, K = make_sequence(drfe, rank * BATCH, BATCH, threads)
+    import shard
+    first, last = shard.weak_block(BATCH, rank)                  # this rank's own frames, no data-path collective
+    gray, depth, K = make_sequence(drfe, first, last - first, threads)
     orb = drfe.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, max_batch=BATCH, device=local_rank)
     cape = drfe.CAPE(H, W, CELL, CELL, False, MIN_COS, MAX_MERGE, max_batch=BATCH, device=local_rank)
     s_orb, s_cape = orb.stream(), cape.stream()

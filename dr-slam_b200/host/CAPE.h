@@ -1,0 +1,174 @@
+// CAPE / PlaneSeg / CylinderSeg / PlaneDetection_CAPE on the drfe C ABI — drop-in for the
+// reference's src/CAPE/CAPE.h:19-53, PlaneSeg.h:15-35, CylinderSeg.h and
+// include/PlaneExtractor.h:84-115 (src/PlaneExtractor.cpp:66-191).  Same constructor arguments,
+// same process(...) argument meaning, same public result fields.  The work runs on the GPU
+// through libdrfe.so; there is no CPU fallback (constructors throw if no device is usable).
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/drfe.h"
+#ifdef DRFE_WITH_OPENCV
+#include <opencv2/core/core.hpp>
+#endif
+#ifdef DRFE_WITH_EIGEN
+#include <Eigen/Dense>
+#endif
+#include "drfe_compat.h"
+
+// Public data members of the reference PlaneSeg (PlaneSeg.h:17-28); bool planar is stored as int
+// in the ABI struct and converted here.
+class PlaneSeg {
+ public:
+  int nr_pts = 0, min_nr_pts = 0;
+  double x_acc = 0, y_acc = 0, z_acc = 0, xx_acc = 0, yy_acc = 0, zz_acc = 0, xy_acc = 0, xz_acc = 0, yz_acc = 0;
+  float score = 0, MSE = 0;
+  bool planar = false;
+  double mean[3] = {0, 0, 0};
+  double normal[3] = {0, 0, 0};
+  double d = 0;
+  PlaneSeg() = default;
+  explicit PlaneSeg(const drfe_plane& p)
+      : nr_pts(p.nr_pts), min_nr_pts(p.min_nr_pts), x_acc(p.x_acc), y_acc(p.y_acc), z_acc(p.z_acc), xx_acc(p.xx_acc),
+        yy_acc(p.yy_acc), zz_acc(p.zz_acc), xy_acc(p.xy_acc), xz_acc(p.xz_acc), yz_acc(p.yz_acc), score(p.score),
+        MSE(p.MSE), planar(p.planar != 0), d(p.d) {
+    for (int i = 0; i < 3; ++i) { mean[i] = p.mean[i]; normal[i] = p.normal[i]; }
+  }
+};
+
+// What CAPE::process hands back per cylinder (CAPE.cpp:434-445).
+class CylinderSeg {
+ public:
+  std::vector<float> radii;
+  std::vector<double> centers;   // 3 per segment
+  double axis[3] = {0, 0, 0};
+};
+
+class CAPE {
+ public:
+#ifdef DRFE_WITH_OPENCV
+  typedef cv::Mat SegImageT;
+#else
+  typedef drfe_compat::Mat8u SegImageT;
+#endif
+  CAPE(int depth_height, int depth_width, int cell_width, int cell_height, bool cylinder_detection,
+       float min_cos_angle_4_merge = 0.97814f, float max_merge_dist = 900.f, int device = 0) {
+    prm_.depth_height = depth_height; prm_.depth_width = depth_width; prm_.cell_width = cell_width; prm_.cell_height = cell_height;
+    prm_.cylinder_detection = cylinder_detection ? 1 : 0;
+    prm_.min_cos_angle_4_merge = min_cos_angle_4_merge; prm_.max_merge_dist = max_merge_dist;
+    if (drfe_cape_create(&prm_, 1, device, &h_) != DRFE_OK) throw std::runtime_error(std::string("CAPE: ") + drfe_last_error());
+    seg_.resize((size_t)depth_height * depth_width);
+    planes_.resize(kPlaneCap);
+  }
+  ~CAPE() { drfe_cape_destroy(h_); }
+  CAPE(const CAPE&) = delete;
+  CAPE& operator=(const CAPE&) = delete;
+
+  // cloud_array: cell-major organised cloud, N x 3 column-major (what organizePointCloudByCell
+  // produces, PlaneExtractor.cpp:80-99).  Works with Eigen::MatrixXf or drfe_compat::MatrixXf.
+  // Like the reference, only labelled pixels of seg_output are written (the caller zeroes it,
+  // PlaneExtractor.cpp:129) and plane_segments_final is appended to (CAPE.cpp:279).
+  template <class MatrixT>
+  void process(MatrixT& cloud_array, int& nr_planes, int& nr_cylinders, SegImageT& seg_output,
+               std::vector<PlaneSeg>& plane_segments_final, std::vector<CylinderSeg>& cylinder_segments_final) {
+    if (drfe_cape_process(h_, cloud_array.data(), seg_.data(), planes_.data(), kPlaneCap, &nr_planes, nullptr, 0, &nr_cylinders) != DRFE_OK)
+      throw std::runtime_error(std::string("CAPE::process: ") + drfe_last_error());
+    finish(nr_planes, seg_output, plane_segments_final);
+    (void)cylinder_segments_final;
+  }
+  // fused PlaneDetection_CAPE path: depth image -> cloud (double math) -> cell-major -> process
+  void processDepth(const float* depth, size_t row_stride_elems, float fx, float fy, float cx, float cy, int& nr_planes,
+                    int& nr_cylinders, SegImageT& seg_output, std::vector<PlaneSeg>& plane_segments_final) {
+    if (drfe_cape_process_depth(h_, depth, row_stride_elems, fx, fy, cx, cy, seg_.data(), planes_.data(), kPlaneCap, &nr_planes,
+                                nullptr, 0, &nr_cylinders) != DRFE_OK)
+      throw std::runtime_error(std::string("CAPE::processDepth: ") + drfe_last_error());
+    finish(nr_planes, seg_output, plane_segments_final);
+  }
+  drfe_cape* handle() { return h_; }
+
+ private:
+  static const int kPlaneCap = 255;
+  void finish(int nr_planes, SegImageT& seg_output, std::vector<PlaneSeg>& out) {
+    for (int i = 0; i < nr_planes; ++i) out.push_back(PlaneSeg(planes_[i]));
+    const int H = prm_.depth_height, W = prm_.depth_width;
+    for (int r = 0; r < H; ++r) {
+      uint8_t* dst = seg_output.ptr(r);
+      const uint8_t* src = seg_.data() + (size_t)r * W;
+      for (int c = 0; c < W; ++c)
+        if (src[c] > 0) dst[c] = src[c];                           // CAPE.cpp:423-425
+    }
+  }
+  drfe_cape_params prm_{};
+  drfe_cape* h_ = nullptr;
+  std::vector<uint8_t> seg_;
+  std::vector<drfe_plane> planes_;
+};
+
+namespace Planar_SLAM {
+
+// PlaneDetection_CAPE (PlaneExtractor.h:84-115): readDepthImage / runPlaneDetection and the public
+// result fields.  plane_cloud (PCL) is replaced by per-plane xyz lists so that no PCL is needed.
+class PlaneDetection_CAPE {
+ public:
+  struct PointT { float x, y, z; };
+  typedef std::vector<PointT> PointCloud;
+
+  PlaneDetection_CAPE() = default;
+  ~PlaneDetection_CAPE() { delete plane_detector; }
+
+  bool readDepthImage(const drfe_compat::Mat32f& depthImg, const float K[9]) {
+    depth_img = depthImg;
+    for (int i = 0; i < 9; ++i) K_[i] = K[i];
+    return !depth_img.empty();
+  }
+
+  void runPlaneDetection() {
+    const int rows = depth_img.rows, cols = depth_img.cols;
+    seg_output.create(rows, cols);
+    seg_output.setTo(0);
+    if (!plane_detector || rows != det_rows_ || cols != det_cols_) {   // the reference news one per frame and leaks it (:149)
+      delete plane_detector;
+      plane_detector = new CAPE(rows, cols, PATCH_SIZE, PATCH_SIZE, cylinder_detection, COS_ANGLE_MAX, MAX_MERGE_DIST);
+      det_rows_ = rows; det_cols_ = cols;
+    }
+    plane_detector->processDepth(depth_img.data, depth_img.step / sizeof(float), K_[0], K_[4], K_[2], K_[5], nr_planes,
+                                 nr_cylinders, seg_output, plane_params);
+    // per-plane point lists (PlaneExtractor.cpp:165-190)
+    plane_cloud.assign(nr_planes, PointCloud());
+    for (int i = 0; i < rows; ++i) {
+      const uint8_t* s = seg_output.ptr(i);
+      const float* drow = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(depth_img.data) + (size_t)i * depth_img.step);
+      for (int j = 0; j < cols; ++j) {
+        const int code = s[j];
+        if (code > 0 && code <= nr_planes) {
+          const double z = (double)drow[j];
+          PointT p;
+          p.x = (float)(((double)j - K_[2]) * z / K_[0]);
+          p.y = (float)(((double)i - K_[5]) * z / K_[4]);
+          p.z = (float)z;
+          plane_cloud[code - 1].push_back(p);
+        }
+      }
+    }
+  }
+
+  std::vector<PointCloud> plane_cloud;
+  std::vector<PlaneSeg> plane_params;
+  std::vector<CylinderSeg> cylinder_params;
+  int nr_planes = 0, nr_cylinders = 0;
+  drfe_compat::Mat8u seg_output;
+  drfe_compat::Mat32f depth_img;
+  float K_[9] = {0};
+  int PATCH_SIZE = 20;
+  float COS_ANGLE_MAX = (float)std::cos(M_PI / 12);
+  float MAX_MERGE_DIST = 50.f;
+  bool cylinder_detection = false;
+  CAPE* plane_detector = nullptr;
+
+ private:
+  int det_rows_ = 0, det_cols_ = 0;
+};
+
+}  // namespace Planar_SLAM
