@@ -157,19 +157,23 @@ __device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, 
 // correctly rounded quotient q, so float(q') == float(q) unless a float rounding midpoint
 // (double mantissa bits 28..0 == 0x10000000) lies within a few ulps of q', or the result is
 // outside the float normal range — those rare cases take the exact division.
-__device__ __noinline__ float div_exact_to_float(double t, double den) { return (float)(t / den); }
-__device__ __forceinline__ float div_to_float(double t, double den, double rden) {
-  const double q = t * rden;
-  const uint32_t lo = (uint32_t)__double2loint(q), ex = ((uint32_t)__double2hiint(q) >> 20) & 0x7FFu;
+__device__ __noinline__ void div_exact_to_float2(double tx, double ty, double fx, double fy, float& x, float& y) {
+  x = (float)(tx / fx);
+  y = (float)(ty / fy);
+}
+// true when float(q) might differ from float(exact quotient): q within a few double ulps of a
+// float rounding midpoint, or outside the float normal range (exact zeros are fine)
+__device__ __forceinline__ bool quotient_needs_exact(double q) {
+  const uint32_t lo = (uint32_t)__double2loint(q), hi = (uint32_t)__double2hiint(q);
+  const uint32_t ex = (hi >> 20) & 0x7FFu;
   const bool near_mid = ((lo & 0x1FFFFFFFu) - 0x0FFFFFFCu) <= 8u;
-  const bool odd_range = (ex - 898u > 251u) && q != 0.0;
-  if (near_mid || odd_range) return div_exact_to_float(t, den);   // rare: kept out of line
-  return (float)q;
+  const bool odd_range = (ex - 898u > 251u) && ((hi << 1) | lo) != 0u;
+  return near_mid || odd_range;
 }
 
-static const int kSumsThreads = 128, kSumsChunk = 8;
+static const int kSumsThreads = 128, kSumsChunk = 5;
 template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __restrict__ Pp, int nframes) {
+__global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int nframes) {
   extern __shared__ __align__(16) float s_zall[];           // [8 groups][npc]
   const CapeDev& P = *Pp;
   const int gid = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;   // global cell index over the batch
@@ -177,9 +181,10 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
   // full-warp mask: both 16-lane groups of a warp run the same shuffles (width 16); a group that
   // exited above is simply absent.  (A per-group runtime mask makes the compiler serialise them.)
   const unsigned mask = 0xFFFFFFFFu;
-  if (gid >= nframes * P.ncells) return;                    // whole 16-lane groups exit together
-  const int f = gid / P.ncells, cell = gid - f * P.ncells;
-  const int npc = P.npc, cw = P.cw;
+  const int ncells = P.ncells;
+  if (gid >= nframes * ncells) return;                      // whole 16-lane groups exit together
+  const int f = gid / ncells, cell = gid - f * ncells;
+  const int npc = P.npc, cw = P.cw, ch = P.ch;
   float* s_z = s_zall + (threadIdx.x >> 4) * npc;
   const long long N = (long long)P.H * P.W;
   float* __restrict__ CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
@@ -192,44 +197,51 @@ __global__ void __launch_bounds__(kSumsThreads) k_cape_sums(const CapeDev* __res
   float ex = 0, ey = 0, ez = 0, exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;  // extra packet
   int cnt = 0;
   const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
-  const float* __restrict__ dsrc = nullptr;
-  if (FROM_DEPTH) dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;
-  const double fx = (double)P.fx, fy = (double)P.fy, pcx = (double)P.cx, pcy = (double)P.cy;
+  // ---- stage z in shared memory (it is also what the depth-jump scans read)
+  if (FROM_DEPTH) {
+    const int drs = (int)P.depth_rs;
+    const float* __restrict__ dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
+    if ((cw & 3) == 0 && (drs & 3) == 0 && ((reinterpret_cast<uintptr_t>(dsrc) & 15) == 0)) {
+      const int q4 = cw >> 2, n4 = npc >> 2;                 // float4 per cell row / per cell
+      for (int j = l; j < n4; j += 16) {
+        const int r = j / q4, c4 = j - r * q4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dsrc + r * drs) + c4);
+        *reinterpret_cast<float4*>(s_z + 4 * j) = v;        // cell-local index = r*cw + 4*c4 = 4*j
+      }
+    } else {
+      for (int i = l; i < npc; i += 16) {
+        const int r = i / cw, c = i - r * cw;
+        s_z[i] = __ldg(dsrc + r * drs + c);
+      }
+    }
+  } else {
+    for (int i = l; i < npc; i += 16) s_z[i] = CZ[i];
+  }
+  __syncwarp(mask);
+  const double fx = (double)P.fx, fy = (double)P.fy;
   const double rfx = 1.0 / fx, rfy = 1.0 / fy;
+  const double col0 = (double)(cc * cw) - (double)P.cx, row0 = (double)(cr * ch) - (double)P.cy;
   int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
   const int step_r = 16 / cw, step_c = 16 - step_r * cw;    // element i + 16
   for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
-    float vz[kSumsChunk], vx[kSumsChunk], vy[kSumsChunk];
-    {
-      int r2 = lr, c2 = lc;
-#pragma unroll
-      for (int u = 0; u < kSumsChunk; ++u) {
-        const int i = i0 + 16 * u;
-        vz[u] = 0.f; vx[u] = 0.f; vy[u] = 0.f;
-        if (i < npc) {
-          if (FROM_DEPTH) vz[u] = __ldg(dsrc + (long long)r2 * P.depth_rs + c2);
-          else { vx[u] = CX[i]; vy[u] = CY[i]; vz[u] = CZ[i]; }
-        }
-        c2 += step_c; r2 += step_r;
-        if (c2 >= cw) { c2 -= cw; ++r2; }
-      }
-    }
 #pragma unroll
     for (int u = 0; u < kSumsChunk; ++u) {
       const int i = i0 + 16 * u;
       if (i < npc) {
-        float x, y, z;
+        float x, y;
+        const float z = s_z[i];
         if (FROM_DEPTH) {
-          // PlaneExtractor.cpp:117-127: all in double, stored as float
-          const double zd = (double)vz[u];
-          x = div_to_float(((double)(cc * cw + lc) - pcx) * zd, fx, rfx);
-          y = div_to_float(((double)(cr * P.ch + lr) - pcy) * zd, fy, rfy);
-          z = vz[u];
+          // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
+          // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
+          const double zd = (double)z;
+          const double tx = (col0 + (double)lc) * zd, ty = (row0 + (double)lr) * zd;
+          const double qx = tx * rfx, qy = ty * rfy;
+          if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
+          else { x = (float)qx; y = (float)qy; }
           CX[i] = x; CY[i] = y; CZ[i] = z;
         } else {
-          x = vx[u]; y = vy[u]; z = vz[u];
+          x = CX[i]; y = CY[i];
         }
-        s_z[i] = z;
         cnt += (z > 0.f);
         if (i < body) {
           if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }

@@ -84,7 +84,7 @@ struct OrbDev {
   int* out_cnt;                     // [B]
   int kp_cap;
   int* status;                      // bit 0: candidate overflow, bit 1: node overflow
-  int fast_tp, fast_rows;
+  int fast_tp, fast_rows, fast_list_off, fast_list_cap;
   int blur_blk_off[DRFE_MAX_LEVELS + 1];   // first k_blur block of each level
 };
 
@@ -244,6 +244,66 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Full threshold-free score of the 4 pixels of quad g in interior row ry: returns the packed bytes
+// e = max(q + 1 - minTh, 0) of pixels 0..3.  tile32: strip rows as words, TP4 words per row.
+__device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t kmin) {
+  // window rows ry..ry+6 (level rows y-3..y+3), bytes 16+4g .. 16+4g+11 (level columns x-3..x+8)
+  uint32_t w[7][3];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t* p = tile32 + (ry + r) * TP4 + 4 + g;
+    w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2];
+  }
+  // 4 adjacent bytes starting at byte offset o (0..8) of row r
+  auto quad = [&](int r, int o) -> uint32_t {
+    return (o & 3) == 0 ? w[r][o >> 2] : __funnelshift_r(w[r][o >> 2], w[r][(o >> 2) + 1], 8 * (o & 3));
+  };
+  const uint32_t vq = quad(3, 3);                          // centres of the 4 pixels
+  const uint32_t v_even = __byte_perm(vq, 0, 0x4240);      // pixels 0,2 as u16x2
+  const uint32_t v_odd = __byte_perm(vq, 0, 0x4341);       // pixels 1,3
+  uint32_t re[16], ro[16];
+#define DRFE_RING(k, dx, dy)                                   \
+  {                                                            \
+    const uint32_t rq = quad(3 + (dy), 3 + (dx));              \
+    re[k] = __byte_perm(rq, 0, 0x4240);                        \
+    ro[k] = __byte_perm(rq, 0, 0x4341);                        \
+  }
+  DRFE_RING(0, 0, 3) DRFE_RING(1, 1, 3) DRFE_RING(2, 2, 2) DRFE_RING(3, 3, 1)
+  DRFE_RING(4, 3, 0) DRFE_RING(5, 3, -1) DRFE_RING(6, 2, -2) DRFE_RING(7, 1, -3)
+  DRFE_RING(8, 0, -3) DRFE_RING(9, -1, -3) DRFE_RING(10, -2, -2) DRFE_RING(11, -3, -1)
+  DRFE_RING(12, -3, 0) DRFE_RING(13, -3, 1) DRFE_RING(14, -2, 2) DRFE_RING(15, -1, 3)
+#undef DRFE_RING
+  // e = max(q + 257, 256 + minTh) - (256 + minTh) = max(q + 1 - minTh, 0) per half (< 256)
+  const uint32_t ee = __vmaxu2(fast_q_pair(re, v_even), kmin) - kmin;
+  const uint32_t eo = __vmaxu2(fast_q_pair(ro, v_odd), kmin) - kmin;
+  return ee | (eo << 8);                                   // bytes: pixel 0,1,2,3
+}
+
+// Necessary condition for "corner at threshold t" on the 4 pixels of a quad: every 9-pixel arc
+// of the ring contains two adjacent compass points (ring 0,4,8,12), so a corner needs an adjacent
+// compass pair both > v + t or both < v - t.  Returns 0 when none of the 4 pixels can be one.
+__device__ __forceinline__ uint32_t fast_compass_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t t2) {
+  const uint32_t* pu = tile32 + ry * TP4 + 4 + g;            // level row y-3: bytes x-3..
+  const uint32_t* pm = pu + 3 * TP4;                         // row y
+  const uint32_t* pd = pu + 6 * TP4;                         // row y+3
+  const uint32_t u0 = pu[0], u1 = pu[1], m0 = pm[0], m1 = pm[1], m2 = pm[2], d0 = pd[0], d1 = pd[1];
+  const uint32_t q8 = __funnelshift_r(u0, u1, 24), q0 = __funnelshift_r(d0, d1, 24);   // (0,-3) and (0,+3): byte offset 3
+  const uint32_t qv = __funnelshift_r(m0, m1, 24);                                     // centres
+  const uint32_t q4 = __funnelshift_r(m1, m2, 16), q12 = m0;                           // (+3,0): offset 6, (-3,0): offset 0
+  uint32_t any = 0;
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    const uint32_t sel = par ? 0x4341u : 0x4240u;
+    const uint32_t v = __byte_perm(qv, 0, sel), r0 = __byte_perm(q0, 0, sel), r4 = __byte_perm(q4, 0, sel),
+                   r8 = __byte_perm(q8, 0, sel), r12 = __byte_perm(q12, 0, sel);
+    const uint32_t mm = __vmaxu2(__vimax3_u16x2(__vminu2(r0, r4), __vminu2(r4, r8), __vminu2(r8, r12)), __vminu2(r12, r0));
+    const uint32_t MM = __vminu2(__vimin3_u16x2(__vmaxu2(r0, r4), __vmaxu2(r4, r8), __vmaxu2(r8, r12)), __vmaxu2(r12, r0));
+    const uint32_t hi = v + t2, lo = MM + t2;
+    any |= (mm - __vminu2(mm, hi)) | (v - __vminu2(v, lo));  // mm > v + t  or  v > MM + t
+  }
+  return any;
+}
+
 // ring offsets (dx,dy), k = 0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
 // (-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)  
 //
@@ -268,12 +328,14 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   const int nrows = strip.nrows;             // interior rows of this strip
   uint8_t* tile = smem;                      // (nrows + 6) x TP: level rows Y0-3.., ROI columns 0..
   uint8_t* score = smem + (size_t)TP * (P.fast_rows + 6);   // (nrows + 2) x TP with zero guards
-  uint32_t* list = reinterpret_cast<uint32_t*>(tile);       // survivors (aliases the tile after stage 2)
+  uint32_t* list = reinterpret_cast<uint32_t*>(smem + P.fast_list_off);   // kept maxima
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_n, s_ini[kMaxStripCells];
   uint4* s_mask = reinterpret_cast<uint4*>(score + (size_t)TP * (P.fast_rows + 2));   // [quads]
+  unsigned short* queue = reinterpret_cast<unsigned short*>(s_mask + (TP >> 2));       // [ntask] quads that pass the compass test
+  __shared__ int s_nq;
   const int tid = threadIdx.x;
-  if (tid == 0) { s_n = 0; mbar_init(&s_bar, 1); }
+  if (tid == 0) { s_n = 0; s_nq = 0; mbar_init(&s_bar, 1); }
   for (int i = tid; i < kMaxStripCells; i += THREADS) s_ini[i] = 0;
   __syncthreads();
   // ---- 1. TMA: one bulk copy per image row
@@ -292,8 +354,6 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   const int wCell = L.wCell;
   const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
   uint32_t* score32 = reinterpret_cast<uint32_t*>(score);
-  for (int i = tid; i < TP4; i += THREADS) { score32[i] = 0; score32[(nrows + 1) * TP4 + i] = 0; }
-  for (int i = tid; i < nrows; i += THREADS) { score32[(i + 1) * TP4] = 0; score32[(i + 1) * TP4 + quads + 1] = 0; }
   // per-quad cell-boundary masks as u16x2 {left even, left odd, right even, right odd}: a pixel
   // in the first (last) column of its cell has no left (right) neighbours
   for (int g = tid; g < quads; g += THREADS) {
@@ -309,61 +369,55 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   }
   const uint32_t kmin = (uint32_t)(256 + P.min_th) * 0x00010001u;
   const int ntask = nrows * quads;
+  const int lane = tid & 31;
+  // the whole score map starts at zero: pixels the compass test rules out are never written
+  for (int i = tid; i < (nrows + 2) * TP4; i += THREADS) score32[i] = 0;
   mbar_wait(&s_bar, 0);                      // the strip's rows have landed
-  for (int task = tid; task < ntask; task += THREADS) {
-    const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-    const int g = task - ry * quads;
-    // window rows ry..ry+6 (level rows y-3..y+3), bytes 16+4g .. 16+4g+11 (level columns x-3..x+8)
-    uint32_t w[7][3];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const uint32_t* p = tile32 + (ry + r) * TP4 + 4 + g;
-      w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2];
+  // 2a. compass test at iniThFAST for every quad; survivors are queued (warp-aggregated)
+  {
+    const uint32_t t2 = (uint32_t)P.ini_th * 0x00010001u;
+    for (int task0 = tid - lane; task0 < ntask; task0 += THREADS) {
+      const int task = task0 + lane;
+      bool pass = false;
+      if (task < ntask) {
+        const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+        pass = fast_compass_quad(tile32, TP4, ry, task - ry * quads, t2) != 0;
+      }
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+      if (bal == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_nq, __popc(bal));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (pass) queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)task;
     }
-    // 4 adjacent bytes starting at byte offset o (0..8) of row r
-    auto quad = [&](int r, int o) -> uint32_t {
-      return (o & 3) == 0 ? w[r][o >> 2] : __funnelshift_r(w[r][o >> 2], w[r][(o >> 2) + 1], 8 * (o & 3));
-    };
-    const uint32_t vq = quad(3, 3);                          // centres of the 4 pixels
-    const uint32_t v_even = __byte_perm(vq, 0, 0x4240);      // pixels 0,2 as u16x2
-    const uint32_t v_odd = __byte_perm(vq, 0, 0x4341);       // pixels 1,3
-    uint32_t re[16], ro[16];
-#define DRFE_RING(k, dx, dy)                                   \
-  {                                                            \
-    const uint32_t rq = quad(3 + (dy), 3 + (dx));              \
-    re[k] = __byte_perm(rq, 0, 0x4240);                        \
-    ro[k] = __byte_perm(rq, 0, 0x4341);                        \
   }
-    DRFE_RING(0, 0, 3) DRFE_RING(1, 1, 3) DRFE_RING(2, 2, 2) DRFE_RING(3, 3, 1)
-    DRFE_RING(4, 3, 0) DRFE_RING(5, 3, -1) DRFE_RING(6, 2, -2) DRFE_RING(7, 1, -3)
-    DRFE_RING(8, 0, -3) DRFE_RING(9, -1, -3) DRFE_RING(10, -2, -2) DRFE_RING(11, -3, -1)
-    DRFE_RING(12, -3, 0) DRFE_RING(13, -3, 1) DRFE_RING(14, -2, 2) DRFE_RING(15, -1, 3)
-#undef DRFE_RING
-    // e = max(q + 257, 256 + minTh) - (256 + minTh) = max(q + 1 - minTh, 0) per half (< 256)
-    const uint32_t ee = __vmaxu2(fast_q_pair(re, v_even), kmin) - kmin;
-    const uint32_t eo = __vmaxu2(fast_q_pair(ro, v_odd), kmin) - kmin;
-    uint32_t packed = ee | (eo << 8);                        // bytes: pixel 0,1,2,3
-    const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
-    if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
-    score32[(ry + 1) * TP4 + g + 1] = packed;
+  __syncthreads();
+  // 2b. full score for the queued quads only, all lanes busy
+  {
+    const int nq = s_nq;
+    for (int qi = tid; qi < nq; qi += THREADS) {
+      const int task = queue[qi];
+      const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+      const int g = task - ry * quads;
+      uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin);
+      const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
+      if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
+      score32[(ry + 1) * TP4 + g + 1] = packed;
+    }
   }
   __syncthreads();
   // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free
-  // on u16x2 pairs (the score map is dense at minThFAST on textured frames)
-  const int e_ini = P.ini_th + 1 - P.min_th;
-  const int list_cap = (TP * (P.fast_rows + 6)) >> 2;
-  const int lane = tid & 31;
-  for (int task0 = tid - lane; task0 < ntask; task0 += THREADS) {
-    const int task = task0 + lane;
-    uint32_t surv = 0, sc0 = 0;
-    int sry = 0, sg = 0;
-    if (task < ntask) {
-    const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-    const int g = task - ry * quads;
-    sry = ry; sg = g;
+  // on u16x2 pairs.
+  // Pass 0 keeps the maxima with q >= iniThFAST (what FAST(iniThFAST) returns) and marks their
+  // cells; only queued quads can hold such a pixel.  Pass 1 runs only if some cell of the strip
+  // got nothing: there FAST(minThFAST) is evaluated densely and its maxima are taken instead
+  // (ORBextractor.cc:812-816).
+  const int list_cap = P.fast_list_cap;
+  const uint32_t kini = (uint32_t)(P.ini_th - P.min_th) * 0x00010001u;   // e > kini <=> q >= iniThFAST
+  const int ncells_x = (iw + wCell - 1) / wCell;
+  // strict-maximum flags (bit k = pixel k) of quad (ry, g) with scores clipped at kth
+  auto nms_quad = [&](int ry, int g, uint32_t c0, uint32_t kth) -> uint32_t {
     const uint32_t* sp = score32 + (ry + 1) * TP4 + g + 1;
-    const uint32_t c0 = sp[0];
-    if (c0 != 0) {
     const uint32_t u0 = sp[-TP4 - 1], u1 = sp[-TP4], u2 = sp[-TP4 + 1];
     const uint32_t m0 = sp[-1], m2 = sp[1];
     const uint32_t d0 = sp[TP4 - 1], d1 = sp[TP4], d2 = sp[TP4 + 1];
@@ -380,64 +434,93 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       const uint32_t rmax = __vimax3_u16x2(__byte_perm(Ru, 0, sel), __byte_perm(Rm, 0, sel), __byte_perm(Rd, 0, sel)) & (par ? mk.w : mk.z);
       const uint32_t nb = __vimax3_u16x2(lmax, rmax, __vmaxu2(__byte_perm(u1, 0, sel), __byte_perm(d1, 0, sel)));
       const uint32_t c = __byte_perm(c0, 0, sel);
-      t[par] = c - __vminu2(c, nb);                          // per half: > 0 <=> strict maximum
+      // scores clipped at the pass threshold: cz > nz <=> c > threshold and c > nb
+      const uint32_t cz = c - __vminu2(c, kth), nz = nb - __vminu2(nb, kth);
+      t[par] = cz - __vminu2(cz, nz);                        // per half: > 0 <=> kept
     }
-    // pack the 4 survivor flags; appended below by the whole warp
-    surv = ((t[0] & 0xFFFFu) ? 1u : 0u) | ((t[1] & 0xFFFFu) ? 2u : 0u) | ((t[0] >> 16) ? 4u : 0u) | ((t[1] >> 16) ? 8u : 0u);
-    sc0 = c0;
-    }  // c0 != 0
-    }  // task < ntask
-    // warp-aggregated append: one shared-memory atomic per warp and pixel slot
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool on = (surv >> k) & 1u;
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, on);
-      if (bal == 0) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (on) {
-        const int slot = base + __popc(bal & ((1u << lane) - 1));
-        const uint32_t e = (sc0 >> (8 * k)) & 0xFF;
-        if (slot < list_cap) list[slot] = (uint32_t)(4 * sg + k) | ((uint32_t)sry << 12) | (e << 24);
+    return ((t[0] & 0xFFFFu) ? 1u : 0u) | ((t[1] & 0xFFFFu) ? 2u : 0u) | ((t[0] >> 16) ? 4u : 0u) | ((t[1] >> 16) ? 8u : 0u);
+  };
+  // pass 0: queued quads only
+  {
+    const int nq = s_nq;
+    for (int qi = tid; qi < nq; qi += THREADS) {
+      const int task = queue[qi];
+      const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+      const int g = task - ry * quads;
+      const uint32_t c0 = score32[(ry + 1) * TP4 + g + 1];
+      if (c0 == 0) continue;
+      uint32_t surv = nms_quad(ry, g, c0, kini);
+      if (surv == 0) continue;
+      int slot = atomicAdd(&s_n, __popc(surv));
+      while (surv) {
+        const int k = __ffs(surv) - 1;
+        surv &= surv - 1;
+        const int x = 4 * g + k;
+        s_ini[__umulhi((uint32_t)x, L.wcell_magic)] = 1;       // benign race: everybody writes 1
+        if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
         else atomicOr(P.status, 1);
+        ++slot;
       }
     }
   }
   __syncthreads();
-  // per-cell count of survivors at iniThFAST (does FAST(iniThFAST) find anything in the cell?)
-  const int n = min(s_n, list_cap);
-  for (int i = tid; i < n; i += THREADS) {
-    const uint32_t ent = list[i];
-    if ((int)(ent >> 24) >= e_ini) atomicAdd(&s_ini[__umulhi(ent & 0xFFFu, L.wcell_magic)], 1);
+  // pass 1: cells where FAST(iniThFAST) found nothing
+  {
+    int missing = 0;
+    for (int c = tid; c < ncells_x; c += THREADS) missing |= (s_ini[c] == 0);
+    if (__syncthreads_or(missing)) {
+      auto needs = [&](int g) -> bool {
+        const int ca = (int)__umulhi((uint32_t)(4 * g), L.wcell_magic), cb = (int)__umulhi((uint32_t)min(4 * g + 3, iw - 1), L.wcell_magic);
+        return s_ini[ca] == 0 || s_ini[cb] == 0;
+      };
+      // FAST(minThFAST) on those cells: dense scores for every quad touching one of them
+      for (int task = tid; task < ntask; task += THREADS) {
+        const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+        const int g = task - ry * quads;
+        if (!needs(g)) continue;
+        uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin);
+        const int rem = iw - 4 * g;
+        if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
+        score32[(ry + 1) * TP4 + g + 1] = packed;
+      }
+      __syncthreads();
+      for (int task = tid; task < ntask; task += THREADS) {
+        const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
+        const int g = task - ry * quads;
+        if (!needs(g)) continue;
+        const uint32_t c0 = score32[(ry + 1) * TP4 + g + 1];
+        if (c0 == 0) continue;
+        uint32_t surv = nms_quad(ry, g, c0, 0u);
+        while (surv) {
+          const int k = __ffs(surv) - 1;
+          surv &= surv - 1;
+          const int x = 4 * g + k;
+          if (s_ini[__umulhi((uint32_t)x, L.wcell_magic)] != 0) continue;   // the fallback applies to the pixel's own cell only
+          const int slot = atomicAdd(&s_n, 1);
+          if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
+          else atomicOr(P.status, 1);
+        }
+      }
+    }
   }
   __syncthreads();
-  // ---- 4. emit (region coordinates: origin (16,16) => interior x + 3)
-  int* cnt = P.cand_cnt + f * P.nlevels + strip.level;
+  // ---- 4. emit (region coordinates: origin (16,16) => interior x + 3), order-free
+  const int n = min(s_n, list_cap);
+  if (n == 0) return;
+  __shared__ int s_base;
+  if (tid == 0) s_base = atomicAdd(P.cand_cnt + f * P.nlevels + strip.level, n);
+  __syncthreads();
   uint32_t* out = P.cand + (long long)f * P.cand_fstride + L.cand_off;
   const int oy = strip.y0 - kEdge + 3;
-  for (int i0 = tid - lane; i0 < n; i0 += THREADS) {
-    const int i = i0 + lane;
-    uint32_t ent = 0;
-    bool keep = false;
-    if (i < n) {
-      ent = list[i];
-      const int e = ent >> 24;
-      keep = e >= e_ini || s_ini[__umulhi(ent & 0xFFFu, L.wcell_magic)] == 0;
-    }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (bal == 0) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(cnt, __popc(bal));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (keep) {
-      const int pos = base + __popc(bal & ((1u << lane) - 1));
-      const uint32_t q = (ent >> 24) + P.min_th - 1;
-      if (pos < L.cand_cap)
-        out[pos] = ((ent & 0xFFF) + 3) | ((((ent >> 12) & 0xFFF) + oy) << 12) | (q << 24);
-      else
-        atomicOr(P.status, 1);
-    }
+  const int base = s_base;
+  for (int i = tid; i < n; i += THREADS) {
+    const uint32_t ent = list[i];
+    const uint32_t q = (ent >> 24) + P.min_th - 1;
+    const int pos = base + i;
+    if (pos < L.cand_cap)
+      out[pos] = ((ent & 0xFFF) + 3) | ((((ent >> 12) & 0xFFF) + oy) << 12) | (q << 24);
+    else
+      atomicOr(P.status, 1);
   }
 }
 
@@ -1067,7 +1150,17 @@ static int orb_build(drfe_orb* h) {
   for (int l = 0; l < nl; ++l) h->max_lkp = std::max(h->max_lkp, D.lv[l].node_cap);
   D.fast_tp = (D.lv[0].w + 15) / 16 * 16;         // smem row pitch of a FAST strip (TMA rows are 16 B multiples)
   D.fast_rows = max_strip_rows;
-  h->fast_smem = (size_t)D.fast_tp * (D.fast_rows + 6) + (size_t)D.fast_tp * (D.fast_rows + 2) + (size_t)D.fast_tp * 4;
+  {
+    // tile | score map (+2 guard rows) | per-quad masks | compass queue (u16 per quad) | list of kept maxima
+    const size_t tp = D.fast_tp, rows = D.fast_rows, max_tasks = (tp / 4) * rows;
+    size_t off = tp * (rows + 6) + tp * (rows + 2) + tp * 4;
+    // queue (u16 per quad), then the list of kept maxima: max_tasks/2 entries, i.e. one maximum per
+    // 8 pixels; denser input overflows loudly (DRFE_ERR_CAPACITY), like the per-level candidate arena
+    off += (max_tasks * 2 + 15) / 16 * 16;
+    D.fast_list_off = (int)off;
+    D.fast_list_cap = (int)(max_tasks / 2);
+    h->fast_smem = off + (size_t)D.fast_list_cap * 4;
+  }
   if (h->fast_smem > 220 * 1024) { set_error("image too wide for the FAST strip kernel (%zu B of shared memory)", h->fast_smem); return DRFE_ERR_ARG; }
   const int NC = h->max_node_cap;
   h->quad_smem = (size_t)NC * (8 + 8 + 8 + 4 + 4 + 16 + 5 * 4 + 8 + 2) + 64;
