@@ -20,10 +20,16 @@
 //        (eig3_sym below) — same eigenpairs to ~1e-15; the GPU runs the same
 //        operation sequence so segmentation decisions are bit-identical.
 //   cv::erode / cv::dilate 3x3 with the default (ignore-outside) border.
+//   B.9  CylinderSeg (src/CAPE/CylinderSeg.cpp:7-247) draws its RANSAC triplets from the
+//        process-global rand(); declared: glibc TYPE_3 rand() seeded with 1 and restarted
+//        at every process() call (GlibcRand below).  Eigen reductions in it are restated
+//        as: dynamic 3-vectors (x0+x1)+x2, fixed Vector3 x0+(x1+x2) (Eigen 3.3 Redux.h),
+//        N*N^T as 2*(sequential sum over the activated cells), no FMA.  The PCA axis sign
+//        is solver-defined (compare up to sign); nothing downstream depends on it.
 // PARITY STATUS: "parity unpinned" by the reference (no tests / fixtures, cannot
-// be built here: needs Eigen + OpenCV headers).  Cylinder extraction
-// (CylinderSeg.cpp) is not restated yet: cylinder_detection must be 0.
+// be built here: needs Eigen + OpenCV headers).
 #include <algorithm>
+#include <array>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -204,13 +210,194 @@ Seg fit_cell(const float* X, const float* Y, const float* Z, int npts, int cell_
   return s;
 }
 
+// glibc rand(): TYPE_3 additive feedback generator (r[i] = r[i-31] + r[i-3], output >> 1),
+// seeded like srand(seed) (stdlib/random_r.c).  Checked against libc in tests/.
+struct GlibcRand {
+  uint32_t r[34];
+  int pos = 0;
+  explicit GlibcRand(uint32_t seed = 1) {
+    std::vector<uint32_t> t(344);
+    int32_t w = (int32_t)(seed ? seed : 1);
+    t[0] = (uint32_t)w;
+    for (int i = 1; i < 31; ++i) {
+      const int32_t hi = w / 127773, lo = w % 127773;
+      w = 16807 * lo - 2836 * hi;
+      if (w < 0) w += 2147483647;
+      t[i] = (uint32_t)w;
+    }
+    for (int i = 31; i < 34; ++i) t[i] = t[i - 31];
+    for (int i = 34; i < 344; ++i) t[i] = t[i - 31] + t[i - 3];
+    for (int i = 0; i < 34; ++i) r[i] = t[310 + i];
+  }
+  int next() {  // r[] is a ring of the last 34 values, pos = oldest
+    const uint32_t v = r[(pos + 3) % 34] + r[(pos + 31) % 34];
+    r[pos] = v;
+    pos = (pos + 1) % 34;
+    return (int)(v >> 1);
+  }
+};
+
+const double kCylScoreMin = 100;            // Params.h:8
+const double kCylSqrMaxDist = 0.0225;       // Params.h:9
+
+// CylinderSeg::CylinderSeg (CylinderSeg.cpp:7-247)
+struct CylSeg {
+  int nr_segments = 0;
+  double axis[3] = {0, 0, 0};
+  std::vector<float> radii;
+  std::vector<std::array<double, 3>> centers;
+  std::vector<std::vector<uint8_t>> inliers;   // [segment][local cell]
+  std::vector<double> MSEs;
+  std::vector<int> local2global;
+  std::vector<uint8_t> cylindrical;
+  std::vector<std::array<float, 3>> P1, P2;
+  std::vector<float> P1P2_norm;
+
+  static double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+  CylSeg(const std::vector<Seg>& grid, const std::vector<uint8_t>& act, int m, GlibcRand& rng) {
+    const int ns = (int)grid.size();
+    std::vector<double> N(3 * m), P(3 * m);   // column j at [3*j .. 3*j+2]
+    local2global.resize(m);
+    int j = 0;
+    for (int i = 0; i < ns; ++i)
+      if (act[i]) {
+        for (int k = 0; k < 3; ++k) { N[3 * j + k] = grid[i].normal[k]; P[3 * j + k] = grid[i].mean[k]; }
+        local2global[j++] = i;
+      }
+    // cov = [N -N][N -N]^T / (2m - 1)   (:43)
+    double c6[6];
+    {
+      static const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
+      for (int e = 0; e < 6; ++e) {
+        double s = 0;
+        for (int q = 0; q < m; ++q) s += N[3 * q + A[e]] * N[3 * q + B[e]];
+        c6[e] = (2.0 * s) / (double)(2 * m - 1);
+      }
+    }
+    double S[3], V[3][3];
+    eig3_sym(c6, S, V);
+    const double score = S[2] / S[0];
+    if (score < kCylScoreMin) return;          // Checkpoint 1 (:53)
+    const double vec[3] = {V[0][0], V[1][0], V[2][0]};
+    axis[0] = vec[0]; axis[1] = vec[1]; axis[2] = vec[2];
+    // projection onto the plane orthogonal to the axis, normalised normals (:59-79)
+    std::vector<double> Pp(3 * m);
+    for (int q = 0; q < m; ++q) {
+      const double pd = dot3(vec, &P[3 * q]);
+      for (int k = 0; k < 3; ++k) Pp[3 * q + k] = P[3 * q + k] - pd * vec[k];
+      const double nd = dot3(vec, &N[3 * q]);
+      for (int k = 0; k < 3; ++k) N[3 * q + k] = N[3 * q + k] - nd * vec[k];
+      const double nn = std::sqrt((N[3 * q] * N[3 * q] + N[3 * q + 1] * N[3 * q + 1]) + N[3 * q + 2] * N[3 * q + 2]);
+      for (int k = 0; k < 3; ++k) N[3 * q + k] = N[3 * q + k] / nn;
+    }
+    // float K = log(1-p_success)/log(1-pow(w,3)) = 43.97.. ; later with w = 0.5: 12.05.. (:82-84,164)
+    float K = (float)((double)std::log(1.0f - 0.8f) / std::log(1.0 - std::pow((double)0.33f, 3)));
+    int m_left = m;
+    std::vector<int> ids_left(m);
+    std::vector<uint8_t> left_mask(m, 1);
+    for (int i = 0; i < m; ++i) ids_left[i] = i;
+    std::vector<double> D(m);
+    std::vector<uint8_t> I(m), I_final(m, 0);
+    while (m_left > 5 && m_left > 0.1 * m) {    // sequential RANSAC (:94)
+      double min_hyp = kCylSqrMaxDist * m_left;
+      const int accepted = (int)(0.9 * m_left);
+      int max_inl = 0;
+      std::fill(I_final.begin(), I_final.end(), 0);   // (reference: uninitialised; only read after a hypothesis wrote it)
+      for (int k = 0; k < K; ++k) {
+        const int id1 = ids_left[rng.next() % m_left];
+        const int id2 = ids_left[rng.next() % m_left];
+        const int id3 = ids_left[rng.next() % m_left];
+        const double *n1 = &N[3 * id1], *n2 = &N[3 * id2], *n3 = &N[3 * id3];
+        const double *p1 = &Pp[3 * id1], *p2 = &Pp[3 * id2], *p3 = &Pp[3 * id3];
+        double e1[3], e2[3], t[3];
+        for (int c = 0; c < 3; ++c) {
+          e1[c] = (n1[c] + n2[c]) + n3[c];
+          e2[c] = (p1[c] + p2[c]) + p3[c];
+          t[c] = (n1[c] * p1[c] + n2[c] * p2[c]) + n3[c] * p3[c];
+        }
+        const double a = 1 - dot3(e1, e1) / 9;
+        const double b = ((t[0] + t[1]) + t[2]) / 3 - dot3(e1, e2) / 9;
+        double r = b / a;
+        double center[3];
+        for (int c = 0; c < 3; ++c) center[c] = (e2[c] - r * e1[c]) / 3;
+        const double rr = r * r;
+        for (int i = 0; i < m; ++i) {
+          const double x = (Pp[3 * i] - r * N[3 * i]) - center[0], y = (Pp[3 * i + 1] - r * N[3 * i + 1]) - center[1],
+                       z = (Pp[3 * i + 2] - r * N[3 * i + 2]) - center[2];
+          D[i] = ((x * x + y * y) + z * z) / rr;
+          I[i] = D[i] < kCylSqrMaxDist;
+        }
+        double dist = 0;                          // MSAC truncated distance (:137-148)
+        int inl = 0;
+        for (int i = 0; i < m; ++i)
+          if (left_mask[i]) {
+            if (I[i]) { ++inl; dist += D[i]; }
+            else dist += kCylSqrMaxDist;
+          }
+        if (dist < min_hyp) {
+          min_hyp = dist;
+          max_inl = inl;
+          for (int i = 0; i < m; ++i) I_final[i] = left_mask[i] ? I[i] : 0;
+          if (inl > accepted) break;
+        }
+      }
+      if (max_inl < 6) break;                     // Checkpoint 2 (:160)
+      K = (float)((double)std::log(1.0f - 0.8f) / std::log(1.0 - std::pow(0.5, 3)));
+      ids_left.clear();
+      for (int i = 0; i < m; ++i) {
+        if (I_final[i]) { left_mask[i] = 0; --m_left; }
+        else if (left_mask[i]) ids_left.push_back(i);
+      }
+      // LLS over all inliers (:178-199)
+      double e1[3] = {0, 0, 0}, e2[3] = {0, 0, 0}, b = 0;
+      for (int i = 0; i < m; ++i)
+        if (I_final[i]) {
+          for (int c = 0; c < 3; ++c) { e1[c] += N[3 * i + c]; e2[c] += Pp[3 * i + c]; }
+          b += (N[3 * i] * Pp[3 * i] + N[3 * i + 1] * Pp[3 * i + 1]) + N[3 * i + 2] * Pp[3 * i + 2];
+        }
+      const double n2 = (double)(max_inl * max_inl);
+      const double a = 1 - dot3(e1, e1) / n2;
+      b /= max_inl;
+      b -= dot3(e1, e2) / n2;
+      double r = b / a;
+      std::array<double, 3> center;
+      for (int c = 0; c < 3; ++c) center[c] = (e2[c] - r * e1[c]) / max_inl;
+      if (r < 0) r = -r;
+      ++nr_segments;
+      radii.push_back((float)r);
+      centers.push_back(center);
+      inliers.push_back(I_final);
+      // point-to-axis distances of the inliers' means (:206-226); fixed-size Vector3d reductions
+      double P2d[3], dir[3];
+      for (int c = 0; c < 3; ++c) { P2d[c] = center[c] + vec[c]; dir[c] = P2d[c] - center[c]; }
+      const double P1P2d = std::sqrt(dir[0] * dir[0] + (dir[1] * dir[1] + dir[2] * dir[2]));
+      double mse = 0;
+      for (int i = 0; i < m; ++i)
+        if (I_final[i]) {
+          const double q[3] = {P[3 * i] - P2d[0], P[3 * i + 1] - P2d[1], P[3 * i + 2] - P2d[2]};
+          const double cx = dir[1] * q[2] - dir[2] * q[1], cy = dir[2] * q[0] - dir[0] * q[2], cz = dir[0] * q[1] - dir[1] * q[0];
+          const double dd = std::sqrt(cx * cx + (cy * cy + cz * cz)) / P1P2d - r;
+          mse += dd * dd;
+        }
+      mse = mse / max_inl;
+      MSEs.push_back(mse);
+      P1.push_back({(float)center[0], (float)center[1], (float)center[2]});
+      P2.push_back({(float)P2d[0], (float)P2d[1], (float)P2d[2]});
+      P1P2_norm.push_back((float)P1P2d);
+      cylindrical.push_back(1);
+    }
+  }
+};
+
 struct CapeOracle {
   int H, W, cw, ch, cyl;
   float max_merge_dist, min_cos;
   int ncx, ncy, ncells, npc;
   std::vector<Seg> grid;
-  std::vector<int32_t> plane_map;
-  std::vector<uint8_t> eroded_map;
+  std::vector<int32_t> plane_map, cyl_map;
+  std::vector<uint8_t> eroded_map, cyl_eroded_map;
+  int nr_cylinders_found = 0;   // size of cylinder_segments_final (CAPE.cpp:434-445)
 
   CapeOracle(int h, int w, int cw_, int ch_, int cyl_, float mc, float mmd)
       : H(h), W(w), cw(cw_), ch(ch_), cyl(cyl_), max_merge_dist(mmd), min_cos(mc) {
@@ -255,13 +442,20 @@ struct CapeOracle {
   }
 
   int process(const float* cloud, uint8_t* seg_out, drfe_plane* planes_out, int plane_cap,
-              int* nr_planes_final) {
+              int* nr_planes_final, drfe_cylinder* cyls_out, int cyl_cap, int* nr_cylinders_final) {
     const size_t N = (size_t)H * W;
     const float* CX = cloud;
     const float* CY = cloud + N;
     const float* CZ = cloud + 2 * N;
     plane_map.assign(ncells, 0);
     eroded_map.assign(ncells, 0);
+    cyl_map.assign(ncells, 0);
+    cyl_eroded_map.assign(ncells, 0);
+    const int cylinder_code_offset = 50;      // CAPE.cpp:53
+    GlibcRand rng(1);                          // declared: restarted per frame (B.9)
+    std::vector<CylSeg> cylinder_segments;
+    std::vector<std::pair<int, int>> cylinder2region;
+    int nr_cylinders = 0;
     std::vector<uint8_t> seg_stack(N, 0);
     std::vector<float> dist_stack(N);
     memset(dist_stack.data(), 100, N * sizeof(float));  // CAPE.cpp:60 (0x64646464)
@@ -340,7 +534,30 @@ struct CapeOracle {
         for (int id = 0; id < ncells; ++id)
           if (activation[id]) plane_map[id] = label;
       }
-      // else: cylinder branch (cylinder_detection) not restated
+      else if (cyl && activated > 5) {
+        // it is an extrusion (CAPE.cpp:179-216)
+        cylinder_segments.emplace_back(grid, activation, activated, rng);
+        CylSeg& cy = cylinder_segments.back();
+        for (int sid = 0; sid < cy.nr_segments; ++sid) {
+          acc.x_acc = acc.y_acc = acc.z_acc = acc.xx_acc = acc.yy_acc = acc.zz_acc = acc.xy_acc = acc.xz_acc = acc.yz_acc = 0;
+          acc.nr_pts = 0;                      // clearPoints
+          for (int c = 0; c < activated; ++c)
+            if (cy.inliers[sid][c]) acc.expand(grid[cy.local2global[c]]);
+          acc.fit();
+          if ((double)acc.MSE < cy.MSEs[sid]) {  // model selection (:195)
+            segs.push_back(acc);
+            for (int c = 0; c < activated; ++c)
+              if (cy.inliers[sid][c]) plane_map[cy.local2global[c]] = (int)segs.size();
+            cy.cylindrical[sid] = 0;
+          } else {
+            ++nr_cylinders;
+            cylinder2region.push_back({(int)cylinder_segments.size() - 1, sid});
+            for (int c = 0; c < activated; ++c)
+              if (cy.inliers[sid][c]) cyl_map[cy.local2global[c]] = nr_cylinders;
+            cy.cylindrical[sid] = 1;
+          }
+        }
+      }
     }
     // ---- plane merging (CAPE.cpp:220-252, getConnectedComponents :459-481)
     const int np = (int)segs.size();
@@ -415,6 +632,52 @@ struct CapeOracle {
       }
     }
     *nr_planes_final = nfinal;
+    // ---- cylinder boundary refinement (CAPE.cpp:323-393)
+    int ncyl_final = 0;
+    if (cyl) {
+      for (int i = 0; i < nr_cylinders; ++i) {
+        const CylSeg& cy = cylinder_segments[cylinder2region[i].first];
+        const int sid = cylinder2region[i].second;
+        for (int id = 0; id < ncells; ++id) mask[id] = cyl_map[id] == i + 1;
+        morph(mask, er, true, true);
+        if (*std::max_element(er.begin(), er.end()) == 0) continue;
+        ++ncyl_final;
+        morph(mask, di, false, false);
+        const uint8_t label = (uint8_t)(cylinder_code_offset + ncyl_final);
+        for (int id = 0; id < ncells; ++id)
+          if (er[id] > 0) cyl_eroded_map[id] = label;
+        const float P2[3] = {cy.P2[sid][0], cy.P2[sid][1], cy.P2[sid][2]};
+        const float P1P2[3] = {P2[0] - cy.P1[sid][0], P2[1] - cy.P1[sid][1], P2[2] - cy.P1[sid][2]};
+        const double norm12 = cy.P1P2_norm[sid], radius = cy.radii[sid];
+        const float max_dist = (float)(9 * cy.MSEs[sid]);
+        for (int id = 0; id < ncells; ++id) {
+          if ((uint8_t)(di[id] - er[id]) == 0) continue;
+          const size_t o = (size_t)id * npc;
+          for (int j = 0; j < npc; ++j) {
+            const float z = CZ[o + j];
+            if (!(z > 0)) continue;
+            const float q[3] = {CX[o + j] - P2[0], CY[o + j] - P2[1], z - P2[2]};
+            const float c0 = P1P2[1] * q[2] - P1P2[2] * q[1], c1 = P1P2[2] * q[0] - P1P2[0] * q[2],
+                        c2 = P1P2[0] * q[1] - P1P2[1] * q[0];
+            const float nrm = std::sqrt(c0 * c0 + (c1 * c1 + c2 * c2));   // fixed-size Vector3f redux
+            float dist = (float)((double)nrm / norm12 - radius);
+            dist *= dist;
+            if (dist < max_dist && dist < dist_stack[o + j]) {
+              dist_stack[o + j] = dist;
+              seg_stack[o + j] = label;
+            }
+          }
+        }
+      }
+    }
+    if (nr_cylinders_final) *nr_cylinders_final = ncyl_final;
+    nr_cylinders_found = nr_cylinders;
+    for (int i = 0; i < nr_cylinders && i < cyl_cap && cyls_out; ++i) {   // CAPE.cpp:434-445
+      const CylSeg& cy = cylinder_segments[cylinder2region[i].first];
+      const int sid = cylinder2region[i].second;
+      cyls_out[i].radius = cy.radii[sid];
+      for (int c = 0; c < 3; ++c) { cyls_out[i].center[c] = cy.centers[sid][c]; cyls_out[i].axis[c] = cy.axis[c]; }
+    }
     // ---- write seg_output in image layout (CAPE.cpp:395-432)
     for (int cr = 0; cr < ncy; ++cr)
       for (int cc = 0; cc < ncx; ++cc) {
@@ -424,6 +687,7 @@ struct CapeOracle {
           uint8_t* row = seg_out + (size_t)(cr * ch + r) * W + cc * cw;
           for (int c = 0; c < cw; ++c) {
             if (eroded_map[id] > 0) row[c] = eroded_map[id];
+            else if (cyl_eroded_map[id] > 0) row[c] = cyl_eroded_map[id];
             else if (st[r * cw + c] > 0) row[c] = st[r * cw + c];
           }
         }
@@ -438,7 +702,6 @@ extern "C" {
 
 void* orc_cape_create(int depth_height, int depth_width, int cell_width, int cell_height,
                       int cylinder_detection, float min_cos_angle_4_merge, float max_merge_dist) {
-  if (cylinder_detection) return nullptr;  // not restated yet
   return new CapeOracle(depth_height, depth_width, cell_width, cell_height, cylinder_detection,
                         min_cos_angle_4_merge, max_merge_dist);
 }
@@ -466,9 +729,19 @@ void orc_cape_depth_to_cloud(void* h, const float* depth, int row_stride, float 
 int orc_cape_process(void* h, const float* cloud, uint8_t* seg_out, drfe_plane* planes,
                      int plane_cap, int* nr_planes, drfe_cylinder* cyls, int cyl_cap,
                      int* nr_cylinders) {
-  (void)cyls; (void)cyl_cap;
-  if (nr_cylinders) *nr_cylinders = 0;
-  return ((CapeOracle*)h)->process(cloud, seg_out, planes, plane_cap, nr_planes);
+  return ((CapeOracle*)h)->process(cloud, seg_out, planes, plane_cap, nr_planes, cyls, cyl_cap, nr_cylinders);
+}
+int orc_cape_cylinders_found(void* h) { return ((CapeOracle*)h)->nr_cylinders_found; }
+int orc_cape_get_cyl_maps(void* h, int32_t* cyl_map, uint8_t* cyl_eroded_map) {
+  CapeOracle* o = (CapeOracle*)h;
+  memcpy(cyl_map, o->cyl_map.data(), o->ncells * sizeof(int32_t));
+  memcpy(cyl_eroded_map, o->cyl_eroded_map.data(), o->ncells);
+  return o->ncells;
+}
+int orc_glibc_rand(uint32_t seed, int n, int32_t* out) {
+  GlibcRand g(seed);
+  for (int i = 0; i < n; ++i) out[i] = g.next();
+  return n;
 }
 int orc_cape_get_cells(void* h, drfe_plane* cells) {
   CapeOracle* o = (CapeOracle*)h;

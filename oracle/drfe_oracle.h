@@ -44,6 +44,12 @@ int orc_cape_process(void* h, const float* cloud_cellmajor, uint8_t* seg_out, dr
                      int* nr_cylinders);
 int orc_cape_get_cells(void* h, drfe_plane* cells);
 int orc_cape_get_grid_maps(void* h, int32_t* plane_map, uint8_t* eroded_map);
+/* cylinder_detection = 1: size of cylinder_segments_final (CAPE.cpp:434-445; nr_cylinders of
+ * orc_cape_process is nr_cylinders_final, the ones that survive erosion), cylinder cell maps */
+int orc_cape_cylinders_found(void* h);
+int orc_cape_get_cyl_maps(void* h, int32_t* cyl_map, uint8_t* cyl_eroded_map);
+/* the declared rand() stream of CylinderSeg: glibc TYPE_3, srand(seed) */
+int orc_glibc_rand(uint32_t seed, int n, int32_t* out);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,8 @@ PLANE_DTYPE = np.dtype([("nr_pts", "<i4"), ("min_nr_pts", "<i4"),
                         ("xy_acc", "<f8"), ("xz_acc", "<f8"), ("yz_acc", "<f8"),
                         ("score", "<f4"), ("MSE", "<f4"), ("planar", "<i4"),
                         ("mean", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8")], align=True)
-assert KP_DTYPE.itemsize == 28 and PLANE_DTYPE.itemsize == C.sizeof(Plane)
+CYL_DTYPE = np.dtype([("radius", "<f4"), ("center", "<f8", (3,)), ("axis", "<f8", (3,))], align=True)
+assert KP_DTYPE.itemsize == 28 and PLANE_DTYPE.itemsize == C.sizeof(Plane) and CYL_DTYPE.itemsize == 56
 
 
 def build(force=False):
@@ -87,6 +88,9 @@ def lib():
                                        C.c_void_p, C.c_int, i32p]
         L.orc_cape_get_cells.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_cape_get_grid_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cape_cylinders_found.argtypes = [C.c_void_p]
+        L.orc_cape_get_cyl_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -200,6 +204,12 @@ def gaussian7(src):
     return dst
 
 
+def glibc_rand(seed, n):
+    out = np.zeros(n, np.int32)
+    lib().orc_glibc_rand(int(seed), n, _p(out))
+    return out
+
+
 def fast_atan2(y, x):
     return lib().orc_fast_atan2(float(y), float(x))
 
@@ -223,7 +233,7 @@ class CapeOracle:
         self.ncx, self.ncy = width // cell_w, height // cell_h
         self.h = self.L.orc_cape_create(height, width, cell_w, cell_h, int(cylinder), min_cos, max_merge_dist)
         if not self.h:
-            raise NotImplementedError("oracle: cylinder detection is not restated")
+            raise RuntimeError("oracle: orc_cape_create failed")
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -244,6 +254,25 @@ class CapeOracle:
         self.L.orc_cape_process(self.h, _p(cloud), _p(seg), _p(planes), plane_cap, C.byref(npl), None, 0,
                                 C.byref(ncy))
         return seg, planes[:npl.value].copy()
+
+    def process_full(self, cloud, plane_cap=256, cyl_cap=64):
+        """CAPE::process with cylinder detection: seg_output, planes, nr_cylinders_final and the
+        cylinder_segments_final list (all cylinders found, CAPE.cpp:434-445)."""
+        cloud = np.ascontiguousarray(cloud, np.float32)
+        seg = np.zeros((self.H, self.W), np.uint8)
+        planes = np.zeros(plane_cap, PLANE_DTYPE)
+        cyls = np.zeros(cyl_cap, CYL_DTYPE)
+        npl, ncy = C.c_int32(0), C.c_int32(0)
+        self.L.orc_cape_process(self.h, _p(cloud), _p(seg), _p(planes), plane_cap, C.byref(npl), _p(cyls), cyl_cap,
+                                C.byref(ncy))
+        found = self.L.orc_cape_cylinders_found(self.h)
+        return seg, planes[:npl.value].copy(), ncy.value, cyls[:found].copy()
+
+    def cyl_maps(self):
+        cm = np.zeros((self.ncy, self.ncx), np.int32)
+        em = np.zeros((self.ncy, self.ncx), np.uint8)
+        self.L.orc_cape_get_cyl_maps(self.h, _p(cm), _p(em))
+        return cm, em
 
     def cells(self):
         out = np.zeros(self.ncx * self.ncy, PLANE_DTYPE)

@@ -402,8 +402,128 @@ def depth_to_cloud(depth, fx, fy, cx, cy, cell_w, cell_h):
     return out.reshape(-1)
 
 
-def cape_process(cloud, H, W, cw, ch, min_cos, max_merge_dist):
-    """CAPE::process (cylinders off).  Returns seg_output, final planes (list of Seg), cells, plane grid map."""
+def glibc_rand_stream(seed=1):
+    """glibc rand() (TYPE_3 additive feedback, stdlib/random_r.c) as a generator; declared stream
+    of CylinderSeg's RANSAC."""
+    r = [0] * 344
+    w = seed if seed else 1
+    r[0] = w
+    for i in range(1, 31):
+        hi, lo = int(w / 127773) if w >= 0 else -int(-w / 127773), 0
+        lo = w - hi * 127773
+        w = 16807 * lo - 2836 * hi
+        if w < 0:
+            w += 2147483647
+        r[i] = w
+    for i in range(31, 34):
+        r[i] = r[i - 31]
+    for i in range(34, 344):
+        r[i] = (r[i - 31] + r[i - 3]) & 0xFFFFFFFF
+    while True:
+        v = (r[-31] + r[-3]) & 0xFFFFFFFF
+        r.append(v)
+        r.pop(0)
+        yield v >> 1
+
+
+class CylRef:
+    """CylinderSeg::CylinderSeg (CylinderSeg.cpp:7-247) with numpy / LAPACK."""
+
+    def __init__(self, grid, act, rng):
+        ids = [i for i in range(len(grid)) if act[i]]
+        m = len(ids)
+        self.local2global = ids
+        self.nr_segments = 0
+        self.radii, self.centers, self.inliers, self.MSEs = [], [], [], []
+        self.P1, self.P2, self.P1P2_norm, self.cylindrical = [], [], [], []
+        self.axis = np.zeros(3)
+        N = np.array([grid[i].normal for i in ids]).T.copy()      # 3 x m
+        P = np.array([grid[i].mean for i in ids]).T.copy()
+        NN = np.concatenate([N, -N], axis=1)
+        cov = (NN @ NN.T) / float(NN.shape[1] - 1)
+        S, V = np.linalg.eigh(cov)
+        if S[2] / S[0] < 100:
+            return
+        vec = V[:, 0].copy()
+        self.axis = vec
+        Pp = P - np.outer(vec, vec @ P)
+        N = N - np.outer(vec, vec @ N)
+        N = N / np.sqrt((N * N).sum(0))
+        K = f32(math.log(f32(1) - f32(0.8)) / math.log(1 - float(f32(0.33)) ** 3))
+        m_left = m
+        ids_left = list(range(m))
+        left = np.ones(m, bool)
+        while m_left > 5 and m_left > 0.1 * m:
+            min_hyp = 0.0225 * m_left
+            accepted = int(0.9 * m_left)
+            max_inl = 0
+            I_final = np.zeros(m, bool)
+            k = 0
+            while k < K:
+                i1 = ids_left[next(rng) % m_left]
+                i2 = ids_left[next(rng) % m_left]
+                i3 = ids_left[next(rng) % m_left]
+                e1 = N[:, i1] + N[:, i2] + N[:, i3]
+                e2 = Pp[:, i1] + Pp[:, i2] + Pp[:, i3]
+                a = 1 - (e1 @ e1) / 9
+                b = (N[:, i1] * Pp[:, i1] + N[:, i2] * Pp[:, i2] + N[:, i3] * Pp[:, i3]).sum() / 3 - (e1 @ e2) / 9
+                with np.errstate(all="ignore"):
+                    r = np.float64(b) / np.float64(a)
+                    center = (e2 - r * e1) / 3
+                    D = (((Pp - r * N) - center[:, None]) ** 2).sum(0) / (r * r)
+                I = D < 0.0225
+                dist, inl = 0.0, 0
+                for i in range(m):            # sequential MSAC sum (:137-148)
+                    if left[i]:
+                        if I[i]:
+                            inl += 1
+                            dist += D[i]
+                        else:
+                            dist += 0.0225
+                if dist < min_hyp:
+                    min_hyp, max_inl = dist, inl
+                    I_final = I & left
+                    if inl > accepted:
+                        break
+                k += 1
+            if max_inl < 6:
+                break
+            K = f32(math.log(f32(1) - f32(0.8)) / math.log(1 - 0.5 ** 3))
+            left = left & ~I_final
+            ids_left = [i for i in range(m) if left[i]]
+            m_left = len(ids_left)
+            e1, e2, b = np.zeros(3), np.zeros(3), 0.0
+            for i in np.flatnonzero(I_final):
+                e1 = e1 + N[:, i]
+                e2 = e2 + Pp[:, i]
+                b += (N[:, i] * Pp[:, i]).sum()
+            n2 = float(max_inl * max_inl)
+            a = 1 - (e1 @ e1) / n2
+            b = b / max_inl - (e1 @ e2) / n2
+            r = b / a
+            center = (e2 - r * e1) / max_inl
+            r = abs(r)
+            self.nr_segments += 1
+            self.radii.append(f32(r))
+            self.centers.append(center)
+            self.inliers.append(I_final.copy())
+            P2d = center + vec
+            dirv = P2d - center
+            n12 = np.linalg.norm(dirv)
+            mse = 0.0
+            for i in np.flatnonzero(I_final):
+                dd = np.linalg.norm(np.cross(dirv, P[:, i] - P2d)) / n12 - r
+                mse += dd * dd
+            self.MSEs.append(mse / max_inl)
+            self.P1.append(center.astype(f32))
+            self.P2.append(P2d.astype(f32))
+            self.P1P2_norm.append(f32(n12))
+            self.cylindrical.append(True)
+
+
+def cape_process(cloud, H, W, cw, ch, min_cos, max_merge_dist, cylinder=False):
+    """CAPE::process.  Returns seg_output, final planes (list of Seg), cells, plane grid map, eroded map and —
+    with cylinder=True — a dict with the cylinder results."""
     import cv2
     import sys
     sys.setrecursionlimit(20000)
@@ -444,7 +564,10 @@ def cape_process(cloud, H, W, cw, ch, min_cos, max_merge_dist):
         unassigned[cid] = True
         remaining += 1
     plane_map = np.zeros((ncy, ncx), np.int32)
+    cyl_map = np.zeros((ncy, ncx), np.int32)
     segs = []
+    rng = glibc_rand_stream(1)
+    cyl_segments, cyl2region = [], []
 
     def grow(x, y, n1, d1, act):
         idx = x + ncx * y
@@ -497,6 +620,27 @@ def cape_process(cloud, H, W, cw, ch, min_cos, max_merge_dist):
             for i in range(ncells):
                 if act[i]:
                     plane_map[i // ncx, i % ncx] = len(segs)
+        elif cylinder and activated > 5:      # extrusion (CAPE.cpp:179-216)
+            cy = CylRef(grid, act, rng)
+            cyl_segments.append(cy)
+            for sid in range(cy.nr_segments):
+                for f in Seg.FIELDS:
+                    setattr(acc, f, 0.0)
+                acc.nr_pts = 0
+                for c in np.flatnonzero(cy.inliers[sid]):
+                    acc.expand(grid[cy.local2global[c]])
+                acc.fit()
+                if float(acc.MSE) < cy.MSEs[sid]:
+                    segs.append(acc.copy())
+                    for c in np.flatnonzero(cy.inliers[sid]):
+                        g = cy.local2global[c]
+                        plane_map[g // ncx, g % ncx] = len(segs)
+                    cy.cylindrical[sid] = False
+                else:
+                    cyl2region.append((len(cyl_segments) - 1, sid))
+                    for c in np.flatnonzero(cy.inliers[sid]):
+                        g = cy.local2global[c]
+                        cyl_map[g // ncx, g % ncx] = len(cyl2region)
     npl = len(segs)
     assoc = np.zeros((npl, npl), bool)
     for r in range(ncy - 1):
@@ -556,6 +700,36 @@ def cape_process(cloud, H, W, cw, ch, min_cos, max_merge_dist):
             upd = (dist < max_dist) & (dist < dist_stack[o:o + npc])
             dist_stack[o:o + npc][upd] = dist[upd]
             seg_stack[o:o + npc][upd] = nr
+    cyl_eroded = np.zeros((ncy, ncx), np.uint8)
+    ncyl_final = 0
+    for i, (reg, sid) in enumerate(cyl2region if cylinder else []):   # CAPE.cpp:323-393
+        cy = cyl_segments[reg]
+        mask = (cyl_map == i + 1).astype(np.uint8)
+        er = cv2.erode(mask, cross)
+        if er.max() == 0:
+            continue
+        ncyl_final += 1
+        di = cv2.dilate(mask, square)
+        diff = cv2.subtract(di, er)
+        label = 50 + ncyl_final
+        cyl_eroded[er > 0] = label
+        P2 = cy.P2[sid]
+        P1P2 = (P2 - cy.P1[sid]).astype(f32)
+        n12, radius = float(cy.P1P2_norm[sid]), float(cy.radii[sid])
+        max_dist = f32(9 * cy.MSEs[sid])
+        for cid in np.flatnonzero(diff.ravel() > 0):
+            o = cid * npc
+            X, Y, Z = CX[o:o + npc], CY[o:o + npc], CZ[o:o + npc]
+            q = np.stack([X - P2[0], Y - P2[1], Z - P2[2]]).astype(f32)
+            c0 = (P1P2[1] * q[2]).astype(f32) - (P1P2[2] * q[1]).astype(f32)
+            c1 = (P1P2[2] * q[0]).astype(f32) - (P1P2[0] * q[2]).astype(f32)
+            c2 = (P1P2[0] * q[1]).astype(f32) - (P1P2[1] * q[0]).astype(f32)
+            nrm = np.sqrt((c0 * c0 + (c1 * c1 + c2 * c2).astype(f32)).astype(f32)).astype(f32)
+            dist = (nrm.astype(np.float64) / n12 - radius).astype(f32)
+            dist = (dist * dist).astype(f32)
+            upd = (Z > 0) & (dist < max_dist) & (dist < dist_stack[o:o + npc])
+            dist_stack[o:o + npc][upd] = dist[upd]
+            seg_stack[o:o + npc][upd] = label
     seg = np.zeros((H, W), np.uint8)
     for cr in range(ncy):
         for cc in range(ncx):
@@ -563,7 +737,16 @@ def cape_process(cloud, H, W, cw, ch, min_cos, max_merge_dist):
             blk = seg[cr * ch:(cr + 1) * ch, cc * cw:(cc + 1) * cw]
             if eroded_map[cr, cc] > 0:
                 blk[:] = eroded_map[cr, cc]
+            elif cyl_eroded[cr, cc] > 0:
+                blk[:] = cyl_eroded[cr, cc]
             else:
                 st = seg_stack[cid * npc:(cid + 1) * npc].reshape(ch, cw)
                 blk[st > 0] = st[st > 0]
+    if cylinder:
+        cyl = dict(nr_cylinders_final=ncyl_final, cyl_map=cyl_map, cyl_eroded=cyl_eroded,
+                   radius=np.array([cyl_segments[r].radii[s_] for r, s_ in cyl2region], f32),
+                   center=np.array([cyl_segments[r].centers[s_] for r, s_ in cyl2region]).reshape(-1, 3),
+                   axis=np.array([cyl_segments[r].axis for r, s_ in cyl2region]).reshape(-1, 3),
+                   mse=np.array([cyl_segments[r].MSEs[s_] for r, s_ in cyl2region]))
+        return seg, final, grid, plane_map, eroded_map, cyl
     return seg, final, grid, plane_map, eroded_map

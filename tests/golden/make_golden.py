@@ -43,11 +43,12 @@ def orb_fixture(name, w, h, scene, seed, nfeatures):
     print(name, "kps", len(R["kps"]), "cands", [len(c) for c in R["cands"]])
 
 
-def cape_fixture(name, w, h, scene, seed, unit, cell, max_merge):
+def cape_fixture(name, w, h, scene, seed, unit, cell, max_merge, cylinder=False):
     _, depth, K = drfe.synth_frame(w, h, scene, seed, unit)
     mc = float(np.float32(np.cos(np.pi / 12)))
     cloud = py_ref.depth_to_cloud(depth, *K, cell, cell)
-    seg, final, grid, pmap, emap = py_ref.cape_process(cloud, h, w, cell, cell, mc, max_merge)
+    res = py_ref.cape_process(cloud, h, w, cell, cell, mc, max_merge, cylinder=cylinder)
+    seg, final, grid, pmap, emap = res[:5]
     q = np.rint(depth / np.float32(unit) * 5000).astype(np.uint16)
     assert np.array_equal((q.astype(np.float32) * np.float32(1.0 / 5000.0) * np.float32(unit)), depth)
     sums = np.array([[getattr(s, f) for f in py_ref.Seg.FIELDS] for s in grid], np.float64)
@@ -62,8 +63,14 @@ def cape_fixture(name, w, h, scene, seed, unit, cell, max_merge):
                plane_d=np.array([p.d for p in final]), plane_nr_pts=np.array([p.nr_pts for p in final], np.int32),
                plane_mse=np.array([p.MSE for p in final], np.float32),
                plane_score=np.array([p.score for p in final], np.float32))
+    if cylinder:
+        c = res[5]
+        out.update(cylinder=np.int32(1), nr_cylinders_final=np.int32(c["nr_cylinders_final"]), cyl_map=c["cyl_map"],
+                   cyl_eroded=c["cyl_eroded"], cyl_radius=c["radius"], cyl_center=c["center"], cyl_axis=c["axis"],
+                   cyl_mse=c["mse"])
     np.savez_compressed(os.path.join(HERE, name), **out)
-    print(name, "planes", len(final), "planar cells", int(out["cell_planar"].sum()))
+    print(name, "planes", len(final), "planar cells", int(out["cell_planar"].sum()),
+          ("cylinders %d (final %d)" % (len(res[5]["radius"]), res[5]["nr_cylinders_final"])) if cylinder else "")
 
 
 if __name__ == "__main__":
@@ -72,3 +79,6 @@ if __name__ == "__main__":
     cape_fixture("cape_640x480_corridor_m.npz", 640, 480, 0, 20260000, 1.0, 20, 50.0)
     cape_fixture("cape_640x480_room_mm.npz", 640, 480, 2, 20260100, 1000.0, 20, 50.0)
     cape_fixture("cape_320x240_room_mm_cell10.npz", 320, 240, 1, 20260033, 1000.0, 10, 50.0)
+    # cylinder detection on (CylinderSeg.cpp; declared glibc rand() stream, seed 1 per frame)
+    cape_fixture("cape_640x480_pillars_mm_cyl.npz", 640, 480, 2, 20260100, 1000.0, 20, 50.0, cylinder=True)
+    cape_fixture("cape_640x480_pillars_m_cyl.npz", 640, 480, 2, 20260300, 1.0, 20, 50.0, cylinder=True)

@@ -37,6 +37,18 @@ def test_orb_oracle_matches_golden(orc, name):
     assert np.array_equal(desc, g["desc"])
 
 
+def test_glibc_rand_stream_matches_libc(orc):
+    """the declared rand() stream of CylinderSeg (App. B.9) is glibc's, checked against the libc of this box"""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (1, 20260000):
+        libc.srand(seed)
+        ref = np.array([libc.rand() for _ in range(1000)], np.int32)
+        assert np.array_equal(orc.glibc_rand(seed, 1000), ref)
+    libc.srand(1)
+    assert orc.glibc_rand(1, 2).tolist() == [1804289383, 846930886]
+
+
 def test_features_per_level_reference_values(orc):
     # SURVEY A.0: ORBextractor(1000, 1.2, 8, ...) -> mnFeaturesPerLevel
     assert orc.OrbOracle(1000).features_per_level() == [217, 181, 151, 126, 105, 87, 73, 60]
@@ -44,16 +56,29 @@ def test_features_per_level_reference_values(orc):
 
 
 @pytest.mark.parametrize("name", ["cape_640x480_corridor_m.npz", "cape_640x480_room_mm.npz",
-                                  "cape_320x240_room_mm_cell10.npz"])
+                                  "cape_320x240_room_mm_cell10.npz", "cape_640x480_pillars_mm_cyl.npz",
+                                  "cape_640x480_pillars_m_cyl.npz"])
 def test_cape_oracle_matches_golden(orc, name):
     g = load_golden(name)
     depth = g["depth_q"].astype(np.float32) * np.float32(1.0 / 5000.0) * g["unit"]
     h, w = depth.shape
     cell = int(g["cell"])
-    o = orc.CapeOracle(h, w, cell, cell, False, float(g["min_cos"]), float(g["max_merge"]))
+    cyl_on = "cylinder" in g
+    o = orc.CapeOracle(h, w, cell, cell, cyl_on, float(g["min_cos"]), float(g["max_merge"]))
     cloud = o.depth_to_cloud(depth, *[float(v) for v in g["K"]])
     assert crc(cloud) == g["cloud_crc"]
-    seg, planes = o.process(cloud)
+    if cyl_on:
+        seg, planes, ncyl_final, cyls = o.process_full(cloud)
+        assert ncyl_final == int(g["nr_cylinders_final"]) and len(cyls) == len(g["cyl_radius"]) > 0
+        cm, ce = o.cyl_maps()
+        assert np.array_equal(cm, g["cyl_map"]) and np.array_equal(ce, g["cyl_eroded"])
+        assert np.allclose(cyls["radius"], g["cyl_radius"], rtol=1e-6)
+        assert np.allclose(cyls["center"], g["cyl_center"], rtol=1e-7, atol=1e-7)
+        # the PCA axis sign is solver-defined (LAPACK there, Jacobi here)
+        assert np.allclose(np.abs(cyls["axis"]), np.abs(g["cyl_axis"]), atol=1e-9)
+        assert int(seg.max()) > 50, "a cylinder label (50 + k) is painted"
+    else:
+        seg, planes = o.process(cloud)
     cells = o.cells()
     assert np.array_equal(cells["planar"].astype(np.uint8), g["cell_planar"])
     assert np.array_equal(cells["nr_pts"], g["cell_nr_pts"])
