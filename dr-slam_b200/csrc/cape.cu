@@ -49,7 +49,31 @@ struct CapeDev {
   uint8_t* seg;                 // [B][H*W]
   int* status;
   struct CellSums* sums;        // [B][ncells] per-cell moment sums (k_cape_sums -> k_cape_fit)
+  // ---- cylinder detection (CylinderSeg.cpp, CAPE.cpp:179-216, 323-393); all null / 0 when it is off
+  int cyl;                      // CAPE(..., cylinder_detection, ...)
+  float cylK1, cylK2;           // RANSAC iteration bounds, float K of CylinderSeg.cpp:84 / :164
+  const uint32_t* rand_tab;     // declared rand() stream (glibc TYPE_3, seed 1), restarted per frame (App. B.9)
+  int rand_n;
+  double* cyl_scratch;          // [B][6][ncells] projected normals / means of the region being fitted
+  struct CylSub* subs;          // [B][max_sub] RANSAC sub-segments in creation order
+  int max_sub;
+  int* cyl_map;                 // [B][ncells] grid_cylinder_seg_map
+  uint8_t* cyl_eroded_map;      // [B][ncells] 50 + k
+  struct CylEq* cyl_eq;         // [B][kMaxPlanes+1] refinement parameters of final cylinder k (1-based)
+  drfe_cylinder* cyls;          // [B][max_sub] cylinder_segments_final (all cylinders found)
+  int* ncyl_found;              // [B]
+  int* ncyl_final;              // [B]
+  int border_rows;              // rows of border_vec per frame: 256 (planes) or 512 (+ cylinders)
 };
+
+// one RANSAC sub-segment of an extruded region: either re-fitted as a plane or kept as a cylinder
+struct CylSub {
+  drfe_plane ps;                // plane through the inlier cells (CAPE.cpp:186-193)
+  double center[3], axis[3], mse;
+  float radius, p1[3], p2[3], n12;
+  int is_cyl, label;            // label: plane number or cylinder number (1-based), set when numbering
+};
+struct CylEq { float p2[3], dir[3]; double n12, radius; float maxd; int pad; };
 
 // ---- 3x3 symmetric eigen-solve (cyclic Jacobi).  Mirrors eig3_sym() of the oracle
 // operation for operation; only + - * / sqrt fabs, no FMA.
@@ -366,6 +390,255 @@ __device__ __forceinline__ uint32_t bv_shr(const uint32_t* V, int nw, int w, int
   return r ? ((hi >> r) | (bv_get(V, nw, w + q + 1) << (32 - r))) : hi;
 }
 
+
+// ------------------------------------------------------------------ cylinders
+// CylinderSeg::CylinderSeg (CylinderSeg.cpp:7-247) for one grown region, run by one warp.  The
+// reference is a chain of sequential decisions (RANSAC draws from one rand() stream, MSAC sums
+// in ascending cell order); per-cell work (projection, hypothesis distances) is spread over the
+// lanes, every ordered double sum is done by one lane in the reference's order, and the small
+// 3-vector algebra is replicated on all lanes.  The operation order of every sum is the reference's (ascending cell order).
+struct CylCtx {
+  const drfe_plane* cells;      // Grid of this frame
+  const float* sums;            // smem [nc][9] or null
+  const int* npts;              // smem [nc]
+  const unsigned short* jobid;  // smem [nc]
+  int nc;
+  int* l2g;                     // smem [nc] local2global_map
+  int* ids_left;                // smem [nc]
+  int* inl;                     // smem [nc] inlier list of the accepted hypothesis
+  unsigned char* flag;          // smem [nc] bit0: ids_left_mask, bit1: I, bit2: I_final
+  double* D;                    // smem [nc]
+  double* sN;                   // global [3][nc] projected, normalised normals
+  double* sP;                   // global [3][nc] projected means
+  const uint32_t* rand_tab; int rand_n;
+  CylSub* subs; int max_sub;
+  unsigned short* subid;        // smem [nc] sub-segment of each cell (0xFFFF: none)
+  float K1, K2;
+  int* status;
+};
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+__device__ __noinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_plane& seedcell, int& rpos, int& nsub) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, nc = X.nc;
+  const double thr = 0.0225;                                 // cylinder_RANSAC_sqr_max_dist (Params.h:9)
+  // local2global_map: the region's cells in ascending order
+  {
+    int base = 0;
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+      const int c = c0 + lane;
+      const bool is = c < nc && X.jobid[c] == j;
+      const unsigned bal = __ballot_sync(FULL, is);
+      if (is) X.l2g[base + __popc(bal & ((1u << lane) - 1))] = c;
+      base += __popc(bal);
+    }
+  }
+  __syncwarp();
+  for (int q = lane; q < m; q += 32) {
+    const drfe_plane& g = X.cells[X.l2g[q]];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { X.sN[k * nc + q] = g.normal[k]; X.sP[k * nc + q] = g.mean[k]; }
+  }
+  __syncwarp();
+  // cov = [N -N][N -N]^T / (2m - 1): six ordered sums, one per lane
+  double c6[6];
+  {
+    double sacc = 0;
+    if (lane < 6) {
+      const int a = lane < 3 ? 0 : (lane < 5 ? 1 : 2), b = lane < 3 ? lane : (lane < 5 ? lane - 2 : 2);
+      for (int q = 0; q < m; ++q) sacc += X.sN[a * nc + q] * X.sN[b * nc + q];
+      sacc = (2.0 * sacc) / (double)(2 * m - 1);
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) c6[e] = __shfl_sync(FULL, sacc, e);
+  }
+  double S[3], V[3][3];
+  eig3_sym(c6, S, V);
+  if (S[2] / S[0] < 100.0) return;                           // Checkpoint 1 (CylinderSeg.cpp:53)
+  const double vec[3] = {V[0][0], V[1][0], V[2][0]};
+  for (int q = lane; q < m; q += 32) {
+    double Pq[3] = {X.sP[q], X.sP[nc + q], X.sP[2 * nc + q]}, Nq[3] = {X.sN[q], X.sN[nc + q], X.sN[2 * nc + q]};
+    const double pd = dot3(vec, Pq), nd = dot3(vec, Nq);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Pq[k] = Pq[k] - pd * vec[k]; Nq[k] = Nq[k] - nd * vec[k]; }
+    const double nn = sqrt((Nq[0] * Nq[0] + Nq[1] * Nq[1]) + Nq[2] * Nq[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { X.sP[k * nc + q] = Pq[k]; X.sN[k * nc + q] = Nq[k] / nn; }
+    X.ids_left[q] = q;
+    X.flag[q] = 1;
+  }
+  __syncwarp();
+  float K = X.K1;
+  int m_left = m;
+  while (m_left > 5 && (double)m_left > 0.1 * (double)m) {    // sequential RANSAC (:94)
+    double min_hyp = thr * (double)m_left;
+    const int accepted = (int)(0.9 * (double)m_left);
+    int max_inl = 0;
+    for (int q = lane; q < m; q += 32) X.flag[q] &= 1;
+    __syncwarp();
+    for (int k = 0; (float)k < K; ++k) {
+      if (rpos + 3 > X.rand_n) { if (lane == 0) atomicOr(X.status, 8); return; }
+      const int id1 = X.ids_left[(int)(X.rand_tab[rpos] % (unsigned)m_left)];
+      const int id2 = X.ids_left[(int)(X.rand_tab[rpos + 1] % (unsigned)m_left)];
+      const int id3 = X.ids_left[(int)(X.rand_tab[rpos + 2] % (unsigned)m_left)];
+      rpos += 3;
+      double e1[3], e2[3], t[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double n1 = X.sN[c * nc + id1], n2 = X.sN[c * nc + id2], n3 = X.sN[c * nc + id3];
+        const double p1 = X.sP[c * nc + id1], p2 = X.sP[c * nc + id2], p3 = X.sP[c * nc + id3];
+        e1[c] = (n1 + n2) + n3;
+        e2[c] = (p1 + p2) + p3;
+        t[c] = (n1 * p1 + n2 * p2) + n3 * p3;
+      }
+      const double a = 1.0 - dot3(e1, e1) / 9.0;
+      const double b = ((t[0] + t[1]) + t[2]) / 3.0 - dot3(e1, e2) / 9.0;
+      const double r = b / a;
+      double center[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) center[c] = (e2[c] - r * e1[c]) / 3.0;
+      const double rr = r * r;
+      for (int tq = lane; tq < m_left; tq += 32) {
+        const int i = X.ids_left[tq];
+        const double x = (X.sP[i] - r * X.sN[i]) - center[0], y = (X.sP[nc + i] - r * X.sN[nc + i]) - center[1],
+                     z = (X.sP[2 * nc + i] - r * X.sN[2 * nc + i]) - center[2];
+        const double d = ((x * x + y * y) + z * z) / rr;
+        X.D[i] = d;
+        X.flag[i] = (unsigned char)((X.flag[i] & 5) | ((d < thr) ? 2 : 0));
+      }
+      __syncwarp();
+      // MSAC truncated distance, ascending cell order (:137-148)
+      double dist = 0.0;
+      int inl = 0;
+      if (lane == 0) {
+        for (int tq = 0; tq < m_left; ++tq) {
+          const int i = X.ids_left[tq];
+          if (X.flag[i] & 2) { ++inl; dist += X.D[i]; }
+          else dist += thr;
+        }
+      }
+      dist = __shfl_sync(FULL, dist, 0);
+      inl = __shfl_sync(FULL, inl, 0);
+      if (dist < min_hyp) {
+        min_hyp = dist;
+        max_inl = inl;
+        for (int q = lane; q < m; q += 32) {
+          const unsigned char f = X.flag[q];
+          X.flag[q] = (unsigned char)((f & 3) | (((f & 3) == 3) ? 4 : 0));
+        }
+        __syncwarp();
+        if (inl > accepted) break;
+      }
+      __syncwarp();
+    }
+    if (max_inl < 6) break;                                   // Checkpoint 2 (:160)
+    K = X.K2;
+    // inlier list; remove the inliers from the remaining cells (:167-176)
+    {
+      int nin = 0, nleft = 0;
+      for (int q0 = 0; q0 < m; q0 += 32) {
+        const int q = q0 + lane;
+        const unsigned char f = q < m ? X.flag[q] : 0;
+        const bool fin = (f & 4) != 0, lf = (f & 1) && !fin;
+        const unsigned bi = __ballot_sync(FULL, fin), bl = __ballot_sync(FULL, lf);
+        if (fin) X.inl[nin + __popc(bi & ((1u << lane) - 1))] = q;
+        if (lf) X.ids_left[nleft + __popc(bl & ((1u << lane) - 1))] = q;
+        if (q < m) X.flag[q] = (unsigned char)((lf ? 1 : 0) | (f & 4));
+        nin += __popc(bi);
+        nleft += __popc(bl);
+      }
+      m_left = nleft;
+    }
+    __syncwarp();
+    // LLS over all inliers (:178-199): seven ordered sums, one per lane
+    double e1[3], e2[3], bsum;
+    {
+      double acc = 0.0;
+      if (lane < 7) {
+        for (int tq = 0; tq < max_inl; ++tq) {
+          const int i = X.inl[tq];
+          double v;
+          if (lane < 3) v = X.sN[lane * nc + i];
+          else if (lane < 6) v = X.sP[(lane - 3) * nc + i];
+          else v = (X.sN[i] * X.sP[i] + X.sN[nc + i] * X.sP[nc + i]) + X.sN[2 * nc + i] * X.sP[2 * nc + i];
+          acc += v;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { e1[c] = __shfl_sync(FULL, acc, c); e2[c] = __shfl_sync(FULL, acc, 3 + c); }
+      bsum = __shfl_sync(FULL, acc, 6);
+    }
+    const double n2 = (double)(max_inl * max_inl);
+    const double a = 1.0 - dot3(e1, e1) / n2;
+    bsum = bsum / (double)max_inl;
+    bsum = bsum - dot3(e1, e2) / n2;
+    double r = bsum / a;
+    double center[3], P2d[3], dir[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) center[c] = (e2[c] - r * e1[c]) / (double)max_inl;
+    if (r < 0) r = -r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { P2d[c] = center[c] + vec[c]; dir[c] = P2d[c] - center[c]; }
+    const double n12 = sqrt(dir[0] * dir[0] + (dir[1] * dir[1] + dir[2] * dir[2]));
+    // MSE of the inliers' point-to-axis distances (:206-226)
+    for (int tq = lane; tq < max_inl; tq += 32) {
+      const int i = X.inl[tq];
+      const drfe_plane& g = X.cells[X.l2g[i]];
+      const double q0 = g.mean[0] - P2d[0], q1 = g.mean[1] - P2d[1], q2 = g.mean[2] - P2d[2];
+      const double cx = dir[1] * q2 - dir[2] * q1, cy = dir[2] * q0 - dir[0] * q2, cz = dir[0] * q1 - dir[1] * q0;
+      const double dd = sqrt(cx * cx + (cy * cy + cz * cz)) / n12 - r;
+      X.D[i] = dd * dd;
+    }
+    __syncwarp();
+    double mse = 0.0;
+    if (lane == 0) {
+      for (int tq = 0; tq < max_inl; ++tq) mse += X.D[X.inl[tq]];
+      mse = mse / (double)max_inl;
+    }
+    mse = __shfl_sync(FULL, mse, 0);
+    // plane through the same cells: clearPoints + expandSegment in ascending order + fitPlane
+    // (CAPE.cpp:186-193); ten ordered sums, one per lane
+    double pacc = 0.0;
+    int pn = 0;
+    if (lane < 9) {
+      for (int tq = 0; tq < max_inl; ++tq) {
+        const int c = X.l2g[X.inl[tq]];
+        pacc += X.sums ? (double)X.sums[c * 9 + lane] : (&X.cells[c].x_acc)[lane];
+      }
+    } else if (lane == 9) {
+      for (int tq = 0; tq < max_inl; ++tq) pn += X.npts[X.l2g[X.inl[tq]]];
+    }
+    double ps9[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ps9[k] = __shfl_sync(FULL, pacc, k);
+    pn = __shfl_sync(FULL, pn, 9);
+    if (nsub >= X.max_sub) { if (lane == 0) atomicOr(X.status, 16); return; }
+    int is_cyl = 0;
+    if (lane == 0) {
+      CylSub& o = X.subs[nsub];
+      o.ps = seedcell;
+      o.ps.x_acc = ps9[0]; o.ps.y_acc = ps9[1]; o.ps.z_acc = ps9[2]; o.ps.xx_acc = ps9[3]; o.ps.yy_acc = ps9[4];
+      o.ps.zz_acc = ps9[5]; o.ps.xy_acc = ps9[6]; o.ps.xz_acc = ps9[7]; o.ps.yz_acc = ps9[8];
+      o.ps.nr_pts = pn;
+      fit_plane(o.ps);
+      is_cyl = ((double)o.ps.MSE < mse) ? 0 : 1;             // model selection (CAPE.cpp:195)
+      o.is_cyl = is_cyl;
+      o.label = 0;
+      o.mse = mse;
+      o.radius = (float)r;
+      o.n12 = (float)n12;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        o.center[c] = center[c]; o.axis[c] = vec[c];
+        o.p1[c] = (float)center[c]; o.p2[c] = (float)P2d[c];
+      }
+    }
+    for (int tq = lane; tq < max_inl; tq += 32) X.subid[X.l2g[X.inl[tq]]] = (unsigned short)nsub;
+    ++nsub;
+    __syncwarp();
+  }
+}
+
 enum { BV_FL = 0, BV_FR, BV_FU, BV_FD, BV_U, BV_A, BV_B, BV_M, BV_H, BV_C0, BV_CL, BV_R0, BV_RL, BV_VALID, BV_COUNT };
 
 template <int THREADS>
@@ -387,8 +660,14 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   short* job_seed = reinterpret_cast<short*>(jobid + nc);         // [max_jobs] seed cell of each job
   uint8_t* pmap = reinterpret_cast<uint8_t*>(job_seed + P.max_jobs);   // [nc] grid_plane_seg_map (labels 1..255)
   uint8_t* job_label = pmap + nc;                                 // [max_jobs] 0 / plane label of the job
+  unsigned short* job_nact = reinterpret_cast<unsigned short*>((reinterpret_cast<uintptr_t>(job_label + P.max_jobs) + 1) & ~(uintptr_t)1);   // [max_jobs] cells of the job
+  // cylinder detection only: [max_jobs+1] first sub-segment of each job, RANSAC flags, distances, inlier list
+  unsigned short* job_sub0 = job_nact + P.max_jobs;
+  unsigned char* cflag = reinterpret_cast<unsigned char*>(job_sub0 + P.max_jobs + 1);
+  double* cylD = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(cflag + nc) + 7) & ~(uintptr_t)7);
+  int* cinl = reinterpret_cast<int*>(cylD + nc);
   __shared__ int merge[kMaxPlanes + 1];
-  __shared__ int s_np, s_njobs;
+  __shared__ int s_np, s_njobs, s_ncyl;
   uint32_t* FL = bv + BV_FL * nw; uint32_t* FR = bv + BV_FR * nw; uint32_t* FU = bv + BV_FU * nw; uint32_t* FD = bv + BV_FD * nw;
   uint32_t* U = bv + BV_U * nw; uint32_t* A = bv + BV_A * nw; uint32_t* Bv = bv + BV_B * nw;
   uint32_t* M = bv + BV_M * nw; uint32_t* Hh = bv + BV_H * nw;
@@ -608,7 +887,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
           if (is_job) jobid[c] = (unsigned short)njobs;
         }
       }
-      if (is_job) { if (lane == 0) job_seed[njobs] = seed; ++njobs; }
+      if (is_job) { if (lane == 0) { job_seed[njobs] = seed; job_nact[njobs] = (unsigned short)nact; } ++njobs; }
       remaining -= nact;
       __syncwarp();
       DRFE_TICK(c_acc) s_nact += nact;
@@ -655,21 +934,69 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     job_label[j] = ps.score > 100 ? 1 : 0;                   // it is a plane (:163)
   }
   __syncthreads();
+  // ---- extruded regions (cylinder_detection, CAPE.cpp:179-216): a region of more than 5 cells that is not
+  // a plane goes through CylinderSeg; regions are taken in job order because they share one rand() stream.
+  CylSub* subs = P.cyl ? P.subs + (long long)f * P.max_sub : nullptr;
+  unsigned short* subid = reinterpret_cast<unsigned short*>(bin);   // bin[] is free after the seed loop
+  if (P.cyl) {
+    for (int c = tid; c < nc; c += THREADS) subid[c] = 0xFFFF;
+    __syncthreads();
+    if (wid == 0) {
+      CylCtx X;
+      X.cells = cells; X.sums = sums_smem ? sums : nullptr; X.npts = npts; X.jobid = jobid; X.nc = nc;
+      X.l2g = list; X.ids_left = reinterpret_cast<int*>(mse); X.inl = cinl; X.flag = cflag; X.D = cylD;
+      X.sN = P.cyl_scratch + (long long)f * 6 * nc; X.sP = X.sN + 3 * nc;
+      X.rand_tab = P.rand_tab; X.rand_n = P.rand_n; X.subs = subs; X.max_sub = P.max_sub; X.subid = subid;
+      X.K1 = P.cylK1; X.K2 = P.cylK2; X.status = P.status;
+      int rpos = 0, nsub = 0;
+      for (int j = 0; j < njobs; ++j) {
+        if (lane == 0) job_sub0[j] = (unsigned short)nsub;
+        if (!job_label[j] && job_nact[j] > 5) cyl_job(X, j, job_nact[j], cells[job_seed[j]], rpos, nsub);
+      }
+      if (lane == 0) job_sub0[njobs] = (unsigned short)nsub;
+    }
+    __syncthreads();
+  }
+  // ---- labels in the reference's push order: job by job; an extruded job contributes its sub-segments
   if (tid == 0) {
-    int np = 0;
+    int np = 0, ncyl = 0;
+    auto next_plane = [&]() -> int {
+      if (np < kMaxPlanes) return ++np;
+      atomicOr(P.status, 1);
+      return 0;
+    };
     for (int j = 0; j < njobs; ++j) {
-      if (!job_label[j]) continue;
-      if (np < kMaxPlanes) job_label[j] = (uint8_t)(++np);
-      else { job_label[j] = 0; atomicOr(P.status, 1); }
+      if (job_label[j]) { job_label[j] = (uint8_t)next_plane(); continue; }
+      if (!P.cyl) continue;
+      for (int s = job_sub0[j]; s < job_sub0[j + 1]; ++s) {
+        if (!subs[s].is_cyl) {
+          const int l = next_plane();
+          subs[s].label = l;
+          if (l) segs[l - 1] = subs[s].ps;
+        } else {
+          subs[s].label = ++ncyl;                              // cylinder2region_map (CAPE.cpp:203-204)
+          drfe_cylinder cyo;
+          cyo.radius = subs[s].radius;
+          for (int k = 0; k < 3; ++k) { cyo.center[k] = subs[s].center[k]; cyo.axis[k] = subs[s].axis[k]; }
+          P.cyls[(long long)f * P.max_sub + ncyl - 1] = cyo;   // cylinder_segments_final (:434-445)
+        }
+      }
     }
     s_np = np;
+    s_ncyl = ncyl;
   }
   __syncthreads();
   for (int j = tid; j < njobs; j += THREADS)
     if (job_label[j]) segs[job_label[j] - 1] = jobseg[j];
   for (int c = tid; c < nc; c += THREADS) {
     const int j = jobid[c];
-    pmap[c] = (j == 0xFFFF) ? 0 : job_label[j];
+    int pl = (j == 0xFFFF) ? 0 : job_label[j], cl = 0;
+    if (P.cyl && subid[c] != 0xFFFF) {
+      const CylSub& sb = subs[subid[c]];
+      if (sb.is_cyl) cl = sb.label; else pl = sb.label;
+    }
+    pmap[c] = (uint8_t)pl;
+    if (P.cyl) P.cyl_map[(long long)f * nc + c] = cl;
   }
   __syncthreads();
   // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
@@ -709,7 +1036,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   __syncthreads();
   // ---- per final plane: cell mask, erode (cross), dilate (square) (CAPE.cpp:254-291)
   uint8_t* eroded_map = P.eroded_map + (long long)f * nc;
-  uint32_t* border = P.border_vec + (long long)f * (kMaxPlanes + 1) * nw;
+  uint32_t* border = P.border_vec + (long long)f * P.border_rows * nw;
   for (int c = tid; c < nc; c += THREADS) eroded_map[c] = 0;
   int nfinal = 0;
   for (int i = 0; i < np; ++i) {
@@ -754,6 +1081,60 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     }
     __syncthreads();
   }
+  // ---- cylinders: same erode / dilate per cylinder region (CAPE.cpp:323-357); border rows follow the planes'
+  if (P.cyl) {
+    uint8_t* cyl_eroded = P.cyl_eroded_map + (long long)f * nc;
+    const int* cyl_map = P.cyl_map + (long long)f * nc;
+    for (int c = tid; c < nc; c += THREADS) cyl_eroded[c] = 0;
+    const int ncyl = s_ncyl;
+    int ncf = 0;
+    for (int i = 0; i < ncyl; ++i) {
+      for (int w = tid; w < nw; w += THREADS) {
+        uint32_t m = 0;
+        const int cend = min(32, nc - (w << 5));
+        for (int b = 0; b < cend; ++b)
+          if (cyl_map[(w << 5) + b] == i + 1) m |= 1u << b;
+        M[w] = m;
+      }
+      __syncthreads();
+      int any = 0;
+      uint32_t er_w[4];
+      for (int w = tid, k = 0; w < nw; w += THREADS, ++k) {
+        const uint32_t m = M[w];
+        const uint32_t l1 = bv_shl(M, nw, w, 1), r1 = bv_shr(M, nw, w, 1);
+        const uint32_t e = m & (l1 | C0[w]) & (r1 | CL[w]) & (bv_shl(M, nw, w, ncx) | R0[w]) & (bv_shr(M, nw, w, ncx) | RL[w]);
+        Hh[w] = m | (l1 & ~C0[w]) | (r1 & ~CL[w]);
+        if (k < 4) er_w[k] = e;
+        any |= (e != 0);
+      }
+      const int keep = __syncthreads_or(any);
+      if (keep && ncf + 1 + 50 > 255) { if (tid == 0) atomicOr(P.status, 32); __syncthreads(); continue; }
+      if (keep) {
+        const int cyl_nr = ++ncf;
+        if (tid == 0) {
+          // the sub-segment with cylinder number i + 1
+          int s = 0;
+          for (int q = 0; q < job_sub0[njobs]; ++q)
+            if (subs[q].is_cyl && subs[q].label == i + 1) s = q;
+          const CylSub& sb = subs[s];
+          CylEq eqo;
+          for (int k = 0; k < 3; ++k) { eqo.p2[k] = sb.p2[k]; eqo.dir[k] = sb.p2[k] - sb.p1[k]; }
+          eqo.n12 = (double)sb.n12; eqo.radius = (double)sb.radius;
+          eqo.maxd = (float)(9.0 * sb.mse); eqo.pad = 0;
+          P.cyl_eq[(long long)f * (kMaxPlanes + 1) + cyl_nr] = eqo;
+        }
+        for (int w = tid, k = 0; w < nw; w += THREADS, ++k) {
+          const uint32_t e = er_w[k & 3];
+          const uint32_t d = (Hh[w] | bv_shl(Hh, nw, w, ncx) | bv_shr(Hh, nw, w, ncx)) & VALID[w];
+          border[(long long)(kMaxPlanes + 1 + cyl_nr) * nw + w] = d & ~e;
+          uint32_t bits = e;
+          while (bits) { const int c = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; cyl_eroded[c] = (uint8_t)(50 + cyl_nr); }
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { P.ncyl_final[f] = ncf; P.ncyl_found[f] = ncyl; }
+  }
   int* plane_map = P.plane_map + (long long)f * nc;
   for (int c = tid; c < nc; c += THREADS) plane_map[c] = pmap[c];
   if (tid == 0) P.nplanes[f] = nfinal;
@@ -765,6 +1146,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 // float distance, subject to < 9*MSE, strict '<' against the running minimum which starts at
 // the bit pattern memset(...,100,...) leaves (0x64646464, CAPE.cpp:60).  Cells inside an
 // eroded mask are painted whole (:410-412).
+template <bool CYL>
 __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__ Pp, int nframes) {
   const CapeDev& P = *Pp;
   const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -775,13 +1157,14 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
   const long long N = (long long)P.H * P.W;
   uint8_t* out = P.seg + (long long)f * N + (long long)(cr * P.ch) * P.W + cc * cw;
   const int er = P.eroded_map[(long long)f * P.ncells + cell];
+  const int cer = CYL ? P.cyl_eroded_map[(long long)f * P.ncells + cell] : 0;
   // planes whose dilated-minus-eroded mask contains this cell (bit p of bits[] = final plane p)
   const int nw = (P.ncells + 31) >> 5, npl = P.nplanes[f];
-  const uint32_t* bvec = P.border_vec + (long long)f * (kMaxPlanes + 1) * nw + (cell >> 5);
-  uint32_t bits[8];
-  uint32_t anyb = 0;
+  const uint32_t* bvec = P.border_vec + (long long)f * P.border_rows * nw + (cell >> 5);
+  uint32_t bits[8], cbits[8];
+  uint32_t anyb = 0, anyc = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) bits[k] = 0;
+  for (int k = 0; k < 8; ++k) { bits[k] = 0; cbits[k] = 0; }
   for (int p0 = 1; p0 <= npl; p0 += 32) {
     const int p = p0 + lane;
     const bool in = p <= npl && ((bvec[(long long)p * nw] >> (cell & 31)) & 1u);
@@ -794,8 +1177,25 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
     }
     anyb |= bal;
   }
-  if (er > 0 || anyb == 0) {
-    for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)er; }
+  if (CYL) {
+    const int ncf = P.ncyl_final[f];
+    const uint32_t* cvec = bvec + (long long)(kMaxPlanes + 1) * nw;
+    for (int p0 = 1; p0 <= ncf; p0 += 32) {
+      const int p = p0 + lane;
+      const bool in = p <= ncf && ((cvec[(long long)p * nw] >> (cell & 31)) & 1u);
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k == (p0 >> 5)) cbits[k] |= bal << 1;
+        if (k == (p0 >> 5) + 1) cbits[k] |= bal >> 31;
+      }
+      anyc |= bal;
+    }
+  }
+  // cells inside an eroded plane mask are painted whole, then cells inside an eroded cylinder mask (:410-416)
+  const int whole = er > 0 ? er : (cer > 0 ? cer : ((anyb | anyc) == 0 ? 0 : -1));
+  if (whole >= 0) {
+    for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)whole; }
     return;
   }
   const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
@@ -817,6 +1217,25 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
         const float v = x * e.x + y * e.y + z * e.z + e.w;
         const float dist = v * v;
         if (dist < maxd[p] && dist < best) { best = dist; lab = p; }
+      }
+    }
+    if (CYL && anyc && z > 0.f) {
+      // point-to-axis distance minus radius (CAPE.cpp:375-385): float cross / norm, double divide
+      const CylEq* ceq = P.cyl_eq + (long long)f * (kMaxPlanes + 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint32_t b = cbits[k];
+        while (b) {
+          const int p = k * 32 + __ffs(b) - 1;
+          b &= b - 1;
+          const CylEq& e = ceq[p];
+          const float q0 = x - e.p2[0], q1 = y - e.p2[1], q2 = z - e.p2[2];
+          const float c0 = e.dir[1] * q2 - e.dir[2] * q1, c1 = e.dir[2] * q0 - e.dir[0] * q2, c2 = e.dir[0] * q1 - e.dir[1] * q0;
+          const float nrm = sqrtf(c0 * c0 + (c1 * c1 + c2 * c2));
+          float dist = (float)((double)nrm / e.n12 - e.radius);
+          dist = dist * dist;
+          if (dist < e.maxd && dist < best) { best = dist; lab = 50 + p; }
+        }
       }
     }
     const int lr = i / cw, lc = i - lr * cw;
@@ -863,6 +1282,25 @@ static int cape_alloc(drfe_cape* h, T** p, size_t count) {
   return DRFE_OK;
 }
 
+// glibc rand(): TYPE_3 additive feedback generator, srand(seed) then n outputs (stdlib/random_r.c).
+// CylinderSeg draws its RANSAC triplets from the process-global rand() (CylinderSeg.cpp:111-113);
+// the declared stream is this one, seed 1, restarted for every frame.
+static void glibc_rand_table(uint32_t seed, int n, std::vector<uint32_t>& out) {
+  std::vector<uint32_t> r(344 + (size_t)n);
+  int32_t w = (int32_t)(seed ? seed : 1);
+  r[0] = (uint32_t)w;
+  for (int i = 1; i < 31; ++i) {
+    const int32_t hi = w / 127773, lo = w % 127773;
+    w = 16807 * lo - 2836 * hi;
+    if (w < 0) w += 2147483647;
+    r[i] = (uint32_t)w;
+  }
+  for (int i = 31; i < 34; ++i) r[i] = r[i - 31];
+  for (size_t i = 34; i < r.size(); ++i) r[i] = r[i - 31] + r[i - 3];
+  out.resize(n);
+  for (int i = 0; i < n; ++i) out[i] = r[344 + i] >> 1;
+}
+
 extern "C" {
 
 int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe_cape** out) {
@@ -871,10 +1309,6 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   if (pr->depth_height < 1 || pr->depth_width < 1 || pr->cell_width < 2 || pr->cell_height < 2 || max_batch < 1 ||
       pr->cell_width * pr->cell_height < 16 || pr->depth_width / pr->cell_width < 2 || pr->depth_height / pr->cell_height < 2) {
     set_error("drfe_cape_create: invalid parameters");
-    return DRFE_ERR_ARG;
-  }
-  if (pr->cylinder_detection) {
-    set_error("drfe_cape_create: cylinder detection is not implemented yet");
     return DRFE_ERR_ARG;
   }
   int ndev = 0;
@@ -907,7 +1341,30 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.jobseg, (size_t)D.max_jobs * B);
   rc |= cape_alloc(h, &D.plane_map, nc * B);
   rc |= cape_alloc(h, &D.eroded_map, nc * B);
-  rc |= cape_alloc(h, &D.border_vec, (size_t)(kMaxPlanes + 1) * ((nc + 31) / 32) * B);
+  D.cyl = pr->cylinder_detection ? 1 : 0;
+  D.border_rows = (kMaxPlanes + 1) * (D.cyl ? 2 : 1);
+  rc |= cape_alloc(h, &D.border_vec, (size_t)D.border_rows * ((nc + 31) / 32) * B);
+  if (D.cyl) {
+    // CylinderSeg.cpp:82-84,164: float K = log(1 - p_success) / log(1 - pow(w, 3)), p_success = 0.8f, w = 0.33f then 0.5
+    D.cylK1 = (float)((double)logf(1.0f - 0.8f) / log(1.0 - pow((double)0.33f, 3)));
+    D.cylK2 = (float)((double)logf(1.0f - 0.8f) / log(1.0 - pow(0.5, 3)));
+    D.max_sub = (int)nc / 6 + 1;
+    D.rand_n = 1 << 16;
+    std::vector<uint32_t> tab;
+    glibc_rand_table(1u, D.rand_n, tab);
+    uint32_t* d_tab = nullptr;
+    rc |= cape_alloc(h, &d_tab, (size_t)D.rand_n);
+    if (!rc && cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = DRFE_ERR_CUDA;
+    D.rand_tab = d_tab;
+    rc |= cape_alloc(h, &D.cyl_scratch, (size_t)6 * nc * B);
+    rc |= cape_alloc(h, &D.subs, (size_t)D.max_sub * B);
+    rc |= cape_alloc(h, &D.cyl_map, nc * B);
+    rc |= cape_alloc(h, &D.cyl_eroded_map, nc * B);
+    rc |= cape_alloc(h, &D.cyl_eq, (size_t)(kMaxPlanes + 1) * B);
+    rc |= cape_alloc(h, &D.cyls, (size_t)D.max_sub * B);
+    rc |= cape_alloc(h, &D.ncyl_found, B);
+    rc |= cape_alloc(h, &D.ncyl_final, B);
+  }
   rc |= cape_alloc(h, &D.segs, (size_t)(kMaxPlanes + 1) * B);
   rc |= cape_alloc(h, &D.planes, (size_t)kMaxPlanes * B);
   rc |= cape_alloc(h, &D.plane_eq, (size_t)(kMaxPlanes + 1) * B);
@@ -923,7 +1380,9 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   }
   {
     const size_t nw = (nc + 31) / 32;
-    const size_t base = (size_t)BV_COUNT * nw * 4 + kHistBins * kHistBins * 4 + 256 * 8 * 4 + nc * (4 + 4 + 4 + 2 + 2 + 1) + (nc / 4 + 1) * 3 + 64;
+    const size_t mj = nc / 4 + 1;
+    const size_t base = (size_t)BV_COUNT * nw * 4 + kHistBins * kHistBins * 4 + 256 * 8 * 4 + nc * (4 + 4 + 4 + 2 + 2 + 1) + mj * 3 + 2 +
+                        mj * 2 + (D.cyl ? (mj + 1) * 2 + nc * (1 + 8 + 4) + 16 : 0) + 64;
     D.grid_sums_smem = (base + nc * 36 <= 160 * 1024) ? 1 : 0;
     h->grid_smem = base + (D.grid_sums_smem ? nc * 36 : 0);
     if (h->grid_smem > 200 * 1024 || nw > 4 * 128) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
@@ -985,7 +1444,8 @@ static int cape_run(drfe_cape* h, int nframes) {
     const long long tot = (long long)h->hd.H * h->hd.W * nframes;
     DRFE_LAUNCH(k_cape_clear_margin, (unsigned)((tot + 255) / 256), 256, 0, st, h->dd, nframes);
   }
-  DRFE_LAUNCH(k_cape_refine, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, nframes);
+  if (h->hd.cyl) DRFE_LAUNCH(k_cape_refine<true>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, nframes);
+  else DRFE_LAUNCH(k_cape_refine<false>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, nframes);
   h->timer.mark("refine", st);
   h->last_frames = nframes;
   h->pending = true;
@@ -1045,7 +1505,6 @@ int drfe_cape_sync(drfe_cape* h) {
 
 int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
                        drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders) {
-  (void)cylinders; (void)cyl_cap;
   if (!h || !nr_planes) { set_error("drfe_cape_download: null argument"); return DRFE_ERR_ARG; }
   if (!h->pending) { set_error("drfe_cape_download: nothing enqueued"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -1061,11 +1520,20 @@ int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int p
     DRFE_CUDA(cudaMemcpy2DAsync(planes, (size_t)plane_cap * sizeof(drfe_plane), h->hd.planes, (size_t)kMaxPlanes * sizeof(drfe_plane),
                                 w, nf, cudaMemcpyDeviceToHost, st));
   }
+  if (h->hd.cyl) {
+    if (nr_cylinders) DRFE_CUDA(cudaMemcpyAsync(nr_cylinders, h->hd.ncyl_final, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (cylinders && cyl_cap > 0) {
+      const size_t w = (size_t)std::min(cyl_cap, h->hd.max_sub) * sizeof(drfe_cylinder);
+      DRFE_CUDA(cudaMemcpy2DAsync(cylinders, (size_t)cyl_cap * sizeof(drfe_cylinder), h->hd.cyls, (size_t)h->hd.max_sub * sizeof(drfe_cylinder),
+                                  w, nf, cudaMemcpyDeviceToHost, st));
+    }
+  }
   DRFE_CUDA(cudaStreamSynchronize(st));
-  if (nr_cylinders) for (int f = 0; f < nf; ++f) nr_cylinders[f] = 0;
+  if (!h->hd.cyl && nr_cylinders) for (int f = 0; f < nf; ++f) nr_cylinders[f] = 0;
   if (status) {
     cudaMemsetAsync(h->hd.status, 0, sizeof(int), st);
-    set_error("CAPE: more than %d planes in a frame", kMaxPlanes);
+    set_error("CAPE: device-side capacity exceeded (status %d: 1 = more than %d planes, 2 = seed rejected, 4 = regions, "
+              "8 = rand() table, 16 = cylinder sub-segments, 32 = cylinder labels)", status, kMaxPlanes);
     return DRFE_ERR_CAPACITY;
   }
   if (planes)
@@ -1121,6 +1589,26 @@ int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16) {
   DeviceScope ds(h->device);
   DRFE_CUDA(cudaStreamSynchronize(h->stream));
   DRFE_CUDA(cudaMemcpy(out16, h->hd.dbg + 16 * frame, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return DRFE_OK;
+}
+int drfe_cape_cylinders_found(drfe_cape* h, int* counts) {
+  if (!h || !counts) { set_error("drfe_cape_cylinders_found: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_cape_cylinders_found: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!h->hd.cyl) { for (int f = 0; f < h->last_frames; ++f) counts[f] = 0; return DRFE_OK; }
+  DRFE_CUDA(cudaMemcpyAsync(counts, h->hd.ncyl_found, h->last_frames * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  return DRFE_OK;
+}
+int drfe_cape_get_cyl_maps(drfe_cape* h, int frame, int32_t* cyl_map, uint8_t* cyl_eroded_map) {
+  int rc = cape_frame_ok(h, frame);
+  if (rc) return rc;
+  if (!h->hd.cyl) { set_error("drfe_cape_get_cyl_maps: cylinder detection is off"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  const size_t nc = h->hd.ncells;
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  if (cyl_map) DRFE_CUDA(cudaMemcpy(cyl_map, h->hd.cyl_map + nc * frame, nc * sizeof(int), cudaMemcpyDeviceToHost));
+  if (cyl_eroded_map) DRFE_CUDA(cudaMemcpy(cyl_eroded_map, h->hd.cyl_eroded_map + nc * frame, nc, cudaMemcpyDeviceToHost));
   return DRFE_OK;
 }
 int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t* eroded_map) {

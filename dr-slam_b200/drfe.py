@@ -63,7 +63,7 @@ SYMBOLS = [
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
-    "drfe_cape_get_grid_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
+    "drfe_cape_get_grid_maps", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
 ]
 
 _lib = None
@@ -124,6 +124,8 @@ def lib():
     L.drfe_cape_get_cloud.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_get_cells.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_get_grid_maps.argtypes = [vp, C.c_int, vp, vp]
+    L.drfe_cape_cylinders_found.argtypes = [vp, vp]
+    L.drfe_cape_get_cyl_maps.argtypes = [vp, C.c_int, vp, vp]
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
     L.drfe_cape_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
@@ -341,6 +343,8 @@ class CAPE:
         self.L.drfe_cape_num_cells(self.h, C.byref(cx), C.byref(cy))
         self.ncx, self.ncy = cx.value, cy.value
         self.plane_cap = 255
+        self.cylinder_detection = bool(cylinder_detection)
+        self.cyl_cap = (self.ncx * self.ncy) // 6 + 1 if cylinder_detection else 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -359,21 +363,38 @@ class CAPE:
         seg = np.empty((self.H, self.W), np.uint8)
         planes = np.zeros(self.plane_cap, PLANE_DTYPE)
         npl, ncyl = C.c_int32(0), C.c_int32(0)
+        cyls = np.zeros(max(self.cyl_cap, 1), CYL_DTYPE)
+        self._nframes = 1
         _check(self.L.drfe_cape_process(self.h, _ptr(cloud), _ptr(seg), _ptr(planes), self.plane_cap, C.byref(npl),
-                                        None, 0, C.byref(ncyl)))
+                                        _ptr(cyls), self.cyl_cap, C.byref(ncyl)))
         if seg_output is not None:
             seg_output[seg > 0] = seg[seg > 0]
             seg = seg_output
-        return npl.value, ncyl.value, seg, planes[:npl.value].copy(), []
+        return npl.value, ncyl.value, seg, planes[:npl.value].copy(), cyls[:self.cylinders_found()[0]].copy()
 
     def process_depth(self, depth, fx, fy, cx, cy):
         depth = np.ascontiguousarray(depth, np.float32)
         seg = np.empty((self.H, self.W), np.uint8)
         planes = np.zeros(self.plane_cap, PLANE_DTYPE)
         npl, ncyl = C.c_int32(0), C.c_int32(0)
+        cyls = np.zeros(max(self.cyl_cap, 1), CYL_DTYPE)
+        self._nframes = 1
         _check(self.L.drfe_cape_process_depth(self.h, _ptr(depth), depth.strides[0] // 4, fx, fy, cx, cy, _ptr(seg),
-                                              _ptr(planes), self.plane_cap, C.byref(npl), None, 0, C.byref(ncyl)))
-        return npl.value, ncyl.value, seg, planes[:npl.value].copy(), []
+                                              _ptr(planes), self.plane_cap, C.byref(npl), _ptr(cyls), self.cyl_cap,
+                                              C.byref(ncyl)))
+        return npl.value, ncyl.value, seg, planes[:npl.value].copy(), cyls[:self.cylinders_found()[0]].copy()
+
+    def cylinders_found(self):
+        """length of cylinder_segments_final per frame of the last call (CAPE.cpp:434-445)"""
+        out = np.zeros(max(getattr(self, "_nframes", 1) or 1, 1), np.int32)
+        _check(self.L.drfe_cape_cylinders_found(self.h, _ptr(out)))
+        return out
+
+    def cyl_maps(self, frame=0):
+        cm = np.zeros((self.ncy, self.ncx), np.int32)
+        em = np.zeros((self.ncy, self.ncx), np.uint8)
+        _check(self.L.drfe_cape_get_cyl_maps(self.h, frame, _ptr(cm), _ptr(em)))
+        return cm, em
 
     # ---- batched
     def enqueue_depth(self, depth, fx, fy, cx, cy, mem_kind=MEM_HOST, nframes=None, row_stride=None, frame_stride=None):
@@ -393,12 +414,17 @@ class CAPE:
         _check(self.L.drfe_cape_enqueue_cloud(self.h, nframes, _ptr(cloud), frame_stride, mem_kind))
         self._nframes = nframes
 
-    def download(self, seg=None, planes=None, nplanes=None):
+    def download(self, seg=None, planes=None, nplanes=None, with_cylinders=False):
         nf = self._nframes
         seg = np.empty((nf, self.H, self.W), np.uint8) if seg is None else seg
         planes = np.zeros((nf, self.plane_cap), PLANE_DTYPE) if planes is None else planes
         nplanes = np.empty(nf, np.int32) if nplanes is None else nplanes
         ncyl = np.empty(nf, np.int32)
+        if with_cylinders:
+            cyls = np.zeros((nf, max(self.cyl_cap, 1)), CYL_DTYPE)
+            _check(self.L.drfe_cape_download(self.h, _ptr(seg), _ptr(planes), planes.shape[1], _ptr(nplanes), _ptr(cyls),
+                                             self.cyl_cap, _ptr(ncyl)))
+            return seg, planes, nplanes, ncyl, cyls, self.cylinders_found()
         _check(self.L.drfe_cape_download(self.h, _ptr(seg), _ptr(planes), planes.shape[1], _ptr(nplanes), None, 0,
                                          _ptr(ncyl)))
         return seg, planes, nplanes

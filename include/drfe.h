@@ -181,9 +181,13 @@ int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_
                             float cy);
 /* wait + copy out.  seg_out: nframes * H*W labels (0 = none, 1..n planes, 51.. cylinders),
  * fully written (the reference only writes labelled pixels of a caller-zeroed image).
- * planes[f*plane_cap + i]; cylinders may be NULL when cylinder detection is off. */
+ * planes[f*plane_cap + i]; cylinders may be NULL when cylinder detection is off.
+ * nr_cylinders[f] = nr_cylinders_final (cylinders that survive erosion, CAPE.cpp:340-346);
+ * cylinders[f*cyl_cap + i] is cylinder_segments_final (CAPE.cpp:434-445), which holds EVERY
+ * cylinder found — drfe_cape_cylinders_found gives that list's length per frame. */
 int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int plane_cap,
                        int* nr_planes, drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders);
+int drfe_cape_cylinders_found(drfe_cape* h, int* counts); /* counts[f] = cylinder_segments_final.size() */
 int drfe_cape_sync(drfe_cape* h);
 void* drfe_cape_stream(drfe_cape* h);
 
@@ -203,6 +207,8 @@ int drfe_cape_get_cloud(drfe_cape* h, int frame, float* cloud_cellmajor);
 int drfe_cape_get_cells(drfe_cape* h, int frame, drfe_plane* cells);
 /* grid_plane_seg_map after region growing + the eroded map used for painting */
 int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t* eroded_map);
+/* cylinder detection on: grid_cylinder_seg_map (cylinder numbers) and its eroded map (labels 50 + k) */
+int drfe_cape_get_cyl_maps(drfe_cape* h, int frame, int32_t* cyl_map, uint8_t* cyl_eroded_map);
 /* diagnostics of the grid stage of one frame: [0] seeds, [1] growth sweeps, [2] sum of candidates,
  * [3] sum of activated cells, [4..8] cycles in bin search+list / seed scan / growth / accumulate /
  * fit+label, [9] clock after set-up, [10] clock at the end */

@@ -150,3 +150,71 @@ def test_plane_detection_wrapper(drfe, orc):
     o = orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
     oseg, oplanes = o.process(o.depth_to_cloud(depth, *K))
     assert pd.nr_planes == len(oplanes) and pd.nr_cylinders == 0 and np.array_equal(pd.seg_output, oseg)
+
+
+# ---------------------------------------------------------------- cylinder detection (CylinderSeg.cpp, config 5)
+def check_cylinders(cp, o, depth, K, f=0, res=None):
+    cloud = o.depth_to_cloud(depth, *K)
+    oseg, oplanes, oncf, ocyls = o.process_full(cloud)
+    pm, em = cp.grid_maps(f)
+    opm, oem = o.grid_maps()
+    assert np.array_equal(pm, opm) and np.array_equal(em, oem), "plane maps (planes re-fitted from extruded regions included)"
+    cm, ce = cp.cyl_maps(f)
+    ocm, oce = o.cyl_maps()
+    assert np.array_equal(cm, ocm), "grid_cylinder_seg_map"
+    assert np.array_equal(ce, oce), "eroded cylinder map (labels 50 + k)"
+    return oseg, oplanes, oncf, ocyls
+
+
+@pytest.mark.parametrize("w,h,scene,seed,unit", [
+    (640, 480, 2, 20260100, 1000.0),
+    (640, 480, 2, 20260105, 1000.0),
+    (640, 480, 2, 20260204, 1000.0),     # a frame with six extruded sub-segments
+    (640, 480, 2, 20260300, 1.0),        # metres: thresholds vacuous, many garbage cylinders
+    (640, 480, 1, 20260502, 1000.0),
+    (1280, 720, 2, 20260400, 1000.0),    # configs[4]: 1280x720, cylinders on
+])
+def test_cape_cylinders_parity(drfe, orc, w, h, scene, seed, unit):
+    _, depth, K = drfe.synth_frame(w, h, scene, seed, unit)
+    cp = drfe.CAPE(h, w, 20, 20, True, MC, 50.0)
+    npl, ncyl, seg, planes, cyls = cp.process_depth(depth, *K)
+    o = orc.CapeOracle(h, w, 20, 20, True, MC, 50.0)
+    oseg, oplanes, oncf, ocyls = check_cylinders(cp, o, depth, K)
+    assert npl == len(oplanes) and ncyl == oncf and len(cyls) == len(ocyls)
+    assert np.array_equal(seg, oseg), "seg_output with cylinder labels"
+    check_planes(planes, oplanes)
+    if len(ocyls):
+        # same operation sequence as the oracle: bit-identical (the bar would be 1e-5)
+        for n in ("radius", "center", "axis"):
+            assert np.array_equal(cyls[n], ocyls[n]), n
+
+
+def test_cape_cylinders_golden(drfe):
+    g = load_golden("cape_640x480_pillars_mm_cyl.npz")
+    depth = g["depth_q"].astype(np.float32) * np.float32(1.0 / 5000.0) * g["unit"]
+    cp = drfe.CAPE(480, 640, 20, 20, True, float(g["min_cos"]), float(g["max_merge"]))
+    npl, ncyl, seg, planes, cyls = cp.process_depth(depth, *[float(v) for v in g["K"]])
+    assert np.array_equal(seg, g["seg"]) and int(seg.max()) > 50
+    assert ncyl == int(g["nr_cylinders_final"]) and len(cyls) == len(g["cyl_radius"])
+    cm, ce = cp.cyl_maps()
+    assert np.array_equal(cm, g["cyl_map"]) and np.array_equal(ce, g["cyl_eroded"])
+    assert np.allclose(cyls["radius"], g["cyl_radius"], rtol=1e-6)
+    assert np.allclose(cyls["center"], g["cyl_center"], rtol=1e-7, atol=1e-7)
+    assert np.allclose(np.abs(cyls["axis"]), np.abs(g["cyl_axis"]), atol=1e-9)   # PCA sign is solver-defined
+    assert np.allclose(planes["normal"], g["plane_normal"], atol=TOL, rtol=0) and np.allclose(planes["d"], g["plane_d"], rtol=1e-9)
+
+
+def test_cape_cylinders_batch_matches_single(drfe, orc):
+    """frames of a batch are independent: the rand() stream restarts per frame (App. B.9)"""
+    seeds = [20260100, 20260105, 20260204, 20260101]
+    frames = [drfe.synth_frame(640, 480, 2, s, 1000.0) for s in seeds]
+    depth = np.stack([fr[1] for fr in frames])
+    K = frames[0][2]
+    cp = drfe.CAPE(480, 640, 20, 20, True, MC, 50.0, max_batch=4)
+    cp.enqueue_depth(depth, *K)
+    seg, planes, npl, ncyl, cyls, found = cp.download(with_cylinders=True)
+    o = orc.CapeOracle(480, 640, 20, 20, True, MC, 50.0)
+    for f in range(4):
+        oseg, oplanes, oncf, ocyls = o.process_full(o.depth_to_cloud(depth[f], *K))
+        assert np.array_equal(seg[f], oseg) and npl[f] == len(oplanes) and ncyl[f] == oncf and found[f] == len(ocyls)
+        assert np.array_equal(cyls[f, :found[f]]["radius"], ocyls["radius"])
