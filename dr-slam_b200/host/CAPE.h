@@ -61,6 +61,7 @@ class CAPE {
     if (drfe_cape_create(&prm_, 1, device, &h_) != DRFE_OK) throw std::runtime_error(std::string("CAPE: ") + drfe_last_error());
     seg_.resize((size_t)depth_height * depth_width);
     planes_.resize(kPlaneCap);
+    if (cylinder_detection) cyls_.resize((size_t)(depth_height / cell_height) * (depth_width / cell_width) / 6 + 1);
   }
   ~CAPE() { drfe_cape_destroy(h_); }
   CAPE(const CAPE&) = delete;
@@ -73,18 +74,21 @@ class CAPE {
   template <class MatrixT>
   void process(MatrixT& cloud_array, int& nr_planes, int& nr_cylinders, SegImageT& seg_output,
                std::vector<PlaneSeg>& plane_segments_final, std::vector<CylinderSeg>& cylinder_segments_final) {
-    if (drfe_cape_process(h_, cloud_array.data(), seg_.data(), planes_.data(), kPlaneCap, &nr_planes, nullptr, 0, &nr_cylinders) != DRFE_OK)
+    if (drfe_cape_process(h_, cloud_array.data(), seg_.data(), planes_.data(), kPlaneCap, &nr_planes, cyls_.data(), (int)cyls_.size(),
+                          &nr_cylinders) != DRFE_OK)
       throw std::runtime_error(std::string("CAPE::process: ") + drfe_last_error());
     finish(nr_planes, seg_output, plane_segments_final);
-    (void)cylinder_segments_final;
+    finish_cylinders(cylinder_segments_final);
   }
   // fused PlaneDetection_CAPE path: depth image -> cloud (double math) -> cell-major -> process
   void processDepth(const float* depth, size_t row_stride_elems, float fx, float fy, float cx, float cy, int& nr_planes,
-                    int& nr_cylinders, SegImageT& seg_output, std::vector<PlaneSeg>& plane_segments_final) {
+                    int& nr_cylinders, SegImageT& seg_output, std::vector<PlaneSeg>& plane_segments_final,
+                    std::vector<CylinderSeg>* cylinder_segments_final = nullptr) {
     if (drfe_cape_process_depth(h_, depth, row_stride_elems, fx, fy, cx, cy, seg_.data(), planes_.data(), kPlaneCap, &nr_planes,
-                                nullptr, 0, &nr_cylinders) != DRFE_OK)
+                                cyls_.data(), (int)cyls_.size(), &nr_cylinders) != DRFE_OK)
       throw std::runtime_error(std::string("CAPE::processDepth: ") + drfe_last_error());
     finish(nr_planes, seg_output, plane_segments_final);
+    if (cylinder_segments_final) finish_cylinders(*cylinder_segments_final);
   }
   drfe_cape* handle() { return h_; }
 
@@ -100,10 +104,22 @@ class CAPE {
         if (src[c] > 0) dst[c] = src[c];                           // CAPE.cpp:423-425
     }
   }
+  // cylinder_segments_final: one CylinderSeg per cylinder found, erosion survivors or not (CAPE.cpp:434-445)
+  void finish_cylinders(std::vector<CylinderSeg>& out) {
+    int found = 0;
+    if (cyls_.empty() || drfe_cape_cylinders_found(h_, &found) != DRFE_OK) return;
+    for (int i = 0; i < found && i < (int)cyls_.size(); ++i) {
+      CylinderSeg cy;
+      cy.radii.push_back(cyls_[i].radius);
+      for (int k = 0; k < 3; ++k) { cy.centers.push_back(cyls_[i].center[k]); cy.axis[k] = cyls_[i].axis[k]; }
+      out.push_back(cy);
+    }
+  }
   drfe_cape_params prm_{};
   drfe_cape* h_ = nullptr;
   std::vector<uint8_t> seg_;
   std::vector<drfe_plane> planes_;
+  std::vector<drfe_cylinder> cyls_;
 };
 
 namespace Planar_SLAM {
@@ -134,7 +150,7 @@ class PlaneDetection_CAPE {
       det_rows_ = rows; det_cols_ = cols;
     }
     plane_detector->processDepth(depth_img.data, depth_img.step / sizeof(float), K_[0], K_[4], K_[2], K_[5], nr_planes,
-                                 nr_cylinders, seg_output, plane_params);
+                                 nr_cylinders, seg_output, plane_params, &cylinder_params);
     // per-plane point lists (PlaneExtractor.cpp:165-190)
     plane_cloud.assign(nr_planes, PointCloud());
     for (int i = 0; i < rows; ++i) {
