@@ -284,26 +284,36 @@ def main():
         .view(drfe.PLANE_DTYPE).reshape(BATCH, PLANE_CAP)
     h_npl = torch.empty(BATCH, dtype=torch.int32).pin_memory().numpy()
 
-    def step_e2e():
-        orb.enqueue(h_gray)
-        cape.enqueue_depth(h_depth, *K)
-        orb.download(h_kps, h_desc, h_cnt)
-        cape.download(h_seg, h_planes, h_npl)
+    # the chunk-pipelined batch calls: per 32-frame chunk H2D | kernels | D2H on three streams per handle
+    def step_e2e(dep, fac):
+        orb.extract_batch(h_gray, h_kps, h_desc, h_cnt)
+        cape.process_depth_batch(dep, *K, depth_factor=fac, seg=h_seg, planes=h_planes, nplanes=h_npl)
+        orb.finish_batch()
+        cape.finish_batch()
+
+    def time_e2e(dep, fac):
+        for _ in range(2):
+            step_e2e(dep, fac)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e(dep, fac)
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * BATCH * e2e_steps / dt
 
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * BATCH * e2e_steps / e2e_s
+    e2e_value = time_e2e(h_depth, 1.0)
+    # the same with the sensor's raw 16-bit depth (TUM png, factor 1/5000) converted on the device (Frame.cc:113-115)
+    fac = np.float32(1.0 / 5000.0)
+    q16 = np.rint(depth * 5000).astype(np.uint16)
+    assert np.array_equal(q16.astype(np.float32) * fac, depth)
+    h_depth16 = pin(q16)
+    e2e_u16 = time_e2e(h_depth16, float(fac))
     h2d = int(h_gray.nbytes + h_depth.nbytes)
     d2h = int(h_kps.nbytes + h_desc.nbytes + h_cnt.nbytes + h_seg.nbytes + h_planes.nbytes + h_npl.nbytes)
 
@@ -349,7 +359,11 @@ def main():
                    "l2": "inputs larger than L2 (393 MB of gray+depth per step per GPU, no flush needed)",
                    "sharding": "independent 256-frame batches per GPU, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "api": "drfe_orb_extract_batch + drfe_cape_process_depth_batch (float depth, pinned host "
+                "buffers, 32-frame chunks pipelined H2D | kernels | D2H)",
+                "raw_u16_depth": {"value": e2e_u16, "unit": "frames/s",
+                                  "h2d_bytes_per_step": int(h_gray.nbytes + h_depth16.nbytes),
+                                  "note": "same call fed the sensor's 16-bit depth, converted on the device (Frame.cc:113-115)"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

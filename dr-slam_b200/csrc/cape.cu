@@ -30,6 +30,7 @@ struct CapeDev {
   float min_cos, max_merge_dist;
   float fx, fy, cx, cy;
   const float* depth; long long depth_rs, depth_fs;   // input depth (may be null: cloud given)
+  const uint16_t* depth16; float depth_factor;        // raw sensor depth: z = (float)u16 * depth_factor (Frame.cc:113-115)
   float* cloud;                 // [B][3][H*W] cell-major
   drfe_plane* cells;            // [B][ncells]
   float* tols;                  // [B][ncells]
@@ -196,17 +197,20 @@ __device__ __forceinline__ bool quotient_needs_exact(double q) {
 }
 
 static const int kSumsThreads = 128, kSumsChunk = 5;
-template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int nframes) {
+// MODE 0: the cell-major cloud is given; 1: float depth image; 2: raw 16-bit depth image scaled by depth_factor
+template <int MODE>
+__global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  constexpr bool FROM_DEPTH = MODE != 0;
   extern __shared__ __align__(16) float s_zall[];           // [8 groups][npc]
   const CapeDev& P = *Pp;
-  const int gid = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;   // global cell index over the batch
+  const int gid0 = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;  // cell index within this launch
   const int l = threadIdx.x & 15;
   // full-warp mask: both 16-lane groups of a warp run the same shuffles (width 16); a group that
   // exited above is simply absent.  (A per-group runtime mask makes the compiler serialise them.)
   const unsigned mask = 0xFFFFFFFFu;
   const int ncells = P.ncells;
-  if (gid >= nframes * ncells) return;                      // whole 16-lane groups exit together
+  if (gid0 >= nframes * ncells) return;                     // whole 16-lane groups exit together
+  const int gid = gid0 + f0 * ncells;                       // global cell index over the batch
   const int f = gid / ncells, cell = gid - f * ncells;
   const int npc = P.npc, cw = P.cw, ch = P.ch;
   float* s_z = s_zall + (threadIdx.x >> 4) * npc;
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
   int cnt = 0;
   const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
   // ---- stage z in shared memory (it is also what the depth-jump scans read)
-  if (FROM_DEPTH) {
+  if (MODE == 1) {
     const int drs = (int)P.depth_rs;
     const float* __restrict__ dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
     if ((cw & 3) == 0 && (drs & 3) == 0 && ((reinterpret_cast<uintptr_t>(dsrc) & 15) == 0)) {
@@ -236,6 +240,25 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
       for (int i = l; i < npc; i += 16) {
         const int r = i / cw, c = i - r * cw;
         s_z[i] = __ldg(dsrc + r * drs + c);
+      }
+    }
+  } else if (MODE == 2) {
+    // imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) (Frame.cc:113-115): float(u16) * float(factor)
+    const int drs = (int)P.depth_rs;
+    const float fac = P.depth_factor;
+    const uint16_t* __restrict__ dsrc = P.depth16 + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
+    if ((cw & 3) == 0 && (drs & 3) == 0 && ((reinterpret_cast<uintptr_t>(dsrc) & 7) == 0)) {
+      const int q4 = cw >> 2, n4 = npc >> 2;
+      for (int j = l; j < n4; j += 16) {
+        const int r = j / q4, c4 = j - r * q4;
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(dsrc + r * drs) + c4);
+        *reinterpret_cast<float4*>(s_z + 4 * j) = make_float4((float)(v.x & 0xFFFFu) * fac, (float)(v.x >> 16) * fac,
+                                                              (float)(v.y & 0xFFFFu) * fac, (float)(v.y >> 16) * fac);
+      }
+    } else {
+      for (int i = l; i < npc; i += 16) {
+        const int r = i / cw, c = i - r * cw;
+        s_z[i] = (float)__ldg(dsrc + r * drs + c) * fac;
       }
     }
   } else {
@@ -324,10 +347,11 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
 // k_cape_fit: one thread per cell — the rest of PlaneSeg::PlaneSeg (PlaneSeg.cpp:78-94): sums
 // widened to double, fitPlane, the depth-dependent MSE test, and the cell's merge tolerance
 // (CAPE.cpp:69-73).
-__global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp, int nframes) {
+__global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   const CapeDev& P = *Pp;
-  const int gid = blockIdx.x * 128 + threadIdx.x;
-  if (gid >= nframes * P.ncells) return;
+  const int gid0 = blockIdx.x * 128 + threadIdx.x;
+  if (gid0 >= nframes * P.ncells) return;
+  const int gid = gid0 + f0 * P.ncells;
   const int f = gid / P.ncells, cell = gid - f * P.ncells;
   const int npc = P.npc;
   CellSums in;
@@ -642,10 +666,10 @@ __device__ __noinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_p
 enum { BV_FL = 0, BV_FR, BV_FU, BV_FD, BV_U, BV_A, BV_B, BV_M, BV_H, BV_C0, BV_CL, BV_R0, BV_RL, BV_VALID, BV_COUNT };
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict__ Pp) {
+__global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict__ Pp, int f0) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CapeDev& P = *Pp;
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int f = blockIdx.x + f0, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nc = P.ncells, ncx = P.ncx, ncy = P.ncy, nw = (nc + 31) >> 5;
   // ---- shared layout
   uint32_t* bv = reinterpret_cast<uint32_t*>(smem);               // [BV_COUNT][nw]
@@ -1147,10 +1171,11 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 // the bit pattern memset(...,100,...) leaves (0x64646464, CAPE.cpp:60).  Cells inside an
 // eroded mask are painted whole (:410-412).
 template <bool CYL>
-__global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__ Pp, int nframes) {
+__global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   const CapeDev& P = *Pp;
-  const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= nframes * P.ncells) return;
+  const int gw0 = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw0 >= nframes * P.ncells) return;
+  const int gw = gw0 + f0 * P.ncells;
   const int f = gw / P.ncells, cell = gw - f * P.ncells;
   const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
   const int npc = P.npc, cw = P.cw;
@@ -1194,8 +1219,19 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
   }
   // cells inside an eroded plane mask are painted whole, then cells inside an eroded cylinder mask (:410-416)
   const int whole = er > 0 ? er : (cer > 0 ? cer : ((anyb | anyc) == 0 ? 0 : -1));
+  // a cell row is cw bytes; with cw and W multiples of 4 everything below moves 4 pixels per lane and access
+  const bool vec4 = ((cw | P.W) & 3) == 0;
+  const int q4 = cw >> 2;
   if (whole >= 0) {
-    for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)whole; }
+    if (vec4) {
+      const uint32_t word = (uint32_t)whole * 0x01010101u;
+      for (int j = lane; j < (npc >> 2); j += 32) {
+        const int lr = j / q4, c4 = j - lr * q4;
+        *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = word;
+      }
+    } else {
+      for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)whole; }
+    }
     return;
   }
   const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
@@ -1203,6 +1239,39 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
   const float* CZ = CY + N;
   const float4* eq = P.plane_eq + (long long)f * (kMaxPlanes + 1);
   const float* maxd = P.plane_maxd + (long long)f * (kMaxPlanes + 1);
+  if (!CYL && vec4 && (npc & 3) == 0) {
+    // planes only: 4 pixels per lane, float4 loads of the cell-major cloud, one word store
+    const float4* X4 = reinterpret_cast<const float4*>(CX);
+    const float4* Y4 = reinterpret_cast<const float4*>(CY);
+    const float4* Z4 = reinterpret_cast<const float4*>(CZ);
+    for (int j = lane; j < (npc >> 2); j += 32) {
+      const float4 xv = X4[j], yv = Y4[j], zv = Z4[j];
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w};
+      float best[4];
+      uint32_t lab = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) best[u] = __uint_as_float(0x64646464u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint32_t b = bits[k];
+        while (b) {
+          const int p = k * 32 + __ffs(b) - 1;
+          b &= b - 1;
+          const float4 e = eq[p];
+          const float md = maxd[p];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float v = xs[u] * e.x + ys[u] * e.y + zs[u] * e.z + e.w;
+            const float dist = v * v;
+            if (dist < md && dist < best[u]) { best[u] = dist; lab = (lab & ~(0xFFu << (8 * u))) | ((uint32_t)p << (8 * u)); }
+          }
+        }
+      }
+      const int lr = j / q4, c4 = j - lr * q4;
+      *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = lab;
+    }
+    return;
+  }
   for (int i = lane; i < npc; i += 32) {
     const float x = CX[i], y = CY[i], z = CZ[i];
     float best = __uint_as_float(0x64646464u);
@@ -1243,12 +1312,13 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
   }
 }
 
-__global__ void k_cape_clear_margin(const CapeDev* __restrict__ Pp, int nframes) {
+__global__ void k_cape_clear_margin(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   // pixels outside the last full cell row/column are never labelled
   const CapeDev& P = *Pp;
   const long long N = (long long)P.H * P.W;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * nframes) return;
+  const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx0 >= N * nframes) return;
+  const long long idx = idx0 + (long long)f0 * N;
   const int p = (int)(idx % N);
   const int r = p / P.W, c = p - r * P.W;
   if (r >= P.ncy * P.ch || c >= P.ncx * P.cw) P.seg[idx] = 0;
@@ -1393,8 +1463,9 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   {
     const size_t sums_smem = (size_t)(kSumsThreads / 16) * D.npc * sizeof(float);
     if (sums_smem > 200 * 1024) { set_error("drfe_cape_create: cells of %d points are too large", D.npc); return fail(DRFE_ERR_ARG); }
-    if (cudaFuncSetAttribute(k_cape_sums<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_cape_sums<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_cape_sums<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_cape_sums<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_cape_sums<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess) {
       set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
     }
   }
@@ -1428,25 +1499,34 @@ int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, 
   return h->timer.read(ms, names, cap, nstages);
 }
 
-static int cape_run(drfe_cape* h, int nframes) {
+// all kernels of frames [f0, f0 + n) on the handle's stream (the device descriptor must be current)
+static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   cudaStream_t st = h->stream;
-  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
-  const int ncell_total = nframes * h->hd.ncells;
+  const int ncell_total = n * h->hd.ncells;
   const size_t sums_smem = (size_t)(kSumsThreads / 16) * h->hd.npc * sizeof(float);
-  if (h->hd.depth) DRFE_LAUNCH(k_cape_sums<true>, (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads, kSumsThreads, sums_smem, st, h->dd, nframes);
-  else DRFE_LAUNCH(k_cape_sums<false>, (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads, kSumsThreads, sums_smem, st, h->dd, nframes);
-  h->timer.mark("cells", st);
-  DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, nframes);
-  h->timer.mark("fit", st);
-  DRFE_LAUNCH(k_cape_grid<128>, nframes, 128, h->grid_smem, st, h->dd);
-  h->timer.mark("grid", st);
+  const int sums_grid = (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads;
+  if (h->hd.depth16) DRFE_LAUNCH(k_cape_sums<2>, sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n);
+  else if (h->hd.depth) DRFE_LAUNCH(k_cape_sums<1>, sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n);
+  else DRFE_LAUNCH(k_cape_sums<0>, sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n);
+  if (timed) h->timer.mark("cells", st);
+  DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
+  if (timed) h->timer.mark("fit", st);
+  DRFE_LAUNCH(k_cape_grid<128>, n, 128, h->grid_smem, st, h->dd, f0);
+  if (timed) h->timer.mark("grid", st);
   if (h->margin) {
-    const long long tot = (long long)h->hd.H * h->hd.W * nframes;
-    DRFE_LAUNCH(k_cape_clear_margin, (unsigned)((tot + 255) / 256), 256, 0, st, h->dd, nframes);
+    const long long tot = (long long)h->hd.H * h->hd.W * n;
+    DRFE_LAUNCH(k_cape_clear_margin, (unsigned)((tot + 255) / 256), 256, 0, st, h->dd, f0, n);
   }
-  if (h->hd.cyl) DRFE_LAUNCH(k_cape_refine<true>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, nframes);
-  else DRFE_LAUNCH(k_cape_refine<false>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, nframes);
-  h->timer.mark("refine", st);
+  if (h->hd.cyl) DRFE_LAUNCH(k_cape_refine<true>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, f0, n);
+  else DRFE_LAUNCH(k_cape_refine<false>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, f0, n);
+  if (timed) h->timer.mark("refine", st);
+  return DRFE_OK;
+}
+
+static int cape_run(drfe_cape* h, int nframes) {
+  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, h->stream));
+  const int rc = cape_launch(h, 0, nframes, true);
+  if (rc != DRFE_OK) return rc;
   h->last_frames = nframes;
   h->pending = true;
   return DRFE_OK;
@@ -1467,7 +1547,7 @@ int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_
   else
     DRFE_CUDA(cudaMemcpy2DAsync(h->hd.cloud, N3 * sizeof(float), cloud, frame_stride * sizeof(float), N3 * sizeof(float), nframes, kind, st));
   h->timer.mark("copy_in", st);
-  h->hd.depth = nullptr;
+  h->hd.depth = nullptr; h->hd.depth16 = nullptr;
   return cape_run(h, nframes);
 }
 
@@ -1492,7 +1572,7 @@ int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_
   } else if (mem_kind == DRFE_MEM_DEVICE) {
     h->hd.depth = depth; h->hd.depth_rs = (long long)row_stride; h->hd.depth_fs = (long long)frame_stride;
   } else { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
-  h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy;
+  h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy; h->hd.depth16 = nullptr;
   return cape_run(h, nframes);
 }
 

@@ -110,4 +110,45 @@ struct StageTimer {
   }
 };
 
+// Streams and events of the chunk-pipelined batch calls (drfe_orb_extract_batch,
+// drfe_cape_process_depth_batch): chunk k's host->device copy runs on `h2d`, its kernels on the
+// handle's stream, its device->host copies on `d2h`, so that the three overlap across chunks.
+struct ChunkPipe {
+  static const int kMaxChunks = 64;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[kMaxChunks], ev_done[kMaxChunks], ev_start = nullptr;
+  int* h_status = nullptr;   // pinned copy of the handle's device status word
+  bool created = false, active = false;
+  int create() {
+    if (created) return DRFE_OK;
+    DRFE_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    DRFE_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    DRFE_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks; ++i) {
+      DRFE_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      DRFE_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    }
+    DRFE_CUDA(cudaHostAlloc((void**)&h_status, sizeof(int), cudaHostAllocDefault));
+    *h_status = 0;
+    created = true;
+    return DRFE_OK;
+  }
+  void destroy() {
+    if (!created) return;
+    cudaStreamSynchronize(h2d); cudaStreamSynchronize(d2h);
+    for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); }
+    cudaEventDestroy(ev_start);
+    cudaStreamDestroy(h2d); cudaStreamDestroy(d2h);
+    cudaFreeHost(h_status);
+    created = false;
+  }
+  // frames per chunk: the caller's wish (<= 0: 32), never more than kMaxChunks chunks
+  static int chunk_size(int nframes, int wish) {
+    int c = wish > 0 ? wish : 32;
+    if (c > nframes) c = nframes;
+    while ((nframes + c - 1) / c > kMaxChunks) ++c;
+    return c;
+  }
+};
+
 }  // namespace drfe

@@ -103,13 +103,13 @@ __device__ __forceinline__ uint8_t* roi_ptr(const OrbDev& P, const LevelDev& L, 
 // recomputed (identical bytes to copyMakeBorder, no second pass).
 __global__ void __launch_bounds__(256) k_pyr_level0(const OrbDev* __restrict__ Pp,
                                                      const uint8_t* __restrict__ src,
-                                                     long long row_stride, long long frame_stride) {
+                                                     long long row_stride, long long frame_stride, int f0) {
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[0];
   const int groups = (L.w + 40 + 3) >> 2;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int by = blockIdx.y * blockDim.y + threadIdx.y;
-  const int f = blockIdx.z;
+  const int f = blockIdx.z + f0;
   if (g >= groups || by >= L.rows) return;
   const uint8_t* s = src + (long long)f * frame_stride + (long long)reflect101(by - kEdge, L.h) * row_stride;
   const int bx = 4 * g - 20;
@@ -132,13 +132,13 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const OrbDev* __restrict__ P
 static const int kPyrTW = 128, kPyrTH = 32;
 struct PyrTile { short g0, by0, sx0, sw4, sy0, nsy, pad0, pad1; };   // first 4-px group, first bordered row, source window
 
-__global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ Pp, int level) {
+__global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ Pp, int level, int f0) {
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[level];
   const LevelDev& S = P.lv[level - 1];
   const PyrTile t = P.ptiles[L.ptile_off + blockIdx.x];
-  const int f = blockIdx.y;
+  const int f = blockIdx.y + f0;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int SW = t.sw4 * 4;                                   // source window pitch (bytes)
   uint8_t* s_src = smem;                                      // [nsy][SW]
@@ -318,11 +318,11 @@ __device__ __forceinline__ uint32_t fast_compass_quad(const uint32_t* __restrict
 //      nothing (the minThFAST fallback, ORBextractor.cc:812-816), in arbitrary order (the
 //      quadtree orders by a key)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp) {
+__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp, int f0) {
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const StripDev strip = P.strips[blockIdx.x];
-  const int f = blockIdx.y;
+  const int f = blockIdx.y + f0;
   const LevelDev& L = P.lv[strip.level];
   const int TP = P.fast_tp;                  // smem row pitch (multiple of 16)
   const int nrows = strip.nrows;             // interior rows of this strip
@@ -565,10 +565,10 @@ __device__ __forceinline__ void child_mid(const QBox& b, int& mx, int& my) {
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__ Pp) {
+__global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__ Pp, int f0) {
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
-  const int level = blockIdx.x, f = blockIdx.y;
+  const int level = blockIdx.x, f = blockIdx.y + f0;
   const LevelDev& L = P.lv[level];
   const int NC = L.node_cap, N = L.nfeat;
   const int tid = threadIdx.x;
@@ -796,12 +796,12 @@ __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int (
   h[3] = __dp4a(c, k1, __dp4a(b, k0, 0u));
 }
 
-__global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp) {
+__global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp, int f0) {
   const OrbDev& P = *Pp;
   int level = 0;
   while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blur_blk_off[level + 1]) ++level;
   const LevelDev& L = P.lv[level];
-  const int f = blockIdx.y;
+  const int f = blockIdx.y + f0;
   if (P.lkp_cnt[f * P.nlevels + level] == 0) return;  // reference skips levels without keypoints (:1081)
   // flattened (row group, 4-pixel column) index, columns fastest
   const int t = ((int)blockIdx.x - P.blur_blk_off[level]) * 256 + threadIdx.x;
@@ -855,14 +855,14 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 static const int kDescWarps = 8;
 static const int kPatchRows = 2 * kEdge + 1, kPatchW4 = 11;   // 39 rows x 44 bytes (39 columns + alignment slack)
-__global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp) {
+__global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp, int f0) {
   // rBRIEF pattern in shared memory, one word (x0,y0,x1,y1 as int8) per test, laid out so
   // that lane j's t-th test sits at word t*32 + j (conflict-free); constant memory would
   // serialise the lane-divergent index
   __shared__ uint32_t s_pat[256];
   __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchW4];
   const OrbDev& P = *Pp;
-  const int level = blockIdx.y, f = blockIdx.z;
+  const int level = blockIdx.y, f = blockIdx.z + f0;
   const LevelDev& L = P.lv[level];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int* cnts = P.lkp_cnt + f * P.nlevels;
@@ -967,11 +967,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   }
 }
 
-__global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int nframes) {
+__global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
   const OrbDev& P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nframes * P.nlevels) { P.cand_cnt[i] = 0; P.lkp_cnt[i] = 0; }
-  if (i < nframes) P.out_cnt[i] = 0;
+  if (i < nframes * P.nlevels) { P.cand_cnt[f0 * P.nlevels + i] = 0; P.lkp_cnt[f0 * P.nlevels + i] = 0; }
+  if (i < nframes) P.out_cnt[f0 + i] = 0;
 }
 
 }  // namespace drfe
@@ -995,6 +995,9 @@ struct drfe_orb {
   int last_frames = 0;
   bool pending = false;
   StageTimer timer;
+  ChunkPipe pipe;
+  int* batch_counts = nullptr;   // host destination of the running batch call
+  int batch_cap = 0;
   std::vector<void*> allocs;
 };
 
@@ -1235,6 +1238,7 @@ int drfe_orb_destroy(drfe_orb* h) {
   if (!h) return DRFE_OK;
   DeviceScope ds(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  h->pipe.destroy();
   for (void* p : h->allocs) cudaFree(p);
   h->timer.destroy();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1272,6 +1276,33 @@ int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, in
   return h->timer.read(ms, names, cap, nstages);
 }
 
+// all kernels of frames [f0, f0 + n) on the handle's stream; src/rs/fs address frame 0 of the batch
+static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
+  cudaStream_t st = h->stream;
+  const OrbDev& D = h->hd;
+  const int nl = D.nlevels;
+  DRFE_LAUNCH(k_zero_counts, (n * nl + 255) / 256, 256, 0, st, h->dd, f0, n);
+  {
+    const LevelDev& L = D.lv[0];
+    dim3 blk(64, 4), grd(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
+    DRFE_LAUNCH(k_pyr_level0, grd, blk, 0, st, h->dd, src, rs, fs, f0);
+  }
+  for (int l = 1; l < nl; ++l) {
+    const LevelDev& L = D.lv[l];
+    DRFE_LAUNCH(k_pyr_resize, dim3(L.ptile_cnt, n), 256, h->pyr_smem, st, h->dd, l, f0);
+  }
+  if (timed) h->timer.mark("pyramid", st);
+  DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0);
+  if (timed) h->timer.mark("fast", st);
+  DRFE_LAUNCH(k_quadtree<256>, dim3(nl, n), 256, h->quad_smem, st, h->dd, f0);
+  if (timed) h->timer.mark("quadtree", st);
+  DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, n), 256, 0, st, h->dd, f0);
+  if (timed) h->timer.mark("blur", st);
+  DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kDescWarps - 1) / kDescWarps, nl, n), kDescWarps * 32, 0, st, h->dd, f0);
+  if (timed) h->timer.mark("orient_describe", st);
+  return DRFE_OK;
+}
+
 int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride, size_t frame_stride,
                      int mem_kind) {
   if (!h || !gray) { set_error("drfe_orb_enqueue: null argument"); return DRFE_ERR_ARG; }
@@ -1297,26 +1328,8 @@ int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_s
   } else if (mem_kind != DRFE_MEM_DEVICE) {
     set_error("drfe_orb_enqueue: bad mem_kind"); return DRFE_ERR_ARG;
   }
-  const int nl = D.nlevels;
-  DRFE_LAUNCH(k_zero_counts, (nframes * nl + 255) / 256, 256, 0, st, h->dd, nframes);
-  {
-    const LevelDev& L = D.lv[0];
-    dim3 blk(64, 4), grd(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, nframes);
-    DRFE_LAUNCH(k_pyr_level0, grd, blk, 0, st, h->dd, src, rs, fs);
-  }
-  for (int l = 1; l < nl; ++l) {
-    const LevelDev& L = D.lv[l];
-    DRFE_LAUNCH(k_pyr_resize, dim3(L.ptile_cnt, nframes), 256, h->pyr_smem, st, h->dd, l);
-  }
-  h->timer.mark("pyramid", st);
-  DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, nframes), 256, h->fast_smem, st, h->dd);
-  h->timer.mark("fast", st);
-  DRFE_LAUNCH(k_quadtree<256>, dim3(nl, nframes), 256, h->quad_smem, st, h->dd);
-  h->timer.mark("quadtree", st);
-  DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, nframes), 256, 0, st, h->dd);
-  h->timer.mark("blur", st);
-  DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kDescWarps - 1) / kDescWarps, nl, nframes), kDescWarps * 32, 0, st, h->dd);
-  h->timer.mark("orient_describe", st);
+  const int rc = orb_launch(h, 0, nframes, src, rs, fs, true);
+  if (rc != DRFE_OK) return rc;
   h->last_frames = nframes;
   h->pending = true;
   return DRFE_OK;
@@ -1380,6 +1393,79 @@ int drfe_orb_extract(drfe_orb* h, const uint8_t* gray, int width, int height, si
   int rc = drfe_orb_enqueue(h, 1, gray, row_stride, row_stride * height, DRFE_MEM_HOST);
   if (rc != DRFE_OK) return rc;
   return drfe_orb_download(h, kps, desc, cap, n);
+}
+
+
+int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride, size_t frame_stride,
+                           drfe_keypoint* kps, uint8_t* desc, int cap_per_frame, int* counts, int chunk_frames) {
+  if (!h || !gray || !counts) { set_error("drfe_orb_extract_batch: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_orb_extract_batch: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  if (row_stride < (size_t)h->width || (nframes > 1 && frame_stride < row_stride * h->height)) { set_error("drfe_orb_extract_batch: bad strides"); return DRFE_ERR_ARG; }
+  if (h->pipe.active) { set_error("drfe_orb_extract_batch: the previous batch was not finished (drfe_orb_finish_batch)"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  if (h->pipe.create() != DRFE_OK) return DRFE_ERR_CUDA;
+  ChunkPipe& pp = h->pipe;
+  cudaStream_t st = h->stream;
+  const int W = h->width, H = h->height, cap = h->hd.kp_cap;
+  const size_t fbytes = (size_t)W * H;
+  const int chunk = ChunkPipe::chunk_size(nframes, chunk_frames);
+  // the copy streams start after whatever the handle's stream was doing with the staging / result buffers
+  DRFE_CUDA(cudaEventRecord(pp.ev_start, st));
+  DRFE_CUDA(cudaStreamWaitEvent(pp.h2d, pp.ev_start, 0));
+  DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_start, 0));
+  const bool dense = row_stride == (size_t)W && frame_stride == fbytes;
+  for (int f0 = 0, k = 0; f0 < nframes; f0 += chunk, ++k) {
+    const int n = std::min(chunk, nframes - f0);
+    if (dense || n == 1)
+      DRFE_CUDA(cudaMemcpy2DAsync(h->d_gray + f0 * fbytes, W, gray + (size_t)f0 * frame_stride, row_stride, W, (size_t)H * (dense ? n : 1),
+                                  cudaMemcpyHostToDevice, pp.h2d));
+    else
+      for (int f = f0; f < f0 + n; ++f)
+        DRFE_CUDA(cudaMemcpy2DAsync(h->d_gray + f * fbytes, W, gray + (size_t)f * frame_stride, row_stride, W, H, cudaMemcpyHostToDevice, pp.h2d));
+    DRFE_CUDA(cudaEventRecord(pp.ev_in[k], pp.h2d));
+    DRFE_CUDA(cudaStreamWaitEvent(st, pp.ev_in[k], 0));
+    const int rc = orb_launch(h, f0, n, h->d_gray, W, (long long)fbytes, false);
+    if (rc != DRFE_OK) return rc;
+    DRFE_CUDA(cudaEventRecord(pp.ev_done[k], st));
+    DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_done[k], 0));
+    DRFE_CUDA(cudaMemcpyAsync(counts + f0, h->hd.out_cnt + f0, n * sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
+    const int wk = std::min(cap, cap_per_frame);
+    if (kps)
+      DRFE_CUDA(cudaMemcpy2DAsync(kps + (size_t)f0 * cap_per_frame, (size_t)cap_per_frame * sizeof(drfe_keypoint), h->hd.out_kp + (size_t)f0 * cap,
+                                  (size_t)cap * sizeof(drfe_keypoint), (size_t)wk * sizeof(drfe_keypoint), n, cudaMemcpyDeviceToHost, pp.d2h));
+    if (desc)
+      DRFE_CUDA(cudaMemcpy2DAsync(desc + (size_t)f0 * cap_per_frame * 32, (size_t)cap_per_frame * 32, h->hd.out_desc + (size_t)f0 * cap * 32,
+                                  (size_t)cap * 32, (size_t)wk * 32, n, cudaMemcpyDeviceToHost, pp.d2h));
+  }
+  DRFE_CUDA(cudaMemcpyAsync(pp.h_status, h->hd.status, sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
+  pp.active = true;
+  h->batch_counts = counts; h->batch_cap = (kps || desc) ? cap_per_frame : 0x7FFFFFFF;
+  h->last_frames = nframes;
+  h->pending = true;
+  return DRFE_OK;
+}
+
+int drfe_orb_finish_batch(drfe_orb* h) {
+  if (!h) { set_error("drfe_orb_finish_batch: null handle"); return DRFE_ERR_ARG; }
+  if (!h->pipe.active) { set_error("drfe_orb_finish_batch: no batch in flight"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaStreamSynchronize(h->pipe.d2h));
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  h->pipe.active = false;
+  if (*h->pipe.h_status) {
+    const int stv = *h->pipe.h_status;
+    *h->pipe.h_status = 0;
+    DRFE_CUDA(cudaMemsetAsync(h->hd.status, 0, sizeof(int), h->stream));
+    set_error("device buffer overflow (status %d: 1 = FAST candidates, 2 = quadtree nodes)", stv);
+    return DRFE_ERR_CAPACITY;
+  }
+  for (int f = 0; f < h->last_frames; ++f)
+    if (h->batch_counts[f] > h->batch_cap) {
+      set_error("drfe_orb_finish_batch: frame %d has %d keypoints, cap_per_frame is %d", f, h->batch_counts[f], h->batch_cap);
+      return DRFE_ERR_CAPACITY;
+    }
+  return DRFE_OK;
 }
 
 // ---------------------------------------------------------------- intermediates

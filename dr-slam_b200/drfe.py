@@ -58,9 +58,11 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
+    "drfe_cape_enqueue_depth_u16", "drfe_cape_process_depth_batch", "drfe_cape_finish_batch",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
     "drfe_cape_get_grid_maps", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
@@ -100,6 +102,8 @@ def lib():
     L.drfe_orb_enqueue.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int]
     L.drfe_orb_download.argtypes = [vp, vp, vp, C.c_int, vp]
     L.drfe_orb_sync.argtypes = [vp]
+    L.drfe_orb_extract_batch.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp, C.c_int, vp, C.c_int]
+    L.drfe_orb_finish_batch.argtypes = [vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
     L.drfe_orb_level_size.argtypes = [vp, C.c_int, i32p, i32p]
@@ -115,6 +119,11 @@ def lib():
     L.drfe_cape_enqueue_depth.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
     L.drfe_cape_download.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp]
     L.drfe_cape_sync.argtypes = [vp]
+    L.drfe_cape_enqueue_depth_u16.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                              C.c_float]
+    L.drfe_cape_process_depth_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, sz, sz, C.c_float, C.c_float, C.c_float,
+                                                C.c_float, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int]
+    L.drfe_cape_finish_batch.argtypes = [vp]
     L.drfe_cape_stream.argtypes = [vp]
     L.drfe_cape_stream.restype = vp
     L.drfe_cape_process.argtypes = [vp, vp, vp, vp, C.c_int, i32p, vp, C.c_int, i32p]
@@ -282,6 +291,23 @@ class ORBextractor:
         _check(self.L.drfe_orb_download(self.h, _ptr(kps), _ptr(desc), self.cap, _ptr(counts)))
         return kps, desc, counts
 
+    def extract_batch(self, gray, kps=None, desc=None, counts=None, chunk_frames=0):
+        """Chunk-pipelined host-in / host-out batch call (asynchronous; finish_batch() waits).
+        gray: (B,H,W) uint8 host array (pinned for copy/compute overlap)."""
+        assert gray.dtype == np.uint8 and gray.ndim == 3 and gray.strides[2] == 1
+        nf = gray.shape[0]
+        kps = np.empty((nf, self.cap), KP_DTYPE) if kps is None else kps
+        desc = np.empty((nf, self.cap, 32), np.uint8) if desc is None else desc
+        counts = np.empty(nf, np.int32) if counts is None else counts
+        self._keep = (gray, kps, desc, counts)
+        _check(self.L.drfe_orb_extract_batch(self.h, nf, _ptr(gray), gray.strides[1], gray.strides[0], _ptr(kps), _ptr(desc),
+                                             kps.shape[1], _ptr(counts), chunk_frames))
+        self._nframes = nf
+        return kps, desc, counts
+
+    def finish_batch(self):
+        _check(self.L.drfe_orb_finish_batch(self.h))
+
     def sync(self):
         _check(self.L.drfe_orb_sync(self.h))
 
@@ -405,6 +431,39 @@ class CAPE:
         _check(self.L.drfe_cape_enqueue_depth(self.h, nframes, _ptr(depth), row_stride, frame_stride, mem_kind,
                                               fx, fy, cx, cy))
         self._nframes = nframes
+
+    def enqueue_depth_u16(self, depth, depth_factor, fx, fy, cx, cy, mem_kind=MEM_HOST, nframes=None, row_stride=None,
+                          frame_stride=None):
+        """raw 16-bit depth: z = float(d) * depth_factor on the device (Frame.cc:113-115)"""
+        if isinstance(depth, np.ndarray):
+            assert depth.dtype == np.uint16 and depth.ndim == 3 and depth.strides[2] == 2
+            nframes, row_stride, frame_stride = depth.shape[0], depth.strides[1] // 2, depth.strides[0] // 2
+            self._keep = depth
+        _check(self.L.drfe_cape_enqueue_depth_u16(self.h, nframes, _ptr(depth), row_stride, frame_stride, mem_kind,
+                                                  depth_factor, fx, fy, cx, cy))
+        self._nframes = nframes
+
+    def process_depth_batch(self, depth, fx, fy, cx, cy, depth_factor=1.0, seg=None, planes=None, nplanes=None,
+                            chunk_frames=0):
+        """Chunk-pipelined host-in / host-out batch call (asynchronous; finish_batch() waits).
+        depth: (B,H,W) float32, or uint16 scaled by depth_factor."""
+        assert depth.ndim == 3 and depth.dtype in (np.float32, np.uint16) and depth.strides[2] == depth.itemsize
+        nf, es = depth.shape[0], depth.itemsize
+        seg = np.empty((nf, self.H, self.W), np.uint8) if seg is None else seg
+        planes = np.zeros((nf, self.plane_cap), PLANE_DTYPE) if planes is None else planes
+        nplanes = np.empty(nf, np.int32) if nplanes is None else nplanes
+        ncyl = np.zeros(nf, np.int32)
+        cyls = np.zeros((nf, max(self.cyl_cap, 1)), CYL_DTYPE)
+        self._keep = (depth, seg, planes, nplanes, ncyl, cyls)
+        _check(self.L.drfe_cape_process_depth_batch(self.h, nf, _ptr(depth), int(depth.dtype == np.uint16), depth_factor,
+                                                    depth.strides[1] // es, depth.strides[0] // es, fx, fy, cx, cy, _ptr(seg),
+                                                    _ptr(planes), planes.shape[1], _ptr(nplanes), _ptr(cyls), self.cyl_cap,
+                                                    _ptr(ncyl), chunk_frames))
+        self._nframes = nf
+        return seg, planes, nplanes, ncyl, cyls
+
+    def finish_batch(self):
+        _check(self.L.drfe_cape_finish_batch(self.h))
 
     def enqueue_cloud(self, cloud, mem_kind=MEM_HOST, nframes=None, frame_stride=None):
         if isinstance(cloud, np.ndarray):

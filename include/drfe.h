@@ -143,6 +143,17 @@ int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_pe
 int drfe_orb_sync(drfe_orb* h);
 void* drfe_orb_stream(drfe_orb* h); /* the handle's cudaStream_t */
 
+/* A whole batch of HOST images in, HOST results out, in one asynchronous call: the batch is cut
+ * into chunks of chunk_frames frames (<= 0: 32) and chunk k's host->device copy, kernels and
+ * device->host copies run on three streams, so PCIe in both directions overlaps the kernels
+ * (pinned host memory is needed for the overlap; pageable memory works, serialised).  The call
+ * returns after queueing; the buffers must stay valid until drfe_orb_finish_batch(), which waits
+ * and reports capacity errors.  Results are those of drfe_orb_enqueue + drfe_orb_download. */
+int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride,
+                           size_t frame_stride, drfe_keypoint* kps, uint8_t* desc,
+                           int cap_per_frame, int* counts, int chunk_frames);
+int drfe_orb_finish_batch(drfe_orb* h);
+
 /* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
  * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
  * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */
@@ -179,6 +190,22 @@ int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_
 int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_t row_stride,
                             size_t frame_stride, int mem_kind, float fx, float fy, float cx,
                             float cy);
+/* The same from the sensor's raw 16-bit depth image: z = (float)d * depth_factor on the device,
+ * i.e. imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) of Frame.cc:113-115 (TUM: factor =
+ * 1/5000) fused into the cloud kernel; halves the host->device bytes of a depth frame. */
+int drfe_cape_enqueue_depth_u16(drfe_cape* h, int nframes, const uint16_t* depth, size_t row_stride,
+                                size_t frame_stride, int mem_kind, float depth_factor, float fx,
+                                float fy, float cx, float cy);
+/* Chunk-pipelined HOST-in / HOST-out batch call (see drfe_orb_extract_batch): depth is float
+ * (depth_is_u16 == 0) or raw uint16_t scaled by depth_factor (depth_is_u16 != 0); results as
+ * drfe_cape_download delivers them.  Asynchronous; drfe_cape_finish_batch() waits. */
+int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, int depth_is_u16,
+                                  float depth_factor, size_t row_stride, size_t frame_stride,
+                                  float fx, float fy, float cx, float cy, uint8_t* seg_out,
+                                  drfe_plane* planes, int plane_cap, int* nr_planes,
+                                  drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders,
+                                  int chunk_frames);
+int drfe_cape_finish_batch(drfe_cape* h);
 /* wait + copy out.  seg_out: nframes * H*W labels (0 = none, 1..n planes, 51.. cylinders),
  * fully written (the reference only writes labelled pixels of a caller-zeroed image).
  * planes[f*plane_cap + i]; cylinders may be NULL when cylinder detection is off.

@@ -73,3 +73,40 @@ def test_cape_full_batch(drfe, orc, sequence):
         assert np.array_equal(seg[f], oseg) and npl[f] == len(oplanes)
         assert np.allclose(planes[f, :npl[f]]["normal"], oplanes["normal"], atol=1e-5, rtol=0)
         assert np.allclose(planes[f, :npl[f]]["d"], oplanes["d"], atol=1e-5, rtol=1e-9)
+
+
+def test_pipelined_batch_calls_match_enqueue_download(drfe):
+    """drfe_orb_extract_batch / drfe_cape_process_depth_batch (chunked H2D | kernels | D2H pipeline) deliver exactly
+    what enqueue + download deliver, for chunk sizes that do and do not divide the batch, and for raw u16 depth."""
+    B = 12
+    frames = [drfe.synth_frame(640, 480, i % 3, 20260900 + i, 1.0) for i in range(B)]
+    gray = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames])
+    K = frames[0][2]
+    mc = float(np.float32(np.cos(np.pi / 12)))
+    orb = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=B)
+    cape = drfe.CAPE(480, 640, 20, 20, False, mc, 50.0, max_batch=B)
+    orb.enqueue(gray)
+    rk, rd, rc = orb.download()
+    cape.enqueue_depth(depth, *K)
+    rseg, rpl, rnp = cape.download()
+    for chunk in (0, 5, 1):
+        kps, desc, cnt = orb.extract_batch(gray, chunk_frames=chunk)
+        seg, planes, npl, _, _ = cape.process_depth_batch(depth, *K, chunk_frames=chunk)
+        orb.finish_batch(); cape.finish_batch()
+        assert np.array_equal(cnt, rc) and np.array_equal(npl, rnp) and np.array_equal(seg, rseg)
+        for f in range(B):
+            assert kps[f, :cnt[f]].tobytes() == rk[f, :rc[f]].tobytes() and np.array_equal(desc[f, :cnt[f]], rd[f, :rc[f]])
+            assert all(np.array_equal(planes[f, :npl[f]][n], rpl[f, :rnp[f]][n]) for n in ("normal", "d", "nr_pts", "MSE"))
+    # raw sensor depth: u16 * (1/5000), converted on the device like Frame.cc:113-115
+    q = np.rint(depth * 5000).astype(np.uint16)
+    fac = np.float32(1.0 / 5000.0)
+    assert np.array_equal(q.astype(np.float32) * fac, depth), "the synthetic depth is quantised like a TUM png"
+    seg, planes, npl, _, _ = cape.process_depth_batch(q, *K, depth_factor=float(fac), chunk_frames=4)
+    cape.finish_batch()
+    assert np.array_equal(seg, rseg) and np.array_equal(npl, rnp)
+    cape.enqueue_depth_u16(q, float(fac), *K)
+    seg2, _, npl2 = cape.download()
+    assert np.array_equal(seg2, rseg) and np.array_equal(npl2, rnp)
+    with pytest.raises(drfe.DrfeError):
+        orb.finish_batch()          # nothing in flight
