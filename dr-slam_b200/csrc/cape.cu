@@ -1340,6 +1340,9 @@ struct drfe_cape {
   int last_frames = 0;
   bool pending = false, margin = false;
   StageTimer timer;
+  ChunkPipe pipe;
+  int* batch_nplanes = nullptr;  // host destination of the running batch call
+  int batch_plane_cap = 0;
   std::vector<void*> allocs;
 };
 
@@ -1478,6 +1481,7 @@ int drfe_cape_destroy(drfe_cape* h) {
   if (!h) return DRFE_OK;
   DeviceScope ds(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  h->pipe.destroy();
   for (void* p : h->allocs) cudaFree(p);
   h->timer.destroy();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1574,6 +1578,117 @@ int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_
   } else { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
   h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy; h->hd.depth16 = nullptr;
   return cape_run(h, nframes);
+}
+
+
+int drfe_cape_enqueue_depth_u16(drfe_cape* h, int nframes, const uint16_t* depth, size_t row_stride, size_t frame_stride,
+                                int mem_kind, float depth_factor, float fx, float fy, float cx, float cy) {
+  if (!h || !depth) { set_error("drfe_cape_enqueue_depth_u16: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_enqueue_depth_u16: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  const int W = h->hd.W, H = h->hd.H;
+  if (row_stride < (size_t)W) { set_error("drfe_cape_enqueue_depth_u16: row_stride < width"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  cudaStream_t st = h->stream;
+  h->timer.begin(st);
+  if (mem_kind == DRFE_MEM_HOST) {
+    uint16_t* stage = reinterpret_cast<uint16_t*>(h->d_depth);
+    for (int f = 0; f < nframes; ++f)
+      DRFE_CUDA(cudaMemcpy2DAsync(stage + (size_t)f * W * H, W * sizeof(uint16_t), depth + f * frame_stride, row_stride * sizeof(uint16_t),
+                                  W * sizeof(uint16_t), H, cudaMemcpyHostToDevice, st));
+    h->hd.depth16 = stage; h->hd.depth_rs = W; h->hd.depth_fs = (long long)W * H;
+    h->timer.mark("h2d", st);
+  } else if (mem_kind == DRFE_MEM_DEVICE) {
+    h->hd.depth16 = depth; h->hd.depth_rs = (long long)row_stride; h->hd.depth_fs = (long long)frame_stride;
+  } else { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
+  h->hd.depth = nullptr; h->hd.depth_factor = depth_factor;
+  h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy;
+  return cape_run(h, nframes);
+}
+
+int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, int depth_is_u16, float depth_factor,
+                                  size_t row_stride, size_t frame_stride, float fx, float fy, float cx, float cy,
+                                  uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
+                                  drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders, int chunk_frames) {
+  if (!h || !depth || !nr_planes) { set_error("drfe_cape_process_depth_batch: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_process_depth_batch: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  const int W = h->hd.W, H = h->hd.H;
+  if (row_stride < (size_t)W || (nframes > 1 && frame_stride < row_stride * H)) { set_error("drfe_cape_process_depth_batch: bad strides"); return DRFE_ERR_ARG; }
+  if (h->pipe.active) { set_error("drfe_cape_process_depth_batch: the previous batch was not finished (drfe_cape_finish_batch)"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  if (h->pipe.create() != DRFE_OK) return DRFE_ERR_CUDA;
+  ChunkPipe& pp = h->pipe;
+  cudaStream_t st = h->stream;
+  const size_t N = (size_t)W * H, esz = depth_is_u16 ? sizeof(uint16_t) : sizeof(float);
+  const int chunk = ChunkPipe::chunk_size(nframes, chunk_frames);
+  if (depth_is_u16) { h->hd.depth16 = reinterpret_cast<const uint16_t*>(h->d_depth); h->hd.depth = nullptr; h->hd.depth_factor = depth_factor; }
+  else { h->hd.depth = h->d_depth; h->hd.depth16 = nullptr; }
+  h->hd.depth_rs = W; h->hd.depth_fs = (long long)N;
+  h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy;
+  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
+  DRFE_CUDA(cudaEventRecord(pp.ev_start, st));
+  DRFE_CUDA(cudaStreamWaitEvent(pp.h2d, pp.ev_start, 0));
+  DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_start, 0));
+  const bool dense = row_stride == (size_t)W && frame_stride == N;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(h->d_depth);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(depth);
+  for (int f0 = 0, k = 0; f0 < nframes; f0 += chunk, ++k) {
+    const int n = std::min(chunk, nframes - f0);
+    if (dense)
+      DRFE_CUDA(cudaMemcpyAsync(stage + f0 * N * esz, src + (size_t)f0 * frame_stride * esz, (size_t)n * N * esz, cudaMemcpyHostToDevice, pp.h2d));
+    else
+      for (int f = f0; f < f0 + n; ++f)
+        DRFE_CUDA(cudaMemcpy2DAsync(stage + f * N * esz, W * esz, src + (size_t)f * frame_stride * esz, row_stride * esz, W * esz, H,
+                                    cudaMemcpyHostToDevice, pp.h2d));
+    DRFE_CUDA(cudaEventRecord(pp.ev_in[k], pp.h2d));
+    DRFE_CUDA(cudaStreamWaitEvent(st, pp.ev_in[k], 0));
+    const int rc = cape_launch(h, f0, n, false);
+    if (rc != DRFE_OK) return rc;
+    DRFE_CUDA(cudaEventRecord(pp.ev_done[k], st));
+    DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_done[k], 0));
+    DRFE_CUDA(cudaMemcpyAsync(nr_planes + f0, h->hd.nplanes + f0, n * sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
+    if (seg_out) DRFE_CUDA(cudaMemcpyAsync(seg_out + f0 * N, h->hd.seg + f0 * N, N * n, cudaMemcpyDeviceToHost, pp.d2h));
+    if (planes && plane_cap > 0)
+      DRFE_CUDA(cudaMemcpy2DAsync(planes + (size_t)f0 * plane_cap, (size_t)plane_cap * sizeof(drfe_plane), h->hd.planes + (size_t)f0 * kMaxPlanes,
+                                  (size_t)kMaxPlanes * sizeof(drfe_plane), (size_t)std::min(plane_cap, kMaxPlanes) * sizeof(drfe_plane), n,
+                                  cudaMemcpyDeviceToHost, pp.d2h));
+    if (h->hd.cyl) {
+      if (nr_cylinders) DRFE_CUDA(cudaMemcpyAsync(nr_cylinders + f0, h->hd.ncyl_final + f0, n * sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
+      if (cylinders && cyl_cap > 0)
+        DRFE_CUDA(cudaMemcpy2DAsync(cylinders + (size_t)f0 * cyl_cap, (size_t)cyl_cap * sizeof(drfe_cylinder), h->hd.cyls + (size_t)f0 * h->hd.max_sub,
+                                    (size_t)h->hd.max_sub * sizeof(drfe_cylinder), (size_t)std::min(cyl_cap, h->hd.max_sub) * sizeof(drfe_cylinder), n,
+                                    cudaMemcpyDeviceToHost, pp.d2h));
+    }
+  }
+  DRFE_CUDA(cudaMemcpyAsync(pp.h_status, h->hd.status, sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
+  if (!h->hd.cyl && nr_cylinders) for (int f = 0; f < nframes; ++f) nr_cylinders[f] = 0;
+  pp.active = true;
+  h->batch_nplanes = nr_planes; h->batch_plane_cap = planes ? plane_cap : 0x7FFFFFFF;
+  h->last_frames = nframes;
+  h->pending = true;
+  return DRFE_OK;
+}
+
+int drfe_cape_finish_batch(drfe_cape* h) {
+  if (!h) { set_error("drfe_cape_finish_batch: null handle"); return DRFE_ERR_ARG; }
+  if (!h->pipe.active) { set_error("drfe_cape_finish_batch: no batch in flight"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaStreamSynchronize(h->pipe.d2h));
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
+  h->pipe.active = false;
+  if (*h->pipe.h_status) {
+    const int stv = *h->pipe.h_status;
+    *h->pipe.h_status = 0;
+    DRFE_CUDA(cudaMemsetAsync(h->hd.status, 0, sizeof(int), h->stream));
+    set_error("CAPE: device-side capacity exceeded (status %d)", stv);
+    return DRFE_ERR_CAPACITY;
+  }
+  for (int f = 0; f < h->last_frames; ++f)
+    if (h->batch_nplanes[f] > h->batch_plane_cap) {
+      set_error("drfe_cape_finish_batch: frame %d has %d planes, plane_cap is %d", f, h->batch_nplanes[f], h->batch_plane_cap);
+      return DRFE_ERR_CAPACITY;
+    }
+  return DRFE_OK;
 }
 
 int drfe_cape_sync(drfe_cape* h) {
