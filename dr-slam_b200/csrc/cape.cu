@@ -665,7 +665,8 @@ __device__ __noinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_p
 
 enum { BV_FL = 0, BV_FR, BV_FU, BV_FD, BV_U, BV_A, BV_B, BV_M, BV_H, BV_C0, BV_CL, BV_R0, BV_RL, BV_VALID, BV_COUNT };
 
-template <int THREADS>
+// CYL: compiled with the cylinder stages (cylinder_detection); the plain instantiation carries none of that code
+template <int THREADS, bool CYL>
 __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict__ Pp, int f0) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CapeDev& P = *Pp;
@@ -960,9 +961,9 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   __syncthreads();
   // ---- extruded regions (cylinder_detection, CAPE.cpp:179-216): a region of more than 5 cells that is not
   // a plane goes through CylinderSeg; regions are taken in job order because they share one rand() stream.
-  CylSub* subs = P.cyl ? P.subs + (long long)f * P.max_sub : nullptr;
+  CylSub* subs = CYL ? P.subs + (long long)f * P.max_sub : nullptr;
   unsigned short* subid = reinterpret_cast<unsigned short*>(bin);   // bin[] is free after the seed loop
-  if (P.cyl) {
+  if (CYL) {
     for (int c = tid; c < nc; c += THREADS) subid[c] = 0xFFFF;
     __syncthreads();
     if (wid == 0) {
@@ -991,7 +992,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     };
     for (int j = 0; j < njobs; ++j) {
       if (job_label[j]) { job_label[j] = (uint8_t)next_plane(); continue; }
-      if (!P.cyl) continue;
+      if (!CYL) continue;
       for (int s = job_sub0[j]; s < job_sub0[j + 1]; ++s) {
         if (!subs[s].is_cyl) {
           const int l = next_plane();
@@ -1015,12 +1016,12 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   for (int c = tid; c < nc; c += THREADS) {
     const int j = jobid[c];
     int pl = (j == 0xFFFF) ? 0 : job_label[j], cl = 0;
-    if (P.cyl && subid[c] != 0xFFFF) {
+    if (CYL && subid[c] != 0xFFFF) {
       const CylSub& sb = subs[subid[c]];
       if (sb.is_cyl) cl = sb.label; else pl = sb.label;
     }
     pmap[c] = (uint8_t)pl;
-    if (P.cyl) P.cyl_map[(long long)f * nc + c] = cl;
+    if (CYL) P.cyl_map[(long long)f * nc + c] = cl;
   }
   __syncthreads();
   // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
@@ -1106,7 +1107,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     __syncthreads();
   }
   // ---- cylinders: same erode / dilate per cylinder region (CAPE.cpp:323-357); border rows follow the planes'
-  if (P.cyl) {
+  if (CYL) {
     uint8_t* cyl_eroded = P.cyl_eroded_map + (long long)f * nc;
     const int* cyl_map = P.cyl_map + (long long)f * nc;
     for (int c = tid; c < nc; c += THREADS) cyl_eroded[c] = 0;
@@ -1460,7 +1461,8 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
     h->grid_smem = base + (D.grid_sums_smem ? nc * 36 : 0);
     if (h->grid_smem > 200 * 1024 || nw > 4 * 128) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
   }
-  if (cudaFuncSetAttribute(k_cape_grid<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_cape_grid<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_cape_grid<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
     set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
   }
   {
@@ -1515,7 +1517,8 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   if (timed) h->timer.mark("cells", st);
   DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
   if (timed) h->timer.mark("fit", st);
-  DRFE_LAUNCH(k_cape_grid<128>, n, 128, h->grid_smem, st, h->dd, f0);
+  if (h->hd.cyl) DRFE_LAUNCH((k_cape_grid<128, true>), n, 128, h->grid_smem, st, h->dd, f0);
+  else DRFE_LAUNCH((k_cape_grid<128, false>), n, 128, h->grid_smem, st, h->dd, f0);
   if (timed) h->timer.mark("grid", st);
   if (h->margin) {
     const long long tot = (long long)h->hd.H * h->hd.W * n;
