@@ -21,6 +21,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "drfe_internal.h"
@@ -57,6 +58,7 @@ struct LevelDev {
   float scale, size;
   long long xtab_off, ytab_off;     // element offsets into the resize tables (level >= 1)
   int ptile_off, ptile_cnt, ptile_gx;   // this level's k_pyr_resize tiles inside OrbDev::ptiles
+  int pcol_off, pcol_groups, ytab2_off; // this level's k_pyr_stream column records / row table inside OrbDev::pcols / ytab2
 };
 
 struct PyrTile;
@@ -71,6 +73,8 @@ struct OrbDev {
   const uint2* rtab;                // resize tables {idx0 | idx1<<16, c0 | c1<<16}
   const StripDev* strips;
   const struct PyrTile* ptiles;     // k_pyr_resize tiles of all levels
+  const struct PyrCol* pcols;       // k_pyr_stream per-column-group records of all levels (null: generic kernel only)
+  const uint2* ytab2;               // k_pyr_stream row table {r0 | b0 << 16, b1} per destination row
   int pyr_src_bytes;                // smem bytes reserved for a tile's source window
   uint32_t* cand;                   // [B][cand_total] packed x | y<<12 | q<<24 (region coords)
   long long cand_fstride;
@@ -98,28 +102,48 @@ __device__ __forceinline__ uint8_t* roi_ptr(const OrbDev& P, const LevelDev& L, 
 }
 
 // ------------------------------------------------------------------ K1 pyramid
-// Each thread writes 4 horizontally adjacent bytes (one aligned uchar4) of the bordered
-// level image; border positions are reflected to their interior source coordinate and
-// recomputed (identical bytes to copyMakeBorder, no second pass).
+// Each thread writes 16 horizontally adjacent bytes (one aligned uint4) of the bordered level
+// image.  Threads are numbered so that whole warps do the same kind of work: first every
+// (row, 16-byte chunk inside the image) pair — one 16-byte load, one 16-byte store — then the
+// chunks that touch the 19 px frame, which gather their bytes from the reflected interior
+// coordinate (identical bytes to copyMakeBorder, no second pass).  ci: chunks inside the image per
+// row (0 when the source is not 16-byte aligned), cb: frame chunks per row, *_magic = ceil(2^32 / n).
 __global__ void __launch_bounds__(256) k_pyr_level0(const OrbDev* __restrict__ Pp,
                                                      const uint8_t* __restrict__ src,
-                                                     long long row_stride, long long frame_stride, int f0) {
+                                                     long long row_stride, long long frame_stride, int f0,
+                                                     int ci, uint32_t ci_magic, int cb, uint32_t cb_magic) {
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[0];
-  const int groups = (L.w + 40 + 3) >> 2;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y * blockDim.y + threadIdx.y;
-  const int f = blockIdx.z + f0;
-  if (g >= groups || by >= L.rows) return;
-  const uint8_t* s = src + (long long)f * frame_stride + (long long)reflect101(by - kEdge, L.h) * row_stride;
-  const int bx = 4 * g - 20;
-  uchar4 o;
-  o.x = __ldg(s + reflect101(bx, L.w));
-  o.y = __ldg(s + reflect101(bx + 1, L.w));
-  o.z = __ldg(s + reflect101(bx + 2, L.w));
-  o.w = __ldg(s + reflect101(bx + 3, L.w));
-  uint8_t* d = P.pyr + L.img_off + (long long)f * L.img_fstride + (long long)by * L.pitch + (kXOff - 20) + 4 * g;
-  *reinterpret_cast<uchar4*>(d) = o;
+  const int f = blockIdx.y + f0;
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t nA = (uint32_t)L.rows * (uint32_t)ci;
+  uint8_t* dbase = P.pyr + L.img_off + (long long)f * L.img_fstride;
+  const uint8_t* sbase = src + (long long)f * frame_stride;
+  if (idx < nA) {
+    const int by = (int)__umulhi(idx, ci_magic), c = (int)idx - by * ci;
+    const uint4 o = __ldg(reinterpret_cast<const uint4*>(sbase + (long long)reflect101(by - kEdge, L.h) * row_stride) + c);
+    *reinterpret_cast<uint4*>(dbase + (long long)by * L.pitch + kXOff + 16 * c) = o;
+    return;
+  }
+  const uint32_t j = idx - nA;
+  if (j >= (uint32_t)L.rows * (uint32_t)cb) return;
+  const int by = (int)__umulhi(j, cb_magic), q = (int)j - by * cb;
+  const int c = q < 2 ? q : q + ci;                              // chunk index from the row start (ROI starts at chunk 2)
+  const uint8_t* s = sbase + (long long)reflect101(by - kEdge, L.h) * row_stride;
+  const int x0 = 16 * c - kXOff;                                 // image column of the chunk's first byte
+  uint32_t w[4];
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int x = x0 + 4 * qq + k;
+      x = min(max(x, -(L.w - 1)), 2 * (L.w - 1));                // bytes outside the frame are never read back; keep the index valid
+      v |= (uint32_t)__ldg(s + reflect101(x, L.w)) << (8 * k);
+    }
+    w[qq] = v;
+  }
+  *reinterpret_cast<uint4*>(dbase + (long long)by * L.pitch + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // cv::resize INTER_LINEAR 8UC1: 11-bit coefficient fixed point.
@@ -191,6 +215,90 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ P
     const uint32_t o2 = (((b0 * (int)(T0.y & 0xFFFF)) >> 16) + ((b1 * (int)(T1.y & 0xFFFF)) >> 16) + 2) >> 2;
     const uint32_t o3 = (((b0 * (int)(T0.y >> 16)) >> 16) + ((b1 * (int)(T1.y >> 16)) >> 16) + 2) >> 2;
     *reinterpret_cast<uint32_t*>(dbase + (long long)by * L.pitch) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+  }
+}
+
+
+// ---- streaming resize (the fast path; k_pyr_resize above stays as the generic fallback)
+// One thread = 4 adjacent columns of the bordered level x kPyrR consecutive interior rows.  Per
+// source row the thread loads the 12 aligned bytes that hold its <= 6 source pixels straight from
+// global memory (neighbouring threads share the lines in L1), realigns them with two funnel
+// shifts and gets each horizontal sum s0*c0 + s1*c1 from ONE funnel shift + ONE 2-way dot product
+// (IDP.2A: 16-bit coefficients x 8-bit pixels).  Source rows are consumed in order — r0(y) is
+// monotone — so each is filtered once and only two rows of sums live in registers; the vertical
+// pass is two high-multiplies per pixel: ((T >> 4) * b) >> 16 == umulhi(T & ~15, b << 12).
+// Rows 1..19 and h-20..h-2 are also stored to their BORDER_REFLECT_101 mirror rows; mirrored
+// columns come for free from the per-column records (a border column is just another column
+// whose source index is the reflected one).
+static const int kPyrR = 16;
+struct PyrCol { uint32_t base, sh, coef[4], pad0, pad1; };   // window base (byte offset in the source ROI row), 8*d_k per byte, c0 | c1 << 16
+
+struct PyrRow { uint32_t w0, w1, w2; };
+__device__ __forceinline__ PyrRow pyr_load(const uint8_t* __restrict__ p) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+  PyrRow r;
+  r.w0 = __ldg(q); r.w1 = __ldg(q + 1); r.w2 = __ldg(q + 2);
+  return r;
+}
+__device__ __forceinline__ void pyr_hfilter(const PyrRow& r, int al, uint32_t sh, const uint32_t (&coef)[4], uint32_t (&T)[4]) {
+  const uint32_t lo = __funnelshift_r(r.w0, r.w1, al), hi = __funnelshift_r(r.w1, r.w2, al);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t v = __funnelshift_rc(lo, hi, (sh >> (8 * k)) & 0xFFu);      // bytes: s0, s1, ...
+    T[k] = __dp2a_lo(coef[k], v, 0u) & ~15u;
+  }
+}
+
+__global__ void __launch_bounds__(128, 10) k_pyr_stream(const OrbDev* __restrict__ Pp, int level, int f0, int R) {
+  const OrbDev& P = *Pp;
+  const LevelDev& L = P.lv[level];
+  const LevelDev& S = P.lv[level - 1];
+  const int g = blockIdx.x * 32 + threadIdx.x;
+  const int y0 = (blockIdx.y * 4 + threadIdx.y) * R;
+  const int f = blockIdx.z + f0;
+  if (g >= L.pcol_groups || y0 >= L.h) return;
+  const int y1 = min(y0 + R, L.h), h = L.h;
+  const PyrCol pc = P.pcols[L.pcol_off + g];
+  const int al = 8 * (int)(pc.base & 3u);
+  const long long sp = S.pitch, dp = L.pitch;
+  const uint2* __restrict__ yt = P.ytab2 + L.ytab2_off;
+  int a = (int)(yt[y0].x & 0xFFFFu);
+  const uint8_t* pn = roi_ptr(P, S, f) + (pc.base & ~3u) + (long long)a * sp;   // next source row to fetch
+  uint8_t* dcol = P.pyr + L.img_off + (long long)f * L.img_fstride + (kXOff - 20) + 4 * g;
+  uint8_t* dptr = dcol + (long long)(y0 + kEdge) * dp;
+  uint32_t Ta[4], Tb[4];
+  {
+    const PyrRow ra = pyr_load(pn), rb = pyr_load(pn + sp);
+    pn += 2 * sp;
+    pyr_hfilter(ra, al, pc.sh, pc.coef, Ta);
+    pyr_hfilter(rb, al, pc.sh, pc.coef, Tb);
+  }
+  PyrRow nx = pyr_load(pn), nx2 = pyr_load(pn + sp);   // rows a + 2 and a + 3, fetched two steps ahead of their use
+  pn += sp;
+#pragma unroll 1
+  for (int y = y0; y < y1; ++y) {
+    const uint2 e = yt[y];                       // {r0 | b0 << 16, b1}
+    int adv = (int)(e.x & 0xFFFFu) - a;          // 0, 1 or 2 source rows to move on; warp-uniform (a warp shares y)
+    a += adv;
+#pragma unroll 1
+    while (adv > 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Ta[k] = Tb[k];
+      pyr_hfilter(nx, al, pc.sh, pc.coef, Tb);
+      nx = nx2;
+      pn += sp;
+      nx2 = pyr_load(pn);
+      --adv;
+    }
+    const uint32_t B0 = (e.x >> 16) << 12, B1 = e.y << 12;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = (__umulhi(Ta[k], B0) + __umulhi(Tb[k], B1) + 2u) >> 2;
+    const uint32_t word = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    *reinterpret_cast<uint32_t*>(dptr) = word;
+    dptr += dp;
+    if (y <= kEdge) { if (y >= 1) *reinterpret_cast<uint32_t*>(dcol + (long long)(kEdge - y) * dp) = word; }
+    if (y >= h - 1 - kEdge) { if (y <= h - 2) *reinterpret_cast<uint32_t*>(dcol + (long long)(kEdge + 2 * (h - 1) - y) * dp) = word; }
   }
 }
 
@@ -1062,6 +1170,9 @@ static int orb_build(drfe_orb* h) {
   D.nlevels = nl; D.B = h->max_batch; D.ini_th = pr.ini_th_fast; D.min_th = pr.min_th_fast;
   std::vector<uint2> rtab;
   std::vector<PyrTile> ptiles;
+  std::vector<PyrCol> pcols;
+  std::vector<uint2> ytab2;
+  bool stream_ok = true;
   int max_pyr_src = 0, max_pyr_nsy = 0;
   std::vector<StripDev> strips;
   long long img_total = 0, blur_total = 0, cand_total = 0;
@@ -1125,6 +1236,36 @@ static int orb_build(drfe_orb* h) {
           max_pyr_nsy = std::max(max_pyr_nsy, nsy);
         }
       L.ptile_cnt = (int)ptiles.size() - L.ptile_off;
+      // k_pyr_stream records: per 4-column group the byte window base, the pixel offsets inside it and the
+      // coefficient pairs; per destination row the first source row and the two vertical coefficients
+      L.pcol_off = (int)pcols.size(); L.pcol_groups = groups;
+      for (int g = 0; g < groups; ++g) {
+        PyrCol pc{};
+        uint32_t i0[4];
+        uint32_t base = 0xFFFFFFFFu;
+        for (int k = 0; k < 4; ++k) {
+          const uint2 e = rtab[L.xtab_off + refl(4 * g - 20 + k, L.w)];
+          i0[k] = e.x & 0xFFFF;
+          const uint32_t i1 = e.x >> 16, c1 = e.y >> 16;
+          if (i1 != i0[k] + 1 && c1 != 0) stream_ok = false;
+          pc.coef[k] = e.y;
+          base = std::min(base, i0[k]);
+        }
+        pc.base = base;
+        for (int k = 0; k < 4; ++k) {
+          if (i0[k] - base > 4) stream_ok = false;
+          pc.sh |= (8u * (i0[k] - base)) << (8 * k);
+        }
+        pcols.push_back(pc);
+      }
+      L.ytab2_off = (int)ytab2.size();
+      for (int y = 0; y < L.h; ++y) {
+        const uint2 e = rtab[L.ytab_off + y];
+        const uint32_t r0 = e.x & 0xFFFF, r1 = e.x >> 16, b0 = e.y & 0xFFFF, b1 = e.y >> 16;
+        if (r1 != r0 + 1 && b1 != 0) stream_ok = false;
+        if (y > 0 && r0 < (rtab[L.ytab_off + y - 1].x & 0xFFFF)) stream_ok = false;
+        ytab2.push_back(make_uint2(r0 | (b0 << 16), b1));
+      }
     }
     // FAST strips: the interior rows [19 + i*hCell, min(19 + (i+1)*hCell, h-19)) of cell row i.
     // Cell (i, j) of the reference's grid (:789-829) evaluates FAST exactly on the pixels
@@ -1188,6 +1329,14 @@ static int orb_build(drfe_orb* h) {
   if (dev_alloc(h, &d_ptiles, ptiles.size())) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(d_ptiles, ptiles.data(), ptiles.size() * sizeof(PyrTile), cudaMemcpyHostToDevice));
   D.ptiles = d_ptiles;
+  if (stream_ok && !pcols.empty() && getenv("DRFE_PYR_GENERIC") == nullptr) {
+    PyrCol* d_pcols; uint2* d_ytab2;
+    if (dev_alloc(h, &d_pcols, pcols.size())) return DRFE_ERR_CUDA;
+    if (dev_alloc(h, &d_ytab2, ytab2.size())) return DRFE_ERR_CUDA;
+    DRFE_CUDA(cudaMemcpy(d_pcols, pcols.data(), pcols.size() * sizeof(PyrCol), cudaMemcpyHostToDevice));
+    DRFE_CUDA(cudaMemcpy(d_ytab2, ytab2.data(), ytab2.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    D.pcols = d_pcols; D.ytab2 = d_ytab2;
+  }
   D.pyr_src_bytes = (max_pyr_src + 15) / 16 * 16;
   h->pyr_smem = (size_t)D.pyr_src_bytes + (size_t)max_pyr_nsy * 32 * sizeof(uint2);
   if (dev_alloc(h, &d_strips, strips.size())) return DRFE_ERR_CUDA;
@@ -1284,12 +1433,26 @@ static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long 
   DRFE_LAUNCH(k_zero_counts, (n * nl + 255) / 256, 256, 0, st, h->dd, f0, n);
   {
     const LevelDev& L = D.lv[0];
-    dim3 blk(64, 4), grd(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
-    DRFE_LAUNCH(k_pyr_level0, grd, blk, 0, st, h->dd, src, rs, fs, f0);
+    const int chunks = (kXOff + L.w + 20 + 15) / 16;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)rs | (uintptr_t)fs) & 15) == 0;
+    const int ci = vec_ok ? L.w / 16 : 0, cb = chunks - ci;
+    const uint32_t ci_magic = ci ? (uint32_t)(((1ull << 32) + ci - 1) / ci) : 0, cb_magic = (uint32_t)(((1ull << 32) + cb - 1) / cb);
+    const long long threads = (long long)L.rows * (ci + cb);
+    DRFE_LAUNCH(k_pyr_level0, dim3((unsigned)((threads + 255) / 256), n), 256, 0, st, h->dd, src, rs, fs, f0, ci, ci_magic, cb, cb_magic);
   }
   for (int l = 1; l < nl; ++l) {
     const LevelDev& L = D.lv[l];
-    DRFE_LAUNCH(k_pyr_resize, dim3(L.ptile_cnt, n), 256, h->pyr_smem, st, h->dd, l, f0);
+    if (D.pcols) {
+      // rows per thread: long strips amortise the two priming rows on the big levels; the small levels are
+      // latency-bound (few warps), so they get short strips = more threads and shorter dependent chains
+      static const int r_env = getenv("DRFE_PYR_R") ? atoi(getenv("DRFE_PYR_R")) : 0;
+      const long long px = (long long)L.w * L.h * n;
+      const int R = r_env > 0 ? r_env : (px >= (24 << 20) ? kPyrR : (px >= (8 << 20) ? 8 : 4));
+      const int strips = (L.h + R - 1) / R;
+      DRFE_LAUNCH(k_pyr_stream, dim3((L.pcol_groups + 31) / 32, (strips + 3) / 4, n), dim3(32, 4), 0, st, h->dd, l, f0, R);
+    } else {
+      DRFE_LAUNCH(k_pyr_resize, dim3(L.ptile_cnt, n), 256, h->pyr_smem, st, h->dd, l, f0);
+    }
   }
   if (timed) h->timer.mark("pyramid", st);
   DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0);
