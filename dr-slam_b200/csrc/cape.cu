@@ -198,7 +198,9 @@ __device__ __forceinline__ bool quotient_needs_exact(double q) {
 
 static const int kSumsThreads = 128, kSumsChunk = 5;
 // MODE 0: the cell-major cloud is given; 1: float depth image; 2: raw 16-bit depth image scaled by depth_factor
-template <int MODE>
+// CELL: compile-time cell edge (square cells of 20 or 10 px, the two sizes DR-SLAM's yaml files use) so that
+// the per-element index arithmetic and bounds tests fold away; 0 = any cell size, read from the descriptor
+template <int MODE, int CELL>
 __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   constexpr bool FROM_DEPTH = MODE != 0;
   extern __shared__ __align__(16) float s_zall[];           // [8 groups][npc]
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
   if (gid0 >= nframes * ncells) return;                     // whole 16-lane groups exit together
   const int gid = gid0 + f0 * ncells;                       // global cell index over the batch
   const int f = gid / ncells, cell = gid - f * ncells;
-  const int npc = P.npc, cw = P.cw, ch = P.ch;
+  const int npc = CELL ? CELL * CELL : P.npc, cw = CELL ? CELL : P.cw, ch = CELL ? CELL : P.ch;
   float* s_z = s_zall + (threadIdx.x >> 4) * npc;
   const long long N = (long long)P.H * P.W;
   float* __restrict__ CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
@@ -270,6 +272,9 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
   const double col0 = (double)(cc * cw) - (double)P.cx, row0 = (double)(cr * ch) - (double)P.cy;
   int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
   const int step_r = 16 / cw, step_c = 16 - step_r * cw;    // element i + 16
+  // (double)j - cx and (double)i - cy of the element, stepped along with (lr, lc): sums of small half-integers, exact
+  double dcol = col0 + (double)lc, drow = row0 + (double)lr;
+  const double dstep_c = (double)step_c, dstep_r = (double)step_r, dcw = (double)cw;
   for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
 #pragma unroll
     for (int u = 0; u < kSumsChunk; ++u) {
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
           // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
           // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
           const double zd = (double)z;
-          const double tx = (col0 + (double)lc) * zd, ty = (row0 + (double)lr) * zd;
+          const double tx = dcol * zd, ty = drow * zd;
           const double qx = tx * rfx, qy = ty * rfy;
           if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
           else { x = (float)qx; y = (float)qy; }
@@ -298,8 +303,8 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
           ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
         }
       }
-      lc += step_c; lr += step_r;
-      if (lc >= cw) { lc -= cw; ++lr; }
+      lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
+      if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
     }
   }
 #pragma unroll
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
     i += step;
     while (i < j) {
       const float z = s_z[i];
-      if (z > 0 && (double)fabsf(z - z_last) < 100.0) z_last = z;
+      if (z > 0 && fabsf(z - z_last) < 100.0f) z_last = z;   // == (double)|dz| < 100.0: 100 is a float
       else if (z > 0) ++jumps;
       i += step;
     }
@@ -1468,11 +1473,13 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   {
     const size_t sums_smem = (size_t)(kSumsThreads / 16) * D.npc * sizeof(float);
     if (sums_smem > 200 * 1024) { set_error("drfe_cape_create: cells of %d points are too large", D.npc); return fail(DRFE_ERR_ARG); }
-    if (cudaFuncSetAttribute(k_cape_sums<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_cape_sums<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_cape_sums<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
-    }
+    cudaError_t e = cudaSuccess;
+#define DRFE_SUMS_ATTR(M, C) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cape_sums<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem)
+    DRFE_SUMS_ATTR(0, 0); DRFE_SUMS_ATTR(1, 0); DRFE_SUMS_ATTR(2, 0);
+    DRFE_SUMS_ATTR(0, 20); DRFE_SUMS_ATTR(1, 20); DRFE_SUMS_ATTR(2, 20);
+    DRFE_SUMS_ATTR(0, 10); DRFE_SUMS_ATTR(1, 10); DRFE_SUMS_ATTR(2, 10);
+#undef DRFE_SUMS_ATTR
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA); }
   }
   if (h->timer.create()) return fail(DRFE_ERR_CUDA);
   *out = h;
@@ -1511,9 +1518,13 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   const int ncell_total = n * h->hd.ncells;
   const size_t sums_smem = (size_t)(kSumsThreads / 16) * h->hd.npc * sizeof(float);
   const int sums_grid = (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads;
-  if (h->hd.depth16) DRFE_LAUNCH(k_cape_sums<2>, sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n);
-  else if (h->hd.depth) DRFE_LAUNCH(k_cape_sums<1>, sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n);
-  else DRFE_LAUNCH(k_cape_sums<0>, sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n);
+  const int mode = h->hd.depth16 ? 2 : (h->hd.depth ? 1 : 0);
+  const int cell = (h->hd.cw == h->hd.ch && (h->hd.cw == 20 || h->hd.cw == 10)) ? h->hd.cw : 0;
+#define DRFE_SUMS(M, C) DRFE_LAUNCH((k_cape_sums<M, C>), sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n)
+#define DRFE_SUMS_MODE(C) do { if (mode == 2) DRFE_SUMS(2, C); else if (mode == 1) DRFE_SUMS(1, C); else DRFE_SUMS(0, C); } while (0)
+  if (cell == 20) DRFE_SUMS_MODE(20); else if (cell == 10) DRFE_SUMS_MODE(10); else DRFE_SUMS_MODE(0);
+#undef DRFE_SUMS_MODE
+#undef DRFE_SUMS
   if (timed) h->timer.mark("cells", st);
   DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
   if (timed) h->timer.mark("fit", st);
