@@ -964,10 +964,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 static const int kDescWarps = 8;
 static const int kPatchRows = 2 * kEdge + 1, kPatchW4 = 11;   // 39 rows x 44 bytes (39 columns + alignment slack)
 __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp, int f0) {
-  // rBRIEF pattern in shared memory, one word (x0,y0,x1,y1 as int8) per test, laid out so
-  // that lane j's t-th test sits at word t*32 + j (conflict-free); constant memory would
+  // rBRIEF pattern in shared memory as floats (x0,y0,x1,y1) per test, laid out so that lane j's
+  // t-th test sits at entry t*32 + j (conflict-free 16-byte loads); constant memory would
   // serialise the lane-divergent index
-  __shared__ uint32_t s_pat[256];
+  __shared__ float4 s_pat[256];
   __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchW4];
   const OrbDev& P = *Pp;
   const int level = blockIdx.y, f = blockIdx.z + f0;
@@ -983,7 +983,9 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   if ((int)blockIdx.x * kDescWarps >= nk) return;           // whole CTA idle
   {
     const int t = threadIdx.x;                                // test index = 8*byte + bit
-    s_pat[(t & 7) * 32 + (t >> 3)] = reinterpret_cast<const uint32_t*>(c_pattern)[t];
+    const uint32_t pw = reinterpret_cast<const uint32_t*>(c_pattern)[t];
+    s_pat[(t & 7) * 32 + (t >> 3)] = make_float4((float)(int8_t)(pw & 0xFF), (float)(int8_t)((pw >> 8) & 0xFF),
+                                                 (float)(int8_t)((pw >> 16) & 0xFF), (float)(int8_t)(pw >> 24));
   }
   __syncthreads();
   const int i = blockIdx.x * kDescWarps + wid;
@@ -1021,8 +1023,10 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   if (lane == 0) {
     angle = fast_atan2_deg((float)m01, (float)m10);
     const float rad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-    a = (float)cos((double)rad);   // correctly rounded cosf/sinf
-    b = (float)sin((double)rad);
+    double sd, cd;
+    sincos((double)rad, &sd, &cd);   // correctly rounded cosf/sinf: double result rounded to float
+    a = (float)cd;
+    b = (float)sd;
   }
   angle = __shfl_sync(0xFFFFFFFFu, angle, 0);
   a = __shfl_sync(0xFFFFFFFFu, a, 0);
@@ -1048,9 +1052,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   int val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint32_t pw = s_pat[j * 32 + lane];
-    const float x0 = (float)(int8_t)(pw & 0xFF), y0 = (float)(int8_t)((pw >> 8) & 0xFF);
-    const float x1 = (float)(int8_t)((pw >> 16) & 0xFF), y1 = (float)(int8_t)(pw >> 24);
+    const float4 pw = s_pat[j * 32 + lane];
+    const float x0 = pw.x, y0 = pw.y, x1 = pw.z, y1 = pw.w;
     const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
