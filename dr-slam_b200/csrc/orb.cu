@@ -389,7 +389,8 @@ __device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ 
 
 // Necessary condition for "corner at threshold t" on the 4 pixels of a quad: every 9-pixel arc
 // of the ring contains two adjacent compass points (ring 0,4,8,12), so a corner needs an adjacent
-// compass pair both > v + t or both < v - t.  Returns 0 when none of the 4 pixels can be one.
+// compass pair both > v + t or both < v - t.  Returns bit 0 / bit 1: some pixel of the even (0, 2) / odd
+// (1, 3) pair can be one; 0 when none of the 4 pixels can.
 __device__ __forceinline__ uint32_t fast_compass_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t t2) {
   const uint32_t* pu = tile32 + ry * TP4 + 4 + g;            // level row y-3: bytes x-3..
   const uint32_t* pm = pu + 3 * TP4;                         // row y
@@ -398,7 +399,7 @@ __device__ __forceinline__ uint32_t fast_compass_quad(const uint32_t* __restrict
   const uint32_t q8 = __funnelshift_r(u0, u1, 24), q0 = __funnelshift_r(d0, d1, 24);   // (0,-3) and (0,+3): byte offset 3
   const uint32_t qv = __funnelshift_r(m0, m1, 24);                                     // centres
   const uint32_t q4 = __funnelshift_r(m1, m2, 16), q12 = m0;                           // (+3,0): offset 6, (-3,0): offset 0
-  uint32_t any = 0;
+  uint32_t flags = 0;
 #pragma unroll
   for (int par = 0; par < 2; ++par) {
     const uint32_t sel = par ? 0x4341u : 0x4240u;
@@ -407,9 +408,10 @@ __device__ __forceinline__ uint32_t fast_compass_quad(const uint32_t* __restrict
     const uint32_t mm = __vmaxu2(__vimax3_u16x2(__vminu2(r0, r4), __vminu2(r4, r8), __vminu2(r8, r12)), __vminu2(r12, r0));
     const uint32_t MM = __vminu2(__vimin3_u16x2(__vmaxu2(r0, r4), __vmaxu2(r4, r8), __vmaxu2(r8, r12)), __vmaxu2(r12, r0));
     const uint32_t hi = v + t2, lo = MM + t2;
-    any |= (mm - __vminu2(mm, hi)) | (v - __vminu2(v, lo));  // mm > v + t  or  v > MM + t
+    const uint32_t any = (mm - __vminu2(mm, hi)) | (v - __vminu2(v, lo));  // mm > v + t  or  v > MM + t
+    flags |= (any ? 1u : 0u) << par;
   }
-  return any;
+  return flags;
 }
 
 // ring offsets (dx,dy), k = 0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)
@@ -481,27 +483,32 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   // the whole score map starts at zero: pixels the compass test rules out are never written
   for (int i = tid; i < (nrows + 2) * TP4; i += THREADS) score32[i] = 0;
   mbar_wait(&s_bar, 0);                      // the strip's rows have landed
-  // 2a. compass test at iniThFAST for every quad; survivors are queued (warp-aggregated)
-  {
-    const uint32_t t2 = (uint32_t)P.ini_th * 0x00010001u;
+  // Work queue of quads: the compass test is a necessary condition, and every later stage (score, NMS) touches
+  // only queued quads.  (Queueing pixel pairs instead was measured slower: when one pair of a quad passes the other
+  // nearly always does, and two pair evaluations cost more than one quad evaluation.)
+  const uint32_t kini = (uint32_t)(P.ini_th - P.min_th) * 0x00010001u;   // e > kini <=> q >= iniThFAST
+  const int ncells_x = (iw + wCell - 1) / wCell;
+  const int list_cap = P.fast_list_cap;
+  // queue every pair of the tasks selected by `want` that passes the compass test at threshold t
+  auto build_queue = [&](uint32_t t2, auto want) {
     for (int task0 = tid - lane; task0 < ntask; task0 += THREADS) {
       const int task = task0 + lane;
-      bool pass = false;
+      uint32_t fl = 0;
       if (task < ntask) {
         const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-        pass = fast_compass_quad(tile32, TP4, ry, task - ry * quads, t2) != 0;
+        const int g = task - ry * quads;
+        if (want(g)) fl = fast_compass_quad(tile32, TP4, ry, g, t2);
       }
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, fl != 0);
       if (bal == 0) continue;
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_nq, __popc(bal));
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (pass) queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)task;
+      if (fl) queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)task;
     }
-  }
-  __syncthreads();
-  // 2b. full score for the queued quads only, all lanes busy
-  {
+  };
+  // scores of the queued quads -> score map, all lanes busy
+  auto eval_queue = [&]() {
     const int nq = s_nq;
     for (int qi = tid; qi < nq; qi += THREADS) {
       const int task = queue[qi];
@@ -512,19 +519,11 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
       score32[(ry + 1) * TP4 + g + 1] = packed;
     }
-  }
-  __syncthreads();
-  // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free
-  // on u16x2 pairs.
-  // Pass 0 keeps the maxima with q >= iniThFAST (what FAST(iniThFAST) returns) and marks their
-  // cells; only queued quads can hold such a pixel.  Pass 1 runs only if some cell of the strip
-  // got nothing: there FAST(minThFAST) is evaluated densely and its maxima are taken instead
-  // (ORBextractor.cc:812-816).
-  const int list_cap = P.fast_list_cap;
-  const uint32_t kini = (uint32_t)(P.ini_th - P.min_th) * 0x00010001u;   // e > kini <=> q >= iniThFAST
-  const int ncells_x = (iw + wCell - 1) / wCell;
-  // strict-maximum flags (bit k = pixel k) of quad (ry, g) with scores clipped at kth
-  auto nms_quad = [&](int ry, int g, uint32_t c0, uint32_t kth) -> uint32_t {
+  };
+  // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free on u16x2 pairs.
+  // strict-maximum flags of pixel pair `par` of quad (ry, g) with scores clipped at kth: bit 0 = pixel par,
+  // bit 1 = pixel par + 2
+  auto nms_pair = [&](int ry, int g, uint32_t c0, int par, uint32_t kth) -> uint32_t {
     const uint32_t* sp = score32 + (ry + 1) * TP4 + g + 1;
     const uint32_t u0 = sp[-TP4 - 1], u1 = sp[-TP4], u2 = sp[-TP4 + 1];
     const uint32_t m0 = sp[-1], m2 = sp[1];
@@ -534,22 +533,28 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     const uint32_t Lu = __funnelshift_r(u0, u1, 24), Ru = __funnelshift_r(u1, u2, 8);
     const uint32_t Lm = __funnelshift_r(m0, c0, 24), Rm = __funnelshift_r(c0, m2, 8);
     const uint32_t Ld = __funnelshift_r(d0, d1, 24), Rd = __funnelshift_r(d1, d2, 8);
-    uint32_t t[2];
-#pragma unroll
-    for (int par = 0; par < 2; ++par) {
-      const uint32_t sel = par ? 0x4341u : 0x4240u;
-      const uint32_t lmax = __vimax3_u16x2(__byte_perm(Lu, 0, sel), __byte_perm(Lm, 0, sel), __byte_perm(Ld, 0, sel)) & (par ? mk.y : mk.x);
-      const uint32_t rmax = __vimax3_u16x2(__byte_perm(Ru, 0, sel), __byte_perm(Rm, 0, sel), __byte_perm(Rd, 0, sel)) & (par ? mk.w : mk.z);
-      const uint32_t nb = __vimax3_u16x2(lmax, rmax, __vmaxu2(__byte_perm(u1, 0, sel), __byte_perm(d1, 0, sel)));
-      const uint32_t c = __byte_perm(c0, 0, sel);
-      // scores clipped at the pass threshold: cz > nz <=> c > threshold and c > nb
-      const uint32_t cz = c - __vminu2(c, kth), nz = nb - __vminu2(nb, kth);
-      t[par] = cz - __vminu2(cz, nz);                        // per half: > 0 <=> kept
-    }
-    return ((t[0] & 0xFFFFu) ? 1u : 0u) | ((t[1] & 0xFFFFu) ? 2u : 0u) | ((t[0] >> 16) ? 4u : 0u) | ((t[1] >> 16) ? 8u : 0u);
+    const uint32_t sel = par ? 0x4341u : 0x4240u;
+    const uint32_t lmax = __vimax3_u16x2(__byte_perm(Lu, 0, sel), __byte_perm(Lm, 0, sel), __byte_perm(Ld, 0, sel)) & (par ? mk.y : mk.x);
+    const uint32_t rmax = __vimax3_u16x2(__byte_perm(Ru, 0, sel), __byte_perm(Rm, 0, sel), __byte_perm(Rd, 0, sel)) & (par ? mk.w : mk.z);
+    const uint32_t nb = __vimax3_u16x2(lmax, rmax, __vmaxu2(__byte_perm(u1, 0, sel), __byte_perm(d1, 0, sel)));
+    const uint32_t c = __byte_perm(c0, 0, sel);
+    // scores clipped at the pass threshold: cz > nz <=> c > threshold and c > nb
+    const uint32_t cz = c - __vminu2(c, kth), nz = nb - __vminu2(nb, kth);
+    const uint32_t t = cz - __vminu2(cz, nz);                  // per half: > 0 <=> kept
+    return ((t & 0xFFFFu) ? 1u : 0u) | ((t >> 16) ? 2u : 0u);
   };
-  // pass 0: queued quads only
-  {
+  // keep pixel k of quad (ry, g): FAST(iniThFAST) maxima mark their cell, FAST(minThFAST) maxima are taken only
+  // in cells that have none (the fallback applies to the pixel's own cell, ORBextractor.cc:812-816)
+  auto keep = [&](int ry, int g, int k, uint32_t c0, bool fallback) {
+    const int x = 4 * g + k;
+    const int cell = (int)__umulhi((uint32_t)x, L.wcell_magic);
+    if (fallback) { if (s_ini[cell] != 0) return; }
+    else s_ini[cell] = 1;                                      // benign race: everybody writes 1
+    const int slot = atomicAdd(&s_n, 1);
+    if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
+    else atomicOr(P.status, 1);
+  };
+  auto nms_queue = [&](uint32_t kth, bool fallback) {
     const int nq = s_nq;
     for (int qi = tid; qi < nq; qi += THREADS) {
       const int task = queue[qi];
@@ -557,22 +562,23 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       const int g = task - ry * quads;
       const uint32_t c0 = score32[(ry + 1) * TP4 + g + 1];
       if (c0 == 0) continue;
-      uint32_t surv = nms_quad(ry, g, c0, kini);
-      if (surv == 0) continue;
-      int slot = atomicAdd(&s_n, __popc(surv));
-      while (surv) {
-        const int k = __ffs(surv) - 1;
-        surv &= surv - 1;
-        const int x = 4 * g + k;
-        s_ini[__umulhi((uint32_t)x, L.wcell_magic)] = 1;       // benign race: everybody writes 1
-        if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
-        else atomicOr(P.status, 1);
-        ++slot;
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const uint32_t surv = nms_pair(ry, g, c0, par, kth);
+        if (surv & 1u) keep(ry, g, par, c0, fallback);
+        if (surv & 2u) keep(ry, g, par + 2, c0, fallback);
       }
     }
-  }
+  };
+  auto all = [](int) { return true; };
+  // ---- pass 0: what FAST(iniThFAST) returns
+  build_queue((uint32_t)P.ini_th * 0x00010001u, all);
   __syncthreads();
-  // pass 1: cells where FAST(iniThFAST) found nothing
+  eval_queue();
+  __syncthreads();
+  nms_queue(kini, false);
+  __syncthreads();
+  // ---- pass 1: cells where FAST(iniThFAST) found nothing get the maxima of FAST(minThFAST)
   {
     int missing = 0;
     for (int c = tid; c < ncells_x; c += THREADS) missing |= (s_ini[c] == 0);
@@ -581,34 +587,13 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
         const int ca = (int)__umulhi((uint32_t)(4 * g), L.wcell_magic), cb = (int)__umulhi((uint32_t)min(4 * g + 3, iw - 1), L.wcell_magic);
         return s_ini[ca] == 0 || s_ini[cb] == 0;
       };
-      // FAST(minThFAST) on those cells: dense scores for every quad touching one of them
-      for (int task = tid; task < ntask; task += THREADS) {
-        const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-        const int g = task - ry * quads;
-        if (!needs(g)) continue;
-        uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin);
-        const int rem = iw - 4 * g;
-        if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
-        score32[(ry + 1) * TP4 + g + 1] = packed;
-      }
+      if (tid == 0) s_nq = 0;
       __syncthreads();
-      for (int task = tid; task < ntask; task += THREADS) {
-        const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-        const int g = task - ry * quads;
-        if (!needs(g)) continue;
-        const uint32_t c0 = score32[(ry + 1) * TP4 + g + 1];
-        if (c0 == 0) continue;
-        uint32_t surv = nms_quad(ry, g, c0, 0u);
-        while (surv) {
-          const int k = __ffs(surv) - 1;
-          surv &= surv - 1;
-          const int x = 4 * g + k;
-          if (s_ini[__umulhi((uint32_t)x, L.wcell_magic)] != 0) continue;   // the fallback applies to the pixel's own cell only
-          const int slot = atomicAdd(&s_n, 1);
-          if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
-          else atomicOr(P.status, 1);
-        }
-      }
+      build_queue((uint32_t)P.min_th * 0x00010001u, needs);
+      __syncthreads();
+      eval_queue();
+      __syncthreads();
+      nms_queue(0u, true);
     }
   }
   __syncthreads();
