@@ -1188,7 +1188,9 @@ static int orb_build(drfe_orb* h) {
     if (L.nIni < 1 || L.nIni > 4) { set_error("unsupported aspect ratio (quadtree roots = %d)", L.nIni); return DRFE_ERR_ARG; }
     L.hX = width / L.nIni;
     for (int i = 0; i <= L.nIni; ++i) L.root_x[i] = (int)(L.hX * (float)i);
-    L.cand_cap = std::min(1 << 16, std::max(1024, (L.regW * L.regH) / 24));
+    // FAST candidates a level can hold: one per 8 px.  (Measured on the synthetic sequences: at most one per 67 px
+    // on level 0 but one per 20 px on level 7 — the density grows as the level shrinks; NMS bounds it by one per 4.)
+    L.cand_cap = std::min(1 << 17, std::max(1024, (L.regW * L.regH) / 8));
     L.cand_off = cand_total; cand_total += L.cand_cap;
     L.node_cap = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
     if (L.node_cap > 0x3FFF) { set_error("nfeatures too large"); return DRFE_ERR_ARG; }

@@ -110,3 +110,24 @@ def test_pipelined_batch_calls_match_enqueue_download(drfe):
     assert np.array_equal(seg2, rseg) and np.array_equal(npl2, rnp)
     with pytest.raises(drfe.DrfeError):
         orb.finish_batch()          # nothing in flight
+
+
+def test_later_shards_of_the_sequence(drfe, orc):
+    """the frames ranks 1..7 of the 8-GPU run get (sequence indices 256..2047): device capacities hold (candidate
+    density grows on the small levels) and spot-checked frames match the oracle"""
+    idx = list(range(256, 2048, 28))
+    data = [drfe.synth_frame(640, 480, (i // 64) % 3, 20260000 + i) for i in idx]
+    gray = np.stack([d[0] for d in data]); depth = np.stack([d[1] for d in data]); K = data[0][2]
+    n = len(idx)
+    orb = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=n)
+    cape = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0, max_batch=n)
+    orb.enqueue(gray); cape.enqueue_depth(depth, *K)
+    kps, desc, cnt = orb.download()
+    seg, planes, npl = cape.download()
+    assert cnt.min() >= 1000 and npl.min() >= 1
+    oo, oc = orc.OrbOracle(1000), orc.CapeOracle(480, 640, 20, 20, False, MC, 50.0)
+    for f in range(0, n, 9):
+        rk, rd = oo.extract(gray[f])
+        assert cnt[f] == len(rk) and kps[f, :cnt[f]].tobytes() == rk.tobytes() and np.array_equal(desc[f, :cnt[f]], rd)
+        oseg, opl = oc.process(oc.depth_to_cloud(depth[f], *K))
+        assert np.array_equal(seg[f], oseg) and npl[f] == len(opl)
