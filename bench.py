@@ -39,9 +39,19 @@ sys.path.insert(0, ROOT)
 
 W, H, NFEAT, BATCH = 640, 480, 1000, 256
 CELL, MAX_MERGE = 20, 50.0
+CYL, UNIT, SCENES = False, 1.0, (0, 1, 2)      # cylinder detection, depth unit scale (1 = metres), scene cycle
 MIN_COS = float(np.float32(np.cos(np.pi / 12)))
 METRIC = "front-end frames/sec (640x480 RGB-D, ORB 1000 kp + CAPE)"
 WORKLOAD = "batched 256-frame synthetic TUM/ICL-shaped RGB-D sequence, ORB 1000 kp + CAPE (20-px cells, cylinders off)"
+
+
+def select_workload(name):
+    """c640 (default) = BASELINE.json configs[2]/[3]; c720 = configs[4], the high-res stress case."""
+    global W, H, NFEAT, BATCH, CYL, UNIT, SCENES, WORKLOAD
+    if name == "c720":
+        W, H, NFEAT, BATCH, CYL, UNIT, SCENES = 1280, 720, 2000, 64, True, 1000.0, (2,)
+        WORKLOAD = ("high-res stress: batched 64-frame synthetic 1280x720 RGB-D room-with-pillars sequence (depth in mm), "
+                    "ORB 2000 kp, 8 levels + CAPE (20-px cells) with cylinder detection on")
 
 
 # ---------------------------------------------------------------- byte model (SURVEY §8d)
@@ -67,7 +77,7 @@ def algorithmic_bytes():
         "blur": 2 * P,                          # blur read + write
         "orient_describe": 749 * N + 512 * N + 60 * N,
         "cells": 4 * WH + 12 * WH + 12 * WH,    # depth read, cloud write, PlaneSeg read (fused in one kernel)
-        "fit": 768 * (48 + 156),                # per-cell sums in, PlaneSeg + tolerance out
+        "fit": (W // CELL) * (H // CELL) * (48 + 156),   # per-cell sums in, PlaneSeg + tolerance out
         "grid": 0,
         "refine": WH,                           # seg_output write (border-cell re-reads are data dependent)
         "total": WH + P + P_src + P + 2 * P + 1321 * N + 29 * WH,
@@ -88,7 +98,7 @@ def measured_peak():
 def make_sequence(drfe, first, count, threads):
     """frames first..first+count-1 of the synthetic sequence: seed = 20260000 + index, scene by block."""
     def one(i):
-        return drfe.synth_frame(W, H, (i // 64) % 3, 20260000 + i, 1.0)
+        return drfe.synth_frame(W, H, SCENES[(i // 64) % len(SCENES)], 20260000 + i, UNIT)
     with ThreadPoolExecutor(max_workers=threads) as ex:
         data = list(ex.map(one, range(first, first + count)))
     return np.stack([d[0] for d in data]), np.stack([d[1] for d in data]), data[0][2]
@@ -144,7 +154,7 @@ def cpu_port_fps(gray, depth, K, nframes, threads):
     def one(i):
         if not hasattr(tl, "o"):
             tl.o = orc.OrbOracle(NFEAT, 1.2, 8, 20, 7)
-            tl.c = orc.CapeOracle(H, W, CELL, CELL, False, MIN_COS, MAX_MERGE)
+            tl.c = orc.CapeOracle(H, W, CELL, CELL, CYL, MIN_COS, MAX_MERGE)
         tl.o.run(gray[i])
         cloud = tl.c.depth_to_cloud(depth[i], *K)
         tl.c.process(cloud)
@@ -197,7 +207,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--workload", default="c640", choices=["c640", "c720"],
+                    help="c640: the headline 640x480 / 1000 kp batch (default); c720: 1280x720 / 2000 kp / cylinders on")
     args = ap.parse_args()
+    select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -221,7 +234,7 @@ def main():
     first, last = shard.weak_block(BATCH, rank)                  # this rank's own frames, no data-path collective
     gray, depth, K = make_sequence(drfe, first, last - first, threads)
     orb = drfe.ORBextractor(NFEAT, 1.2, 8, 20, 7, W, H, max_batch=BATCH, device=local_rank)
-    cape = drfe.CAPE(H, W, CELL, CELL, False, MIN_COS, MAX_MERGE, max_batch=BATCH, device=local_rank)
+    cape = drfe.CAPE(H, W, CELL, CELL, CYL, MIN_COS, MAX_MERGE, max_batch=BATCH, device=local_rank)
     s_orb, s_cape = orb.stream(), cape.stream()
 
     # device-resident inputs (torch tensors are plain device memory here)
@@ -309,8 +322,11 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     e2e_value = time_e2e(h_depth, 1.0)
     # the same with the sensor's raw 16-bit depth (TUM png, factor 1/5000) converted on the device (Frame.cc:113-115)
-    fac = np.float32(1.0 / 5000.0)
-    q16 = np.rint(depth * 5000).astype(np.uint16)
+    fac = np.float32(np.float32(1.0 / 5000.0) * np.float32(UNIT))
+    q16 = np.rint(depth / np.float32(UNIT) * 5000).astype(np.uint16)
+    if UNIT != 1.0:     # the generator scales metres by UNIT after quantising; one factor reproduces it only approximately
+        depth = q16.astype(np.float32) * fac
+        h_depth[...] = depth
     assert np.array_equal(q16.astype(np.float32) * fac, depth)
     h_depth16 = pin(q16)
     e2e_u16 = time_e2e(h_depth16, float(fac))
@@ -356,7 +372,8 @@ def main():
         "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": BATCH, "width": W, "height": H,
                    "nfeatures": NFEAT, "nlevels": 8, "scale_factor": 1.2, "fast": [20, 7], "cape_cell": CELL,
-                   "l2": "inputs larger than L2 (393 MB of gray+depth per step per GPU, no flush needed)",
+                   "cylinder_detection": CYL,
+                   "l2": "inputs larger than L2 (%d MB of gray+depth per step per GPU, no flush needed)" % (BATCH * W * H * 5 // 1000000),
                    "sharding": "independent 256-frame batches per GPU, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "drfe_orb_extract_batch + drfe_cape_process_depth_batch (float depth, pinned host "
