@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "drfe_internal.h"
@@ -447,7 +448,9 @@ struct CylCtx {
 };
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
 
-__device__ __noinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_plane& seedcell, int& rpos, int& nsub) {
+// (forced inline: a real call inside k_cape_grid slows the whole kernel — measured 3.4x on the seed loop —
+// presumably because the shared-memory pointers then travel as generic addresses through the ABI)
+__device__ __forceinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_plane& seedcell, int& rpos, int& nsub) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, nc = X.nc;
   const double thr = 0.0225;                                 // cylinder_RANSAC_sqr_max_dist (Params.h:9)
@@ -505,12 +508,23 @@ __device__ __noinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_p
     int max_inl = 0;
     for (int q = lane; q < m; q += 32) X.flag[q] &= 1;
     __syncwarp();
-    for (int k = 0; (float)k < K; ++k) {
-      if (rpos + 3 > X.rand_n) { if (lane == 0) atomicOr(X.status, 8); return; }
-      const int id1 = X.ids_left[(int)(X.rand_tab[rpos] % (unsigned)m_left)];
-      const int id2 = X.ids_left[(int)(X.rand_tab[rpos + 1] % (unsigned)m_left)];
-      const int id3 = X.ids_left[(int)(X.rand_tab[rpos + 2] % (unsigned)m_left)];
-      rpos += 3;
+    // The K hypotheses of a run are independent up to the accept / early-break logic and their rand() draws
+    // are known in advance (hypothesis k uses draws 3k .. 3k+2), so 32 of them are evaluated at once, one per
+    // lane: every lane walks the remaining cells in ascending order and accumulates ITS hypothesis's MSAC sum in
+    // the reference's order (:137-148; all lanes read the same cell at the same time, the loads broadcast).
+    // The accept test is then replayed over the lanes in k order; hypotheses after an early break were
+    // speculative and their draws are not consumed.
+    double best_r = 0.0, best_c[3] = {0.0, 0.0, 0.0};
+    bool found = false, stop = false;
+    int k = 0;
+    while (!stop && (float)k < K) {
+      int nh = 0;
+      while (nh < 32 && (float)(k + nh) < K) ++nh;
+      if (rpos + 3 * nh > X.rand_n) { if (lane == 0) atomicOr(X.status, 8); return; }
+      const int lk = lane < nh ? lane : 0;                    // idle lanes shadow hypothesis 0
+      const int id1 = X.ids_left[(int)(X.rand_tab[rpos + 3 * lk] % (unsigned)m_left)];
+      const int id2 = X.ids_left[(int)(X.rand_tab[rpos + 3 * lk + 1] % (unsigned)m_left)];
+      const int id3 = X.ids_left[(int)(X.rand_tab[rpos + 3 * lk + 2] % (unsigned)m_left)];
       double e1[3], e2[3], t[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -527,39 +541,44 @@ __device__ __noinline__ void cyl_job(const CylCtx& X, int j, int m, const drfe_p
 #pragma unroll
       for (int c = 0; c < 3; ++c) center[c] = (e2[c] - r * e1[c]) / 3.0;
       const double rr = r * r;
-      for (int tq = lane; tq < m_left; tq += 32) {
+      double dist = 0.0;
+      int inl = 0;
+      for (int tq = 0; tq < m_left; ++tq) {
         const int i = X.ids_left[tq];
         const double x = (X.sP[i] - r * X.sN[i]) - center[0], y = (X.sP[nc + i] - r * X.sN[nc + i]) - center[1],
                      z = (X.sP[2 * nc + i] - r * X.sN[2 * nc + i]) - center[2];
         const double d = ((x * x + y * y) + z * z) / rr;
-        X.D[i] = d;
-        X.flag[i] = (unsigned char)((X.flag[i] & 5) | ((d < thr) ? 2 : 0));
+        if (d < thr) { ++inl; dist += d; }
+        else dist += thr;
       }
-      __syncwarp();
-      // MSAC truncated distance, ascending cell order (:137-148)
-      double dist = 0.0;
-      int inl = 0;
-      if (lane == 0) {
-        for (int tq = 0; tq < m_left; ++tq) {
-          const int i = X.ids_left[tq];
-          if (X.flag[i] & 2) { ++inl; dist += X.D[i]; }
-          else dist += thr;
+      int used = nh;
+      for (int j = 0; j < nh; ++j) {
+        const double dj = __shfl_sync(FULL, dist, j);
+        if (dj < min_hyp) {
+          min_hyp = dj;
+          max_inl = __shfl_sync(FULL, inl, j);
+          best_r = __shfl_sync(FULL, r, j);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) best_c[c] = __shfl_sync(FULL, center[c], j);
+          found = true;
+          if (max_inl > accepted) { used = j + 1; stop = true; break; }
         }
       }
-      dist = __shfl_sync(FULL, dist, 0);
-      inl = __shfl_sync(FULL, inl, 0);
-      if (dist < min_hyp) {
-        min_hyp = dist;
-        max_inl = inl;
-        for (int q = lane; q < m; q += 32) {
-          const unsigned char f = X.flag[q];
-          X.flag[q] = (unsigned char)((f & 3) | (((f & 3) == 3) ? 4 : 0));
-        }
-        __syncwarp();
-        if (inl > accepted) break;
-      }
-      __syncwarp();
+      rpos += 3 * used;
+      k += used;
     }
+    if (found) {
+      // I_final of the accepted hypothesis (:150-156): the same distances, recomputed
+      const double rr = best_r * best_r;
+      for (int tq = lane; tq < m_left; tq += 32) {
+        const int i = X.ids_left[tq];
+        const double x = (X.sP[i] - best_r * X.sN[i]) - best_c[0], y = (X.sP[nc + i] - best_r * X.sN[nc + i]) - best_c[1],
+                     z = (X.sP[2 * nc + i] - best_r * X.sN[2 * nc + i]) - best_c[2];
+        const double d = ((x * x + y * y) + z * z) / rr;
+        if (d < thr) X.flag[i] |= 4;
+      }
+    }
+    __syncwarp();
     if (max_inl < 6) break;                                   // Checkpoint 2 (:160)
     K = X.K2;
     // inlier list; remove the inliers from the remaining cells (:167-176)
@@ -788,6 +807,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     const uint32_t r_fl = (one_word && lane < nw) ? FL[lane] : 0u, r_fr = (one_word && lane < nw) ? FR[lane] : 0u,
                    r_fu = (one_word && lane < nw) ? FU[lane] : 0u, r_fd = (one_word && lane < nw) ? FD[lane] : 0u;
     for (int guard = 0; remaining > 0 && guard <= nc; ++guard) {
+      __syncwarp();   // the loop body is warp-collective throughout: start every iteration converged
       // most frequent bin, first maximum wins (Histogram.cpp:49-55)
       unsigned best = 0;
       for (int b = lane; b < kHistBins * kHistBins; b += 32) {
@@ -1462,7 +1482,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
     const size_t mj = nc / 4 + 1;
     const size_t base = (size_t)BV_COUNT * nw * 4 + kHistBins * kHistBins * 4 + 256 * 8 * 4 + nc * (4 + 4 + 4 + 2 + 2 + 1) + mj * 3 + 2 +
                         mj * 2 + (D.cyl ? (mj + 1) * 2 + nc * (1 + 8 + 4) + 16 : 0) + 64;
-    D.grid_sums_smem = (base + nc * 36 <= 160 * 1024) ? 1 : 0;
+    D.grid_sums_smem = (base + nc * 36 <= 200 * 1024) ? 1 : 0;
     h->grid_smem = base + (D.grid_sums_smem ? nc * 36 : 0);
     if (h->grid_smem > 200 * 1024 || nw > 4 * 128) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
   }

@@ -28,11 +28,14 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--nfeatures", type=int, default=1000)
+    ap.add_argument("--cyl", type=int, default=0, help="cylinder detection on")
+    ap.add_argument("--unit", type=float, default=1.0, help="depth unit scale (1000 = millimetres)")
+    ap.add_argument("--scene", type=int, default=-1, help="fixed scene (default: cycle 0,1,2)")
     a = ap.parse_args()
     import torch
     B, W, H = a.frames, a.width, a.height
     uniq = min(B, 32)
-    data = [drfe.synth_frame(W, H, (i // 8) % 3, 20260000 + i, 1.0) for i in range(uniq)]
+    data = [drfe.synth_frame(W, H, a.scene if a.scene >= 0 else (i // 8) % 3, 20260000 + i, a.unit) for i in range(uniq)]
     gray = np.stack([data[i % uniq][0] for i in range(B)])
     depth = np.stack([data[i % uniq][1] for i in range(B)])
     K = data[0][2]
@@ -51,7 +54,7 @@ def main():
         res.update(dict(orb.stage_times()))
         print("keypoints/frame: mean %.1f" % orb.download()[2].mean())
     if a.only in ("", "cape"):
-        cape = drfe.CAPE(H, W, 20, 20, False, bench.MIN_COS, 50.0, max_batch=B)
+        cape = drfe.CAPE(H, W, 20, 20, bool(a.cyl), bench.MIN_COS, 50.0, max_batch=B)
         for _ in range(2):
             cape.enqueue_depth(d_depth.data_ptr(), *K, mem_kind=drfe.MEM_DEVICE, nframes=B, row_stride=W, frame_stride=W * H)
         cape.sync()
