@@ -183,7 +183,7 @@ __device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, 
 // correctly rounded quotient q, so float(q') == float(q) unless a float rounding midpoint
 // (double mantissa bits 28..0 == 0x10000000) lies within a few ulps of q', or the result is
 // outside the float normal range — those rare cases take the exact division.
-__device__ __noinline__ void div_exact_to_float2(double tx, double ty, double fx, double fy, float& x, float& y) {
+__device__ __forceinline__ void div_exact_to_float2(double tx, double ty, double fx, double fy, float& x, float& y) {
   x = (float)(tx / fx);
   y = (float)(ty / fy);
 }
