@@ -1063,6 +1063,99 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   }
 }
 
+
+// ------------------------------------------------------------------ per-frame steps after extraction
+// Frame::UndistortKeyPoints (Frame.cc:835-861; cv::undistortPoints with R = I, P = K: five fixed-point
+// iterations in double), ComputeStereoFromRGBD (:893-911) and AssignFeaturesToGrid (:224-237) on the keypoints
+// the batch just produced.  One CTA per frame; the grid lists come out in the reference's order (cells x-major,
+// ascending keypoint index inside a cell) through a count / scan / rank pass over shared memory.
+static const int kGridCells = DRFE_FRAME_GRID_COLS * DRFE_FRAME_GRID_ROWS;
+struct PostDev {
+  drfe_frame_params prm;
+  const float* depth; long long depth_rs, depth_fs;
+  drfe_keypoint* keys_un; float* u_right; float* kp_depth;   // [B][kp_cap]
+  uint16_t* grid_count;                                         // [B][kGridCells]
+  uint16_t* grid_index;                                         // [B][kp_cap]
+};
+
+__device__ __forceinline__ void undistort_point(const drfe_frame_params& p, float u, float v, float& ou, float& ov) {
+  const double fx = p.fx, fy = p.fy, cx = p.cx, cy = p.cy;
+  const double k1 = p.dist[0], k2 = p.dist[1], p1 = p.dist[2], p2 = p.dist[3], k3 = p.dist[4];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double x = ((double)u - cx) * ifx, y = ((double)v - cy) * ify;
+  const double x0 = x, y0 = y;
+#pragma unroll 1
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+    const double dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+    const double dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  ou = (float)(fx * x + cx);
+  ov = (float)(fy * y + cy);
+}
+
+__global__ void __launch_bounds__(256) k_frame_post(const OrbDev* __restrict__ Pp, PostDev Q) {
+  __shared__ __align__(4) unsigned short s_cnt[kGridCells];     // keypoints per cell, then exclusive offsets
+  extern __shared__ unsigned short s_cell[];       // [kp_cap] cell of each keypoint (0xFFFF: outside the grid)
+  __shared__ int s_warp[8];
+  const OrbDev& P = *Pp;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int n = min(P.out_cnt[f], P.kp_cap);
+  const drfe_frame_params& prm = Q.prm;
+  for (int c = tid; c < kGridCells; c += 256) s_cnt[c] = 0;
+  __syncthreads();
+  const float inv_w = __fdiv_rn((float)DRFE_FRAME_GRID_COLS, __fsub_rn(prm.max_x, prm.min_x));
+  const float inv_h = __fdiv_rn((float)DRFE_FRAME_GRID_ROWS, __fsub_rn(prm.max_y, prm.min_y));
+  const long long o = (long long)f * P.kp_cap;
+  const float* depth = Q.depth + (long long)f * Q.depth_fs;
+  for (int i = tid; i < n; i += 256) {
+    const drfe_keypoint k = P.out_kp[o + i];
+    drfe_keypoint ku = k;
+    if (prm.dist[0] != 0.0f) undistort_point(prm, k.x, k.y, ku.x, ku.y);
+    Q.keys_un[o + i] = ku;
+    const float d = depth[(long long)(int)k.y * Q.depth_rs + (int)k.x];      // imDepth.at<float>(v, u): floats truncate
+    Q.kp_depth[o + i] = d > 0 ? d : -1.f;
+    Q.u_right[o + i] = d > 0 ? __fsub_rn(ku.x, __fdiv_rn(prm.bf, d)) : -1.f;
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(ku.x, prm.min_x), inv_w));   // PosInGrid (:816-825)
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(ku.y, prm.min_y), inv_h));
+    unsigned short cell = 0xFFFF;
+    if (px >= 0 && px < DRFE_FRAME_GRID_COLS && py >= 0 && py < DRFE_FRAME_GRID_ROWS) {
+      cell = (unsigned short)(px * DRFE_FRAME_GRID_ROWS + py);
+      atomicAdd(reinterpret_cast<unsigned int*>(s_cnt) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);   // counts < 65536: halves never carry
+    }
+    s_cell[i] = cell;
+  }
+  __syncthreads();
+  uint16_t* gc = Q.grid_count + (long long)f * kGridCells;
+  // counts out, then exclusive scan of the 3072 counts: 12 cells per thread
+  int loc[12], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { loc[k] = s_cnt[tid * 12 + k]; gc[tid * 12 + k] = (uint16_t)loc[k]; sum += loc[k]; }
+  int inc = sum;
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  int base = inc - sum;
+  for (int w = 0; w < wid; ++w) base += s_warp[w];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { s_cnt[tid * 12 + k] = (unsigned short)base; base += loc[k]; }
+  __syncthreads();
+  // stable placement: rank of keypoint i inside its cell = number of earlier keypoints of the same cell
+  uint16_t* gi = Q.grid_index + o;
+  for (int i = tid; i < n; i += 256) {
+    const unsigned short cell = s_cell[i];
+    if (cell == 0xFFFF) continue;
+    int rank = 0;
+    for (int j = 0; j < i; ++j) rank += (s_cell[j] == cell);
+    gi[s_cnt[cell] + rank] = (uint16_t)i;
+  }
+}
+
 __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
   const OrbDev& P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1092,6 +1185,8 @@ struct drfe_orb {
   bool pending = false;
   StageTimer timer;
   ChunkPipe pipe;
+  PostDev post{};                // buffers of drfe_orb_frame_post, allocated on first use
+  float* d_post_depth = nullptr;
   int* batch_counts = nullptr;   // host destination of the running batch call
   int batch_cap = 0;
   std::vector<void*> allocs;
@@ -1618,6 +1713,81 @@ int drfe_orb_finish_batch(drfe_orb* h) {
       set_error("drfe_orb_finish_batch: frame %d has %d keypoints, cap_per_frame is %d", f, h->batch_counts[f], h->batch_cap);
       return DRFE_ERR_CAPACITY;
     }
+  return DRFE_OK;
+}
+
+
+// Frame::ComputeImageBounds (Frame.cc:863-891)
+int drfe_frame_image_bounds(drfe_frame_params* p, int width, int height) {
+  if (!p || width < 1 || height < 1) { set_error("drfe_frame_image_bounds: bad argument"); return DRFE_ERR_ARG; }
+  if (p->dist[0] != 0.0f) {
+    const float cu[4] = {0.f, (float)width, 0.f, (float)width}, cv[4] = {0.f, 0.f, (float)height, (float)height};
+    float x[4], y[4];
+    for (int i = 0; i < 4; ++i) {   // the same five iterations as undistort_point, on the host
+      const double fx = p->fx, fy = p->fy, cx = p->cx, cy = p->cy;
+      const double k1 = p->dist[0], k2 = p->dist[1], p1 = p->dist[2], p2 = p->dist[3], k3 = p->dist[4];
+      const double ifx = 1. / fx, ify = 1. / fy;
+      double xx = ((double)cu[i] - cx) * ifx, yy = ((double)cv[i] - cy) * ify;
+      const double x0 = xx, y0 = yy;
+      for (int j = 0; j < 5; ++j) {
+        const double r2 = xx * xx + yy * yy;
+        const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+        const double dx = 2 * p1 * xx * yy + p2 * (r2 + 2 * xx * xx);
+        const double dy = p1 * (r2 + 2 * yy * yy) + 2 * p2 * xx * yy;
+        xx = (x0 - dx) * icdist;
+        yy = (y0 - dy) * icdist;
+      }
+      x[i] = (float)(fx * xx + cx); y[i] = (float)(fy * yy + cy);
+    }
+    p->min_x = std::min(x[0], x[2]); p->max_x = std::max(x[1], x[3]);
+    p->min_y = std::min(y[0], y[1]); p->max_y = std::max(y[2], y[3]);
+  } else {
+    p->min_x = 0.f; p->max_x = (float)width; p->min_y = 0.f; p->max_y = (float)height;
+  }
+  return DRFE_OK;
+}
+
+int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* depth, size_t row_stride, size_t frame_stride,
+                        int mem_kind, drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count,
+                        uint16_t* grid_index, int cap_per_frame) {
+  if (!h || !p || !depth) { set_error("drfe_orb_frame_post: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_orb_frame_post: nothing enqueued"); return DRFE_ERR_STATE; }
+  if (!(p->max_x > p->min_x) || !(p->max_y > p->min_y)) { set_error("drfe_orb_frame_post: image bounds not set (drfe_frame_image_bounds)"); return DRFE_ERR_ARG; }
+  if (row_stride < (size_t)h->width) { set_error("drfe_orb_frame_post: row_stride < width"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames, cap = h->hd.kp_cap, B = h->max_batch;
+  const size_t N = (size_t)h->width * h->height;
+  PostDev& Q = h->post;
+  if (!Q.keys_un) {
+    if (dev_alloc(h, &Q.keys_un, (size_t)cap * B) || dev_alloc(h, &Q.u_right, (size_t)cap * B) || dev_alloc(h, &Q.kp_depth, (size_t)cap * B) ||
+        dev_alloc(h, &Q.grid_count, (size_t)kGridCells * B) || dev_alloc(h, &Q.grid_index, (size_t)cap * B)) return DRFE_ERR_CUDA;
+    DRFE_CUDA(cudaFuncSetAttribute(k_frame_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * sizeof(unsigned short))));
+  }
+  Q.prm = *p;
+  if (mem_kind == DRFE_MEM_HOST) {
+    if (!h->d_post_depth && dev_alloc(h, &h->d_post_depth, N * B)) return DRFE_ERR_CUDA;
+    for (int f = 0; f < nf; ++f)
+      DRFE_CUDA(cudaMemcpy2DAsync(h->d_post_depth + f * N, h->width * sizeof(float), depth + f * frame_stride, row_stride * sizeof(float),
+                                  h->width * sizeof(float), h->height, cudaMemcpyHostToDevice, st));
+    Q.depth = h->d_post_depth; Q.depth_rs = h->width; Q.depth_fs = (long long)N;
+  } else if (mem_kind == DRFE_MEM_DEVICE) {
+    Q.depth = depth; Q.depth_rs = (long long)row_stride; Q.depth_fs = (long long)frame_stride;
+  } else { set_error("drfe_orb_frame_post: bad mem_kind"); return DRFE_ERR_ARG; }
+  DRFE_LAUNCH(k_frame_post, nf, 256, cap * sizeof(unsigned short), st, h->dd, Q);
+  const int wk = std::min(cap, cap_per_frame);
+  if (keys_un)
+    DRFE_CUDA(cudaMemcpy2DAsync(keys_un, (size_t)cap_per_frame * sizeof(drfe_keypoint), Q.keys_un, (size_t)cap * sizeof(drfe_keypoint),
+                                (size_t)wk * sizeof(drfe_keypoint), nf, cudaMemcpyDeviceToHost, st));
+  if (u_right)
+    DRFE_CUDA(cudaMemcpy2DAsync(u_right, (size_t)cap_per_frame * 4, Q.u_right, (size_t)cap * 4, (size_t)wk * 4, nf, cudaMemcpyDeviceToHost, st));
+  if (kp_depth)
+    DRFE_CUDA(cudaMemcpy2DAsync(kp_depth, (size_t)cap_per_frame * 4, Q.kp_depth, (size_t)cap * 4, (size_t)wk * 4, nf, cudaMemcpyDeviceToHost, st));
+  if (grid_count) DRFE_CUDA(cudaMemcpyAsync(grid_count, Q.grid_count, (size_t)kGridCells * nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+  if (grid_index)
+    DRFE_CUDA(cudaMemcpy2DAsync(grid_index, (size_t)cap_per_frame * 2, Q.grid_index, (size_t)cap * 2, (size_t)wk * 2, nf, cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }
 

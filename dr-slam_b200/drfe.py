@@ -44,6 +44,12 @@ class CapeParams(C.Structure):
                 ("min_cos_angle_4_merge", C.c_float), ("max_merge_dist", C.c_float)]
 
 
+class FrameParams(C.Structure):
+    """mK, mDistCoef, mbf and the image bounds of Frame (Frame.cc:863-891)"""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 5),
+                ("bf", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
 class DrfeError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("drfe error %d: %s" % (code, msg))
@@ -58,7 +64,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -104,6 +110,8 @@ def lib():
     L.drfe_orb_sync.argtypes = [vp]
     L.drfe_orb_extract_batch.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp, C.c_int, vp, C.c_int]
     L.drfe_orb_finish_batch.argtypes = [vp]
+    L.drfe_frame_image_bounds.argtypes = [vp, C.c_int, C.c_int]
+    L.drfe_orb_frame_post.argtypes = [vp, vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
     L.drfe_orb_level_size.argtypes = [vp, C.c_int, i32p, i32p]
@@ -307,6 +315,26 @@ class ORBextractor:
 
     def finish_batch(self):
         _check(self.L.drfe_orb_finish_batch(self.h))
+
+    def frame_params(self, fx, fy, cx, cy, dist, bf):
+        """mK / mDistCoef / mbf + Frame::ComputeImageBounds for this handle's image size"""
+        p = FrameParams(fx, fy, cx, cy, (C.c_float * 5)(*dist), bf, 0, 0, 0, 0)
+        _check(self.L.drfe_frame_image_bounds(C.byref(p), self.width, self.height))
+        return p
+
+    def frame_post(self, p, depth, mem_kind=MEM_HOST, row_stride=None, frame_stride=None):
+        """UndistortKeyPoints + ComputeStereoFromRGBD + AssignFeaturesToGrid on the last batch's keypoints:
+        (mvKeysUn, mvuRight, mvDepth, grid counts [nf, 64, 48], grid index lists [nf, cap])"""
+        nf = self._nframes
+        if isinstance(depth, np.ndarray):
+            assert depth.dtype == np.float32 and depth.ndim == 3 and depth.strides[2] == 4 and depth.shape[0] == nf
+            row_stride, frame_stride = depth.strides[1] // 4, depth.strides[0] // 4
+        ku = np.empty((nf, self.cap), KP_DTYPE)
+        ur, kd = np.empty((nf, self.cap), np.float32), np.empty((nf, self.cap), np.float32)
+        gc, gi = np.empty((nf, 64, 48), np.uint16), np.empty((nf, self.cap), np.uint16)
+        _check(self.L.drfe_orb_frame_post(self.h, C.byref(p), _ptr(depth), row_stride, frame_stride, mem_kind, _ptr(ku), _ptr(ur),
+                                          _ptr(kd), _ptr(gc), _ptr(gi), self.cap))
+        return ku, ur, kd, gc, gi
 
     def sync(self):
         _check(self.L.drfe_orb_sync(self.h))

@@ -154,6 +154,30 @@ int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t
                            int cap_per_frame, int* counts, int chunk_frames);
 int drfe_orb_finish_batch(drfe_orb* h);
 
+/* ------------------------------------------------------------------ per-frame steps after extraction
+ * ("next" row of SURVEY.md 8f): what Frame::Frame does with the keypoints right after ExtractORB —
+ * UndistortKeyPoints (Frame.cc:835-861), ComputeStereoFromRGBD (:893-911) and AssignFeaturesToGrid
+ * (:224-237, PosInGrid :816-825) — on the keypoints of the handle's last batch, which are already
+ * on the device. */
+#define DRFE_FRAME_GRID_COLS 64 /* FRAME_GRID_COLS / FRAME_GRID_ROWS of include/Frame.h */
+#define DRFE_FRAME_GRID_ROWS 48
+typedef struct drfe_frame_params {
+  float fx, fy, cx, cy;               /* mK */
+  float dist[5];                      /* mDistCoef: k1 k2 p1 p2 k3 (dist[0] == 0: keypoints are copied) */
+  float bf;                           /* mbf = baseline * fx */
+  float min_x, max_x, min_y, max_y;   /* mnMinX .. mnMaxY (drfe_frame_image_bounds) */
+} drfe_frame_params;
+/* Frame::ComputeImageBounds (Frame.cc:863-891): fills min_x .. max_y of *p from the other fields. */
+int drfe_frame_image_bounds(drfe_frame_params* p, int width, int height);
+/* depth: the float depth image(s) of the same frames (host or device).  Outputs on the host, any may
+ * be NULL: keys_un[f*cap + i] (mvKeysUn), u_right / kp_depth[f*cap + i] (mvuRight / mvDepth, -1 where
+ * the depth is not positive), grid_count[f*3072 + x*48 + y] = mGrid[x][y].size(), grid_index[f*cap ..]
+ * = the keypoint indices of all cells concatenated in x-major cell order, ascending inside a cell
+ * (what the push_back loop produces). */
+int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* depth, size_t row_stride,
+                        size_t frame_stride, int mem_kind, drfe_keypoint* keys_un, float* u_right,
+                        float* kp_depth, uint16_t* grid_count, uint16_t* grid_index, int cap_per_frame);
+
 /* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
  * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
  * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */

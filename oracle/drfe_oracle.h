@@ -31,6 +31,13 @@ float orc_fast_atan2(float y, float x);
 int orc_distribute_quadtree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N,
                             float* out_xyr, int cap, int* tie);
 
+/* per-frame steps after extraction: Frame::UndistortKeyPoints / ComputeImageBounds / ComputeStereoFromRGBD /
+ * AssignFeaturesToGrid (Frame.cc:835-911, 224-237); returns the number of keypoints placed in the grid */
+void orc_undistort_point(const drfe_frame_params* p, float u, float v, float* ou, float* ov);
+int orc_frame_image_bounds(drfe_frame_params* p, int width, int height);
+int orc_frame_post(const drfe_frame_params* p, const drfe_keypoint* keys, int n, const float* depth, int row_stride,
+                   drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count, uint16_t* grid_index);
+
 /* ---- CAPE (cape_oracle.cpp) ---- */
 void* orc_cape_create(int depth_height, int depth_width, int cell_width, int cell_height,
                       int cylinder_detection, float min_cos_angle_4_merge, float max_merge_dist);

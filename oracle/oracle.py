@@ -37,6 +37,11 @@ PLANE_DTYPE = np.dtype([("nr_pts", "<i4"), ("min_nr_pts", "<i4"),
                         ("xy_acc", "<f8"), ("xz_acc", "<f8"), ("yz_acc", "<f8"),
                         ("score", "<f4"), ("MSE", "<f4"), ("planar", "<i4"),
                         ("mean", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8")], align=True)
+class FrameParams(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 5),
+                ("bf", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
 CYL_DTYPE = np.dtype([("radius", "<f4"), ("center", "<f8", (3,)), ("axis", "<f8", (3,))], align=True)
 assert KP_DTYPE.itemsize == 28 and PLANE_DTYPE.itemsize == C.sizeof(Plane) and CYL_DTYPE.itemsize == 56
 
@@ -79,6 +84,10 @@ def lib():
         L.orc_fast_atan2.restype = C.c_float
         L.orc_distribute_quadtree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_void_p, C.c_int, i32p]
+        L.orc_undistort_point.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_frame_image_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_frame_post.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cape_create.restype = C.c_void_p
         L.orc_cape_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
         L.orc_cape_destroy.argtypes = [C.c_void_p]
@@ -202,6 +211,25 @@ def gaussian7(src):
     dst = np.empty_like(src)
     lib().orc_gaussian7_u8(_p(src), src.shape[1], src.shape[0], _p(dst))
     return dst
+
+
+def frame_params(fx, fy, cx, cy, dist, bf, width, height):
+    """mK / mDistCoef / mbf + Frame::ComputeImageBounds (Frame.cc:863-891)"""
+    p = FrameParams(fx, fy, cx, cy, (C.c_float * 5)(*dist), bf, 0, 0, 0, 0)
+    lib().orc_frame_image_bounds(C.byref(p), width, height)
+    return p
+
+
+def frame_post(p, keys, depth):
+    """UndistortKeyPoints + ComputeStereoFromRGBD + AssignFeaturesToGrid (Frame.cc:835-911, 224-237)"""
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    depth = np.ascontiguousarray(depth, np.float32)
+    n = len(keys)
+    ku = np.zeros(n, KP_DTYPE)
+    ur, kd = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    gc, gi = np.zeros(64 * 48, np.uint16), np.zeros(max(n, 1), np.uint16)
+    placed = lib().orc_frame_post(C.byref(p), _p(keys), n, _p(depth), depth.shape[1], _p(ku), _p(ur), _p(kd), _p(gc), _p(gi))
+    return ku, ur, kd, gc, gi[:placed].copy()
 
 
 def glibc_rand(seed, n):

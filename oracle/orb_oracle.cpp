@@ -656,4 +656,62 @@ int orc_distribute_quadtree(const float* xyr, int n, int minX, int maxX, int min
   return (int)r.size();
 }
 
+// ---- per-frame steps after extraction: UndistortKeyPoints (Frame.cc:835-861; the
+// arithmetic is cv::undistortPoints with R = I, P = K: 5 fixed-point iterations in double, OpenCV 3.4
+// undistort.cpp cvUndistortPointsInternal), ComputeStereoFromRGBD (:893-911), AssignFeaturesToGrid
+// (:224-237) with PosInGrid (:816-825).
+void orc_undistort_point(const drfe_frame_params* p, float u, float v, float* ou, float* ov) {
+  const double fx = p->fx, fy = p->fy, cx = p->cx, cy = p->cy;
+  const double k1 = p->dist[0], k2 = p->dist[1], p1 = p->dist[2], p2 = p->dist[3], k3 = p->dist[4];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double x = ((double)u - cx) * ifx, y = ((double)v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+    const double dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+    const double dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  // P = K, R = I: xx = fx*x + 0*y + cx, ww = 1 / (0*x + 0*y + 1)
+  const double xx = fx * x + cx, yy = fy * y + cy;
+  *ou = (float)xx; *ov = (float)yy;
+}
+int orc_frame_image_bounds(drfe_frame_params* p, int width, int height) {
+  if (p->dist[0] != 0.0f) {
+    float x[4], y[4];
+    const float cu[4] = {0.f, (float)width, 0.f, (float)width}, cv[4] = {0.f, 0.f, (float)height, (float)height};
+    for (int i = 0; i < 4; ++i) orc_undistort_point(p, cu[i], cv[i], &x[i], &y[i]);
+    p->min_x = std::min(x[0], x[2]); p->max_x = std::max(x[1], x[3]);
+    p->min_y = std::min(y[0], y[1]); p->max_y = std::max(y[2], y[3]);
+  } else {
+    p->min_x = 0.f; p->max_x = (float)width; p->min_y = 0.f; p->max_y = (float)height;
+  }
+  return 0;
+}
+int orc_frame_post(const drfe_frame_params* p, const drfe_keypoint* keys, int n, const float* depth, int row_stride,
+                   drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count, uint16_t* grid_index) {
+  const int GC = DRFE_FRAME_GRID_COLS, GR = DRFE_FRAME_GRID_ROWS;
+  const float inv_w = (float)GC / (float)(p->max_x - p->min_x), inv_h = (float)GR / (float)(p->max_y - p->min_y);
+  std::vector<std::vector<uint16_t>> grid(GC * GR);
+  for (int i = 0; i < n; ++i) {
+    drfe_keypoint ku = keys[i];
+    if (p->dist[0] != 0.0f) orc_undistort_point(p, keys[i].x, keys[i].y, &ku.x, &ku.y);
+    keys_un[i] = ku;
+    const float d = depth[(size_t)(int)keys[i].y * row_stride + (int)keys[i].x];   // imDepth.at<float>(v, u): floats truncate
+    u_right[i] = -1.f; kp_depth[i] = -1.f;
+    if (d > 0) { kp_depth[i] = d; u_right[i] = ku.x - p->bf / d; }
+    const int px = (int)roundf((ku.x - p->min_x) * inv_w), py = (int)roundf((ku.y - p->min_y) * inv_h);
+    if (px < 0 || px >= GC || py < 0 || py >= GR) continue;
+    grid[px * GR + py].push_back((uint16_t)i);
+  }
+  int o = 0;
+  for (int c = 0; c < GC * GR; ++c) {
+    grid_count[c] = (uint16_t)grid[c].size();
+    for (uint16_t i : grid[c]) grid_index[o++] = i;
+  }
+  return o;
+}
+
 }  // extern "C"
