@@ -1414,6 +1414,8 @@ static int orb_build(drfe_orb* h) {
   if (dev_alloc(h, &d_ptiles, ptiles.size())) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(d_ptiles, ptiles.data(), ptiles.size() * sizeof(PyrTile), cudaMemcpyHostToDevice));
   D.ptiles = d_ptiles;
+  // DRFE_PYR_GENERIC=1 forces the generic tile kernel (kept for scale factors the streaming kernel cannot take;
+  // the environment switch exists so that the tests can exercise it)
   if (stream_ok && !pcols.empty() && getenv("DRFE_PYR_GENERIC") == nullptr) {
     PyrCol* d_pcols; uint2* d_ytab2;
     if (dev_alloc(h, &d_pcols, pcols.size())) return DRFE_ERR_CUDA;
@@ -1530,9 +1532,8 @@ static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long 
     if (D.pcols) {
       // rows per thread: long strips amortise the two priming rows on the big levels; the small levels are
       // latency-bound (few warps), so they get short strips = more threads and shorter dependent chains
-      static const int r_env = getenv("DRFE_PYR_R") ? atoi(getenv("DRFE_PYR_R")) : 0;
       const long long px = (long long)L.w * L.h * n;
-      const int R = r_env > 0 ? r_env : (px >= (24 << 20) ? kPyrR : (px >= (8 << 20) ? 8 : 4));
+      const int R = px >= (24 << 20) ? kPyrR : (px >= (8 << 20) ? 8 : 4);
       const int strips = (L.h + R - 1) / R;
       DRFE_LAUNCH(k_pyr_stream, dim3((L.pcol_groups + 31) / 32, (strips + 3) / 4, n), dim3(32, 4), 0, st, h->dd, l, f0, R);
     } else {

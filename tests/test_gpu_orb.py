@@ -5,7 +5,7 @@ descriptors bit-identical on >= 99.5 % of keypoints, the rest within Hamming dis
 import numpy as np
 import pytest
 
-from conftest import KP_FIELDS, load_golden, sort_rows
+from conftest import KP_FIELDS, ROOT, load_golden, sort_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -165,3 +165,24 @@ def test_other_pyramid_settings(drfe, orc):
         rk, rd = check_frame_against_oracle(ex, o, gray, 0)
         check_result(kps, desc, rk, rd)
         ex.close()
+
+
+def test_generic_pyramid_kernel_still_matches(drfe):
+    """k_pyr_resize (the tile kernel kept as fallback for scale factors the streaming kernel cannot take) is forced
+    with DRFE_PYR_GENERIC=1 in a child process and must produce the golden pyramid bytes and keypoints too"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, zlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import drfe\n"
+        "g = np.load(%r)\n"
+        "ex = drfe.ORBextractor(int(g['nfeatures']), 1.2, 8, 20, 7, g['gray'].shape[1], g['gray'].shape[0])\n"
+        "kps, desc = ex(g['gray'])\n"
+        "assert all(np.uint32(zlib.crc32(ex.pyramid(0, l, bordered=True).tobytes())) == g['pyr_crc_%%d' %% l] for l in range(8))\n"
+        "assert kps.tobytes() == g['kps'].tobytes() and np.array_equal(desc, g['desc'])\n"
+        "print('generic ok')\n"
+    ) % (os.path.join(ROOT, "dr-slam_b200"), ROOT, os.path.join(ROOT, "tests", "golden", "orb_640x480_room.npz"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DRFE_PYR_GENERIC="1"), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "generic ok" in out.stdout, out.stderr[-2000:]
