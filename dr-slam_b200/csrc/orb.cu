@@ -49,6 +49,7 @@ struct LevelDev {
   uint32_t blur_magic;              // ceil(2^32 / blur_nq)
   uint32_t wcell_magic;             // ceil(2^32 / wCell): interior x -> cell column by __umulhi
   uint32_t quads_magic;             // ceil(2^32 / quads), quads = ceil((w-38)/4): task -> row by __umulhi
+  uint32_t groups_magic;            // ceil(2^32 / groups), groups = ceil(quads/4): 16-pixel group task -> row
   float hX;
   int root_x[5];                    // root boundaries int(hX*i), i = 0..nIni (nIni <= 4)
   int cand_cap;
@@ -387,29 +388,34 @@ __device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ 
   return ee | (eo << 8);                                   // bytes: pixel 0,1,2,3
 }
 
-// Necessary condition for "corner at threshold t" on the 4 pixels of a quad: every 9-pixel arc
-// of the ring contains two adjacent compass points (ring 0,4,8,12), so a corner needs an adjacent
-// compass pair both > v + t or both < v - t.  Returns bit 0 / bit 1: some pixel of the even (0, 2) / odd
-// (1, 3) pair can be one; 0 when none of the 4 pixels can.
-__device__ __forceinline__ uint32_t fast_compass_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t t2) {
-  const uint32_t* pu = tile32 + ry * TP4 + 4 + g;            // level row y-3: bytes x-3..
+// Necessary condition for "corner at threshold t" on the 4 pixels of a quad: every 9-pixel arc of the
+// ring contains two adjacent compass points (ring 0,4,8,12), and the adjacent compass pairs are exactly
+// {r0,r8} x {r4,r12}, so a corner needs (|r0-v| > t or |r8-v| > t) and (|r4-v| > t or |r12-v| > t).
+// (Dropping the "same sign" part of the condition lets 4 pixels go through one VABSDIFF4 per compass
+// point; on textured frames it passes 41.6 % of the quads instead of 39.5 %.)
+// One call tests the 4 quads 4G..4G+3 of interior row ry (16 pixels; their window starts at a 16-byte
+// boundary of the strip row): bit k of the result = quad 4G+k may hold a corner.
+// cadd = (127 - min(t,127)) * 0x01010101: a > t  <=>  bit 7 of (a | ((a & 0x7f) + 127 - t)).
+__device__ __forceinline__ uint32_t fast_compass_group(const uint32_t* __restrict__ tile32, int TP4, int ry, int G, uint32_t cadd) {
+  const uint32_t* pu = tile32 + ry * TP4 + 4 + 4 * G;        // level row y-3: bytes x-3.. of quad 4G
   const uint32_t* pm = pu + 3 * TP4;                         // row y
   const uint32_t* pd = pu + 6 * TP4;                         // row y+3
-  const uint32_t u0 = pu[0], u1 = pu[1], m0 = pm[0], m1 = pm[1], m2 = pm[2], d0 = pd[0], d1 = pd[1];
-  const uint32_t q8 = __funnelshift_r(u0, u1, 24), q0 = __funnelshift_r(d0, d1, 24);   // (0,-3) and (0,+3): byte offset 3
-  const uint32_t qv = __funnelshift_r(m0, m1, 24);                                     // centres
-  const uint32_t q4 = __funnelshift_r(m1, m2, 16), q12 = m0;                           // (+3,0): offset 6, (-3,0): offset 0
+  const uint4 ua = *reinterpret_cast<const uint4*>(pu), ma = *reinterpret_cast<const uint4*>(pm), da = *reinterpret_cast<const uint4*>(pd);
+  const uint2 mb = *reinterpret_cast<const uint2*>(pm + 4);
+  const uint32_t U[5] = {ua.x, ua.y, ua.z, ua.w, pu[4]}, D[5] = {da.x, da.y, da.z, da.w, pd[4]};
+  const uint32_t M[6] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y};
   uint32_t flags = 0;
 #pragma unroll
-  for (int par = 0; par < 2; ++par) {
-    const uint32_t sel = par ? 0x4341u : 0x4240u;
-    const uint32_t v = __byte_perm(qv, 0, sel), r0 = __byte_perm(q0, 0, sel), r4 = __byte_perm(q4, 0, sel),
-                   r8 = __byte_perm(q8, 0, sel), r12 = __byte_perm(q12, 0, sel);
-    const uint32_t mm = __vmaxu2(__vimax3_u16x2(__vminu2(r0, r4), __vminu2(r4, r8), __vminu2(r8, r12)), __vminu2(r12, r0));
-    const uint32_t MM = __vminu2(__vimin3_u16x2(__vmaxu2(r0, r4), __vmaxu2(r4, r8), __vmaxu2(r8, r12)), __vmaxu2(r12, r0));
-    const uint32_t hi = v + t2, lo = MM + t2;
-    const uint32_t any = (mm - __vminu2(mm, hi)) | (v - __vminu2(v, lo));  // mm > v + t  or  v > MM + t
-    flags |= (any ? 1u : 0u) << par;
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t v = __funnelshift_r(M[k], M[k + 1], 24);                              // centres: byte offset 3
+    const uint32_t a8 = __vabsdiffu4(__funnelshift_r(U[k], U[k + 1], 24), v);            // (0,-3)
+    const uint32_t a0 = __vabsdiffu4(__funnelshift_r(D[k], D[k + 1], 24), v);            // (0,+3)
+    const uint32_t a4 = __vabsdiffu4(__funnelshift_r(M[k + 1], M[k + 2], 16), v);        // (+3,0): offset 6
+    const uint32_t a12 = __vabsdiffu4(M[k], v);                                           // (-3,0): offset 0
+    const uint32_t h8 = (a8 & 0x7F7F7F7Fu) + cadd, h0 = (a0 & 0x7F7F7F7Fu) + cadd;
+    const uint32_t h4 = (a4 & 0x7F7F7F7Fu) + cadd, h12 = (a12 & 0x7F7F7F7Fu) + cadd;
+    const uint32_t vert = a8 | h8 | a0 | h0, horz = a4 | h4 | a12 | h12;
+    flags |= ((vert & horz & 0x80808080u) ? 1u : 0u) << k;
   }
   return flags;
 }
@@ -464,47 +470,65 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   const int wCell = L.wCell;
   const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
   uint32_t* score32 = reinterpret_cast<uint32_t*>(score);
-  // per-quad cell-boundary masks as u16x2 {left even, left odd, right even, right odd}: a pixel
-  // in the first (last) column of its cell has no left (right) neighbours
+  // per-quad cell-boundary masks, one u16 lane per pixel {left even, left odd, right even, right odd}:
+  // a pixel in the first (last) column of its cell has no left (right) neighbours
   for (int g = tid; g < quads; g += THREADS) {
     uint32_t ml = 0, mr = 0;
+    int xm = (4 * g) % wCell;                                 // x mod wCell, stepped
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int x = 4 * g + k;
-      if (x % wCell != 0) ml |= 0xFFu << (8 * k);
-      if ((x + 1) % wCell != 0) mr |= 0xFFu << (8 * k);
+      if (xm != 0) ml |= 1u << k;
+      if (++xm == wCell) xm = 0;
+      if (xm != 0) mr |= 1u << k;
     }
-    s_mask[g] = make_uint4(__byte_perm(ml, 0, 0x4240), __byte_perm(ml, 0, 0x4341), __byte_perm(mr, 0, 0x4240),
-                           __byte_perm(mr, 0, 0x4341));
+    auto lanes = [](uint32_t m, int lo, int hi) { return ((m >> lo) & 1u ? 0xFFFFu : 0u) | ((m >> hi) & 1u ? 0xFFFF0000u : 0u); };
+    s_mask[g] = make_uint4(lanes(ml, 0, 2), lanes(ml, 1, 3), lanes(mr, 0, 2), lanes(mr, 1, 3));
   }
   const uint32_t kmin = (uint32_t)(256 + P.min_th) * 0x00010001u;
-  const int ntask = nrows * quads;
   const int lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   // the whole score map starts at zero: pixels the compass test rules out are never written
-  for (int i = tid; i < (nrows + 2) * TP4; i += THREADS) score32[i] = 0;
+  {
+    uint4* s4 = reinterpret_cast<uint4*>(score32);
+    for (int i = tid; i < (nrows + 2) * (TP4 >> 2); i += THREADS) s4[i] = make_uint4(0, 0, 0, 0);
+  }
   mbar_wait(&s_bar, 0);                      // the strip's rows have landed
-  // Work queue of quads: the compass test is a necessary condition, and every later stage (score, NMS) touches
-  // only queued quads.  (Queueing pixel pairs instead was measured slower: when one pair of a quad passes the other
-  // nearly always does, and two pair evaluations cost more than one quad evaluation.)
-  const uint32_t kini = (uint32_t)(P.ini_th - P.min_th) * 0x00010001u;   // e > kini <=> q >= iniThFAST
+  // Work queue of quads (entries ry << 10 | g): the compass test is a necessary condition, and every later stage
+  // (score, NMS) touches only queued quads.  (Queueing pixel pairs instead was measured slower: when one pair of a
+  // quad passes the other nearly always does, and two pair evaluations cost more than one quad evaluation.)
+  const uint32_t kini = (uint32_t)(P.ini_th - P.min_th);                 // e > kini <=> q >= iniThFAST
   const int ncells_x = (iw + wCell - 1) / wCell;
   const int list_cap = P.fast_list_cap;
-  // queue every pair of the tasks selected by `want` that passes the compass test at threshold t
-  auto build_queue = [&](uint32_t t2, auto want) {
-    for (int task0 = tid - lane; task0 < ntask; task0 += THREADS) {
+  const int groups = (quads + 3) >> 2;                                    // 16-pixel groups per row
+  const int ngtask = nrows * groups;
+  // queue every quad of the rows/groups selected by `want` that passes the compass test at threshold t
+  auto build_queue = [&](int t, auto want) {
+    const uint32_t cadd = (uint32_t)(127 - min(t, 127)) * 0x01010101u;
+    for (int task0 = tid - lane; task0 < ngtask; task0 += THREADS) {
       const int task = task0 + lane;
       uint32_t fl = 0;
-      if (task < ntask) {
-        const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-        const int g = task - ry * quads;
-        if (want(g)) fl = fast_compass_quad(tile32, TP4, ry, g, t2);
+      int ry = 0, G = 0;
+      if (task < ngtask) {
+        ry = (int)__umulhi((uint32_t)task, L.groups_magic);
+        G = task - ry * groups;
+        fl = fast_compass_group(tile32, TP4, ry, G, cadd);
+        const int rem = quads - 4 * G;                          // quads of this group inside the row
+        if (rem < 4) fl &= (1u << rem) - 1u;
+        fl = want(G, fl);
       }
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, fl != 0);
-      if (bal == 0) continue;
+      const unsigned any = __ballot_sync(0xFFFFFFFFu, fl != 0);
+      if (any == 0) continue;
+      const unsigned b0 = __ballot_sync(0xFFFFFFFFu, fl & 1u), b1 = __ballot_sync(0xFFFFFFFFu, fl & 2u),
+                     b2 = __ballot_sync(0xFFFFFFFFu, fl & 4u), b3 = __ballot_sync(0xFFFFFFFFu, fl & 8u);
+      const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
       int base = 0;
-      if (lane == 0) base = atomicAdd(&s_nq, __popc(bal));
+      if (lane == 0) base = atomicAdd(&s_nq, n0 + n1 + n2 + n3);
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (fl) queue[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)task;
+      const uint32_t ent = (uint32_t)(ry << 10) | (uint32_t)(4 * G);
+      if (fl & 1u) queue[base + __popc(b0 & lt_mask)] = (unsigned short)ent;
+      if (fl & 2u) queue[base + n0 + __popc(b1 & lt_mask)] = (unsigned short)(ent + 1);
+      if (fl & 4u) queue[base + n0 + n1 + __popc(b2 & lt_mask)] = (unsigned short)(ent + 2);
+      if (fl & 8u) queue[base + n0 + n1 + n2 + __popc(b3 & lt_mask)] = (unsigned short)(ent + 3);
     }
   };
   // scores of the queued quads -> score map, all lanes busy
@@ -512,67 +536,92 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     const int nq = s_nq;
     for (int qi = tid; qi < nq; qi += THREADS) {
       const int task = queue[qi];
-      const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-      const int g = task - ry * quads;
+      const int ry = task >> 10, g = task & 1023;
       uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin);
       const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
       if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
       score32[(ry + 1) * TP4 + g + 1] = packed;
     }
   };
-  // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free on u16x2 pairs.
-  // strict-maximum flags of pixel pair `par` of quad (ry, g) with scores clipped at kth: bit 0 = pixel par,
-  // bit 1 = pixel par + 2
-  auto nms_pair = [&](int ry, int g, uint32_t c0, int par, uint32_t kth) -> uint32_t {
+  // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free.  Scores are
+  // compared as u16 lanes whose HIGH byte is the pixel of interest and whose low byte is whatever byte precedes
+  // it in the score row: min/max of such lanes have the right high byte, and "c > n" is tested as
+  // (c & 0xff00) > (n | 0x00ff), so no byte is ever extracted.  Lanes of a funnel shift of the score words
+  // (x0 | x1 | x2 = quads g-1, g, g+1), pixel numbers relative to quad g:
+  //   x1: pixels 1,3    f24 = (x0:x1)>>24: pixels 0,2    f16 = (x0:x1)>>16: pixels -1,1    f8 = (x1:x2)>>8: pixels 2,4
+  // Returns bit k = pixel k of the quad is a strict maximum with e > kth.
+  auto nms_quad = [&](int ry, int g, uint32_t kth) -> uint32_t {
     const uint32_t* sp = score32 + (ry + 1) * TP4 + g + 1;
     const uint32_t u0 = sp[-TP4 - 1], u1 = sp[-TP4], u2 = sp[-TP4 + 1];
-    const uint32_t m0 = sp[-1], m2 = sp[1];
+    const uint32_t m0 = sp[-1], m1 = sp[0], m2 = sp[1];
     const uint32_t d0 = sp[TP4 - 1], d1 = sp[TP4], d2 = sp[TP4 + 1];
+    if (m1 == 0) return 0u;
     const uint4 mk = s_mask[g];
-    // byte k of L* = pixel k-1, of R* = pixel k+1
-    const uint32_t Lu = __funnelshift_r(u0, u1, 24), Ru = __funnelshift_r(u1, u2, 8);
-    const uint32_t Lm = __funnelshift_r(m0, c0, 24), Rm = __funnelshift_r(c0, m2, 8);
-    const uint32_t Ld = __funnelshift_r(d0, d1, 24), Rd = __funnelshift_r(d1, d2, 8);
-    const uint32_t sel = par ? 0x4341u : 0x4240u;
-    const uint32_t lmax = __vimax3_u16x2(__byte_perm(Lu, 0, sel), __byte_perm(Lm, 0, sel), __byte_perm(Ld, 0, sel)) & (par ? mk.y : mk.x);
-    const uint32_t rmax = __vimax3_u16x2(__byte_perm(Ru, 0, sel), __byte_perm(Rm, 0, sel), __byte_perm(Rd, 0, sel)) & (par ? mk.w : mk.z);
-    const uint32_t nb = __vimax3_u16x2(lmax, rmax, __vmaxu2(__byte_perm(u1, 0, sel), __byte_perm(d1, 0, sel)));
-    const uint32_t c = __byte_perm(c0, 0, sel);
-    // scores clipped at the pass threshold: cz > nz <=> c > threshold and c > nb
-    const uint32_t cz = c - __vminu2(c, kth), nz = nb - __vminu2(nb, kth);
-    const uint32_t t = cz - __vminu2(cz, nz);                  // per half: > 0 <=> kept
-    return ((t & 0xFFFFu) ? 1u : 0u) | ((t >> 16) ? 2u : 0u);
+    const uint32_t u24 = __funnelshift_r(u0, u1, 24), u16 = __funnelshift_r(u0, u1, 16), u8 = __funnelshift_r(u1, u2, 8);
+    const uint32_t m24 = __funnelshift_r(m0, m1, 24), m16 = __funnelshift_r(m0, m1, 16), m8 = __funnelshift_r(m1, m2, 8);
+    const uint32_t d24 = __funnelshift_r(d0, d1, 24), d16 = __funnelshift_r(d0, d1, 16), d8 = __funnelshift_r(d1, d2, 8);
+    const uint32_t th = (kth << 8 | 0xFFu) * 0x00010001u;
+    // even pixels 0,2: centre m24, left column f16, right column x1, above/below f24
+    const uint32_t nb_e = __vimax3_u16x2(__vimax3_u16x2(u16, m16, d16) & mk.x, __vimax3_u16x2(u1, m1, d1) & mk.z, __vmaxu2(u24, d24));
+    // odd pixels 1,3: centre x1, left column f24, right column f8, above/below x1
+    const uint32_t nb_o = __vimax3_u16x2(__vimax3_u16x2(u24, m24, d24) & mk.y, __vimax3_u16x2(u8, m8, d8) & mk.w, __vmaxu2(u1, d1));
+    const uint32_t ce = m24 & 0xFF00FF00u, co = m1 & 0xFF00FF00u;
+    const uint32_t te = ce - __vminu2(ce, __vmaxu2(nb_e | 0x00FF00FFu, th));      // per lane: > 0 <=> kept
+    const uint32_t to = co - __vminu2(co, __vmaxu2(nb_o | 0x00FF00FFu, th));
+    return ((te & 0xFFFFu) ? 1u : 0u) | ((to & 0xFFFFu) ? 2u : 0u) | ((te >> 16) ? 4u : 0u) | ((to >> 16) ? 8u : 0u);
   };
-  // keep pixel k of quad (ry, g): FAST(iniThFAST) maxima mark their cell, FAST(minThFAST) maxima are taken only
-  // in cells that have none (the fallback applies to the pixel's own cell, ORBextractor.cc:812-816)
-  auto keep = [&](int ry, int g, int k, uint32_t c0, bool fallback) {
-    const int x = 4 * g + k;
-    const int cell = (int)__umulhi((uint32_t)x, L.wcell_magic);
-    if (fallback) { if (s_ini[cell] != 0) return; }
-    else s_ini[cell] = 1;                                      // benign race: everybody writes 1
-    const int slot = atomicAdd(&s_n, 1);
-    if (slot < list_cap) list[slot] = (uint32_t)x | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
-    else atomicOr(P.status, 1);
-  };
+  // Kept maxima -> list.  FAST(iniThFAST) maxima mark their cell; FAST(minThFAST) maxima are taken only in cells
+  // that have none (the fallback applies to the pixel's own cell, ORBextractor.cc:812-816).  List slots come from
+  // one ballot + one shared atomic per warp and round.
   auto nms_queue = [&](uint32_t kth, bool fallback) {
     const int nq = s_nq;
-    for (int qi = tid; qi < nq; qi += THREADS) {
-      const int task = queue[qi];
-      const int ry = (int)__umulhi((uint32_t)task, L.quads_magic);
-      const int g = task - ry * quads;
-      const uint32_t c0 = score32[(ry + 1) * TP4 + g + 1];
-      if (c0 == 0) continue;
+    for (int qi0 = tid - lane; qi0 < nq; qi0 += THREADS) {
+      const int qi = qi0 + lane;
+      uint32_t surv = 0, c0 = 0;
+      int ry = 0, g = 0;
+      if (qi < nq) {
+        const int task = queue[qi];
+        ry = task >> 10; g = task & 1023;
+        surv = nms_quad(ry, g, kth);
+        if (surv) {
+          c0 = score32[(ry + 1) * TP4 + g + 1];
+          const int ca = (int)__umulhi((uint32_t)(4 * g), L.wcell_magic), cb = (int)__umulhi((uint32_t)min(4 * g + 3, iw - 1), L.wcell_magic);
+          if (fallback) {
+            // cells that had FAST(iniThFAST) corners keep those only
+            if (ca == cb) { if (s_ini[ca] != 0) surv = 0; }
+            else {
 #pragma unroll
-      for (int par = 0; par < 2; ++par) {
-        const uint32_t surv = nms_pair(ry, g, c0, par, kth);
-        if (surv & 1u) keep(ry, g, par, c0, fallback);
-        if (surv & 2u) keep(ry, g, par + 2, c0, fallback);
+              for (int k = 0; k < 4; ++k)
+                if ((surv >> k & 1u) && s_ini[(int)__umulhi((uint32_t)(4 * g + k), L.wcell_magic)] != 0) surv &= ~(1u << k);
+            }
+          } else {
+            if (ca == cb) s_ini[ca] = 1;                         // benign race: everybody writes 1
+            else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (surv >> k & 1u) s_ini[(int)__umulhi((uint32_t)(4 * g + k), L.wcell_magic)] = 1;
+            }
+          }
+        }
+      }
+      // usually one round; a quad straddling a cell edge can hold up to three maxima
+      unsigned bal = __ballot_sync(0xFFFFFFFFu, surv != 0);
+      while (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (surv) {
+          const int k = __ffs(surv) - 1, slot = base + __popc(bal & lt_mask);
+          if (slot < list_cap) list[slot] = (uint32_t)(4 * g + k) | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
+          else atomicOr(P.status, 1);
+          surv &= surv - 1u;
+        }
+        bal = __ballot_sync(0xFFFFFFFFu, surv != 0);
       }
     }
   };
-  auto all = [](int) { return true; };
   // ---- pass 0: what FAST(iniThFAST) returns
-  build_queue((uint32_t)P.ini_th * 0x00010001u, all);
+  build_queue(P.ini_th, [](int, uint32_t fl) { return fl; });
   __syncthreads();
   eval_queue();
   __syncthreads();
@@ -583,13 +632,23 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     int missing = 0;
     for (int c = tid; c < ncells_x; c += THREADS) missing |= (s_ini[c] == 0);
     if (__syncthreads_or(missing)) {
-      auto needs = [&](int g) -> bool {
-        const int ca = (int)__umulhi((uint32_t)(4 * g), L.wcell_magic), cb = (int)__umulhi((uint32_t)min(4 * g + 3, iw - 1), L.wcell_magic);
-        return s_ini[ca] == 0 || s_ini[cb] == 0;
+      // only quads that touch a cell without corners
+      auto needs = [&](int G, uint32_t fl) -> uint32_t {
+        if (fl == 0) return 0u;
+        const int x0 = 16 * G;
+        const int ca = (int)__umulhi((uint32_t)x0, L.wcell_magic), cb = (int)__umulhi((uint32_t)min(x0 + 15, iw - 1), L.wcell_magic);
+        if (ca == cb) return s_ini[ca] == 0 ? fl : 0u;
+        uint32_t keep = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xa = min(x0 + 4 * k, iw - 1), xb = min(x0 + 4 * k + 3, iw - 1);
+          if (s_ini[(int)__umulhi((uint32_t)xa, L.wcell_magic)] == 0 || s_ini[(int)__umulhi((uint32_t)xb, L.wcell_magic)] == 0) keep |= 1u << k;
+        }
+        return fl & keep;
       };
       if (tid == 0) s_nq = 0;
       __syncthreads();
-      build_queue((uint32_t)P.min_th * 0x00010001u, needs);
+      build_queue(P.min_th, needs);
       __syncthreads();
       eval_queue();
       __syncthreads();
@@ -1366,6 +1425,9 @@ static int orb_build(drfe_orb* h) {
       const unsigned quads = (unsigned)((L.w - 2 * kEdge + 3) / 4);
       L.quads_magic = (uint32_t)(((1ull << 32) + quads - 1) / quads);
       L.wcell_magic = (uint32_t)(((1ull << 32) + L.wCell - 1) / L.wCell);
+      const unsigned groups = (quads + 3) / 4;
+      L.groups_magic = (uint32_t)(((1ull << 32) + groups - 1) / groups);
+      if (quads > 1023) { set_error("image too wide for the FAST strip kernel (%u quads per row)", quads); return DRFE_ERR_ARG; }
     }
     L.blur_nq = (L.w + 3) / 4;
     L.blur_magic = (uint32_t)(((1ull << 32) + L.blur_nq - 1) / L.blur_nq);
@@ -1379,6 +1441,7 @@ static int orb_build(drfe_orb* h) {
   for (int l = 0; l < nl; ++l) h->max_lkp = std::max(h->max_lkp, D.lv[l].node_cap);
   D.fast_tp = (D.lv[0].w + 15) / 16 * 16;         // smem row pitch of a FAST strip (TMA rows are 16 B multiples)
   D.fast_rows = max_strip_rows;
+  if (max_strip_rows > 63) { set_error("FAST strip of %d rows (queue entries hold 6 row bits)", max_strip_rows); return DRFE_ERR_ARG; }
   {
     // tile | score map (+2 guard rows) | per-quad masks | compass queue (u16 per quad) | list of kept maxima
     const size_t tp = D.fast_tp, rows = D.fast_rows, max_tasks = (tp / 4) * rows;
