@@ -308,28 +308,42 @@ __global__ void __launch_bounds__(128, 10) k_pyr_stream(const OrbDev* __restrict
 //   A = min over the 16 nine-pixel arcs of max(r over the arc)
 //   B = max over the 16 nine-pixel arcs of min(r over the arc)
 //   q = max(v - A, B - v) - 1          (= OpenCV's cornerScore; corner at threshold t <=> q >= t)
-// Two pixels are processed per 32-bit register as u16x2 (VIMNMX3.U16x2 on sm_100a).
-// Returns (q + 257) per half, i.e. always positive.
-__device__ __forceinline__ uint32_t fast_q_pair(const uint32_t (&r)[16], uint32_t v) {
-  uint32_t mn3[16], mx3[16];
+// Two pixels are processed per 32-bit register as u16 lanes (VIMNMX3.U16x2 on sm_100a) whose HIGH byte is
+// the pixel and whose low byte is arbitrary (the neighbouring image byte): min/max of such lanes carry the
+// right high byte, so the ring needs no byte extraction at all — every packed min/max, PRMT, SHF and LOP3
+// issues on the half-rate ALU pipe (tools/ubench/pipes.cu), which is what bounds this kernel.
+// Arcs k and k+1 (k even) share the 8 pixels k+1..k+8:  max(min arc k, min arc k+1) =
+// min(r[k+1..k+8], max(r[k], r[k+9])); with pair minima p[j] = min(r[j], r[j+1]) (j odd) and
+// pp[j] = min(p[j], p[j+2]) that is min3(pp[k+1], pp[k+5], max(r[k], r[k+9])): 36 operations per polarity.
+// Returns e = max(q + 1 - minTh, 0) in the high byte of each lane (low bytes 0); kmin8 = minTh << 8 per lane.
+__device__ __forceinline__ uint32_t fast_e_lanes(const uint32_t (&r)[16], uint32_t v, uint32_t kmin8) {
+  uint32_t pmn[8], pmx[8];                                    // pairs (1,2) (3,4) ... (15,0)
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-    mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+  for (int j = 0; j < 8; ++j) {
+    pmn[j] = __vminu2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+    pmx[j] = __vmaxu2(r[2 * j + 1], r[(2 * j + 2) & 15]);
   }
-  uint32_t B = 0x00000000u, A = 0x7FFF7FFFu;
+  uint32_t qmn[8], qmx[8];                                    // 4 consecutive pixels 2j+1 .. 2j+4
 #pragma unroll
-  for (int k = 0; k < 16; k += 2) {
-    const uint32_t a = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
-    const uint32_t b = __vimin3_u16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
-    B = __vimax3_u16x2(B, a, b);
-    const uint32_t c = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
-    const uint32_t e = __vimax3_u16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
-    A = __vimin3_u16x2(A, c, e);
+  for (int j = 0; j < 8; ++j) {
+    qmn[j] = __vminu2(pmn[j], pmn[(j + 1) & 7]);
+    qmx[j] = __vmaxu2(pmx[j], pmx[(j + 1) & 7]);
   }
-  // halves never borrow: v + 256 - A >= 1 and B + 256 - v >= 1
-  const uint32_t t1 = v + 0x01000100u - A, t2 = B + 0x01000100u - v;
-  return __vmaxu2(t1, t2);
+  uint32_t bv[8], av[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {                               // k = 2i: pixels k+1..k+8 = q[i], q[i+2]
+    const uint32_t hi = __vmaxu2(r[2 * i], r[(2 * i + 9) & 15]), lo = __vminu2(r[2 * i], r[(2 * i + 9) & 15]);
+    bv[i] = __vimin3_u16x2(qmn[i], qmn[(i + 2) & 7], hi);
+    av[i] = __vimax3_u16x2(qmx[i], qmx[(i + 2) & 7], lo);
+  }
+  uint32_t B = __vimax3_u16x2(bv[0], bv[1], bv[2]), A = __vimin3_u16x2(av[0], av[1], av[2]);
+  B = __vimax3_u16x2(B, bv[3], bv[4]); A = __vimin3_u16x2(A, av[3], av[4]);
+  B = __vimax3_u16x2(B, bv[5], bv[6]); A = __vimin3_u16x2(A, av[5], av[6]);
+  B = __vmaxu2(B, bv[7]); A = __vminu2(A, av[7]);
+  const uint32_t vh = v & 0xFF00FF00u, Ah = A & 0xFF00FF00u, Bh = B & 0xFF00FF00u;
+  const uint32_t d1 = vh - __vminu2(vh, Ah), d2 = Bh - __vminu2(Bh, vh);     // max(v - A, 0), max(B - v, 0), << 8
+  const uint32_t E = __vmaxu2(d1, d2);                                         // (q + 1) << 8 when positive
+  return E - __vminu2(E, kmin8);
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
@@ -355,7 +369,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // Full threshold-free score of the 4 pixels of quad g in interior row ry: returns the packed bytes
 // e = max(q + 1 - minTh, 0) of pixels 0..3.  tile32: strip rows as words, TP4 words per row.
-__device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t kmin) {
+__device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t kmin8) {
   // window rows ry..ry+6 (level rows y-3..y+3), bytes 16+4g .. 16+4g+11 (level columns x-3..x+8)
   uint32_t w[7][3];
 #pragma unroll
@@ -367,25 +381,23 @@ __device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ 
   auto quad = [&](int r, int o) -> uint32_t {
     return (o & 3) == 0 ? w[r][o >> 2] : __funnelshift_r(w[r][o >> 2], w[r][(o >> 2) + 1], 8 * (o & 3));
   };
+  // Lanes with the pixel in the high byte: the word of 4 adjacent bytes is that for pixels 1,3 as it stands
+  // and for pixels 0,2 after a shift by one byte (an IMAD.SHL on the FMA pipe, not the ALU pipe).
   const uint32_t vq = quad(3, 3);                          // centres of the 4 pixels
-  const uint32_t v_even = __byte_perm(vq, 0, 0x4240);      // pixels 0,2 as u16x2
-  const uint32_t v_odd = __byte_perm(vq, 0, 0x4341);       // pixels 1,3
   uint32_t re[16], ro[16];
 #define DRFE_RING(k, dx, dy)                                   \
   {                                                            \
-    const uint32_t rq = quad(3 + (dy), 3 + (dx));              \
-    re[k] = __byte_perm(rq, 0, 0x4240);                        \
-    ro[k] = __byte_perm(rq, 0, 0x4341);                        \
+    ro[k] = quad(3 + (dy), 3 + (dx));                          \
+    re[k] = ro[k] * 256u;                                      \
   }
   DRFE_RING(0, 0, 3) DRFE_RING(1, 1, 3) DRFE_RING(2, 2, 2) DRFE_RING(3, 3, 1)
   DRFE_RING(4, 3, 0) DRFE_RING(5, 3, -1) DRFE_RING(6, 2, -2) DRFE_RING(7, 1, -3)
   DRFE_RING(8, 0, -3) DRFE_RING(9, -1, -3) DRFE_RING(10, -2, -2) DRFE_RING(11, -3, -1)
   DRFE_RING(12, -3, 0) DRFE_RING(13, -3, 1) DRFE_RING(14, -2, 2) DRFE_RING(15, -1, 3)
 #undef DRFE_RING
-  // e = max(q + 257, 256 + minTh) - (256 + minTh) = max(q + 1 - minTh, 0) per half (< 256)
-  const uint32_t ee = __vmaxu2(fast_q_pair(re, v_even), kmin) - kmin;
-  const uint32_t eo = __vmaxu2(fast_q_pair(ro, v_odd), kmin) - kmin;
-  return ee | (eo << 8);                                   // bytes: pixel 0,1,2,3
+  const uint32_t ee = fast_e_lanes(re, vq * 256u, kmin8);  // pixels 0,2 in the high bytes
+  const uint32_t eo = fast_e_lanes(ro, vq, kmin8);         // pixels 1,3
+  return (ee >> 8) | eo;                                   // bytes: pixel 0,1,2,3
 }
 
 // Necessary condition for "corner at threshold t" on the 4 pixels of a quad: every 9-pixel arc of the
@@ -484,7 +496,7 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     auto lanes = [](uint32_t m, int lo, int hi) { return ((m >> lo) & 1u ? 0xFFFFu : 0u) | ((m >> hi) & 1u ? 0xFFFF0000u : 0u); };
     s_mask[g] = make_uint4(lanes(ml, 0, 2), lanes(ml, 1, 3), lanes(mr, 0, 2), lanes(mr, 1, 3));
   }
-  const uint32_t kmin = (uint32_t)(256 + P.min_th) * 0x00010001u;
+  const uint32_t kmin8 = (uint32_t)(P.min_th << 8) * 0x00010001u;
   const int lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   // the whole score map starts at zero: pixels the compass test rules out are never written
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     for (int qi = tid; qi < nq; qi += THREADS) {
       const int task = queue[qi];
       const int ry = task >> 10, g = task & 1023;
-      uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin);
+      uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin8);
       const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
       if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
       score32[(ry + 1) * TP4 + g + 1] = packed;
