@@ -198,156 +198,188 @@ __device__ __forceinline__ bool quotient_needs_exact(double q) {
 }
 
 static const int kSumsThreads = 128, kSumsChunk = 5;
+static const int kSumsCells = 4;     // consecutive cells per 16-lane group (depth of cell c+2 is in flight while c is summed)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // MODE 0: the cell-major cloud is given; 1: float depth image; 2: raw 16-bit depth image scaled by depth_factor
 // CELL: compile-time cell edge (square cells of 20 or 10 px, the two sizes DR-SLAM's yaml files use) so that
-// the per-element index arithmetic and bounds tests fold away; 0 = any cell size, read from the descriptor
+// the per-element index arithmetic and bounds tests fold away; 0 = any cell size, read from the descriptor.
+// A 16-lane group walks kSumsCells consecutive cells; with a float depth image whose cell rows are 16-byte
+// aligned, the depth of the next two cells is copied into a two-slot shared-memory ring by cp.async (LDGSTS)
+// while the current cell is summed, so only the group's first load latency is exposed.
 template <int MODE, int CELL>
 __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   constexpr bool FROM_DEPTH = MODE != 0;
-  extern __shared__ __align__(16) float s_zall[];           // [8 groups][npc]
+  extern __shared__ __align__(16) float s_zall[];           // [8 groups][2 slots][npc]
   const CapeDev& P = *Pp;
-  const int gid0 = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;  // cell index within this launch
+  const int grp = (blockIdx.x * kSumsThreads + threadIdx.x) >> 4;
   const int l = threadIdx.x & 15;
   // full-warp mask: both 16-lane groups of a warp run the same shuffles (width 16); a group that
-  // exited above is simply absent.  (A per-group runtime mask makes the compiler serialise them.)
+  // has returned is simply absent.  (A per-group runtime mask makes the compiler serialise them.)
   const unsigned mask = 0xFFFFFFFFu;
   const int ncells = P.ncells;
-  if (gid0 >= nframes * ncells) return;                     // whole 16-lane groups exit together
-  const int gid = gid0 + f0 * ncells;                       // global cell index over the batch
-  const int f = gid / ncells, cell = gid - f * ncells;
+  const int total = nframes * ncells;
+  const int first = grp * kSumsCells;                       // first cell of this group within the launch
+  if (first >= total) return;                               // whole 16-lane groups exit together
+  const int ncell_here = min(kSumsCells, total - first);
   const int npc = CELL ? CELL * CELL : P.npc, cw = CELL ? CELL : P.cw, ch = CELL ? CELL : P.ch;
-  float* s_z = s_zall + (threadIdx.x >> 4) * npc;
+  float* s_ring = s_zall + (threadIdx.x >> 4) * 2 * npc;
   const long long N = (long long)P.H * P.W;
-  float* __restrict__ CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
-  float* __restrict__ CY = CX + N;
-  float* __restrict__ CZ = CY + N;
   const int body = (npc / 16) * 16;
   const bool has_extra = npc - body >= 8;
   const int full8 = has_extra ? body + 8 : body;
-  float ax = 0, ay = 0, az = 0, axx = 0, ayy = 0, azz = 0, axy = 0, axz = 0, ayz = 0;
-  float ex = 0, ey = 0, ez = 0, exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;  // extra packet
-  int cnt = 0;
-  const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
-  // ---- stage z in shared memory (it is also what the depth-jump scans read)
-  if (MODE == 1) {
-    const int drs = (int)P.depth_rs;
+  const int drs = (int)P.depth_rs;
+  // every cell row starts on a 16-byte boundary: rows can be moved as float4 (MODE 1) / 4 x u16 (MODE 2)
+  const bool vec1 = MODE == 1 && (cw & 3) == 0 && (drs & 3) == 0 && (P.depth_fs & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.depth) & 15) == 0);
+  const bool vec2 = MODE == 2 && (cw & 3) == 0 && (drs & 3) == 0 && (P.depth_fs & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.depth16) & 7) == 0);
+  // asynchronous copy of cell (first + c)'s depth into ring slot c & 1 (MODE 1, aligned)
+  auto prefetch = [&](int c) {
+    const int gid = first + c + f0 * ncells;
+    const int f = gid / ncells, cell = gid - f * ncells;
+    const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
     const float* __restrict__ dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
-    if ((cw & 3) == 0 && (drs & 3) == 0 && ((reinterpret_cast<uintptr_t>(dsrc) & 15) == 0)) {
-      const int q4 = cw >> 2, n4 = npc >> 2;                 // float4 per cell row / per cell
-      for (int j = l; j < n4; j += 16) {
-        const int r = j / q4, c4 = j - r * q4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dsrc + r * drs) + c4);
-        *reinterpret_cast<float4*>(s_z + 4 * j) = v;        // cell-local index = r*cw + 4*c4 = 4*j
-      }
-    } else {
-      for (int i = l; i < npc; i += 16) {
-        const int r = i / cw, c = i - r * cw;
-        s_z[i] = __ldg(dsrc + r * drs + c);
-      }
+    float* dst = s_ring + (c & 1) * npc;
+    const int q4 = cw >> 2, n4 = npc >> 2;                   // float4 per cell row / per cell
+    for (int j = l; j < n4; j += 16) {
+      const int r = j / q4, c4 = j - r * q4;
+      cp_async16(dst + 4 * j, dsrc + r * drs + 4 * c4);      // cell-local index = r*cw + 4*c4 = 4*j
     }
-  } else if (MODE == 2) {
-    // imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) (Frame.cc:113-115): float(u16) * float(factor)
-    const int drs = (int)P.depth_rs;
-    const float fac = P.depth_factor;
-    const uint16_t* __restrict__ dsrc = P.depth16 + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
-    if ((cw & 3) == 0 && (drs & 3) == 0 && ((reinterpret_cast<uintptr_t>(dsrc) & 7) == 0)) {
-      const int q4 = cw >> 2, n4 = npc >> 2;
-      for (int j = l; j < n4; j += 16) {
-        const int r = j / q4, c4 = j - r * q4;
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(dsrc + r * drs) + c4);
-        *reinterpret_cast<float4*>(s_z + 4 * j) = make_float4((float)(v.x & 0xFFFFu) * fac, (float)(v.x >> 16) * fac,
-                                                              (float)(v.y & 0xFFFFu) * fac, (float)(v.y >> 16) * fac);
-      }
-    } else {
-      for (int i = l; i < npc; i += 16) {
-        const int r = i / cw, c = i - r * cw;
-        s_z[i] = (float)__ldg(dsrc + r * drs + c) * fac;
-      }
-    }
-  } else {
-    for (int i = l; i < npc; i += 16) s_z[i] = CZ[i];
-  }
-  __syncwarp(mask);
+    cp_async_commit();
+  };
+  if (vec1) { prefetch(0); if (ncell_here > 1) prefetch(1); }
   const double fx = (double)P.fx, fy = (double)P.fy;
   const double rfx = 1.0 / fx, rfy = 1.0 / fy;
-  const double col0 = (double)(cc * cw) - (double)P.cx, row0 = (double)(cr * ch) - (double)P.cy;
-  int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
   const int step_r = 16 / cw, step_c = 16 - step_r * cw;    // element i + 16
-  // (double)j - cx and (double)i - cy of the element, stepped along with (lr, lc): sums of small half-integers, exact
-  double dcol = col0 + (double)lc, drow = row0 + (double)lr;
   const double dstep_c = (double)step_c, dstep_r = (double)step_r, dcw = (double)cw;
-  for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
-#pragma unroll
-    for (int u = 0; u < kSumsChunk; ++u) {
-      const int i = i0 + 16 * u;
-      if (i < npc) {
-        float x, y;
-        const float z = s_z[i];
-        if (FROM_DEPTH) {
-          // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
-          // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
-          const double zd = (double)z;
-          const double tx = dcol * zd, ty = drow * zd;
-          const double qx = tx * rfx, qy = ty * rfy;
-          if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
-          else { x = (float)qx; y = (float)qy; }
-          CX[i] = x; CY[i] = y; CZ[i] = z;
-        } else {
-          x = CX[i]; y = CY[i];
-        }
-        cnt += (z > 0.f);
-        if (i < body) {
-          if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
-          else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
-                 axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
-        } else if (i < full8) {
-          ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
+  for (int c = 0; c < ncell_here; ++c) {
+    const int gid = first + c + f0 * ncells;                  // global cell index over the batch
+    const int f = gid / ncells, cell = gid - f * ncells;
+    float* s_z = s_ring + (c & 1) * npc;
+    float* __restrict__ CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+    float* __restrict__ CY = CX + N;
+    float* __restrict__ CZ = CY + N;
+    float ax = 0, ay = 0, az = 0, axx = 0, ayy = 0, azz = 0, axy = 0, axz = 0, ayz = 0;
+    float ex = 0, ey = 0, ez = 0, exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;  // extra packet
+    int cnt = 0;
+    const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
+    // ---- stage z in shared memory (it is also what the depth-jump scans read)
+    if (MODE == 1) {
+      if (vec1) {
+        if (c + 1 < ncell_here) cp_async_wait<1>(); else cp_async_wait<0>();
+      } else {
+        const float* __restrict__ dsrc = P.depth + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
+        for (int i = l; i < npc; i += 16) {
+          const int r = i / cw, cl = i - r * cw;
+          s_z[i] = __ldg(dsrc + r * drs + cl);
         }
       }
-      lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
-      if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
+    } else if (MODE == 2) {
+      // imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) (Frame.cc:113-115): float(u16) * float(factor)
+      const float fac = P.depth_factor;
+      const uint16_t* __restrict__ dsrc = P.depth16 + (long long)f * P.depth_fs + (long long)(cr * ch) * P.depth_rs + cc * cw;
+      if (vec2) {
+        const int q4 = cw >> 2, n4 = npc >> 2;
+        for (int j = l; j < n4; j += 16) {
+          const int r = j / q4, c4 = j - r * q4;
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(dsrc + r * drs) + c4);
+          *reinterpret_cast<float4*>(s_z + 4 * j) = make_float4((float)(v.x & 0xFFFFu) * fac, (float)(v.x >> 16) * fac,
+                                                                (float)(v.y & 0xFFFFu) * fac, (float)(v.y >> 16) * fac);
+        }
+      } else {
+        for (int i = l; i < npc; i += 16) {
+          const int r = i / cw, cl = i - r * cw;
+          s_z[i] = (float)__ldg(dsrc + r * drs + cl) * fac;
+        }
+      }
+    } else {
+      for (int i = l; i < npc; i += 16) s_z[i] = CZ[i];
     }
-  }
+    __syncwarp(mask);
+    const double col0 = (double)(cc * cw) - (double)P.cx, row0 = (double)(cr * ch) - (double)P.cy;
+    int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
+    // (double)j - cx and (double)i - cy of the element, stepped along with (lr, lc): sums of small half-integers, exact
+    double dcol = col0 + (double)lc, drow = row0 + (double)lr;
+    for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) cnt += __shfl_down_sync(mask, cnt, o, 16);
-  // (body is a multiple of 16, so element body+j was handled by lane j: the extra packet is in place)
-  float sx = tree16(ax, has_extra, mask, ex), sy = tree16(ay, has_extra, mask, ey), sz = tree16(az, has_extra, mask, ez),
-        sxx = tree16(axx, has_extra, mask, exx), syy = tree16(ayy, has_extra, mask, eyy),
-        szz = tree16(azz, has_extra, mask, ezz), sxy = tree16(axy, has_extra, mask, exy),
-        sxz = tree16(axz, has_extra, mask, exz), syz = tree16(ayz, has_extra, mask, eyz);
-  __syncwarp(mask);                                         // s_z and the cloud are complete
-  // depth-jump scans through the middle row (lane 0) and the middle column (lane 1)
-  int jumps = 0;
-  if (l < 2) {
-    const int chh = npc / cw;
-    int i, j, step;
-    float z_last;
-    if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_last = fmaxf(s_z[i], s_z[i + 1]); }
-    else { i = cw / 2; j = npc - i; step = cw; z_last = fmaxf(s_z[i], s_z[i + cw]); }
-    i += step;
-    while (i < j) {
-      const float z = s_z[i];
-      if (z > 0 && fabsf(z - z_last) < 100.0f) z_last = z;   // == (double)|dz| < 100.0: 100 is a float
-      else if (z > 0) ++jumps;
-      i += step;
+      for (int u = 0; u < kSumsChunk; ++u) {
+        const int i = i0 + 16 * u;
+        if (i < npc) {
+          float x, y;
+          const float z = s_z[i];
+          if (FROM_DEPTH) {
+            // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
+            // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
+            const double zd = (double)z;
+            const double tx = dcol * zd, ty = drow * zd;
+            const double qx = tx * rfx, qy = ty * rfy;
+            if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
+            else { x = (float)qx; y = (float)qy; }
+            CX[i] = x; CY[i] = y; CZ[i] = z;
+          } else {
+            x = CX[i]; y = CY[i];
+          }
+          cnt += (z > 0.f);
+          if (i < body) {
+            if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
+            else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
+                   axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
+          } else if (i < full8) {
+            ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
+          }
+        }
+        lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
+        if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
+      }
     }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) cnt += __shfl_down_sync(mask, cnt, o, 16);
+    // (body is a multiple of 16, so element body+j was handled by lane j: the extra packet is in place)
+    float sx = tree16(ax, has_extra, mask, ex), sy = tree16(ay, has_extra, mask, ey), sz = tree16(az, has_extra, mask, ez),
+          sxx = tree16(axx, has_extra, mask, exx), syy = tree16(ayy, has_extra, mask, eyy),
+          szz = tree16(azz, has_extra, mask, ezz), sxy = tree16(axy, has_extra, mask, exy),
+          sxz = tree16(axz, has_extra, mask, exz), syz = tree16(ayz, has_extra, mask, eyz);
+    __syncwarp(mask);                                         // s_z and the cloud are complete
+    // depth-jump scans through the middle row (lane 0) and the middle column (lane 1)
+    int jumps = 0;
+    if (l < 2) {
+      const int chh = npc / cw;
+      int i, j, step;
+      float z_last;
+      if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_last = fmaxf(s_z[i], s_z[i + 1]); }
+      else { i = cw / 2; j = npc - i; step = cw; z_last = fmaxf(s_z[i], s_z[i + cw]); }
+      i += step;
+      while (i < j) {
+        const float z = s_z[i];
+        if (z > 0 && fabsf(z - z_last) < 100.0f) z_last = z;   // == (double)|dz| < 100.0: 100 is a float
+        else if (z > 0) ++jumps;
+        i += step;
+      }
+    }
+    const int jumps_v = __shfl_down_sync(mask, jumps, 1, 16);
+    if (l == 0) {
+      // scalar tail (Eigen's unaligned end), sequential
+      for (int i = full8; i < npc; ++i) {
+        const float x = CX[i], y = CY[i], z = CZ[i];
+        sx = sx + x; sy = sy + y; sz = sz + z; sxx = sxx + x * x; syy = syy + y * y; szz = szz + z * z;
+        sxy = sxy + x * y; sxz = sxz + x * z; syz = syz + y * z;
+      }
+      CellSums o;
+      o.s[0] = sx; o.s[1] = sy; o.s[2] = sz; o.s[3] = sxx; o.s[4] = syy; o.s[5] = szz; o.s[6] = sxy; o.s[7] = sxz; o.s[8] = syz;
+      o.cnt = cnt;
+      o.planar = (cnt >= npc / 2 && jumps <= 1 && jumps_v <= 1) ? 1 : 0;
+      o.pad = 0;
+      float4* dst = reinterpret_cast<float4*>(P.sums + (long long)gid);
+      const float4* srcv = reinterpret_cast<const float4*>(&o);
+      dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2];
+    }
+    // the scans are done with this slot (the shuffle above is after them in every lane): refill it
+    if (vec1 && c + 2 < ncell_here) prefetch(c + 2);
   }
-  const int jumps_v = __shfl_down_sync(mask, jumps, 1, 16);
-  if (l != 0) return;
-  // scalar tail (Eigen's unaligned end), sequential
-  for (int i = full8; i < npc; ++i) {
-    const float x = CX[i], y = CY[i], z = CZ[i];
-    sx = sx + x; sy = sy + y; sz = sz + z; sxx = sxx + x * x; syy = syy + y * y; szz = szz + z * z;
-    sxy = sxy + x * y; sxz = sxz + x * z; syz = syz + y * z;
-  }
-  CellSums o;
-  o.s[0] = sx; o.s[1] = sy; o.s[2] = sz; o.s[3] = sxx; o.s[4] = syy; o.s[5] = szz; o.s[6] = sxy; o.s[7] = sxz; o.s[8] = syz;
-  o.cnt = cnt;
-  o.planar = (cnt >= npc / 2 && jumps <= 1 && jumps_v <= 1) ? 1 : 0;
-  o.pad = 0;
-  float4* dst = reinterpret_cast<float4*>(P.sums + (long long)gid);
-  const float4* srcv = reinterpret_cast<const float4*>(&o);
-  dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2];
 }
 
 // k_cape_fit: one thread per cell — the rest of PlaneSeg::PlaneSeg (PlaneSeg.cpp:78-94): sums
@@ -1491,7 +1523,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
     set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
   }
   {
-    const size_t sums_smem = (size_t)(kSumsThreads / 16) * D.npc * sizeof(float);
+    const size_t sums_smem = (size_t)(kSumsThreads / 16) * 2 * D.npc * sizeof(float);
     if (sums_smem > 200 * 1024) { set_error("drfe_cape_create: cells of %d points are too large", D.npc); return fail(DRFE_ERR_ARG); }
     cudaError_t e = cudaSuccess;
 #define DRFE_SUMS_ATTR(M, C) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cape_sums<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem)
@@ -1536,8 +1568,9 @@ int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, 
 static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   cudaStream_t st = h->stream;
   const int ncell_total = n * h->hd.ncells;
-  const size_t sums_smem = (size_t)(kSumsThreads / 16) * h->hd.npc * sizeof(float);
-  const int sums_grid = (ncell_total * 16 + kSumsThreads - 1) / kSumsThreads;
+  const size_t sums_smem = (size_t)(kSumsThreads / 16) * 2 * h->hd.npc * sizeof(float);
+  const int sums_groups = (ncell_total + kSumsCells - 1) / kSumsCells;
+  const int sums_grid = (sums_groups * 16 + kSumsThreads - 1) / kSumsThreads;
   const int mode = h->hd.depth16 ? 2 : (h->hd.depth ? 1 : 0);
   const int cell = (h->hd.cw == h->hd.ch && (h->hd.cw == 20 || h->hd.cw == 10)) ? h->hd.cw : 0;
 #define DRFE_SUMS(M, C) DRFE_LAUNCH((k_cape_sums<M, C>), sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n)
