@@ -1387,6 +1387,79 @@ __global__ void k_cape_clear_margin(const CapeDev* __restrict__ Pp, int f0, int 
 // ====================================================================== host side
 using namespace drfe;
 
+// ------------------------------------------------------------------ per-plane point lists
+// PlaneDetection_CAPE::runPlaneDetection after CAPE::process (PlaneExtractor.cpp:165-190): every pixel whose
+// seg_output code is > 0 appends its (x, y, z) to plane_cloud[code - 1], pixels visited in row-major order.
+// One CTA per frame, each of its 32 warps owns a contiguous run of pixels: pass 1 counts the run's pixels per
+// label (one shared-memory add per group of equal labels in a 32-pixel step, via match.any), an exclusive scan
+// over (label, warp) turns the counts into output positions, pass 2 re-reads the labels and writes the points
+// (stable: lower pixel index first inside a label).  Codes above nr_planes (cylinder labels 51+) are skipped —
+// the reference would index plane_cloud out of range there; DR-SLAM runs CAPE with cylinder detection off.
+static const int kPtsWarps = 32;
+static __global__ void __launch_bounds__(kPtsWarps * 32) k_cape_plane_points(const CapeDev* __restrict__ Pp, int f0, float* __restrict__ out,
+                                                                     int* __restrict__ offsets, uint32_t magic_w, uint32_t magic_cw, uint32_t magic_ch) {
+  extern __shared__ int s_pos[];                              // [kPtsWarps][np + 1] counts, then running output positions
+  __shared__ int s_start[kMaxPlanes + 2];
+  const CapeDev& P = *Pp;
+  const int f = blockIdx.x + f0;
+  const int np = min(P.nplanes[f], kMaxPlanes);
+  const int N = P.H * P.W;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  int* offs = offsets + (long long)f * (kMaxPlanes + 1);
+  if (np == 0) { if (tid == 0) offs[0] = 0; return; }
+  const int stride = np + 1;
+  for (int i = tid; i < kPtsWarps * stride; i += kPtsWarps * 32) s_pos[i] = 0;
+  __syncthreads();
+  const uint8_t* __restrict__ seg = P.seg + (long long)f * N;
+  const int run = ((N + kPtsWarps - 1) / kPtsWarps + 31) & ~31;  // pixels per warp, a multiple of 32
+  const int p0 = w * run, p1 = min(p0 + run, N);
+  int* mine = s_pos + w * stride;
+  for (int p = p0 + lane; p - lane < p1; p += 32) {
+    int key = p < p1 ? seg[p] : 0;
+    if (key > np) key = 0;
+    const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+    if (key && (m & lt) == 0) mine[key] += __popc(m);         // the group's lowest lane adds its size
+  }
+  __syncthreads();
+  if (tid < np) {                                              // total of label tid + 1
+    int t = 0;
+    for (int k = 0; k < kPtsWarps; ++k) t += s_pos[k * stride + tid + 1];
+    s_start[tid + 1] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run_tot = 0;
+    for (int L = 1; L <= np; ++L) { const int t = s_start[L]; s_start[L] = run_tot; offs[L - 1] = run_tot; run_tot += t; }
+    offs[np] = run_tot;
+  }
+  __syncthreads();
+  if (tid < np) {
+    int at = s_start[tid + 1];
+    for (int k = 0; k < kPtsWarps; ++k) { const int t = s_pos[k * stride + tid + 1]; s_pos[k * stride + tid + 1] = at; at += t; }
+  }
+  __syncthreads();
+  const float* __restrict__ CX = P.cloud + (long long)f * 3 * N;
+  float* __restrict__ dst = out + (long long)f * 3 * N;
+  for (int p = p0 + lane; p - lane < p1; p += 32) {
+    int key = p < p1 ? seg[p] : 0;
+    if (key > np) key = 0;
+    const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (key && lane == leader) { base = mine[key]; mine[key] = base + __popc(m); }
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (key) {
+      const int r = (int)__umulhi((uint32_t)p, magic_w), c = p - r * P.W;
+      const int cell_r = (int)__umulhi((uint32_t)r, magic_ch), cell_c = (int)__umulhi((uint32_t)c, magic_cw);
+      const int idx = (cell_r * P.ncx + cell_c) * P.npc + (r - cell_r * P.ch) * P.cw + (c - cell_c * P.cw);
+      float* o = dst + 3ll * (base + __popc(m & lt));
+      o[0] = CX[idx]; o[1] = CX[idx + N]; o[2] = CX[idx + 2 * N];
+    }
+    __syncwarp();
+  }
+}
+
 struct drfe_cape {
   int device = 0, max_batch = 0;
   drfe_cape_params prm{};
@@ -1400,6 +1473,9 @@ struct drfe_cape {
   StageTimer timer;
   ChunkPipe pipe;
   int* batch_nplanes = nullptr;  // host destination of the running batch call
+  float* d_plane_pts = nullptr;  // [B][H*W][3] per-plane point lists (allocated by the first drfe_cape_plane_points)
+  int* d_plane_offs = nullptr;   // [B][kMaxPlanes+1]
+  std::vector<int> h_plane_offs;
   int batch_plane_cap = 0;
   std::vector<void*> allocs;
 };
@@ -1801,6 +1877,44 @@ int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int p
   if (planes)
     for (int f = 0; f < nf; ++f)
       if (nr_planes[f] > plane_cap) { set_error("drfe_cape_download: frame %d has %d planes, plane_cap is %d", f, nr_planes[f], plane_cap); return DRFE_ERR_CAPACITY; }
+  return DRFE_OK;
+}
+
+int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
+  if (!h || !points || !offsets || plane_cap < 1) { set_error("drfe_cape_plane_points: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_cape_plane_points: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  const size_t N = (size_t)h->hd.H * h->hd.W;
+  if (!h->d_plane_pts) {
+    if (cape_alloc(h, &h->d_plane_pts, (size_t)h->max_batch * N * 3)) return DRFE_ERR_CUDA;
+    if (cape_alloc(h, &h->d_plane_offs, (size_t)h->max_batch * (kMaxPlanes + 1))) return DRFE_ERR_CUDA;
+    h->h_plane_offs.resize((size_t)h->max_batch * (kMaxPlanes + 1));
+    DRFE_CUDA(cudaFuncSetAttribute(k_cape_plane_points, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtsWarps * (kMaxPlanes + 1) * (int)sizeof(int)));
+  }
+  auto magic = [](unsigned d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };
+  DRFE_LAUNCH(k_cape_plane_points, nf, kPtsWarps * 32, kPtsWarps * (kMaxPlanes + 1) * sizeof(int), st, h->dd, 0, h->d_plane_pts, h->d_plane_offs,
+              magic((unsigned)h->hd.W), magic((unsigned)h->hd.cw), magic((unsigned)h->hd.ch));
+  int* ho = h->h_plane_offs.data();
+  DRFE_CUDA(cudaMemcpyAsync(ho, h->d_plane_offs, (size_t)nf * (kMaxPlanes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  std::vector<int> np(nf);
+  DRFE_CUDA(cudaMemcpyAsync(np.data(), h->hd.nplanes, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  for (int f = 0; f < nf; ++f) {
+    const int n = std::min(np[f], kMaxPlanes);
+    if (n > plane_cap) { set_error("drfe_cape_plane_points: frame %d has %d planes, plane_cap is %d", f, n, plane_cap); return DRFE_ERR_CAPACITY; }
+    const int* src = ho + (size_t)f * (kMaxPlanes + 1);
+    int* dst = offsets + (size_t)f * (plane_cap + 1);
+    for (int i = 0; i <= n; ++i) dst[i] = src[i];
+    for (int i = n + 1; i <= plane_cap; ++i) dst[i] = src[n];
+    if ((size_t)src[n] > cap_per_frame) { set_error("drfe_cape_plane_points: frame %d has %d plane points, cap_per_frame is %zu", f, src[n], cap_per_frame); return DRFE_ERR_CAPACITY; }
+    if (src[n] > 0)
+      DRFE_CUDA(cudaMemcpyAsync(points + (size_t)f * cap_per_frame * 3, h->d_plane_pts + (size_t)f * N * 3, (size_t)src[n] * 3 * sizeof(float),
+                                cudaMemcpyDeviceToHost, st));
+  }
+  DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }
 

@@ -71,7 +71,7 @@ SYMBOLS = [
     "drfe_cape_enqueue_depth_u16", "drfe_cape_process_depth_batch", "drfe_cape_finish_batch",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
-    "drfe_cape_get_grid_maps", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
+    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
 ]
 
 _lib = None
@@ -142,6 +142,7 @@ def lib():
     L.drfe_cape_get_cells.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_get_grid_maps.argtypes = [vp, C.c_int, vp, vp]
     L.drfe_cape_cylinders_found.argtypes = [vp, vp]
+    L.drfe_cape_plane_points.argtypes = [vp, vp, sz, vp, C.c_int]
     L.drfe_cape_get_cyl_maps.argtypes = [vp, C.c_int, vp, vp]
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
@@ -437,6 +438,16 @@ class CAPE:
                                               _ptr(planes), self.plane_cap, C.byref(npl), _ptr(cyls), self.cyl_cap,
                                               C.byref(ncyl)))
         return npl.value, ncyl.value, seg, planes[:npl.value].copy(), cyls[:self.cylinders_found()[0]].copy()
+
+    def plane_points(self, nframes=None, plane_cap=255):
+        """plane_cloud of PlaneDetection_CAPE::runPlaneDetection (PlaneExtractor.cpp:165-190) for the frames of the
+        last call: a list (per frame) of lists (per plane) of (n, 3) float32 arrays, pixels in row-major order."""
+        nf = nframes or max(getattr(self, "_nframes", 1) or 1, 1)
+        N = self.H * self.W
+        pts = np.zeros((nf, N, 3), np.float32)
+        offs = np.zeros((nf, plane_cap + 1), np.int32)
+        _check(self.L.drfe_cape_plane_points(self.h, _ptr(pts), N, _ptr(offs), plane_cap))
+        return pts, offs
 
     def cylinders_found(self):
         """length of cylinder_segments_final per frame of the last call (CAPE.cpp:434-445)"""

@@ -90,6 +90,15 @@ class CAPE {
     finish(nr_planes, seg_output, plane_segments_final);
     if (cylinder_segments_final) finish_cylinders(*cylinder_segments_final);
   }
+  // plane_cloud of PlaneDetection_CAPE (PlaneExtractor.cpp:165-190) for the frame just processed: xyz of plane p are
+  // points[3*offsets[p]] .. points[3*offsets[p+1]), gathered on the device (drfe_cape_plane_points)
+  void planePoints(std::vector<float>& points, std::vector<int>& offsets) {
+    const size_t N = (size_t)prm_.depth_height * prm_.depth_width;
+    points.resize(N * 3);
+    offsets.assign(kPlaneCap + 1, 0);
+    if (drfe_cape_plane_points(h_, points.data(), N, offsets.data(), kPlaneCap) != DRFE_OK)
+      throw std::runtime_error(std::string("CAPE::planePoints: ") + drfe_last_error());
+  }
   drfe_cape* handle() { return h_; }
 
  private:
@@ -151,22 +160,12 @@ class PlaneDetection_CAPE {
     }
     plane_detector->processDepth(depth_img.data, depth_img.step / sizeof(float), K_[0], K_[4], K_[2], K_[5], nr_planes,
                                  nr_cylinders, seg_output, plane_params, &cylinder_params);
-    // per-plane point lists (PlaneExtractor.cpp:165-190)
+    // per-plane point lists (PlaneExtractor.cpp:165-190), gathered on the device from seg_output and the cloud
+    plane_detector->planePoints(pts_, offs_);
     plane_cloud.assign(nr_planes, PointCloud());
-    for (int i = 0; i < rows; ++i) {
-      const uint8_t* s = seg_output.ptr(i);
-      const float* drow = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(depth_img.data) + (size_t)i * depth_img.step);
-      for (int j = 0; j < cols; ++j) {
-        const int code = s[j];
-        if (code > 0 && code <= nr_planes) {
-          const double z = (double)drow[j];
-          PointT p;
-          p.x = (float)(((double)j - K_[2]) * z / K_[0]);
-          p.y = (float)(((double)i - K_[5]) * z / K_[4]);
-          p.z = (float)z;
-          plane_cloud[code - 1].push_back(p);
-        }
-      }
+    for (int p = 0; p < nr_planes; ++p) {
+      const PointT* first = reinterpret_cast<const PointT*>(pts_.data()) + offs_[p];
+      plane_cloud[p].assign(first, first + (offs_[p + 1] - offs_[p]));
     }
   }
 
@@ -185,6 +184,8 @@ class PlaneDetection_CAPE {
 
  private:
   int det_rows_ = 0, det_cols_ = 0;
+  std::vector<float> pts_;
+  std::vector<int> offs_;
 };
 
 }  // namespace Planar_SLAM

@@ -238,6 +238,15 @@ int drfe_cape_finish_batch(drfe_cape* h);
  * cylinder found — drfe_cape_cylinders_found gives that list's length per frame. */
 int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int plane_cap,
                        int* nr_planes, drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders);
+/* The per-plane point lists PlaneDetection_CAPE::runPlaneDetection builds after CAPE::process
+ * (plane_cloud, PlaneExtractor.cpp:165-190; "next" row of SURVEY.md 8f): for every frame of the last
+ * batch, the cloud points (x, y, z) of the pixels whose seg_output code is 1..nr_planes, grouped by
+ * plane and in row-major pixel order inside a plane, gathered on the device so that the 3.7 MB cloud
+ * of a frame never has to cross PCIe.  points[(f*cap_per_frame + k)*3 ..]: plane p of frame f is
+ * k in [offsets[f*(plane_cap+1) + p], offsets[f*(plane_cap+1) + p + 1]).  Codes above nr_planes
+ * (cylinder labels) are not gathered: the reference indexes plane_cloud out of range for them. */
+int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, int* offsets,
+                           int plane_cap);
 int drfe_cape_cylinders_found(drfe_cape* h, int* counts); /* counts[f] = cylinder_segments_final.size() */
 int drfe_cape_sync(drfe_cape* h);
 void* drfe_cape_stream(drfe_cape* h);

@@ -283,6 +283,18 @@ class CapeOracle:
                                 C.byref(ncy))
         return seg, planes[:npl.value].copy()
 
+    def plane_points(self, cloud, seg, nr_planes):
+        """plane_cloud of PlaneDetection_CAPE::runPlaneDetection (reference src/PlaneExtractor.cpp:165-190): for every
+        pixel in row-major order whose seg_output code is > 0, its cloud point goes to plane_cloud[code - 1].
+        cloud: the cell-major organised cloud (organizePointCloudByCell, :80-99) — the un-organised cloud_array the
+        reference reads is the same points in image order.  Returns a list of (n, 3) float32 arrays."""
+        H, W, cw, ch = self.H, self.W, self.cw, self.ch
+        r, c = np.mgrid[0:H, 0:W]
+        idx = ((r // ch) * (W // cw) + (c // cw)) * (cw * ch) + (r % ch) * cw + (c % cw)     # cell_map, :135-148
+        xyz = np.asarray(cloud, np.float32).reshape(3, H * W)[:, idx.ravel()].T            # image order, (H*W, 3)
+        code = np.asarray(seg).ravel()
+        return [xyz[code == p + 1] for p in range(nr_planes)]
+
     def process_full(self, cloud, plane_cap=256, cyl_cap=64):
         """CAPE::process with cylinder detection: seg_output, planes, nr_cylinders_final and the
         cylinder_segments_final list (all cylinders found, CAPE.cpp:434-445)."""
