@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the pipelined e2e batch calls (0 = library default)")
     ap.add_argument("--workload", default="c640", choices=["c640", "c720"],
                     help="c640: the headline 640x480 / 1000 kp batch (default); c720: 1280x720 / 2000 kp / cylinders on")
     args = ap.parse_args()
@@ -305,8 +306,8 @@ def main():
 
     # the chunk-pipelined batch calls: per 32-frame chunk H2D | kernels | D2H on three streams per handle
     def step_e2e(dep, fac):
-        orb.extract_batch(h_gray, h_kps, h_desc, h_cnt)
-        cape.process_depth_batch(dep, *K, depth_factor=fac, seg=h_seg, planes=h_planes, nplanes=h_npl)
+        orb.extract_batch(h_gray, h_kps, h_desc, h_cnt, chunk_frames=args.chunk)
+        cape.process_depth_batch(dep, *K, depth_factor=fac, seg=h_seg, planes=h_planes, nplanes=h_npl, chunk_frames=args.chunk)
         orb.finish_batch()
         cape.finish_batch()
 
@@ -363,8 +364,9 @@ def main():
         traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "k_fast_strips is bound by the integer ALU pipe, not by HBM (ncu: alu pipe 67-72 %, dram 4 %; "
-                        "profiles/r01_d_*_full.txt); the HBM fraction is reported as the contract asks" if dom == "fast" else None,
+                "note": "k_fast_strips is bound by the half-rate integer ALU pipe, not by HBM (ncu: alu pipe ~70 %, dram 4 %, "
+                        "profiles/r01_*_full.txt; tools/ubench/pipes.cu); the HBM fraction is reported as the contract asks"
+                        if dom == "fast" else None,
                 "alg_bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms,
                 "whole_step": {"alg_bytes_per_frame": alg["total"],
                                "achieved": alg["total"] * BATCH * args.steps / (ms * 1e-3) / 1e9,
@@ -391,12 +393,16 @@ def main():
                    "cylinder_detection": CYL,
                    "l2": "inputs larger than L2 (%d MB of gray+depth per step per GPU, no flush needed)" % (BATCH * W * H * 5 // 1000000),
                    "sharding": "independent 256-frame batches per GPU, no collective"},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "drfe_orb_extract_batch + drfe_cape_process_depth_batch (float depth, pinned host "
-                "buffers, 32-frame chunks pipelined H2D | kernels | D2H)",
-                "raw_u16_depth": {"value": e2e_u16, "unit": "frames/s",
-                                  "h2d_bytes_per_step": int(h_gray.nbytes + h_depth16.nbytes),
-                                  "note": "same call fed the sensor's 16-bit depth, converted on the device (Frame.cc:113-115)"}},
+        # headline e2e: what Frame::Frame receives — the gray image and the sensor's raw 16-bit depth (imDepth is
+        # converted to float INSIDE the path, Frame.cc:113-115); the float-depth variant of the same call is kept beside it
+        "e2e": {"value": e2e_u16, "unit": "frames/s", "h2d_bytes_per_step": int(h_gray.nbytes + h_depth16.nbytes),
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "drfe_orb_extract_batch + drfe_cape_process_depth_batch (gray u8 + raw u16 depth as Frame::Frame gets "
+                       "them, depth scaled on the device as Frame.cc:113-115 does; pinned host buffers, 32-frame chunks "
+                       "pipelined H2D | kernels | D2H)",
+                "float_depth": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                                "note": "same call fed float depth (what PlaneDetection_CAPE::readDepthImage takes); "
+                                        "H2D-bound: 393 MB per step over PCIe"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
