@@ -116,6 +116,32 @@ def test_low_contrast_triggers_min_threshold_fallback(drfe, orc):
     assert (c0[:, 2] < 20).any() and (c0[:, 2] >= 20).any()               # both thresholds in play
 
 
+@pytest.mark.parametrize("kind", ["noise", "dots", "steps"])
+def test_dense_and_adversarial_corner_patterns(drfe, orc, kind):
+    """Patterns that stress the FAST stages: uniform noise (corners of both polarities everywhere, equal-score
+    neighbours, maxima on both sides of cell edges), isolated single-pixel dots on a ramp (many equal scores, each
+    cell's NMS decided by strictness), and intensity steps near the thresholds (|d| == t must not count)."""
+    rng = np.random.default_rng(11)
+    if kind == "noise":
+        img = rng.integers(0, 256, (480, 640)).astype(np.uint8)
+        img[:, 320:] = (img[:, 320:] // 8 + 100).astype(np.uint8)          # right half: amplitude 32, thresholds matter
+    elif kind == "dots":
+        img = np.tile((np.arange(640) // 5).astype(np.uint8), (480, 1))
+        ys, xs = rng.integers(20, 460, 4000), rng.integers(20, 620, 4000)
+        img[ys, xs] = np.where(rng.random(4000) < 0.5, 255, 0)
+    else:
+        img = np.full((480, 640), 100, np.uint8)
+        for k, d in enumerate((6, 7, 8, 19, 20, 21, 22, 40)):              # steps of exactly t-1, t, t+1 (t = 7, 20)
+            img[60 * k:60 * k + 30, :] = 100 + d
+            img[60 * k:60 * k + 30, ::17] = 100
+            img[60 * k + 5:60 * k + 30:7, 3::13] = 100 - d
+    ex = drfe.ORBextractor(1000, 1.2, 8, 20, 7)
+    kps, desc = ex(img)
+    rk, rd = check_frame_against_oracle(ex, orc.OrbOracle(1000), img, 0)
+    check_result(kps, desc, rk, rd)
+    assert len(kps) > 0
+
+
 def test_few_corners_sparse_quadtree(drfe, orc):
     """Far fewer candidates than nfeatures: every node ends with one key, nothing to drop."""
     img = np.full((480, 640), 100, np.uint8)
