@@ -48,8 +48,6 @@ struct LevelDev {
   int blur_nq;                      // 4-pixel columns of the blur kernel, ceil(w/4)
   uint32_t blur_magic;              // ceil(2^32 / blur_nq)
   uint32_t wcell_magic;             // ceil(2^32 / wCell): interior x -> cell column by __umulhi
-  uint32_t quads_magic;             // ceil(2^32 / quads), quads = ceil((w-38)/4): task -> row by __umulhi
-  uint32_t groups_magic;            // ceil(2^32 / groups), groups = ceil(quads/4): 16-pixel group task -> row
   float hX;
   int root_x[5];                    // root boundaries int(hX*i), i = 0..nIni (nIni <= 4)
   int cand_cap;
@@ -63,7 +61,12 @@ struct LevelDev {
 };
 
 struct PyrTile;
-struct StripDev { short level, y0, nrows, pad; };   // FAST strip: interior rows [y0, y0+nrows) of one cell row
+// FAST strip: interior rows [y0, y0+nrows) of one cell row, interior columns [x0, x0+xw).  Levels wider than
+// kFastSplitWidth are cut into segments of 16 cell columns (x0 is then a multiple of both the cell width and 16, which
+// keeps the TMA source and the 16-pixel compass groups 16-byte aligned), so that a CTA's shared memory stays near 70 KB
+// (3 CTAs per SM) whatever the image width; per-cell NMS makes segments independent.
+struct StripDev { short level, y0, nrows, x0, xw, pad; uint32_t groups_magic; };   // groups_magic = ceil(2^32 / groups)
+static const int kFastSplitWidth = 704, kFastSegCells = 16;
 static const int kMaxStripCells = 160;
 
 struct OrbDev {
@@ -468,15 +471,15 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   __syncthreads();
   // ---- 1. TMA: one bulk copy per image row
   {
-    const uint32_t row_bytes = (uint32_t)((L.w + 15) & ~15);
-    const uint8_t* src = roi_ptr(P, L, f) + (long long)(strip.y0 - 3) * L.pitch;
+    const uint32_t row_bytes = (uint32_t)((min(strip.xw + 2 * kEdge, L.w - strip.x0) + 15) & ~15);
+    const uint8_t* src = roi_ptr(P, L, f) + (long long)(strip.y0 - 3) * L.pitch + strip.x0;
     if (tid == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nrows + 6));
     for (int r = tid; r < nrows + 6; r += THREADS) bulk_g2s(tile + (size_t)r * TP, src + (long long)r * L.pitch, row_bytes, &s_bar);
   }
   // ---- 2. scores.  Score map: (nrows + 2) x TP4 words, one word = 4 pixels; word column 0 and
   // quads + 1 and rows 0 and nrows + 1 are zero guards (neighbours outside the strip belong to
   // other cells and count as 0).
-  const int iw = L.w - 2 * kEdge;            // interior width
+  const int iw = strip.xw;                   // interior width of this strip (segment)
   const int quads = (iw + 3) >> 2;
   const int TP4 = TP >> 2;
   const int wCell = L.wCell;
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       uint32_t fl = 0;
       int ry = 0, G = 0;
       if (task < ngtask) {
-        ry = (int)__umulhi((uint32_t)task, L.groups_magic);
+        ry = (int)__umulhi((uint32_t)task, strip.groups_magic);
         G = task - ry * groups;
         fl = fast_compass_group(tile32, TP4, ry, G, cadd);
         const int rem = quads - 4 * G;                          // quads of this group inside the row
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
     const uint32_t q = (ent >> 24) + P.min_th - 1;
     const int pos = base + i;
     if (pos < L.cand_cap)
-      out[pos] = ((ent & 0xFFF) + 3) | ((((ent >> 12) & 0xFFF) + oy) << 12) | (q << 24);
+      out[pos] = ((ent & 0xFFF) + 3 + strip.x0) | ((((ent >> 12) & 0xFFF) + oy) << 12) | (q << 24);
     else
       atomicOr(P.status, 1);
   }
@@ -1330,7 +1333,7 @@ static int orb_build(drfe_orb* h) {
   int max_pyr_src = 0, max_pyr_nsy = 0;
   std::vector<StripDev> strips;
   long long img_total = 0, blur_total = 0, cand_total = 0;
-  int lkp_total = 0, kp_cap = 0, max_strip_rows = 0;
+  int lkp_total = 0, kp_cap = 0, max_strip_rows = 0, max_strip_tp = 0;
   for (int l = 0; l < nl; ++l) {
     LevelDev& L = D.lv[l];
     L.w = cv_round_f((float)h->width * h->inv_scale[l]);
@@ -1426,20 +1429,25 @@ static int orb_build(drfe_orb* h) {
     // FAST strips: the interior rows [19 + i*hCell, min(19 + (i+1)*hCell, h-19)) of cell row i.
     // Cell (i, j) of the reference's grid (:789-829) evaluates FAST exactly on the pixels
     // [19 + j*wCell, ..) x [19 + i*hCell, ..) clipped to [19, w-19) x [19, h-19) (App. A.3b).
-    if (L.nCols > kMaxStripCells) { set_error("image too wide (%d FAST cell columns)", L.nCols); return DRFE_ERR_ARG; }
-    for (int i = 0; i < L.nRows; ++i) {
-      const int y0 = kEdge + i * L.hCell, y1 = std::min(y0 + L.hCell, L.h - kEdge);
-      if (y1 <= y0) continue;
-      strips.push_back(StripDev{(short)l, (short)y0, (short)(y1 - y0), 0});
-      max_strip_rows = std::max(max_strip_rows, y1 - y0);
-    }
     {
-      const unsigned quads = (unsigned)((L.w - 2 * kEdge + 3) / 4);
-      L.quads_magic = (uint32_t)(((1ull << 32) + quads - 1) / quads);
+      const int iw = L.w - 2 * kEdge;
+      const int seg_cells = iw > kFastSplitWidth ? kFastSegCells : L.nCols;
+      if (seg_cells > kMaxStripCells) { set_error("image too wide (%d FAST cell columns)", L.nCols); return DRFE_ERR_ARG; }
       L.wcell_magic = (uint32_t)(((1ull << 32) + L.wCell - 1) / L.wCell);
-      const unsigned groups = (quads + 3) / 4;
-      L.groups_magic = (uint32_t)(((1ull << 32) + groups - 1) / groups);
-      if (quads > 1023) { set_error("image too wide for the FAST strip kernel (%u quads per row)", quads); return DRFE_ERR_ARG; }
+      for (int i = 0; i < L.nRows; ++i) {
+        const int y0 = kEdge + i * L.hCell, y1 = std::min(y0 + L.hCell, L.h - kEdge);
+        if (y1 <= y0) continue;
+        for (int j0 = 0; j0 < L.nCols; j0 += seg_cells) {
+          const int x0 = j0 * L.wCell, x1 = std::min((j0 + seg_cells) * L.wCell, iw);
+          if (x1 <= x0) continue;
+          const unsigned quads = (unsigned)((x1 - x0 + 3) / 4), groups = (quads + 3) / 4;
+          if (quads > 1023) { set_error("image too wide for the FAST strip kernel (%u quads per row)", quads); return DRFE_ERR_ARG; }
+          strips.push_back(StripDev{(short)l, (short)y0, (short)(y1 - y0), (short)x0, (short)(x1 - x0), 0,
+                                    (uint32_t)(((1ull << 32) + groups - 1) / groups)});
+          max_strip_rows = std::max(max_strip_rows, y1 - y0);
+          max_strip_tp = std::max(max_strip_tp, (std::min(x1 - x0 + 2 * kEdge, L.w - x0) + 15) / 16 * 16);
+        }
+      }
     }
     L.blur_nq = (L.w + 3) / 4;
     L.blur_magic = (uint32_t)(((1ull << 32) + L.blur_nq - 1) / L.blur_nq);
@@ -1451,7 +1459,7 @@ static int orb_build(drfe_orb* h) {
   h->nstrips = (int)strips.size();
   D.cand_fstride = cand_total; D.lkp_fstride = lkp_total; D.kp_cap = kp_cap; h->max_lkp = 0;
   for (int l = 0; l < nl; ++l) h->max_lkp = std::max(h->max_lkp, D.lv[l].node_cap);
-  D.fast_tp = (D.lv[0].w + 15) / 16 * 16;         // smem row pitch of a FAST strip (TMA rows are 16 B multiples)
+  D.fast_tp = max_strip_tp;                       // smem row pitch of a FAST strip (TMA rows are 16 B multiples)
   D.fast_rows = max_strip_rows;
   if (max_strip_rows > 63) { set_error("FAST strip of %d rows (queue entries hold 6 row bits)", max_strip_rows); return DRFE_ERR_ARG; }
   {

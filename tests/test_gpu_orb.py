@@ -48,7 +48,8 @@ def check_result(kps, desc, rk, rd):
     (640, 480, 800, 2, 20260031),       # Realsense.yaml uses 800 features
     (320, 240, 500, 0, 20260005),
     (1280, 720, 2000, 2, 20260140),     # configs[4] geometry (2 quadtree roots)
-    (752, 480, 1200, 1, 20260009),      # non-4:3 aspect, odd level sizes
+    (752, 480, 1200, 1, 20260009),      # non-4:3 aspect, odd level sizes; level 0 is cut into two FAST segments
+    (1920, 1080, 3000, 1, 20260201),    # wide levels: up to four 16-cell FAST segments per cell row
 ])
 def test_orb_stage_parity(drfe, orc, w, h, nfeat, scene, seed):
     gray, _, _ = drfe.synth_frame(w, h, scene, seed)
