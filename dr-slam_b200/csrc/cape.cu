@@ -854,13 +854,20 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
       if (ncand < 5) break;                                  // Checkpoint 1 (:120)
       // candidate cells in ascending order
       {
+        // four words of cells per round: the bin loads are issued together, ahead of the ballots and list stores
         int base = 0;
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-          const int c = c0 + lane;
-          const bool is = c < nc && bin[c] == best_bin;
-          const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
-          if (is) list[base + __popc(bal & ((1u << lane) - 1))] = c;
-          base += __popc(bal);
+        const unsigned lt = (1u << lane) - 1u;
+        for (int c0 = 0; c0 < nc; c0 += 128) {
+          short bv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const int c = c0 + 32 * k + lane; bv[k] = c < nc ? bin[c] : (short)-2; }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool is = bv[k] == best_bin;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, is);
+            if (is) list[base + __popc(bal & lt)] = c0 + 32 * k + lane;
+            base += __popc(bal);
+          }
         }
       }
       __syncwarp();
