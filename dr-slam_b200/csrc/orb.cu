@@ -32,8 +32,10 @@ static const int kEdge = 19;     // EDGE_THRESHOLD (ORBextractor.cc:74)
 static const int kXOff = 32;     // byte offset of ROI column 0 inside a bordered row
 static const int kHalfPatch = 15;
 
-__constant__ __align__(16) int8_t c_pattern[1024];
 __constant__ int c_umax[16];
+// the rBRIEF pattern as floats (x0,y0,x1,y1) per test, entry t*32 + j = test t of descriptor byte j: lane j's t-th
+// load is one coalesced 16-byte word per lane, served by L1 (4 KB, shared by every warp of the SM)
+__device__ float4 g_pattern_f4[256];
 static const int8_t h_pattern[1024] = {
 #include "../../include/drfe_orb_pattern.inc"
 };
@@ -1023,10 +1025,6 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 static const int kDescWarps = 8;
 static const int kPatchRows = 2 * kEdge + 1, kPatchW4 = 11;   // 39 rows x 44 bytes (39 columns + alignment slack)
 __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp, int f0) {
-  // rBRIEF pattern in shared memory as floats (x0,y0,x1,y1) per test, laid out so that lane j's
-  // t-th test sits at entry t*32 + j (conflict-free 16-byte loads); constant memory would
-  // serialise the lane-divergent index
-  __shared__ float4 s_pat[256];
   __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchW4];
   const OrbDev& P = *Pp;
   const int level = blockIdx.y, f = blockIdx.z + f0;
@@ -1040,13 +1038,6 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
     P.out_cnt[f] = min(tot, P.kp_cap);
   }
   if ((int)blockIdx.x * kDescWarps >= nk) return;           // whole CTA idle
-  {
-    const int t = threadIdx.x;                                // test index = 8*byte + bit
-    const uint32_t pw = reinterpret_cast<const uint32_t*>(c_pattern)[t];
-    s_pat[(t & 7) * 32 + (t >> 3)] = make_float4((float)(int8_t)(pw & 0xFF), (float)(int8_t)((pw >> 8) & 0xFF),
-                                                 (float)(int8_t)((pw >> 16) & 0xFF), (float)(int8_t)(pw >> 24));
-  }
-  __syncthreads();
   const int i = blockIdx.x * kDescWarps + wid;
   if (i >= nk) return;
   int base = 0;
@@ -1111,7 +1102,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   int val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 pw = s_pat[j * 32 + lane];
+    const float4 pw = __ldg(&g_pattern_f4[j * 32 + lane]);
     const float x0 = pw.x, y0 = pw.y, x1 = pw.z, y1 = pw.w;
     const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
@@ -1517,8 +1508,13 @@ static int orb_build(drfe_orb* h) {
   DRFE_CUDA(cudaMemset(D.status, 0, sizeof(int)));
   if (dev_alloc(h, &h->dd, 1)) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(h->dd, &D, sizeof(D), cudaMemcpyHostToDevice));
-  DRFE_CUDA(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
   DRFE_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+  {
+    std::vector<float4> pf(256);
+    for (int t = 0; t < 256; ++t)      // test index t = 8*byte + bit -> entry bit*32 + byte
+      pf[(t & 7) * 32 + (t >> 3)] = make_float4((float)h_pattern[4 * t], (float)h_pattern[4 * t + 1], (float)h_pattern[4 * t + 2], (float)h_pattern[4 * t + 3]);
+    DRFE_CUDA(cudaMemcpyToSymbol(g_pattern_f4, pf.data(), sizeof(float4) * 256));
+  }
   DRFE_CUDA(cudaFuncSetAttribute(k_fast_strips<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
   DRFE_CUDA(cudaFuncSetAttribute(k_quadtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->quad_smem));
   if (h->timer.create()) return DRFE_ERR_CUDA;
