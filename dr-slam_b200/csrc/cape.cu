@@ -1023,6 +1023,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     job_label[j] = ps.score > 100 ? 1 : 0;                   // it is a plane (:163)
   }
   __syncthreads();
+  if (tid == 0 && P.dbg) P.dbg[(long long)f * 16 + 12] = clock64();   // after accumulate + fit of the jobs
   // ---- extruded regions (cylinder_detection, CAPE.cpp:179-216): a region of more than 5 cells that is not
   // a plane goes through CylinderSeg; regions are taken in job order because they share one rand() stream.
   CylSub* subs = CYL ? P.subs + (long long)f * P.max_sub : nullptr;
@@ -1046,6 +1047,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     }
     __syncthreads();
   }
+  if (tid == 0 && P.dbg) P.dbg[(long long)f * 16 + 13] = clock64();   // after the cylinder jobs
   // ---- labels in the reference's push order: job by job; an extruded job contributes its sub-segments
   if (tid == 0) {
     int np = 0, ncyl = 0;
@@ -1088,6 +1090,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     if (CYL) P.cyl_map[(long long)f * nc + c] = cl;
   }
   __syncthreads();
+  if (tid == 0 && P.dbg) P.dbg[(long long)f * 16 + 14] = clock64();   // after labelling
   // ---- plane merging (CAPE.cpp:220-252; getConnectedComponents :459-481)
   const int np = s_np;
   for (int c = tid; c < nc; c += THREADS) {

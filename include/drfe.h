@@ -271,7 +271,8 @@ int drfe_cape_get_grid_maps(drfe_cape* h, int frame, int32_t* plane_map, uint8_t
 int drfe_cape_get_cyl_maps(drfe_cape* h, int frame, int32_t* cyl_map, uint8_t* cyl_eroded_map);
 /* diagnostics of the grid stage of one frame: [0] seeds, [1] growth sweeps, [2] sum of candidates,
  * [3] sum of activated cells, [4..8] cycles in bin search+list / seed scan / growth / accumulate /
- * fit+label, [9] clock after set-up, [10] clock at the end */
+ * fit+label, [9] clock after set-up, [10] clock at the end, [11] after the seed loop, [12] after the jobs'
+ * accumulate + fit, [13] after the cylinder jobs, [14] after labelling */
 int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16);
 int drfe_cape_set_profiling(drfe_cape* h, int on);
 int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages);

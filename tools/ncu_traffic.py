@@ -21,6 +21,7 @@ def main():
         rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
         hdr, units = rows[0], rows[1]
         kn, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        ia = hdr.index("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
         for d in rows[2:]:
             name = d[kn].split("(")[0].replace("void ", "").replace("drfe::", "")
             base = name.split("<")[0]
@@ -32,6 +33,7 @@ def main():
             s["dram_bytes"] += b
             s["ncu_time_us"] += t
             s["launches"] += 1
+            s["alu_pipe_pct"] = max(s.get("alu_pipe_pct", 0.0), float(d[ia].replace(",", "")))
     json.dump({"source": note, "stages": stages}, open(out, "w"), indent=1)
     print(json.dumps(stages, indent=1))
 

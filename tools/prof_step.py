@@ -67,7 +67,9 @@ def main():
         dbg = np.stack([cape.debug_counters(i) for i in range(min(B, 32))])
         names = ["seeds", "sweeps", "sum_ncand", "sum_nact", "cyc_argmax_list", "cyc_scan", "cyc_grow", "cyc_accum", "cyc_fit"]
         print("grid stage per frame (mean over %d frames): " % len(dbg) + ", ".join("%s %.0f" % (n, dbg[:, i].mean()) for i, n in enumerate(names)) +
-              ", cyc_tail %.0f" % (dbg[:, 10] - dbg[:, 9] - dbg[:, 4:9].sum(1)).mean())
+              ", cyc_tail %.0f" % (dbg[:, 10] - dbg[:, 9] - dbg[:, 4:9].sum(1)).mean() +
+              " (jobs %.0f, cylinders %.0f, labels %.0f, merge..end %.0f)" % ((dbg[:, 12] - dbg[:, 11]).mean(), (dbg[:, 13] - dbg[:, 12]).mean(),
+                                                                           (dbg[:, 14] - dbg[:, 13]).mean(), (dbg[:, 10] - dbg[:, 14]).mean()))
     tot = sum(res.values())
     print("stage ms per %d-frame batch (serialised): " % B + ", ".join("%s %.3f" % kv for kv in res.items()) +
           " | total %.3f ms => %.0f frames/s" % (tot, B / tot * 1e3))
