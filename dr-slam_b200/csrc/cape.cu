@@ -1251,63 +1251,60 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
   uint8_t* out = P.seg + (long long)f * N + (long long)(cr * P.ch) * P.W + cc * cw;
   const int er = P.eroded_map[(long long)f * P.ncells + cell];
   const int cer = CYL ? P.cyl_eroded_map[(long long)f * P.ncells + cell] : 0;
-  // planes whose dilated-minus-eroded mask contains this cell (bit p of bits[] = final plane p)
-  const int nw = (P.ncells + 31) >> 5, npl = P.nplanes[f];
-  const uint32_t* bvec = P.border_vec + (long long)f * P.border_rows * nw + (cell >> 5);
-  uint32_t bits[8], cbits[8];
-  uint32_t anyb = 0, anyc = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { bits[k] = 0; cbits[k] = 0; }
-  for (int p0 = 1; p0 <= npl; p0 += 32) {
-    const int p = p0 + lane;
-    const bool in = p <= npl && ((bvec[(long long)p * nw] >> (cell & 31)) & 1u);
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);     // bit j = plane p0 + j
-    // planes p0 .. p0+31 straddle words (p0 >> 5) and (p0 >> 5) + 1 of bits[] (p0 = 1 mod 32)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k == (p0 >> 5)) bits[k] |= bal << 1;
-      if (k == (p0 >> 5) + 1) bits[k] |= bal >> 31;
-    }
-    anyb |= bal;
-  }
-  if (CYL) {
-    const int ncf = P.ncyl_final[f];
-    const uint32_t* cvec = bvec + (long long)(kMaxPlanes + 1) * nw;
-    for (int p0 = 1; p0 <= ncf; p0 += 32) {
-      const int p = p0 + lane;
-      const bool in = p <= ncf && ((cvec[(long long)p * nw] >> (cell & 31)) & 1u);
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (k == (p0 >> 5)) cbits[k] |= bal << 1;
-        if (k == (p0 >> 5) + 1) cbits[k] |= bal >> 31;
-      }
-      anyc |= bal;
-    }
-  }
-  // cells inside an eroded plane mask are painted whole, then cells inside an eroded cylinder mask (:410-416)
-  const int whole = er > 0 ? er : (cer > 0 ? cer : ((anyb | anyc) == 0 ? 0 : -1));
   // a cell row is cw bytes; with cw and W multiples of 4 everything below moves 4 pixels per lane and access
   const bool vec4 = ((cw | P.W) & 3) == 0;
   const int q4 = cw >> 2;
-  if (whole >= 0) {
-    if (vec4) {
+  const uint32_t q4_magic = (65536u + (uint32_t)q4 - 1u) / (uint32_t)max(q4, 1);   // j / q4 == (j * magic) >> 16 for j < 2^16 / q4
+  auto paint = [&](int whole) {
+    if (vec4 && npc < 8192) {
       const uint32_t word = (uint32_t)whole * 0x01010101u;
       for (int j = lane; j < (npc >> 2); j += 32) {
-        const int lr = j / q4, c4 = j - lr * q4;
+        const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
         *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = word;
       }
     } else {
       for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)whole; }
     }
-    return;
+  };
+  // cells inside an eroded plane mask are painted whole, then cells inside an eroded cylinder mask (:410-416): the
+  // common case, decided before anything else is read
+  if (er > 0) { paint(er); return; }
+  if (CYL && cer > 0) { paint(cer); return; }
+  // planes whose dilated-minus-eroded mask contains this cell: bit b of bits[m] = final plane 32*m + b + 1
+  const int nw = (P.ncells + 31) >> 5, npl = P.nplanes[f];
+  const uint32_t* bvec = P.border_vec + (long long)f * P.border_rows * nw + (cell >> 5);
+  uint32_t bits[8], cbits[8];
+  uint32_t anyb = 0, anyc = 0;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    bits[m] = 0; cbits[m] = 0;
+    if (32 * m < npl) {                                          // warp-uniform
+      const int p = 32 * m + lane + 1;
+      const bool in = p <= npl && ((bvec[(long long)p * nw] >> (cell & 31)) & 1u);
+      bits[m] = __ballot_sync(0xFFFFFFFFu, in);
+      anyb |= bits[m];
+    }
   }
+  if (CYL) {
+    const int ncf = P.ncyl_final[f];
+    const uint32_t* cvec = bvec + (long long)(kMaxPlanes + 1) * nw;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      if (32 * m < ncf) {
+        const int p = 32 * m + lane + 1;
+        const bool in = p <= ncf && ((cvec[(long long)p * nw] >> (cell & 31)) & 1u);
+        cbits[m] = __ballot_sync(0xFFFFFFFFu, in);
+        anyc |= cbits[m];
+      }
+    }
+  }
+  if ((anyb | anyc) == 0) { paint(0); return; }
   const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
   const float* CY = CX + N;
   const float* CZ = CY + N;
   const float4* eq = P.plane_eq + (long long)f * (kMaxPlanes + 1);
   const float* maxd = P.plane_maxd + (long long)f * (kMaxPlanes + 1);
-  if (!CYL && vec4 && (npc & 3) == 0) {
+  if (!CYL && vec4 && (npc & 3) == 0 && npc < 8192) {
     // planes only: 4 pixels per lane, float4 loads of the cell-major cloud, one word store
     const float4* X4 = reinterpret_cast<const float4*>(CX);
     const float4* Y4 = reinterpret_cast<const float4*>(CY);
@@ -1323,7 +1320,7 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
       for (int k = 0; k < 8; ++k) {
         uint32_t b = bits[k];
         while (b) {
-          const int p = k * 32 + __ffs(b) - 1;
+          const int p = k * 32 + __ffs(b);
           b &= b - 1;
           const float4 e = eq[p];
           const float md = maxd[p];
@@ -1335,7 +1332,7 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
           }
         }
       }
-      const int lr = j / q4, c4 = j - lr * q4;
+      const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
       *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = lab;
     }
     return;
@@ -1348,7 +1345,7 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
     for (int k = 0; k < 8; ++k) {
       uint32_t b = bits[k];
       while (b) {
-        const int p = k * 32 + __ffs(b) - 1;
+        const int p = k * 32 + __ffs(b);
         b &= b - 1;
         const float4 e = eq[p];
         const float v = x * e.x + y * e.y + z * e.z + e.w;
@@ -1363,7 +1360,7 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
       for (int k = 0; k < 8; ++k) {
         uint32_t b = cbits[k];
         while (b) {
-          const int p = k * 32 + __ffs(b) - 1;
+          const int p = k * 32 + __ffs(b);
           b &= b - 1;
           const CylEq& e = ceq[p];
           const float q0 = x - e.p2[0], q1 = y - e.p2[1], q2 = z - e.p2[2];
