@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "drfe_internal.h"
@@ -304,36 +305,51 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
     int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
     // (double)j - cx and (double)i - cy of the element, stepped along with (lr, lc): sums of small half-integers, exact
     double dcol = col0 + (double)lc, drow = row0 + (double)lr;
-    for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
-#pragma unroll
-      for (int u = 0; u < kSumsChunk; ++u) {
-        const int i = i0 + 16 * u;
-        if (i < npc) {
-          float x, y;
-          const float z = s_z[i];
-          if (FROM_DEPTH) {
-            // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
-            // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
-            const double zd = (double)z;
-            const double tx = dcol * zd, ty = drow * zd;
-            const double qx = tx * rfx, qy = ty * rfy;
-            if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
-            else { x = (float)qx; y = (float)qy; }
-            CX[i] = x; CY[i] = y; CZ[i] = z;
-          } else {
-            x = CX[i]; y = CY[i];
-          }
-          cnt += (z > 0.f);
-          if (i < body) {
-            if (i < 16) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
-            else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
-                   axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
-          } else if (i < full8) {
-            ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
-          }
+    // one element: FIRST = the lane's first element (it starts the accumulators), CHECKED = bounds tests needed
+    auto element = [&](int i, auto first_tag, auto checked_tag) {
+      constexpr bool FIRST = decltype(first_tag)::value, CHECKED = decltype(checked_tag)::value;
+      if (!CHECKED || i < npc) {
+        float x, y;
+        const float z = s_z[i];
+        if (FROM_DEPTH) {
+          // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
+          // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
+          const double zd = (double)z;
+          const double tx = dcol * zd, ty = drow * zd;
+          const double qx = tx * rfx, qy = ty * rfy;
+          if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
+          else { x = (float)qx; y = (float)qy; }
+          CX[i] = x; CY[i] = y; CZ[i] = z;
+        } else {
+          x = CX[i]; y = CY[i];
         }
-        lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
-        if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
+        cnt += (z > 0.f);
+        if (!CHECKED || i < body) {
+          if (CHECKED ? i < 16 : FIRST) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
+          else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
+                 axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
+        } else if (i < full8) {
+          ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
+        }
+      }
+      lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
+      if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
+    };
+    if (CELL == 20) {
+      // 400 = 5 x 5 x 16 elements: every lane owns exactly 25, no bounds tests; the first round is peeled because it
+      // starts the accumulators
+      element(l, std::true_type(), std::false_type());
+#pragma unroll
+      for (int u = 1; u < kSumsChunk; ++u) element(l + 16 * u, std::false_type(), std::false_type());
+#pragma unroll 1
+      for (int i0 = l + 16 * kSumsChunk; i0 < 400; i0 += 16 * kSumsChunk) {
+#pragma unroll
+        for (int u = 0; u < kSumsChunk; ++u) element(i0 + 16 * u, std::false_type(), std::false_type());
+      }
+    } else {
+      for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
+#pragma unroll
+        for (int u = 0; u < kSumsChunk; ++u) element(i0 + 16 * u, std::false_type(), std::true_type());
       }
     }
 #pragma unroll
@@ -344,20 +360,51 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
           szz = tree16(azz, has_extra, mask, ezz), sxy = tree16(axy, has_extra, mask, exy),
           sxz = tree16(axz, has_extra, mask, exz), syz = tree16(ayz, has_extra, mask, eyz);
     __syncwarp(mask);                                         // s_z and the cloud are complete
-    // depth-jump scans through the middle row (lane 0) and the middle column (lane 1)
+    // depth-jump scans through the middle row and the middle column (PlaneSeg.cpp:36-76): z_last follows the valid
+    // depths as long as consecutive valid ones differ by < 100; a valid depth further away is a jump and leaves z_last
+    // alone.  Without jumps z_last is simply the previous valid depth, so the 16 lanes first test every element
+    // against its previous valid one (found in a ballot mask); only a group that sees a violation replays the scan
+    // sequentially (lane 0: row, lane 1: column) to count the jumps.
     int jumps = 0;
-    if (l < 2) {
+    {
       const int chh = npc / cw;
-      int i, j, step;
-      float z_last;
-      if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_last = fmaxf(s_z[i], s_z[i + 1]); }
-      else { i = cw / 2; j = npc - i; step = cw; z_last = fmaxf(s_z[i], s_z[i + cw]); }
-      i += step;
-      while (i < j) {
-        const float z = s_z[i];
-        if (z > 0 && fabsf(z - z_last) < 100.0f) z_last = z;   // == (double)|dz| < 100.0: 100 is a float
-        else if (z > 0) ++jumps;
+      const int shift = threadIdx.x & 16;                     // this group's half of a ballot
+      bool fail = false;
+      if (cw <= 32 && chh <= 32) {
+#pragma unroll
+        for (int sc = 0; sc < 2; ++sc) {
+          const int base = sc == 0 ? cw * (chh / 2) : cw / 2, step = sc == 0 ? 1 : cw, n = sc == 0 ? cw : chh;
+          const float za = l < n ? s_z[base + l * step] : 0.f, zb = l + 16 < n ? s_z[base + (l + 16) * step] : 0.f;
+          const uint32_t va = (__ballot_sync(mask, za > 0.f) >> shift) & 0xFFFFu, vb = (__ballot_sync(mask, zb > 0.f) >> shift) & 0xFFFFu;
+          const uint32_t valid = va | (vb << 16);
+          const float z_init = fmaxf(s_z[base], s_z[base + step]);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int k = l + 16 * h2;
+            const float z = h2 ? zb : za;
+            if (k >= 1 && z > 0.f) {
+              const uint32_t before = valid & ((1u << k) - 2u);   // valid elements 1 .. k-1
+              const float zp = before ? s_z[base + (31 - __clz(before)) * step] : z_init;
+              fail |= !(fabsf(z - zp) < 100.0f);                   // == (double)|dz| < 100.0: 100 is a float
+            }
+          }
+        }
+      } else {
+        fail = true;
+      }
+      const bool group_fail = ((__ballot_sync(mask, fail) >> shift) & 0xFFFFu) != 0;
+      if (group_fail && l < 2) {
+        int i, j, step;
+        float z_last;
+        if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_last = fmaxf(s_z[i], s_z[i + 1]); }
+        else { i = cw / 2; j = npc - i; step = cw; z_last = fmaxf(s_z[i], s_z[i + cw]); }
         i += step;
+        while (i < j) {
+          const float z = s_z[i];
+          if (z > 0 && fabsf(z - z_last) < 100.0f) z_last = z;
+          else if (z > 0) ++jumps;
+          i += step;
+        }
       }
     }
     const int jumps_v = __shfl_down_sync(mask, jumps, 1, 16);

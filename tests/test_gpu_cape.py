@@ -63,6 +63,25 @@ def test_cape_parity(drfe, orc, w, h, scene, seed, unit, cell, mmd):
     cp.close()
 
 
+def test_size_not_a_multiple_of_the_cell(drfe, orc):
+    """CAPE truncates to whole cells (`w / cell`, CAPE.cpp:18-19): the pixels right of / below the last full cell are
+    never labelled, everything else is as on the cropped image."""
+    _, depth, K = drfe.synth_frame(656, 490, 1, 20260005, 1000.0)          # 32 x 24 full cells + a 16 x 10 px margin
+    cp = drfe.CAPE(490, 656, 20, 20, False, MC, 50.0)
+    npl, _, seg, planes, _ = cp.process_depth(depth, *K)
+    o = orc.CapeOracle(490, 656, 20, 20, False, MC, 50.0)
+    oseg, oplanes = o.process(o.depth_to_cloud(depth, *K))
+    assert npl == len(oplanes) > 0 and np.array_equal(seg, oseg)
+    assert not seg[480:].any() and not seg[:, 640:].any()
+    check_planes(planes, oplanes)
+    # batch of 3 with the paint / margin path, against the single-frame results
+    cp3 = drfe.CAPE(490, 656, 20, 20, False, MC, 50.0, max_batch=3)
+    d3 = np.stack([depth, depth[::-1].copy(), depth])
+    cp3.enqueue_depth(d3, *K, nframes=3)
+    seg3 = cp3.download()[0]
+    assert np.array_equal(seg3[0], seg) and np.array_equal(seg3[2], seg)
+
+
 def test_process_cloud_entry_equals_depth_entry(drfe, orc):
     """CAPE::process(cloud_array, ...) boundary: same result as the fused depth entry."""
     _, depth, K = drfe.synth_frame(640, 480, 1, 20260055, 1000.0)
