@@ -32,6 +32,17 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
       if (T == 11) { asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); }
       if (T == 12) { if (i & 1) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); else a[i] = __vimax3_u16x2(a[i], b[i], b[(i + 1) % CHAINS]); }
       if (T == 13) { asm volatile("max.bf16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); }
+      if (T == 14) a[i] = __dp4a(a[i], b[i], a[i]);
+      if (T == 15) a[i] = __dp2a_lo(a[i], b[i], a[i]);
+      if (T == 16) a[i] = __umulhi(a[i], b[i]) + 1u;
+      if (T == 17) { if (i & 1) a[i] = __dp4a(a[i], b[i], a[i]); else a[i] = __vimax3_u16x2(a[i], b[i], b[(i + 1) % CHAINS]); }
+      if (T == 18) { if (i & 1) a[i] = __dp4a(a[i], b[i], a[i]); else a[i] = a[i] * 3 + b[i]; }
+      if (T == 19) { float x = __uint_as_float(a[i]), y = __uint_as_float(b[i]); a[i] = __float_as_uint(__fmaf_rn(x, y, x)); }
+      if (T == 20) { if (i & 1) { float x = __uint_as_float(a[i]), y = __uint_as_float(b[i]); a[i] = __float_as_uint(__fmaf_rn(x, y, x)); } else a[i] = __vimax3_u16x2(a[i], b[i], b[(i + 1) % CHAINS]); }
+      if (T == 21) a[i] = (a[i] << 3) + b[i];            // LEA
+      if (T == 22) a[i] = __popc(a[i]) + b[i];
+      if (T == 23) a[i] = (uint32_t)__float2int_rn(__uint_as_float(a[i])) + b[i];
+      if (T == 24) { if (i & 1) { float x = __uint_as_float(a[i]), y = __uint_as_float(b[i]); a[i] = __float_as_uint(__fmaf_rn(x, y, x)); } else a[i] = a[i] * 3 + b[i]; }
     }
   }
   uint32_t s = 0;
@@ -71,5 +82,16 @@ int main() {
   run<11>("max.f16x2 asm", 1);
   run<12>("VIMNMX3 / max.f16x2 alternating", 1);
   run<13>("max.bf16x2 asm", 1);
+  run<14>("IDP.4A", 1);
+  run<15>("IDP.2A", 1);
+  run<16>("IMAD.HI (+IADD)", 2);
+  run<17>("VIMNMX3 / IDP.4A alternating", 1);
+  run<18>("IMAD / IDP.4A alternating", 1);
+  run<19>("FFMA", 1);
+  run<20>("VIMNMX3 / FFMA alternating", 1);
+  run<21>("LEA (shift-add)", 1);
+  run<22>("POPC + IADD", 2);
+  run<23>("F2I + IADD", 2);
+  run<24>("IMAD / FFMA alternating", 1);
   return 0;
 }
