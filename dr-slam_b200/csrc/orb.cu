@@ -1099,23 +1099,16 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   }
   __syncwarp();
   const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch) + kEdge * (kPatchW4 * 4) + ox + kEdge;   // patch centre
-  // 32-bit shared address of the patch centre minus the rounding bias of (row, column); all address arithmetic wraps
-  const uint32_t pcm = smem_u32(pc) - 0x4B400000u * (uint32_t)(kPatchW4 * 4 + 1);
-  auto patch_at = [](uint32_t addr) -> int { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return (int)v; };
   int val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 pw = __ldg(&g_pattern_f4[j * 32 + lane]);
     const float x0 = pw.x, y0 = pw.y, x1 = pw.z, y1 = pw.w;
-    // cvRound (round half to even) of the steered coordinates without F2I, which issues at about a quarter of the
-    // FADD rate (tools/ubench/pipes.cu): v + 1.5 * 2^23 leaves round(v) in the low mantissa bits, and the constant
-    // 0x4B400000 of both coordinates folds into the patch address
-    const float kMagic = 12582912.f;
-    const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)), kMagic));
-    const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)), kMagic));
-    const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)), kMagic));
-    const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)), kMagic));
-    const int t0 = patch_at(pcm + (uint32_t)r0 * (uint32_t)(kPatchW4 * 4) + (uint32_t)c0), t1 = patch_at(pcm + (uint32_t)r1 * (uint32_t)(kPatchW4 * 4) + (uint32_t)c1);
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = pc[r0 * (kPatchW4 * 4) + c0], t1 = pc[r1 * (kPatchW4 * 4) + c1];
     val |= (t0 < t1) << j;
   }
   const int o = base + i;
