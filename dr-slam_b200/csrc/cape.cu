@@ -1105,8 +1105,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     };
     for (int j = 0; j < njobs; ++j) {
       if (job_label[j]) { job_label[j] = (uint8_t)next_plane(); continue; }
-      if (!CYL) continue;
-      for (int s = job_sub0[j]; s < job_sub0[j + 1]; ++s) {
+      for (int s = CYL ? job_sub0[j] : 0, s_end = CYL ? job_sub0[j + 1] : 0; s < s_end; ++s) {
         if (!subs[s].is_cyl) {
           const int l = next_plane();
           subs[s].label = l;

@@ -1639,7 +1639,6 @@ int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_s
   DeviceScope ds(h->device);
   if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
   cudaStream_t st = h->stream;
-  const OrbDev& D = h->hd;
   const uint8_t* src = gray;
   long long rs = (long long)row_stride, fs = (long long)frame_stride;
   h->timer.begin(st);
