@@ -1044,6 +1044,24 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   for (int l = 0; l < level; ++l) base += cnts[l];
   const uint32_t e = P.lkp[(long long)f * P.lkp_fstride + L.kp_off + i];
   const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;   // cvRound of integral coords
+  // The 39x39 blurred patch around the keypoint (|rotated pattern coordinate| <= 18 < EDGE_THRESHOLD) does not depend
+  // on the angle: it goes to shared memory by 4-byte cp.async (LDGSTS: no registers held, no separate shared store),
+  // issued here so that the copy is in flight while IC_Angle and the angle's sine/cosine are computed.
+  uint32_t* patch = s_patch[wid];
+  const int xb = (cx - kEdge) & ~3, ox = (cx - kEdge) - xb;
+  {
+    const uint8_t* bsrc = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)(cy - kEdge) * L.bpitch + xb;
+    const uint32_t pdst = smem_u32(patch);
+#pragma unroll
+    for (int k = 0; k < (kPatchRows * kPatchW4 + 31) / 32; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < kPatchRows * kPatchW4) {
+        const int r = idx / kPatchW4, wc = idx - r * kPatchW4;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pdst + 4u * (uint32_t)idx), "l"(bsrc + r * L.bpitch + 4 * wc) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   // ---- IC_Angle: moments over the radius-15 disc.  Lane l owns column u = l - 15; the disc is
   // symmetric (|u| <= umax[|v|] <=> |v| <= umax[|u|]), so the lane's row range is a constant.
   const uint8_t* img = roi_ptr(P, L, f) + (long long)cy * L.pitch + cx;
@@ -1081,22 +1099,9 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
   angle = __shfl_sync(0xFFFFFFFFu, angle, 0);
   a = __shfl_sync(0xFFFFFFFFu, a, 0);
   b = __shfl_sync(0xFFFFFFFFu, b, 0);
-  // ---- rBRIEF: lane j computes descriptor byte j (8 tests).  The 39x39 blurred patch around
-  // the keypoint (|rotated pattern coordinate| <= 18 < EDGE_THRESHOLD) is staged in shared
-  // memory with aligned word loads; the 512 steered samples are then shared-memory gathers.
-  uint32_t* patch = s_patch[wid];
-  const int xb = (cx - kEdge) & ~3, ox = (cx - kEdge) - xb;
-  {
-    const uint8_t* bsrc = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)(cy - kEdge) * L.bpitch + xb;
-#pragma unroll
-    for (int k = 0; k < (kPatchRows * kPatchW4 + 31) / 32; ++k) {
-      const int idx = lane + 32 * k;
-      if (idx < kPatchRows * kPatchW4) {
-        const int r = idx / kPatchW4, wc = idx - r * kPatchW4;
-        patch[idx] = __ldg(reinterpret_cast<const uint32_t*>(bsrc + r * L.bpitch) + wc);
-      }
-    }
-  }
+  // ---- rBRIEF: lane j computes descriptor byte j (8 tests); the 512 steered samples are shared-memory gathers
+  // from the patch whose asynchronous copy was started before IC_Angle.
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch) + kEdge * (kPatchW4 * 4) + ox + kEdge;   // patch centre
   int val = 0;
