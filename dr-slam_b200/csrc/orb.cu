@@ -548,17 +548,35 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       if (fl & 8u) queue[base + n0 + n1 + n2 + __popc(b3 & lt_mask)] = (unsigned short)(ent + 3);
     }
   };
-  // scores of the queued quads -> score map, all lanes busy
-  auto eval_queue = [&]() {
+  // scores of the queued quads -> score map, all lanes busy.  Every warp owns a contiguous chunk of the queue and
+  // compacts it in place while it goes: only quads holding a score above the pass threshold (e > kth in some byte)
+  // stay, so that the NMS pass below visits about half as many quads (a quad passing the compass test holds a
+  // FAST(iniTh) corner in 47 % of the cases).  Returns the number of entries this warp kept.
+  const int wid = tid >> 5;
+  auto eval_queue = [&](uint32_t kth) -> int {
     const int nq = s_nq;
-    for (int qi = tid; qi < nq; qi += THREADS) {
-      const int task = queue[qi];
-      const int ry = task >> 10, g = task & 1023;
-      uint32_t packed = fast_eval_quad(tile32, TP4, ry, g, kmin8);
-      const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
-      if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
-      score32[(ry + 1) * TP4 + g + 1] = packed;
+    const int chunk = (((nq + (THREADS >> 5) - 1) / (THREADS >> 5)) + 31) & ~31;
+    const int q0 = wid * chunk, q1 = min(q0 + chunk, nq);
+    const uint32_t cadd = (127u - min(kth, 127u)) * 0x01010101u;   // byte > kth  <=>  bit 7 of (a | ((a & 0x7f) + 127 - kth))
+    int wp = q0;
+    for (int qb = q0; qb < q1; qb += 32) {
+      const int qi = qb + lane;
+      uint32_t packed = 0;
+      int task = 0;
+      if (qi < q1) {
+        task = queue[qi];
+        const int ry = task >> 10, g = task & 1023;
+        packed = fast_eval_quad(tile32, TP4, ry, g, kmin8);
+        const int rem = iw - 4 * g;                              // pixels of this quad inside the interior
+        if (rem < 4) packed &= 0xFFFFFFFFu >> (8 * (4 - rem));
+        score32[(ry + 1) * TP4 + g + 1] = packed;
+      }
+      const bool stay = ((packed | ((packed & 0x7F7F7F7Fu) + cadd)) & 0x80808080u) != 0;
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, stay);     // (every lane has read its entry: the ballot orders it)
+      if (stay) queue[wp + __popc(bal & lt_mask)] = (unsigned short)task;
+      wp += __popc(bal);
     }
+    return wp - q0;
   };
   // ---- 3. per-cell non-maximum suppression: strict maximum over the 8 neighbours, branch-free.  Scores are
   // compared as u16 lanes whose HIGH byte is the pixel of interest and whose low byte is whatever byte precedes
@@ -590,13 +608,15 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   // Kept maxima -> list.  FAST(iniThFAST) maxima mark their cell; FAST(minThFAST) maxima are taken only in cells
   // that have none (the fallback applies to the pixel's own cell, ORBextractor.cc:812-816).  List slots come from
   // one ballot + one shared atomic per warp and round.
-  auto nms_queue = [&](uint32_t kth, bool fallback) {
+  auto nms_queue = [&](uint32_t kth, bool fallback, int kept) {
     const int nq = s_nq;
-    for (int qi0 = tid - lane; qi0 < nq; qi0 += THREADS) {
-      const int qi = qi0 + lane;
+    const int chunk = (((nq + (THREADS >> 5) - 1) / (THREADS >> 5)) + 31) & ~31;
+    const int q0 = wid * chunk, q1 = q0 + kept;                 // this warp's compacted entries
+    for (int qb = q0; qb < q1; qb += 32) {
+      const int qi = qb + lane;
       uint32_t surv = 0, c0 = 0;
       int ry = 0, g = 0;
-      if (qi < nq) {
+      if (qi < q1) {
         const int task = queue[qi];
         ry = task >> 10; g = task & 1023;
         surv = nms_quad(ry, g, kth);
@@ -640,9 +660,9 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   // ---- pass 0: what FAST(iniThFAST) returns
   build_queue(P.ini_th, [](int, uint32_t fl) { return fl; });
   __syncthreads();
-  eval_queue();
+  const int kept0 = eval_queue(kini);
   __syncthreads();
-  nms_queue(kini, false);
+  nms_queue(kini, false, kept0);
   __syncthreads();
   // ---- pass 1: cells where FAST(iniThFAST) found nothing get the maxima of FAST(minThFAST)
   {
@@ -667,9 +687,9 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
       __syncthreads();
       build_queue(P.min_th, needs);
       __syncthreads();
-      eval_queue();
+      const int kept1 = eval_queue(0u);
       __syncthreads();
-      nms_queue(0u, true);
+      nms_queue(0u, true, kept1);
     }
   }
   __syncthreads();
