@@ -973,17 +973,25 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
 // One thread = a 4-pixel-wide column of kBlurRows output rows: per input row three aligned
 // words, the horizontal pass as two u8 dot products (IDP.4A) per pixel, the vertical pass over
 // a 7-row register window.  No shared memory: neighbouring threads hit the same L1 lines.
-static const int kBlurRows = 16;
-__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int (&h)[4]) {
+// rows per thread: measured 0.286 / 0.220 / 0.246 / 0.268 ms per 256 frames for 4 / 8 / 16 / 32 — the kernel is bound by
+// load latency (long-scoreboard stalls), so more, shorter threads win over fewer redundant row filters
+static const int kBlurRows = 8, kBlurAhead = 2;
+struct BlurRow { uint32_t a, b, c; };                                   // columns x-4 .. x+7 of one source row
+__device__ __forceinline__ BlurRow blur_load(const uint8_t* __restrict__ row) {
   const uint32_t* p = reinterpret_cast<const uint32_t*>(row);
-  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);     // columns x-4 .. x+7
+  BlurRow w;
+  w.a = __ldg(p); w.b = __ldg(p + 1); w.c = __ldg(p + 2);
+  return w;
+}
+__device__ __forceinline__ void blur_hfilter(const BlurRow& w, int (&h)[4]) {
   const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);    // taps -3..0
   const uint32_t k1 = 48u | (34u << 8) | (18u << 16);                  // taps +1..+3
-  h[0] = __dp4a(__funnelshift_r(b, c, 8), k1, __dp4a(__funnelshift_r(a, b, 8), k0, 0u));
-  h[1] = __dp4a(__funnelshift_r(b, c, 16), k1, __dp4a(__funnelshift_r(a, b, 16), k0, 0u));
-  h[2] = __dp4a(__funnelshift_r(b, c, 24), k1, __dp4a(__funnelshift_r(a, b, 24), k0, 0u));
-  h[3] = __dp4a(c, k1, __dp4a(b, k0, 0u));
+  h[0] = __dp4a(__funnelshift_r(w.b, w.c, 8), k1, __dp4a(__funnelshift_r(w.a, w.b, 8), k0, 0u));
+  h[1] = __dp4a(__funnelshift_r(w.b, w.c, 16), k1, __dp4a(__funnelshift_r(w.a, w.b, 16), k0, 0u));
+  h[2] = __dp4a(__funnelshift_r(w.b, w.c, 24), k1, __dp4a(__funnelshift_r(w.a, w.b, 24), k0, 0u));
+  h[3] = __dp4a(w.c, k1, __dp4a(w.b, k0, 0u));
 }
+__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int (&h)[4]) { blur_hfilter(blur_load(row), h); }
 
 __global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp, int f0) {
   const OrbDev& P = *Pp;
@@ -1004,10 +1012,17 @@ __global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp, int
   int h[7][4];
 #pragma unroll
   for (int r = 0; r < 6; ++r) blur_hrow(src + (long long)r * L.pitch, h[r]);
+  // the rows to come are loaded kBlurAhead steps before they are filtered (the kernel was waiting on its loads: 9.6
+  // warps per issue slot stalled on the long scoreboard).  Rows past the strip are inside the 19-px border frame or the
+  // spare row of the level buffer, so the prefetch needs no bounds test.
+  BlurRow nx[kBlurAhead];
+#pragma unroll
+  for (int k = 0; k < kBlurAhead; ++k) nx[k] = blur_load(src + (long long)(6 + k) * L.pitch);
 #pragma unroll
   for (int r = 0; r < kBlurRows; ++r) {
     if (r < nrows) {
-      blur_hrow(src + (long long)(r + 6) * L.pitch, h[(r + 6) % 7]);
+      blur_hfilter(nx[r % kBlurAhead], h[(r + 6) % 7]);
+      if (r + kBlurAhead < nrows) nx[r % kBlurAhead] = blur_load(src + (long long)(r + 6 + kBlurAhead) * L.pitch);
       uint32_t o = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
