@@ -433,44 +433,58 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
 // widened to double, fitPlane, the depth-dependent MSE test, and the cell's merge tolerance
 // (CAPE.cpp:69-73).
 __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  // the 152-byte PlaneSeg records of the block's 128 cells leave through shared memory as full 16-byte words of
+  // consecutive addresses (a struct store per thread touched 32 lines per instruction)
+  __shared__ __align__(16) drfe_plane s_out[128];
+  static_assert(sizeof(drfe_plane) % 8 == 0, "drfe_plane is moved as 8-byte words");
   const CapeDev& P = *Pp;
   const int gid0 = blockIdx.x * 128 + threadIdx.x;
-  if (gid0 >= nframes * P.ncells) return;
-  const int gid = gid0 + f0 * P.ncells;
-  const int f = gid / P.ncells, cell = gid - f * P.ncells;
-  const int npc = P.npc;
-  CellSums in;
-  {
-    const float4* srcv = reinterpret_cast<const float4*>(P.sums + (long long)gid);
-    float4* d = reinterpret_cast<float4*>(&in);
-    d[0] = srcv[0]; d[1] = srcv[1]; d[2] = srcv[2];
-  }
-  drfe_plane s;
-  memset(&s, 0, sizeof(s));                        // zero-filled PlaneSeg storage (App. B.2)
-  s.min_nr_pts = npc / 2;
-  s.nr_pts = in.cnt;
-  s.planar = in.planar;
-  float tol = 0.f;
-  if (s.planar) {
-    s.x_acc = in.s[0]; s.y_acc = in.s[1]; s.z_acc = in.s[2]; s.xx_acc = in.s[3]; s.yy_acc = in.s[4]; s.zz_acc = in.s[5];
-    s.xy_acc = in.s[6]; s.xz_acc = in.s[7]; s.yz_acc = in.s[8];
-    fit_plane(s);
-    const double lim = 0.000001425 * s.mean[2] * s.mean[2] + 10.0;   // Params.h:6-7
-    if ((double)s.MSE > lim * lim) s.planar = 0;
-    if (s.planar) {  // cell_distance_tols (CAPE.cpp:69-73)
-      const long long N = (long long)P.H * P.W;
-      const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
-      const float* CY = CX + N;
-      const float* CZ = CY + N;
-      const float dx = CX[npc - 1] - CX[0], dy = CY[npc - 1] - CY[0], dz = CZ[npc - 1] - CZ[0];
-      const float diam = sqrtf(dx * dx + dy * dy + dz * dz);
-      const float sin_merge = (float)sqrt(1.0 - (double)P.min_cos * (double)P.min_cos);
-      const float t = fminf(fmaxf(diam * sin_merge, 20.0f), P.max_merge_dist);
-      tol = t * t;
+  const int total = nframes * P.ncells;
+  if (gid0 < total) {
+    const int gid = gid0 + f0 * P.ncells;
+    const int f = gid / P.ncells, cell = gid - f * P.ncells;
+    const int npc = P.npc;
+    CellSums in;
+    {
+      const float4* srcv = reinterpret_cast<const float4*>(P.sums + (long long)gid);
+      float4* d = reinterpret_cast<float4*>(&in);
+      d[0] = srcv[0]; d[1] = srcv[1]; d[2] = srcv[2];
     }
+    drfe_plane s;
+    memset(&s, 0, sizeof(s));                        // zero-filled PlaneSeg storage (App. B.2)
+    s.min_nr_pts = npc / 2;
+    s.nr_pts = in.cnt;
+    s.planar = in.planar;
+    float tol = 0.f;
+    if (s.planar) {
+      s.x_acc = in.s[0]; s.y_acc = in.s[1]; s.z_acc = in.s[2]; s.xx_acc = in.s[3]; s.yy_acc = in.s[4]; s.zz_acc = in.s[5];
+      s.xy_acc = in.s[6]; s.xz_acc = in.s[7]; s.yz_acc = in.s[8];
+      fit_plane(s);
+      const double lim = 0.000001425 * s.mean[2] * s.mean[2] + 10.0;   // Params.h:6-7
+      if ((double)s.MSE > lim * lim) s.planar = 0;
+      if (s.planar) {  // cell_distance_tols (CAPE.cpp:69-73)
+        const long long N = (long long)P.H * P.W;
+        const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+        const float* CY = CX + N;
+        const float* CZ = CY + N;
+        const float dx = CX[npc - 1] - CX[0], dy = CY[npc - 1] - CY[0], dz = CZ[npc - 1] - CZ[0];
+        const float diam = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float sin_merge = (float)sqrt(1.0 - (double)P.min_cos * (double)P.min_cos);
+        const float t = fminf(fmaxf(diam * sin_merge, 20.0f), P.max_merge_dist);
+        tol = t * t;
+      }
+    }
+    s_out[threadIdx.x] = s;
+    P.tols[gid] = tol;
   }
-  P.cells[gid] = s;
-  P.tols[gid] = tol;
+  __syncthreads();
+  {
+    const int nvalid = min(128, total - (int)blockIdx.x * 128);
+    const int nwords = nvalid * (int)(sizeof(drfe_plane) / 8);
+    const uint2* src = reinterpret_cast<const uint2*>(s_out);
+    uint2* dst = reinterpret_cast<uint2*>(P.cells + ((long long)blockIdx.x * 128 + (long long)f0 * P.ncells));
+    for (int i = threadIdx.x; i < nwords; i += 128) dst[i] = src[i];
+  }
 }
 
 // ------------------------------------------------------------------ grid stage
