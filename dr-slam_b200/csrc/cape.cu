@@ -819,7 +819,10 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
   const drfe_plane* cells = P.cells + (long long)f * nc;
   const float* tols = P.tols + (long long)f * nc;
   drfe_plane* segs = P.segs + (long long)f * (kMaxPlanes + 1);
-  for (int i = tid; i < kHistBins * kHistBins; i += THREADS) hist[i] = 0;
+  // first / last cell that ever fell into each bin: cells only leave a bin, so the candidate scan of a seed can stay
+  // inside [first, last] (a plane's cells are spatially compact) and stop once it has found the histogram's count
+  __shared__ int s_bfirst[kHistBins * kHistBins], s_blast[kHistBins * kHistBins];
+  for (int i = tid; i < kHistBins * kHistBins; i += THREADS) { hist[i] = 0; s_bfirst[i] = 0x7FFFFFFF; s_blast[i] = -1; }
   for (int i = tid; i < 256 * 8; i += THREADS) assoc[i] = 0;
   if (tid == 0) { s_np = 0; s_njobs = 0; }
   __syncthreads();
@@ -854,6 +857,8 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
         if (xq > 0) yq = (int)((kHistBins - 1) * (atan2(nx / pn, ny / pn) - (-3.14)) / (3.14 - (-3.14)));
         b = yq * kHistBins + xq;
         atomicAdd(&hist[b], 1);
+        atomicMin(&s_bfirst[b], c);
+        atomicMax(&s_blast[b], c);
         // can this cell be activated from neighbour p (RegionGrowing called with p's normal and d)?
         const double tol = (double)tols[c];
         auto edge = [&](int p) -> bool {
@@ -918,7 +923,8 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
         // four words of cells per round: the bin loads are issued together, ahead of the ballots and list stores
         int base = 0;
         const unsigned lt = (1u << lane) - 1u;
-        for (int c0 = 0; c0 < nc; c0 += 128) {
+        const int c_end = s_blast[best_bin] + 1;
+        for (int c0 = s_bfirst[best_bin] & ~31; c0 < c_end && base < ncand; c0 += 128) {
           short bv[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) { const int c = c0 + 32 * k + lane; bv[k] = c < nc ? bin[c] : (short)-2; }
@@ -1051,24 +1057,59 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 #undef DRFE_TICK
   }
   __syncthreads();
-  // ---- jobs: new_ps = *Grid[seed], then expandSegment(Grid[i]) for every activated i in ascending
-  // order (the seed is counted twice, :134,146-149).  One thread per (job, sum).
   const int njobs = s_njobs;
   double* jobacc = P.jobacc + (long long)f * P.max_jobs * 10;
   drfe_plane* jobseg = P.jobseg + (long long)f * P.max_jobs;
   const bool sums_smem = P.grid_sums_smem != 0;
+  // The cells of every job, ascending, one job after the other (counting sort by job: job_nact[] are the counts), so
+  // that a job's sums visit its own cells only.  list[] and mse[] are free between the seed loop and the cylinder stage.
+  int* jcell = list;                                          // [sum of job_nact]
+  int* job_off = reinterpret_cast<int*>(mse);                 // [njobs + 1]
+  int* job_cur = job_off + njobs + 1;                         // [njobs] fill positions
+  if (wid == 0) {
+    const unsigned lt = (1u << lane) - 1u;
+    int run = 0;
+    for (int j0 = 0; j0 < njobs; j0 += 32) {
+      const int j = j0 + lane;
+      const int v = j < njobs ? (int)job_nact[j] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+      if (j < njobs) { job_off[j] = run + inc - v; job_cur[j] = run + inc - v; }
+      run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+    if (lane == 0) job_off[njobs] = run;
+    __syncwarp();
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+      const int c = c0 + lane;
+      const int j = c < nc ? (int)jobid[c] : 0xFFFF;
+      const bool has = j != 0xFFFF;
+      const unsigned act = __ballot_sync(0xFFFFFFFFu, has);
+      if (has) {
+        const unsigned m = __match_any_sync(act, j);          // lanes of this word in the same job
+        const int leader = __ffs(m) - 1;
+        int pos = 0;
+        if (lane == leader) { pos = job_cur[j]; job_cur[j] = pos + __popc(m); }
+        pos = __shfl_sync(m, pos, leader);
+        jcell[pos + __popc(m & lt)] = c;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- jobs: new_ps = *Grid[seed], then expandSegment(Grid[i]) for every activated i in ascending
+  // order (the seed is counted twice, :134,146-149).  One thread per (job, sum).
   for (int t = tid; t < njobs * 10; t += THREADS) {
     const int j = t / 10, k = t - j * 10;
     const drfe_plane& sd = cells[job_seed[j]];
+    const int i0 = job_off[j], i1 = job_off[j + 1];
     if (k < 9) {
       double acc = (&sd.x_acc)[k];
-      for (int c = 0; c < nc; ++c)
-        if (jobid[c] == j) acc += sums_smem ? (double)sums[c * 9 + k] : (&cells[c].x_acc)[k];
+      for (int i = i0; i < i1; ++i) { const int c = jcell[i]; acc += sums_smem ? (double)sums[c * 9 + k] : (&cells[c].x_acc)[k]; }
       jobacc[j * 10 + k] = acc;
     } else {
       int acc = sd.nr_pts;
-      for (int c = 0; c < nc; ++c)
-        if (jobid[c] == j) acc += npts[c];
+      for (int i = i0; i < i1; ++i) acc += npts[jcell[i]];
       jobacc[j * 10 + 9] = (double)acc;
     }
   }
