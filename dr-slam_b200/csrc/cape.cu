@@ -27,6 +27,9 @@ static const int kMaxPlanes = 255;       // labels are uchar (CAPE.cpp:286)
 static const int kHistBins = 20;
 
 struct CellSums;
+// MSE, normal-histogram bin (-1: not planar), planar flag and bits 0..3 = the cell can be activated from its left / right /
+// upper / lower neighbour
+struct CellMeta { float mse; short bin; uint8_t edge, planar; };
 struct CapeDev {
   int H, W, cw, ch, ncx, ncy, ncells, npc, B;
   float min_cos, max_merge_dist;
@@ -36,6 +39,7 @@ struct CapeDev {
   float* cloud;                 // [B][3][H*W] cell-major
   drfe_plane* cells;            // [B][ncells]
   float* tols;                  // [B][ncells]
+  struct CellMeta* cell_meta;   // [B][ncells] what the grid stage reads of every cell (k_cape_edges)
   int* plane_map;               // [B][ncells]
   uint8_t* eroded_map;          // [B][ncells]
   uint32_t* border_vec;         // [B][kMaxPlanes+1][ceil(ncells/32)] bit c of row p: cell c is in mask_diff of final plane p (1-based)
@@ -487,6 +491,49 @@ __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp
   }
 }
 
+// k_cape_edges: one thread per cell, after k_cape_fit — what the grid stage needs of every cell besides its plane:
+// the bin of the normal histogram (CAPE.cpp:82-101, Histogram.cpp:15-43: double acos / atan2) and whether
+// RegionGrowing (CAPE.cpp:485-506) would activate the cell from each of its four neighbours.  Both depend on the
+// cell and its neighbours only, so they are computed here by 196 k threads instead of by the grid stage's 128.
+__global__ void __launch_bounds__(128) k_cape_edges(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  const CapeDev& P = *Pp;
+  const int gid0 = blockIdx.x * 128 + threadIdx.x;
+  if (gid0 >= nframes * P.ncells) return;
+  const int gid = gid0 + f0 * P.ncells;
+  const int f = gid / P.ncells, c = gid - f * P.ncells;
+  const int ncx = P.ncx, ncy = P.ncy;
+  const int y = c / ncx, x = c - y * ncx;
+  const drfe_plane* cells = P.cells + (long long)f * P.ncells;
+  const drfe_plane& g = cells[c];
+  int b = -1;
+  unsigned e = 0;
+  if (g.planar != 0) {
+    const double min_cos = (double)P.min_cos;
+    const double nx = g.normal[0], ny = g.normal[1], nz = g.normal[2];
+    const double mx = g.mean[0], my = g.mean[1], mz = g.mean[2];
+    const double pn = sqrt(nx * nx + ny * ny);
+    const double polar = acos(-nz);
+    const int xq = (int)((kHistBins - 1) * (polar - 0.0) / (3.14 - 0.0));
+    int yq = 0;
+    if (xq > 0) yq = (int)((kHistBins - 1) * (atan2(nx / pn, ny / pn) - (-3.14)) / (3.14 - (-3.14)));
+    b = yq * kHistBins + xq;
+    // can this cell be activated from neighbour p (RegionGrowing called with p's normal and d)?
+    const double tol = (double)P.tols[gid];
+    auto edge = [&](int p) -> bool {
+      const drfe_plane& a = cells[p];
+      const double dist = a.normal[0] * mx + a.normal[1] * my + a.normal[2] * mz + a.d;
+      return !(a.normal[0] * nx + a.normal[1] * ny + a.normal[2] * nz < min_cos || dist * dist > tol);
+    };
+    if (x > 0 && edge(c - 1)) e |= 1u;
+    if (x + 1 < ncx && edge(c + 1)) e |= 2u;
+    if (y > 0 && edge(c - ncx)) e |= 4u;
+    if (y + 1 < ncy && edge(c + ncx)) e |= 8u;
+  }
+  CellMeta m;
+  m.mse = g.MSE; m.bin = (short)b; m.edge = (uint8_t)e; m.planar = g.planar != 0 ? 1 : 0;
+  *reinterpret_cast<uint2*>(P.cell_meta + gid) = *reinterpret_cast<const uint2*>(&m);
+}
+
 // ------------------------------------------------------------------ grid stage
 // CAPE::process between the per-cell fits and the per-pixel refinement (CAPE.cpp:82-291), one
 // CTA per frame.  The cell grid is handled as bit vectors (bit c = cell c, 32 cells per word):
@@ -835,41 +882,28 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
     int y = 0, x = 0;
     if (valid) {
       y = c / ncx; x = c - y * ncx;
-      const drfe_plane& g = cells[c];
-      planar = g.planar != 0;
-      mse[c] = g.MSE;
-      npts[c] = g.nr_pts;
+      // everything the loop below needs of a cell comes from two compact records: CellMeta (k_cape_edges) and the
+      // moment sums of k_cape_sums, which are the PlaneSeg sums of every planar cell (floats, widened exactly)
+      CellMeta meta;
+      *reinterpret_cast<uint2*>(&meta) = *reinterpret_cast<const uint2*>(P.cell_meta + (long long)f * nc + c);
+      const float4* sv = reinterpret_cast<const float4*>(P.sums + (long long)f * nc + c);
+      const float4 s0 = sv[0], s1 = sv[1], s2 = sv[2];          // s[0..8], cnt, planar-so-far, pad
+      planar = meta.planar != 0;
+      mse[c] = meta.mse;
+      npts[c] = __float_as_int(s2.y);
       pmap[c] = 0;
       jobid[c] = 0xFFFF;
       if (P.grid_sums_smem) {
-        const double* sp = &g.x_acc;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) sums[c * 9 + k] = (float)sp[k];     // exact: the sums are floats widened to double
+        float* d = sums + c * 9;
+        d[0] = s0.x; d[1] = s0.y; d[2] = s0.z; d[3] = s0.w; d[4] = s1.x; d[5] = s1.y; d[6] = s1.z; d[7] = s1.w; d[8] = s2.x;
       }
-      int b = -1;
+      const int b = meta.bin;
       if (planar) {
-        const double nx = g.normal[0], ny = g.normal[1], nz = g.normal[2];
-        const double mx = g.mean[0], my = g.mean[1], mz = g.mean[2];
-        const double pn = sqrt(nx * nx + ny * ny);
-        const double polar = acos(-nz);
-        const int xq = (int)((kHistBins - 1) * (polar - 0.0) / (3.14 - 0.0));
-        int yq = 0;
-        if (xq > 0) yq = (int)((kHistBins - 1) * (atan2(nx / pn, ny / pn) - (-3.14)) / (3.14 - (-3.14)));
-        b = yq * kHistBins + xq;
+        const unsigned e = meta.edge;
         atomicAdd(&hist[b], 1);
         atomicMin(&s_bfirst[b], c);
         atomicMax(&s_blast[b], c);
-        // can this cell be activated from neighbour p (RegionGrowing called with p's normal and d)?
-        const double tol = (double)tols[c];
-        auto edge = [&](int p) -> bool {
-          const drfe_plane& a = cells[p];
-          const double dist = a.normal[0] * mx + a.normal[1] * my + a.normal[2] * mz + a.d;
-          return !(a.normal[0] * nx + a.normal[1] * ny + a.normal[2] * nz < min_cos || dist * dist > tol);
-        };
-        if (x > 0) fl = edge(c - 1);
-        if (x + 1 < ncx) fr = edge(c + 1);
-        if (y > 0) fu = edge(c - ncx);
-        if (y + 1 < ncy) fd = edge(c + ncx);
+        fl = e & 1u; fr = e & 2u; fu = e & 4u; fd = e & 8u;
       }
       bin[c] = (short)b;
     }
@@ -1649,6 +1683,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.cloud, 3 * N * B);
   rc |= cape_alloc(h, &D.cells, nc * B);
   rc |= cape_alloc(h, &D.tols, nc * B);
+  rc |= cape_alloc(h, &D.cell_meta, nc * B);
   rc |= cape_alloc(h, &D.sums, nc * B);
   rc |= cape_alloc(h, &D.dbg, 16 * B);
   D.max_jobs = (int)nc / 4 + 1;
@@ -1764,6 +1799,7 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
 #undef DRFE_SUMS
   if (timed) h->timer.mark("cells", st);
   DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
+  DRFE_LAUNCH(k_cape_edges, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
   if (timed) h->timer.mark("fit", st);
   if (h->hd.cyl) DRFE_LAUNCH((k_cape_grid<128, true>), n, 128, h->grid_smem, st, h->dd, f0);
   else DRFE_LAUNCH((k_cape_grid<128, false>), n, 128, h->grid_smem, st, h->dd, f0);
