@@ -44,3 +44,39 @@ def test_cpp_adapters_match_oracle(drfe, orc, scene, seed):
     for i, line in enumerate(out.stdout.splitlines()[1:]):
         v = [float(x) for x in re.findall(r"-?\d+\.\d+", line)]
         assert np.allclose(v[:3], oplanes["normal"][i], atol=1e-5) and abs(v[3] - oplanes["d"][i]) < 1e-5
+
+
+def test_handles_are_usable_from_fresh_host_threads(drfe, orc):
+    """Frame::Frame starts a new std::thread per frame for ExtractORB and for the plane extractor (Frame.cc:124-134):
+    handles created on one thread must work from any other, ORB and CAPE at the same time, with the same results."""
+    import threading
+    MC = float(np.float32(np.cos(np.pi / 12)))
+    frames = [drfe.synth_frame(640, 480, i % 3, 20260300 + i) for i in range(6)]
+    K = frames[0][2]
+    ex = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480)
+    cp = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0)
+    want = []
+    for g, d, _ in frames:                                  # sequential, this thread
+        kps, desc = ex(g, None)
+        npl, _, seg, planes, _ = cp.process_depth(d, *K)
+        want.append((kps.copy(), desc.copy(), npl, seg.copy()))
+    got = [None] * len(frames)
+    for i, (g, d, _) in enumerate(frames):                  # one fresh thread per frame and extractor, as Frame does
+        out = {}
+
+        def run_orb():
+            out["orb"] = ex(g, None)
+
+        def run_cape():
+            out["cape"] = cp.process_depth(d, *K)
+
+        ts = [threading.Thread(target=run_orb), threading.Thread(target=run_cape)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        got[i] = out
+    for w, o in zip(want, got):
+        kps, desc = o["orb"]
+        assert all(np.array_equal(kps[n], w[0][n]) for n in kps.dtype.names) and np.array_equal(desc, w[1])
+        assert o["cape"][0] == w[2] and np.array_equal(o["cape"][2], w[3])
