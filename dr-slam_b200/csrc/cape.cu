@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
       dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2];
     }
     // the scans are done with this slot (the shuffle above is after them in every lane): refill it
+    __syncwarp(mask);
     if (vec1 && c + 2 < ncell_here) prefetch(c + 2);
   }
 }
