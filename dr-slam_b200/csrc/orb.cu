@@ -1261,6 +1261,90 @@ __global__ void __launch_bounds__(256) k_frame_post(const OrbDev* __restrict__ P
   }
 }
 
+// ------------------------------------------------------------------ descriptor search by projection
+// The data-parallel core of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:69-116) on
+// the device-resident results of drfe_orb_frame_post: for every query (a projected map point) the keypoints
+// Frame::GetFeaturesInArea returns (Frame.cc:730-779: grid cells x-major, push_back order inside a cell, level and
+// |dx|,|dy| < r filters), minus occupied ones and those failing the right-coordinate test, ranked by
+// ORBmatcher::DescriptorDistance (:1712-1728) into best / second best with the reference's strict '<' updates.
+// The ratio test and the in-order assignment F.mvpMapPoints[bestIdx] = pMP stay with the caller.
+// One CTA per frame: the cell offsets (prefix sum of the cell counts) go to shared memory, then a thread per query.
+struct SearchDev {
+  const drfe_proj_query* q; const uint8_t* qdesc; const uint8_t* occupied; const int* nq; drfe_proj_match* out; int qcap;
+};
+__global__ void __launch_bounds__(256) k_search_projection(const OrbDev* __restrict__ Pp, PostDev Q, SearchDev S) {
+  __shared__ unsigned short s_off[kGridCells + 1];
+  __shared__ int s_part[256];
+  const OrbDev& P = *Pp;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const uint16_t* gc = Q.grid_count + (long long)f * kGridCells;
+  {
+    // exclusive prefix sum of the 3072 cell counts: 12 cells per thread, then a scan of the 256 partial sums
+    constexpr int PER = kGridCells / 256;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += gc[tid * PER + k]; }
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int i = 0; i < 256; ++i) { const int t = s_part[i]; s_part[i] = run; run += t; } s_off[kGridCells] = (unsigned short)run; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) s_off[tid * PER + k] = (unsigned short)(s_part[tid] + loc[k]);
+    __syncthreads();
+  }
+  const drfe_frame_params& prm = Q.prm;
+  const float inv_w = __fdiv_rn((float)DRFE_FRAME_GRID_COLS, __fsub_rn(prm.max_x, prm.min_x));
+  const float inv_h = __fdiv_rn((float)DRFE_FRAME_GRID_ROWS, __fsub_rn(prm.max_y, prm.min_y));
+  const drfe_keypoint* ku = Q.keys_un + (long long)f * P.kp_cap;
+  const float* ur = Q.u_right + (long long)f * P.kp_cap;
+  const uint16_t* gi = Q.grid_index + (long long)f * P.kp_cap;
+  const uint32_t* desc = reinterpret_cast<const uint32_t*>(P.out_desc + (long long)f * P.kp_cap * 32);
+  const uint8_t* occ = S.occupied ? S.occupied + (long long)f * P.kp_cap : nullptr;
+  const int nq = min(S.nq[f], S.qcap);
+  for (int qi = tid; qi < nq; qi += 256) {
+    const drfe_proj_query q = S.q[(long long)f * S.qcap + qi];
+    const uint32_t* qd = reinterpret_cast<const uint32_t*>(S.qdesc + ((long long)f * S.qcap + qi) * 32);
+    uint32_t d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = qd[k];
+    drfe_proj_match m;
+    m.best_dist = 256; m.best_idx = -1; m.best_level = -1; m.best_dist2 = 256; m.best_level2 = -1;
+    // Frame::GetFeaturesInArea (Frame.cc:735-749)
+    const float x = q.x, y = q.y, r = q.r;
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, prm.min_x), r), inv_w)));
+    const int cx1 = min(DRFE_FRAME_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, prm.min_x), r), inv_w)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, prm.min_y), r), inv_h)));
+    const int cy1 = min(DRFE_FRAME_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, prm.min_y), r), inv_h)));
+    if (cx0 < DRFE_FRAME_GRID_COLS && cx1 >= 0 && cy0 < DRFE_FRAME_GRID_ROWS && cy1 >= 0) {
+      const bool check_levels = (q.min_level > 0) || (q.max_level >= 0);
+      for (int ix = cx0; ix <= cx1; ++ix)
+        for (int iy = cy0; iy <= cy1; ++iy) {
+          const int cell = ix * DRFE_FRAME_GRID_ROWS + iy;
+          for (int j = s_off[cell]; j < s_off[cell + 1]; ++j) {
+            const int idx = gi[j];
+            const drfe_keypoint kp = ku[idx];
+            if (check_levels) {
+              if (kp.octave < q.min_level) continue;
+              if (q.max_level >= 0 && kp.octave > q.max_level) continue;
+            }
+            if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+            // ORBmatcher.cc:88-101
+            if (occ && occ[idx]) continue;
+            const float u = ur[idx];
+            if (u > 0.f && fabsf(__fsub_rn(q.xr, u)) > r) continue;
+            const uint32_t* kd = desc + idx * 8;
+            int dist = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dist += __popc(d[k] ^ kd[k]);
+            if (dist < m.best_dist) { m.best_dist2 = m.best_dist; m.best_dist = dist; m.best_level2 = m.best_level; m.best_level = kp.octave; m.best_idx = idx; }
+            else if (dist < m.best_dist2) { m.best_level2 = kp.octave; m.best_dist2 = dist; }
+          }
+        }
+    }
+    S.out[(long long)f * S.qcap + qi] = m;
+  }
+}
+
 __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
   const OrbDev& P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1292,6 +1376,8 @@ struct drfe_orb {
   ChunkPipe pipe;
   PostDev post{};                // buffers of drfe_orb_frame_post, allocated on first use
   float* d_post_depth = nullptr;
+  drfe_proj_query* d_sq = nullptr; uint8_t* d_sdesc = nullptr; uint8_t* d_socc = nullptr; int* d_snq = nullptr;   // drfe_orb_search_by_projection
+  drfe_proj_match* d_sout = nullptr; int search_qcap = 0;
   int* batch_counts = nullptr;   // host destination of the running batch call
   int batch_cap = 0;
   std::vector<void*> allocs;
@@ -1906,6 +1992,33 @@ int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* de
   if (grid_count) DRFE_CUDA(cudaMemcpyAsync(grid_count, Q.grid_count, (size_t)kGridCells * nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
   if (grid_index)
     DRFE_CUDA(cudaMemcpy2DAsync(grid_index, (size_t)cap_per_frame * 2, Q.grid_index, (size_t)cap * 2, (size_t)wk * 2, nf, cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries, const uint8_t* qdesc,
+                                  const uint8_t* occupied, int qcap, drfe_proj_match* out) {
+  if (!h || !nqueries || !queries || !qdesc || !out || qcap < 1) { set_error("drfe_orb_search_by_projection: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || !h->post.keys_un) { set_error("drfe_orb_search_by_projection: run drfe_orb_frame_post first"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames, cap = h->hd.kp_cap, B = h->max_batch;
+  if (qcap > h->search_qcap) {            // (re)allocate the query-side buffers; the old ones stay in the handle's arena until destroy
+    if (dev_alloc(h, &h->d_sq, (size_t)qcap * B) || dev_alloc(h, &h->d_sdesc, (size_t)qcap * B * 32) || dev_alloc(h, &h->d_sout, (size_t)qcap * B)) return DRFE_ERR_CUDA;
+    if (!h->d_socc && (dev_alloc(h, &h->d_socc, (size_t)cap * B) || dev_alloc(h, &h->d_snq, (size_t)B))) return DRFE_ERR_CUDA;
+    h->search_qcap = qcap;
+  }
+  for (int f = 0; f < nf; ++f)
+    if (nqueries[f] < 0 || nqueries[f] > qcap) { set_error("drfe_orb_search_by_projection: frame %d has %d queries, qcap is %d", f, nqueries[f], qcap); return DRFE_ERR_ARG; }
+  DRFE_CUDA(cudaMemcpyAsync(h->d_snq, nqueries, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));
+  DRFE_CUDA(cudaMemcpyAsync(h->d_sq, queries, (size_t)nf * qcap * sizeof(drfe_proj_query), cudaMemcpyHostToDevice, st));
+  DRFE_CUDA(cudaMemcpyAsync(h->d_sdesc, qdesc, (size_t)nf * qcap * 32, cudaMemcpyHostToDevice, st));
+  if (occupied) DRFE_CUDA(cudaMemcpyAsync(h->d_socc, occupied, (size_t)nf * cap, cudaMemcpyHostToDevice, st));
+  SearchDev S;
+  S.q = h->d_sq; S.qdesc = h->d_sdesc; S.occupied = occupied ? h->d_socc : nullptr; S.nq = h->d_snq; S.out = h->d_sout; S.qcap = qcap;
+  DRFE_LAUNCH(k_search_projection, nf, 256, 0, st, h->dd, h->post, S);
+  DRFE_CUDA(cudaMemcpyAsync(out, h->d_sout, (size_t)nf * qcap * sizeof(drfe_proj_match), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }

@@ -27,6 +27,8 @@ PLANE_DTYPE = np.dtype([("nr_pts", "<i4"), ("min_nr_pts", "<i4"),
                         ("xy_acc", "<f8"), ("xz_acc", "<f8"), ("yz_acc", "<f8"),
                         ("score", "<f4"), ("MSE", "<f4"), ("planar", "<i4"),
                         ("mean", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8")], align=True)
+QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("xr", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
+MATCH_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "<i4"), ("best_dist2", "<i4"), ("best_level2", "<i4")])
 CYL_DTYPE = np.dtype([("radius", "<f4"), ("center", "<f8", (3,)), ("axis", "<f8", (3,))], align=True)
 
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -64,7 +66,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -112,6 +114,7 @@ def lib():
     L.drfe_orb_finish_batch.argtypes = [vp]
     L.drfe_frame_image_bounds.argtypes = [vp, C.c_int, C.c_int]
     L.drfe_orb_frame_post.argtypes = [vp, vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+    L.drfe_orb_search_by_projection.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
     L.drfe_orb_level_size.argtypes = [vp, C.c_int, i32p, i32p]
@@ -336,6 +339,23 @@ class ORBextractor:
         _check(self.L.drfe_orb_frame_post(self.h, C.byref(p), _ptr(depth), row_stride, frame_stride, mem_kind, _ptr(ku), _ptr(ur),
                                           _ptr(kd), _ptr(gc), _ptr(gi), self.cap))
         return ku, ur, kd, gc, gi
+
+    def search_by_projection(self, queries, qdesc, nqueries=None, occupied=None):
+        """Core of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:69-116) on the frames of
+        the last frame_post: queries (nf, qcap) QUERY_DTYPE, qdesc (nf, qcap, 32) uint8, occupied (nf, cap) uint8 or None
+        -> (nf, qcap) MATCH_DTYPE"""
+        nf = self._nframes
+        queries = np.ascontiguousarray(queries, QUERY_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        assert queries.shape[0] == nf and qdesc.shape == queries.shape + (32,)
+        qcap = queries.shape[1]
+        nq = np.full(nf, qcap, np.int32) if nqueries is None else np.ascontiguousarray(nqueries, np.int32)
+        if occupied is not None:
+            occupied = np.ascontiguousarray(occupied, np.uint8)
+            assert occupied.shape == (nf, self.cap)
+        out = np.zeros((nf, qcap), MATCH_DTYPE)
+        _check(self.L.drfe_orb_search_by_projection(self.h, _ptr(nq), _ptr(queries), _ptr(qdesc), _ptr(occupied), qcap, _ptr(out)))
+        return out
 
     def sync(self):
         _check(self.L.drfe_orb_sync(self.h))

@@ -178,6 +178,27 @@ int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* de
                         size_t frame_stride, int mem_kind, drfe_keypoint* keys_un, float* u_right,
                         float* kp_depth, uint16_t* grid_count, uint16_t* grid_index, int cap_per_frame);
 
+/* The data-parallel core of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+ * (ORBmatcher.cc:46-130; first step of SURVEY.md 8f next-3) on the device-resident results of the last
+ * drfe_orb_frame_post: per query, the keypoints Frame::GetFeaturesInArea(x, y, r, min_level, max_level)
+ * returns (Frame.cc:730-779) — minus those flagged in occupied[] (F.mvpMapPoints[idx] with observations,
+ * :88-90) and those whose mvuRight is > 0 and further than r from xr (:92-97) — ranked by
+ * ORBmatcher::DescriptorDistance (:1712-1728) into best / second best exactly as lines 103-115 do.
+ * The caller passes r = RadiusByViewingCos(...) * th * mvScaleFactors[level], applies the ratio test
+ * (:119-122) and does the in-order assignment (:124), which is sequential Tracking logic. */
+typedef struct drfe_proj_query {
+  float x, y, r, xr;                 /* mTrackProjX, mTrackProjY, window radius, mTrackProjXR      */
+  int32_t min_level, max_level;      /* nPredictedLevel - 1, nPredictedLevel                       */
+} drfe_proj_query;
+typedef struct drfe_proj_match {
+  int32_t best_dist, best_idx, best_level, best_dist2, best_level2; /* 256 / -1 when there is none */
+} drfe_proj_match;
+/* queries[f*qcap + i], qdesc[(f*qcap + i)*32 ..] for i < nqueries[f]; occupied[f*max_keypoints + idx]
+ * (may be NULL); out[f*qcap + i].  All pointers are host memory; frames = the handle's last batch. */
+int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries,
+                                  const uint8_t* qdesc, const uint8_t* occupied, int qcap,
+                                  drfe_proj_match* out);
+
 /* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
  * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
  * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */

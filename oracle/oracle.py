@@ -232,6 +232,64 @@ def frame_post(p, keys, depth):
     return ku, ur, kd, gc, gi[:placed].copy()
 
 
+def search_by_projection(p, keys_un, u_right, grid_count, grid_index, desc, queries, qdesc, occupied=None):
+    """The inner loops of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (reference
+    src/ORBmatcher.cc:69-116) restated literally, float32 arithmetic step by step: Frame::GetFeaturesInArea
+    (src/Frame.cc:730-779) over mGrid (grid_count [64][48] + grid_index: the cells' lists concatenated x-major, as
+    frame_post returns them), the occupied / right-coordinate skips, ORBmatcher::DescriptorDistance (:1712-1728) and the
+    best / second-best update.  queries: records (x, y, r, xr, min_level, max_level); returns records
+    (best_dist, best_idx, best_level, best_dist2, best_level2)."""
+    f32 = np.float32
+    gc = np.asarray(grid_count).reshape(64, 48)
+    off = np.concatenate([[0], np.cumsum(gc.ravel())]).astype(np.int64)
+    inv_w = f32(64) / f32(f32(p.max_x) - f32(p.min_x))
+    inv_h = f32(48) / f32(f32(p.max_y) - f32(p.min_y))
+    out = np.zeros(len(queries), [("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "<i4"), ("best_dist2", "<i4"), ("best_level2", "<i4")])
+    kx, ky, ko = keys_un["x"], keys_un["y"], keys_un["octave"]
+    d32 = np.ascontiguousarray(desc).view(np.uint32).reshape(len(desc), 8)
+    for qi, q in enumerate(queries):
+        x, y, r, xr = f32(q["x"]), f32(q["y"]), f32(q["r"]), f32(q["xr"])
+        lo, hi = int(q["min_level"]), int(q["max_level"])
+        best, best_idx, best_lvl, best2, best_lvl2 = 256, -1, -1, 256, -1
+        vind = []
+        cx0 = max(0, int(np.floor(f32(f32(f32(x - f32(p.min_x)) - r) * inv_w))))
+        cx1 = min(63, int(np.ceil(f32(f32(f32(x - f32(p.min_x)) + r) * inv_w))))
+        cy0 = max(0, int(np.floor(f32(f32(f32(y - f32(p.min_y)) - r) * inv_h))))
+        cy1 = min(47, int(np.ceil(f32(f32(f32(y - f32(p.min_y)) + r) * inv_h))))
+        if cx0 < 64 and cx1 >= 0 and cy0 < 48 and cy1 >= 0:
+            check = lo > 0 or hi >= 0
+            for ix in range(cx0, cx1 + 1):
+                for iy in range(cy0, cy1 + 1):
+                    c = ix * 48 + iy
+                    for j in range(off[c], off[c + 1]):
+                        idx = int(grid_index[j])
+                        if check:
+                            if ko[idx] < lo:
+                                continue
+                            if hi >= 0 and ko[idx] > hi:
+                                continue
+                        if abs(f32(kx[idx] - x)) < r and abs(f32(ky[idx] - y)) < r:
+                            vind.append(idx)
+        qd = np.ascontiguousarray(qdesc[qi]).view(np.uint32)
+        for idx in vind:
+            if occupied is not None and occupied[idx]:
+                continue
+            if u_right[idx] > 0 and abs(f32(xr - u_right[idx])) > r:
+                continue
+            dist = 0
+            for k in range(8):                       # the reference's bit tricks = a population count per word
+                v = int(qd[k] ^ d32[idx, k])
+                v = v - ((v >> 1) & 0x55555555)
+                v = (v & 0x33333333) + ((v >> 2) & 0x33333333)
+                dist += ((((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) & 0xFFFFFFFF) >> 24
+            if dist < best:
+                best2, best, best_lvl2, best_lvl, best_idx = best, dist, best_lvl, int(ko[idx]), idx
+            elif dist < best2:
+                best_lvl2, best2 = int(ko[idx]), dist
+        out[qi] = (best, best_idx, best_lvl, best2, best_lvl2)
+    return out
+
+
 def glibc_rand(seed, n):
     out = np.zeros(n, np.int32)
     lib().orc_glibc_rand(int(seed), n, _p(out))
