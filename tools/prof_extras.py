@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Wall time of the optional calls after a 256-frame batch (host buffers in and out, so PCIe included):
+drfe_orb_frame_post, drfe_orb_search_by_projection (1000 queries per frame), drfe_cape_plane_points."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dr-slam_b200"))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import drfe  # noqa: E402
+
+
+def timed(fn, n=5):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        r = fn()
+    return (time.perf_counter() - t0) / n * 1e3, r
+
+
+def main():
+    B, W, H = 256, 640, 480
+    data = [drfe.synth_frame(W, H, (i // 8) % 3, 20260000 + i) for i in range(32)]
+    gray = np.stack([data[i % 32][0] for i in range(B)])
+    depth = np.stack([data[i % 32][1] for i in range(B)])
+    K = data[0][2]
+    orb = drfe.ORBextractor(1000, 1.2, 8, 20, 7, W, H, max_batch=B)
+    cape = drfe.CAPE(H, W, 20, 20, False, bench.MIN_COS, 50.0, max_batch=B)
+    orb.enqueue(gray)
+    kps, desc, cnt = orb.download()
+    cape.enqueue_depth(depth, *K, nframes=B)
+    cape.download()
+    p = orb.frame_params(*K, [0.1, -0.05, 0.001, 0.0005, 0.0], 40.0)
+    ms, (ku, ur, kd, gc, gi) = timed(lambda: orb.frame_post(p, depth))
+    print("drfe_orb_frame_post            %7.2f ms per %d frames (depth from the host: %d MB H2D)" % (ms, B, depth.nbytes >> 20))
+    rng = np.random.default_rng(1)
+    Q = np.zeros((B, 1000), drfe.QUERY_DTYPE)
+    src = rng.integers(0, 1000, (B, 1000))
+    Q["x"] = np.take_along_axis(ku["x"], src, 1) + rng.normal(0, 3, (B, 1000)).astype(np.float32)
+    Q["y"] = np.take_along_axis(ku["y"], src, 1) + rng.normal(0, 3, (B, 1000)).astype(np.float32)
+    Q["r"], Q["xr"] = 7.0, Q["x"] - 20
+    lv = np.take_along_axis(ku["octave"], src, 1)
+    Q["min_level"], Q["max_level"] = lv - 1, lv
+    QD = np.take_along_axis(desc, src[:, :, None], 1)
+    ms, m = timed(lambda: orb.search_by_projection(Q, QD))
+    print("drfe_orb_search_by_projection  %7.2f ms per %d frames x 1000 queries (%.1f%% matched)" % (ms, B, 100.0 * (m["best_idx"] >= 0).mean()))
+    ms, (pts, offs) = timed(lambda: cape.plane_points(B), n=3)
+    print("drfe_cape_plane_points         %7.2f ms per %d frames (%d MB of points D2H, pageable destination)" % (ms, B, int(offs.max(1).sum()) * 12 >> 20))
+    # the same into pinned host memory (what a caller that cares would pass)
+    import ctypes as C
+    import torch
+    N = W * H
+    pin_pts = torch.empty((B, N, 3), dtype=torch.float32).pin_memory().numpy()
+    pin_off = torch.empty((B, 256), dtype=torch.int32).pin_memory().numpy()
+    pin_depth = torch.from_numpy(depth).pin_memory().numpy()
+
+    def pp():
+        drfe._check(cape.L.drfe_cape_plane_points(cape.h, pin_pts.ctypes.data, N, pin_off.ctypes.data, 255))
+    ms, _ = timed(pp, n=3)
+    print("drfe_cape_plane_points         %7.2f ms per %d frames (pinned destination)" % (ms, B))
+    ms, _ = timed(lambda: orb.frame_post(p, pin_depth))
+    print("drfe_orb_frame_post            %7.2f ms per %d frames (pinned depth)" % (ms, B))
+    import torch as _t
+    d_depth = _t.from_numpy(depth).cuda()
+    ms, _ = timed(lambda: orb.frame_post(p, d_depth.data_ptr(), mem_kind=drfe.MEM_DEVICE, row_stride=W, frame_stride=W * H))
+    print("drfe_orb_frame_post            %7.2f ms per %d frames (depth already on the device)" % (ms, B))
+
+
+if __name__ == "__main__":
+    main()
