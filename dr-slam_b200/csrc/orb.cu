@@ -1272,29 +1272,65 @@ __global__ void __launch_bounds__(256) k_frame_post(const OrbDev* __restrict__ P
 struct SearchDev {
   const drfe_proj_query* q; const uint8_t* qdesc; const uint8_t* occupied; const int* nq; drfe_proj_match* out; int qcap;
 };
+
+// exclusive prefix sum of the 3072 mGrid cell counts of one frame into s_off[0 .. 3072] (all 256 threads of the CTA)
+__device__ __forceinline__ void grid_offsets(const uint16_t* __restrict__ gc, unsigned short* s_off, int* s_part) {
+  const int tid = threadIdx.x;
+  constexpr int PER = kGridCells / 256;
+  int loc[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += gc[tid * PER + k]; }
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) { int run = 0; for (int i = 0; i < 256; ++i) { const int t = s_part[i]; s_part[i] = run; run += t; } s_off[kGridCells] = (unsigned short)run; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < PER; ++k) s_off[tid * PER + k] = (unsigned short)(s_part[tid] + loc[k]);
+  __syncthreads();
+}
+
+// Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (Frame.cc:730-779): visit(idx, kp) for every index the reference
+// pushes into vIndices, in its order (cells x-major, push_back order inside a cell)
+template <class Visit>
+__device__ __forceinline__ void features_in_area(const drfe_frame_params& prm, const unsigned short* s_off, const uint16_t* __restrict__ gi,
+                                                 const drfe_keypoint* __restrict__ ku, float x, float y, float r, int min_level, int max_level,
+                                                 Visit&& visit) {
+  const float inv_w = __fdiv_rn((float)DRFE_FRAME_GRID_COLS, __fsub_rn(prm.max_x, prm.min_x));
+  const float inv_h = __fdiv_rn((float)DRFE_FRAME_GRID_ROWS, __fsub_rn(prm.max_y, prm.min_y));
+  const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, prm.min_x), r), inv_w)));
+  const int cx1 = min(DRFE_FRAME_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, prm.min_x), r), inv_w)));
+  const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, prm.min_y), r), inv_h)));
+  const int cy1 = min(DRFE_FRAME_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, prm.min_y), r), inv_h)));
+  if (!(cx0 < DRFE_FRAME_GRID_COLS && cx1 >= 0 && cy0 < DRFE_FRAME_GRID_ROWS && cy1 >= 0)) return;
+  const bool check_levels = (min_level > 0) || (max_level >= 0);
+  for (int ix = cx0; ix <= cx1; ++ix)
+    for (int iy = cy0; iy <= cy1; ++iy) {
+      const int cell = ix * DRFE_FRAME_GRID_ROWS + iy;
+      for (int j = s_off[cell]; j < s_off[cell + 1]; ++j) {
+        const int idx = gi[j];
+        const drfe_keypoint kp = ku[idx];
+        if (check_levels) {
+          if (kp.octave < min_level) continue;
+          if (max_level >= 0 && kp.octave > max_level) continue;
+        }
+        if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+        visit(idx, kp);
+      }
+    }
+}
+
+__device__ __forceinline__ int descriptor_distance(const uint32_t (&d)[8], const uint32_t* __restrict__ kd) {   // ORBmatcher.cc:1712-1728
+  const uint4 a = *reinterpret_cast<const uint4*>(kd), b = *reinterpret_cast<const uint4*>(kd + 4);
+  return __popc(d[0] ^ a.x) + __popc(d[1] ^ a.y) + __popc(d[2] ^ a.z) + __popc(d[3] ^ a.w) + __popc(d[4] ^ b.x) + __popc(d[5] ^ b.y) +
+         __popc(d[6] ^ b.z) + __popc(d[7] ^ b.w);
+}
+
 __global__ void __launch_bounds__(256) k_search_projection(const OrbDev* __restrict__ Pp, PostDev Q, SearchDev S) {
   __shared__ unsigned short s_off[kGridCells + 1];
   __shared__ int s_part[256];
   const OrbDev& P = *Pp;
   const int f = blockIdx.x, tid = threadIdx.x;
-  const uint16_t* gc = Q.grid_count + (long long)f * kGridCells;
-  {
-    // exclusive prefix sum of the 3072 cell counts: 12 cells per thread, then a scan of the 256 partial sums
-    constexpr int PER = kGridCells / 256;
-    int loc[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += gc[tid * PER + k]; }
-    s_part[tid] = sum;
-    __syncthreads();
-    if (tid == 0) { int run = 0; for (int i = 0; i < 256; ++i) { const int t = s_part[i]; s_part[i] = run; run += t; } s_off[kGridCells] = (unsigned short)run; }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) s_off[tid * PER + k] = (unsigned short)(s_part[tid] + loc[k]);
-    __syncthreads();
-  }
-  const drfe_frame_params& prm = Q.prm;
-  const float inv_w = __fdiv_rn((float)DRFE_FRAME_GRID_COLS, __fsub_rn(prm.max_x, prm.min_x));
-  const float inv_h = __fdiv_rn((float)DRFE_FRAME_GRID_ROWS, __fsub_rn(prm.max_y, prm.min_y));
+  grid_offsets(Q.grid_count + (long long)f * kGridCells, s_off, s_part);
   const drfe_keypoint* ku = Q.keys_un + (long long)f * P.kp_cap;
   const float* ur = Q.u_right + (long long)f * P.kp_cap;
   const uint16_t* gi = Q.grid_index + (long long)f * P.kp_cap;
@@ -1309,40 +1345,159 @@ __global__ void __launch_bounds__(256) k_search_projection(const OrbDev* __restr
     for (int k = 0; k < 8; ++k) d[k] = qd[k];
     drfe_proj_match m;
     m.best_dist = 256; m.best_idx = -1; m.best_level = -1; m.best_dist2 = 256; m.best_level2 = -1;
-    // Frame::GetFeaturesInArea (Frame.cc:735-749)
-    const float x = q.x, y = q.y, r = q.r;
-    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, prm.min_x), r), inv_w)));
-    const int cx1 = min(DRFE_FRAME_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, prm.min_x), r), inv_w)));
-    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, prm.min_y), r), inv_h)));
-    const int cy1 = min(DRFE_FRAME_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, prm.min_y), r), inv_h)));
-    if (cx0 < DRFE_FRAME_GRID_COLS && cx1 >= 0 && cy0 < DRFE_FRAME_GRID_ROWS && cy1 >= 0) {
-      const bool check_levels = (q.min_level > 0) || (q.max_level >= 0);
-      for (int ix = cx0; ix <= cx1; ++ix)
-        for (int iy = cy0; iy <= cy1; ++iy) {
-          const int cell = ix * DRFE_FRAME_GRID_ROWS + iy;
-          for (int j = s_off[cell]; j < s_off[cell + 1]; ++j) {
-            const int idx = gi[j];
-            const drfe_keypoint kp = ku[idx];
-            if (check_levels) {
-              if (kp.octave < q.min_level) continue;
-              if (q.max_level >= 0 && kp.octave > q.max_level) continue;
-            }
-            if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
-            // ORBmatcher.cc:88-101
-            if (occ && occ[idx]) continue;
-            const float u = ur[idx];
-            if (u > 0.f && fabsf(__fsub_rn(q.xr, u)) > r) continue;
-            const uint32_t* kd = desc + idx * 8;
-            int dist = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) dist += __popc(d[k] ^ kd[k]);
-            if (dist < m.best_dist) { m.best_dist2 = m.best_dist; m.best_dist = dist; m.best_level2 = m.best_level; m.best_level = kp.octave; m.best_idx = idx; }
-            else if (dist < m.best_dist2) { m.best_level2 = kp.octave; m.best_dist2 = dist; }
-          }
-        }
-    }
+    features_in_area(Q.prm, s_off, gi, ku, q.x, q.y, q.r, q.min_level, q.max_level, [&](int idx, const drfe_keypoint& kp) {
+      // ORBmatcher.cc:88-101
+      if (occ && occ[idx]) return;
+      const float u = ur[idx];
+      if (u > 0.f && fabsf(__fsub_rn(q.xr, u)) > q.r) return;
+      const int dist = descriptor_distance(d, desc + idx * 8);
+      if (dist < m.best_dist) { m.best_dist2 = m.best_dist; m.best_dist = dist; m.best_level2 = m.best_level; m.best_level = kp.octave; m.best_idx = idx; }
+      else if (dist < m.best_dist2) { m.best_level2 = kp.octave; m.best_dist2 = dist; }
+    });
     S.out[(long long)f * S.qcap + qi] = m;
   }
+}
+
+// ------------------------------------------------------------------ frame-to-frame search by projection
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1396-1535), whole.
+// One CTA per current frame.  The reference visits the last frame's points in order and a match made by point j (if its
+// map point has observations) hides that keypoint from every later point (:1471-1473).  Here all points search in
+// parallel against owner[idx] = the lowest-numbered observed point that chose keypoint idx in the previous sweep (-1: held
+// on entry), skipping idx when owner[idx] < i, until a sweep changes no choice.  That fixed point satisfies the
+// reference's recurrence point by point, and the recurrence has one solution (induction on i), so it is the reference's
+// result; point i is final after at most i + 1 sweeps, in practice after 2-3.  Then rotation histogram / three maxima.
+struct TrackDev {
+  const drfe_track_params* tp; const drfe_last_point* pts; const uint8_t* pdesc; const uint8_t* occupied; const int* np;
+  int32_t* match_key; int32_t* match_dist; int32_t* key_point; int* nmatches; int* sweeps; int pcap;
+};
+__global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restrict__ Pp, PostDev Q, TrackDev S) {
+  extern __shared__ int s_dyn[];
+  __shared__ unsigned short s_off[kGridCells + 1];
+  __shared__ int s_part[256];
+  __shared__ int s_hist[DRFE_HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  __shared__ int s_cnt[2];
+  const OrbDev& P = *Pp;
+  const int f = blockIdx.x, tid = threadIdx.x, cap = P.kp_cap;
+  int* owner = s_dyn;                 // [cap]
+  int* choice = s_dyn + cap;          // [pcap] matched keypoint of point i or -1
+  int* cdist = choice + S.pcap;       // [pcap] bestDist
+  grid_offsets(Q.grid_count + (long long)f * kGridCells, s_off, s_part);
+  const drfe_frame_params prm = Q.prm;
+  const drfe_track_params tp = S.tp[f];
+  const drfe_keypoint* ku = Q.keys_un + (long long)f * cap;
+  const float* ur = Q.u_right + (long long)f * cap;
+  const uint16_t* gi = Q.grid_index + (long long)f * cap;
+  const uint32_t* desc = reinterpret_cast<const uint32_t*>(P.out_desc + (long long)f * cap * 32);
+  const uint8_t* occ = S.occupied ? S.occupied + (long long)f * cap : nullptr;
+  const drfe_last_point* pts = S.pts + (long long)f * S.pcap;
+  const int np = min(S.np[f], S.pcap);
+  const int nkeys = P.out_cnt[f];
+  for (int i = tid; i < np; i += 256) choice[i] = -1;
+  int sweeps = 0;
+  for (;;) {
+    // owner[] from the previous sweep's choices
+    for (int k = tid; k < cap; k += 256) owner[k] = (occ && k < nkeys && occ[k]) ? -1 : 0x7fffffff;
+    __syncthreads();
+    for (int i = tid; i < np; i += 256)
+      if (choice[i] >= 0 && (pts[i].flags & DRFE_LP_OBSERVED)) atomicMin(&owner[choice[i]], i);
+    __syncthreads();
+    int changed = 0;
+    for (int i = tid; i < np; i += 256) {
+      const drfe_last_point lp = pts[i];
+      int best = 256, best_idx = -1;
+      if (lp.flags & DRFE_LP_VALID) {
+        // :1426-1442  x3Dc = Rcw*x3Dw + tcw: cv::gemm's 3x3 float path (products and sums in float, left to right, then + c)
+        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp.Tcw[0], lp.X), __fmul_rn(tp.Tcw[1], lp.Y)), __fmul_rn(tp.Tcw[2], lp.Z)), tp.Tcw[3]);
+        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp.Tcw[4], lp.X), __fmul_rn(tp.Tcw[5], lp.Y)), __fmul_rn(tp.Tcw[6], lp.Z)), tp.Tcw[7]);
+        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp.Tcw[8], lp.X), __fmul_rn(tp.Tcw[9], lp.Y)), __fmul_rn(tp.Tcw[10], lp.Z)), tp.Tcw[11]);
+        const float invzc = (float)(1.0 / (double)zc);
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(prm.fx, xc), invzc), prm.cx);
+        const float v = __fadd_rn(__fmul_rn(__fmul_rn(prm.fy, yc), invzc), prm.cy);
+        const bool in = !(invzc < 0.f) && !(u < prm.min_x || u > prm.max_x) && !(v < prm.min_y || v > prm.max_y) && u == u && v == v;
+        if (in) {
+          const int oct = lp.octave;
+          const float radius = __fmul_rn(tp.th, P.lv[oct].scale);
+          const int lo = tp.mode == 1 ? oct : tp.mode == 2 ? 0 : oct - 1;
+          const int hi = tp.mode == 1 ? -1 : tp.mode == 2 ? oct : oct + 1;
+          const float urp = __fsub_rn(u, __fmul_rn(prm.bf, invzc));
+          const uint32_t* qd = reinterpret_cast<const uint32_t*>(S.pdesc + ((long long)f * S.pcap + i) * 32);
+          uint32_t d[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = qd[k];
+          features_in_area(prm, s_off, gi, ku, u, v, radius, lo, hi, [&](int idx, const drfe_keypoint&) {
+            if (owner[idx] < i) return;                                        // :1471-1473
+            const float r2 = ur[idx];
+            if (r2 > 0.f && fabsf(__fsub_rn(urp, r2)) > radius) return;        // :1475-1481
+            const int dist = descriptor_distance(d, desc + idx * 8);
+            if (dist < best) { best = dist; best_idx = idx; }                  // :1487-1491
+          });
+        }
+      }
+      const int c = best <= DRFE_TH_HIGH ? best_idx : -1;                      // :1494 (256 when nothing was compared)
+      changed |= (c != choice[i]);
+      choice[i] = c; cdist[i] = best;
+    }
+    ++sweeps;
+    if (!__syncthreads_or(changed)) break;
+  }
+  // rotation consistency (:1499-1532)
+  if (tid < DRFE_HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid < 2) s_cnt[tid] = 0;
+  for (int k = tid; k < cap; k += 256) owner[k] = -1;                          // becomes key_point
+  __syncthreads();
+  const float factor = 1.0f / DRFE_HISTO_LENGTH;
+  auto rot_bin = [&](int i) {
+    float rot = __fsub_rn(pts[i].angle, ku[choice[i]].angle);
+    if (rot < 0.f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == DRFE_HISTO_LENGTH) bin = 0;
+    return bin;
+  };
+  int mine = 0;
+  for (int i = tid; i < np; i += 256)
+    if (choice[i] >= 0) {
+      ++mine;
+      if (tp.check_orientation) { const int b = rot_bin(i); if (b >= 0 && b < DRFE_HISTO_LENGTH) atomicAdd(&s_hist[b], 1); }
+    }
+  if (mine) atomicAdd(&s_cnt[0], mine);
+  __syncthreads();
+  if (tid == 0) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    if (tp.check_orientation) {                                               // ComputeThreeMaxima (:1666-1707)
+      int max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < DRFE_HISTO_LENGTH; ++i) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+    }
+    s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+  }
+  __syncthreads();
+  // the in-order assignment mvpMapPoints[bestIdx2] = pMP leaves the highest-numbered point that chose the keypoint
+  for (int i = tid; i < np; i += 256)
+    if (choice[i] >= 0) atomicMax(&owner[choice[i]], i);
+  __syncthreads();
+  if (tp.check_orientation) {
+    int removed = 0;
+    for (int i = tid; i < np; i += 256)
+      if (choice[i] >= 0) {
+        const int b = rot_bin(i);
+        if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { owner[choice[i]] = -2; ++removed; }   // set to NULL, nmatches-- (:1527-1528)
+      }
+    if (removed) atomicAdd(&s_cnt[1], removed);
+  }
+  __syncthreads();
+  if (S.key_point) for (int k = tid; k < cap; k += 256) S.key_point[(long long)f * cap + k] = owner[k];
+  for (int i = tid; i < np; i += 256) {
+    S.match_key[(long long)f * S.pcap + i] = choice[i];
+    S.match_dist[(long long)f * S.pcap + i] = cdist[i];
+  }
+  if (tid == 0) { S.nmatches[f] = s_cnt[0] - s_cnt[1]; S.sweeps[f] = sweeps; }
 }
 
 __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
@@ -1377,6 +1532,7 @@ struct drfe_orb {
   PostDev post{};                // buffers of drfe_orb_frame_post, allocated on first use
   float* d_post_depth = nullptr;
   drfe_proj_query* d_sq = nullptr; uint8_t* d_sdesc = nullptr; uint8_t* d_socc = nullptr; int* d_snq = nullptr;   // drfe_orb_search_by_projection
+  drfe_track_params* d_ttp = nullptr; drfe_last_point* d_tpts = nullptr; uint8_t* d_tdesc = nullptr; int32_t* d_tout = nullptr; int32_t* d_tkey = nullptr; int* d_tcnt = nullptr; int track_pcap = 0;   // drfe_orb_search_last_frame
   drfe_proj_match* d_sout = nullptr; int search_qcap = 0;
   int* batch_counts = nullptr;   // host destination of the running batch call
   int batch_cap = 0;
@@ -2019,6 +2175,53 @@ int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_p
   S.q = h->d_sq; S.qdesc = h->d_sdesc; S.occupied = occupied ? h->d_socc : nullptr; S.nq = h->d_snq; S.out = h->d_sout; S.qcap = qcap;
   DRFE_LAUNCH(k_search_projection, nf, 256, 0, st, h->dd, h->post, S);
   DRFE_CUDA(cudaMemcpyAsync(out, h->d_sout, (size_t)nf * qcap * sizeof(drfe_proj_match), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const int* npoints, const drfe_last_point* points,
+                               const uint8_t* pdesc, const uint8_t* occupied, int pcap, int32_t* match_key, int32_t* match_dist,
+                               int32_t* key_point, int* nmatches, int* sweeps) {
+  if (!h || !tp || !npoints || !points || !pdesc || pcap < 1) { set_error("drfe_orb_search_last_frame: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || !h->post.keys_un) { set_error("drfe_orb_search_last_frame: run drfe_orb_frame_post first"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames, cap = h->hd.kp_cap, B = h->max_batch;
+  const size_t smem = ((size_t)cap + 2 * (size_t)pcap) * sizeof(int);
+  if (smem > 160 * 1024) { set_error("drfe_orb_search_last_frame: pcap %d too large", pcap); return DRFE_ERR_CAPACITY; }
+  for (int f = 0; f < nf; ++f) {
+    if (npoints[f] < 0 || npoints[f] > pcap) { set_error("drfe_orb_search_last_frame: frame %d has %d points, pcap is %d", f, npoints[f], pcap); return DRFE_ERR_ARG; }
+    if (tp[f].mode < 0 || tp[f].mode > 2) { set_error("drfe_orb_search_last_frame: frame %d: mode %d", f, tp[f].mode); return DRFE_ERR_ARG; }
+    for (int i = 0; i < npoints[f]; ++i) {
+      const drfe_last_point& lp = points[(size_t)f * pcap + i];
+      if ((lp.flags & DRFE_LP_VALID) && (lp.octave < 0 || lp.octave >= h->prm.nlevels)) {
+        set_error("drfe_orb_search_last_frame: frame %d point %d: octave %d", f, i, lp.octave); return DRFE_ERR_ARG;
+      }
+    }
+  }
+  if (pcap > h->track_pcap) {
+    if (dev_alloc(h, &h->d_tpts, (size_t)pcap * B) || dev_alloc(h, &h->d_tdesc, (size_t)pcap * B * 32) || dev_alloc(h, &h->d_tout, (size_t)pcap * B * 2)) return DRFE_ERR_CUDA;
+    if (!h->d_ttp && (dev_alloc(h, &h->d_ttp, (size_t)B) || dev_alloc(h, &h->d_tkey, (size_t)cap * B) || dev_alloc(h, &h->d_tcnt, (size_t)B * 3))) return DRFE_ERR_CUDA;
+    if (!h->d_socc && (dev_alloc(h, &h->d_socc, (size_t)cap * B) || dev_alloc(h, &h->d_snq, (size_t)B))) return DRFE_ERR_CUDA;
+    DRFE_CUDA(cudaFuncSetAttribute(k_search_last_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->track_pcap = pcap;
+  }
+  DRFE_CUDA(cudaMemcpyAsync(h->d_tcnt, npoints, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));
+  DRFE_CUDA(cudaMemcpyAsync(h->d_ttp, tp, (size_t)nf * sizeof(drfe_track_params), cudaMemcpyHostToDevice, st));
+  DRFE_CUDA(cudaMemcpyAsync(h->d_tpts, points, (size_t)nf * pcap * sizeof(drfe_last_point), cudaMemcpyHostToDevice, st));
+  DRFE_CUDA(cudaMemcpyAsync(h->d_tdesc, pdesc, (size_t)nf * pcap * 32, cudaMemcpyHostToDevice, st));
+  if (occupied) DRFE_CUDA(cudaMemcpyAsync(h->d_socc, occupied, (size_t)nf * cap, cudaMemcpyHostToDevice, st));
+  TrackDev S;
+  S.tp = h->d_ttp; S.pts = h->d_tpts; S.pdesc = h->d_tdesc; S.occupied = occupied ? h->d_socc : nullptr; S.np = h->d_tcnt;
+  S.match_key = h->d_tout; S.match_dist = h->d_tout + (size_t)pcap * B; S.key_point = h->d_tkey; S.nmatches = h->d_tcnt + B; S.sweeps = h->d_tcnt + 2 * B;
+  S.pcap = pcap;
+  DRFE_LAUNCH(k_search_last_frame, nf, 256, smem, st, h->dd, h->post, S);
+  if (match_key) DRFE_CUDA(cudaMemcpyAsync(match_key, S.match_key, (size_t)nf * pcap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (match_dist) DRFE_CUDA(cudaMemcpyAsync(match_dist, S.match_dist, (size_t)nf * pcap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (key_point) DRFE_CUDA(cudaMemcpyAsync(key_point, S.key_point, (size_t)nf * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (nmatches) DRFE_CUDA(cudaMemcpyAsync(nmatches, S.nmatches, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (sweeps) DRFE_CUDA(cudaMemcpyAsync(sweeps, S.sweeps, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }

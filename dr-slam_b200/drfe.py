@@ -29,6 +29,9 @@ PLANE_DTYPE = np.dtype([("nr_pts", "<i4"), ("min_nr_pts", "<i4"),
                         ("mean", "<f8", (3,)), ("normal", "<f8", (3,)), ("d", "<f8")], align=True)
 QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("xr", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
 MATCH_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "<i4"), ("best_dist2", "<i4"), ("best_level2", "<i4")])
+LAST_POINT_DTYPE = np.dtype([("X", "<f4"), ("Y", "<f4"), ("Z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4")])
+TRACK_PARAMS_DTYPE = np.dtype([("Tcw", "<f4", (12,)), ("th", "<f4"), ("mode", "<i4"), ("check_orientation", "<i4")])
+LP_VALID, LP_OBSERVED = 1, 2
 CYL_DTYPE = np.dtype([("radius", "<f4"), ("center", "<f8", (3,)), ("axis", "<f8", (3,))], align=True)
 
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -66,7 +69,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -115,6 +118,7 @@ def lib():
     L.drfe_frame_image_bounds.argtypes = [vp, C.c_int, C.c_int]
     L.drfe_orb_frame_post.argtypes = [vp, vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     L.drfe_orb_search_by_projection.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.drfe_orb_search_last_frame.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
     L.drfe_orb_level_size.argtypes = [vp, C.c_int, i32p, i32p]
@@ -356,6 +360,27 @@ class ORBextractor:
         out = np.zeros((nf, qcap), MATCH_DTYPE)
         _check(self.L.drfe_orb_search_by_projection(self.h, _ptr(nq), _ptr(queries), _ptr(qdesc), _ptr(occupied), qcap, _ptr(out)))
         return out
+
+    def search_last_frame(self, tp, points, pdesc, npoints=None, occupied=None):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1396-1535) with the frames of
+        the last frame_post as the current frames: tp (nf,) TRACK_PARAMS_DTYPE, points (nf, pcap) LAST_POINT_DTYPE, pdesc
+        (nf, pcap, 32) uint8, occupied (nf, cap) uint8 or None -> (match_key, match_dist, key_point, nmatches, sweeps)"""
+        nf = self._nframes
+        tp = np.ascontiguousarray(tp, TRACK_PARAMS_DTYPE)
+        points = np.ascontiguousarray(points, LAST_POINT_DTYPE)
+        pdesc = np.ascontiguousarray(pdesc, np.uint8)
+        assert tp.shape == (nf,) and points.shape[0] == nf and pdesc.shape == points.shape + (32,)
+        pcap = points.shape[1]
+        npts = np.full(nf, pcap, np.int32) if npoints is None else np.ascontiguousarray(npoints, np.int32)
+        if occupied is not None:
+            occupied = np.ascontiguousarray(occupied, np.uint8)
+            assert occupied.shape == (nf, self.cap)
+        mk, md = np.zeros((nf, pcap), np.int32), np.zeros((nf, pcap), np.int32)
+        kp = np.zeros((nf, self.cap), np.int32)
+        nm, sw = np.zeros(nf, np.int32), np.zeros(nf, np.int32)
+        _check(self.L.drfe_orb_search_last_frame(self.h, _ptr(tp), _ptr(npts), _ptr(points), _ptr(pdesc), _ptr(occupied), pcap,
+                                                 _ptr(mk), _ptr(md), _ptr(kp), _ptr(nm), _ptr(sw)))
+        return mk, md, kp, nm, sw
 
     def sync(self):
         _check(self.L.drfe_orb_sync(self.h))

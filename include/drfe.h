@@ -199,6 +199,45 @@ int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_p
                                   const uint8_t* qdesc, const uint8_t* occupied, int qcap,
                                   drfe_proj_match* out);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1396-1535),
+ * the matcher TrackWithMotionModel runs on every frame — whole function, on the device-resident results of the last
+ * drfe_orb_frame_post (the current frames) — SURVEY.md 8f next-3.  Per last-frame point i with a map point that is not
+ * an outlier (:1417-1423): x3Dc = Rcw*x3Dw + tcw (cv::Mat float product, :1426-1427), the projection (:1429-1442),
+ * radius = th * mvScaleFactors[octave] (:1447), Frame::GetFeaturesInArea with the level range bForward / bBackward
+ * select (:1451-1456), the skips of keypoints that already hold a map point with observations (:1471-1473) and of
+ * keypoints failing the right-coordinate test (:1475-1481), DescriptorDistance, first minimum (:1487-1491), match if
+ * bestDist <= TH_HIGH (:1494).  The reference's loop is sequential because a match made by point j makes later
+ * points skip that keypoint; the device reaches the same result as the fixed point of "every point searches in
+ * parallel, skipping the keypoints that lower-numbered points with observations chose in the previous sweep"
+ * (point 0 is final after one sweep, point i after at most i + 1; two or three sweeps in practice).  Then the rotation
+ * histogram (:1499-1509), ComputeThreeMaxima (:1666-1707) and the removal of the other bins (:1512-1532). */
+#define DRFE_TH_HIGH 100     /* ORBmatcher::TH_HIGH (ORBmatcher.cc:38) */
+#define DRFE_HISTO_LENGTH 30 /* ORBmatcher::HISTO_LENGTH (:40) */
+typedef struct drfe_last_point {
+  float X, Y, Z;   /* LastFrame.mvpMapPoints[i]->GetWorldPos()                                              */
+  float angle;     /* LastFrame.mvKeysUn[i].angle                                                           */
+  int32_t octave;  /* LastFrame.mvKeys[i].octave                                                            */
+  int32_t flags;   /* DRFE_LP_VALID: map point present and !mvbOutlier[i]; DRFE_LP_OBSERVED: Observations() > 0 */
+} drfe_last_point;
+#define DRFE_LP_VALID 1
+#define DRFE_LP_OBSERVED 2
+typedef struct drfe_track_params {
+  float Tcw[12];             /* rows 0..2 of CurrentFrame.mTcw, row-major 3x4: [Rcw | tcw]                  */
+  float th;                  /* window factor (15 / 7 in TrackWithMotionModel, doubled on the retry)        */
+  int32_t mode;              /* 0: levels octave-1 .. octave+1; 1: bForward (>= octave); 2: bBackward (0 .. octave) (:1413-1414, :1451-1456) */
+  int32_t check_orientation; /* mbCheckOrientation                                                          */
+} drfe_track_params;
+/* tp[f], npoints[f], points[f*pcap + i], pdesc[(f*pcap + i)*32 ..] (pMP->GetDescriptor()); occupied[f*max_keypoints + idx]
+ * != 0: CurrentFrame.mvpMapPoints[idx] holds an observed map point on entry (NULL: none, what TrackWithMotionModel's
+ * fill(NULL) gives).  Outputs (host, any may be NULL): match_key[f*pcap + i] = bestIdx2 of point i or -1 and
+ * match_dist[f*pcap + i] = its bestDist (256 if no candidate), both BEFORE the rotation check; key_point[f*max_keypoints
+ * + idx] = the point i that CurrentFrame.mvpMapPoints[idx] holds on return, or -1; nmatches[f] = the return value;
+ * sweeps[f] = parallel sweeps used. */
+int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const int* npoints,
+                               const drfe_last_point* points, const uint8_t* pdesc, const uint8_t* occupied,
+                               int pcap, int32_t* match_key, int32_t* match_dist, int32_t* key_point,
+                               int* nmatches, int* sweeps);
+
 /* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
  * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
  * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */

@@ -290,6 +290,171 @@ def search_by_projection(p, keys_un, u_right, grid_count, grid_index, desc, quer
     return out
 
 
+def features_in_area(p, keys_un, off, grid_index, x, y, r, lo=-1, hi=-1):
+    """Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (reference src/Frame.cc:730-779), float32 step by step;
+    off = exclusive prefix sum of the [64][48] cell counts."""
+    f32 = np.float32
+    x, y, r = f32(x), f32(y), f32(r)
+    inv_w = f32(64) / f32(f32(p.max_x) - f32(p.min_x))
+    inv_h = f32(48) / f32(f32(p.max_y) - f32(p.min_y))
+    kx, ky, ko = keys_un["x"], keys_un["y"], keys_un["octave"]
+    vind = []
+    cx0 = max(0, int(np.floor(f32(f32(f32(x - f32(p.min_x)) - r) * inv_w))))
+    if cx0 >= 64:
+        return vind
+    cx1 = min(63, int(np.ceil(f32(f32(f32(x - f32(p.min_x)) + r) * inv_w))))
+    if cx1 < 0:
+        return vind
+    cy0 = max(0, int(np.floor(f32(f32(f32(y - f32(p.min_y)) - r) * inv_h))))
+    if cy0 >= 48:
+        return vind
+    cy1 = min(47, int(np.ceil(f32(f32(f32(y - f32(p.min_y)) + r) * inv_h))))
+    if cy1 < 0:
+        return vind
+    check = lo > 0 or hi >= 0
+    for ix in range(cx0, cx1 + 1):
+        for iy in range(cy0, cy1 + 1):
+            c = ix * 48 + iy
+            for j in range(off[c], off[c + 1]):
+                idx = int(grid_index[j])
+                if check:
+                    if ko[idx] < lo:
+                        continue
+                    if hi >= 0 and ko[idx] > hi:
+                        continue
+                if abs(f32(kx[idx] - x)) < r and abs(f32(ky[idx] - y)) < r:
+                    vind.append(idx)
+    return vind
+
+
+def descriptor_distance(a32, b32):
+    """ORBmatcher::DescriptorDistance (reference src/ORBmatcher.cc:1712-1728): the bit tricks, word by word"""
+    dist = 0
+    for k in range(8):
+        v = int(a32[k] ^ b32[k])
+        v = v - ((v >> 1) & 0x55555555)
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333)
+        dist += ((((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) & 0xFFFFFFFF) >> 24
+    return dist
+
+
+LAST_POINT_DTYPE = np.dtype([("X", "<f4"), ("Y", "<f4"), ("Z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4")])
+LP_VALID, LP_OBSERVED = 1, 2
+TH_HIGH, HISTO_LENGTH = 100, 30
+
+
+def search_last_frame(p, scale_factors, keys_un, u_right, grid_count, grid_index, desc, Tcw, th, mode, check_orientation,
+                      points, pdesc, occupied=None):
+    """ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (reference
+    src/ORBmatcher.cc:1396-1535) restated literally: the sequential loop over the last frame's points with the in-order
+    assignment CurrentFrame.mvpMapPoints[bestIdx2] = pMP, the rotation histogram, ComputeThreeMaxima (:1666-1707) and the
+    removal of the other bins.  Rcw*x3Dw+tcw follows cv::gemm's small-matrix float path (products and sums in float, left
+    to right, then + c; tests/test_search_last_frame.py checks that model against cv2.gemm); no FMA contraction.
+    mode: 0 neither, 1 bForward, 2 bBackward (:1413-1414, computed by the caller).  mvpMapPoints of the current frame is
+    modelled as `holder[idx]` = index of the last-frame point it holds (-1: untouched, -2: set to NULL by the rotation
+    check); occupied[idx] != 0: holds an observed map point on entry.
+    Returns (match_key, match_dist, holder, nmatches)."""
+    f32, f64 = np.float32, np.float64
+    T = np.asarray(Tcw, f32).reshape(3, 4)
+    gc = np.asarray(grid_count).reshape(64, 48)
+    off = np.concatenate([[0], np.cumsum(gc.ravel())]).astype(np.int64)
+    d32 = np.ascontiguousarray(desc).view(np.uint32).reshape(len(desc), 8)
+    n = len(keys_un)
+    holder = np.full(n, -1, np.int32)
+    held_observed = np.zeros(n, bool) if occupied is None else (np.asarray(occupied[:n]) != 0)
+    held_observed = held_observed.copy()
+    match_key = np.full(len(points), -1, np.int32)
+    match_dist = np.full(len(points), 256, np.int32)
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = f32(1.0) / f32(HISTO_LENGTH)
+    nmatches = 0
+    th = f32(th)
+    fx, fy, cx, cy, bf = f32(p.fx), f32(p.fy), f32(p.cx), f32(p.cy), f32(p.bf)
+    with np.errstate(all="ignore"):
+        for i, lp in enumerate(points):
+            if not (lp["flags"] & LP_VALID):
+                continue
+            X = (f32(lp["X"]), f32(lp["Y"]), f32(lp["Z"]))
+            c3 = []
+            for r in range(3):
+                t0 = f32(f32(f32(T[r, 0] * X[0]) + f32(T[r, 1] * X[1])) + f32(T[r, 2] * X[2]))
+                c3.append(f32(f64(t0) + f64(T[r, 3])))
+            xc, yc = c3[0], c3[1]
+            invzc = f32(f64(1.0) / f64(c3[2]))
+            if invzc < 0:
+                continue
+            u = f32(f32(f32(fx * xc) * invzc) + cx)
+            v = f32(f32(f32(fy * yc) * invzc) + cy)
+            if u < f32(p.min_x) or u > f32(p.max_x):
+                continue
+            if v < f32(p.min_y) or v > f32(p.max_y):
+                continue
+            if np.isnan(u) or np.isnan(v):      # z == 0 and x (y) == 0: undefined in the reference ((int)floor(NaN)); declared: no match
+                continue
+            octave = int(lp["octave"])
+            radius = f32(th * f32(scale_factors[octave]))
+            if mode == 1:
+                vind = features_in_area(p, keys_un, off, grid_index, u, v, radius, octave, -1)
+            elif mode == 2:
+                vind = features_in_area(p, keys_un, off, grid_index, u, v, radius, 0, octave)
+            else:
+                vind = features_in_area(p, keys_un, off, grid_index, u, v, radius, octave - 1, octave + 1)
+            if not vind:
+                continue
+            dmp = np.ascontiguousarray(pdesc[i]).view(np.uint32)
+            best, best_idx = 256, -1
+            for i2 in vind:
+                if held_observed[i2]:
+                    continue
+                if u_right[i2] > 0:
+                    ur = f32(u - f32(bf * invzc))
+                    er = abs(f32(ur - u_right[i2]))
+                    if er > radius:
+                        continue
+                dist = descriptor_distance(dmp, d32[i2])
+                if dist < best:
+                    best, best_idx = dist, i2
+            match_dist[i] = best
+            if best <= TH_HIGH:
+                holder[best_idx] = i
+                held_observed[best_idx] = bool(lp["flags"] & LP_OBSERVED)
+                match_key[i] = best_idx
+                nmatches += 1
+                if check_orientation:
+                    rot = f32(f32(lp["angle"]) - f32(keys_un["angle"][best_idx]))
+                    if rot < 0.0:
+                        rot = f32(rot + f32(360.0))
+                    t = f32(rot * factor)
+                    b = int(np.floor(f64(t) + 0.5)) if t >= 0 else -int(np.floor(-f64(t) + 0.5))   # round(): half away from zero
+                    if b == HISTO_LENGTH:
+                        b = 0
+                    assert 0 <= b < HISTO_LENGTH
+                    rot_hist[b].append(best_idx)
+    if check_orientation:
+        ind1 = ind2 = ind3 = -1
+        max1 = max2 = max3 = 0
+        for i in range(HISTO_LENGTH):
+            s = len(rot_hist[i])
+            if s > max1:
+                max3, max2, max1 = max2, max1, s
+                ind3, ind2, ind1 = ind2, ind1, i
+            elif s > max2:
+                max3, max2 = max2, s
+                ind3, ind2 = ind2, i
+            elif s > max3:
+                max3, ind3 = s, i
+        if f32(max2) < f32(f32(0.1) * f32(max1)):
+            ind2 = ind3 = -1
+        elif f32(max3) < f32(f32(0.1) * f32(max1)):
+            ind3 = -1
+        for i in range(HISTO_LENGTH):
+            if i != ind1 and i != ind2 and i != ind3:
+                for idx in rot_hist[i]:
+                    holder[idx] = -2
+                    nmatches -= 1
+    return match_key, match_dist, holder, nmatches
+
+
 def glibc_rand(seed, n):
     out = np.zeros(n, np.int32)
     lib().orc_glibc_rand(int(seed), n, _p(out))
