@@ -151,4 +151,14 @@ struct ChunkPipe {
   }
 };
 
+// what bow.cu needs of an ORB handle's last batch (defined in orb.cu, where struct drfe_orb lives)
+struct OrbBatchView {
+  int device, nframes, cap;
+  bool pending;
+  cudaStream_t stream;
+  const uint8_t* desc;  // [B][cap][32]
+  const int* cnt;       // [B]
+};
+int orb_batch_view(drfe_orb* h, OrbBatchView* v);
+
 }  // namespace drfe

@@ -1803,6 +1803,13 @@ static int orb_build(drfe_orb* h) {
   return DRFE_OK;
 }
 
+int drfe::orb_batch_view(drfe_orb* h, OrbBatchView* v) {
+  if (!h || !v) return DRFE_ERR_ARG;
+  v->device = h->device; v->nframes = h->last_frames; v->cap = h->hd.kp_cap; v->pending = h->pending; v->stream = h->stream;
+  v->desc = h->hd.out_desc; v->cnt = h->hd.out_cnt;
+  return DRFE_OK;
+}
+
 extern "C" {
 
 int drfe_orb_create(const drfe_orb_params* params, int width, int height, int max_batch, int device,

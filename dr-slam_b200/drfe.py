@@ -69,7 +69,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -118,6 +118,11 @@ def lib():
     L.drfe_frame_image_bounds.argtypes = [vp, C.c_int, C.c_int]
     L.drfe_orb_frame_post.argtypes = [vp, vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     L.drfe_orb_search_by_projection.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.drfe_vocab_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.drfe_vocab_destroy.argtypes = [vp]
+    L.drfe_vocab_destroy.restype = None
+    L.drfe_vocab_words.argtypes = [vp]
+    L.drfe_orb_compute_bow.argtypes = [vp, vp, C.c_int] + [vp] * 9
     L.drfe_orb_search_last_frame.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
@@ -223,6 +228,35 @@ def _stage_times(fn, h):
     n = C.c_int32(0)
     _check(fn(h, C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), 16, C.byref(n)))
     return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+
+class Vocabulary:
+    """ORBVocabulary on the device, from the arrays TemplatedVocabulary::loadFromTextFile parses"""
+
+    def __init__(self, k, L, scoring, weighting, parent, is_leaf, descriptors, weights, device=0):
+        self.L_ = lib()
+        parent = np.ascontiguousarray(parent, np.int32)
+        is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        descriptors = np.ascontiguousarray(descriptors, np.uint8)
+        weights = np.ascontiguousarray(weights, np.float64)
+        assert descriptors.shape == (len(parent), 32) and len(is_leaf) == len(parent) == len(weights)
+        self.h = C.c_void_p()
+        _check(self.L_.drfe_vocab_create(k, L, scoring, weighting, len(parent), _ptr(parent), _ptr(is_leaf), _ptr(descriptors),
+                                         _ptr(weights), device, C.byref(self.h)))
+
+    def words(self):
+        return self.L_.drfe_vocab_words(self.h)
+
+    def close(self):
+        if self.h:
+            self.L_.drfe_vocab_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ORBextractor:
@@ -381,6 +415,22 @@ class ORBextractor:
         _check(self.L.drfe_orb_search_last_frame(self.h, _ptr(tp), _ptr(npts), _ptr(points), _ptr(pdesc), _ptr(occupied), pcap,
                                                  _ptr(mk), _ptr(md), _ptr(kp), _ptr(nm), _ptr(sw)))
         return mk, md, kp, nm, sw
+
+    def compute_bow(self, vocab, levelsup=4):
+        """Frame::ComputeBoW (Frame.cc:828-833) on the last batch's descriptors -> per frame (word_id, node_id,
+        [(word, value)], [(node, [indices])])"""
+        nf, cap = self._nframes, self.cap
+        wid, nid = np.zeros((nf, cap), np.int32), np.zeros((nf, cap), np.int32)
+        bn, bw, bv = np.zeros(nf, np.int32), np.zeros((nf, cap), np.int32), np.zeros((nf, cap), np.float64)
+        fn, fnode, fstart, ffeat = np.zeros(nf, np.int32), np.zeros((nf, cap), np.int32), np.zeros((nf, cap + 1), np.int32), np.zeros((nf, cap), np.int32)
+        _check(self.L.drfe_orb_compute_bow(self.h, vocab.h, levelsup, _ptr(wid), _ptr(nid), _ptr(bn), _ptr(bw), _ptr(bv), _ptr(fn),
+                                           _ptr(fnode), _ptr(fstart), _ptr(ffeat)))
+        out = []
+        for f in range(nf):
+            bow = [(int(bw[f, j]), float(bv[f, j])) for j in range(bn[f])]
+            fv = [(int(fnode[f, j]), ffeat[f, fstart[f, j]:fstart[f, j + 1]].tolist()) for j in range(fn[f])]
+            out.append((wid[f], nid[f], bow, fv))
+        return out
 
     def sync(self):
         _check(self.L.drfe_orb_sync(self.h))

@@ -238,6 +238,34 @@ int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const i
                                int pcap, int32_t* match_key, int32_t* match_dist, int32_t* key_point,
                                int* nmatches, int* sweeps);
 
+/* ------------------------------------------------------------------ Frame::ComputeBoW
+ * Frame::ComputeBoW (Frame.cc:828-833) = ORBVocabulary::transform(descriptors, mBowVec, mFeatVec, 4)
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1194): every descriptor descends the vocabulary tree
+ * (:1217-1258: at each node the child at the smallest FORB::distance, first minimum wins, FORB.cpp:81-101) to a word;
+ * BowVector::addWeight sums the word's weight once per descriptor (BowVector.cpp:34-46), BowVector::normalize divides by
+ * the L1 / L2 norm accumulated in word order (:62-84); FeatureVector::addFeature lists the descriptor indices per node at
+ * level L - levelsup (FeatureVector.cpp:31-45).  The vocabulary is given as the arrays
+ * TemplatedVocabulary::loadFromTextFile parses (TemplatedVocabulary.h:1338-1422): node i + 1 of the file is row i. */
+typedef struct drfe_vocab drfe_vocab;
+/* k, L, scoring, weighting: the header line of the vocabulary file (m_k, m_L, ScoringType, WeightingType; the ORB
+ * vocabulary of ORB-SLAM2 is 10 6 0 0 = L1_NORM, TF_IDF).  Rows i < nnodes: parent[i] (node id of the parent; 0 = root),
+ * is_leaf[i], descriptors[32*i ..], weights[i].  Word ids are assigned to the leaves in file order (:1408-1415).
+ * Scorings whose mustNormalize() is true (L1_NORM, L2_NORM, the ones ORB-SLAM uses) are supported. */
+int drfe_vocab_create(int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
+                      const uint8_t* is_leaf, const uint8_t* descriptors, const double* weights, int device,
+                      drfe_vocab** out);
+void drfe_vocab_destroy(drfe_vocab* v);
+int drfe_vocab_words(const drfe_vocab* v); /* m_words.size() */
+/* transform() of the device-resident descriptors of the handle's last batch (same device as the vocabulary).
+ * Outputs on the host, any may be NULL, cap = the handle's max_keypoints:
+ *   word_id / node_id [f*cap + i]  the word and the level-(L - levelsup) node of descriptor i (-1 = word stopped, weight 0)
+ *   bow_n[f], bow_word / bow_value [f*cap + j]   mBowVec in key order (std::map iteration order)
+ *   fv_n[f], fv_node [f*cap + j], fv_start [f*(cap+1) + j], fv_feat [f*cap + ..]   mFeatVec in key order: the descriptor
+ *   indices of node fv_node[j] are fv_feat[fv_start[j] .. fv_start[j+1]) (ascending, the push_back order). */
+int drfe_orb_compute_bow(drfe_orb* h, const drfe_vocab* v, int levelsup, int32_t* word_id, int32_t* node_id,
+                         int* bow_n, int32_t* bow_word, double* bow_value, int* fv_n, int32_t* fv_node,
+                         int32_t* fv_start, int32_t* fv_feat);
+
 /* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
  * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
  * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */

@@ -455,6 +455,121 @@ def search_last_frame(p, scale_factors, keys_un, u_right, grid_count, grid_index
     return match_key, match_dist, holder, nmatches
 
 
+class Vocabulary:
+    """DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB> as ORB-SLAM uses it (reference Thirdparty/DBoW2/DBoW2/
+    TemplatedVocabulary.h), built from the arrays loadFromTextFile parses (:1338-1422): row i = node i + 1 of the file."""
+
+    def __init__(self, k, L, scoring, weighting, parent, is_leaf, descriptors, weights):
+        self.k, self.L, self.scoring, self.weighting = k, L, scoring, weighting
+        n = len(parent)
+        self.children = [[] for _ in range(n + 1)]
+        self.desc = np.zeros((n + 1, 32), np.uint8)
+        self.weight = [0.0] * (n + 1)
+        self.word_id = [0] * (n + 1)
+        self.nwords = 0
+        for i in range(n):
+            nid = i + 1
+            self.children[int(parent[i])].append(nid)            # :1391
+            self.desc[nid] = descriptors[i]
+            self.weight[nid] = float(weights[i])
+            if is_leaf[i]:                                       # :1408-1415
+                self.word_id[nid] = self.nwords
+                self.nwords += 1
+        self.desc32 = self.desc.view(np.uint32)
+
+    def transform_one(self, feature32, levelsup):
+        """transform(feature, word_id, weight, nid, levelsup) (:1217-1258)"""
+        nid_level = self.L - levelsup
+        nid = 0 if nid_level <= 0 else None
+        final_id, current_level = 0, 0
+        while True:
+            current_level += 1
+            nodes = self.children[final_id]
+            final_id = nodes[0]
+            best_d = descriptor_distance(feature32, self.desc32[final_id])   # FORB::distance (FORB.cpp:81-101)
+            for cid in nodes[1:]:
+                d = descriptor_distance(feature32, self.desc32[cid])
+                if d < best_d:
+                    best_d, final_id = d, cid
+            if current_level == nid_level:
+                nid = final_id
+            if not self.children[final_id]:
+                break
+        if nid is None:        # *nid is uninitialised in the reference when a leaf sits above level L - levelsup; declared: the leaf
+            nid = final_id
+        return self.word_id[final_id], self.weight[final_id], nid
+
+    def transform(self, descriptors, levelsup=4):
+        """transform(features, BowVector&, FeatureVector&, levelsup) (:1126-1194) with BowVector::addWeight /
+        addIfNotExist / normalize (BowVector.cpp:34-84) and FeatureVector::addFeature (FeatureVector.cpp:31-45).
+        Returns (word_id[i], node_id[i]) per descriptor (-1: stopped), the BowVector as [(word, value)] and the
+        FeatureVector as [(node, [indices])], both in std::map iteration order."""
+        d32 = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32).view(np.uint32)
+        v, fv = {}, {}
+        words, nodes = np.full(len(d32), -1, np.int32), np.full(len(d32), -1, np.int32)
+        must = self.scoring != 5                                  # ScoringObject.h:73-89
+        for i in range(len(d32)):
+            wid, w, nid = self.transform_one(d32[i], levelsup)
+            if w > 0:
+                if self.weighting <= 1:                           # TF_IDF, TF
+                    if wid in v:
+                        v[wid] += w
+                    else:
+                        v[wid] = w
+                elif wid not in v:                                # IDF, BINARY
+                    v[wid] = w
+                fv.setdefault(nid, []).append(i)
+                words[i], nodes[i] = wid, nid
+        keys = sorted(v)
+        if self.weighting <= 1 and v and not must:
+            nd = float(len(v))
+            for k in keys:
+                v[k] /= nd
+        if must:
+            norm = 0.0
+            if self.scoring != 1:                                 # L1
+                for k in keys:
+                    norm += abs(v[k])
+            else:
+                for k in keys:
+                    norm += v[k] * v[k]
+                norm = float(np.sqrt(np.float64(norm)))
+            if norm > 0.0:
+                for k in keys:
+                    v[k] /= norm
+        return words, nodes, [(k, v[k]) for k in keys], [(k, fv[k]) for k in sorted(fv)]
+
+
+def synth_vocabulary(k, L, seed, scoring=0, weighting=0, ragged=False):
+    """A random k-ary tree of depth L in the file layout of ORBvoc.txt (nodes written level by level, a node's children
+    next to each other): child descriptors = the parent's with bits flipped (so descents are decided by few bits and
+    ties occur), idf-like weights, a few stopped words (weight 0); ragged: some subtrees end early and some nodes have
+    fewer children."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, wt = [], [], [], []
+    frontier = [(0, np.zeros(32, np.uint8), 0)]
+    nid = 0
+    while frontier:
+        nxt = []
+        for pid, pdesc, depth in frontier:
+            nk = k if not ragged else int(rng.integers(2, k + 1))
+            for c in range(nk):
+                nid += 1
+                d = pdesc.copy()
+                for b in rng.integers(0, 256, max(2, 96 >> depth)):
+                    d[b >> 3] ^= 1 << (b & 7)
+                if c and rng.random() < 0.08:
+                    d = desc[-1].copy()                           # duplicate of the previous sibling: a tie, the first wins
+                is_leaf = depth + 1 == L or (ragged and depth + 1 >= 3 and rng.random() < 0.1)
+                parent.append(pid); leaf.append(1 if is_leaf else 0); desc.append(d)
+                wt.append((0.0 if rng.random() < 0.03 else float(rng.uniform(0.5, 9.0))) if is_leaf else 0.0)
+                if not is_leaf:
+                    nxt.append((nid, d, depth + 1))
+        frontier = nxt
+    return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=np.array(parent, np.int32), is_leaf=np.array(leaf, np.uint8),
+                descriptors=np.array(desc, np.uint8), weights=np.array(wt, np.float64))
+
+
 def glibc_rand(seed, n):
     out = np.zeros(n, np.int32)
     lib().orc_glibc_rand(int(seed), n, _p(out))
