@@ -156,6 +156,137 @@ __global__ void __launch_bounds__(256) k_bow_reduce(const int* __restrict__ cnt,
   if (tid == 0) O.fv_n[f] = nn;
 }
 
+// ------------------------------------------------------------------ ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches)
+// (reference src/ORBmatcher.cc:160-292).  CTA per frame, warp per vocabulary node present in both FeatureVectors.  Inside a
+// node the reference walks the keyframe's features in order and skips frame features an earlier one matched (:218-219);
+// the warp repeats parallel sweeps against owner[idx] = the earliest position that chose idx in the previous sweep until
+// nothing changes, which is the reference's in-order result (see k_search_last_frame in orb.cu).
+struct BowSearchDev {
+  const int* kf_n; const uint8_t* kf_desc; const float* kf_angle; const uint8_t* kf_valid;
+  const int* kf_fv_n; const int* kf_fv_node; const int* kf_fv_start; const int* kf_fv_feat;
+  const int* f_fv_n; const int* f_fv_node; const int* f_fv_start; const int* f_fv_feat;
+  int* kf_match; int* f_match; int* nmatches;
+  int kcap; float nnratio; int check_orientation;
+};
+__global__ void __launch_bounds__(256) k_search_bow(const uint8_t* __restrict__ fdesc, const drfe_keypoint* __restrict__ fkp,
+                                                    const int* __restrict__ fcnt, int cap, BowSearchDev S) {
+  extern __shared__ int s_dyn[];
+  __shared__ int s_hist[DRFE_HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  __shared__ int s_cnt[2];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kcap = S.kcap;
+  int* owner = s_dyn;            // [cap]   by frame feature
+  int* choice = s_dyn + cap;     // [kcap]  by keyframe feature: bestIdxF if accepted, else -1
+  const int nk = min(S.kf_n[f], kcap), nF = min(fcnt[f], cap);
+  const uint32_t* FD = reinterpret_cast<const uint32_t*>(fdesc + (long long)f * cap * 32);
+  const uint32_t* KD = reinterpret_cast<const uint32_t*>(S.kf_desc + (long long)f * kcap * 32);
+  const uint8_t* kvalid = S.kf_valid + (long long)f * kcap;
+  const int* knode = S.kf_fv_node + (long long)f * kcap;
+  const int* kstart = S.kf_fv_start + (long long)f * (kcap + 1);
+  const int* kfeat = S.kf_fv_feat + (long long)f * kcap;
+  const int* fnode = S.f_fv_node + (long long)f * cap;
+  const int* fstart = S.f_fv_start + (long long)f * (cap + 1);
+  const int* ffeat = S.f_fv_feat + (long long)f * cap;
+  const int nkn = min(S.kf_fv_n[f], kcap), nfn = min(S.f_fv_n[f], cap);
+  for (int i = tid; i < kcap; i += 256) choice[i] = -1;
+  for (int i = tid; i < cap; i += 256) owner[i] = 0x7fffffff;
+  __syncthreads();
+  for (int j = warp; j < nkn; j += 8) {
+    // the node of the frame's FeatureVector with the same id (:186-261 is a sorted intersection)
+    const int id = knode[j];
+    int lo = 0, hi = nfn;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (fnode[mid] < id) lo = mid + 1; else hi = mid; }
+    if (lo >= nfn || fnode[lo] != id) continue;
+    const int a0 = kstart[j], na = kstart[j + 1] - a0, b0 = fstart[lo], nb = fstart[lo + 1] - b0;
+    for (;;) {
+      for (int t = lane; t < nb; t += 32) { const int idx = ffeat[b0 + t]; if (idx >= 0 && idx < nF) owner[idx] = 0x7fffffff; }
+      __syncwarp();
+      for (int t = lane; t < na; t += 32) { const int c = choice[kfeat[a0 + t]]; if (c >= 0) atomicMin(&owner[c], t); }
+      __syncwarp();
+      int changed = 0;
+      for (int t = lane; t < na; t += 32) {
+        const int ik = kfeat[a0 + t];
+        int c = -1;
+        if (ik >= 0 && ik < nk && kvalid[ik]) {                                   // :196-202
+          uint32_t d[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = KD[ik * 8 + k];
+          int best1 = 256, best2 = 256, bidx = -1;
+          for (int u = 0; u < nb; ++u) {
+            const int idx = ffeat[b0 + u];
+            if (idx < 0 || idx >= nF) continue;
+            if (owner[idx] < t) continue;                                          // :218-219
+            const uint4 p = *reinterpret_cast<const uint4*>(FD + idx * 8), q = *reinterpret_cast<const uint4*>(FD + idx * 8 + 4);
+            const int dist = __popc(d[0] ^ p.x) + __popc(d[1] ^ p.y) + __popc(d[2] ^ p.z) + __popc(d[3] ^ p.w) + __popc(d[4] ^ q.x) +
+                             __popc(d[5] ^ q.y) + __popc(d[6] ^ q.z) + __popc(d[7] ^ q.w);
+            if (dist < best1) { best2 = best1; best1 = dist; bidx = idx; }
+            else if (dist < best2) best2 = dist;
+          }
+          if (best1 <= DRFE_TH_LOW && (float)best1 < __fmul_rn(S.nnratio, (float)best2)) c = bidx;   // :234-238
+        }
+        changed |= (c != choice[ik >= 0 && ik < kcap ? ik : 0]);
+        if (ik >= 0 && ik < kcap) choice[ik] = c;
+      }
+      if (!__any_sync(0xffffffffu, changed)) break;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // rotation consistency (:244-254, 271-289)
+  if (tid < DRFE_HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid < 2) s_cnt[tid] = 0;
+  for (int i = tid; i < cap; i += 256) owner[i] = -1;                            // becomes f_match
+  __syncthreads();
+  const float factor = 1.0f / DRFE_HISTO_LENGTH;
+  const float* kang = S.kf_angle + (long long)f * kcap;
+  const drfe_keypoint* kp = fkp + (long long)f * cap;
+  auto rot_bin = [&](int i) {
+    float rot = __fsub_rn(kang[i], kp[choice[i]].angle);
+    if (rot < 0.f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == DRFE_HISTO_LENGTH) bin = 0;
+    return bin;
+  };
+  int mine = 0;
+  for (int i = tid; i < nk; i += 256)
+    if (choice[i] >= 0) {
+      ++mine;
+      owner[choice[i]] = i;                                                        // a frame feature is matched at most once
+      if (S.check_orientation) { const int b = rot_bin(i); if (b >= 0 && b < DRFE_HISTO_LENGTH) atomicAdd(&s_hist[b], 1); }
+    }
+  if (mine) atomicAdd(&s_cnt[0], mine);
+  __syncthreads();
+  if (tid == 0) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    if (S.check_orientation) {                                                    // ComputeThreeMaxima (:1666-1707)
+      int max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < DRFE_HISTO_LENGTH; ++i) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+    }
+    s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+  }
+  __syncthreads();
+  if (S.check_orientation) {
+    int removed = 0;
+    for (int i = tid; i < nk; i += 256)
+      if (choice[i] >= 0) {
+        const int b = rot_bin(i);
+        if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { owner[choice[i]] = -1; ++removed; }
+      }
+    if (removed) atomicAdd(&s_cnt[1], removed);
+  }
+  __syncthreads();
+  for (int i = tid; i < cap; i += 256) S.f_match[(long long)f * cap + i] = owner[i];
+  for (int i = tid; i < kcap; i += 256) S.kf_match[(long long)f * kcap + i] = choice[i];
+  if (tid == 0) S.nmatches[f] = s_cnt[0] - s_cnt[1];
+}
+
 }  // namespace drfe
 
 using namespace drfe;
@@ -283,5 +414,76 @@ int drfe_orb_compute_bow(drfe_orb* h, const drfe_vocab* vc, int levelsup, int32_
   DRFE_CUDA(d2h(fv_start, O.fv_start, (size_t)nf * (cap + 1) * 4));
   DRFE_CUDA(d2h(fv_feat, O.fv_feat, items * 4));
   DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+int drfe_orb_search_by_bow(drfe_orb* h, int kcap, const int* kf_n, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                           const int* kf_fv_n, const int32_t* kf_fv_node, const int32_t* kf_fv_start, const int32_t* kf_fv_feat,
+                           const int* f_fv_n, const int32_t* f_fv_node, const int32_t* f_fv_start, const int32_t* f_fv_feat, float nnratio,
+                           int check_orientation, int32_t* kf_match, int32_t* f_match, int* nmatches) {
+  OrbBatchView B;
+  if (orb_batch_view(h, &B) || kcap < 1 || !kf_n || !kf_desc || !kf_angle || !kf_valid || !kf_fv_n || !kf_fv_node || !kf_fv_start ||
+      !kf_fv_feat || !f_fv_n || !f_fv_node || !f_fv_start || !f_fv_feat) {
+    set_error("drfe_orb_search_by_bow: bad argument"); return DRFE_ERR_ARG;
+  }
+  if (!B.pending) { set_error("drfe_orb_search_by_bow: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(B.device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  const int nf = B.nframes, cap = B.cap;
+  for (int f = 0; f < nf; ++f) {
+    if (kf_n[f] < 0 || kf_n[f] > kcap || kf_fv_n[f] < 0 || kf_fv_n[f] > kcap || f_fv_n[f] < 0 || f_fv_n[f] > cap) {
+      set_error("drfe_orb_search_by_bow: frame %d: counts out of range", f); return DRFE_ERR_ARG;
+    }
+    // the lists a FeatureVector can hold: ascending node ids, starts ascending within the feature array
+    for (int j = 0; j < kf_fv_n[f]; ++j) {
+      const int32_t* st = kf_fv_start + (size_t)f * (kcap + 1);
+      if (st[j] < 0 || st[j + 1] < st[j] || st[j + 1] > kcap || (j && kf_fv_node[(size_t)f * kcap + j] <= kf_fv_node[(size_t)f * kcap + j - 1])) {
+        set_error("drfe_orb_search_by_bow: frame %d: keyframe FeatureVector entry %d is malformed", f, j); return DRFE_ERR_ARG;
+      }
+    }
+    for (int j = 0; j < f_fv_n[f]; ++j) {
+      const int32_t* st = f_fv_start + (size_t)f * (cap + 1);
+      if (st[j] < 0 || st[j + 1] < st[j] || st[j + 1] > cap || (j && f_fv_node[(size_t)f * cap + j] <= f_fv_node[(size_t)f * cap + j - 1])) {
+        set_error("drfe_orb_search_by_bow: frame %d: frame FeatureVector entry %d is malformed", f, j); return DRFE_ERR_ARG;
+      }
+    }
+  }
+  const size_t smem = ((size_t)cap + kcap) * sizeof(int);
+  if (smem > 200 * 1024) { set_error("drfe_orb_search_by_bow: kcap %d too large", kcap); return DRFE_ERR_CAPACITY; }
+  cudaStream_t st = B.stream;
+  // one stream-ordered scratch block per call
+  const size_t nk = (size_t)nf * kcap, nc = (size_t)nf * cap;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_desc = take(nk * 32), o_ang = take(nk * 4), o_val = take(nk), o_kn = take((size_t)nf * 4), o_kfn = take((size_t)nf * 4),
+               o_knode = take(nk * 4), o_kstart = take((size_t)nf * (kcap + 1) * 4), o_kfeat = take(nk * 4), o_ffn = take((size_t)nf * 4),
+               o_fnode = take(nc * 4), o_fstart = take((size_t)nf * (cap + 1) * 4), o_ffeat = take(nc * 4), o_km = take(nk * 4),
+               o_fm = take(nc * 4), o_nm = take((size_t)nf * 4);
+  char* d = nullptr;
+  DRFE_CUDA(cudaMallocAsync((void**)&d, off, st));
+  auto up = [&](size_t o, const void* src, size_t bytes) { return cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, st); };
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  acc(up(o_desc, kf_desc, nk * 32)); acc(up(o_ang, kf_angle, nk * 4)); acc(up(o_val, kf_valid, nk)); acc(up(o_kn, kf_n, (size_t)nf * 4));
+  acc(up(o_kfn, kf_fv_n, (size_t)nf * 4)); acc(up(o_knode, kf_fv_node, nk * 4)); acc(up(o_kstart, kf_fv_start, (size_t)nf * (kcap + 1) * 4));
+  acc(up(o_kfeat, kf_fv_feat, nk * 4)); acc(up(o_ffn, f_fv_n, (size_t)nf * 4)); acc(up(o_fnode, f_fv_node, nc * 4));
+  acc(up(o_fstart, f_fv_start, (size_t)nf * (cap + 1) * 4)); acc(up(o_ffeat, f_fv_feat, nc * 4));
+  BowSearchDev S;
+  S.kf_n = (const int*)(d + o_kn); S.kf_desc = (const uint8_t*)(d + o_desc); S.kf_angle = (const float*)(d + o_ang); S.kf_valid = (const uint8_t*)(d + o_val);
+  S.kf_fv_n = (const int*)(d + o_kfn); S.kf_fv_node = (const int*)(d + o_knode); S.kf_fv_start = (const int*)(d + o_kstart); S.kf_fv_feat = (const int*)(d + o_kfeat);
+  S.f_fv_n = (const int*)(d + o_ffn); S.f_fv_node = (const int*)(d + o_fnode); S.f_fv_start = (const int*)(d + o_fstart); S.f_fv_feat = (const int*)(d + o_ffeat);
+  S.kf_match = (int*)(d + o_km); S.f_match = (int*)(d + o_fm); S.nmatches = (int*)(d + o_nm);
+  S.kcap = kcap; S.nnratio = nnratio; S.check_orientation = check_orientation;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_search_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    k_search_bow<<<nf, 256, smem, st>>>(B.desc, B.kp, B.cnt, cap, S);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+  }
+  auto down = [&](void* dst, size_t o, size_t bytes) { if (dst && e == cudaSuccess) e = cudaMemcpyAsync(dst, d + o, bytes, cudaMemcpyDeviceToHost, st); };
+  down(kf_match, o_km, nk * 4); down(f_match, o_fm, nc * 4); down(nmatches, o_nm, (size_t)nf * 4);
+  cudaFreeAsync(d, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { set_error("drfe_orb_search_by_bow: %s", cudaGetErrorString(e)); return DRFE_ERR_CUDA; }
   return DRFE_OK;
 }

@@ -158,6 +158,7 @@ struct OrbBatchView {
   cudaStream_t stream;
   const uint8_t* desc;  // [B][cap][32]
   const int* cnt;       // [B]
+  const drfe_keypoint* kp;  // [B][cap] mvKeys
 };
 int orb_batch_view(drfe_orb* h, OrbBatchView* v);
 

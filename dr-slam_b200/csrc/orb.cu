@@ -1806,7 +1806,7 @@ static int orb_build(drfe_orb* h) {
 int drfe::orb_batch_view(drfe_orb* h, OrbBatchView* v) {
   if (!h || !v) return DRFE_ERR_ARG;
   v->device = h->device; v->nframes = h->last_frames; v->cap = h->hd.kp_cap; v->pending = h->pending; v->stream = h->stream;
-  v->desc = h->hd.out_desc; v->cnt = h->hd.out_cnt;
+  v->desc = h->hd.out_desc; v->cnt = h->hd.out_cnt; v->kp = h->hd.out_kp;
   return DRFE_OK;
 }
 

@@ -266,6 +266,28 @@ int drfe_orb_compute_bow(drfe_orb* h, const drfe_vocab* v, int levelsup, int32_t
                          int* bow_n, int32_t* bow_word, double* bow_value, int* fv_n, int32_t* fv_node,
                          int32_t* fv_start, int32_t* fv_feat);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (ORBmatcher.cc:160-292), whole:
+ * frame f of the handle's last batch is F, matched against one keyframe per frame.  For every vocabulary node both
+ * FeatureVectors hold (:186-261, a sorted intersection), every keyframe feature with a good map point looks for its
+ * best / second best descriptor among F's features of that node that are not matched yet (:200-232), accepts with
+ * bestDist1 <= TH_LOW and the ratio test (:234-238), then the rotation histogram (:244-254, 271-289).  The reference's
+ * "not matched yet" makes the loop sequential inside a node; the device reaches the same result as the fixed point of
+ * parallel sweeps (a warp per node), as drfe_orb_search_last_frame does.  Nodes are independent of each other.
+ * Keyframe side (host): kf_n[f] features, kf_desc[(f*kcap + i)*32 ..] (pKF->mDescriptors), kf_angle[f*kcap + i]
+ * (pKF->mvKeysUn[i].angle), kf_valid[f*kcap + i] != 0: vpMapPointsKF[i] && !isBad(); its FeatureVector kf_fv_n[f],
+ * kf_fv_node[f*kcap + j], kf_fv_start[f*(kcap+1) + j], kf_fv_feat[f*kcap + ..].  Frame side: its FeatureVector in the
+ * layout drfe_orb_compute_bow returns (cap = max_keypoints); descriptors and angles are on the device.
+ * Outputs (host, any may be NULL): kf_match[f*kcap + i] = bestIdxF of keyframe feature i or -1, BEFORE the rotation check;
+ * f_match[f*cap + idx] = the keyframe feature whose map point vpMapPointMatches[idx] holds on return, or -1 (NULL);
+ * nmatches[f] = the return value. */
+#define DRFE_TH_LOW 50 /* ORBmatcher::TH_LOW (ORBmatcher.cc:39) */
+int drfe_orb_search_by_bow(drfe_orb* h, int kcap, const int* kf_n, const uint8_t* kf_desc, const float* kf_angle,
+                           const uint8_t* kf_valid, const int* kf_fv_n, const int32_t* kf_fv_node,
+                           const int32_t* kf_fv_start, const int32_t* kf_fv_feat, const int* f_fv_n,
+                           const int32_t* f_fv_node, const int32_t* f_fv_start, const int32_t* f_fv_feat,
+                           float nnratio, int check_orientation, int32_t* kf_match, int32_t* f_match,
+                           int* nmatches);
+
 /* mvImagePyramid access (ORBextractor.h:85) and per-stage intermediates, copied to host.
  * bordered != 0 returns the (w+38)x(h+38) buffer including the 19-px BORDER_REFLECT_101
  * frame that ComputePyramid builds (ORBextractor.cc:1107-1132). */

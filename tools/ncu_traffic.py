@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 STAGE = {"k_fast_strips": "fast", "k_quadtree": "quadtree", "k_blur": "blur", "k_orient_describe": "orient_describe",
-         "k_cape_sums": "cells", "k_cape_fit": "fit", "k_cape_grid": "grid", "k_cape_refine": "refine",
+         "k_cape_sums": "cells", "k_cape_fit": "fit", "k_cape_edges": "fit", "k_cape_grid": "grid", "k_cape_refine": "refine",
          "k_pyr_stream": "pyramid", "k_pyr_level0": "pyramid"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 

@@ -48,6 +48,38 @@ def main():
     QD = np.take_along_axis(desc, src[:, :, None], 1)
     ms, m = timed(lambda: orb.search_by_projection(Q, QD))
     print("drfe_orb_search_by_projection  %7.2f ms per %d frames x 1000 queries (%.1f%% matched)" % (ms, B, 100.0 * (m["best_idx"] >= 0).mean()))
+    # ORBmatcher::SearchByProjection(CurrentFrame, LastFrame): 1000 last-frame points per frame, identity pose
+    tp = np.zeros(B, drfe.TRACK_PARAMS_DTYPE)
+    tp["Tcw"] = np.eye(3, 4, dtype=np.float32).ravel()
+    tp["th"], tp["check_orientation"] = 15.0, 1
+    P = np.zeros((B, 1000), drfe.LAST_POINT_DTYPE)
+    z = np.where(np.take_along_axis(kd, src, 1) > 0, np.take_along_axis(kd, src, 1), 2.0)
+    P["X"], P["Y"], P["Z"] = (Q["x"] - K[2]) * z / K[0], (Q["y"] - K[3]) * z / K[1], z
+    P["angle"] = np.take_along_axis(ku["angle"], src, 1)
+    P["octave"], P["flags"] = lv, drfe.LP_VALID | drfe.LP_OBSERVED
+    ms, r = timed(lambda: orb.search_last_frame(tp, P, QD))
+    print("drfe_orb_search_last_frame     %7.2f ms per %d frames x 1000 points (%.1f matches per frame, %.1f sweeps)" % (ms, B, r[3].mean(), r[4].mean()))
+    # Frame::ComputeBoW against a vocabulary of the ORB vocabulary's size (k = 10, L = 6: 1 111 110 nodes, 10^6 words)
+    k, L = 10, 6
+    sizes = [k ** l for l in range(1, L + 1)]
+    first = np.cumsum([1] + sizes)                                     # node id of the first node of level l + 1
+    parent = np.concatenate([np.repeat(np.arange(first[l] - (sizes[l - 1] if l else 1), first[l]), k) for l in range(L)]).astype(np.int32)
+    nn = len(parent)
+    leaf = np.zeros(nn, np.uint8)
+    leaf[-sizes[-1]:] = 1
+    vd = rng.integers(0, 256, (nn, 32), dtype=np.uint8)
+    wt = np.where(leaf > 0, rng.uniform(0.5, 9.0, nn), 0.0)
+    t0 = time.perf_counter()
+    voc = drfe.Vocabulary(k, L, 0, 0, parent, leaf, vd, wt)
+    print("drfe_vocab_create              %7.2f ms (%d nodes, %d words, %d MB on the device)" % ((time.perf_counter() - t0) * 1e3, nn, voc.words(), nn * 52 >> 20))
+    L_ = orb.L
+    bn, fn = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    bw, bv = np.zeros((B, orb.cap), np.int32), np.zeros((B, orb.cap), np.float64)
+    fnode, fstart, ffeat = np.zeros((B, orb.cap), np.int32), np.zeros((B, orb.cap + 1), np.int32), np.zeros((B, orb.cap), np.int32)
+    vp = lambda a: a.ctypes.data
+    ms, _ = timed(lambda: L_.drfe_orb_compute_bow(orb.h, voc.h, 4, None, None, vp(bn), vp(bw), vp(bv), vp(fn), vp(fnode), vp(fstart), vp(ffeat)))
+    print("drfe_orb_compute_bow           %7.2f ms per %d frames (%.0f words, %.0f nodes per frame)" % (ms, B, bn.mean(), fn.mean()))
+    voc.close()
     ms, (pts, offs) = timed(lambda: cape.plane_points(B), n=3)
     print("drfe_cape_plane_points         %7.2f ms per %d frames (%d MB of points D2H, pageable destination)" % (ms, B, int(offs.max(1).sum()) * 12 >> 20))
     # the same into pinned host memory (what a caller that cares would pass)
