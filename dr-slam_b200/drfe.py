@@ -69,7 +69,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_search_by_bow",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -123,6 +123,7 @@ def lib():
     L.drfe_vocab_destroy.restype = None
     L.drfe_vocab_words.argtypes = [vp]
     L.drfe_orb_compute_bow.argtypes = [vp, vp, C.c_int] + [vp] * 9
+    L.drfe_orb_search_by_bow.argtypes = [vp, C.c_int] + [vp] * 12 + [C.c_float, C.c_int, vp, vp, vp]
     L.drfe_orb_search_last_frame.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
@@ -431,6 +432,40 @@ class ORBextractor:
             fv = [(int(fnode[f, j]), ffeat[f, fstart[f, j]:fstart[f, j + 1]].tolist()) for j in range(fn[f])]
             out.append((wid[f], nid[f], bow, fv))
         return out
+
+    @staticmethod
+    def pack_feature_vectors(fvs, cap):
+        """[(node, [indices])] per frame -> the flat layout of drfe_orb_compute_bow / drfe_orb_search_by_bow"""
+        nf = len(fvs)
+        n, node, start, feat = np.zeros(nf, np.int32), np.zeros((nf, cap), np.int32), np.zeros((nf, cap + 1), np.int32), np.zeros((nf, cap), np.int32)
+        for f, fv in enumerate(fvs):
+            n[f] = len(fv)
+            o = 0
+            for j, (nid, idx) in enumerate(fv):
+                node[f, j], start[f, j] = nid, o
+                feat[f, o:o + len(idx)] = idx
+                o += len(idx)
+            start[f, len(fv)] = o
+        return n, node, start, feat
+
+    def search_by_bow(self, kf_n, kf_desc, kf_angle, kf_valid, kf_fvs, f_fvs, nnratio=0.7, check_orientation=True):
+        """ORBmatcher::SearchByBoW(pKF, F, matches) (ORBmatcher.cc:160-292), frame f of the last batch against keyframe f:
+        kf_desc (nf, kcap, 32), kf_angle / kf_valid (nf, kcap), FeatureVectors as [(node, [indices])] per frame
+        -> (kf_match (nf, kcap), f_match (nf, cap), nmatches (nf,))"""
+        nf = self._nframes
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8)
+        kcap = kf_desc.shape[1]
+        kf_angle = np.ascontiguousarray(kf_angle, np.float32)
+        kf_valid = np.ascontiguousarray(kf_valid, np.uint8)
+        kf_n = np.ascontiguousarray(kf_n, np.int32)
+        assert kf_desc.shape == (nf, kcap, 32) and kf_angle.shape == (nf, kcap) == kf_valid.shape
+        kn, knode, kstart, kfeat = self.pack_feature_vectors(kf_fvs, kcap)
+        fn, fnode, fstart, ffeat = self.pack_feature_vectors(f_fvs, self.cap)
+        km, fm, nm = np.zeros((nf, kcap), np.int32), np.zeros((nf, self.cap), np.int32), np.zeros(nf, np.int32)
+        _check(self.L.drfe_orb_search_by_bow(self.h, kcap, _ptr(kf_n), _ptr(kf_desc), _ptr(kf_angle), _ptr(kf_valid), _ptr(kn), _ptr(knode),
+                                             _ptr(kstart), _ptr(kfeat), _ptr(fn), _ptr(fnode), _ptr(fstart), _ptr(ffeat), nnratio,
+                                             int(check_orientation), _ptr(km), _ptr(fm), _ptr(nm)))
+        return km, fm, nm
 
     def sync(self):
         _check(self.L.drfe_orb_sync(self.h))

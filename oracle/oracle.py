@@ -570,6 +570,87 @@ def synth_vocabulary(k, L, seed, scoring=0, weighting=0, ragged=False):
                 descriptors=np.array(desc, np.uint8), weights=np.array(wt, np.float64))
 
 
+TH_LOW = 50
+
+
+def search_by_bow(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv, nnratio=0.7, check_orientation=True):
+    """ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (reference
+    src/ORBmatcher.cc:160-292) restated literally: the two FeatureVectors ([(node, [indices])] in key order) walked in
+    step (:186-261; lower_bound on a mismatch), per keyframe feature with a good map point (kf_valid) the best / second
+    best among the frame's features of the node that hold no match yet, TH_LOW and ratio test, rotation histogram,
+    ComputeThreeMaxima and the removal of the other bins.  vpMapPointMatches is modelled as f_match[idx] = keyframe
+    feature index or -1 (NULL).  Returns (kf_match before the rotation check, f_match, nmatches)."""
+    f32 = np.float32
+    kd32 = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32).view(np.uint32)
+    fd32 = np.ascontiguousarray(f_desc, np.uint8).reshape(-1, 32).view(np.uint32)
+    f_match = np.full(len(fd32), -1, np.int32)
+    kf_match = np.full(len(kd32), -1, np.int32)
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = f32(1.0) / f32(HISTO_LENGTH)
+    nmatches = 0
+    ki, fi = 0, 0
+    while ki < len(kf_fv) and fi < len(f_fv):
+        if kf_fv[ki][0] == f_fv[fi][0]:
+            for real_kf in kf_fv[ki][1]:
+                if not kf_valid[real_kf]:
+                    continue
+                best1, best_idx, best2 = 256, -1, 256
+                for real_f in f_fv[fi][1]:
+                    if f_match[real_f] >= 0:
+                        continue
+                    dist = descriptor_distance(kd32[real_kf], fd32[real_f])
+                    if dist < best1:
+                        best2, best1, best_idx = best1, dist, real_f
+                    elif dist < best2:
+                        best2 = dist
+                if best1 <= TH_LOW:
+                    if f32(best1) < f32(f32(nnratio) * f32(best2)):
+                        f_match[best_idx] = real_kf
+                        kf_match[real_kf] = best_idx
+                        if check_orientation:
+                            rot = f32(f32(kf_angle[real_kf]) - f32(f_angle[best_idx]))
+                            if rot < 0.0:
+                                rot = f32(rot + f32(360.0))
+                            b = int(np.floor(np.float64(f32(rot * factor)) + 0.5))     # round(); rot >= 0 here
+                            if b == HISTO_LENGTH:
+                                b = 0
+                            assert 0 <= b < HISTO_LENGTH
+                            rot_hist[b].append(best_idx)
+                        nmatches += 1
+            ki += 1
+            fi += 1
+        elif kf_fv[ki][0] < f_fv[fi][0]:
+            while ki < len(kf_fv) and kf_fv[ki][0] < f_fv[fi][0]:     # lower_bound
+                ki += 1
+        else:
+            while fi < len(f_fv) and f_fv[fi][0] < kf_fv[ki][0]:
+                fi += 1
+    if check_orientation:
+        ind1 = ind2 = ind3 = -1
+        max1 = max2 = max3 = 0
+        for i in range(HISTO_LENGTH):
+            sz = len(rot_hist[i])
+            if sz > max1:
+                max3, max2, max1 = max2, max1, sz
+                ind3, ind2, ind1 = ind2, ind1, i
+            elif sz > max2:
+                max3, max2 = max2, sz
+                ind3, ind2 = ind2, i
+            elif sz > max3:
+                max3, ind3 = sz, i
+        if f32(max2) < f32(f32(0.1) * f32(max1)):
+            ind2 = ind3 = -1
+        elif f32(max3) < f32(f32(0.1) * f32(max1)):
+            ind3 = -1
+        for i in range(HISTO_LENGTH):
+            if i == ind1 or i == ind2 or i == ind3:
+                continue
+            for idx in rot_hist[i]:
+                f_match[idx] = -1
+                nmatches -= 1
+    return kf_match, f_match, nmatches
+
+
 def glibc_rand(seed, n):
     out = np.zeros(n, np.int32)
     lib().orc_glibc_rand(int(seed), n, _p(out))

@@ -128,3 +128,78 @@ def test_gpu_compute_bow_edge_cases(drfe, orc):
     same_maps(got[1], orc.Vocabulary(**voc).transform(desc))
     with pytest.raises(drfe.DrfeError):
         drfe.Vocabulary(10, 3, 0, 0, np.array([5], np.int32), [1], np.zeros((1, 32), np.uint8), [1.0])   # parent after the node
+
+
+# ---------------------------------------------------------------- ORBmatcher::SearchByBoW (ORBmatcher.cc:160-292)
+def make_keyframe(desc, angles, seed, n_extra=150):
+    """a keyframe that saw the same scene: the frame's descriptors with bits flipped (some heavily), shuffled, plus
+    unrelated ones; a block of identical descriptors so that several keyframe features want the same frame feature"""
+    rng = np.random.default_rng(seed)
+    n = len(desc)
+    perm = rng.permutation(n)
+    kd = desc[perm].copy()
+    for i in range(n):
+        for b in rng.integers(0, 256, int(rng.choice([0, 3, 8, 20, 60], p=[0.2, 0.3, 0.3, 0.15, 0.05]))):
+            kd[i, b >> 3] ^= 1 << (b & 7)
+    ka = np.mod(angles[perm] + rng.normal(0, 5, n) + np.where(rng.random(n) < 0.15, rng.uniform(0, 360, n), 0), 360).astype(np.float32)
+    kd[20:28] = kd[20]                                                     # eight copies: in-order occupancy decides
+    kd = np.vstack([kd, rng.integers(0, 256, (n_extra, 32), dtype=np.uint8)])
+    ka = np.concatenate([ka, rng.uniform(0, 360, n_extra).astype(np.float32)])
+    valid = (rng.random(len(kd)) < 0.85).astype(np.uint8)
+    valid[20:28] = 1
+    return kd, ka, valid
+
+
+def test_oracle_search_by_bow_properties(drfe, orc):
+    gray, desc = frame_descriptors(drfe, orc, 20260510)
+    keys, _ = orc.OrbOracle(1000).extract(gray)
+    V = orc.Vocabulary(**orc.synth_vocabulary(10, 4, 41))
+    kd, ka, valid = make_keyframe(desc, keys["angle"], 2)
+    f_fv = V.transform(desc, 2)[3]
+    kf_fv = V.transform(kd, 2)[3]
+    km, fm, nm = orc.search_by_bow(kd, ka, valid, kf_fv, desc, keys["angle"], f_fv, 0.7, True)
+    km0, fm0, nm0 = orc.search_by_bow(kd, ka, valid, kf_fv, desc, keys["angle"], f_fv, 0.7, False)
+    assert np.array_equal(km, km0) and nm0 == (km0 >= 0).sum() > 200 and nm < nm0
+    node_of_f = {i: nid for nid, l in f_fv for i in l}
+    node_of_k = {i: nid for nid, l in kf_fv for i in l}
+    ham = lambda a, b: int(np.unpackbits(a ^ b).sum())
+    m = np.nonzero(km0 >= 0)[0]
+    assert len(set(km0[m])) == len(m)                                        # a frame feature is matched once
+    for i in m:
+        assert valid[i] and node_of_k[i] == node_of_f[km0[i]] and ham(kd[i], desc[km0[i]]) <= orc.TH_LOW and fm0[km0[i]] == i
+    assert (fm0 >= 0).sum() == len(m) and (fm >= 0).sum() == nm
+    assert (km0[20:28] >= 0).sum() >= 1
+
+
+@pytest.mark.gpu
+def test_gpu_search_by_bow(drfe, orc):
+    B = 3
+    frames = [frame_descriptors(drfe, orc, 20260510 + 3 * i, scene=i % 3) for i in range(B)]
+    ex = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=B)
+    ex.enqueue(np.stack([f[0] for f in frames]))
+    kps, desc, cnt = ex.download()
+    voc = orc.synth_vocabulary(10, 4, 41)
+    V, G = orc.Vocabulary(**voc), drfe.Vocabulary(**voc)
+    bows = ex.compute_bow(G, 2)
+    kcap = 1200
+    KD, KA, KV = np.zeros((B, kcap, 32), np.uint8), np.zeros((B, kcap), np.float32), np.zeros((B, kcap), np.uint8)
+    kn, kfvs = np.zeros(B, np.int32), []
+    for f in range(B):
+        n = int(cnt[f])
+        kd, ka, valid = make_keyframe(desc[f, :n], kps[f, :n]["angle"], 50 + f, n_extra=0 if f == 2 else 150)
+        if f == 2:
+            kd, ka, valid = kd[:40], ka[:40], valid[:40]                   # a small keyframe: most frame nodes have no partner
+        kn[f] = len(kd)
+        KD[f, :kn[f]], KA[f, :kn[f]], KV[f, :kn[f]] = kd, ka, valid
+        kfvs.append(V.transform(kd, 2)[3])
+    for nnratio, check in ((0.7, True), (0.9, False)):
+        km, fm, nm = ex.search_by_bow(kn, KD, KA, KV, kfvs, [b[3] for b in bows], nnratio, check)
+        for f in range(B):
+            n = int(cnt[f])
+            wkm, wfm, wnm = orc.search_by_bow(KD[f, :kn[f]], KA[f, :kn[f]], KV[f, :kn[f]], kfvs[f], desc[f, :n], kps[f, :n]["angle"], bows[f][3],
+                                              nnratio, check)
+            assert np.array_equal(km[f, :kn[f]], wkm) and (km[f, kn[f]:] == -1).all(), f
+            assert np.array_equal(fm[f, :n], wfm) and (fm[f, n:] == -1).all(), f
+            assert nm[f] == wnm, f
+        assert nm[0] > 200
+    G.close()
