@@ -1908,7 +1908,8 @@ int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, 
   ChunkPipe& pp = h->pipe;
   cudaStream_t st = h->stream;
   const size_t N = (size_t)W * H, esz = depth_is_u16 ? sizeof(uint16_t) : sizeof(float);
-  const int chunk = ChunkPipe::chunk_size(nframes, chunk_frames);
+  int cstart[ChunkPipe::kMaxChunks + 1];
+  const int nchunks = ChunkPipe::schedule(nframes, chunk_frames, cstart);
   if (depth_is_u16) { h->hd.depth16 = reinterpret_cast<const uint16_t*>(h->d_depth); h->hd.depth = nullptr; h->hd.depth_factor = depth_factor; }
   else { h->hd.depth = h->d_depth; h->hd.depth16 = nullptr; }
   h->hd.depth_rs = W; h->hd.depth_fs = (long long)N;
@@ -1920,8 +1921,8 @@ int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, 
   const bool dense = row_stride == (size_t)W && frame_stride == N;
   uint8_t* stage = reinterpret_cast<uint8_t*>(h->d_depth);
   const uint8_t* src = reinterpret_cast<const uint8_t*>(depth);
-  for (int f0 = 0, k = 0; f0 < nframes; f0 += chunk, ++k) {
-    const int n = std::min(chunk, nframes - f0);
+  for (int k = 0; k < nchunks; ++k) {
+    const int f0 = cstart[k], n = cstart[k + 1] - f0;
     if (dense)
       DRFE_CUDA(cudaMemcpyAsync(stage + f0 * N * esz, src + (size_t)f0 * frame_stride * esz, (size_t)n * N * esz, cudaMemcpyHostToDevice, pp.h2d));
     else

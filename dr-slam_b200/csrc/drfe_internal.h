@@ -142,12 +142,26 @@ struct ChunkPipe {
     cudaFreeHost(h_status);
     created = false;
   }
-  // frames per chunk: the caller's wish (<= 0: 32), never more than kMaxChunks chunks
-  static int chunk_size(int nframes, int wish) {
-    int c = wish > 0 ? wish : 32;
-    if (c > nframes) c = nframes;
-    while ((nframes + c - 1) / c > kMaxChunks) ++c;
-    return c;
+  // chunk boundaries start[0 .. n]: the caller's wish (> 0: uniform chunks of that many frames, never more than kMaxChunks), or
+  // (<= 0) 32-frame chunks with a ramp at both ends (8, 16, 32 ... 32, 16, 8) when the batch is long enough: the first kernels
+  // start after a quarter of a chunk's H2D copy and the last chunk's kernels + D2H copy (the part nothing overlaps) are short
+  static int schedule(int nframes, int wish, int* start) {
+    int n = 0, f = 0;
+    if (wish <= 0 && nframes >= 128) {
+      const int head[2] = {8, 16};
+      for (int i = 0; i < 2; ++i) { start[n++] = f; f += head[i]; }
+      const int mid_end = nframes - 24;
+      while (f < mid_end) { start[n++] = f; f += (mid_end - f < 32) ? mid_end - f : 32; }
+      start[n++] = f; f += 16;
+      start[n++] = f; f += 8;
+    } else {
+      int c = wish > 0 ? wish : 32;
+      if (c > nframes) c = nframes;
+      while ((nframes + c - 1) / c > kMaxChunks) ++c;
+      for (; f < nframes; f += c) start[n++] = f;
+    }
+    start[n] = nframes;
+    return n;
   }
 };
 

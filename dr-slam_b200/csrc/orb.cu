@@ -2025,14 +2025,15 @@ int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t
   cudaStream_t st = h->stream;
   const int W = h->width, H = h->height, cap = h->hd.kp_cap;
   const size_t fbytes = (size_t)W * H;
-  const int chunk = ChunkPipe::chunk_size(nframes, chunk_frames);
+  int cstart[ChunkPipe::kMaxChunks + 1];
+  const int nchunks = ChunkPipe::schedule(nframes, chunk_frames, cstart);
   // the copy streams start after whatever the handle's stream was doing with the staging / result buffers
   DRFE_CUDA(cudaEventRecord(pp.ev_start, st));
   DRFE_CUDA(cudaStreamWaitEvent(pp.h2d, pp.ev_start, 0));
   DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_start, 0));
   const bool dense = row_stride == (size_t)W && frame_stride == fbytes;
-  for (int f0 = 0, k = 0; f0 < nframes; f0 += chunk, ++k) {
-    const int n = std::min(chunk, nframes - f0);
+  for (int k = 0; k < nchunks; ++k) {
+    const int f0 = cstart[k], n = cstart[k + 1] - f0;
     if (dense || n == 1)
       DRFE_CUDA(cudaMemcpy2DAsync(h->d_gray + f0 * fbytes, W, gray + (size_t)f0 * frame_stride, row_stride, W, (size_t)H * (dense ? n : 1),
                                   cudaMemcpyHostToDevice, pp.h2d));
