@@ -94,6 +94,10 @@ class ORBextractor {
   std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
   bool keep_pyramid = false;
+  // the device handle (keypoints, descriptors and pyramid of the last call stay on the device): what ORBVocabulary.h and
+  // ORBmatcher.h run on
+  drfe_orb* handle() const { return h_; }
+  int max_keypoints() const { return cap_; }
 
  protected:
   void run(const uint8_t* data, int w, int h, size_t step, int& n) {

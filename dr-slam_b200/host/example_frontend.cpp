@@ -1,7 +1,9 @@
 // Host-side usage of the adapters, written the way Frame::Frame drives the extractors
 // (reference src/Frame.cc:124-134: one std::thread per extractor, then join): ORB and the CAPE
 // plane detection run concurrently on one synthetic RGB-D frame; prints a digest that
-// tests/test_gpu_adapters.py compares with the CPU oracle.
+// tests/test_gpu_adapters.py compares with the CPU oracle.  With a vocabulary file (argv[3], ORBvoc.txt format) it goes on
+// like Tracking does: the per-frame steps on the keypoints, Frame::ComputeBoW, and the two whole-function matchers with
+// the frame matched against itself (identity pose / itself as the keyframe).
 //   build:  g++ -std=c++17 -O2 example_frontend.cpp -o example_frontend -L.. -ldrfe -Wl,-rpath,'$ORIGIN/..' -lpthread
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +11,7 @@
 
 #include "CAPE.h"
 #include "ORBextractor.h"
+#include "ORBmatcher.h"
 
 static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
   const uint8_t* b = (const uint8_t*)p;
@@ -52,6 +55,41 @@ int main(int argc, char** argv) {
     for (int i = 0; i < planes.nr_planes; ++i)
       printf("plane %d n %.9f %.9f %.9f d %.9f\n", i, planes.plane_params[i].normal[0], planes.plane_params[i].normal[1],
              planes.plane_params[i].normal[2], planes.plane_params[i].d);
+    if (argc > 3) {
+      drfe_frame_params fp = {fx, fy, cx, cy, {0.1f, -0.05f, 0.001f, 0.0005f, 0.f}, 40.f, 0, 0, 0, 0};
+      drfe_frame_image_bounds(&fp, W, H);                              // Frame::ComputeImageBounds, first frame only
+      std::vector<drfe_compat::KeyPoint> keysUn;
+      std::vector<float> uRight, kpDepth;
+      Planar_SLAM::FramePost(orb, fp, depth.data(), W, H, &keysUn, &uRight, &kpDepth);
+      Planar_SLAM::ORBVocabulary voc;
+      if (!voc.loadFromTextFile(argv[3])) { fprintf(stderr, "cannot load %s\n", argv[3]); return 3; }
+      DBoW2::BowVector bow;
+      DBoW2::FeatureVector fv;
+      voc.transform(orb, bow, fv, 4);                                  // Frame::ComputeBoW (Frame.cc:828-833)
+      uint64_t hb = 1469598103934665603ull, hf = hb;
+      for (auto& kv : bow) { hb = fnv1a(&kv.first, 4, hb); hb = fnv1a(&kv.second, 8, hb); }
+      for (auto& kv : fv) { hf = fnv1a(&kv.first, 4, hf); hf = fnv1a(kv.second.data(), kv.second.size() * 4, hf); }
+      // TrackWithMotionModel against itself: every keypoint with depth is a last-frame point at its own back-projection
+      const int n = (int)keys.size();
+      std::vector<drfe_last_point> last(n);
+      std::vector<uint8_t> lastDesc(desc.data, desc.data + (size_t)n * 32), good(n, 1);
+      std::vector<float> ang(n);
+      for (int i = 0; i < n; ++i) {
+        const float z = kpDepth[i] > 0 ? kpDepth[i] : 2.f;
+        last[i] = {(keysUn[i].pt.x - cx) * z / fx, (keysUn[i].pt.y - cy) * z / fy, z, keysUn[i].angle, keysUn[i].octave,
+                   DRFE_LP_VALID | DRFE_LP_OBSERVED};
+        ang[i] = keysUn[i].angle;
+      }
+      const float Tcw[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+      Planar_SLAM::ORBmatcher matcher(0.9f, true);                     // Tracking.cc: ORBmatcher matcher(0.9,true)
+      std::vector<int32_t> mp, mb;
+      const int nproj = matcher.SearchByProjection(orb, Tcw, last, lastDesc, 15.f, 0, mp);
+      Planar_SLAM::ORBmatcher matcher2(0.7f, true);                    // TrackReferenceKeyFrame: ORBmatcher matcher(0.7,true)
+      const int nbow = matcher2.SearchByBoW(lastDesc, ang, good, fv, orb, fv, mb);
+      printf("words %u bow %zu bow_hash %016llx fv %zu fv_hash %016llx proj %d proj_hash %016llx bowmatch %d bowmatch_hash %016llx\n", voc.size(),
+             bow.size(), (unsigned long long)hb, fv.size(), (unsigned long long)hf, nproj, (unsigned long long)fnv1a(mp.data(), (size_t)n * 4), nbow,
+             (unsigned long long)fnv1a(mb.data(), (size_t)n * 4));
+    }
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 1;

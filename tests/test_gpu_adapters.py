@@ -80,3 +80,51 @@ def test_handles_are_usable_from_fresh_host_threads(drfe, orc):
         kps, desc = o["orb"]
         assert all(np.array_equal(kps[n], w[0][n]) for n in kps.dtype.names) and np.array_equal(desc, w[1])
         assert o["cape"][0] == w[2] and np.array_equal(o["cape"][2], w[3])
+
+
+def write_vocabulary_file(path, voc):
+    """TemplatedVocabulary::saveToTextFile format (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1427-1452), what ORBvoc.txt is"""
+    with open(path, "w") as f:
+        f.write("%d %d  %d %d\n" % (voc["k"], voc["L"], voc["scoring"], voc["weighting"]))
+        for i in range(len(voc["parent"])):
+            f.write("%d %d %s %r\n" % (voc["parent"][i], voc["is_leaf"][i], " ".join(str(int(b)) for b in voc["descriptors"][i]), float(voc["weights"][i])))
+
+
+def test_cpp_vocabulary_and_matchers(drfe, orc, tmp_path):
+    """host/ORBVocabulary.h (loadFromTextFile + transform) and host/ORBmatcher.h (the two whole-function matchers) from C++,
+    against the oracle on the same frame"""
+    import struct
+    scene, seed = 1, 20260042
+    voc = orc.synth_vocabulary(10, 5, 61)
+    vf = str(tmp_path / "voc.txt")
+    write_vocabulary_file(vf, voc)
+    out = subprocess.run([EXE, str(scene), str(seed), vf], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("words ")][0]
+    m = re.match(r"words (\d+) bow (\d+) bow_hash (\w+) fv (\d+) fv_hash (\w+) proj (-?\d+) proj_hash (\w+) bowmatch (-?\d+) bowmatch_hash (\w+)", line)
+    assert m, line
+    gray, depth, K = drfe.synth_frame(640, 480, scene, seed)
+    keys, desc = orc.OrbOracle(1000).extract(gray)
+    n = len(keys)
+    V = orc.Vocabulary(**voc)
+    _, _, bow, fv = V.transform(desc, 4)
+    assert int(m.group(1)) == V.nwords and int(m.group(2)) == len(bow) and int(m.group(4)) == len(fv)
+    hb = b"".join(struct.pack("<Id", k, v) for k, v in bow)
+    hf = b"".join(struct.pack("<I", k) + np.array(l, np.uint32).tobytes() for k, l in fv)
+    assert int(m.group(3), 16) == fnv1a(hb) and int(m.group(5), 16) == fnv1a(hf)
+    # the two matchers: same inputs as example_frontend.cpp builds
+    p = orc.frame_params(*K, [0.1, -0.05, 0.001, 0.0005, 0.0], 40.0, 640, 480)
+    ku, ur, kd, gc, gi = orc.frame_post(p, keys, depth)
+    f32 = np.float32
+    pts = np.zeros(n, orc.LAST_POINT_DTYPE)
+    z = np.where(kd > 0, kd, f32(2.0)).astype(f32)
+    pts["X"] = (ku["x"] - f32(K[2])) * z / f32(K[0])
+    pts["Y"] = (ku["y"] - f32(K[3])) * z / f32(K[1])
+    pts["Z"], pts["angle"], pts["octave"], pts["flags"] = z, ku["angle"], ku["octave"], orc.LP_VALID | orc.LP_OBSERVED
+    sf = np.array(orc.OrbOracle(1000).scale_factors(), f32)
+    mk, md, holder, nm = orc.search_last_frame(p, sf, ku, ur, gc, gi, desc, np.eye(3, 4, dtype=f32).ravel(), 15.0, 0, 1, pts, desc)
+    assert int(m.group(6)) == nm and nm > 500
+    assert int(m.group(7), 16) == fnv1a(holder.astype(np.int32).tobytes())
+    km, fm, nb = orc.search_by_bow(desc, ku["angle"], np.ones(n, np.uint8), fv, desc, keys["angle"], fv, 0.7, True)
+    assert int(m.group(8)) == nb and nb > 300
+    assert int(m.group(9), 16) == fnv1a(fm.astype(np.int32).tobytes())
