@@ -1500,6 +1500,27 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
   if (tid == 0) { S.nmatches[f] = s_cnt[0] - s_cnt[1]; S.sweeps[f] = sweeps; }
 }
 
+// cv::cvtColor(..., CV_RGB2GRAY and friends) of Tracking::GrabImageRGBD (Tracking.cc:194-207) in cv's fixed point: a thread
+// converts 4 pixels (12 or 16 bytes in, one 32-bit word out)
+template <int CH>
+__global__ void __launch_bounds__(256) k_color_to_gray(const uint8_t* __restrict__ src, long long rs, long long fs, uint8_t* __restrict__ dst, int W, int H,
+                                                       int cr, int cg, int cb, int shift, int swap_rb) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, f = blockIdx.z;
+  if (x4 >= W) return;
+  const uint8_t* p = src + f * fs + y * rs + (long long)x4 * CH;
+  uint8_t* q = dst + ((long long)f * H + y) * W + x4;
+  const int half = 1 << (shift - 1);
+  uint32_t out = 0;
+  const int n = min(4, W - x4);
+  for (int i = 0; i < n; ++i) {
+    const int c0 = p[i * CH], c1 = p[i * CH + 1], c2 = p[i * CH + 2];
+    const int r = swap_rb ? c2 : c0, b = swap_rb ? c0 : c2;
+    out |= (uint32_t)((r * cr + c1 * cg + b * cb + half) >> shift) << (8 * i);
+  }
+  if (n == 4 && (W & 3) == 0) *reinterpret_cast<uint32_t*>(q) = out;
+  else for (int i = 0; i < n; ++i) q[i] = (uint8_t)(out >> (8 * i));
+}
+
 __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
   const OrbDev& P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1522,6 +1543,7 @@ struct drfe_orb {
   OrbDev* dd = nullptr;        // device copy
   cudaStream_t stream = nullptr;
   uint8_t* d_gray = nullptr;   // staging for host inputs [B][H][W]
+  uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
   void* d_rtab = nullptr; void* d_strips = nullptr;
   int nstrips = 0, blur_blocks = 0, max_node_cap = 0, max_lkp = 0;
   size_t fast_smem = 0, quad_smem = 0, pyr_smem = 0;
@@ -1948,6 +1970,55 @@ int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_s
   if (rc != DRFE_OK) return rc;
   h->last_frames = nframes;
   h->pending = true;
+  h->gray_valid = (mem_kind == DRFE_MEM_HOST);
+  return DRFE_OK;
+}
+
+int drfe_orb_enqueue_color(drfe_orb* h, int nframes, const uint8_t* pixels, int channels, int rgb_order, int coeffs, size_t row_stride,
+                           size_t frame_stride, int mem_kind) {
+  if (!h || !pixels) { set_error("drfe_orb_enqueue_color: null argument"); return DRFE_ERR_ARG; }
+  if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_orb_enqueue_color: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
+  if ((channels != 3 && channels != 4) || (coeffs != DRFE_GRAY_Q15 && coeffs != DRFE_GRAY_Q14)) { set_error("drfe_orb_enqueue_color: channels %d / coeffs %d", channels, coeffs); return DRFE_ERR_ARG; }
+  const int W = h->width, H = h->height;
+  if (row_stride < (size_t)W * channels || (nframes > 1 && frame_stride < row_stride * H)) { set_error("drfe_orb_enqueue_color: bad strides"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const uint8_t* src = pixels;
+  long long rs = (long long)row_stride, fs = (long long)frame_stride;
+  h->timer.begin(st);
+  if (mem_kind == DRFE_MEM_HOST) {
+    const size_t line = (size_t)W * channels;
+    if (!h->d_color || h->color_bytes < line * H * h->max_batch) {
+      if (dev_alloc(h, &h->d_color, line * H * h->max_batch)) return DRFE_ERR_CUDA;
+      h->color_bytes = line * H * h->max_batch;
+    }
+    for (int f = 0; f < nframes; ++f)
+      DRFE_CUDA(cudaMemcpy2DAsync(h->d_color + (size_t)f * line * H, line, pixels + f * frame_stride, row_stride, line, H, cudaMemcpyHostToDevice, st));
+    src = h->d_color; rs = (long long)line; fs = (long long)(line * H);
+    h->timer.mark("h2d", st);
+  } else if (mem_kind != DRFE_MEM_DEVICE) {
+    set_error("drfe_orb_enqueue_color: bad mem_kind"); return DRFE_ERR_ARG;
+  }
+  const bool q15 = coeffs == DRFE_GRAY_Q15;
+  const int cr = q15 ? 9798 : 4899, cg = q15 ? 19235 : 9617, cb = q15 ? 3735 : 1868, shift = q15 ? 15 : 14;
+  const dim3 grid(((W + 3) / 4 + 255) / 256, H, nframes);
+  if (channels == 3) DRFE_LAUNCH(k_color_to_gray<3>, grid, 256, 0, st, src, rs, fs, h->d_gray, W, H, cr, cg, cb, shift, rgb_order ? 0 : 1);
+  else DRFE_LAUNCH(k_color_to_gray<4>, grid, 256, 0, st, src, rs, fs, h->d_gray, W, H, cr, cg, cb, shift, rgb_order ? 0 : 1);
+  const int rc = orb_launch(h, 0, nframes, h->d_gray, W, (long long)W * H, true);
+  if (rc != DRFE_OK) return rc;
+  h->last_frames = nframes;
+  h->pending = true;
+  h->gray_valid = true;
+  return DRFE_OK;
+}
+
+int drfe_orb_get_gray(drfe_orb* h, int frame, uint8_t* dst) {
+  if (!h || !dst) { set_error("drfe_orb_get_gray: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || !h->gray_valid || frame < 0 || frame >= h->last_frames) { set_error("drfe_orb_get_gray: no converted frame %d", frame); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  DRFE_CUDA(cudaMemcpyAsync(dst, h->d_gray + (size_t)frame * h->width * h->height, (size_t)h->width * h->height, cudaMemcpyDeviceToHost, h->stream));
+  DRFE_CUDA(cudaStreamSynchronize(h->stream));
   return DRFE_OK;
 }
 

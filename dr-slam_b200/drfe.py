@@ -69,7 +69,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_search_by_bow",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_enqueue_color", "drfe_orb_get_gray", "drfe_orb_search_by_bow",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -124,6 +124,8 @@ def lib():
     L.drfe_vocab_words.argtypes = [vp]
     L.drfe_orb_compute_bow.argtypes = [vp, vp, C.c_int] + [vp] * 9
     L.drfe_orb_search_by_bow.argtypes = [vp, C.c_int] + [vp] * 12 + [C.c_float, C.c_int, vp, vp, vp]
+    L.drfe_orb_enqueue_color.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int]
+    L.drfe_orb_get_gray.argtypes = [vp, C.c_int, vp]
     L.drfe_orb_search_last_frame.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
@@ -416,6 +418,19 @@ class ORBextractor:
         _check(self.L.drfe_orb_search_last_frame(self.h, _ptr(tp), _ptr(npts), _ptr(points), _ptr(pdesc), _ptr(occupied), pcap,
                                                  _ptr(mk), _ptr(md), _ptr(kp), _ptr(nm), _ptr(sw)))
         return mk, md, kp, nm, sw
+
+    def enqueue_color(self, pixels, rgb_order=True, coeffs=0, mem_kind=MEM_HOST):
+        """cvtColor(..., CV_RGB2GRAY / BGR / RGBA / BGRA) of Tracking::GrabImageRGBD (Tracking.cc:194-207) + enqueue:
+        pixels (B,H,W,3|4) uint8; coeffs 0 = Q15 (OpenCV 4.x), 1 = Q14 (OpenCV <= 3.4)"""
+        assert pixels.dtype == np.uint8 and pixels.ndim == 4 and pixels.shape[3] in (3, 4) and pixels.strides[3] == 1 and pixels.strides[2] == pixels.shape[3]
+        nf = pixels.shape[0]
+        _check(self.L.drfe_orb_enqueue_color(self.h, nf, _ptr(pixels), pixels.shape[3], int(rgb_order), coeffs, pixels.strides[1], pixels.strides[0], mem_kind))
+        self._nframes = nf
+
+    def get_gray(self, frame=0):
+        g = np.empty((self.height, self.width), np.uint8)
+        _check(self.L.drfe_orb_get_gray(self.h, frame, _ptr(g)))
+        return g
 
     def compute_bow(self, vocab, levelsup=4):
         """Frame::ComputeBoW (Frame.cc:828-833) on the last batch's descriptors -> per frame (word_id, node_id,

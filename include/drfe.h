@@ -143,8 +143,23 @@ int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_pe
 int drfe_orb_sync(drfe_orb* h);
 void* drfe_orb_stream(drfe_orb* h); /* the handle's cudaStream_t */
 
+/* The colour conversion Tracking::GrabImageRGBD does before the frame is built (Tracking.cc:194-207:
+ * cvtColor(mImGray, mImGray, CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY)) fused in
+ * front of drfe_orb_enqueue: pixels = interleaved 8-bit colour frames (channels 3 or 4, rgb_order != 0: R first as in
+ * CV_RGB2GRAY, 0: B first), row_stride / frame_stride in BYTES.  coeffs selects cv::cvtColor's fixed-point arithmetic:
+ * DRFE_GRAY_Q15 = (R*9798 + G*19235 + B*3735 + 2^14) >> 15 — OpenCV 4.x and late 3.4.x; bit-identical to cv2 4.13 on
+ * all 2^24 colours (tests/test_gpu_color.py); DRFE_GRAY_Q14 = (R*4899 + G*9617 + B*1868 + 2^13) >> 14 — OpenCV 2.4 ..
+ * 3.4.x before the bit-exact rewrite (published constants R2Y / G2Y / B2Y, yuv_shift 14; no library here to pin it
+ * against).  drfe_orb_get_gray copies the converted frame (mImGray) back. */
+#define DRFE_GRAY_Q15 0
+#define DRFE_GRAY_Q14 1
+int drfe_orb_enqueue_color(drfe_orb* h, int nframes, const uint8_t* pixels, int channels, int rgb_order,
+                           int coeffs, size_t row_stride, size_t frame_stride, int mem_kind);
+int drfe_orb_get_gray(drfe_orb* h, int frame, uint8_t* dst);
+
 /* A whole batch of HOST images in, HOST results out, in one asynchronous call: the batch is cut
- * into chunks of chunk_frames frames (<= 0: 32) and chunk k's host->device copy, kernels and
+ * into chunks of chunk_frames frames (<= 0: 32-frame chunks with 8- and 16-frame chunks at both
+ * ends, so that the first kernels start early and the last copy out is short) and chunk k's host->device copy, kernels and
  * device->host copies run on three streams, so PCIe in both directions overlaps the kernels
  * (pinned host memory is needed for the overlap; pageable memory works, serialised).  The call
  * returns after queueing; the buffers must stay valid until drfe_orb_finish_batch(), which waits
