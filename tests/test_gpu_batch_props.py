@@ -131,3 +131,31 @@ def test_later_shards_of_the_sequence(drfe, orc):
         assert cnt[f] == len(rk) and kps[f, :cnt[f]].tobytes() == rk.tobytes() and np.array_equal(desc[f, :cnt[f]], rd)
         oseg, opl = oc.process(oc.depth_to_cloud(depth[f], *K))
         assert np.array_equal(seg[f], oseg) and npl[f] == len(opl)
+
+
+def test_default_chunk_schedule_on_a_long_batch(drfe):
+    """batches of 128 frames and more use the ramped chunk schedule (8, 16, 32 ... 32, 16, 8) by default: same results as
+    enqueue + download, frame by frame, for a batch whose middle part is not a multiple of 32"""
+    n = 136
+    base = [drfe.synth_frame(640, 480, i % 3, 20260950 + i, 1.0) for i in range(8)]
+    order = [(7 * i + i // 8) % 8 for i in range(n)]
+    gray = np.stack([base[j][0] for j in order])
+    depth = np.stack([base[j][1] for j in order])
+    K = base[0][2]
+    orb = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=n)
+    cape = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0, max_batch=n)
+    orb.enqueue(gray)
+    rk, rd, rc = orb.download()
+    cape.enqueue_depth(depth, *K)
+    rseg, rpl, rnp = cape.download()
+    kps, desc, cnt = orb.extract_batch(gray)
+    seg, planes, npl, _, _ = cape.process_depth_batch(depth, *K)
+    orb.finish_batch(); cape.finish_batch()
+    assert np.array_equal(cnt, rc) and np.array_equal(npl, rnp) and np.array_equal(seg, rseg)
+    for f in range(n):
+        assert kps[f, :cnt[f]].tobytes() == rk[f, :rc[f]].tobytes() and np.array_equal(desc[f, :cnt[f]], rd[f, :rc[f]])
+        assert planes[f, :npl[f]].tobytes() == rpl[f, :rnp[f]].tobytes()
+    first = {j: order.index(j) for j in range(8)}
+    for f in range(n):                                   # repeated inputs give repeated outputs wherever they sit in a chunk
+        g = first[order[f]]
+        assert cnt[f] == cnt[g] and np.array_equal(desc[f, :cnt[f]], desc[g, :cnt[g]]) and np.array_equal(seg[f], seg[g])
