@@ -154,7 +154,7 @@ def test_default_chunk_schedule_on_a_long_batch(drfe):
     assert np.array_equal(cnt, rc) and np.array_equal(npl, rnp) and np.array_equal(seg, rseg)
     for f in range(n):
         assert kps[f, :cnt[f]].tobytes() == rk[f, :rc[f]].tobytes() and np.array_equal(desc[f, :cnt[f]], rd[f, :rc[f]])
-        assert planes[f, :npl[f]].tobytes() == rpl[f, :rnp[f]].tobytes()
+        assert all(np.array_equal(planes[f, :npl[f]][nm], rpl[f, :rnp[f]][nm]) for nm in ("normal", "d", "nr_pts", "MSE"))
     first = {j: order.index(j) for j in range(8)}
     for f in range(n):                                   # repeated inputs give repeated outputs wherever they sit in a chunk
         g = first[order[f]]
