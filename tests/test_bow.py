@@ -203,3 +203,20 @@ def test_gpu_search_by_bow(drfe, orc):
             assert nm[f] == wnm, f
         assert nm[0] > 200
     G.close()
+
+
+@pytest.mark.gpu
+def test_gpu_compute_bow_2000kp(drfe, orc):
+    """1280x720 / 2000 keypoints: the per-frame sort runs on 4096 keys"""
+    gray, _, _ = drfe.synth_frame(1280, 720, 2, 20260520)
+    keys, desc = orc.OrbOracle(2000).extract(gray)
+    ex = drfe.ORBextractor(2000, 1.2, 8, 20, 7, 1280, 720, max_batch=2)
+    ex.enqueue(np.stack([gray, gray[::-1].copy()]))
+    kps, gd, cnt = ex.download()
+    assert np.array_equal(gd[0, :cnt[0]], desc) and cnt[0] >= 2000
+    voc = orc.synth_vocabulary(10, 4, 71)
+    V, G = orc.Vocabulary(**voc), drfe.Vocabulary(**voc)
+    got = ex.compute_bow(G, 2)
+    same_maps(got[0], V.transform(desc, 2))
+    same_maps(got[1], V.transform(gd[1, :cnt[1]], 2))
+    G.close()

@@ -63,11 +63,11 @@ def make_last_frame(orc, p, keys_un, kp_depth, desc, Tcw, npts, seed, cascade=Tr
     return pts, pd
 
 
-def current_frame(drfe, orc, seed, scene=1):
-    gray, depth, _ = drfe.synth_frame(640, 480, scene, seed)
-    o = orc.OrbOracle(1000)
+def current_frame(drfe, orc, seed, scene=1, size=(640, 480), nfeatures=1000):
+    gray, depth, _ = drfe.synth_frame(size[0], size[1], scene, seed)
+    o = orc.OrbOracle(nfeatures)
     keys, desc = o.extract(gray)
-    p = orc.frame_params(*K, DIST, 40.0, 640, 480)
+    p = orc.frame_params(*K, DIST, 40.0, size[0], size[1])
     ku, ur, kd, gc, gi = orc.frame_post(p, keys, depth)
     return gray, depth, p, ku, ur, kd, gc, gi, desc, np.array(o.scale_factors(), np.float32)
 
@@ -217,10 +217,10 @@ def test_parallel_sweeps_reach_the_sequential_result(drfe, orc):
         assert 3 <= sweeps < 40
 
 
-def gpu_case(drfe, orc, seeds, scenes, modes, checks, ths, npts, with_occ):
+def gpu_case(drfe, orc, seeds, scenes, modes, checks, ths, npts, with_occ, size=(640, 480), nfeatures=1000):
     B = len(seeds)
-    frames = [current_frame(drfe, orc, s, scene=sc) for s, sc in zip(seeds, scenes)]
-    ex = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=B)
+    frames = [current_frame(drfe, orc, s, scene=sc, size=size, nfeatures=nfeatures) for s, sc in zip(seeds, scenes)]
+    ex = drfe.ORBextractor(nfeatures, 1.2, 8, 20, 7, size[0], size[1], max_batch=B)
     ex.enqueue(np.stack([f[0] for f in frames]))
     kps, desc, cnt = ex.download()
     p = ex.frame_params(*K, DIST, 40.0)
@@ -267,3 +267,10 @@ def test_gpu_search_last_frame(drfe, orc):
 def test_gpu_search_last_frame_no_occupied(drfe, orc):
     """what TrackWithMotionModel does: mvpMapPoints filled with NULL before the call"""
     gpu_case(drfe, orc, [20260450, 20260455], [1, 2], [0, 0], [1, 1], [15.0, 15.0], [1000, 30], False)
+
+
+@pytest.mark.gpu
+def test_gpu_search_last_frame_1280x720_2000kp(drfe, orc):
+    """BASELINE configs[4] shape: 2000 keypoints per frame, 2400 last-frame points (capacities beyond one CTA pass)"""
+    mk, sw, nm = gpu_case(drfe, orc, [20260460, 20260461], [2, 1], [0, 2], [1, 1], [15.0, 7.0], [2400, 1500], True, size=(1280, 720), nfeatures=2000)
+    assert (mk[0] >= 0).sum() > 1000
