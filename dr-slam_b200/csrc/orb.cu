@@ -1275,17 +1275,21 @@ struct SearchDev {
 
 // exclusive prefix sum of the 3072 mGrid cell counts of one frame into s_off[0 .. 3072] (all 256 threads of the CTA)
 __device__ __forceinline__ void grid_offsets(const uint16_t* __restrict__ gc, unsigned short* s_off, int* s_part) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x;                 // the first 256 threads work, every thread of the CTA takes the barriers
   constexpr int PER = kGridCells / 256;
   int loc[PER], sum = 0;
+  if (tid < 256) {
 #pragma unroll
-  for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += gc[tid * PER + k]; }
-  s_part[tid] = sum;
+    for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += gc[tid * PER + k]; }
+    s_part[tid] = sum;
+  }
   __syncthreads();
   if (tid == 0) { int run = 0; for (int i = 0; i < 256; ++i) { const int t = s_part[i]; s_part[i] = run; run += t; } s_off[kGridCells] = (unsigned short)run; }
   __syncthreads();
+  if (tid < 256) {
 #pragma unroll
-  for (int k = 0; k < PER; ++k) s_off[tid * PER + k] = (unsigned short)(s_part[tid] + loc[k]);
+    for (int k = 0; k < PER; ++k) s_off[tid * PER + k] = (unsigned short)(s_part[tid] + loc[k]);
+  }
   __syncthreads();
 }
 
@@ -1366,11 +1370,13 @@ __global__ void __launch_bounds__(256) k_search_projection(const OrbDev* __restr
 // on entry), skipping idx when owner[idx] < i, until a sweep changes no choice.  That fixed point satisfies the
 // reference's recurrence point by point, and the recurrence has one solution (induction on i), so it is the reference's
 // result; point i is final after at most i + 1 sweeps, in practice after 2-3.  Then rotation histogram / three maxima.
+// threads per CTA (= per frame): one point per thread for up to 1024 last-frame points; 64 registers per thread
+constexpr int kTrackThreads = 1024;
 struct TrackDev {
   const drfe_track_params* tp; const drfe_last_point* pts; const uint8_t* pdesc; const uint8_t* occupied; const int* np;
   int32_t* match_key; int32_t* match_dist; int32_t* key_point; int* nmatches; int* sweeps; int pcap;
 };
-__global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restrict__ Pp, PostDev Q, TrackDev S) {
+__global__ void __launch_bounds__(kTrackThreads) k_search_last_frame(const OrbDev* __restrict__ Pp, PostDev Q, TrackDev S) {
   extern __shared__ int s_dyn[];
   __shared__ unsigned short s_off[kGridCells + 1];
   __shared__ int s_part[256];
@@ -1382,6 +1388,8 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
   int* owner = s_dyn;                 // [cap]
   int* choice = s_dyn + cap;          // [pcap] matched keypoint of point i or -1
   int* cdist = choice + S.pcap;       // [pcap] bestDist
+  int* bidx = cdist + S.pcap;         // [pcap] the keypoint that gave bestDist (also when bestDist > TH_HIGH), -1: nothing compared
+  unsigned char* skipped = reinterpret_cast<unsigned char*>(bidx + S.pcap);   // [pcap] the last search of point i skipped a taken keypoint
   grid_offsets(Q.grid_count + (long long)f * kGridCells, s_off, s_part);
   const drfe_frame_params prm = Q.prm;
   const drfe_track_params tp = S.tp[f];
@@ -1393,19 +1401,23 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
   const drfe_last_point* pts = S.pts + (long long)f * S.pcap;
   const int np = min(S.np[f], S.pcap);
   const int nkeys = P.out_cnt[f];
-  for (int i = tid; i < np; i += 256) choice[i] = -1;
+  for (int i = tid; i < np; i += kTrackThreads) choice[i] = -1;
   int sweeps = 0;
   for (;;) {
     // owner[] from the previous sweep's choices
-    for (int k = tid; k < cap; k += 256) owner[k] = (occ && k < nkeys && occ[k]) ? -1 : 0x7fffffff;
+    for (int k = tid; k < cap; k += kTrackThreads) owner[k] = (occ && k < nkeys && occ[k]) ? -1 : 0x7fffffff;
     __syncthreads();
-    for (int i = tid; i < np; i += 256)
+    for (int i = tid; i < np; i += kTrackThreads)
       if (choice[i] >= 0 && (pts[i].flags & DRFE_LP_OBSERVED)) atomicMin(&owner[choice[i]], i);
     __syncthreads();
     int changed = 0;
-    for (int i = tid; i < np; i += 256) {
+    for (int i = tid; i < np; i += kTrackThreads) {
+      // a point whose last search skipped nothing (so it saw its unconstrained first minimum) keeps that result as long as
+      // that keypoint is not taken by a lower-numbered point: hiding other candidates cannot change a first minimum
+      if (sweeps > 0 && !skipped[i] && (bidx[i] < 0 || owner[bidx[i]] >= i)) continue;
       const drfe_last_point lp = pts[i];
       int best = 256, best_idx = -1;
+      bool skip = false;
       if (lp.flags & DRFE_LP_VALID) {
         // :1426-1442  x3Dc = Rcw*x3Dw + tcw: cv::gemm's 3x3 float path (products and sums in float, left to right, then + c)
         const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp.Tcw[0], lp.X), __fmul_rn(tp.Tcw[1], lp.Y)), __fmul_rn(tp.Tcw[2], lp.Z)), tp.Tcw[3]);
@@ -1426,7 +1438,7 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
 #pragma unroll
           for (int k = 0; k < 8; ++k) d[k] = qd[k];
           features_in_area(prm, s_off, gi, ku, u, v, radius, lo, hi, [&](int idx, const drfe_keypoint&) {
-            if (owner[idx] < i) return;                                        // :1471-1473
+            if (owner[idx] < i) { skip = true; return; }                       // :1471-1473
             const float r2 = ur[idx];
             if (r2 > 0.f && fabsf(__fsub_rn(urp, r2)) > radius) return;        // :1475-1481
             const int dist = descriptor_distance(d, desc + idx * 8);
@@ -1436,7 +1448,7 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
       }
       const int c = best <= DRFE_TH_HIGH ? best_idx : -1;                      // :1494 (256 when nothing was compared)
       changed |= (c != choice[i]);
-      choice[i] = c; cdist[i] = best;
+      choice[i] = c; cdist[i] = best; bidx[i] = best_idx; skipped[i] = skip;
     }
     ++sweeps;
     if (!__syncthreads_or(changed)) break;
@@ -1444,7 +1456,7 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
   // rotation consistency (:1499-1532)
   if (tid < DRFE_HISTO_LENGTH) s_hist[tid] = 0;
   if (tid < 2) s_cnt[tid] = 0;
-  for (int k = tid; k < cap; k += 256) owner[k] = -1;                          // becomes key_point
+  for (int k = tid; k < cap; k += kTrackThreads) owner[k] = -1;                          // becomes key_point
   __syncthreads();
   const float factor = 1.0f / DRFE_HISTO_LENGTH;
   auto rot_bin = [&](int i) {
@@ -1455,7 +1467,7 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
     return bin;
   };
   int mine = 0;
-  for (int i = tid; i < np; i += 256)
+  for (int i = tid; i < np; i += kTrackThreads)
     if (choice[i] >= 0) {
       ++mine;
       if (tp.check_orientation) { const int b = rot_bin(i); if (b >= 0 && b < DRFE_HISTO_LENGTH) atomicAdd(&s_hist[b], 1); }
@@ -1479,12 +1491,12 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
   }
   __syncthreads();
   // the in-order assignment mvpMapPoints[bestIdx2] = pMP leaves the highest-numbered point that chose the keypoint
-  for (int i = tid; i < np; i += 256)
+  for (int i = tid; i < np; i += kTrackThreads)
     if (choice[i] >= 0) atomicMax(&owner[choice[i]], i);
   __syncthreads();
   if (tp.check_orientation) {
     int removed = 0;
-    for (int i = tid; i < np; i += 256)
+    for (int i = tid; i < np; i += kTrackThreads)
       if (choice[i] >= 0) {
         const int b = rot_bin(i);
         if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { owner[choice[i]] = -2; ++removed; }   // set to NULL, nmatches-- (:1527-1528)
@@ -1492,8 +1504,8 @@ __global__ void __launch_bounds__(256) k_search_last_frame(const OrbDev* __restr
     if (removed) atomicAdd(&s_cnt[1], removed);
   }
   __syncthreads();
-  if (S.key_point) for (int k = tid; k < cap; k += 256) S.key_point[(long long)f * cap + k] = owner[k];
-  for (int i = tid; i < np; i += 256) {
+  if (S.key_point) for (int k = tid; k < cap; k += kTrackThreads) S.key_point[(long long)f * cap + k] = owner[k];
+  for (int i = tid; i < np; i += kTrackThreads) {
     S.match_key[(long long)f * S.pcap + i] = choice[i];
     S.match_dist[(long long)f * S.pcap + i] = cdist[i];
   }
@@ -2267,7 +2279,7 @@ int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const i
   if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
   cudaStream_t st = h->stream;
   const int nf = h->last_frames, cap = h->hd.kp_cap, B = h->max_batch;
-  const size_t smem = ((size_t)cap + 2 * (size_t)pcap) * sizeof(int);
+  const size_t smem = ((size_t)cap + 3 * (size_t)pcap) * sizeof(int) + (size_t)pcap;
   if (smem > 160 * 1024) { set_error("drfe_orb_search_last_frame: pcap %d too large", pcap); return DRFE_ERR_CAPACITY; }
   for (int f = 0; f < nf; ++f) {
     if (npoints[f] < 0 || npoints[f] > pcap) { set_error("drfe_orb_search_last_frame: frame %d has %d points, pcap is %d", f, npoints[f], pcap); return DRFE_ERR_ARG; }
@@ -2295,7 +2307,7 @@ int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const i
   S.tp = h->d_ttp; S.pts = h->d_tpts; S.pdesc = h->d_tdesc; S.occupied = occupied ? h->d_socc : nullptr; S.np = h->d_tcnt;
   S.match_key = h->d_tout; S.match_dist = h->d_tout + (size_t)pcap * B; S.key_point = h->d_tkey; S.nmatches = h->d_tcnt + B; S.sweeps = h->d_tcnt + 2 * B;
   S.pcap = pcap;
-  DRFE_LAUNCH(k_search_last_frame, nf, 256, smem, st, h->dd, h->post, S);
+  DRFE_LAUNCH(k_search_last_frame, nf, kTrackThreads, smem, st, h->dd, h->post, S);
   if (match_key) DRFE_CUDA(cudaMemcpyAsync(match_key, S.match_key, (size_t)nf * pcap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (match_dist) DRFE_CUDA(cudaMemcpyAsync(match_dist, S.match_dist, (size_t)nf * pcap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (key_point) DRFE_CUDA(cudaMemcpyAsync(key_point, S.key_point, (size_t)nf * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -59,6 +59,16 @@ def main():
     P["octave"], P["flags"] = lv, drfe.LP_VALID | drfe.LP_OBSERVED
     ms, r = timed(lambda: orb.search_last_frame(tp, P, QD))
     print("drfe_orb_search_last_frame     %7.2f ms per %d frames x 1000 points (%.1f matches per frame, %.1f sweeps)" % (ms, B, r[3].mean(), r[4].mean()))
+    ms0, _ = timed(lambda: orb.search_last_frame(tp, P, QD, np.zeros(B, np.int32)))
+    print("   of which copies + launch     %7.2f ms (same call with 0 points per frame: same H2D / D2H volume)" % ms0)
+    uniq = np.stack([rng.permutation(1000) for _ in range(B)])          # every point aims at its own keypoint: the tracking case
+    P2, QD2 = P.copy(), np.take_along_axis(desc, uniq[:, :, None], 1)
+    z2 = np.where(np.take_along_axis(kd, uniq, 1) > 0, np.take_along_axis(kd, uniq, 1), 2.0)
+    P2["X"] = (np.take_along_axis(ku["x"], uniq, 1) - K[2]) * z2 / K[0]
+    P2["Y"] = (np.take_along_axis(ku["y"], uniq, 1) - K[3]) * z2 / K[1]
+    P2["Z"], P2["angle"], P2["octave"] = z2, np.take_along_axis(ku["angle"], uniq, 1), np.take_along_axis(ku["octave"], uniq, 1)
+    ms, r = timed(lambda: orb.search_last_frame(tp, P2, QD2))
+    print("drfe_orb_search_last_frame     %7.2f ms, points without collisions (%.1f matches per frame, %.1f sweeps)" % (ms, r[3].mean(), r[4].mean()))
     # Frame::ComputeBoW against a vocabulary of the ORB vocabulary's size (k = 10, L = 6: 1 111 110 nodes, 10^6 words)
     k, L = 10, 6
     sizes = [k ** l for l in range(1, L + 1)]
