@@ -1651,6 +1651,13 @@ static void glibc_rand_table(uint32_t seed, int n, std::vector<uint32_t>& out) {
   for (int i = 0; i < n; ++i) out[i] = r[344 + i] >> 1;
 }
 
+int drfe::cape_depth_view(drfe_cape* h, CapeDepthView* v) {
+  if (!h || !v) return DRFE_ERR_ARG;
+  v->device = h->device; v->nframes = h->last_frames; v->width = h->hd.W; v->height = h->hd.H; v->pending = h->pending; v->stream = h->stream;
+  v->depth = h->hd.depth; v->depth16 = h->hd.depth16; v->factor = h->hd.depth_factor; v->row_stride = h->hd.depth_rs; v->frame_stride = h->hd.depth_fs;
+  return DRFE_OK;
+}
+
 extern "C" {
 
 int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe_cape** out) {

@@ -176,4 +176,16 @@ struct OrbBatchView {
 };
 int orb_batch_view(drfe_orb* h, OrbBatchView* v);
 
+// the depth images a CAPE handle's last enqueue / batch call left on the device (defined in cape.cu)
+struct CapeDepthView {
+  int device, nframes, width, height;
+  bool pending;
+  cudaStream_t stream;
+  const float* depth;        // float metres, or
+  const uint16_t* depth16;   // raw sensor depth, z = (float)u16 * factor
+  float factor;
+  long long row_stride, frame_stride;   // in elements
+};
+int cape_depth_view(drfe_cape* h, CapeDepthView* v);
+
 }  // namespace drfe

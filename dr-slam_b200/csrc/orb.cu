@@ -1178,6 +1178,7 @@ static const int kGridCells = DRFE_FRAME_GRID_COLS * DRFE_FRAME_GRID_ROWS;
 struct PostDev {
   drfe_frame_params prm;
   const float* depth; long long depth_rs, depth_fs;
+  const uint16_t* depth16; float depth_factor;                 // raw sensor depth instead: (float)u16 * factor (Frame.cc:113-115)
   drfe_keypoint* keys_un; float* u_right; float* kp_depth;   // [B][kp_cap]
   uint16_t* grid_count;                                         // [B][kGridCells]
   uint16_t* grid_index;                                         // [B][kp_cap]
@@ -1221,7 +1222,8 @@ __global__ void __launch_bounds__(256) k_frame_post(const OrbDev* __restrict__ P
     drfe_keypoint ku = k;
     if (prm.dist[0] != 0.0f) undistort_point(prm, k.x, k.y, ku.x, ku.y);
     Q.keys_un[o + i] = ku;
-    const float d = depth[(long long)(int)k.y * Q.depth_rs + (int)k.x];      // imDepth.at<float>(v, u): floats truncate
+    const long long dpos = (long long)(int)k.y * Q.depth_rs + (int)k.x;      // imDepth.at<float>(v, u): floats truncate
+    const float d = Q.depth16 ? __fmul_rn((float)Q.depth16[(long long)f * Q.depth_fs + dpos], Q.depth_factor) : depth[dpos];
     Q.kp_depth[o + i] = d > 0 ? d : -1.f;
     Q.u_right[o + i] = d > 0 ? __fsub_rn(ku.x, __fdiv_rn(prm.bf, d)) : -1.f;
     const int px = (int)roundf(__fmul_rn(__fsub_rn(ku.x, prm.min_x), inv_w));   // PosInGrid (:816-825)
@@ -1555,6 +1557,7 @@ struct drfe_orb {
   OrbDev* dd = nullptr;        // device copy
   cudaStream_t stream = nullptr;
   uint8_t* d_gray = nullptr;   // staging for host inputs [B][H][W]
+  cudaEvent_t ev_shared = nullptr;   // drfe_orb_frame_post_shared_depth
   uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
   void* d_rtab = nullptr; void* d_strips = nullptr;
   int nstrips = 0, blur_blocks = 0, max_node_cap = 0, max_lkp = 0;
@@ -1879,6 +1882,7 @@ int drfe_orb_destroy(drfe_orb* h) {
   h->pipe.destroy();
   for (void* p : h->allocs) cudaFree(p);
   h->timer.destroy();
+  if (h->ev_shared) cudaEventDestroy(h->ev_shared);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DRFE_OK;
@@ -2199,34 +2203,12 @@ int drfe_frame_image_bounds(drfe_frame_params* p, int width, int height) {
   return DRFE_OK;
 }
 
-int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* depth, size_t row_stride, size_t frame_stride,
-                        int mem_kind, drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count,
-                        uint16_t* grid_index, int cap_per_frame) {
-  if (!h || !p || !depth) { set_error("drfe_orb_frame_post: null argument"); return DRFE_ERR_ARG; }
-  if (!h->pending) { set_error("drfe_orb_frame_post: nothing enqueued"); return DRFE_ERR_STATE; }
-  if (!(p->max_x > p->min_x) || !(p->max_y > p->min_y)) { set_error("drfe_orb_frame_post: image bounds not set (drfe_frame_image_bounds)"); return DRFE_ERR_ARG; }
-  if (row_stride < (size_t)h->width) { set_error("drfe_orb_frame_post: row_stride < width"); return DRFE_ERR_ARG; }
-  DeviceScope ds(h->device);
-  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+// launch k_frame_post on the depth Q names and copy the requested outputs out
+static int frame_post_run(drfe_orb* h, drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count, uint16_t* grid_index,
+                          int cap_per_frame) {
   cudaStream_t st = h->stream;
-  const int nf = h->last_frames, cap = h->hd.kp_cap, B = h->max_batch;
-  const size_t N = (size_t)h->width * h->height;
+  const int nf = h->last_frames, cap = h->hd.kp_cap;
   PostDev& Q = h->post;
-  if (!Q.keys_un) {
-    if (dev_alloc(h, &Q.keys_un, (size_t)cap * B) || dev_alloc(h, &Q.u_right, (size_t)cap * B) || dev_alloc(h, &Q.kp_depth, (size_t)cap * B) ||
-        dev_alloc(h, &Q.grid_count, (size_t)kGridCells * B) || dev_alloc(h, &Q.grid_index, (size_t)cap * B)) return DRFE_ERR_CUDA;
-    DRFE_CUDA(cudaFuncSetAttribute(k_frame_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * sizeof(unsigned short))));
-  }
-  Q.prm = *p;
-  if (mem_kind == DRFE_MEM_HOST) {
-    if (!h->d_post_depth && dev_alloc(h, &h->d_post_depth, N * B)) return DRFE_ERR_CUDA;
-    for (int f = 0; f < nf; ++f)
-      DRFE_CUDA(cudaMemcpy2DAsync(h->d_post_depth + f * N, h->width * sizeof(float), depth + f * frame_stride, row_stride * sizeof(float),
-                                  h->width * sizeof(float), h->height, cudaMemcpyHostToDevice, st));
-    Q.depth = h->d_post_depth; Q.depth_rs = h->width; Q.depth_fs = (long long)N;
-  } else if (mem_kind == DRFE_MEM_DEVICE) {
-    Q.depth = depth; Q.depth_rs = (long long)row_stride; Q.depth_fs = (long long)frame_stride;
-  } else { set_error("drfe_orb_frame_post: bad mem_kind"); return DRFE_ERR_ARG; }
   DRFE_LAUNCH(k_frame_post, nf, 256, cap * sizeof(unsigned short), st, h->dd, Q);
   const int wk = std::min(cap, cap_per_frame);
   if (keys_un)
@@ -2241,6 +2223,69 @@ int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* de
     DRFE_CUDA(cudaMemcpy2DAsync(grid_index, (size_t)cap_per_frame * 2, Q.grid_index, (size_t)cap * 2, (size_t)wk * 2, nf, cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
+}
+
+static int frame_post_buffers(drfe_orb* h, const drfe_frame_params* p) {
+  const int cap = h->hd.kp_cap, B = h->max_batch;
+  PostDev& Q = h->post;
+  if (!Q.keys_un) {
+    if (dev_alloc(h, &Q.keys_un, (size_t)cap * B) || dev_alloc(h, &Q.u_right, (size_t)cap * B) || dev_alloc(h, &Q.kp_depth, (size_t)cap * B) ||
+        dev_alloc(h, &Q.grid_count, (size_t)kGridCells * B) || dev_alloc(h, &Q.grid_index, (size_t)cap * B)) return DRFE_ERR_CUDA;
+    DRFE_CUDA(cudaFuncSetAttribute(k_frame_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * sizeof(unsigned short))));
+  }
+  Q.prm = *p;
+  Q.depth = nullptr; Q.depth16 = nullptr; Q.depth_factor = 1.f;
+  return DRFE_OK;
+}
+
+int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* depth, size_t row_stride, size_t frame_stride,
+                        int mem_kind, drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count,
+                        uint16_t* grid_index, int cap_per_frame) {
+  if (!h || !p || !depth) { set_error("drfe_orb_frame_post: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_orb_frame_post: nothing enqueued"); return DRFE_ERR_STATE; }
+  if (!(p->max_x > p->min_x) || !(p->max_y > p->min_y)) { set_error("drfe_orb_frame_post: image bounds not set (drfe_frame_image_bounds)"); return DRFE_ERR_ARG; }
+  if (row_stride < (size_t)h->width) { set_error("drfe_orb_frame_post: row_stride < width"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames, B = h->max_batch;
+  const size_t N = (size_t)h->width * h->height;
+  if (frame_post_buffers(h, p)) return DRFE_ERR_CUDA;
+  PostDev& Q = h->post;
+  if (mem_kind == DRFE_MEM_HOST) {
+    if (!h->d_post_depth && dev_alloc(h, &h->d_post_depth, N * B)) return DRFE_ERR_CUDA;
+    for (int f = 0; f < nf; ++f)
+      DRFE_CUDA(cudaMemcpy2DAsync(h->d_post_depth + f * N, h->width * sizeof(float), depth + f * frame_stride, row_stride * sizeof(float),
+                                  h->width * sizeof(float), h->height, cudaMemcpyHostToDevice, st));
+    Q.depth = h->d_post_depth; Q.depth_rs = h->width; Q.depth_fs = (long long)N;
+  } else if (mem_kind == DRFE_MEM_DEVICE) {
+    Q.depth = depth; Q.depth_rs = (long long)row_stride; Q.depth_fs = (long long)frame_stride;
+  } else { set_error("drfe_orb_frame_post: bad mem_kind"); return DRFE_ERR_ARG; }
+  return frame_post_run(h, keys_un, u_right, kp_depth, grid_count, grid_index, cap_per_frame);
+}
+
+int drfe_orb_frame_post_shared_depth(drfe_orb* h, drfe_cape* cape, const drfe_frame_params* p, drfe_keypoint* keys_un, float* u_right,
+                                     float* kp_depth, uint16_t* grid_count, uint16_t* grid_index, int cap_per_frame) {
+  CapeDepthView V;
+  if (!h || !p || cape_depth_view(cape, &V)) { set_error("drfe_orb_frame_post_shared_depth: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || !V.pending) { set_error("drfe_orb_frame_post_shared_depth: nothing enqueued"); return DRFE_ERR_STATE; }
+  if (!V.depth && !V.depth16) { set_error("drfe_orb_frame_post_shared_depth: the CAPE handle was fed a cloud, not depth images"); return DRFE_ERR_STATE; }
+  if (V.device != h->device || V.width != h->width || V.height != h->height || V.nframes < h->last_frames) {
+    set_error("drfe_orb_frame_post_shared_depth: the CAPE handle holds %d frames of %dx%d on device %d, the extractor %d of %dx%d on device %d",
+              V.nframes, V.width, V.height, V.device, h->last_frames, h->width, h->height, h->device);
+    return DRFE_ERR_ARG;
+  }
+  if (!(p->max_x > p->min_x) || !(p->max_y > p->min_y)) { set_error("drfe_orb_frame_post_shared_depth: image bounds not set (drfe_frame_image_bounds)"); return DRFE_ERR_ARG; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  if (frame_post_buffers(h, p)) return DRFE_ERR_CUDA;
+  // the depth copy was queued on the CAPE handle's stream: this handle's stream waits for it (no host synchronisation)
+  if (!h->ev_shared) DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming));
+  DRFE_CUDA(cudaEventRecord(h->ev_shared, V.stream));
+  DRFE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_shared, 0));
+  PostDev& Q = h->post;
+  Q.depth = V.depth; Q.depth16 = V.depth16; Q.depth_factor = V.factor; Q.depth_rs = V.row_stride; Q.depth_fs = V.frame_stride;
+  return frame_post_run(h, keys_un, u_right, kp_depth, grid_count, grid_index, cap_per_frame);
 }
 
 int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries, const uint8_t* qdesc,

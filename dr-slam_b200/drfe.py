@@ -69,7 +69,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_enqueue_color", "drfe_orb_get_gray", "drfe_orb_search_by_bow",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_frame_post_shared_depth", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_enqueue_color", "drfe_orb_get_gray", "drfe_orb_search_by_bow",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -117,6 +117,7 @@ def lib():
     L.drfe_orb_finish_batch.argtypes = [vp]
     L.drfe_frame_image_bounds.argtypes = [vp, C.c_int, C.c_int]
     L.drfe_orb_frame_post.argtypes = [vp, vp, vp, sz, sz, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+    L.drfe_orb_frame_post_shared_depth.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L.drfe_orb_search_by_projection.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.drfe_vocab_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.drfe_vocab_destroy.argtypes = [vp]
@@ -379,6 +380,16 @@ class ORBextractor:
         gc, gi = np.empty((nf, 64, 48), np.uint16), np.empty((nf, self.cap), np.uint16)
         _check(self.L.drfe_orb_frame_post(self.h, C.byref(p), _ptr(depth), row_stride, frame_stride, mem_kind, _ptr(ku), _ptr(ur),
                                           _ptr(kd), _ptr(gc), _ptr(gi), self.cap))
+        return ku, ur, kd, gc, gi
+
+    def frame_post_shared_depth(self, p, cape):
+        """frame_post on the depth images the CAPE handle already holds on the device (one H2D copy of imDepth serves both
+        extractors, as in Frame::Frame)"""
+        nf = self._nframes
+        ku = np.empty((nf, self.cap), KP_DTYPE)
+        ur, kd = np.empty((nf, self.cap), np.float32), np.empty((nf, self.cap), np.float32)
+        gc, gi = np.empty((nf, 64, 48), np.uint16), np.empty((nf, self.cap), np.uint16)
+        _check(self.L.drfe_orb_frame_post_shared_depth(self.h, cape.h, C.byref(p), _ptr(ku), _ptr(ur), _ptr(kd), _ptr(gc), _ptr(gi), self.cap))
         return ku, ur, kd, gc, gi
 
     def search_by_projection(self, queries, qdesc, nqueries=None, occupied=None):

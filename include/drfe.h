@@ -193,6 +193,15 @@ int drfe_orb_frame_post(drfe_orb* h, const drfe_frame_params* p, const float* de
                         size_t frame_stride, int mem_kind, drfe_keypoint* keys_un, float* u_right,
                         float* kp_depth, uint16_t* grid_count, uint16_t* grid_index, int cap_per_frame);
 
+/* The same with the depth images a CAPE handle already holds on the device (its last enqueue_depth / enqueue_depth_u16 /
+ * process_depth_batch of the same frames: float metres, or the sensor's raw 16-bit depth, converted per gathered pixel
+ * as (float)u16 * factor like imDepth.convertTo(CV_32F, mDepthMapFactor), Frame.cc:113-115): the depth crosses PCIe once
+ * for both extractors, as one imDepth serves both in Frame::Frame.  The handle's stream waits for the CAPE stream on the
+ * device.  In a batch call the CAPE handle's drfe_cape_finish_batch must have returned (its copies run on their own stream). */
+int drfe_orb_frame_post_shared_depth(drfe_orb* h, drfe_cape* cape, const drfe_frame_params* p,
+                                     drfe_keypoint* keys_un, float* u_right, float* kp_depth,
+                                     uint16_t* grid_count, uint16_t* grid_index, int cap_per_frame);
+
 /* The data-parallel core of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)
  * (ORBmatcher.cc:46-130; first step of SURVEY.md 8f next-3) on the device-resident results of the last
  * drfe_orb_frame_post: per query, the keypoints Frame::GetFeaturesInArea(x, y, r, min_level, max_level)

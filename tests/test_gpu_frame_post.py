@@ -45,3 +45,42 @@ def test_frame_post_batch_device_depth(drfe, orc):
     ku, ur, kd, gc, gi = ex.frame_post(p, d_depth.data_ptr(), mem_kind=drfe.MEM_DEVICE, row_stride=640, frame_stride=640 * 480)
     for f in range(B):
         check_frame(orc, p_o, kps[f, :cnt[f]], depth[f], ku[f], ur[f], kd[f], gc[f], gi[f])
+
+
+def test_frame_post_shares_the_depth_of_the_cape_handle(drfe, orc):
+    """Frame::Frame gives one imDepth to the plane extractor and to ComputeStereoFromRGBD: the depth a CAPE handle uploaded
+    (float metres, or raw u16 scaled on the device like convertTo, Frame.cc:113-115) serves drfe_orb_frame_post too"""
+    B = 6
+    data = [drfe.synth_frame(640, 480, i % 3, 20260720 + i) for i in range(B)]
+    gray = np.stack([d[0] for d in data]); depth = np.stack([d[1] for d in data])
+    K = data[0][2]
+    mc = float(np.float32(np.cos(np.pi / 12)))
+    ex = drfe.ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=B)
+    cp = drfe.CAPE(480, 640, 20, 20, False, mc, 50.0, max_batch=B)
+    p = ex.frame_params(*TUM1)
+    ex.enqueue(gray)
+    cp.enqueue_depth(depth, *K)                                  # no host synchronisation in between: the streams order it
+    got = ex.frame_post_shared_depth(p, cp)
+    want = ex.frame_post(p, depth)
+    for g, w in zip(got, want):
+        assert g.tobytes() == w.tobytes()
+    # raw 16-bit depth
+    q = np.rint(depth * 5000).astype(np.uint16)
+    fac = np.float32(1.0 / 5000.0)
+    assert np.array_equal(q.astype(np.float32) * fac, depth)
+    cp.enqueue_depth_u16(q, float(fac), *K)
+    got = ex.frame_post_shared_depth(p, cp)
+    for g, w in zip(got, want):
+        assert g.tobytes() == w.tobytes()
+    # after a pipelined batch call
+    seg, planes, npl, _, _ = cp.process_depth_batch(q, *K, depth_factor=float(fac))
+    cp.finish_batch()
+    got = ex.frame_post_shared_depth(p, cp)
+    for g, w in zip(got, want):
+        assert g.tobytes() == w.tobytes()
+    # a handle that was fed a cloud has no depth to share
+    cloud = orc.CapeOracle(480, 640, 20, 20, False, mc, 50.0).depth_to_cloud(depth[0], *K)
+    cp1 = drfe.CAPE(480, 640, 20, 20, False, mc, 50.0, max_batch=B)
+    cp1.enqueue_cloud(np.stack([cloud] * B))
+    with pytest.raises(drfe.DrfeError):
+        ex.frame_post_shared_depth(p, cp1)
