@@ -325,6 +325,7 @@ class ORBextractor:
         n = C.c_int32(0)
         _check(self.L.drfe_orb_extract(self.h, _ptr(image), image.shape[1], image.shape[0], image.strides[0],
                                        _ptr(kps), _ptr(desc), self.cap, C.byref(n)))
+        self._nframes = 1
         return kps[:n.value].copy(), desc[:n.value].copy()
 
     # ---- batched

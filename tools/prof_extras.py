@@ -111,6 +111,23 @@ def main():
     ms, _ = timed(lambda: orb.frame_post(p, d_depth.data_ptr(), mem_kind=drfe.MEM_DEVICE, row_stride=W, frame_stride=W * H))
     print("drfe_orb_frame_post            %7.2f ms per %d frames (depth already on the device)" % (ms, B))
 
+    ms, _ = timed(lambda: orb.frame_post_shared_depth(p, cape))
+    print("drfe_orb_frame_post_shared_depth %5.2f ms per %d frames (the depth the CAPE handle uploaded)" % (ms, B))
+    # the per-frame sequence Tracking runs after the two extractors, on one frame (latency, host in / host out)
+    orb1 = drfe.ORBextractor(1000, 1.2, 8, 20, 7, W, H)
+    cape1 = drfe.CAPE(H, W, 20, 20, False, bench.MIN_COS, 50.0)
+    voc = drfe.Vocabulary(k, L, 0, 0, parent, leaf, vd, wt)
+    tp1, P1, QD1 = tp[:1].copy(), P2[:1].copy(), QD2[:1].copy()
+
+    def one_frame():
+        orb1(gray[0], None)
+        cape1.process_depth(depth[0], *K)
+        orb1.frame_post_shared_depth(p, cape1)
+        orb1.compute_bow(voc)
+        return orb1.search_last_frame(tp1, P1, QD1)
+    ms, r = timed(one_frame, n=50)
+    print("one frame: extract + planes + frame_post + ComputeBoW + SearchByProjection(last frame)  %.3f ms (%d matches)" % (ms, r[3][0]))
+
 
 if __name__ == "__main__":
     main()
