@@ -1535,6 +1535,81 @@ __global__ void __launch_bounds__(256) k_color_to_gray(const uint8_t* __restrict
   else for (int i = 0; i < n; ++i) q[i] = (uint8_t)(out >> (8 * i));
 }
 
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:46-130) whole: k_search_projection's
+// search + ratio test + in-order assignment, the latter by parallel sweeps to the fixed point as in k_search_last_frame.
+// Here a hidden candidate can change the second best and with it the ratio test, so every sweep searches every point again.
+struct LocalDev {
+  const drfe_proj_query* q; const uint8_t* qdesc; const uint8_t* qflags; const uint8_t* occupied; const int* nq;
+  drfe_proj_match* out; int32_t* assigned; int32_t* key_point; int* nmatches; int qcap; float nnratio;
+};
+__global__ void __launch_bounds__(kTrackThreads) k_search_local_points(const OrbDev* __restrict__ Pp, PostDev Q, LocalDev S) {
+  extern __shared__ int s_dyn[];
+  __shared__ unsigned short s_off[kGridCells + 1];
+  __shared__ int s_part[256];
+  __shared__ int s_cnt;
+  const OrbDev& P = *Pp;
+  const int f = blockIdx.x, tid = threadIdx.x, cap = P.kp_cap;
+  int* owner = s_dyn;            // [cap]
+  int* choice = s_dyn + cap;     // [qcap]
+  grid_offsets(Q.grid_count + (long long)f * kGridCells, s_off, s_part);
+  const drfe_frame_params prm = Q.prm;
+  const drfe_keypoint* ku = Q.keys_un + (long long)f * cap;
+  const float* ur = Q.u_right + (long long)f * cap;
+  const uint16_t* gi = Q.grid_index + (long long)f * cap;
+  const uint32_t* desc = reinterpret_cast<const uint32_t*>(P.out_desc + (long long)f * cap * 32);
+  const uint8_t* occ = S.occupied ? S.occupied + (long long)f * cap : nullptr;
+  const uint8_t* qfl = S.qflags + (long long)f * S.qcap;
+  const int nq = min(S.nq[f], S.qcap), nkeys = P.out_cnt[f];
+  for (int i = tid; i < nq; i += kTrackThreads) choice[i] = -1;
+  if (tid == 0) s_cnt = 0;
+  for (;;) {
+    for (int k = tid; k < cap; k += kTrackThreads) owner[k] = (occ && k < nkeys && occ[k]) ? -1 : 0x7fffffff;
+    __syncthreads();
+    for (int i = tid; i < nq; i += kTrackThreads)
+      if (choice[i] >= 0 && (qfl[i] & DRFE_LP_OBSERVED)) atomicMin(&owner[choice[i]], i);
+    __syncthreads();
+    int changed = 0;
+    for (int i = tid; i < nq; i += kTrackThreads) {
+      drfe_proj_match m;
+      m.best_dist = 256; m.best_idx = -1; m.best_level = -1; m.best_dist2 = 256; m.best_level2 = -1;
+      int c = -1;
+      if (qfl[i] & DRFE_LP_VALID) {
+        const drfe_proj_query q = S.q[(long long)f * S.qcap + i];
+        const uint32_t* qd = reinterpret_cast<const uint32_t*>(S.qdesc + ((long long)f * S.qcap + i) * 32);
+        uint32_t d[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = qd[k];
+        features_in_area(prm, s_off, gi, ku, q.x, q.y, q.r, q.min_level, q.max_level, [&](int idx, const drfe_keypoint& kp) {
+          if (owner[idx] < i) return;                                                          // :88-90
+          const float u = ur[idx];
+          if (u > 0.f && fabsf(__fsub_rn(q.xr, u)) > q.r) return;                              // :92-97
+          const int dist = descriptor_distance(d, desc + idx * 8);
+          if (dist < m.best_dist) { m.best_dist2 = m.best_dist; m.best_dist = dist; m.best_level2 = m.best_level; m.best_level = kp.octave; m.best_idx = idx; }
+          else if (dist < m.best_dist2) { m.best_level2 = kp.octave; m.best_dist2 = dist; }
+        });
+        if (m.best_dist <= DRFE_TH_HIGH &&                                                     // :117-126
+            !(m.best_level == m.best_level2 && (float)m.best_dist > __fmul_rn(S.nnratio, (float)m.best_dist2)))
+          c = m.best_idx;
+      }
+      changed |= (c != choice[i]);
+      choice[i] = c;
+      S.out[(long long)f * S.qcap + i] = m;
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  for (int k = tid; k < cap; k += kTrackThreads) owner[k] = -1;
+  __syncthreads();
+  int mine = 0;
+  for (int i = tid; i < nq; i += kTrackThreads) {
+    S.assigned[(long long)f * S.qcap + i] = choice[i];
+    if (choice[i] >= 0) { ++mine; atomicMax(&owner[choice[i]], i); }     // the last writer of F.mvpMapPoints[bestIdx] stays
+  }
+  if (mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  for (int k = tid; k < cap; k += kTrackThreads) S.key_point[(long long)f * cap + k] = owner[k];
+  if (tid == 0) S.nmatches[f] = s_cnt;
+}
+
 __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
   const OrbDev& P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2312,6 +2387,50 @@ int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_p
   DRFE_LAUNCH(k_search_projection, nf, 256, 0, st, h->dd, h->post, S);
   DRFE_CUDA(cudaMemcpyAsync(out, h->d_sout, (size_t)nf * qcap * sizeof(drfe_proj_match), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+int drfe_orb_search_local_points(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries, const uint8_t* qdesc, const uint8_t* qflags,
+                                 const uint8_t* occupied, int qcap, float nnratio, drfe_proj_match* out, int32_t* assigned, int32_t* key_point,
+                                 int* nmatches) {
+  if (!h || !nqueries || !queries || !qdesc || !qflags || qcap < 1) { set_error("drfe_orb_search_local_points: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || !h->post.keys_un) { set_error("drfe_orb_search_local_points: run drfe_orb_frame_post first"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames, cap = h->hd.kp_cap;
+  const size_t smem = ((size_t)cap + qcap) * sizeof(int);
+  if (smem > 160 * 1024) { set_error("drfe_orb_search_local_points: qcap %d too large", qcap); return DRFE_ERR_CAPACITY; }
+  for (int f = 0; f < nf; ++f)
+    if (nqueries[f] < 0 || nqueries[f] > qcap) { set_error("drfe_orb_search_local_points: frame %d has %d queries, qcap is %d", f, nqueries[f], qcap); return DRFE_ERR_ARG; }
+  // one stream-ordered scratch block per call
+  const size_t nq = (size_t)nf * qcap, nc = (size_t)nf * cap;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_q = take(nq * sizeof(drfe_proj_query)), o_d = take(nq * 32), o_fl = take(nq), o_occ = take(nc), o_n = take((size_t)nf * 4),
+               o_out = take(nq * sizeof(drfe_proj_match)), o_as = take(nq * 4), o_kp = take(nc * 4), o_nm = take((size_t)nf * 4);
+  char* d = nullptr;
+  DRFE_CUDA(cudaMallocAsync((void**)&d, off, st));
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  auto up = [&](size_t o, const void* src, size_t bytes) { acc(cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, st)); };
+  up(o_q, queries, nq * sizeof(drfe_proj_query)); up(o_d, qdesc, nq * 32); up(o_fl, qflags, nq); up(o_n, nqueries, (size_t)nf * 4);
+  if (occupied) up(o_occ, occupied, nc);
+  LocalDev S;
+  S.q = (const drfe_proj_query*)(d + o_q); S.qdesc = (const uint8_t*)(d + o_d); S.qflags = (const uint8_t*)(d + o_fl);
+  S.occupied = occupied ? (const uint8_t*)(d + o_occ) : nullptr; S.nq = (const int*)(d + o_n); S.out = (drfe_proj_match*)(d + o_out);
+  S.assigned = (int32_t*)(d + o_as); S.key_point = (int32_t*)(d + o_kp); S.nmatches = (int*)(d + o_nm); S.qcap = qcap; S.nnratio = nnratio;
+  acc(cudaFuncSetAttribute(k_search_local_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (e == cudaSuccess) {
+    k_search_local_points<<<nf, kTrackThreads, smem, st>>>(h->dd, h->post, S);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    acc(cudaGetLastError());
+  }
+  auto down = [&](void* dst, size_t o, size_t bytes) { if (dst) acc(cudaMemcpyAsync(dst, d + o, bytes, cudaMemcpyDeviceToHost, st)); };
+  down(out, o_out, nq * sizeof(drfe_proj_match)); down(assigned, o_as, nq * 4); down(key_point, o_kp, nc * 4); down(nmatches, o_nm, (size_t)nf * 4);
+  cudaFreeAsync(d, st);
+  acc(cudaStreamSynchronize(st));
+  if (e != cudaSuccess) { set_error("drfe_orb_search_local_points: %s", cudaGetErrorString(e)); return DRFE_ERR_CUDA; }
   return DRFE_OK;
 }
 

@@ -69,7 +69,7 @@ SYMBOLS = [
     "drfe_orb_create", "drfe_orb_destroy", "drfe_orb_get_levels", "drfe_orb_get_scale_factor",
     "drfe_orb_get_scale_factors", "drfe_orb_features_per_level", "drfe_orb_max_keypoints",
     "drfe_orb_extract", "drfe_orb_enqueue", "drfe_orb_download", "drfe_orb_sync", "drfe_orb_stream",
-    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_frame_post_shared_depth", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_enqueue_color", "drfe_orb_get_gray", "drfe_orb_search_by_bow",
+    "drfe_orb_extract_batch", "drfe_orb_finish_batch", "drfe_frame_image_bounds", "drfe_orb_frame_post", "drfe_orb_frame_post_shared_depth", "drfe_orb_search_by_projection", "drfe_orb_search_last_frame", "drfe_orb_search_local_points", "drfe_vocab_create", "drfe_vocab_destroy", "drfe_vocab_words", "drfe_orb_compute_bow", "drfe_orb_enqueue_color", "drfe_orb_get_gray", "drfe_orb_search_by_bow",
     "drfe_orb_level_size", "drfe_orb_get_pyramid", "drfe_orb_get_blurred", "drfe_orb_get_candidates",
     "drfe_orb_get_level_keypoints", "drfe_orb_set_profiling", "drfe_orb_stage_times",
     "drfe_cape_create", "drfe_cape_destroy", "drfe_cape_enqueue_cloud", "drfe_cape_enqueue_depth",
@@ -127,6 +127,7 @@ def lib():
     L.drfe_orb_search_by_bow.argtypes = [vp, C.c_int] + [vp] * 12 + [C.c_float, C.c_int, vp, vp, vp]
     L.drfe_orb_enqueue_color.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, sz, sz, C.c_int]
     L.drfe_orb_get_gray.argtypes = [vp, C.c_int, vp]
+    L.drfe_orb_search_local_points.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp, vp, vp]
     L.drfe_orb_search_last_frame.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.drfe_orb_stream.argtypes = [vp]
     L.drfe_orb_stream.restype = vp
@@ -409,6 +410,25 @@ class ORBextractor:
         out = np.zeros((nf, qcap), MATCH_DTYPE)
         _check(self.L.drfe_orb_search_by_projection(self.h, _ptr(nq), _ptr(queries), _ptr(qdesc), _ptr(occupied), qcap, _ptr(out)))
         return out
+
+    def search_local_points(self, queries, qdesc, qflags, nnratio=0.8, nqueries=None, occupied=None):
+        """ORBmatcher::SearchByProjection(F, vpMapPoints, th) whole (ORBmatcher.cc:46-130): -> (match records (nf, qcap),
+        assigned (nf, qcap), key_point (nf, cap), nmatches (nf,))"""
+        nf = self._nframes
+        queries = np.ascontiguousarray(queries, QUERY_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        qflags = np.ascontiguousarray(qflags, np.uint8)
+        assert queries.shape[0] == nf and qdesc.shape == queries.shape + (32,) and qflags.shape == queries.shape
+        qcap = queries.shape[1]
+        nq = np.full(nf, qcap, np.int32) if nqueries is None else np.ascontiguousarray(nqueries, np.int32)
+        if occupied is not None:
+            occupied = np.ascontiguousarray(occupied, np.uint8)
+            assert occupied.shape == (nf, self.cap)
+        out, asg = np.zeros((nf, qcap), MATCH_DTYPE), np.zeros((nf, qcap), np.int32)
+        kp, nm = np.zeros((nf, self.cap), np.int32), np.zeros(nf, np.int32)
+        _check(self.L.drfe_orb_search_local_points(self.h, _ptr(nq), _ptr(queries), _ptr(qdesc), _ptr(qflags), _ptr(occupied), qcap, nnratio,
+                                                   _ptr(out), _ptr(asg), _ptr(kp), _ptr(nm)))
+        return out, asg, kp, nm
 
     def search_last_frame(self, tp, points, pdesc, npoints=None, occupied=None):
         """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1396-1535) with the frames of

@@ -223,6 +223,20 @@ int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_p
                                   const uint8_t* qdesc, const uint8_t* occupied, int qcap,
                                   drfe_proj_match* out);
 
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (ORBmatcher.cc:46-130) WHOLE, the matcher
+ * of Tracking::SearchLocalPoints / TrackLocalMap: the loops of drfe_orb_search_by_projection plus what that call leaves to
+ * the caller — the ratio test (:119-122) and the in-order assignment F.mvpMapPoints[bestIdx] = pMP (:124), whose effect on
+ * later map points (:88-90) the device reproduces with the parallel sweeps of drfe_orb_search_last_frame.
+ * qflags[f*qcap + i]: DRFE_LP_VALID = pMP->mbTrackInView && !pMP->isBad() (:55-59), DRFE_LP_OBSERVED = pMP->Observations() > 0;
+ * occupied as in drfe_orb_search_by_projection (F.mvpMapPoints[idx] holds an observed point on entry: the matches of the
+ * previous tracking stage).  Outputs (host, any may be NULL): out[f*qcap + i] = best / second best as the reference's loop
+ * leaves them; assigned[f*qcap + i] = bestIdx if map point i was assigned, else -1; key_point[f*max_keypoints + idx] = the
+ * map point index F.mvpMapPoints[idx] holds on return or -1 (untouched); nmatches[f] = the return value. */
+int drfe_orb_search_local_points(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries,
+                                 const uint8_t* qdesc, const uint8_t* qflags, const uint8_t* occupied, int qcap,
+                                 float nnratio, drfe_proj_match* out, int32_t* assigned, int32_t* key_point,
+                                 int* nmatches);
+
 /* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1396-1535),
  * the matcher TrackWithMotionModel runs on every frame — whole function, on the device-resident results of the last
  * drfe_orb_frame_post (the current frames) — SURVEY.md 8f next-3.  Per last-frame point i with a map point that is not

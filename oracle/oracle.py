@@ -290,6 +290,54 @@ def search_by_projection(p, keys_un, u_right, grid_count, grid_index, desc, quer
     return out
 
 
+def search_local_points(p, keys_un, u_right, grid_count, grid_index, desc, queries, qdesc, qflags, nnratio, occupied=None):
+    """ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (reference src/ORBmatcher.cc:46-130)
+    whole, restated literally: the sequential loop over the map points with the skips of :55-59 (qflags & LP_VALID), the
+    window search, best / second best, the ratio test (:119-122) and the in-order assignment F.mvpMapPoints[bestIdx] = pMP
+    (:124), which later map points see through Observations() > 0 (:88-90).  queries as in search_by_projection (r already
+    multiplied by th and the scale factor).  Returns (match records, assigned, holder, nmatches)."""
+    f32 = np.float32
+    gc = np.asarray(grid_count).reshape(64, 48)
+    off = np.concatenate([[0], np.cumsum(gc.ravel())]).astype(np.int64)
+    d32 = np.ascontiguousarray(desc).view(np.uint32).reshape(len(desc), 8)
+    n = len(keys_un)
+    out = np.zeros(len(queries), [("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "<i4"), ("best_dist2", "<i4"), ("best_level2", "<i4")])
+    out["best_dist"], out["best_idx"], out["best_level"], out["best_dist2"], out["best_level2"] = 256, -1, -1, 256, -1
+    assigned = np.full(len(queries), -1, np.int32)
+    holder = np.full(n, -1, np.int32)
+    held_observed = (np.zeros(n, bool) if occupied is None else (np.asarray(occupied[:n]) != 0)).copy()
+    ko = keys_un["octave"]
+    nmatches = 0
+    for i, q in enumerate(queries):
+        if not (qflags[i] & LP_VALID):
+            continue
+        r, xr = f32(q["r"]), f32(q["xr"])
+        vind = features_in_area(p, keys_un, off, grid_index, q["x"], q["y"], r, int(q["min_level"]), int(q["max_level"]))
+        if not vind:
+            continue
+        qd = np.ascontiguousarray(qdesc[i]).view(np.uint32)
+        best, best_idx, best_lvl, best2, best_lvl2 = 256, -1, -1, 256, -1
+        for idx in vind:
+            if held_observed[idx]:
+                continue
+            if u_right[idx] > 0 and abs(f32(xr - u_right[idx])) > r:
+                continue
+            dist = descriptor_distance(qd, d32[idx])
+            if dist < best:
+                best2, best, best_lvl2, best_lvl, best_idx = best, dist, best_lvl, int(ko[idx]), idx
+            elif dist < best2:
+                best_lvl2, best2 = int(ko[idx]), dist
+        out[i] = (best, best_idx, best_lvl, best2, best_lvl2)
+        if best <= TH_HIGH:
+            if best_lvl == best_lvl2 and f32(best) > f32(f32(nnratio) * f32(best2)):
+                continue
+            holder[best_idx] = i
+            held_observed[best_idx] = bool(qflags[i] & LP_OBSERVED)
+            assigned[i] = best_idx
+            nmatches += 1
+    return out, assigned, holder, nmatches
+
+
 def features_in_area(p, keys_un, off, grid_index, x, y, r, lo=-1, hi=-1):
     """Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (reference src/Frame.cc:730-779), float32 step by step;
     off = exclusive prefix sum of the [64][48] cell counts."""
