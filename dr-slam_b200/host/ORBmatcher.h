@@ -1,6 +1,6 @@
-// The two matchers of Planar_SLAM::ORBmatcher (reference include/ORBmatcher.h, src/ORBmatcher.cc) that run whole on the
-// device, on the drfe C ABI: SearchByProjection(CurrentFrame, LastFrame, th, bMono) (:1396-1535) and SearchByBoW(pKF, F,
-// vpMapPointMatches) (:160-292).  The current frame is the extractor's last call (keypoints, descriptors, grid on the
+// The three per-frame matchers of Planar_SLAM::ORBmatcher (reference include/ORBmatcher.h, src/ORBmatcher.cc) that run whole
+// on the device, on the drfe C ABI: SearchByProjection(F, vpMapPoints, th) (:46-130), SearchByProjection(CurrentFrame,
+// LastFrame, th, bMono) (:1396-1535) and SearchByBoW(pKF, F, vpMapPointMatches) (:160-292).  The current frame is the extractor's last call (keypoints, descriptors, grid on the
 // device after FramePost); map points are referred to by their index in the other frame, the caller maps indices back to
 // MapPoint* (INTEGRATION.md).
 #pragma once
@@ -43,6 +43,23 @@ class ORBmatcher {
     if (n == 0) return 0;
     if (drfe_orb_search_last_frame(cur.handle(), &tp, &n, last.data(), lastDesc.data(), nullptr, n, nullptr, nullptr, mvpMapPoints.data(), &nmatches,
                                    nullptr) != DRFE_OK)
+      throw std::runtime_error(std::string("ORBmatcher::SearchByProjection: ") + drfe_last_error());
+    return nmatches;
+  }
+
+  // SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (:46-130), the matcher of SearchLocalPoints:
+  // queries[i] = {mTrackProjX, mTrackProjY, r * F.mvScaleFactors[level] (r = RadiusByViewingCos(mTrackViewCos) [* th]),
+  // mTrackProjXR, level - 1, level}, flags[i] = DRFE_LP_VALID (mbTrackInView && !isBad()) | DRFE_LP_OBSERVED, descs = the map
+  // points' descriptors, occupied[idx] != 0 where F.mvpMapPoints[idx] already holds an observed point.  On return
+  // mvpMapPoints[idx] = index of the map point assigned to keypoint idx, or -1 (untouched).
+  int SearchByProjection(ORBextractor& F, const std::vector<drfe_proj_query>& queries, const std::vector<uint8_t>& descs,
+                         const std::vector<uint8_t>& flags, const std::vector<uint8_t>& occupied, std::vector<int32_t>& mvpMapPoints) {
+    const int n = (int)queries.size();
+    mvpMapPoints.assign(F.max_keypoints(), -1);
+    int nmatches = 0;
+    if (n == 0) return 0;
+    if (drfe_orb_search_local_points(F.handle(), &n, queries.data(), descs.data(), flags.data(), occupied.empty() ? nullptr : occupied.data(), n,
+                                     mfNNratio, nullptr, nullptr, mvpMapPoints.data(), &nmatches) != DRFE_OK)
       throw std::runtime_error(std::string("ORBmatcher::SearchByProjection: ") + drfe_last_error());
     return nmatches;
   }
