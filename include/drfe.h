@@ -288,7 +288,8 @@ typedef struct drfe_vocab drfe_vocab;
 /* k, L, scoring, weighting: the header line of the vocabulary file (m_k, m_L, ScoringType, WeightingType; the ORB
  * vocabulary of ORB-SLAM2 is 10 6 0 0 = L1_NORM, TF_IDF).  Rows i < nnodes: parent[i] (node id of the parent; 0 = root),
  * is_leaf[i], descriptors[32*i ..], weights[i].  Word ids are assigned to the leaves in file order (:1408-1415).
- * Scorings whose mustNormalize() is true (L1_NORM, L2_NORM, the ones ORB-SLAM uses) are supported. */
+ * All six scorings are handled as ScoringObject.h:73-89 defines them (L1 / L2 normalisation, none for DOT_PRODUCT) and the
+ * four weightings as transform does (TF_IDF / TF: addWeight, IDF / BINARY: addIfNotExist). */
 int drfe_vocab_create(int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
                       const uint8_t* is_leaf, const uint8_t* descriptors, const double* weights, int device,
                       drfe_vocab** out);
