@@ -222,6 +222,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 from C (NCCL prints its version
+    # there under NCCL_DEBUG=VERSION) go to stderr for the rest of the run, the JSON line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args, rank)
         return
