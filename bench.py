@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the pipelined e2e batch calls (0 = library default)")
+    ap.add_argument("--e2e-threads", type=int, default=1, help="host threads issuing the two e2e batch calls (2: one per extractor; measured slower)")
     ap.add_argument("--workload", default="c640", choices=["c640", "c720"],
                     help="c640: the headline 640x480 / 1000 kp batch (default); c720: 1280x720 / 2000 kp / cylinders on")
     args = ap.parse_args()
@@ -314,9 +315,20 @@ def main():
     h_npl = torch.empty(BATCH, dtype=torch.int32).pin_memory().numpy()
 
     # the chunk-pipelined batch calls: per 32-frame chunk H2D | kernels | D2H on three streams per handle
+    # One host thread issues both calls back to back.  Issuing them from two threads (one per extractor, --e2e-threads 2)
+    # was measured slower on the B200 box (47 k -> 35 k frames/s): the two handles' H2D copies then interleave on the copy
+    # engine and the longer ORB chain gets its first chunks later.
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=1) if args.e2e_threads > 1 else None
+
     def step_e2e(dep, fac):
-        orb.extract_batch(h_gray, h_kps, h_desc, h_cnt, chunk_frames=args.chunk)
-        cape.process_depth_batch(dep, *K, depth_factor=fac, seg=h_seg, planes=h_planes, nplanes=h_npl, chunk_frames=args.chunk)
+        if pool is not None:
+            fut = pool.submit(orb.extract_batch, h_gray, h_kps, h_desc, h_cnt, args.chunk)
+            cape.process_depth_batch(dep, *K, depth_factor=fac, seg=h_seg, planes=h_planes, nplanes=h_npl, chunk_frames=args.chunk)
+            fut.result()
+        else:
+            orb.extract_batch(h_gray, h_kps, h_desc, h_cnt, chunk_frames=args.chunk)
+            cape.process_depth_batch(dep, *K, depth_factor=fac, seg=h_seg, planes=h_planes, nplanes=h_npl, chunk_frames=args.chunk)
         orb.finish_batch()
         cape.finish_batch()
 
@@ -439,7 +451,8 @@ def main():
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "drfe_orb_extract_batch + drfe_cape_process_depth_batch (gray u8 + raw u16 depth as Frame::Frame gets "
                        "them, depth scaled on the device as Frame.cc:113-115 does; pinned host buffers, 32-frame chunks "
-                       "pipelined H2D | kernels | D2H)",
+                       "(8/16-frame chunks at both ends) pipelined H2D | kernels | D2H; the two calls issued from %d host "
+                       "thread(s))" % (2 if pool is not None else 1),
                 "float_depth": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                                 "note": "same call fed float depth (what PlaneDetection_CAPE::readDepthImage takes); "
                                         "H2D-bound: 393 MB per step over PCIe"}},
