@@ -83,3 +83,17 @@ def test_synth_frame_is_deterministic(drfe):
     assert a[2] == (262.5, 262.5, 159.5, 119.5)
     g, d, _ = drfe.synth_frame(640, 480, 1, 20260001, 1000.0)
     assert g.std() > 20 and 1000 < d[d > 0].min() and d.max() < 15000 and 0.005 < (d == 0).mean() < 0.2
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/drfe.h is the drop-in boundary: it must compile as C99 (no C++ or torch types in the signatures)"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "drfe.h"\nint main(void) { drfe_keypoint k; drfe_plane p; drfe_last_point l; drfe_track_params t; drfe_proj_query q;\n'
+                   '  (void)k; (void)p; (void)l; (void)t; (void)q; return sizeof(drfe_keypoint) == 28 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
