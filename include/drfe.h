@@ -10,6 +10,14 @@
  *   PlaneDetection_CAPE::runPlaneDetection()  (depth -> organized cloud -> CAPE)
  *        reference src/PlaneExtractor.cpp:111-191
  *
+ * and, on the results those leave on the device, the data-parallel per-frame steps either side of them
+ * ("next" rows of SURVEY.md 8f), each entry point citing what it replaces:
+ *   cvtColor to gray (Tracking.cc:194-207), depth scaling (Frame.cc:113-115)
+ *   UndistortKeyPoints / ComputeStereoFromRGBD / AssignFeaturesToGrid (Frame.cc:835-911, 224-237)
+ *   per-plane point lists (PlaneExtractor.cpp:165-190)
+ *   Frame::ComputeBoW = DBoW2 transform (Frame.cc:828-833, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1258)
+ *   ORBmatcher::SearchByProjection (map points :46-130, last frame :1396-1535), SearchByBoW (:160-292)
+ *
  * Plain C, POD only (no OpenCV / Eigen / torch types).  Every function returns an
  * int status: 0 = DRFE_OK, negative = error (drfe_last_error() has the text).  There
  * is NO CPU fallback: if no CUDA device is usable every create call fails loudly.
