@@ -1507,9 +1507,9 @@ __global__ void __launch_bounds__(kTrackThreads) k_search_last_frame(const OrbDe
   }
   __syncthreads();
   if (S.key_point) for (int k = tid; k < cap; k += kTrackThreads) S.key_point[(long long)f * cap + k] = owner[k];
-  for (int i = tid; i < np; i += kTrackThreads) {
-    S.match_key[(long long)f * S.pcap + i] = choice[i];
-    S.match_dist[(long long)f * S.pcap + i] = cdist[i];
+  for (int i = tid; i < S.pcap; i += kTrackThreads) {                          // slots past npoints[f]: no match
+    S.match_key[(long long)f * S.pcap + i] = i < np ? choice[i] : -1;
+    S.match_dist[(long long)f * S.pcap + i] = i < np ? cdist[i] : 256;
   }
   if (tid == 0) { S.nmatches[f] = s_cnt[0] - s_cnt[1]; S.sweeps[f] = sweeps; }
 }
@@ -1600,7 +1600,14 @@ __global__ void __launch_bounds__(kTrackThreads) k_search_local_points(const Orb
   for (int k = tid; k < cap; k += kTrackThreads) owner[k] = -1;
   __syncthreads();
   int mine = 0;
-  for (int i = tid; i < nq; i += kTrackThreads) {
+  for (int i = tid; i < S.qcap; i += kTrackThreads) {
+    if (i >= nq) {                                                        // slots past nqueries[f]: the empty record
+      drfe_proj_match m;
+      m.best_dist = 256; m.best_idx = -1; m.best_level = -1; m.best_dist2 = 256; m.best_level2 = -1;
+      S.out[(long long)f * S.qcap + i] = m;
+      S.assigned[(long long)f * S.qcap + i] = -1;
+      continue;
+    }
     S.assigned[(long long)f * S.qcap + i] = choice[i];
     if (choice[i] >= 0) { ++mine; atomicMax(&owner[choice[i]], i); }     // the last writer of F.mvpMapPoints[bestIdx] stays
   }

@@ -250,7 +250,7 @@ def gpu_case(drfe, orc, seeds, scenes, modes, checks, ths, npts, with_occ, size=
         assert np.array_equal(md[f, :m], wmd), f
         assert np.array_equal(kp[f, :n], wh), f
         assert nm[f] == wnm, f
-        assert (kp[f, n:] == -1).all()
+        assert (kp[f, n:] == -1).all() and (mk[f, m:] == -1).all() and (md[f, m:] == 256).all()
     return mk, sw, nm
 
 

@@ -176,4 +176,5 @@ def test_gpu_search_local_points(drfe, orc):
             for name in wrec.dtype.names:
                 assert np.array_equal(rec[f, :m][name], wrec[name]), (f, name)
             assert np.array_equal(asg[f, :m], wasg) and np.array_equal(kp[f, :n], wh) and nm[f] == wnm, f
+            assert (asg[f, m:] == -1).all() and (rec[f, m:]["best_idx"] == -1).all() and (rec[f, m:]["best_dist"] == 256).all()
         assert nm[0] > 300 and nm[2] == 0
