@@ -151,7 +151,9 @@ struct ChunkPipe {
       const int head[2] = {8, 16};
       for (int i = 0; i < 2; ++i) { start[n++] = f; f += head[i]; }
       const int mid_end = nframes - 24;
-      while (f < mid_end) { start[n++] = f; f += (mid_end - f < 32) ? mid_end - f : 32; }
+      int mid = 32;                                              // larger middle chunks on very long batches: at most kMaxChunks chunks
+      while ((mid_end - 24 + mid - 1) / mid > kMaxChunks - 4) ++mid;
+      while (f < mid_end) { start[n++] = f; f += (mid_end - f < mid) ? mid_end - f : mid; }
       start[n++] = f; f += 16;
       start[n++] = f; f += 8;
     } else {

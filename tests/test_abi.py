@@ -97,3 +97,21 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_chunk_schedule_host_logic(tmp_path):
+    """ChunkPipe::schedule (the chunk boundaries of the pipelined batch calls): every batch length 1..3000 and every
+    chunk wish gives between 1 and kMaxChunks non-empty chunks that tile the batch; 256 frames give the ramped
+    8, 16, 32 ... 32, 16, 8 schedule.  Host-only C++ (tests/host/chunk_schedule_test.cpp), no GPU."""
+    import shutil
+    import subprocess
+    cuda_inc = "/usr/local/cuda/include"
+    if not shutil.which("g++") or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path / "sched")
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "dr-slam_b200", "csrc"), "-I", cuda_inc,
+                        os.path.join(ROOT, "tests", "host", "chunk_schedule_test.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip() == "11: 8 16 32 32 32 32 32 32 16 16 8"
