@@ -62,3 +62,23 @@ def test_frame_post_matches_reference_loops(orc, drfe, calib):
     assert np.array_equal(gc.reshape(64, 48), np.array([[len(c) for c in col] for col in grid], np.uint16))
     assert gi.tolist() == [i for col in grid for c in col for i in c]
     assert gc.sum() == len(gi) > 900
+
+
+@pytest.mark.parametrize("calib,size", [(TUM1, (640, 480)), (ICL, (640, 480)), (TUM1, (1280, 720)),
+                                        (dict(TUM1, dist=[-0.3, 0.12, 0.001, -0.002, 0.0]), (752, 480))])
+def test_product_image_bounds_equal_oracle_and_cv2(drfe, orc, calib, size):
+    """drfe_frame_image_bounds (Frame::ComputeImageBounds, Frame.cc:863-891) is host code of the product library and runs
+    without a GPU: it must equal the oracle's and the four corners undistorted by cv2.undistortPoints"""
+    import ctypes as C
+    w, h = size
+    p = drfe.FrameParams(calib["fx"], calib["fy"], calib["cx"], calib["cy"], (C.c_float * 5)(*calib["dist"]), calib["bf"], 0, 0, 0, 0)
+    assert drfe.lib().drfe_frame_image_bounds(C.byref(p), w, h) == 0
+    o = orc.frame_params(calib["fx"], calib["fy"], calib["cx"], calib["cy"], calib["dist"], calib["bf"], w, h)
+    assert (p.min_x, p.max_x, p.min_y, p.max_y) == (o.min_x, o.max_x, o.min_y, o.max_y)
+    if calib["dist"][0] != 0.0:
+        c = cv_undistort(np.array([[0, 0], [w, 0], [0, h], [w, h]], np.float32), calib)
+        assert p.min_x == min(c[0, 0], c[2, 0]) and p.max_x == max(c[1, 0], c[3, 0])
+        assert p.min_y == min(c[0, 1], c[1, 1]) and p.max_y == max(c[2, 1], c[3, 1])
+    else:
+        assert (p.min_x, p.max_x, p.min_y, p.max_y) == (0.0, float(w), 0.0, float(h))
+    assert drfe.lib().drfe_frame_image_bounds(None, w, h) == drfe.ERR_ARG
