@@ -115,3 +115,22 @@ def test_chunk_schedule_host_logic(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.strip() == "11: 8 16 32 32 32 32 32 32 16 16 8"
+
+
+def test_vocabulary_argument_checks_without_a_gpu(drfe):
+    """drfe_vocab_create applies TemplatedVocabulary::loadFromTextFile's header checks (TemplatedVocabulary.h:1359) before it
+    touches a device, and fails loudly without one"""
+    L = drfe.lib()
+    h = C.c_void_p()
+    parent = np.zeros(3, np.int32)
+    leaf = np.ones(3, np.uint8)
+    desc = np.zeros((3, 32), np.uint8)
+    wt = np.ones(3, np.float64)
+    args = lambda k, Lv, s, w: L.drfe_vocab_create(k, Lv, s, w, 3, parent.ctypes.data, leaf.ctypes.data, desc.ctypes.data, wt.ctypes.data, 0, C.byref(h))  # noqa: E731
+    for bad in ((25, 6, 0, 0), (10, 0, 0, 0), (10, 11, 0, 0), (10, 6, 6, 0), (10, 6, 0, 4), (-1, 6, 0, 0)):
+        assert args(*bad) == drfe.ERR_ARG, bad
+    assert L.drfe_vocab_create(10, 6, 0, 0, 3, None, leaf.ctypes.data, desc.ctypes.data, wt.ctypes.data, 0, C.byref(h)) == drfe.ERR_ARG
+    assert L.drfe_vocab_words(None) == 0
+    L.drfe_vocab_destroy(None)
+    if drfe.device_count() == 0:
+        assert args(10, 6, 0, 0) == drfe.ERR_CUDA and b"no CPU fallback" in L.drfe_last_error()
