@@ -38,6 +38,16 @@ int orc_frame_image_bounds(drfe_frame_params* p, int width, int height);
 int orc_frame_post(const drfe_frame_params* p, const drfe_keypoint* keys, int n, const float* depth, int row_stride,
                    drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count, uint16_t* grid_index);
 
+/* ---- matchers (match_oracle.cpp): the C++ restatement beside the Python one of oracle.py ---- */
+int orc_search_last_frame(const drfe_frame_params* p, const float* scale_factors, const drfe_keypoint* keys_un, const float* u_right, int n,
+                          const uint16_t* grid_count, const uint16_t* grid_index, const uint8_t* desc, const float* Tcw, float th, int mode,
+                          int check_orientation, const drfe_last_point* points, const uint8_t* pdesc, int npoints, const uint8_t* occupied,
+                          int32_t* match_key, int32_t* match_dist, int32_t* holder);
+int orc_search_local_points(const drfe_frame_params* p, const drfe_keypoint* keys_un, const float* u_right, int n, const uint16_t* grid_count,
+                            const uint16_t* grid_index, const uint8_t* desc, const drfe_proj_query* queries, const uint8_t* qdesc,
+                            const uint8_t* qflags, int nq, float mfNNratio, const uint8_t* occupied, drfe_proj_match* out, int32_t* assigned,
+                            int32_t* holder);
+
 /* ---- CAPE (cape_oracle.cpp) ---- */
 void* orc_cape_create(int depth_height, int depth_width, int cell_width, int cell_height,
                       int cylinder_detection, float min_cos_angle_4_merge, float max_merge_dist);

@@ -699,6 +699,55 @@ def search_by_bow(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv, nnr
     return kf_match, f_match, nmatches
 
 
+MATCH_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "<i4"), ("best_dist2", "<i4"), ("best_level2", "<i4")])
+QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("xr", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
+
+
+def search_last_frame_cpp(p, scale_factors, keys_un, u_right, grid_count, grid_index, desc, Tcw, th, mode, check_orientation,
+                          points, pdesc, occupied=None):
+    """the C++ restatement of the same function (oracle/match_oracle.cpp, std::vector / push_back as the reference) — same
+    arguments and results as search_last_frame"""
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    n, m = len(keys_un), len(points)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    ur = np.ascontiguousarray(u_right, np.float32)
+    gc = np.ascontiguousarray(np.asarray(grid_count).ravel(), np.uint16)
+    gi = np.ascontiguousarray(grid_index, np.uint16)
+    d = np.ascontiguousarray(desc, np.uint8)
+    T = np.ascontiguousarray(Tcw, np.float32)
+    pts = np.ascontiguousarray(points, LAST_POINT_DTYPE)
+    pd = np.ascontiguousarray(pdesc, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied[:n], np.uint8)
+    mk, md, holder = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros(n, np.int32)
+    f = lib().orc_search_last_frame
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    nm = f(C.addressof(p), _p(sf), _p(keys_un), _p(ur), n, _p(gc), _p(gi), _p(d), _p(T), float(th), int(mode), int(check_orientation), _p(pts), _p(pd), m,
+           None if occ is None else _p(occ), _p(mk), _p(md), _p(holder))
+    return mk, md, holder, nm
+
+
+def search_local_points_cpp(p, keys_un, u_right, grid_count, grid_index, desc, queries, qdesc, qflags, nnratio, occupied=None):
+    """the C++ restatement of search_local_points (oracle/match_oracle.cpp)"""
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    n, m = len(keys_un), len(queries)
+    ur = np.ascontiguousarray(u_right, np.float32)
+    gc = np.ascontiguousarray(np.asarray(grid_count).ravel(), np.uint16)
+    gi = np.ascontiguousarray(grid_index, np.uint16)
+    d = np.ascontiguousarray(desc, np.uint8)
+    q = np.ascontiguousarray(queries, QUERY_DTYPE)
+    qd = np.ascontiguousarray(qdesc, np.uint8)
+    fl = np.ascontiguousarray(qflags, np.uint8)
+    occ = None if occupied is None else np.ascontiguousarray(occupied[:n], np.uint8)
+    out, asg, holder = np.zeros(m, MATCH_DTYPE), np.zeros(m, np.int32), np.zeros(n, np.int32)
+    f = lib().orc_search_local_points
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_float] + [C.c_void_p] * 4
+    nm = f(C.addressof(p), _p(keys_un), _p(ur), n, _p(gc), _p(gi), _p(d), _p(q), _p(qd), _p(fl), m, float(nnratio), None if occ is None else _p(occ),
+           _p(out), _p(asg), _p(holder))
+    return out, asg, holder, nm
+
+
 def glibc_rand(seed, n):
     out = np.zeros(n, np.int32)
     lib().orc_glibc_rand(int(seed), n, _p(out))
