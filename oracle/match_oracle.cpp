@@ -4,6 +4,7 @@
 //   ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, ..) reference src/ORBmatcher.cc:1396-1535
 //   ORBmatcher::ComputeThreeMaxima / DescriptorDistance                             reference src/ORBmatcher.cc:1666-1728
 //   Frame::GetFeaturesInArea                                                        reference src/Frame.cc:730-779
+//   (further down) DBoW2 transform with BowVector / FeatureVector, ORBmatcher::SearchByBoW
 // tests/test_match_oracle.py requires the two restatements to agree value for value.  Float expressions are written as
 // the reference writes them; the library is built with -ffp-contract=off (declared: no FMA contraction).
 #include <cmath>
@@ -213,6 +214,182 @@ int orc_search_local_points(const drfe_frame_params* p, const drfe_keypoint* key
       observed[bestIdx] = (qflags[iMP] & DRFE_LP_OBSERVED) != 0;
       assigned[iMP] = bestIdx;
       nmatches++;
+    }
+  }
+  return nmatches;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- DBoW2 transform and SearchByBoW, with the reference's std::maps
+//   TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup)  Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1258
+//   BowVector::addWeight / addIfNotExist / normalize                                Thirdparty/DBoW2/DBoW2/BowVector.cpp:34-84
+//   FeatureVector::addFeature                                                       Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)                  src/ORBmatcher.cc:160-292
+#include <map>
+
+namespace {
+
+struct Node {   // TemplatedVocabulary::Node (TemplatedVocabulary.h:297-330)
+  unsigned id = 0;
+  double weight = 0;
+  std::vector<unsigned> children;
+  unsigned parent = 0;
+  uint8_t descriptor[32] = {0};
+  unsigned word_id = 0;
+  bool isLeaf() const { return children.empty(); }
+};
+
+typedef std::map<unsigned, double> BowVector;
+typedef std::map<unsigned, std::vector<unsigned>> FeatureVector;
+
+void addWeight(BowVector& v, unsigned id, double w) {   // BowVector.cpp:34-46
+  BowVector::iterator vit = v.lower_bound(id);
+  if (vit != v.end() && !(v.key_comp()(id, vit->first))) vit->second += w;
+  else v.insert(vit, BowVector::value_type(id, w));
+}
+void addIfNotExist(BowVector& v, unsigned id, double w) {   // :50-58
+  BowVector::iterator vit = v.lower_bound(id);
+  if (vit == v.end() || (v.key_comp()(id, vit->first))) v.insert(vit, BowVector::value_type(id, w));
+}
+void addFeature(FeatureVector& fv, unsigned id, unsigned i_feature) {   // FeatureVector.cpp:31-45
+  FeatureVector::iterator vit = fv.lower_bound(id);
+  if (vit != fv.end() && vit->first == id) vit->second.push_back(i_feature);
+  else { vit = fv.insert(vit, FeatureVector::value_type(id, std::vector<unsigned>())); vit->second.push_back(i_feature); }
+}
+
+}  // namespace
+
+extern "C" {
+
+// returns the BowVector size; bow_key / bow_value and fv_node / fv_start / fv_feat receive the maps in iteration order
+int orc_bow_transform(int L, int scoring, int weighting, int nnodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* descriptors,
+                      const double* weights, const uint8_t* features, int nfeatures, int levelsup, int32_t* word_of, int32_t* node_of,
+                      int32_t* bow_key, double* bow_value, int* fv_n, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat) {
+  // loadFromTextFile (:1376-1418)
+  std::vector<Node> m_nodes(1);
+  unsigned nwords = 0;
+  for (int i = 0; i < nnodes; ++i) {
+    const unsigned nid = m_nodes.size();
+    m_nodes.resize(m_nodes.size() + 1);
+    m_nodes[nid].id = nid;
+    m_nodes[nid].parent = parent[i];
+    m_nodes[parent[i]].children.push_back(nid);
+    memcpy(m_nodes[nid].descriptor, descriptors + (size_t)i * 32, 32);
+    m_nodes[nid].weight = weights[i];
+    if (is_leaf[i] > 0) m_nodes[nid].word_id = nwords++;
+  }
+  BowVector v;
+  FeatureVector fv;
+  const bool must = scoring != 5;               // ScoringObject.h:73-89
+  const bool l2 = scoring == 1;
+  for (int i_feature = 0; i_feature < nfeatures; ++i_feature) {
+    const uint8_t* feature = features + (size_t)i_feature * 32;
+    // transform(feature, word_id, weight, nid, levelsup) (:1217-1258)
+    const int nid_level = L - levelsup;
+    unsigned nid = 0;
+    bool nid_set = nid_level <= 0;
+    unsigned final_id = 0;
+    int current_level = 0;
+    do {
+      ++current_level;
+      const std::vector<unsigned>& nodes = m_nodes[final_id].children;
+      final_id = nodes[0];
+      double best_d = DescriptorDistance(feature, m_nodes[final_id].descriptor);
+      for (std::vector<unsigned>::const_iterator nit = nodes.begin() + 1; nit != nodes.end(); ++nit) {
+        const unsigned id = *nit;
+        const double d = DescriptorDistance(feature, m_nodes[id].descriptor);
+        if (d < best_d) { best_d = d; final_id = id; }
+      }
+      if (current_level == nid_level) { nid = final_id; nid_set = true; }
+    } while (!m_nodes[final_id].isLeaf());
+    if (!nid_set) nid = final_id;               // declared (the reference leaves *nid uninitialised)
+    const unsigned id = m_nodes[final_id].word_id;
+    const double w = m_nodes[final_id].weight;
+    word_of[i_feature] = -1; node_of[i_feature] = -1;
+    if (w > 0) {
+      if (weighting <= 1) addWeight(v, id, w); else addIfNotExist(v, id, w);
+      addFeature(fv, nid, i_feature);
+      word_of[i_feature] = (int32_t)id; node_of[i_feature] = (int32_t)nid;
+    }
+  }
+  if (weighting <= 1 && !v.empty() && !must) {  // :1164-1170
+    const double nd = v.size();
+    for (BowVector::iterator vit = v.begin(); vit != v.end(); vit++) vit->second /= nd;
+  }
+  if (must) {                                   // BowVector::normalize (:62-84)
+    double norm = 0.0;
+    if (!l2) { for (BowVector::iterator it = v.begin(); it != v.end(); ++it) norm += fabs(it->second); }
+    else { for (BowVector::iterator it = v.begin(); it != v.end(); ++it) norm += it->second * it->second; norm = sqrt(norm); }
+    if (norm > 0.0) for (BowVector::iterator it = v.begin(); it != v.end(); ++it) it->second /= norm;
+  }
+  int j = 0;
+  for (BowVector::const_iterator it = v.begin(); it != v.end(); ++it, ++j) { bow_key[j] = (int32_t)it->first; bow_value[j] = it->second; }
+  int k = 0, o = 0;
+  for (FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++k) {
+    fv_node[k] = (int32_t)it->first; fv_start[k] = o;
+    for (size_t t = 0; t < it->second.size(); ++t) fv_feat[o++] = (int32_t)it->second[t];
+  }
+  fv_start[k] = o;
+  *fv_n = k;
+  return j;
+}
+
+// SearchByBoW: FeatureVectors given flat (node, start, feat); f_match models vpMapPointMatches (keyframe feature index or -1)
+int orc_search_by_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, int nk, int kf_fv_n, const int32_t* kf_fv_node,
+                      const int32_t* kf_fv_start, const int32_t* kf_fv_feat, const uint8_t* f_desc, const float* f_angle, int nf, int f_fv_n,
+                      const int32_t* f_fv_node, const int32_t* f_fv_start, const int32_t* f_fv_feat, float mfNNratio, int check_orientation,
+                      int32_t* kf_match, int32_t* f_match) {
+  const int TH_LOW = 50;
+  FeatureVector vFeatVecKF, FFeatVec;
+  for (int j = 0; j < kf_fv_n; ++j) vFeatVecKF[kf_fv_node[j]] = std::vector<unsigned>(kf_fv_feat + kf_fv_start[j], kf_fv_feat + kf_fv_start[j + 1]);
+  for (int j = 0; j < f_fv_n; ++j) FFeatVec[f_fv_node[j]] = std::vector<unsigned>(f_fv_feat + f_fv_start[j], f_fv_feat + f_fv_start[j + 1]);
+  for (int i = 0; i < nf; ++i) f_match[i] = -1;
+  for (int i = 0; i < nk; ++i) kf_match[i] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  FeatureVector::const_iterator KFit = vFeatVecKF.begin(), Fit = FFeatVec.begin(), KFend = vFeatVecKF.end(), Fend = FFeatVec.end();
+  while (KFit != KFend && Fit != Fend) {
+    if (KFit->first == Fit->first) {
+      const std::vector<unsigned> vIndicesKF = KFit->second, vIndicesF = Fit->second;
+      for (size_t iKF = 0; iKF < vIndicesKF.size(); iKF++) {
+        const unsigned realIdxKF = vIndicesKF[iKF];
+        if (!kf_valid[realIdxKF]) continue;
+        const uint8_t* dKF = kf_desc + (size_t)realIdxKF * 32;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (size_t iF = 0; iF < vIndicesF.size(); iF++) {
+          const unsigned realIdxF = vIndicesF[iF];
+          if (f_match[realIdxF] >= 0) continue;
+          const int dist = DescriptorDistance(dKF, f_desc + (size_t)realIdxF * 32);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= TH_LOW) {
+          if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+            f_match[bestIdxF] = realIdxKF;
+            kf_match[realIdxKF] = bestIdxF;
+            if (check_orientation) {
+              float rot = kf_angle[realIdxKF] - f_angle[bestIdxF];
+              if (rot < 0.0) rot += 360.0f;
+              int bin = round(rot * factor);
+              if (bin == HISTO_LENGTH) bin = 0;
+              rotHist[bin].push_back(bestIdxF);
+            }
+            nmatches++;
+          }
+        }
+      }
+      KFit++; Fit++;
+    } else if (KFit->first < Fit->first) KFit = vFeatVecKF.lower_bound(Fit->first);
+    else Fit = FFeatVec.lower_bound(KFit->first);
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { f_match[rotHist[i][j]] = -1; nmatches--; }
     }
   }
   return nmatches;

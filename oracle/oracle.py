@@ -748,6 +748,52 @@ def search_local_points_cpp(p, keys_un, u_right, grid_count, grid_index, desc, q
     return out, asg, holder, nm
 
 
+def bow_transform_cpp(voc, descriptors, levelsup=4):
+    """the C++ restatement of Vocabulary.transform with the reference's std::maps (oracle/match_oracle.cpp): same results"""
+    d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+    n = len(d)
+    parent = np.ascontiguousarray(voc["parent"], np.int32)
+    leaf = np.ascontiguousarray(voc["is_leaf"], np.uint8)
+    vd = np.ascontiguousarray(voc["descriptors"], np.uint8)
+    wt = np.ascontiguousarray(voc["weights"], np.float64)
+    words, nodes = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    bk, bv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    fn = C.c_int(0)
+    fnode, fstart, ffeat = np.zeros(max(n, 1), np.int32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.int32)
+    f = lib().orc_bow_transform
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 8
+    nb = f(int(voc["L"]), int(voc["scoring"]), int(voc["weighting"]), len(parent), _p(parent), _p(leaf), _p(vd), _p(wt), _p(d), n, int(levelsup),
+           _p(words), _p(nodes), _p(bk), _p(bv), C.addressof(fn), _p(fnode), _p(fstart), _p(ffeat))
+    bow = [(int(bk[j]), float(bv[j])) for j in range(nb)]
+    fv = [(int(fnode[j]), ffeat[fstart[j]:fstart[j + 1]].tolist()) for j in range(fn.value)]
+    return words, nodes, bow, fv
+
+
+def _flat_fv(fv):
+    node = np.array([k for k, _ in fv], np.int32)
+    start = np.cumsum([0] + [len(l) for _, l in fv]).astype(np.int32)
+    feat = np.array([i for _, l in fv for i in l], np.int32)
+    return np.ascontiguousarray(node), np.ascontiguousarray(start), np.ascontiguousarray(feat if len(feat) else np.zeros(1, np.int32))
+
+
+def search_by_bow_cpp(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv, nnratio=0.7, check_orientation=True):
+    """the C++ restatement of search_by_bow (oracle/match_oracle.cpp, the reference's map iterators and lower_bound)"""
+    kd = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
+    fd = np.ascontiguousarray(f_desc, np.uint8).reshape(-1, 32)
+    ka, fa = np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(f_angle, np.float32)
+    kv = np.ascontiguousarray(kf_valid, np.uint8)
+    kn, ks, kf = _flat_fv(kf_fv)
+    fn, fs, ff = _flat_fv(f_fv)
+    km, fm = np.zeros(len(kd), np.int32), np.zeros(len(fd), np.int32)
+    f = lib().orc_search_by_bow
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    nm = f(_p(kd), _p(ka), _p(kv), len(kd), len(kf_fv), _p(kn) if len(kn) else None, _p(ks), _p(kf), _p(fd), _p(fa), len(fd), len(f_fv),
+           _p(fn) if len(fn) else None, _p(fs), _p(ff), float(nnratio), int(check_orientation), _p(km), _p(fm))
+    return km, fm, nm
+
+
 def glibc_rand(seed, n):
     out = np.zeros(n, np.int32)
     lib().orc_glibc_rand(int(seed), n, _p(out))
