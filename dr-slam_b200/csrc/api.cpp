@@ -1,9 +1,24 @@
 // drfe C ABI: process-wide pieces (error text, version, launch counter).
 #include <cuda_runtime.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "drfe_internal.h"
 
 namespace drfe {
+
+cudaError_t raise_dyn_smem_impl(const void* func, int device, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> high;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = high[std::make_pair(func, device)];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 static thread_local char t_err[512] = "";
 std::atomic<long long> g_launches{0};

@@ -393,7 +393,7 @@ int drfe_orb_compute_bow(drfe_orb* h, const drfe_vocab* vc, int levelsup, int32_
   while (N < cap) N <<= 1;
   const size_t smem = (size_t)N * 8 + ((size_t)N + 1) * 4;
   if (smem > 200 * 1024) { set_error("drfe_orb_compute_bow: %d keypoints per frame do not fit", cap); return DRFE_ERR_CAPACITY; }
-  DRFE_CUDA(cudaFuncSetAttribute(k_bow_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DRFE_CUDA(raise_dyn_smem(k_bow_reduce, B.device, (size_t)(smem)));
   cudaStream_t st = B.stream;
   VocabDev V = v->dev;
   V.nid_level = v->L - levelsup;
@@ -474,7 +474,7 @@ int drfe_orb_search_by_bow(drfe_orb* h, int kcap, const int* kf_n, const uint8_t
   S.f_fv_n = (const int*)(d + o_ffn); S.f_fv_node = (const int*)(d + o_fnode); S.f_fv_start = (const int*)(d + o_fstart); S.f_fv_feat = (const int*)(d + o_ffeat);
   S.kf_match = (int*)(d + o_km); S.f_match = (int*)(d + o_fm); S.nmatches = (int*)(d + o_nm);
   S.kcap = kcap; S.nnratio = nnratio; S.check_orientation = check_orientation;
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_search_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = raise_dyn_smem(k_search_bow, B.device, (size_t)(smem));
   if (e == cudaSuccess) {
     k_search_bow<<<nf, 256, smem, st>>>(B.desc, B.kp, B.cnt, cap, S);
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -173,7 +173,7 @@ __device__ __forceinline__ void expand_seg(drfe_plane& a, const drfe_plane& b) {
 // memory for the two depth-jump scans (PlaneSeg.cpp:36-76), which two lanes run side by side.
 // Output per cell: 9 float sums, the valid-point count and the planarity flags so far
 // (CellSums); k_cape_fit turns that into the PlaneSeg with one thread per cell.
-struct CellSums { float s[9]; int cnt; int planar; int pad; };
+struct CellSums { float s[9]; int cnt; int planar; float diam; };   // diam: distance between the cell's first and last point
 
 __device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, float extra8) {
   float p = v + __shfl_down_sync(mask, v, 8, 16);        // lane[l] + lane[l+8]
@@ -184,22 +184,41 @@ __device__ __forceinline__ float tree16(float v, bool has_extra, unsigned mask, 
   return p;  // valid in lane 0 of the group
 }
 
-// (float)(t / den) without the fp64 division: q' = t * RN(1/den) is within 2 ulps of the
-// correctly rounded quotient q, so float(q') == float(q) unless a float rounding midpoint
-// (double mantissa bits 28..0 == 0x10000000) lies within a few ulps of q', or the result is
-// outside the float normal range — those rare cases take the exact division.
-__device__ __forceinline__ void div_exact_to_float2(double tx, double ty, double fx, double fy, float& x, float& y) {
-  x = (float)(tx / fx);
-  y = (float)(ty / fy);
+// ---- depth -> X, Y (PlaneExtractor.cpp:117-127): x = ((double)j - cx) * z / fx in double, stored as float.
+// (float)(t / den) without the fp64 division: q' = z * (dcol * RN(1/fx)) carries three roundings, so it is within
+// 4 ulps of the correctly rounded quotient q = RN(dcol * z / fx) (the product dcol * z is exact: a small half-integer
+// times a float), and float(q') == float(q) unless a float rounding midpoint (double mantissa bits 28..0 ==
+// 0x10000000) lies within a few ulps of q' — or the result leaves the float normal range, which a depth inside
+// [2^-20, 2^20) and sane intrinsics (XyCtx::sane) rule out.  Those rare cases take the exact division, so every
+// kernel that converts a depth (k_cape_sums, k_cape_refine, k_cape_cloud) produces the reference's bits.
+struct XyCtx { double fx, fy, rfx, rfy, cx, cy; bool sane; };
+__device__ __forceinline__ XyCtx xy_ctx(const CapeDev& P) {
+  XyCtx C;
+  C.fx = (double)P.fx; C.fy = (double)P.fy; C.cx = (double)P.cx; C.cy = (double)P.cy;
+  C.rfx = 1.0 / C.fx; C.rfy = 1.0 / C.fy;
+  C.sane = P.fx >= 0x1p-10f && P.fx <= 0x1p20f && P.fy >= 0x1p-10f && P.fy <= 0x1p20f && fabsf(P.cx) <= 32768.f && fabsf(P.cy) <= 32768.f &&
+           P.W <= 32768 && P.H <= 32768;
+  return C;
 }
-// true when float(q) might differ from float(exact quotient): q within a few double ulps of a
-// float rounding midpoint, or outside the float normal range (exact zeros are fine)
-__device__ __forceinline__ bool quotient_needs_exact(double q) {
-  const uint32_t lo = (uint32_t)__double2loint(q), hi = (uint32_t)__double2hiint(q);
-  const uint32_t ex = (hi >> 20) & 0x7FFu;
-  const bool near_mid = ((lo & 0x1FFFFFFFu) - 0x0FFFFFFCu) <= 8u;
-  const bool odd_range = (ex - 898u > 251u) && ((hi << 1) | lo) != 0u;
-  return near_mid || odd_range;
+// true when float(qx) or float(qy) might differ from the float of the exact quotient: within 8 double ulps of a float
+// rounding midpoint, or z outside {0} u [2^-20, 2^20)
+__device__ __forceinline__ bool xy_needs_exact(float z, double qx, double qy) {
+  const uint32_t a = ((uint32_t)__double2loint(qx) & 0x1FFFFFFFu) - 0x0FFFFFF8u;
+  const uint32_t b = ((uint32_t)__double2loint(qy) & 0x1FFFFFFFu) - 0x0FFFFFF8u;
+  const uint32_t zb = __float_as_uint(z);
+  return min(a, b) <= 16u || ((zb - 0x35800000u) >= 0x14000000u && zb != 0u);
+}
+__device__ __noinline__ void xy_exact(float z, double dcol, double drow, double fx, double fy, float& x, float& y) {
+  const double zd = (double)z;
+  x = (float)(dcol * zd / fx);
+  y = (float)(drow * zd / fy);
+}
+// one pixel, column offset dcol = (double)j - cx and row offset drow = (double)i - cy (both exact)
+__device__ __forceinline__ void xy_from_depth(const XyCtx& C, float z, double dcol, double drow, float& x, float& y) {
+  const double zd = (double)z;
+  const double qx = zd * (dcol * C.rfx), qy = zd * (drow * C.rfy);
+  if (!C.sane || xy_needs_exact(z, qx, qy)) xy_exact(z, dcol, drow, C.fx, C.fy, x, y);
+  else { x = (float)qx; y = (float)qy; }
 }
 
 static const int kSumsThreads = 128, kSumsChunk = 5;
@@ -217,6 +236,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // A 16-lane group walks kSumsCells consecutive cells; with a float depth image whose cell rows are 16-byte
 // aligned, the depth of the next two cells is copied into a two-slot shared-memory ring by cp.async (LDGSTS)
 // while the current cell is summed, so only the group's first load latency is exposed.
+// The cloud itself is NOT written (it was 900 MB per 256-frame step, two thirds of the kernel's DRAM traffic, for a
+// refinement stage that reads a third of it): k_cape_refine converts the depth of its border cells again, and
+// k_cape_cloud materialises the cell-major cloud when a caller asks for it (drfe_cape_get_cloud / plane_points).
 template <int MODE, int CELL>
 __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   constexpr bool FROM_DEPTH = MODE != 0;
@@ -257,19 +279,20 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
     cp_async_commit();
   };
   if (vec1) { prefetch(0); if (ncell_here > 1) prefetch(1); }
-  const double fx = (double)P.fx, fy = (double)P.fy;
-  const double rfx = 1.0 / fx, rfy = 1.0 / fy;
+  const XyCtx C = xy_ctx(P);
   const int step_r = 16 / cw, step_c = 16 - step_r * cw;    // element i + 16
   const double dstep_c = (double)step_c, dstep_r = (double)step_r, dcw = (double)cw;
+  const int last_lane = (npc - 1) & 15;                      // the lane that owns the cell's last element
   for (int c = 0; c < ncell_here; ++c) {
     const int gid = first + c + f0 * ncells;                  // global cell index over the batch
     const int f = gid / ncells, cell = gid - f * ncells;
     float* s_z = s_ring + (c & 1) * npc;
-    float* __restrict__ CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
-    float* __restrict__ CY = CX + N;
-    float* __restrict__ CZ = CY + N;
+    const float* __restrict__ CX = MODE == 0 ? P.cloud + (long long)f * 3 * N + (long long)cell * npc : nullptr;
+    const float* __restrict__ CY = CX + N;
+    const float* __restrict__ CZ = CY + N;
     float ax = 0, ay = 0, az = 0, axx = 0, ayy = 0, azz = 0, axy = 0, axz = 0, ayz = 0;
     float ex = 0, ey = 0, ez = 0, exx = 0, eyy = 0, ezz = 0, exy = 0, exz = 0, eyz = 0;  // extra packet
+    float x_first = 0, y_first = 0, z_first = 0, x_last = 0, y_last = 0, z_last = 0;     // elements 0 and npc - 1 (the cell's diameter)
     int cnt = 0;
     const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
     // ---- stage z in shared memory (it is also what the depth-jump scans read)
@@ -305,55 +328,88 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
       for (int i = l; i < npc; i += 16) s_z[i] = CZ[i];
     }
     __syncwarp(mask);
-    const double col0 = (double)(cc * cw) - (double)P.cx, row0 = (double)(cr * ch) - (double)P.cy;
-    int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
-    // (double)j - cx and (double)i - cy of the element, stepped along with (lr, lc): sums of small half-integers, exact
-    double dcol = col0 + (double)lc, drow = row0 + (double)lr;
-    // one element: FIRST = the lane's first element (it starts the accumulators), CHECKED = bounds tests needed
-    auto element = [&](int i, auto first_tag, auto checked_tag) {
+    // (double)j - cx and (double)i - cy of the cell's first pixel: differences of small (half-)integers, exact
+    const double col0 = (double)(cc * cw) - C.cx, row0 = (double)(cr * ch) - C.cy;
+    // the moment sums of one element: FIRST = the lane's first element (it starts the accumulators), CHECKED = bounds tests needed
+    auto accumulate = [&](int i, float x, float y, float z, auto first_tag, auto checked_tag) {
       constexpr bool FIRST = decltype(first_tag)::value, CHECKED = decltype(checked_tag)::value;
-      if (!CHECKED || i < npc) {
-        float x, y;
-        const float z = s_z[i];
-        if (FROM_DEPTH) {
-          // PlaneExtractor.cpp:117-127: x = ((double)j - cx) * z / fx in double, stored as float.
-          // (col0 + lc is exact: both are small half-integers, as is (double)j - cx.)
-          const double zd = (double)z;
-          const double tx = dcol * zd, ty = drow * zd;
-          const double qx = tx * rfx, qy = ty * rfy;
-          if (quotient_needs_exact(qx) || quotient_needs_exact(qy)) div_exact_to_float2(tx, ty, fx, fy, x, y);   // rare, out of line
-          else { x = (float)qx; y = (float)qy; }
-          CX[i] = x; CY[i] = y; CZ[i] = z;
-        } else {
-          x = CX[i]; y = CY[i];
-        }
-        cnt += (z > 0.f);
-        if (!CHECKED || i < body) {
-          if (CHECKED ? i < 16 : FIRST) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
-          else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
-                 axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
-        } else if (i < full8) {
-          ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
-        }
+      cnt += (z > 0.f);
+      if (!CHECKED || i < body) {
+        if (CHECKED ? i < 16 : FIRST) { ax = x; ay = y; az = z; axx = x * x; ayy = y * y; azz = z * z; axy = x * y; axz = x * z; ayz = y * z; }
+        else { ax = ax + x; ay = ay + y; az = az + z; axx = axx + x * x; ayy = ayy + y * y; azz = azz + z * z;
+               axy = axy + x * y; axz = axz + x * z; ayz = ayz + y * z; }
+      } else if (i < full8) {
+        ex = x; ey = y; ez = z; exx = x * x; eyy = y * y; ezz = z * z; exy = x * y; exz = x * z; eyz = y * z;
       }
-      lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
-      if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
     };
-    if (CELL == 20) {
-      // 400 = 5 x 5 x 16 elements: every lane owns exactly 25, no bounds tests; the first round is peeled because it
-      // starts the accumulators
-      element(l, std::true_type(), std::false_type());
+    if (CELL == 20 && FROM_DEPTH) {
+      // 400 = 5 chunks x 5 x 16 elements and 5 x 16 elements = 4 whole cell rows: element l + 16 u + 80 k of a lane sits in
+      // column lc[u] (the same for every chunk k) and row lr[u] + 4 k, so the column factors are five loop invariants and
+      // the row offsets advance by an exact 4.0 per chunk; every lane owns exactly 25 elements, no bounds tests
+      double kx[kSumsChunk], dr[kSumsChunk];
 #pragma unroll
-      for (int u = 1; u < kSumsChunk; ++u) element(l + 16 * u, std::false_type(), std::false_type());
+      for (int u = 0; u < kSumsChunk; ++u) {
+        const int i = l + 16 * u, lr = i / 20, lc = i - 20 * lr;
+        kx[u] = (col0 + (double)lc) * C.rfx;
+        dr[u] = row0 + (double)lr;
+      }
+      auto chunk = [&](int i0, auto first_tag) {
+#pragma unroll
+        for (int u = 0; u < kSumsChunk; ++u) {
+          const int i = i0 + 16 * u;
+          const float z = s_z[i];
+          const double zd = (double)z;
+          const double qx = zd * kx[u], qy = zd * (dr[u] * C.rfy);
+          float x, y;
+          if (!C.sane || xy_needs_exact(z, qx, qy)) {             // rare, out of line
+            const int lr = i / 20, lc = i - 20 * lr;
+            xy_exact(z, col0 + (double)lc, row0 + (double)lr, C.fx, C.fy, x, y);
+          } else { x = (float)qx; y = (float)qy; }
+          dr[u] += 4.0;
+          if (decltype(first_tag)::value && u == 0) accumulate(i, x, y, z, std::true_type(), std::false_type());
+          else accumulate(i, x, y, z, std::false_type(), std::false_type());
+        }
+      };
+      chunk(l, std::true_type());
 #pragma unroll 1
-      for (int i0 = l + 16 * kSumsChunk; i0 < 400; i0 += 16 * kSumsChunk) {
-#pragma unroll
-        for (int u = 0; u < kSumsChunk; ++u) element(i0 + 16 * u, std::false_type(), std::false_type());
+      for (int i0 = l + 16 * kSumsChunk; i0 < 400; i0 += 16 * kSumsChunk) chunk(i0, std::false_type());
+      if (l == 0) {                                             // the cell's first and last point once more, for its diameter
+        z_first = s_z[0]; z_last = s_z[399];
+        xy_from_depth(C, z_first, col0, row0, x_first, y_first);
+        xy_from_depth(C, z_last, col0 + 19.0, row0 + 19.0, x_last, y_last);
       }
     } else {
-      for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
+      int lr = l / cw, lc = l - lr * cw;                        // (row, column) of element i inside the cell
+      // (double)j - cx and (double)i - cy of the element, stepped along with (lr, lc): sums of small half-integers, exact
+      double dcol = col0 + (double)lc, drow = row0 + (double)lr;
+      auto element = [&](int i, auto first_tag, auto checked_tag) {
+        constexpr bool CHECKED = decltype(checked_tag)::value;
+        if (!CHECKED || i < npc) {
+          float x, y;
+          const float z = s_z[i];
+          if (FROM_DEPTH) xy_from_depth(C, z, dcol, drow, x, y);
+          else { x = CX[i]; y = CY[i]; }
+          if (i == 0) { x_first = x; y_first = y; z_first = z; }
+          if (i == npc - 1) { x_last = x; y_last = y; z_last = z; }
+          accumulate(i, x, y, z, first_tag, checked_tag);
+        }
+        lc += step_c; lr += step_r; dcol += dstep_c; drow += dstep_r;
+        if (lc >= cw) { lc -= cw; ++lr; dcol -= dcw; drow += 1.0; }
+      };
+      if (CELL == 20) {
+        element(l, std::true_type(), std::false_type());
 #pragma unroll
-        for (int u = 0; u < kSumsChunk; ++u) element(i0 + 16 * u, std::false_type(), std::true_type());
+        for (int u = 1; u < kSumsChunk; ++u) element(l + 16 * u, std::false_type(), std::false_type());
+#pragma unroll 1
+        for (int i0 = l + 16 * kSumsChunk; i0 < 400; i0 += 16 * kSumsChunk) {
+#pragma unroll
+          for (int u = 0; u < kSumsChunk; ++u) element(i0 + 16 * u, std::false_type(), std::false_type());
+        }
+      } else {
+        for (int i0 = l; i0 < npc; i0 += 16 * kSumsChunk) {
+#pragma unroll
+          for (int u = 0; u < kSumsChunk; ++u) element(i0 + 16 * u, std::false_type(), std::true_type());
+        }
       }
     }
 #pragma unroll
@@ -363,7 +419,11 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
           sxx = tree16(axx, has_extra, mask, exx), syy = tree16(ayy, has_extra, mask, eyy),
           szz = tree16(azz, has_extra, mask, ezz), sxy = tree16(axy, has_extra, mask, exy),
           sxz = tree16(axz, has_extra, mask, exz), syz = tree16(ayz, has_extra, mask, eyz);
-    __syncwarp(mask);                                         // s_z and the cloud are complete
+    // the cell's last element, for its diameter (CAPE.cpp:69-73 reads rows 0 and npc - 1 of the cell's block)
+    if (!(CELL == 20 && FROM_DEPTH)) {
+      x_last = __shfl_sync(mask, x_last, last_lane, 16); y_last = __shfl_sync(mask, y_last, last_lane, 16); z_last = __shfl_sync(mask, z_last, last_lane, 16);
+    }
+    __syncwarp(mask);                                         // s_z is complete
     // depth-jump scans through the middle row and the middle column (PlaneSeg.cpp:36-76): z_last follows the valid
     // depths as long as consecutive valid ones differ by < 100; a valid depth further away is a jump and leaves z_last
     // alone.  Without jumps z_last is simply the previous valid depth, so the 16 lanes first test every element
@@ -399,13 +459,13 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
       const bool group_fail = ((__ballot_sync(mask, fail) >> shift) & 0xFFFFu) != 0;
       if (group_fail && l < 2) {
         int i, j, step;
-        float z_last;
-        if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_last = fmaxf(s_z[i], s_z[i + 1]); }
-        else { i = cw / 2; j = npc - i; step = cw; z_last = fmaxf(s_z[i], s_z[i + cw]); }
+        float z_prev;
+        if (l == 0) { i = cw * (chh / 2); j = i + cw; step = 1; z_prev = fmaxf(s_z[i], s_z[i + 1]); }
+        else { i = cw / 2; j = npc - i; step = cw; z_prev = fmaxf(s_z[i], s_z[i + cw]); }
         i += step;
         while (i < j) {
           const float z = s_z[i];
-          if (z > 0 && fabsf(z - z_last) < 100.0f) z_last = z;
+          if (z > 0 && fabsf(z - z_prev) < 100.0f) z_prev = z;
           else if (z > 0) ++jumps;
           i += step;
         }
@@ -415,7 +475,10 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
     if (l == 0) {
       // scalar tail (Eigen's unaligned end), sequential
       for (int i = full8; i < npc; ++i) {
-        const float x = CX[i], y = CY[i], z = CZ[i];
+        float x, y;
+        const float z = s_z[i];
+        if (FROM_DEPTH) { const int lr = i / cw, lc = i - lr * cw; xy_from_depth(C, z, col0 + (double)lc, row0 + (double)lr, x, y); }
+        else { x = CX[i]; y = CY[i]; }
         sx = sx + x; sy = sy + y; sz = sz + z; sxx = sxx + x * x; syy = syy + y * y; szz = szz + z * z;
         sxy = sxy + x * y; sxz = sxz + x * z; syz = syz + y * z;
       }
@@ -423,7 +486,9 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
       o.s[0] = sx; o.s[1] = sy; o.s[2] = sz; o.s[3] = sxx; o.s[4] = syy; o.s[5] = szz; o.s[6] = sxy; o.s[7] = sxz; o.s[8] = syz;
       o.cnt = cnt;
       o.planar = (cnt >= npc / 2 && jumps <= 1 && jumps_v <= 1) ? 1 : 0;
-      o.pad = 0;
+      // cloud_array.block(cell)[npc - 1] - [0], the cell's diameter (CAPE.cpp:70-72)
+      const float dx = x_last - x_first, dy = y_last - y_first, dz = z_last - z_first;
+      o.diam = sqrtf(dx * dx + dy * dy + dz * dz);
       float4* dst = reinterpret_cast<float4*>(P.sums + (long long)gid);
       const float4* srcv = reinterpret_cast<const float4*>(&o);
       dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2];
@@ -431,6 +496,38 @@ __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __
     // the scans are done with this slot (the shuffle above is after them in every lane): refill it
     __syncwarp(mask);
     if (vec1 && c + 2 < ncell_here) prefetch(c + 2);
+  }
+}
+
+// The cell-major cloud of organizePointCloudByCell (PlaneExtractor.cpp:80-99, 112-127), on demand: thread = 4 pixels
+// of an image row (cells are at least 2 wide; a quad may straddle cells, every pixel is placed on its own).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_cape_cloud(const CapeDev* __restrict__ Pp, int nframes) {
+  const CapeDev& P = *Pp;
+  const XyCtx C = xy_ctx(P);
+  const int W = P.W, H = P.H, q = (W + 3) >> 2;
+  const long long N = (long long)H * W;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)nframes * H * q) return;
+  const int f = (int)(t / ((long long)H * q));
+  const int rem = (int)(t - (long long)f * H * q);
+  const int r = rem / q, c0 = 4 * (rem - r * q);
+  float* CX = P.cloud + (long long)f * 3 * N;
+  if (r >= P.ncy * P.ch) return;                                // below the last full cell row: not part of any cell
+  const int cell_r = r / P.ch, lr = r - cell_r * P.ch;
+  const double drow = (double)r - C.cy;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + k;
+    if (c >= P.ncx * P.cw) break;
+    float z;
+    if (MODE == 1) z = __ldg(P.depth + (long long)f * P.depth_fs + (long long)r * P.depth_rs + c);
+    else z = (float)__ldg(P.depth16 + (long long)f * P.depth_fs + (long long)r * P.depth_rs + c) * P.depth_factor;
+    float x, y;
+    xy_from_depth(C, z, (double)c - C.cx, drow, x, y);
+    const int cell_c = c / P.cw, lc = c - cell_c * P.cw;
+    const long long idx = (long long)(cell_r * P.ncx + cell_c) * P.npc + lr * P.cw + lc;
+    CX[idx] = x; CX[idx + N] = y; CX[idx + 2 * N] = z;
   }
 }
 
@@ -447,7 +544,7 @@ __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp
   const int total = nframes * P.ncells;
   if (gid0 < total) {
     const int gid = gid0 + f0 * P.ncells;
-    const int f = gid / P.ncells, cell = gid - f * P.ncells;
+    
     const int npc = P.npc;
     CellSums in;
     {
@@ -467,13 +564,8 @@ __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp
       fit_plane(s);
       const double lim = 0.000001425 * s.mean[2] * s.mean[2] + 10.0;   // Params.h:6-7
       if ((double)s.MSE > lim * lim) s.planar = 0;
-      if (s.planar) {  // cell_distance_tols (CAPE.cpp:69-73)
-        const long long N = (long long)P.H * P.W;
-        const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
-        const float* CY = CX + N;
-        const float* CZ = CY + N;
-        const float dx = CX[npc - 1] - CX[0], dy = CY[npc - 1] - CY[0], dz = CZ[npc - 1] - CZ[0];
-        const float diam = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (s.planar) {  // cell_distance_tols (CAPE.cpp:69-73); the cell's diameter comes with the sums
+        const float diam = in.diam;
         const float sin_merge = (float)sqrt(1.0 - (double)P.min_cos * (double)P.min_cos);
         const float t = fminf(fmaxf(diam * sin_merge, 20.0f), P.max_merge_dist);
         tol = t * t;
@@ -1374,8 +1466,10 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 // float distance, subject to < 9*MSE, strict '<' against the running minimum which starts at
 // the bit pattern memset(...,100,...) leaves (0x64646464, CAPE.cpp:60).  Cells inside an
 // eroded mask are painted whole (:410-412).
-template <bool CYL>
-__global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+// MODE as in k_cape_sums: with a depth image the points of a border cell are converted again here (the same
+// arithmetic, hence the same bits) instead of being read back from a cloud that k_cape_sums no longer writes.
+template <bool CYL, int MODE>
+__global__ void __launch_bounds__(256, 3) k_cape_refine(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   const CapeDev& P = *Pp;
   const int gw0 = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw0 >= nframes * P.ncells) return;
@@ -1435,19 +1529,57 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
     }
   }
   if ((anyb | anyc) == 0) { paint(0); return; }
-  const float* CX = P.cloud + (long long)f * 3 * N + (long long)cell * npc;
+  const float* CX = MODE == 0 ? P.cloud + (long long)f * 3 * N + (long long)cell * npc : nullptr;
   const float* CY = CX + N;
   const float* CZ = CY + N;
+  const XyCtx C = xy_ctx(P);
+  const double col0 = (double)(cc * cw) - C.cx, row0 = (double)(cr * P.ch) - C.cy;
+  const long long dbase = (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;   // the cell's first depth element
   const float4* eq = P.plane_eq + (long long)f * (kMaxPlanes + 1);
   const float* maxd = P.plane_maxd + (long long)f * (kMaxPlanes + 1);
-  if (!CYL && vec4 && (npc & 3) == 0 && npc < 8192) {
-    // planes only: 4 pixels per lane, float4 loads of the cell-major cloud, one word store
+  if (!CYL && vec4 && (npc & 3) == 0 && npc < 8192 &&
+      (MODE == 0 || (((P.depth_rs | P.depth_fs) & 3) == 0 && (reinterpret_cast<uintptr_t>(MODE == 1 ? (const void*)P.depth : (const void*)P.depth16) & (MODE == 1 ? 15 : 7)) == 0))) {
+    // planes only: 4 pixels per lane (float4 loads of the cell-major cloud, or one aligned 4-pixel depth load), one word store
     const float4* X4 = reinterpret_cast<const float4*>(CX);
     const float4* Y4 = reinterpret_cast<const float4*>(CY);
     const float4* Z4 = reinterpret_cast<const float4*>(CZ);
-    for (int j = lane; j < (npc >> 2); j += 32) {
-      const float4 xv = X4[j], yv = Y4[j], zv = Z4[j];
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w};
+    // the depth of every quad this lane will handle is requested before any of it is used (a border cell is a few
+    // dependent iterations per lane: one load latency per iteration was a quarter of the kernel's stall samples)
+    constexpr int kAhead = 4;                                   // 4 x 32 quads = cells of up to 512 pixels in one go
+    const int nq = npc >> 2;
+    float4 zq[kAhead];
+    auto load_depth = [&](int j) -> float4 {
+      const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
+      if (MODE == 1) return __ldg(reinterpret_cast<const float4*>(P.depth + dbase + (long long)lr * P.depth_rs + 4 * c4));
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(P.depth16 + dbase + (long long)lr * P.depth_rs + 4 * c4));
+      const float fac = P.depth_factor;
+      return make_float4((float)(v.x & 0xFFFFu) * fac, (float)(v.x >> 16) * fac, (float)(v.y & 0xFFFFu) * fac, (float)(v.y >> 16) * fac);
+    };
+    if (MODE != 0) {
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) { const int j = lane + 32 * a; zq[a] = j < nq ? load_depth(j) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    const double rfx = C.rfx, rfy = C.rfy;
+    (void)rfx; (void)rfy;
+#pragma unroll 1
+    for (int j0 = lane; j0 < nq; j0 += 32 * kAhead) {
+#pragma unroll
+     for (int a = 0; a < kAhead; ++a) {
+      const int j = j0 + 32 * a;
+      if (j >= nq) break;
+      const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
+      float xs[4], ys[4], zs[4];
+      if (MODE == 0) {
+        const float4 xv = X4[j], yv = Y4[j], zv = Z4[j];
+        xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w; ys[0] = yv.x; ys[1] = yv.y; ys[2] = yv.z; ys[3] = yv.w;
+        zs[0] = zv.x; zs[1] = zv.y; zs[2] = zv.z; zs[3] = zv.w;
+      } else {
+        const float4 zv = j0 == lane ? zq[a] : load_depth(j);   // cells of more than 512 pixels: later rounds load on the spot
+        zs[0] = zv.x; zs[1] = zv.y; zs[2] = zv.z; zs[3] = zv.w;
+        const double drow = row0 + (double)lr, dcol = col0 + (double)(4 * c4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xy_from_depth(C, zs[u], dcol + (double)u, drow, xs[u], ys[u]);
+      }
       float best[4];
       uint32_t lab = 0;
 #pragma unroll
@@ -1468,13 +1600,20 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
           }
         }
       }
-      const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
       *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = lab;
+     }
     }
     return;
   }
   for (int i = lane; i < npc; i += 32) {
-    const float x = CX[i], y = CY[i], z = CZ[i];
+    const int lr = i / cw, lc = i - lr * cw;
+    float x, y, z;
+    if (MODE == 0) { x = CX[i]; y = CY[i]; z = CZ[i]; }
+    else {
+      if (MODE == 1) z = __ldg(P.depth + dbase + (long long)lr * P.depth_rs + lc);
+      else z = (float)__ldg(P.depth16 + dbase + (long long)lr * P.depth_rs + lc) * P.depth_factor;
+      xy_from_depth(C, z, col0 + (double)lc, row0 + (double)lr, x, y);
+    }
     float best = __uint_as_float(0x64646464u);
     int lab = 0;
 #pragma unroll
@@ -1508,7 +1647,6 @@ __global__ void __launch_bounds__(256) k_cape_refine(const CapeDev* __restrict__
         }
       }
     }
-    const int lr = i / cw, lc = i - lr * cw;
     out[(long long)lr * P.W + lc] = (uint8_t)lab;
   }
 }
@@ -1613,6 +1751,7 @@ struct drfe_cape {
   size_t grid_smem = 0;
   int last_frames = 0;
   bool pending = false, margin = false;
+  bool cloud_valid = false;      // hd.cloud holds the cell-major cloud of the last enqueue (given by the caller, or materialised on demand)
   StageTimer timer;
   ChunkPipe pipe;
   int* batch_nplanes = nullptr;  // host destination of the running batch call
@@ -1688,7 +1827,6 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   int rc = DRFE_OK;
   auto fail = [&](int code) { drfe_cape_destroy(h); return code; };
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(DRFE_ERR_CUDA); }
-  rc |= cape_alloc(h, &D.cloud, 3 * N * B);
   rc |= cape_alloc(h, &D.cells, nc * B);
   rc |= cape_alloc(h, &D.tols, nc * B);
   rc |= cape_alloc(h, &D.cell_meta, nc * B);
@@ -1733,7 +1871,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &h->d_depth, N * B);
   rc |= cape_alloc(h, &h->dd, 1);
   if (rc) return fail(DRFE_ERR_CUDA);
-  if (cudaMemset(D.status, 0, sizeof(int)) != cudaSuccess || cudaMemset(D.cloud, 0, 3 * N * B * sizeof(float)) != cudaSuccess) {
+  if (cudaMemset(D.status, 0, sizeof(int)) != cudaSuccess) {
     set_error("cudaMemset failed"); return fail(DRFE_ERR_CUDA);
   }
   {
@@ -1745,15 +1883,15 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
     h->grid_smem = base + (D.grid_sums_smem ? nc * 36 : 0);
     if (h->grid_smem > 200 * 1024 || nw > 4 * 128) { set_error("drfe_cape_create: too many cells (%zu) for the grid stage", nc); return fail(DRFE_ERR_ARG); }
   }
-  if (cudaFuncSetAttribute(k_cape_grid<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess ||
-      cudaFuncSetAttribute(k_cape_grid<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grid_smem) != cudaSuccess) {
+  if (raise_dyn_smem((k_cape_grid<128, false>), h->device, (size_t)(h->grid_smem)) != cudaSuccess ||
+      raise_dyn_smem((k_cape_grid<128, true>), h->device, (size_t)(h->grid_smem)) != cudaSuccess) {
     set_error("cudaFuncSetAttribute failed"); return fail(DRFE_ERR_CUDA);
   }
   {
     const size_t sums_smem = (size_t)(kSumsThreads / 16) * 2 * D.npc * sizeof(float);
     if (sums_smem > 200 * 1024) { set_error("drfe_cape_create: cells of %d points are too large", D.npc); return fail(DRFE_ERR_ARG); }
     cudaError_t e = cudaSuccess;
-#define DRFE_SUMS_ATTR(M, C) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cape_sums<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sums_smem)
+#define DRFE_SUMS_ATTR(M, C) if (e == cudaSuccess) e = raise_dyn_smem((k_cape_sums<M, C>), h->device, sums_smem)
     DRFE_SUMS_ATTR(0, 0); DRFE_SUMS_ATTR(1, 0); DRFE_SUMS_ATTR(2, 0);
     DRFE_SUMS_ATTR(0, 20); DRFE_SUMS_ATTR(1, 20); DRFE_SUMS_ATTR(2, 20);
     DRFE_SUMS_ATTR(0, 10); DRFE_SUMS_ATTR(1, 10); DRFE_SUMS_ATTR(2, 10);
@@ -1816,9 +1954,38 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
     const long long tot = (long long)h->hd.H * h->hd.W * n;
     DRFE_LAUNCH(k_cape_clear_margin, (unsigned)((tot + 255) / 256), 256, 0, st, h->dd, f0, n);
   }
-  if (h->hd.cyl) DRFE_LAUNCH(k_cape_refine<true>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, f0, n);
-  else DRFE_LAUNCH(k_cape_refine<false>, (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, f0, n);
+#define DRFE_REFINE(CYL, M) DRFE_LAUNCH((k_cape_refine<CYL, M>), (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, f0, n)
+#define DRFE_REFINE_MODE(CYL) do { if (mode == 2) DRFE_REFINE(CYL, 2); else if (mode == 1) DRFE_REFINE(CYL, 1); else DRFE_REFINE(CYL, 0); } while (0)
+  if (h->hd.cyl) DRFE_REFINE_MODE(true); else DRFE_REFINE_MODE(false);
+#undef DRFE_REFINE_MODE
+#undef DRFE_REFINE
   if (timed) h->timer.mark("refine", st);
+  return DRFE_OK;
+}
+
+// The cell-major cloud buffer (3.7 MB per 640x480 frame) exists only for callers that hand a cloud in
+// (drfe_cape_enqueue_cloud) or ask for it (drfe_cape_get_cloud, drfe_cape_plane_points).
+static int cape_cloud_buffer(drfe_cape* h) {
+  if (h->hd.cloud) return DRFE_OK;
+  const size_t n = (size_t)3 * h->hd.H * h->hd.W * h->max_batch;
+  if (cape_alloc(h, &h->hd.cloud, n)) return DRFE_ERR_CUDA;
+  DRFE_CUDA(cudaMemsetAsync(h->hd.cloud, 0, n * sizeof(float), h->stream));
+  return DRFE_OK;
+}
+// organizePointCloudByCell on demand: converts the depth of the last enqueue (which must still be where the caller put it
+// when it was given as a device pointer) into the cell-major cloud, once
+static int cape_materialize_cloud(drfe_cape* h) {
+  if (h->cloud_valid) return DRFE_OK;
+  if (!h->hd.depth && !h->hd.depth16) { set_error("no depth image to build the cloud from"); return DRFE_ERR_STATE; }
+  int rc = cape_cloud_buffer(h);
+  if (rc != DRFE_OK) return rc;
+  cudaStream_t st = h->stream;
+  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
+  const long long threads = (long long)h->last_frames * h->hd.H * ((h->hd.W + 3) / 4);
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (h->hd.depth16) DRFE_LAUNCH(k_cape_cloud<2>, blocks, 256, 0, st, h->dd, h->last_frames);
+  else DRFE_LAUNCH(k_cape_cloud<1>, blocks, 256, 0, st, h->dd, h->last_frames);
+  h->cloud_valid = true;
   return DRFE_OK;
 }
 
@@ -1838,6 +2005,7 @@ int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_
   if (frame_stride < N3 && nframes > 1) { set_error("drfe_cape_enqueue_cloud: frame_stride too small"); return DRFE_ERR_ARG; }
   DeviceScope ds(h->device);
   cudaStream_t st = h->stream;
+  if (cape_cloud_buffer(h) != DRFE_OK) return DRFE_ERR_CUDA;
   h->timer.begin(st);
   const cudaMemcpyKind kind = mem_kind == DRFE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   if (mem_kind != DRFE_MEM_HOST && mem_kind != DRFE_MEM_DEVICE) { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
@@ -1847,7 +2015,9 @@ int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_
     DRFE_CUDA(cudaMemcpy2DAsync(h->hd.cloud, N3 * sizeof(float), cloud, frame_stride * sizeof(float), N3 * sizeof(float), nframes, kind, st));
   h->timer.mark("copy_in", st);
   h->hd.depth = nullptr; h->hd.depth16 = nullptr;
-  return cape_run(h, nframes);
+  const int rc = cape_run(h, nframes);
+  h->cloud_valid = rc == DRFE_OK;
+  return rc;
 }
 
 int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_t row_stride, size_t frame_stride,
@@ -1872,6 +2042,7 @@ int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_
     h->hd.depth = depth; h->hd.depth_rs = (long long)row_stride; h->hd.depth_fs = (long long)frame_stride;
   } else { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
   h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy; h->hd.depth16 = nullptr;
+  h->cloud_valid = false;
   return cape_run(h, nframes);
 }
 
@@ -1897,6 +2068,7 @@ int drfe_cape_enqueue_depth_u16(drfe_cape* h, int nframes, const uint16_t* depth
   } else { set_error("bad mem_kind"); return DRFE_ERR_ARG; }
   h->hd.depth = nullptr; h->hd.depth_factor = depth_factor;
   h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy;
+  h->cloud_valid = false;
   return cape_run(h, nframes);
 }
 
@@ -1921,6 +2093,7 @@ int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, 
   else { h->hd.depth = h->d_depth; h->hd.depth16 = nullptr; }
   h->hd.depth_rs = W; h->hd.depth_fs = (long long)N;
   h->hd.fx = fx; h->hd.fy = fy; h->hd.cx = cx; h->hd.cy = cy;
+  h->cloud_valid = false;
   DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
   DRFE_CUDA(cudaEventRecord(pp.ev_start, st));
   DRFE_CUDA(cudaStreamWaitEvent(pp.h2d, pp.ev_start, 0));
@@ -1939,7 +2112,7 @@ int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, 
     DRFE_CUDA(cudaEventRecord(pp.ev_in[k], pp.h2d));
     DRFE_CUDA(cudaStreamWaitEvent(st, pp.ev_in[k], 0));
     const int rc = cape_launch(h, f0, n, false);
-    if (rc != DRFE_OK) return rc;
+    if (rc != DRFE_OK) { cudaStreamSynchronize(pp.h2d); cudaStreamSynchronize(st); cudaStreamSynchronize(pp.d2h); return rc; }   // nothing stays queued on the caller's buffers
     DRFE_CUDA(cudaEventRecord(pp.ev_done[k], st));
     DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_done[k], 0));
     DRFE_CUDA(cudaMemcpyAsync(nr_planes + f0, h->hd.nplanes + f0, n * sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
@@ -2041,11 +2214,13 @@ int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, in
   cudaStream_t st = h->stream;
   const int nf = h->last_frames;
   const size_t N = (size_t)h->hd.H * h->hd.W;
+  if (h->pipe.active) { set_error("drfe_cape_plane_points: a batch call is in flight (drfe_cape_finish_batch first)"); return DRFE_ERR_STATE; }
+  { const int rc = cape_materialize_cloud(h); if (rc != DRFE_OK) return rc; }
   if (!h->d_plane_pts) {
     if (cape_alloc(h, &h->d_plane_pts, (size_t)h->max_batch * N * 3)) return DRFE_ERR_CUDA;
     if (cape_alloc(h, &h->d_plane_offs, (size_t)h->max_batch * (kMaxPlanes + 1))) return DRFE_ERR_CUDA;
     h->h_plane_offs.resize((size_t)h->max_batch * (kMaxPlanes + 1));
-    DRFE_CUDA(cudaFuncSetAttribute(k_cape_plane_points, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtsWarps * (kMaxPlanes + 1) * (int)sizeof(int)));
+    DRFE_CUDA(raise_dyn_smem(k_cape_plane_points, h->device, (size_t)(kPtsWarps * (kMaxPlanes + 1) * (int)sizeof(int))));
   }
   auto magic = [](unsigned d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };
   DRFE_LAUNCH(k_cape_plane_points, nf, kPtsWarps * 32, kPtsWarps * (kMaxPlanes + 1) * sizeof(int), st, h->dd, 0, h->d_plane_pts, h->d_plane_offs,
@@ -2100,6 +2275,8 @@ int drfe_cape_get_cloud(drfe_cape* h, int frame, float* cloud) {
   if (rc) return rc;
   DeviceScope ds(h->device);
   const size_t N3 = (size_t)3 * h->hd.H * h->hd.W;
+  rc = cape_materialize_cloud(h);
+  if (rc) return rc;
   DRFE_CUDA(cudaStreamSynchronize(h->stream));
   DRFE_CUDA(cudaMemcpy(cloud, h->hd.cloud + N3 * frame, N3 * sizeof(float), cudaMemcpyDeviceToHost));
   return DRFE_OK;

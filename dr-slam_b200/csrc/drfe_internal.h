@@ -38,6 +38,14 @@ extern std::atomic<long long> g_launches;      // counted by DRFE_LAUNCH
     }                                                                                     \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (kernel, device), not to a handle, and the last setter
+// wins: two live handles of different geometry would shrink each other's limit.  raise_dyn_smem keeps a
+// process-wide high-water mark per (kernel, device) under a mutex and only ever raises the attribute.  The
+// current device must be `device`.
+cudaError_t raise_dyn_smem_impl(const void* func, int device, size_t bytes);
+template <typename K>
+inline cudaError_t raise_dyn_smem(K* kernel, int device, size_t bytes) { return raise_dyn_smem_impl((const void*)kernel, device, bytes); }
+
 // RAII "make this device current for the scope" (handles are callable from any thread)
 struct DeviceScope {
   int prev = -1;

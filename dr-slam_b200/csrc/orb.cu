@@ -33,9 +33,6 @@ static const int kXOff = 32;     // byte offset of ROI column 0 inside a bordere
 static const int kHalfPatch = 15;
 
 __constant__ int c_umax[16];
-// the rBRIEF pattern as floats (x0,y0,x1,y1) per test, entry t*32 + j = test t of descriptor byte j: lane j's t-th
-// load is one coalesced 16-byte word per lane, served by L1 (4 KB, shared by every warp of the SM)
-__device__ float4 g_pattern_f4[256];
 static const int8_t h_pattern[1024] = {
 #include "../../include/drfe_orb_pattern.inc"
 };
@@ -649,8 +646,17 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (surv) {
           const int k = __ffs(surv) - 1, slot = base + __popc(bal & lt_mask);
-          if (slot < list_cap) list[slot] = (uint32_t)(4 * g + k) | ((uint32_t)ry << 12) | (((c0 >> (8 * k)) & 0xFFu) << 24);
-          else atomicOr(P.status, 1);
+          const uint32_t sc = (c0 >> (8 * k)) & 0xFFu;
+          if (slot < list_cap) list[slot] = (uint32_t)(4 * g + k) | ((uint32_t)ry << 12) | (sc << 24);
+          else {
+            // the shared list holds one maximum per 8 px; denser strips (strict 3x3 maxima can reach one per 4 px) put the
+            // rest straight into the level's arena, which is sized for the densest possible image
+            const int pos = atomicAdd(P.cand_cnt + f * P.nlevels + strip.level, 1);
+            if (pos < L.cand_cap)
+              (P.cand + (long long)f * P.cand_fstride + L.cand_off)[pos] =
+                  (uint32_t)(4 * g + k + 3 + strip.x0) | ((uint32_t)(ry + strip.y0 - kEdge + 3) << 12) | ((sc + P.min_th - 1) << 24);
+            else atomicOr(P.status, 1);
+          }
           surv &= surv - 1u;
         }
         bal = __ballot_sync(0xFFFFFFFFu, surv != 0);
@@ -1057,10 +1063,39 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-static const int kDescWarps = 8;
-static const int kPatchRows = 2 * kEdge + 1, kPatchW4 = 11;   // 39 rows x 44 bytes (39 columns + alignment slack)
-__global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDev* __restrict__ Pp, int f0) {
-  __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchW4];
+// A warp owns kOdG consecutive keypoints of one (frame, level) and runs three phases, so that the scalar parts of
+// the work are spread over the lanes instead of being paid once per keypoint by a whole warp, and so that every
+// global access is a coalesced asynchronous copy (the kernel is bound by L1 wavefronts, not by issue slots: with one
+// lane per image row in the loads, 9 loads touched 279 lines per keypoint and the L1 ran at 95 %):
+//   1. IC_Angle moments, one keypoint at a time.  The 31 x 36-byte window of the level image (aligned words around the
+//      radius-15 disc) is staged in shared memory by 4-byte cp.async, consecutive lanes = consecutive words, three
+//      keypoints ahead; then lane l = disc row v = l - 15 reads its 9 words (pitch 9 words: conflict-free), realigns
+//      them by funnel shifts, masks the bytes outside the disc (|u| <= umax[|v|]) and gets sum(u * I) and sum(I) as
+//      8 + 8 four-way dot products (IDP.4A) instead of 31 byte loads and multiplies; m01 = v * sum(I).  Lane k keeps
+//      the reduced moments of keypoint k.
+//   2. every lane finishes its own keypoint in parallel: fastAtan2, the correctly rounded sine / cosine (double),
+//      the cv::KeyPoint record.  (A warp per keypoint spent a quarter of its instructions here with one lane active.)
+//   3. rBRIEF, one keypoint at a time: 39 rows x 64 bytes of the blurred level (|rotated pattern coordinate| <= 18
+//      < EDGE_THRESHOLD, plus the slack of a 16-byte aligned start) are staged by 16-byte cp.async into a two-slot ring,
+//      keypoint k+1's copy in flight while keypoint k's 512 steered samples are gathered; lane j computes descriptor
+//      byte j, its 8 tests' pattern points live in 8 registers as packed signed bytes.
+static const int kOdWarps = 4, kOdG = 16;
+static const int kRawRows = 2 * kHalfPatch + 1, kRawW4 = 9, kRawWords = kRawRows * kRawW4, kRawSlots = 4;   // 31 rows x 36 bytes
+static const int kRawIters = (kRawWords + 31) / 32;
+static const int kPatchRows = 2 * kEdge + 1, kPatchPitch = 80, kPatchChunks = kPatchRows * 4;   // 39 rows, 64 bytes used of an 80-byte pitch (bank spread)
+static const int kPatchIters = (kPatchChunks + 31) / 32;
+static const int kOdWarpBytes = 2 * kPatchRows * kPatchPitch;                                    // per warp: the larger of the two rings
+static_assert(kRawSlots * kRawWords * 4 <= kOdWarpBytes, "the raw ring shares the patch ring's memory");
+__device__ uint32_t g_pattern_s8[256];   // entry t * 32 + j = test t of descriptor byte j: x0 | y0 << 8 | x1 << 16 | y1 << 24, signed bytes
+
+__device__ __forceinline__ int dp4a_su(uint32_t w_s8, uint32_t d_u8, int acc) {   // signed weights x unsigned bytes
+  int r;
+  asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(w_s8), "r"(d_u8), "r"(acc));
+  return r;
+}
+
+__global__ void __launch_bounds__(kOdWarps * 32, 8) k_orient_describe(const OrbDev* __restrict__ Pp, int f0) {
+  __shared__ __align__(16) uint8_t s_ring[kOdWarps][kOdWarpBytes];
   const OrbDev& P = *Pp;
   const int level = blockIdx.y, f = blockIdx.z + f0;
   const LevelDev& L = P.lv[level];
@@ -1072,99 +1107,157 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_describe(const OrbDe
     for (int l = 0; l < P.nlevels; ++l) tot += cnts[l];
     P.out_cnt[f] = min(tot, P.kp_cap);
   }
-  if ((int)blockIdx.x * kDescWarps >= nk) return;           // whole CTA idle
-  const int i = blockIdx.x * kDescWarps + wid;
-  if (i >= nk) return;
-  int base = 0;
-  for (int l = 0; l < level; ++l) base += cnts[l];
-  const uint32_t e = P.lkp[(long long)f * P.lkp_fstride + L.kp_off + i];
-  const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;   // cvRound of integral coords
-  // The 39x39 blurred patch around the keypoint (|rotated pattern coordinate| <= 18 < EDGE_THRESHOLD) does not depend
-  // on the angle: it goes to shared memory by 4-byte cp.async (LDGSTS: no registers held, no separate shared store),
-  // issued here so that the copy is in flight while IC_Angle and the angle's sine/cosine are computed.
-  uint32_t* patch = s_patch[wid];
-  const int xb = (cx - kEdge) & ~3, ox = (cx - kEdge) - xb;
-  {
-    const uint8_t* bsrc = P.blur + L.blur_off + (long long)f * L.blur_fstride + (long long)(cy - kEdge) * L.bpitch + xb;
-    const uint32_t pdst = smem_u32(patch);
+  const int k0 = ((int)blockIdx.x * kOdWarps + wid) * kOdG;     // this warp's first keypoint of the level
+  if (k0 >= nk) return;
+  const int ng = min(kOdG, nk - k0);
+  int base = k0;
+  for (int l = 0; l < level; ++l) base += cnts[l];              // output slot of keypoint k0
+  const uint32_t e_mine = lane < ng ? P.lkp[(long long)f * P.lkp_fstride + L.kp_off + k0 + lane] : 0u;   // x | y << 12 | response << 24
+  const uint32_t ring = smem_u32(s_ring[wid]);
+
+  // ---- 1. moments
+  // staging of keypoint k's window into raw slot k & 3: word idx = lane + 32 * it -> row idx / 9, word idx % 9
+  const uint8_t* img = roi_ptr(P, L, f);
+  const int pitch = L.pitch;
+  const int rr0 = lane / kRawW4, rw0 = lane - rr0 * kRawW4;
+  auto stage_raw = [&](int k) {
+    if (k < ng) {
+      const uint32_t e = __shfl_sync(0xFFFFFFFFu, e_mine, k);
+      const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF;
+      const uint8_t* src = img + (long long)(cy - kHalfPatch) * pitch + ((cx - kHalfPatch) & ~3);   // ROI rows are 4-byte aligned at column 0
+      const uint32_t dst = ring + (uint32_t)((k & (kRawSlots - 1)) * kRawWords * 4) + 4u * (uint32_t)lane;
+      int r = rr0, wc = rw0;
 #pragma unroll
-    for (int k = 0; k < (kPatchRows * kPatchW4 + 31) / 32; ++k) {
-      const int idx = lane + 32 * k;
-      if (idx < kPatchRows * kPatchW4) {
-        const int r = idx / kPatchW4, wc = idx - r * kPatchW4;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pdst + 4u * (uint32_t)idx), "l"(bsrc + r * L.bpitch + 4 * wc) : "memory");
+      for (int it = 0; it < kRawIters; ++it) {
+        if (it < kRawIters - 1 || lane + 32 * it < kRawWords)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * (uint32_t)it), "l"(src + r * pitch + 4 * wc) : "memory");
+        r += 3; wc += 32 - 3 * kRawW4;                           // idx += 32 = 3 * 9 + 5
+        if (wc >= kRawW4) { wc -= kRawW4; ++r; }
       }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");        // (an empty group when k >= ng keeps the wait counts uniform)
+  };
+  stage_raw(0); stage_raw(1); stage_raw(2);
+  // byte b of the realigned row is column u = b - 15; bytes outside the disc are masked to 0
+  const int v = lane - kHalfPatch;
+  uint32_t dmask[8];
+  {
+    const int m = lane < kRawRows ? c_umax[abs(v)] : -1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (abs(4 * j + t - kHalfPatch) <= m) w |= 0xFFu << (8 * t);
+      dmask[j] = w;
+    }
+  }
+  int my10 = 0, my01 = 0;
+  for (int k = 0; k < ng; ++k) {
+    stage_raw(k + 3);                                           // slot (k + 3) & 3 was read by keypoint k - 1: every lane is past its reduction
+    asm volatile("cp.async.wait_group 3;" ::: "memory");
+    __syncwarp();
+    const uint32_t e = __shfl_sync(0xFFFFFFFFu, e_mine, k);
+    const int sh = 8 * (((int)(e & 0xFFF) - kHalfPatch) & 3);
+    int su = 0, s1 = 0;
+    if (lane < kRawRows) {
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(s_ring[wid]) + (k & (kRawSlots - 1)) * kRawWords + lane * kRawW4;
+      uint32_t w[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) w[j] = rw[j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t d = __funnelshift_r(w[j], w[j + 1], sh) & dmask[j];
+        const int u0 = 4 * j - kHalfPatch;                      // weights u0 .. u0 + 3 as signed bytes
+        const uint32_t wu = (uint32_t)(u0 & 0xFF) | ((uint32_t)((u0 + 1) & 0xFF) << 8) | ((uint32_t)((u0 + 2) & 0xFF) << 16) | ((uint32_t)((u0 + 3) & 0xFF) << 24);
+        su = dp4a_su(wu, d, su);
+        s1 = (int)__dp4a(d, 0x01010101u, (uint32_t)s1);
+      }
+    }
+    int m10 = su, m01 = v * s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
+      m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+    }
+    if (lane == k) { my10 = m10; my01 = m01; }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");         // (only empty groups are left)
+  __syncwarp();                                                 // the ring changes hands: raw windows -> blurred patches
+
+  // ---- staging of keypoint k's blurred patch into patch slot k & 1: 16-byte chunk idx = lane + 32 * it -> row idx / 4
+  const uint8_t* blur = P.blur + L.blur_off + (long long)f * L.blur_fstride;
+  const int bpitch = L.bpitch;
+  auto stage_patch = [&](int k) {
+    const uint32_t e = __shfl_sync(0xFFFFFFFFu, e_mine, k);
+    const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF;
+    const uint8_t* src = blur + (long long)(cy - kEdge + (lane >> 2)) * bpitch + ((cx - kEdge) & ~15) + 16 * (lane & 3);
+    const uint32_t dst = ring + (uint32_t)((k & 1) * kPatchRows * kPatchPitch) + (uint32_t)((lane >> 2) * kPatchPitch + 16 * (lane & 3));
+#pragma unroll
+    for (int it = 0; it < kPatchIters; ++it) {
+      if (it < kPatchIters - 1 || lane + 32 * it < kPatchChunks)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(8 * it * kPatchPitch)), "l"(src + (long long)(8 * it) * bpitch) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // ---- IC_Angle: moments over the radius-15 disc.  Lane l owns column u = l - 15; the disc is
-  // symmetric (|u| <= umax[|v|] <=> |v| <= umax[|u|]), so the lane's row range is a constant.
-  const uint8_t* img = roi_ptr(P, L, f) + (long long)cy * L.pitch + cx;
-  int m10 = 0, m01 = 0;
-  const int u = lane - kHalfPatch;
-  const int vmax = (lane < 31) ? c_umax[abs(u)] : -1;
-  {
-    int sum = 0;
-    const uint8_t* ip = img + u - kHalfPatch * L.pitch;
-#pragma unroll
-    for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-      if (abs(v) <= vmax) {
-        const int val = *ip;
-        sum += val;
-        m01 += v * val;
-      }
-      ip += L.pitch;
-    }
-    m10 = u * sum;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m10 += __shfl_down_sync(0xFFFFFFFFu, m10, o);
-    m01 += __shfl_down_sync(0xFFFFFFFFu, m01, o);
-  }
-  float angle = 0.f, a = 0.f, b = 0.f;
-  if (lane == 0) {
-    angle = fast_atan2_deg((float)m01, (float)m10);
+  };
+  stage_patch(0);                                               // in flight during phase 2
+
+  // ---- 2. angle, sine / cosine and the keypoint record of this lane's keypoint
+  float a = 0.f, b = 0.f;
+  if (lane < ng) {
+    const float angle = fast_atan2_deg((float)my01, (float)my10);
     const float rad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     double sd, cd;
     sincos((double)rad, &sd, &cd);   // correctly rounded cosf/sinf: double result rounded to float
     a = (float)cd;
     b = (float)sd;
+    const int o = base + lane;
+    if (o < P.kp_cap) {
+      const int cx = e_mine & 0xFFF, cy = (e_mine >> 12) & 0xFFF;   // cvRound of integral coords
+      drfe_keypoint kp;
+      // pt *= mvScaleFactor[level] for level > 0 (ORBextractor.cc:1095-1101)
+      kp.x = level ? __fmul_rn((float)cx, L.scale) : (float)cx;
+      kp.y = level ? __fmul_rn((float)cy, L.scale) : (float)cy;
+      kp.size = L.size;
+      kp.angle = angle;
+      kp.response = (float)(e_mine >> 24);
+      kp.octave = level;
+      kp.class_id = -1;
+      P.out_kp[(long long)f * P.kp_cap + o] = kp;
+    }
   }
-  angle = __shfl_sync(0xFFFFFFFFu, angle, 0);
-  a = __shfl_sync(0xFFFFFFFFu, a, 0);
-  b = __shfl_sync(0xFFFFFFFFu, b, 0);
-  // ---- rBRIEF: lane j computes descriptor byte j (8 tests); the 512 steered samples are shared-memory gathers
-  // from the patch whose asynchronous copy was started before IC_Angle.
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-  const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch) + kEdge * (kPatchW4 * 4) + ox + kEdge;   // patch centre
-  int val = 0;
+  // ---- 3. rBRIEF: lane j computes descriptor byte j (8 tests) of one keypoint at a time
+  uint32_t pat[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 pw = __ldg(&g_pattern_f4[j * 32 + lane]);
-    const float x0 = pw.x, y0 = pw.y, x1 = pw.z, y1 = pw.w;
-    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = pc[r0 * (kPatchW4 * 4) + c0], t1 = pc[r1 * (kPatchW4 * 4) + c1];
-    val |= (t0 < t1) << j;
-  }
-  const int o = base + i;
-  if (o >= P.kp_cap) return;
-  P.out_desc[((long long)f * P.kp_cap + o) * 32 + lane] = (uint8_t)val;
-  if (lane == 0) {
-    drfe_keypoint kp;
-    // pt *= mvScaleFactor[level] for level > 0 (ORBextractor.cc:1095-1101)
-    kp.x = level ? __fmul_rn((float)cx, L.scale) : (float)cx;
-    kp.y = level ? __fmul_rn((float)cy, L.scale) : (float)cy;
-    kp.size = L.size;
-    kp.angle = angle;
-    kp.response = (float)resp;
-    kp.octave = level;
-    kp.class_id = -1;
-    P.out_kp[(long long)f * P.kp_cap + o] = kp;
+  for (int j = 0; j < 8; ++j) pat[j] = g_pattern_s8[j * 32 + lane];
+  for (int k = 0; k < ng; ++k) {
+    if (k + 1 < ng) {
+      stage_patch(k + 1);                                       // slot (k + 1) & 1 was read by keypoint k - 1: all lanes are past it
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t e = __shfl_sync(0xFFFFFFFFu, e_mine, k);
+    const float ak = __shfl_sync(0xFFFFFFFFu, a, k), bk = __shfl_sync(0xFFFFFFFFu, b, k);
+    const int ox = ((int)(e & 0xFFF) - kEdge) & 15;
+    const uint8_t* pc = s_ring[wid] + (k & 1) * kPatchRows * kPatchPitch + kEdge * kPatchPitch + ox + kEdge;   // patch centre
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t pw = pat[j];
+      const float x0 = (float)(signed char)(pw & 0xFF), y0 = (float)(signed char)((pw >> 8) & 0xFF),
+                  x1 = (float)(signed char)((pw >> 16) & 0xFF), y1 = (float)(signed char)(pw >> 24);
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bk), __fmul_rn(y0, ak)));
+      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ak), __fmul_rn(y0, bk)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bk), __fmul_rn(y1, ak)));
+      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ak), __fmul_rn(y1, bk)));
+      const int t0 = pc[r0 * kPatchPitch + c0], t1 = pc[r1 * kPatchPitch + c1];
+      val |= (t0 < t1) << j;
+    }
+    const int o = base + k;
+    if (o < P.kp_cap) P.out_desc[((long long)f * P.kp_cap + o) * 32 + lane] = (uint8_t)val;
+    __syncwarp();                                               // everybody is done with slot k & 1 before it is refilled
   }
 }
 
@@ -1646,6 +1739,7 @@ struct drfe_orb {
   size_t fast_smem = 0, quad_smem = 0, pyr_smem = 0;
   int last_frames = 0;
   bool pending = false;
+  bool post_valid = false;       // drfe_orb_frame_post ran on the batch that is on the device now
   StageTimer timer;
   ChunkPipe pipe;
   PostDev post{};                // buffers of drfe_orb_frame_post, allocated on first use
@@ -1749,9 +1843,22 @@ static int orb_build(drfe_orb* h) {
     if (L.nIni < 1 || L.nIni > 4) { set_error("unsupported aspect ratio (quadtree roots = %d)", L.nIni); return DRFE_ERR_ARG; }
     L.hX = width / L.nIni;
     for (int i = 0; i <= L.nIni; ++i) L.root_x[i] = (int)(L.hX * (float)i);
-    // FAST candidates a level can hold: one per 8 px.  (Measured on the synthetic sequences: at most one per 67 px
-    // on level 0 but one per 20 px on level 7 — the density grows as the level shrinks; NMS bounds it by one per 4.)
-    L.cand_cap = std::min(1 << 17, std::max(1024, (L.regW * L.regH) / 8));
+    // FAST candidates a level can hold: the most that per-cell strict 3x3 non-maximum suppression can leave, i.e.
+    // ceil(w/2) * ceil(h/2) per cell interior of w x h pixels — no image can overflow the arena.  (Measured on the
+    // synthetic sequences: at most one per 67 px on level 0 and one per 20 px on level 7.)
+    {
+      const int iw = L.w - 2 * kEdge, ih = L.h - 2 * kEdge;
+      long long cap = 0;
+      for (int i = 0; i < L.nRows; ++i) {
+        const int hc = std::min((i + 1) * L.hCell, ih) - i * L.hCell;
+        if (hc <= 0) continue;
+        for (int j = 0; j < L.nCols; ++j) {
+          const int wc = std::min((j + 1) * L.wCell, iw) - j * L.wCell;
+          if (wc > 0) cap += (long long)((wc + 1) / 2) * ((hc + 1) / 2);
+        }
+      }
+      L.cand_cap = (int)std::min<long long>(1 << 21, std::max<long long>(1024, cap));
+    }
     L.cand_off = cand_total; cand_total += L.cand_cap;
     L.node_cap = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
     if (L.node_cap > 0x3FFF) { set_error("nfeatures too large"); return DRFE_ERR_ARG; }
@@ -1911,13 +2018,14 @@ static int orb_build(drfe_orb* h) {
   DRFE_CUDA(cudaMemcpy(h->dd, &D, sizeof(D), cudaMemcpyHostToDevice));
   DRFE_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
   {
-    std::vector<float4> pf(256);
-    for (int t = 0; t < 256; ++t)      // test index t = 8*byte + bit -> entry bit*32 + byte
-      pf[(t & 7) * 32 + (t >> 3)] = make_float4((float)h_pattern[4 * t], (float)h_pattern[4 * t + 1], (float)h_pattern[4 * t + 2], (float)h_pattern[4 * t + 3]);
-    DRFE_CUDA(cudaMemcpyToSymbol(g_pattern_f4, pf.data(), sizeof(float4) * 256));
+    std::vector<uint32_t> ps(256);
+    for (int t = 0; t < 256; ++t)
+      ps[(t & 7) * 32 + (t >> 3)] = (uint32_t)(uint8_t)h_pattern[4 * t] | ((uint32_t)(uint8_t)h_pattern[4 * t + 1] << 8) |
+                                    ((uint32_t)(uint8_t)h_pattern[4 * t + 2] << 16) | ((uint32_t)(uint8_t)h_pattern[4 * t + 3] << 24);
+    DRFE_CUDA(cudaMemcpyToSymbol(g_pattern_s8, ps.data(), sizeof(uint32_t) * 256));
   }
-  DRFE_CUDA(cudaFuncSetAttribute(k_fast_strips<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem));
-  DRFE_CUDA(cudaFuncSetAttribute(k_quadtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->quad_smem));
+  DRFE_CUDA(raise_dyn_smem((k_fast_strips<256>), h->device, (size_t)(h->fast_smem)));
+  DRFE_CUDA(raise_dyn_smem((k_quadtree<256>), h->device, (size_t)(h->quad_smem)));
   if (h->timer.create()) return DRFE_ERR_CUDA;
   return DRFE_OK;
 }
@@ -2003,6 +2111,7 @@ int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, in
 // all kernels of frames [f0, f0 + n) on the handle's stream; src/rs/fs address frame 0 of the batch
 static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
   cudaStream_t st = h->stream;
+  h->post_valid = false;         // the keypoints drfe_orb_frame_post worked on are being replaced
   const OrbDev& D = h->hd;
   const int nl = D.nlevels;
   DRFE_LAUNCH(k_zero_counts, (n * nl + 255) / 256, 256, 0, st, h->dd, f0, n);
@@ -2035,7 +2144,7 @@ static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long 
   if (timed) h->timer.mark("quadtree", st);
   DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, n), 256, 0, st, h->dd, f0);
   if (timed) h->timer.mark("blur", st);
-  DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kDescWarps - 1) / kDescWarps, nl, n), kDescWarps * 32, 0, st, h->dd, f0);
+  DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kOdWarps * kOdG - 1) / (kOdWarps * kOdG), nl, n), kOdWarps * 32, 0, st, h->dd, f0);
   if (timed) h->timer.mark("orient_describe", st);
   return DRFE_OK;
 }
@@ -2172,9 +2281,9 @@ int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_pe
 int drfe_orb_extract(drfe_orb* h, const uint8_t* gray, int width, int height, size_t row_stride, drfe_keypoint* kps,
                      uint8_t* desc, int cap, int* n) {
   if (!h) { set_error("drfe_orb_extract: null handle"); return DRFE_ERR_ARG; }
-  if (!gray || width == 0 || height == 0) return DRFE_OK;  // empty image: silent return (ORBextractor.cc:1046)
-  if (width != h->width || height != h->height) { set_error("drfe_orb_extract: image is %dx%d, handle was created for %dx%d", width, height, h->width, h->height); return DRFE_ERR_ARG; }
   if (!n) { set_error("drfe_orb_extract: null count pointer"); return DRFE_ERR_ARG; }
+  if (!gray || width == 0 || height == 0) { *n = 0; return DRFE_OK; }  // empty image: silent return (ORBextractor.cc:1046); the caller's containers stay as they are
+  if (width != h->width || height != h->height) { set_error("drfe_orb_extract: image is %dx%d, handle was created for %dx%d", width, height, h->width, h->height); return DRFE_ERR_ARG; }
   int rc = drfe_orb_enqueue(h, 1, gray, row_stride, row_stride * height, DRFE_MEM_HOST);
   if (rc != DRFE_OK) return rc;
   return drfe_orb_download(h, kps, desc, cap, n);
@@ -2212,7 +2321,7 @@ int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t
     DRFE_CUDA(cudaEventRecord(pp.ev_in[k], pp.h2d));
     DRFE_CUDA(cudaStreamWaitEvent(st, pp.ev_in[k], 0));
     const int rc = orb_launch(h, f0, n, h->d_gray, W, (long long)fbytes, false);
-    if (rc != DRFE_OK) return rc;
+    if (rc != DRFE_OK) { cudaStreamSynchronize(pp.h2d); cudaStreamSynchronize(st); cudaStreamSynchronize(pp.d2h); return rc; }   // nothing stays queued on the caller's buffers
     DRFE_CUDA(cudaEventRecord(pp.ev_done[k], st));
     DRFE_CUDA(cudaStreamWaitEvent(pp.d2h, pp.ev_done[k], 0));
     DRFE_CUDA(cudaMemcpyAsync(counts + f0, h->hd.out_cnt + f0, n * sizeof(int), cudaMemcpyDeviceToHost, pp.d2h));
@@ -2292,6 +2401,7 @@ static int frame_post_run(drfe_orb* h, drfe_keypoint* keys_un, float* u_right, f
   const int nf = h->last_frames, cap = h->hd.kp_cap;
   PostDev& Q = h->post;
   DRFE_LAUNCH(k_frame_post, nf, 256, cap * sizeof(unsigned short), st, h->dd, Q);
+  h->post_valid = true;
   const int wk = std::min(cap, cap_per_frame);
   if (keys_un)
     DRFE_CUDA(cudaMemcpy2DAsync(keys_un, (size_t)cap_per_frame * sizeof(drfe_keypoint), Q.keys_un, (size_t)cap * sizeof(drfe_keypoint),
@@ -2310,10 +2420,11 @@ static int frame_post_run(drfe_orb* h, drfe_keypoint* keys_un, float* u_right, f
 static int frame_post_buffers(drfe_orb* h, const drfe_frame_params* p) {
   const int cap = h->hd.kp_cap, B = h->max_batch;
   PostDev& Q = h->post;
+  if (cap > 65535) { set_error("drfe_orb_frame_post: %d keypoints per frame do not fit the 16-bit grid indices", cap); return DRFE_ERR_CAPACITY; }
   if (!Q.keys_un) {
     if (dev_alloc(h, &Q.keys_un, (size_t)cap * B) || dev_alloc(h, &Q.u_right, (size_t)cap * B) || dev_alloc(h, &Q.kp_depth, (size_t)cap * B) ||
         dev_alloc(h, &Q.grid_count, (size_t)kGridCells * B) || dev_alloc(h, &Q.grid_index, (size_t)cap * B)) return DRFE_ERR_CUDA;
-    DRFE_CUDA(cudaFuncSetAttribute(k_frame_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * sizeof(unsigned short))));
+    DRFE_CUDA(raise_dyn_smem(k_frame_post, h->device, (size_t)((cap * sizeof(unsigned short)))));
   }
   Q.prm = *p;
   Q.depth = nullptr; Q.depth16 = nullptr; Q.depth_factor = 1.f;
@@ -2373,7 +2484,7 @@ int drfe_orb_frame_post_shared_depth(drfe_orb* h, drfe_cape* cape, const drfe_fr
 int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries, const uint8_t* qdesc,
                                   const uint8_t* occupied, int qcap, drfe_proj_match* out) {
   if (!h || !nqueries || !queries || !qdesc || !out || qcap < 1) { set_error("drfe_orb_search_by_projection: bad argument"); return DRFE_ERR_ARG; }
-  if (!h->pending || !h->post.keys_un) { set_error("drfe_orb_search_by_projection: run drfe_orb_frame_post first"); return DRFE_ERR_STATE; }
+  if (!h->pending || !h->post.keys_un || !h->post_valid) { set_error("drfe_orb_search_by_projection: run drfe_orb_frame_post on this batch first"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
   if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
   cudaStream_t st = h->stream;
@@ -2401,7 +2512,7 @@ int drfe_orb_search_local_points(drfe_orb* h, const int* nqueries, const drfe_pr
                                  const uint8_t* occupied, int qcap, float nnratio, drfe_proj_match* out, int32_t* assigned, int32_t* key_point,
                                  int* nmatches) {
   if (!h || !nqueries || !queries || !qdesc || !qflags || qcap < 1) { set_error("drfe_orb_search_local_points: bad argument"); return DRFE_ERR_ARG; }
-  if (!h->pending || !h->post.keys_un) { set_error("drfe_orb_search_local_points: run drfe_orb_frame_post first"); return DRFE_ERR_STATE; }
+  if (!h->pending || !h->post.keys_un || !h->post_valid) { set_error("drfe_orb_search_local_points: run drfe_orb_frame_post on this batch first"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
   if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
   cudaStream_t st = h->stream;
@@ -2427,7 +2538,7 @@ int drfe_orb_search_local_points(drfe_orb* h, const int* nqueries, const drfe_pr
   S.q = (const drfe_proj_query*)(d + o_q); S.qdesc = (const uint8_t*)(d + o_d); S.qflags = (const uint8_t*)(d + o_fl);
   S.occupied = occupied ? (const uint8_t*)(d + o_occ) : nullptr; S.nq = (const int*)(d + o_n); S.out = (drfe_proj_match*)(d + o_out);
   S.assigned = (int32_t*)(d + o_as); S.key_point = (int32_t*)(d + o_kp); S.nmatches = (int*)(d + o_nm); S.qcap = qcap; S.nnratio = nnratio;
-  acc(cudaFuncSetAttribute(k_search_local_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  acc(raise_dyn_smem(k_search_local_points, h->device, (size_t)(smem)));
   if (e == cudaSuccess) {
     k_search_local_points<<<nf, kTrackThreads, smem, st>>>(h->dd, h->post, S);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -2445,7 +2556,7 @@ int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const i
                                const uint8_t* pdesc, const uint8_t* occupied, int pcap, int32_t* match_key, int32_t* match_dist,
                                int32_t* key_point, int* nmatches, int* sweeps) {
   if (!h || !tp || !npoints || !points || !pdesc || pcap < 1) { set_error("drfe_orb_search_last_frame: bad argument"); return DRFE_ERR_ARG; }
-  if (!h->pending || !h->post.keys_un) { set_error("drfe_orb_search_last_frame: run drfe_orb_frame_post first"); return DRFE_ERR_STATE; }
+  if (!h->pending || !h->post.keys_un || !h->post_valid) { set_error("drfe_orb_search_last_frame: run drfe_orb_frame_post on this batch first"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
   if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
   cudaStream_t st = h->stream;
@@ -2466,7 +2577,7 @@ int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const i
     if (dev_alloc(h, &h->d_tpts, (size_t)pcap * B) || dev_alloc(h, &h->d_tdesc, (size_t)pcap * B * 32) || dev_alloc(h, &h->d_tout, (size_t)pcap * B * 2)) return DRFE_ERR_CUDA;
     if (!h->d_ttp && (dev_alloc(h, &h->d_ttp, (size_t)B) || dev_alloc(h, &h->d_tkey, (size_t)cap * B) || dev_alloc(h, &h->d_tcnt, (size_t)B * 3))) return DRFE_ERR_CUDA;
     if (!h->d_socc && (dev_alloc(h, &h->d_socc, (size_t)cap * B) || dev_alloc(h, &h->d_snq, (size_t)B))) return DRFE_ERR_CUDA;
-    DRFE_CUDA(cudaFuncSetAttribute(k_search_last_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DRFE_CUDA(raise_dyn_smem(k_search_last_frame, h->device, (size_t)(smem)));
     h->track_pcap = pcap;
   }
   DRFE_CUDA(cudaMemcpyAsync(h->d_tcnt, npoints, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));

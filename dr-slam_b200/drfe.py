@@ -55,6 +55,11 @@ class FrameParams(C.Structure):
                 ("bf", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
 
+class PoolParams(C.Structure):
+    _fields_ = [("orb", OrbParams), ("cape", CapeParams), ("width", C.c_int32), ("height", C.c_int32),
+                ("max_batch", C.c_int32), ("chunk_frames", C.c_int32)]
+
+
 class DrfeError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("drfe error %d: %s" % (code, msg))
@@ -76,7 +81,9 @@ SYMBOLS = [
     "drfe_cape_enqueue_depth_u16", "drfe_cape_process_depth_batch", "drfe_cape_finish_batch",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
-    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times", "drfe_synth_frame",
+    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
+    "drfe_pool_create", "drfe_pool_destroy", "drfe_pool_num_devices", "drfe_pool_max_keypoints", "drfe_pool_extract_batch",
+    "drfe_pool_device_times", "drfe_host_alloc", "drfe_host_free", "drfe_host_register", "drfe_host_unregister",
 ]
 
 _lib = None
@@ -164,7 +171,17 @@ def lib():
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
     L.drfe_cape_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
-    L.drfe_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_float, vp, vp, vp, vp, vp, vp]
+    L.drfe_pool_create.argtypes = [C.POINTER(PoolParams), vp, C.c_int, C.POINTER(vp)]
+    L.drfe_pool_destroy.argtypes = [vp]
+    L.drfe_pool_num_devices.argtypes = [vp]
+    L.drfe_pool_max_keypoints.argtypes = [vp]
+    L.drfe_pool_extract_batch.argtypes = [vp, C.c_int, vp, sz, sz, vp, C.c_int, C.c_float, sz, sz, C.c_float, C.c_float, C.c_float, C.c_float,
+                                          vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp]
+    L.drfe_pool_device_times.argtypes = [vp, vp, C.c_int]
+    L.drfe_host_alloc.argtypes = [C.POINTER(vp), sz, C.c_int]
+    L.drfe_host_free.argtypes = [vp]
+    L.drfe_host_register.argtypes = [vp, sz]
+    L.drfe_host_unregister.argtypes = [vp]
     _lib = L
     return L
 
@@ -193,13 +210,19 @@ def kernel_launch_count():
 
 
 def synth_frame(width=640, height=480, scene=0, seed=20260000, depth_unit_scale=1.0):
-    """Deterministic procedural RGB-D frame -> (gray u8 HxW, depth f32 HxW, (fx, fy, cx, cy))."""
-    gray = np.empty((height, width), np.uint8)
-    depth = np.empty((height, width), np.float32)
-    K = [C.c_float() for _ in range(4)]
-    _check(lib().drfe_synth_frame(width, height, scene, seed, depth_unit_scale, _ptr(gray), _ptr(depth),
-                                  *[C.cast(C.byref(k), C.c_void_p) for k in K]))
-    return gray, depth, tuple(k.value for k in K)
+    """The tests' synthetic RGB-D frame.  The generator is not part of the product library: it lives in
+    tools/synth (libdrfe_synth.so); this wrapper only keeps the tests' call sites short."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "drfe_synth", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "synth", "synth.py"))
+    global _synth_mod
+    if _synth_mod is None:
+        _synth_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_synth_mod)
+    return _synth_mod.synth_frame(width, height, scene, seed, depth_unit_scale)
+
+
+_synth_mod = None
 
 
 class Event:
@@ -233,6 +256,71 @@ def _stage_times(fn, h):
     n = C.c_int32(0)
     _check(fn(h, C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), 16, C.byref(n)))
     return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+
+def host_array(shape, dtype, write_combined=False):
+    """numpy array over pinned host memory from drfe_host_alloc (kept alive by the array's base object)"""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(lib().drfe_host_alloc(C.byref(p), max(n, 1), int(write_combined)))
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().drfe_host_free(self.ptr)
+            except Exception:
+                pass
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    buf._owner = _Owner(p)
+    return np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+
+
+class Pool:
+    """drfe_pool: one batch of host frames sharded over several devices (contiguous blocks), results by frame index."""
+
+    def __init__(self, devices, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, width=640, height=480,
+                 cell=20, cylinder_detection=False, min_cos=0.97814, max_merge_dist=900.0, max_batch=256, chunk_frames=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.width, self.height, self.max_batch = width, height, max_batch
+        prm = PoolParams(OrbParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST),
+                         CapeParams(height, width, cell, cell, int(cylinder_detection), min_cos, max_merge_dist), width, height, max_batch, chunk_frames)
+        dev = np.ascontiguousarray(devices, np.int32)
+        _check(self.L.drfe_pool_create(C.byref(prm), _ptr(dev), len(dev), C.byref(self.h)))
+        self.cap = self.L.drfe_pool_max_keypoints(self.h)
+        self.ndev = self.L.drfe_pool_num_devices(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drfe_pool_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def extract_batch(self, gray, depth, fx, fy, cx, cy, depth_factor=1.0, out=None, plane_cap=64):
+        """gray (B,H,W) u8, depth (B,H,W) f32 or u16 (host) -> dict of per-frame results (out: preallocated dict to reuse)"""
+        assert gray.dtype == np.uint8 and gray.ndim == 3 and gray.strides[2] == 1
+        assert depth.dtype in (np.float32, np.uint16) and depth.shape == gray.shape and depth.strides[2] == depth.itemsize
+        nf = gray.shape[0]
+        if out is None:
+            out = {"kps": np.empty((nf, self.cap), KP_DTYPE), "desc": np.empty((nf, self.cap, 32), np.uint8), "counts": np.empty(nf, np.int32),
+                   "seg": np.empty((nf, self.height, self.width), np.uint8), "planes": np.empty((nf, plane_cap), PLANE_DTYPE),
+                   "nplanes": np.empty(nf, np.int32)}
+        es = depth.itemsize
+        _check(self.L.drfe_pool_extract_batch(self.h, nf, _ptr(gray), gray.strides[1], gray.strides[0], _ptr(depth), int(depth.dtype == np.uint16),
+                                              depth_factor, depth.strides[1] // es, depth.strides[0] // es, fx, fy, cx, cy,
+                                              _ptr(out["kps"]), _ptr(out["desc"]), out["kps"].shape[1], _ptr(out["counts"]), _ptr(out["seg"]),
+                                              _ptr(out["planes"]), out["planes"].shape[1], _ptr(out["nplanes"]), None, 0, None))
+        return out
+
+    def device_times(self):
+        ms = np.zeros(self.ndev, np.float32)
+        _check(self.L.drfe_pool_device_times(self.h, _ptr(ms), self.ndev))
+        return ms
 
 
 class Vocabulary:
@@ -547,7 +635,7 @@ class ORBextractor:
         return out
 
     def candidates(self, frame, level):
-        cap = 1 << 16
+        cap = 1 << 19
         buf = np.empty((cap, 3), np.float32)
         n = C.c_int32(0)
         _check(self.L.drfe_orb_get_candidates(self.h, frame, level, _ptr(buf), cap, C.byref(n)))
@@ -616,11 +704,11 @@ class CAPE:
                                               C.byref(ncyl)))
         return npl.value, ncyl.value, seg, planes[:npl.value].copy(), cyls[:self.cylinders_found()[0]].copy()
 
-    def plane_points(self, nframes=None, plane_cap=255):
+    def plane_points(self, nframes=None, plane_cap=255, cap_per_frame=None):
         """plane_cloud of PlaneDetection_CAPE::runPlaneDetection (PlaneExtractor.cpp:165-190) for the frames of the
         last call: a list (per frame) of lists (per plane) of (n, 3) float32 arrays, pixels in row-major order."""
         nf = nframes or max(getattr(self, "_nframes", 1) or 1, 1)
-        N = self.H * self.W
+        N = cap_per_frame or self.H * self.W
         pts = np.zeros((nf, N, 3), np.float32)
         offs = np.zeros((nf, plane_cap + 1), np.int32)
         _check(self.L.drfe_cape_plane_points(self.h, _ptr(pts), N, _ptr(offs), plane_cap))

@@ -153,6 +153,10 @@ class PlaneDetection_CAPE {
     const int rows = depth_img.rows, cols = depth_img.cols;
     seg_output.create(rows, cols);
     seg_output.setTo(0);
+    // CAPE::process appends (CAPE.cpp:279) and the reference uses one PlaneDetection_CAPE per Frame; this object may
+    // be run again, so its results start empty: plane_params[i], plane_cloud[i] and label i + 1 of seg_output line up
+    plane_params.clear();
+    cylinder_params.clear();
     if (!plane_detector || rows != det_rows_ || cols != det_cols_) {   // the reference news one per frame and leaks it (:149)
       delete plane_detector;
       plane_detector = new CAPE(rows, cols, PATCH_SIZE, PATCH_SIZE, cylinder_detection, COS_ANGLE_MAX, MAX_MERGE_DIST);

@@ -12,6 +12,7 @@
 #include "CAPE.h"
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include "drfe_synth.h"   // tools/synth: the tests' input generator, compiled into this example, not part of libdrfe
 
 static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
   const uint8_t* b = (const uint8_t*)p;
@@ -26,7 +27,7 @@ int main(int argc, char** argv) {
   std::vector<uint8_t> gray((size_t)W * H);
   std::vector<float> depth((size_t)W * H);
   float fx, fy, cx, cy;
-  if (drfe_synth_frame(W, H, scene, seed, 1.0f, gray.data(), depth.data(), &fx, &fy, &cx, &cy) != DRFE_OK) return 2;
+  if (drfe_synth_frame(W, H, scene, seed, 1.0f, gray.data(), depth.data(), &fx, &fy, &cx, &cy) != 0) return 2;
 
   try {
     Planar_SLAM::ORBextractor orb(1000, 1.2f, 8, 20, 7);          // Tracking.cc:120-126

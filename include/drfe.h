@@ -434,12 +434,43 @@ int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16);
 int drfe_cape_set_profiling(drfe_cape* h, int on);
 int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages);
 
-/* ------------------------------------------------------------------ synthetic input
- * Deterministic procedural RGB-D frame (textured Manhattan corridor / room) used by the
- * tests and bench: gray u8 (w*h) and depth f32 metres (w*h), seed selects the camera pose.
- * Host-only helper, no GPU involved.  scene: 0 = corridor, 1 = room, 2 = room + pillars. */
-int drfe_synth_frame(int width, int height, int scene, uint32_t seed, float depth_unit_scale,
-                     uint8_t* gray, float* depth, float* fx, float* fy, float* cx, float* cy);
+/* ------------------------------------------------------------------ several devices
+ * Frames are independent (ORBextractor keeps no state across frames, Frame.cc:124-134 builds a fresh
+ * PlaneDetection per frame), so a pool cuts a batch of host frames into contiguous blocks, one per device; every
+ * device has its own ORB + CAPE handle pair, its own streams and staging arenas, and its own persistent host thread
+ * that drives the chunk-pipelined batch calls; results land in the caller's arrays BY FRAME INDEX.  No collective
+ * and no peer traffic.  The same device may be listed more than once (two workers sharing a GPU).
+ * What a caller with G GPUs replaces: the per-frame std::thread pair of Frame::Frame (Frame.cc:124-134) run over a
+ * recorded sequence (Examples/RGB-D/rgbd_tum.cc:76-115 feeds frames one by one). */
+typedef struct drfe_pool drfe_pool;
+typedef struct drfe_pool_params {
+  drfe_orb_params orb;
+  drfe_cape_params cape;       /* depth_width / depth_height are taken from width / height below */
+  int32_t width, height;       /* image size, the same for gray and depth */
+  int32_t max_batch;           /* most frames one drfe_pool_extract_batch call may carry, over all devices */
+  int32_t chunk_frames;        /* frames per pipelined chunk on a device, 0 = library default */
+} drfe_pool_params;
+int drfe_pool_create(const drfe_pool_params* params, const int* devices, int ndevices, drfe_pool** out);
+int drfe_pool_destroy(drfe_pool* p);
+int drfe_pool_num_devices(const drfe_pool* p);
+int drfe_pool_max_keypoints(const drfe_pool* p);     /* = drfe_orb_max_keypoints of every device's handle */
+/* One batch, host in / host out; arguments as drfe_orb_extract_batch + drfe_cape_process_depth_batch, every array
+ * indexed by frame (kps [nframes][cap_per_frame], desc [nframes][cap_per_frame][32], seg_out [nframes][H][W],
+ * planes [nframes][plane_cap], cylinders [nframes][cyl_cap]; any output except counts / nr_planes may be null).
+ * Returns when every device has delivered its block; the first failing device's status and text otherwise. */
+int drfe_pool_extract_batch(drfe_pool* p, int nframes, const uint8_t* gray, size_t gray_row_stride, size_t gray_frame_stride,
+                            const void* depth, int depth_is_u16, float depth_factor, size_t depth_row_stride,
+                            size_t depth_frame_stride, float fx, float fy, float cx, float cy, drfe_keypoint* kps, uint8_t* desc,
+                            int cap_per_frame, int* counts, uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
+                            drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders);
+/* device time (CUDA events, first H2D to last D2H) each device spent on its block of the last batch */
+int drfe_pool_device_times(const drfe_pool* p, float* ms, int cap);
+/* Pinned host memory for the batch calls (pageable buffers make every copy synchronous): allocate, or register a
+ * buffer the application already owns (e.g. the cv::Mat data of a recorded sequence). */
+int drfe_host_alloc(void** ptr, size_t bytes, int write_combined);
+int drfe_host_free(void* ptr);
+int drfe_host_register(void* ptr, size_t bytes);
+int drfe_host_unregister(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 // Deterministic procedural RGB-D frames for tests and bench: a textured
 // Manhattan corridor / room seen by a pinhole camera, gray u8 + depth f32.
-// Host-only helper exported through the C ABI (drfe_synth_frame); no GPU, no libm
+// Test / bench INPUT GENERATOR, not part of the product: built as tools/synth/libdrfe_synth.so (plain g++),
+// declared in tools/synth/drfe_synth.h, loaded by tools/synth/synth.py.  Host only; no GPU, no libm
 // transcendental calls (only + - * / sqrt floor) and built with -ffp-contract=off so the
 // same seed gives the same bytes on any x86-64 host.
 #include <cmath>
@@ -8,7 +9,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../include/drfe.h"
+#include "drfe_synth.h"
 
 namespace {
 
@@ -135,10 +136,13 @@ bool hit_pillar(const Pillar& c, V3 o, V3 d, float floor_y, Hit& h) {
 extern "C" int drfe_synth_frame(int width, int height, int scene, uint32_t seed,
                                 float depth_unit_scale, uint8_t* gray, float* depth, float* fx,
                                 float* fy, float* cx, float* cy) {
-  if (width < 32 || height < 32 || !gray || !depth) return DRFE_ERR_ARG;
+  if (width < 32 || height < 32 || !gray || !depth) return -1;
   const float f = 525.0f * (float)width / 640.0f;
   const float pcx = ((float)width - 1.f) * 0.5f, pcy = ((float)height - 1.f) * 0.5f;
-  if (fx) *fx = f; if (fy) *fy = f; if (cx) *cx = pcx; if (cy) *cy = pcy;
+  if (fx) *fx = f;
+  if (fy) *fy = f;
+  if (cx) *cx = pcx;
+  if (cy) *cy = pcy;
 
   // ---- scene
   std::vector<Box> boxes;
@@ -216,5 +220,5 @@ extern "C" int drfe_synth_frame(int width, int height, int scene, uint32_t seed,
       float r = std::floor(val + 0.5f);
       gray[(size_t)v * width + u] = (uint8_t)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
     }
-  return DRFE_OK;
+  return 0;
 }
