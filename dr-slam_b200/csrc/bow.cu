@@ -373,6 +373,7 @@ int drfe_vocab_create(int k, int L, int scoring, int weighting, int nnodes, cons
 
 int drfe_orb_compute_bow(drfe_orb* h, const drfe_vocab* vc, int levelsup, int32_t* word_id, int32_t* node_id, int* bow_n,
                          int32_t* bow_word, double* bow_value, int* fv_n, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat) {
+  NvtxRange nvtx_("drfe_orb_compute_bow");
   drfe_vocab* v = const_cast<drfe_vocab*>(vc);
   OrbBatchView B;
   if (!v || orb_batch_view(h, &B)) { set_error("drfe_orb_compute_bow: null argument"); return DRFE_ERR_ARG; }
@@ -421,6 +422,7 @@ int drfe_orb_search_by_bow(drfe_orb* h, int kcap, const int* kf_n, const uint8_t
                            const int* kf_fv_n, const int32_t* kf_fv_node, const int32_t* kf_fv_start, const int32_t* kf_fv_feat,
                            const int* f_fv_n, const int32_t* f_fv_node, const int32_t* f_fv_start, const int32_t* f_fv_feat, float nnratio,
                            int check_orientation, int32_t* kf_match, int32_t* f_match, int* nmatches) {
+  NvtxRange nvtx_("drfe_orb_search_by_bow");
   OrbBatchView B;
   if (orb_batch_view(h, &B) || kcap < 1 || !kf_n || !kf_desc || !kf_angle || !kf_valid || !kf_fv_n || !kf_fv_node || !kf_fv_start ||
       !kf_fv_feat || !f_fv_n || !f_fv_node || !f_fv_start || !f_fv_feat) {

@@ -1469,7 +1469,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 // MODE as in k_cape_sums: with a depth image the points of a border cell are converted again here (the same
 // arithmetic, hence the same bits) instead of being read back from a cloud that k_cape_sums no longer writes.
 template <bool CYL, int MODE>
-__global__ void __launch_bounds__(256, 3) k_cape_refine(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+__global__ void __launch_bounds__(256, 2) k_cape_refine(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   const CapeDev& P = *Pp;
   const int gw0 = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw0 >= nframes * P.ncells) return;
@@ -1559,8 +1559,25 @@ __global__ void __launch_bounds__(256, 3) k_cape_refine(const CapeDev* __restric
 #pragma unroll
       for (int a = 0; a < kAhead; ++a) { const int j = lane + 32 * a; zq[a] = j < nq ? load_depth(j) : make_float4(0.f, 0.f, 0.f, 0.f); }
     }
-    const double rfx = C.rfx, rfy = C.rfy;
-    (void)rfx; (void)rfy;
+    // the cell's first kLocal planes (ascending plane number; a border cell rarely sees more than two) come into
+    // registers with independent loads before the pixel loop; whatever is left stays in `bits` for the generic loop
+    constexpr int kLocal = 4;
+    float4 peq[kLocal];
+    float pmd[kLocal];
+    int pid[kLocal], nloc = 0;
+    uint32_t any_rest = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      while (bits[k] && nloc < kLocal) {
+        const int p = k * 32 + __ffs(bits[k]);
+        bits[k] &= bits[k] - 1;
+#pragma unroll
+        for (int i = 0; i < kLocal; ++i)
+          if (i == nloc) { pid[i] = p; peq[i] = eq[p]; pmd[i] = maxd[p]; }
+        ++nloc;
+      }
+      any_rest |= bits[k];
+    }
 #pragma unroll 1
     for (int j0 = lane; j0 < nq; j0 += 32 * kAhead) {
 #pragma unroll
@@ -1585,18 +1602,32 @@ __global__ void __launch_bounds__(256, 3) k_cape_refine(const CapeDev* __restric
 #pragma unroll
       for (int u = 0; u < 4; ++u) best[u] = __uint_as_float(0x64646464u);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        uint32_t b = bits[k];
-        while (b) {
-          const int p = k * 32 + __ffs(b);
-          b &= b - 1;
-          const float4 e = eq[p];
-          const float md = maxd[p];
+      for (int i = 0; i < kLocal; ++i) {
+        if (i < nloc) {
+          const float4 e = peq[i];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float v = xs[u] * e.x + ys[u] * e.y + zs[u] * e.z + e.w;
             const float dist = v * v;
-            if (dist < md && dist < best[u]) { best[u] = dist; lab = (lab & ~(0xFFu << (8 * u))) | ((uint32_t)p << (8 * u)); }
+            if (dist < pmd[i] && dist < best[u]) { best[u] = dist; lab = (lab & ~(0xFFu << (8 * u))) | ((uint32_t)pid[i] << (8 * u)); }
+          }
+        }
+      }
+      if (any_rest) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint32_t b = bits[k];
+          while (b) {
+            const int p = k * 32 + __ffs(b);
+            b &= b - 1;
+            const float4 e = eq[p];
+            const float md = maxd[p];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float v = xs[u] * e.x + ys[u] * e.y + zs[u] * e.z + e.w;
+              const float dist = v * v;
+              if (dist < md && dist < best[u]) { best[u] = dist; lab = (lab & ~(0xFFu << (8 * u))) | ((uint32_t)p << (8 * u)); }
+            }
           }
         }
       }
@@ -1931,6 +1962,7 @@ int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, 
 
 // all kernels of frames [f0, f0 + n) on the handle's stream (the device descriptor must be current)
 static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
+  NvtxRange nvtx_("cape_launch");
   cudaStream_t st = h->stream;
   const int ncell_total = n * h->hd.ncells;
   const size_t sums_smem = (size_t)(kSumsThreads / 16) * 2 * h->hd.npc * sizeof(float);
@@ -1999,6 +2031,7 @@ static int cape_run(drfe_cape* h, int nframes) {
 }
 
 int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_t frame_stride, int mem_kind) {
+  NvtxRange nvtx_("drfe_cape_enqueue_cloud");
   if (!h || !cloud) { set_error("drfe_cape_enqueue_cloud: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_enqueue_cloud: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   const size_t N3 = (size_t)3 * h->hd.H * h->hd.W;
@@ -2022,6 +2055,7 @@ int drfe_cape_enqueue_cloud(drfe_cape* h, int nframes, const float* cloud, size_
 
 int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_t row_stride, size_t frame_stride,
                             int mem_kind, float fx, float fy, float cx, float cy) {
+  NvtxRange nvtx_("drfe_cape_enqueue_depth");
   if (!h || !depth) { set_error("drfe_cape_enqueue_depth: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_enqueue_depth: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   const int W = h->hd.W, H = h->hd.H;
@@ -2049,6 +2083,7 @@ int drfe_cape_enqueue_depth(drfe_cape* h, int nframes, const float* depth, size_
 
 int drfe_cape_enqueue_depth_u16(drfe_cape* h, int nframes, const uint16_t* depth, size_t row_stride, size_t frame_stride,
                                 int mem_kind, float depth_factor, float fx, float fy, float cx, float cy) {
+  NvtxRange nvtx_("drfe_cape_enqueue_depth_u16");
   if (!h || !depth) { set_error("drfe_cape_enqueue_depth_u16: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_enqueue_depth_u16: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   const int W = h->hd.W, H = h->hd.H;
@@ -2076,6 +2111,7 @@ int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, 
                                   size_t row_stride, size_t frame_stride, float fx, float fy, float cx, float cy,
                                   uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
                                   drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders, int chunk_frames) {
+  NvtxRange nvtx_("drfe_cape_process_depth_batch");
   if (!h || !depth || !nr_planes) { set_error("drfe_cape_process_depth_batch: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_cape_process_depth_batch: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   const int W = h->hd.W, H = h->hd.H;
@@ -2139,6 +2175,7 @@ int drfe_cape_process_depth_batch(drfe_cape* h, int nframes, const void* depth, 
 }
 
 int drfe_cape_finish_batch(drfe_cape* h) {
+  NvtxRange nvtx_("drfe_cape_finish_batch");
   if (!h) { set_error("drfe_cape_finish_batch: null handle"); return DRFE_ERR_ARG; }
   if (!h->pipe.active) { set_error("drfe_cape_finish_batch: no batch in flight"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -2169,6 +2206,7 @@ int drfe_cape_sync(drfe_cape* h) {
 
 int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int plane_cap, int* nr_planes,
                        drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders) {
+  NvtxRange nvtx_("drfe_cape_download");
   if (!h || !nr_planes) { set_error("drfe_cape_download: null argument"); return DRFE_ERR_ARG; }
   if (!h->pending) { set_error("drfe_cape_download: nothing enqueued"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -2207,6 +2245,7 @@ int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int p
 }
 
 int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
+  NvtxRange nvtx_("drfe_cape_plane_points");
   if (!h || !points || !offsets || plane_cap < 1) { set_error("drfe_cape_plane_points: bad argument"); return DRFE_ERR_ARG; }
   if (!h->pending) { set_error("drfe_cape_plane_points: nothing enqueued"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);

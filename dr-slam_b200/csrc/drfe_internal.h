@@ -1,6 +1,7 @@
 // Internal helpers shared by the drfe CUDA translation units (not installed).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only (the tools inject the implementation); a no-op without a profiler attached
 
 #include <atomic>
 #include <cstdarg>
@@ -45,6 +46,15 @@ extern std::atomic<long long> g_launches;      // counted by DRFE_LAUNCH
 cudaError_t raise_dyn_smem_impl(const void* func, int device, size_t bytes);
 template <typename K>
 inline cudaError_t raise_dyn_smem(K* kernel, int device, size_t bytes) { return raise_dyn_smem_impl((const void*)kernel, device, bytes); }
+
+// NVTX range for the scope: host-side spans of the entry points and of every stage's launches, so that an Nsight Systems
+// timeline of an application shows which drfe call / stage a kernel belongs to
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // RAII "make this device current for the scope" (handles are callable from any thread)
 struct DeviceScope {

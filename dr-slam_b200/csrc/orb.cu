@@ -1078,7 +1078,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 //   3. rBRIEF, one keypoint at a time: 39 rows x 64 bytes of the blurred level (|rotated pattern coordinate| <= 18
 //      < EDGE_THRESHOLD, plus the slack of a 16-byte aligned start) are staged by 16-byte cp.async into a two-slot ring,
 //      keypoint k+1's copy in flight while keypoint k's 512 steered samples are gathered; lane j computes descriptor
-//      byte j, its 8 tests' pattern points live in 8 registers as packed signed bytes.
+//      byte j, its 8 tests' pattern points live in 8 registers as packed bytes; no I2F / F2I anywhere (see below).
 static const int kOdWarps = 4, kOdG = 16;
 static const int kRawRows = 2 * kHalfPatch + 1, kRawW4 = 9, kRawWords = kRawRows * kRawW4, kRawSlots = 4;   // 31 rows x 36 bytes
 static const int kRawIters = (kRawWords + 31) / 32;
@@ -1086,7 +1086,7 @@ static const int kPatchRows = 2 * kEdge + 1, kPatchPitch = 80, kPatchChunks = kP
 static const int kPatchIters = (kPatchChunks + 31) / 32;
 static const int kOdWarpBytes = 2 * kPatchRows * kPatchPitch;                                    // per warp: the larger of the two rings
 static_assert(kRawSlots * kRawWords * 4 <= kOdWarpBytes, "the raw ring shares the patch ring's memory");
-__device__ uint32_t g_pattern_s8[256];   // entry t * 32 + j = test t of descriptor byte j: x0 | y0 << 8 | x1 << 16 | y1 << 24, signed bytes
+__device__ uint32_t g_pattern_s8[256];   // entry t * 32 + j = test t of descriptor byte j: x0 | y0 << 8 | x1 << 16 | y1 << 24, each coordinate + 32 as a byte
 
 __device__ __forceinline__ int dp4a_su(uint32_t w_s8, uint32_t d_u8, int acc) {   // signed weights x unsigned bytes
   int r;
@@ -1241,19 +1241,30 @@ __global__ void __launch_bounds__(kOdWarps * 32, 8) k_orient_describe(const OrbD
     const uint32_t e = __shfl_sync(0xFFFFFFFFu, e_mine, k);
     const float ak = __shfl_sync(0xFFFFFFFFu, a, k), bk = __shfl_sync(0xFFFFFFFFu, b, k);
     const int ox = ((int)(e & 0xFFF) - kEdge) & 15;
-    const uint8_t* pc = s_ring[wid] + (k & 1) * kPatchRows * kPatchPitch + kEdge * kPatchPitch + ox + kEdge;   // patch centre
+    // No conversion instructions (I2F / F2I run on the quarter-rate XU pipe, which was 77 % busy and bound the kernel):
+    //  * a pattern coordinate v is stored as the byte v + 32; PRMT puts it under the exponent of 2^23 (0x4B000000 | byte
+    //    = 8388608 + byte as a float) and one exact subtraction leaves float(v);
+    //  * cvRound of a steered coordinate t is t + 1.5 * 2^23 (the sum is rounded to an integer, half to even, like
+    //    cvRound), whose bit pattern is 0x4B400000 + round(t): the row * pitch + column of the sample is computed
+    //    straight from the two bit patterns in wrapping 32-bit arithmetic, the constants folded into `corner`.
+    const uint32_t corner = ring + (uint32_t)((k & 1) * kPatchRows * kPatchPitch + kEdge * kPatchPitch + ox + kEdge) -
+                            0x4B400000u * (uint32_t)(kPatchPitch + 1);
+    auto sample = [&](float x, float y) -> uint32_t {          // I[cy + round(x*b + y*a)][cx + round(x*a - y*b)] of the blurred level
+      const float rm = __fadd_rn(__fadd_rn(__fmul_rn(x, bk), __fmul_rn(y, ak)), 12582912.f);
+      const float cm = __fadd_rn(__fsub_rn(__fmul_rn(x, ak), __fmul_rn(y, bk)), 12582912.f);
+      uint32_t v;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(__float_as_uint(rm) * (uint32_t)kPatchPitch + __float_as_uint(cm) + corner));
+      return v;
+    };
     int val = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t pw = pat[j];
-      const float x0 = (float)(signed char)(pw & 0xFF), y0 = (float)(signed char)((pw >> 8) & 0xFF),
-                  x1 = (float)(signed char)((pw >> 16) & 0xFF), y1 = (float)(signed char)(pw >> 24);
-      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bk), __fmul_rn(y0, ak)));
-      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ak), __fmul_rn(y0, bk)));
-      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bk), __fmul_rn(y1, ak)));
-      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ak), __fmul_rn(y1, bk)));
-      const int t0 = pc[r0 * kPatchPitch + c0], t1 = pc[r1 * kPatchPitch + c1];
-      val |= (t0 < t1) << j;
+      const float x0 = __fsub_rn(__uint_as_float(__byte_perm(pw, 0x4B000000u, 0x7440)), 8388640.f),
+                  y0 = __fsub_rn(__uint_as_float(__byte_perm(pw, 0x4B000000u, 0x7441)), 8388640.f),
+                  x1 = __fsub_rn(__uint_as_float(__byte_perm(pw, 0x4B000000u, 0x7442)), 8388640.f),
+                  y1 = __fsub_rn(__uint_as_float(__byte_perm(pw, 0x4B000000u, 0x7443)), 8388640.f);
+      val |= (sample(x0, y0) < sample(x1, y1)) << j;
     }
     const int o = base + k;
     if (o < P.kp_cap) P.out_desc[((long long)f * P.kp_cap + o) * 32 + lane] = (uint8_t)val;
@@ -2020,8 +2031,8 @@ static int orb_build(drfe_orb* h) {
   {
     std::vector<uint32_t> ps(256);
     for (int t = 0; t < 256; ++t)
-      ps[(t & 7) * 32 + (t >> 3)] = (uint32_t)(uint8_t)h_pattern[4 * t] | ((uint32_t)(uint8_t)h_pattern[4 * t + 1] << 8) |
-                                    ((uint32_t)(uint8_t)h_pattern[4 * t + 2] << 16) | ((uint32_t)(uint8_t)h_pattern[4 * t + 3] << 24);
+      ps[(t & 7) * 32 + (t >> 3)] = (uint32_t)(h_pattern[4 * t] + 32) | ((uint32_t)(h_pattern[4 * t + 1] + 32) << 8) |
+                                    ((uint32_t)(h_pattern[4 * t + 2] + 32) << 16) | ((uint32_t)(h_pattern[4 * t + 3] + 32) << 24);
     DRFE_CUDA(cudaMemcpyToSymbol(g_pattern_s8, ps.data(), sizeof(uint32_t) * 256));
   }
   DRFE_CUDA(raise_dyn_smem((k_fast_strips<256>), h->device, (size_t)(h->fast_smem)));
@@ -2110,6 +2121,7 @@ int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, in
 
 // all kernels of frames [f0, f0 + n) on the handle's stream; src/rs/fs address frame 0 of the batch
 static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
+  NvtxRange nvtx_("orb_launch");
   cudaStream_t st = h->stream;
   h->post_valid = false;         // the keypoints drfe_orb_frame_post worked on are being replaced
   const OrbDev& D = h->hd;
@@ -2151,6 +2163,7 @@ static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long 
 
 int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride, size_t frame_stride,
                      int mem_kind) {
+  NvtxRange nvtx_("drfe_orb_enqueue");
   if (!h || !gray) { set_error("drfe_orb_enqueue: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_orb_enqueue: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   if (row_stride < (size_t)h->width) { set_error("drfe_orb_enqueue: row_stride < width"); return DRFE_ERR_ARG; }
@@ -2183,6 +2196,7 @@ int drfe_orb_enqueue(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_s
 
 int drfe_orb_enqueue_color(drfe_orb* h, int nframes, const uint8_t* pixels, int channels, int rgb_order, int coeffs, size_t row_stride,
                            size_t frame_stride, int mem_kind) {
+  NvtxRange nvtx_("drfe_orb_enqueue_color");
   if (!h || !pixels) { set_error("drfe_orb_enqueue_color: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_orb_enqueue_color: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   if ((channels != 3 && channels != 4) || (coeffs != DRFE_GRAY_Q15 && coeffs != DRFE_GRAY_Q14)) { set_error("drfe_orb_enqueue_color: channels %d / coeffs %d", channels, coeffs); return DRFE_ERR_ARG; }
@@ -2249,6 +2263,7 @@ static int orb_check_status(drfe_orb* h) {
 }
 
 int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_per_frame, int* counts) {
+  NvtxRange nvtx_("drfe_orb_download");
   if (!h || !counts) { set_error("drfe_orb_download: null argument"); return DRFE_ERR_ARG; }
   if (!h->pending) { set_error("drfe_orb_download: nothing enqueued"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -2280,6 +2295,7 @@ int drfe_orb_download(drfe_orb* h, drfe_keypoint* kps, uint8_t* desc, int cap_pe
 
 int drfe_orb_extract(drfe_orb* h, const uint8_t* gray, int width, int height, size_t row_stride, drfe_keypoint* kps,
                      uint8_t* desc, int cap, int* n) {
+  NvtxRange nvtx_("drfe_orb_extract");
   if (!h) { set_error("drfe_orb_extract: null handle"); return DRFE_ERR_ARG; }
   if (!n) { set_error("drfe_orb_extract: null count pointer"); return DRFE_ERR_ARG; }
   if (!gray || width == 0 || height == 0) { *n = 0; return DRFE_OK; }  // empty image: silent return (ORBextractor.cc:1046); the caller's containers stay as they are
@@ -2292,6 +2308,7 @@ int drfe_orb_extract(drfe_orb* h, const uint8_t* gray, int width, int height, si
 
 int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t row_stride, size_t frame_stride,
                            drfe_keypoint* kps, uint8_t* desc, int cap_per_frame, int* counts, int chunk_frames) {
+  NvtxRange nvtx_("drfe_orb_extract_batch");
   if (!h || !gray || !counts) { set_error("drfe_orb_extract_batch: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > h->max_batch) { set_error("drfe_orb_extract_batch: nframes %d outside [1,%d]", nframes, h->max_batch); return DRFE_ERR_ARG; }
   if (row_stride < (size_t)h->width || (nframes > 1 && frame_stride < row_stride * h->height)) { set_error("drfe_orb_extract_batch: bad strides"); return DRFE_ERR_ARG; }
@@ -2342,6 +2359,7 @@ int drfe_orb_extract_batch(drfe_orb* h, int nframes, const uint8_t* gray, size_t
 }
 
 int drfe_orb_finish_batch(drfe_orb* h) {
+  NvtxRange nvtx_("drfe_orb_finish_batch");
   if (!h) { set_error("drfe_orb_finish_batch: null handle"); return DRFE_ERR_ARG; }
   if (!h->pipe.active) { set_error("drfe_orb_finish_batch: no batch in flight"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -2397,6 +2415,7 @@ int drfe_frame_image_bounds(drfe_frame_params* p, int width, int height) {
 // launch k_frame_post on the depth Q names and copy the requested outputs out
 static int frame_post_run(drfe_orb* h, drfe_keypoint* keys_un, float* u_right, float* kp_depth, uint16_t* grid_count, uint16_t* grid_index,
                           int cap_per_frame) {
+  NvtxRange nvtx_("frame_post_run");
   cudaStream_t st = h->stream;
   const int nf = h->last_frames, cap = h->hd.kp_cap;
   PostDev& Q = h->post;
@@ -2483,6 +2502,7 @@ int drfe_orb_frame_post_shared_depth(drfe_orb* h, drfe_cape* cape, const drfe_fr
 
 int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries, const uint8_t* qdesc,
                                   const uint8_t* occupied, int qcap, drfe_proj_match* out) {
+  NvtxRange nvtx_("drfe_orb_search_by_projection");
   if (!h || !nqueries || !queries || !qdesc || !out || qcap < 1) { set_error("drfe_orb_search_by_projection: bad argument"); return DRFE_ERR_ARG; }
   if (!h->pending || !h->post.keys_un || !h->post_valid) { set_error("drfe_orb_search_by_projection: run drfe_orb_frame_post on this batch first"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -2511,6 +2531,7 @@ int drfe_orb_search_by_projection(drfe_orb* h, const int* nqueries, const drfe_p
 int drfe_orb_search_local_points(drfe_orb* h, const int* nqueries, const drfe_proj_query* queries, const uint8_t* qdesc, const uint8_t* qflags,
                                  const uint8_t* occupied, int qcap, float nnratio, drfe_proj_match* out, int32_t* assigned, int32_t* key_point,
                                  int* nmatches) {
+  NvtxRange nvtx_("drfe_orb_search_local_points");
   if (!h || !nqueries || !queries || !qdesc || !qflags || qcap < 1) { set_error("drfe_orb_search_local_points: bad argument"); return DRFE_ERR_ARG; }
   if (!h->pending || !h->post.keys_un || !h->post_valid) { set_error("drfe_orb_search_local_points: run drfe_orb_frame_post on this batch first"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
@@ -2555,6 +2576,7 @@ int drfe_orb_search_local_points(drfe_orb* h, const int* nqueries, const drfe_pr
 int drfe_orb_search_last_frame(drfe_orb* h, const drfe_track_params* tp, const int* npoints, const drfe_last_point* points,
                                const uint8_t* pdesc, const uint8_t* occupied, int pcap, int32_t* match_key, int32_t* match_dist,
                                int32_t* key_point, int* nmatches, int* sweeps) {
+  NvtxRange nvtx_("drfe_orb_search_last_frame");
   if (!h || !tp || !npoints || !points || !pdesc || pcap < 1) { set_error("drfe_orb_search_last_frame: bad argument"); return DRFE_ERR_ARG; }
   if (!h->pending || !h->post.keys_un || !h->post_valid) { set_error("drfe_orb_search_last_frame: run drfe_orb_frame_post on this batch first"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);

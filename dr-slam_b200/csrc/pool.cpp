@@ -59,6 +59,7 @@ void worker_run(drfe_pool* p, PoolWorker* w) {
   const int n = w->f1 - w->f0;
   w->rc = DRFE_OK; w->err.clear(); w->ms = 0.f;
   if (n <= 0) return;
+  drfe::NvtxRange nvtx_("drfe_pool worker block");
   const size_t f0 = (size_t)w->f0;
   const size_t desz = J.depth_is_u16 ? sizeof(uint16_t) : sizeof(float);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -151,6 +152,7 @@ int drfe_pool_extract_batch(drfe_pool* p, int nframes, const uint8_t* gray, size
                             int depth_is_u16, float depth_factor, size_t depth_row_stride, size_t depth_frame_stride, float fx, float fy, float cx,
                             float cy, drfe_keypoint* kps, uint8_t* desc, int cap_per_frame, int* counts, uint8_t* seg_out, drfe_plane* planes,
                             int plane_cap, int* nr_planes, drfe_cylinder* cylinders, int cyl_cap, int* nr_cylinders) {
+  drfe::NvtxRange nvtx_("drfe_pool_extract_batch");
   if (!p || !gray || !depth || !counts || !nr_planes) { drfe::set_error("drfe_pool_extract_batch: null argument"); return DRFE_ERR_ARG; }
   if (nframes < 1 || nframes > p->prm.max_batch) { drfe::set_error("drfe_pool_extract_batch: nframes %d outside [1,%d]", nframes, p->prm.max_batch); return DRFE_ERR_ARG; }
   const int nd = (int)p->workers.size();
@@ -165,10 +167,12 @@ int drfe_pool_extract_batch(drfe_pool* p, int nframes, const uint8_t* gray, size
     J.seg = seg_out; J.planes = planes; J.plane_cap = plane_cap; J.nr_planes = nr_planes;
     J.cyls = cylinders; J.cyl_cap = cyl_cap; J.nr_cyls = nr_cylinders;
     J.chunk_frames = p->prm.chunk_frames;
-    // contiguous blocks, as even as possible: device i gets frames [i * nframes / nd, (i + 1) * nframes / nd)
+    // contiguous blocks that differ by at most one frame, the first (nframes % nd) devices take the longer ones
+    // (the same rule as dr-slam_b200/shard.py frame_block, which the torchrun ranks of bench.py use)
+    const int base = nframes / nd, extra = nframes % nd;
     for (int i = 0; i < nd; ++i) {
-      p->workers[i].f0 = (int)((long long)i * nframes / nd);
-      p->workers[i].f1 = (int)((long long)(i + 1) * nframes / nd);
+      p->workers[i].f0 = i * base + std::min(i, extra);
+      p->workers[i].f1 = p->workers[i].f0 + base + (i < extra ? 1 : 0);
     }
     p->remaining = nd;
     ++p->generation;

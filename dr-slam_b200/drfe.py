@@ -432,7 +432,8 @@ class ORBextractor:
         kps = np.empty((nf, self.cap), KP_DTYPE) if kps is None else kps
         desc = np.empty((nf, self.cap, 32), np.uint8) if desc is None else desc
         counts = np.empty(nf, np.int32) if counts is None else counts
-        _check(self.L.drfe_orb_download(self.h, _ptr(kps), _ptr(desc), self.cap, _ptr(counts)))
+        assert kps.shape[1] == desc.shape[1]
+        _check(self.L.drfe_orb_download(self.h, _ptr(kps), _ptr(desc), kps.shape[1], _ptr(counts)))
         return kps, desc, counts
 
     def extract_batch(self, gray, kps=None, desc=None, counts=None, chunk_frames=0):

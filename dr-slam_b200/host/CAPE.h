@@ -133,8 +133,10 @@ class CAPE {
 
 namespace Planar_SLAM {
 
-// PlaneDetection_CAPE (PlaneExtractor.h:84-115): readDepthImage / runPlaneDetection and the public
-// result fields.  plane_cloud (PCL) is replaced by per-plane xyz lists so that no PCL is needed.
+// PlaneDetection_CAPE (PlaneExtractor.h:84-115): readColorImage / readDepthImage / runPlaneDetection and the public
+// result fields.  plane_cloud (PCL) is replaced by per-plane xyz lists so that no PCL is needed.  With
+// -DDRFE_WITH_OPENCV the members are the reference's cv::Mat's (seg_output is CV_8U like its cv::Mat_<uchar>,
+// K_ the 3x3 CV_32F camera matrix); otherwise the stand-ins of drfe_compat.h.
 class PlaneDetection_CAPE {
  public:
   struct PointT { float x, y, z; };
@@ -142,17 +144,44 @@ class PlaneDetection_CAPE {
 
   PlaneDetection_CAPE() = default;
   ~PlaneDetection_CAPE() { delete plane_detector; }
+  PlaneDetection_CAPE(const PlaneDetection_CAPE&) = delete;
+  PlaneDetection_CAPE& operator=(const PlaneDetection_CAPE&) = delete;
 
+#ifdef DRFE_WITH_OPENCV
+  bool readColorImage(cv::Mat RGBImg) {                            // PlaneExtractor.cpp:71-78 (the colour image is not used by the path)
+    color_img_ = RGBImg;
+    return !(color_img_.empty() || color_img_.depth() != CV_8U);
+  }
+  bool readDepthImage(cv::Mat depthImg, cv::Mat& K) {              // PlaneExtractor.cpp:101-109
+    depth_img = depthImg;
+    K_ = K;
+    return !(depth_img.empty() || depth_img.depth() != CV_32F);
+  }
+  cv::Mat seg_output, color_img_, depth_img, K_;
+#else
   bool readDepthImage(const drfe_compat::Mat32f& depthImg, const float K[9]) {
     depth_img = depthImg;
     for (int i = 0; i < 9; ++i) K_[i] = K[i];
     return !depth_img.empty();
   }
+  drfe_compat::Mat8u seg_output;
+  drfe_compat::Mat32f depth_img;
+  float K_[9] = {0};
+#endif
 
   void runPlaneDetection() {
     const int rows = depth_img.rows, cols = depth_img.cols;
+#ifdef DRFE_WITH_OPENCV
+    seg_output.create(rows, cols, CV_8U);                          // cv::Mat_<uchar>(rows, cols, uchar(0)), PlaneExtractor.cpp:129
+    seg_output.setTo(cv::Scalar(0));
+    const float* depth = depth_img.ptr<float>(0);
+    const float fx = K_.at<float>(0, 0), fy = K_.at<float>(1, 1), cx = K_.at<float>(0, 2), cy = K_.at<float>(1, 2);   // :113-116
+#else
     seg_output.create(rows, cols);
     seg_output.setTo(0);
+    const float* depth = depth_img.data;
+    const float fx = K_[0], fy = K_[4], cx = K_[2], cy = K_[5];
+#endif
     // CAPE::process appends (CAPE.cpp:279) and the reference uses one PlaneDetection_CAPE per Frame; this object may
     // be run again, so its results start empty: plane_params[i], plane_cloud[i] and label i + 1 of seg_output line up
     plane_params.clear();
@@ -162,8 +191,8 @@ class PlaneDetection_CAPE {
       plane_detector = new CAPE(rows, cols, PATCH_SIZE, PATCH_SIZE, cylinder_detection, COS_ANGLE_MAX, MAX_MERGE_DIST);
       det_rows_ = rows; det_cols_ = cols;
     }
-    plane_detector->processDepth(depth_img.data, depth_img.step / sizeof(float), K_[0], K_[4], K_[2], K_[5], nr_planes,
-                                 nr_cylinders, seg_output, plane_params, &cylinder_params);
+    plane_detector->processDepth(depth, (size_t)depth_img.step / sizeof(float), fx, fy, cx, cy, nr_planes, nr_cylinders, seg_output,
+                                 plane_params, &cylinder_params);
     // per-plane point lists (PlaneExtractor.cpp:165-190), gathered on the device from seg_output and the cloud
     plane_detector->planePoints(pts_, offs_);
     plane_cloud.assign(nr_planes, PointCloud());
@@ -177,9 +206,6 @@ class PlaneDetection_CAPE {
   std::vector<PlaneSeg> plane_params;
   std::vector<CylinderSeg> cylinder_params;
   int nr_planes = 0, nr_cylinders = 0;
-  drfe_compat::Mat8u seg_output;
-  drfe_compat::Mat32f depth_img;
-  float K_[9] = {0};
   int PATCH_SIZE = 20;
   float COS_ANGLE_MAX = (float)std::cos(M_PI / 12);
   float MAX_MERGE_DIST = 50.f;

@@ -1,0 +1,91 @@
+// The adapters' DRFE_WITH_OPENCV / DRFE_WITH_EIGEN branches — the code a DR-SLAM maintainer actually compiles — built
+// against the mock headers of tests/host/mock and driven with the REFERENCE's call shapes:
+//   (*mpORBextractorLeft)(im, cv::Mat(), mvKeys, mDescriptors)                          Frame.cc:473-478
+//   planeDetector.readDepthImage(imDepth, K); planeDetector.runPlaneDetection()         Frame.cc:1096-1104
+//   plane_detector->process(cloud_array_organized, nr_planes, nr_cylinders, seg_output, plane_params, cylinder_params)
+//                                                                                        PlaneExtractor.cpp:149-154
+// Prints the same digest line as dr-slam_b200/host/example_frontend (tests/test_gpu_adapters.py compares the two and
+// the oracle).  Test infrastructure; build: see tests/test_host_adapters_opencv.py.
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+
+#include "CAPE.h"
+#include "ORBextractor.h"
+#include "drfe_synth.h"
+
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+  const uint8_t* b = (const uint8_t*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+int main(int argc, char** argv) {
+  const int W = 640, H = 480;
+  const int scene = argc > 1 ? atoi(argv[1]) : 1;
+  const uint32_t seed = argc > 2 ? (uint32_t)atoll(argv[2]) : 20260042u;
+  cv::Mat im(H, W, CV_8UC1), imDepth(H, W, CV_32FC1), K(3, 3, CV_32FC1);
+  float fx, fy, cx, cy;
+  if (drfe_synth_frame(W, H, scene, seed, 1.0f, im.data, imDepth.ptr<float>(0), &fx, &fy, &cx, &cy) != 0) return 2;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) K.at<float>(r, c) = 0.f;
+  K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy; K.at<float>(2, 2) = 1.f;
+  try {
+    Planar_SLAM::ORBextractor orb(1000, 1.2f, 8, 20, 7);
+    Planar_SLAM::PlaneDetection_CAPE planes;
+    planes.PATCH_SIZE = 20; planes.MAX_MERGE_DIST = 50.f;
+    std::vector<cv::KeyPoint> mvKeys;
+    cv::Mat mDescriptors;
+    std::thread threadORB([&] { orb(im, cv::Mat(), mvKeys, mDescriptors); });
+    std::thread threadPlanes([&] {
+      planes.readDepthImage(imDepth, K);
+      planes.runPlaneDetection();
+    });
+    threadORB.join();
+    threadPlanes.join();
+    size_t npts = 0;
+    for (auto& pc : planes.plane_cloud) npts += pc.size();
+    // descriptors row by row: a cv::Mat need not be continuous
+    uint64_t dh = 1469598103934665603ull;
+    for (int i = 0; i < mDescriptors.rows; ++i) dh = fnv1a(mDescriptors.ptr(i), 32, dh);
+    uint64_t sh = 1469598103934665603ull;
+    for (int r = 0; r < H; ++r) sh = fnv1a(planes.seg_output.ptr(r), (size_t)W, sh);
+    printf("keypoints %zu kp_hash %016llx desc_hash %016llx planes %d seg_hash %016llx plane_points %zu levels %d\n", mvKeys.size(),
+           (unsigned long long)fnv1a(mvKeys.data(), mvKeys.size() * sizeof(mvKeys[0])), (unsigned long long)dh, planes.nr_planes,
+           (unsigned long long)sh, npts, orb.GetLevels());
+    for (int i = 0; i < planes.nr_planes; ++i)
+      printf("plane %d n %.9f %.9f %.9f d %.9f\n", i, planes.plane_params[i].normal[0], planes.plane_params[i].normal[1],
+             planes.plane_params[i].normal[2], planes.plane_params[i].d);
+    // CAPE::process with the reference's argument list on an Eigen::MatrixXf cloud (cell-major, N x 3 column-major) built
+    // the way PlaneExtractor.cpp:112-148 builds it
+    const int cw = 20, ch = 20, ncx = W / cw;
+    Eigen::MatrixXf cloud(W * H, 3);
+    for (int r = 0; r < H; ++r)
+      for (int c = 0; c < W; ++c) {
+        const double z = (double)imDepth.at<float>(r, c);
+        const int id = ((r / ch) * ncx + c / cw) * cw * ch + (r % ch) * cw + (c % cw);
+        cloud(id, 0) = (float)(((double)c - (double)cx) * z / (double)fx);
+        cloud(id, 1) = (float)(((double)r - (double)cy) * z / (double)fy);
+        cloud(id, 2) = (float)z;
+      }
+    CAPE detector(H, W, cw, ch, false, planes.COS_ANGLE_MAX, 50.f);
+    int nr_planes = 0, nr_cylinders = 0;
+    cv::Mat seg(H, W, CV_8U);
+    seg.setTo(cv::Scalar(0));
+    std::vector<PlaneSeg> plane_params;
+    std::vector<CylinderSeg> cylinder_params;
+    detector.process(cloud, nr_planes, nr_cylinders, seg, plane_params, cylinder_params);
+    uint64_t sh2 = 1469598103934665603ull;
+    for (int r = 0; r < H; ++r) sh2 = fnv1a(seg.ptr(r), (size_t)W, sh2);
+    printf("process planes %d cylinders %d seg_hash %016llx appended %zu\n", nr_planes, nr_cylinders, (unsigned long long)sh2, plane_params.size());
+    // an empty image leaves the caller's containers untouched (ORBextractor.cc:1046-1047)
+    std::vector<cv::KeyPoint> untouched(3);
+    cv::Mat d2;
+    orb(cv::Mat(), cv::Mat(), untouched, d2);
+    printf("empty_image keeps %zu\n", untouched.size());
+  } catch (const std::exception& e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

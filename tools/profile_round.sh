@@ -6,7 +6,7 @@ tag=${1:-prof}
 mkdir -p gpurun_out
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_launches.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/${tag}_launches.log 2>&1
 # 13 ORB + 5 CAPE launches per step in prof_step (ORB first, then CAPE): skip the 2 warm-up steps of each
 ncu --set full --clock-control none --import-source on -k regex:'k_pyr_stream|k_pyr_level0|k_fast|k_quadtree|k_blur|k_orient' -s 26 -c 13 -f \
     -o gpurun_out/${tag}_full_orb python tools/prof_step.py --steps 1 --only orb > gpurun_out/${tag}_full_orb.log 2>&1
