@@ -54,6 +54,9 @@ struct CapeDev {
   float* plane_maxd;            // [B][kMaxPlanes+1] 9*MSE
   int* nplanes;                 // [B]
   uint8_t* seg;                 // [B][H*W]
+  uint8_t* cell_label;          // [B][ncells] label a cell is painted with as a whole (k_cape_refine_plan -> k_cape_paint)
+  int2* border_list;            // [B * ncells] {batch-wide cell index, mask of its first 32 planes} of the launch's border cells (k_cape_refine_plan -> k_cape_refine_border)
+  int* border_count;            // [1]
   int* status;
   struct CellSums* sums;        // [B][ncells] per-cell moment sums (k_cape_sums -> k_cape_fit)
   // ---- cylinder detection (CylinderSeg.cpp, CAPE.cpp:179-216, 323-393); all null / 0 when it is off
@@ -1462,237 +1465,295 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 }
 
 // ------------------------------------------------------------------ refinement + output
-// One warp per cell.  Label per pixel = argmin over final planes (in order) of the squared
-// float distance, subject to < 9*MSE, strict '<' against the running minimum which starts at
-// the bit pattern memset(...,100,...) leaves (0x64646464, CAPE.cpp:60).  Cells inside an
-// eroded mask are painted whole (:410-412).
-// MODE as in k_cape_sums: with a depth image the points of a border cell are converted again here (the same
-// arithmetic, hence the same bits) instead of being read back from a cloud that k_cape_sums no longer writes.
-template <bool CYL, int MODE>
-__global__ void __launch_bounds__(256, 2) k_cape_refine(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+// Label per pixel = argmin over final planes (in order) of the squared float distance, subject to < 9*MSE, strict '<'
+// against the running minimum which starts at the bit pattern memset(...,100,...) leaves (0x64646464, CAPE.cpp:60);
+// cells inside an eroded mask are painted whole (:410-412).  Three launches:
+//   k_cape_refine_plan    thread per cell: the label a cell is painted with as a whole (eroded plane mask, then eroded
+//                         cylinder mask, else 0) and — for the cells inside some plane's / cylinder's dilated-minus-eroded
+//                         mask — an entry in the launch's list of border cells;
+//   k_cape_paint          image space, one word (4 pixels) per thread: every pixel gets its cell's label, the margin
+//                         outside the last full cell row / column gets 0 (fully coalesced stores of seg_output);
+//   k_cape_refine_border  one warp per LISTED cell, warps looping over the list: the per-pixel argmin.  Only the cells
+//                         that need it (29 % on the synthetic sequence) occupy warps: when the same kernel also painted,
+//                         a block kept its slots until its one or two border cells were done and the SMs ran at 15 %
+//                         occupancy.  With a depth image the points of a border cell are converted again here (the same
+//                         arithmetic, hence the same bits) instead of being read back from a cloud that k_cape_sums no
+//                         longer writes.
+template <bool CYL>
+__global__ void __launch_bounds__(256) k_cape_refine_plan(const CapeDev* __restrict__ Pp, int f0, int nframes) {
   const CapeDev& P = *Pp;
-  const int gw0 = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw0 >= nframes * P.ncells) return;
-  const int gw = gw0 + f0 * P.ncells;
-  const int f = gw / P.ncells, cell = gw - f * P.ncells;
-  const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
+  const int gid0 = blockIdx.x * 256 + threadIdx.x;
+  if (gid0 >= nframes * P.ncells) return;
+  const int gid = gid0 + f0 * P.ncells;
+  const int f = gid / P.ncells, cell = gid - f * P.ncells;
+  const int er = P.eroded_map[gid];
+  const int cer = CYL ? P.cyl_eroded_map[gid] : 0;
+  const int label = er > 0 ? er : (cer > 0 ? cer : 0);
+  P.cell_label[gid] = (uint8_t)label;
+  if (label) return;
+  const int nw = (P.ncells + 31) >> 5;
+  const uint32_t* bvec = P.border_vec + (long long)f * P.border_rows * nw + (cell >> 5);
+  const uint32_t bit = 1u << (cell & 31);
+  bool border = false;
+  uint32_t first32 = 0;                                          // bit b: final plane b + 1 has this cell in its border mask
+  const int npl = P.nplanes[f];
+  for (int p = 1; p <= npl; ++p)
+    if (bvec[(long long)p * nw] & bit) { border = true; if (p <= 32) first32 |= 1u << (p - 1); }
+  if (CYL) {
+    const int ncf = P.ncyl_final[f];
+    const uint32_t* cvec = bvec + (long long)(kMaxPlanes + 1) * nw;
+    for (int p = 1; p <= ncf && !border; ++p) border = (cvec[(long long)p * nw] & bit) != 0;
+  }
+  if (border) P.border_list[atomicAdd(P.border_count, 1)] = make_int2(gid, (int)first32);
+}
+
+// grid (words of a row / 64, rows / 4, frames), block (64, 4); magic_* = ceil(2^32 / d) for d = cell width, cell height
+__global__ void __launch_bounds__(256) k_cape_paint(const CapeDev* __restrict__ Pp, int f0, uint32_t magic_cw, uint32_t magic_ch) {
+  const CapeDev& P = *Pp;
+  const int W = P.W, H = P.H;
+  const int c0 = 4 * (blockIdx.x * 64 + threadIdx.x), r = blockIdx.y * 4 + threadIdx.y;
+  if (c0 >= W || r >= H) return;
+  const int f = blockIdx.z + f0;
+  const uint8_t* lab = P.cell_label + (long long)f * P.ncells;
+  const int cell_r = (int)__umulhi((uint32_t)r, magic_ch);
+  uint8_t* out = P.seg + ((long long)f * H + r) * W + c0;
+  uint32_t word = 0;
+  if (cell_r < P.ncy) {
+    const uint8_t* row = lab + cell_r * P.ncx;
+    const int ca = (int)__umulhi((uint32_t)c0, magic_cw), cb = (int)__umulhi((uint32_t)(c0 + 3), magic_cw);
+    if (ca == cb) word = ca < P.ncx ? (uint32_t)row[ca] * 0x01010101u : 0u;      // the usual case: the 4 pixels share a cell
+    else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cell_c = (int)__umulhi((uint32_t)(c0 + k), magic_cw);
+        if (cell_c < P.ncx) word |= (uint32_t)row[cell_c] << (8 * k);
+      }
+    }
+  }
+  if ((W & 3) == 0) *reinterpret_cast<uint32_t*>(out) = word;
+  else
+    for (int k = 0; k < 4 && c0 + k < W; ++k) out[k] = (uint8_t)(word >> (8 * k));
+}
+
+static const int kBorderWarps = 4;     // warps per block of k_cape_refine_border
+template <bool CYL, int MODE>
+__global__ void __launch_bounds__(kBorderWarps * 32, CYL ? 4 : 5) k_cape_refine_border(const CapeDev* __restrict__ Pp) {
+  const CapeDev& P = *Pp;
+  const int lane = threadIdx.x & 31;
+  const int nlist = *P.border_count;
   const int npc = P.npc, cw = P.cw;
   const long long N = (long long)P.H * P.W;
-  uint8_t* out = P.seg + (long long)f * N + (long long)(cr * P.ch) * P.W + cc * cw;
-  const int er = P.eroded_map[(long long)f * P.ncells + cell];
-  const int cer = CYL ? P.cyl_eroded_map[(long long)f * P.ncells + cell] : 0;
   // a cell row is cw bytes; with cw and W multiples of 4 everything below moves 4 pixels per lane and access
   const bool vec4 = ((cw | P.W) & 3) == 0;
   const int q4 = cw >> 2;
   const uint32_t q4_magic = (65536u + (uint32_t)q4 - 1u) / (uint32_t)max(q4, 1);   // j / q4 == (j * magic) >> 16 for j < 2^16 / q4
-  auto paint = [&](int whole) {
-    if (vec4 && npc < 8192) {
-      const uint32_t word = (uint32_t)whole * 0x01010101u;
-      for (int j = lane; j < (npc >> 2); j += 32) {
-        const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
-        *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = word;
-      }
-    } else {
-      for (int i = lane; i < npc; i += 32) { const int lr = i / cw, lc = i - lr * cw; out[(long long)lr * P.W + lc] = (uint8_t)whole; }
-    }
-  };
-  // cells inside an eroded plane mask are painted whole, then cells inside an eroded cylinder mask (:410-416): the
-  // common case, decided before anything else is read
-  if (er > 0) { paint(er); return; }
-  if (CYL && cer > 0) { paint(cer); return; }
-  // planes whose dilated-minus-eroded mask contains this cell: bit b of bits[m] = final plane 32*m + b + 1
-  const int nw = (P.ncells + 31) >> 5, npl = P.nplanes[f];
-  const uint32_t* bvec = P.border_vec + (long long)f * P.border_rows * nw + (cell >> 5);
-  uint32_t bits[8], cbits[8];
-  uint32_t anyb = 0, anyc = 0;
-#pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    bits[m] = 0; cbits[m] = 0;
-    if (32 * m < npl) {                                          // warp-uniform
-      const int p = 32 * m + lane + 1;
-      const bool in = p <= npl && ((bvec[(long long)p * nw] >> (cell & 31)) & 1u);
-      bits[m] = __ballot_sync(0xFFFFFFFFu, in);
-      anyb |= bits[m];
-    }
-  }
-  if (CYL) {
-    const int ncf = P.ncyl_final[f];
-    const uint32_t* cvec = bvec + (long long)(kMaxPlanes + 1) * nw;
+  const XyCtx C = xy_ctx(P);
+  for (int li = blockIdx.x * kBorderWarps + (threadIdx.x >> 5); li < nlist; li += gridDim.x * kBorderWarps) {
+    const int2 ent = P.border_list[li];
+    const int gw = ent.x;
+    const int f = gw / P.ncells, cell = gw - f * P.ncells;
+    const int cr = cell / P.ncx, cc = cell - cr * P.ncx;
+    uint8_t* out = P.seg + (long long)f * N + (long long)(cr * P.ch) * P.W + cc * cw;
+    // planes whose dilated-minus-eroded mask contains this cell: bit b of bits[m] = final plane 32*m + b + 1.  The first 32
+    // come with the list entry; frames with more planes gather the rest from the border vectors
+    const int nw = (P.ncells + 31) >> 5, npl = P.nplanes[f];
+    const uint32_t* bvec = P.border_vec + (long long)f * P.border_rows * nw + (cell >> 5);
+    uint32_t bits[8], cbits[8];
+    uint32_t anyc = 0;
+    bits[0] = (uint32_t)ent.y;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      if (32 * m < ncf) {
-        const int p = 32 * m + lane + 1;
-        const bool in = p <= ncf && ((cvec[(long long)p * nw] >> (cell & 31)) & 1u);
-        cbits[m] = __ballot_sync(0xFFFFFFFFu, in);
-        anyc |= cbits[m];
-      }
-    }
-  }
-  if ((anyb | anyc) == 0) { paint(0); return; }
-  const float* CX = MODE == 0 ? P.cloud + (long long)f * 3 * N + (long long)cell * npc : nullptr;
-  const float* CY = CX + N;
-  const float* CZ = CY + N;
-  const XyCtx C = xy_ctx(P);
-  const double col0 = (double)(cc * cw) - C.cx, row0 = (double)(cr * P.ch) - C.cy;
-  const long long dbase = (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;   // the cell's first depth element
-  const float4* eq = P.plane_eq + (long long)f * (kMaxPlanes + 1);
-  const float* maxd = P.plane_maxd + (long long)f * (kMaxPlanes + 1);
-  if (!CYL && vec4 && (npc & 3) == 0 && npc < 8192 &&
-      (MODE == 0 || (((P.depth_rs | P.depth_fs) & 3) == 0 && (reinterpret_cast<uintptr_t>(MODE == 1 ? (const void*)P.depth : (const void*)P.depth16) & (MODE == 1 ? 15 : 7)) == 0))) {
-    // planes only: 4 pixels per lane (float4 loads of the cell-major cloud, or one aligned 4-pixel depth load), one word store
-    const float4* X4 = reinterpret_cast<const float4*>(CX);
-    const float4* Y4 = reinterpret_cast<const float4*>(CY);
-    const float4* Z4 = reinterpret_cast<const float4*>(CZ);
-    // the depth of every quad this lane will handle is requested before any of it is used (a border cell is a few
-    // dependent iterations per lane: one load latency per iteration was a quarter of the kernel's stall samples)
-    constexpr int kAhead = 4;                                   // 4 x 32 quads = cells of up to 512 pixels in one go
-    const int nq = npc >> 2;
-    float4 zq[kAhead];
-    auto load_depth = [&](int j) -> float4 {
-      const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
-      if (MODE == 1) return __ldg(reinterpret_cast<const float4*>(P.depth + dbase + (long long)lr * P.depth_rs + 4 * c4));
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(P.depth16 + dbase + (long long)lr * P.depth_rs + 4 * c4));
-      const float fac = P.depth_factor;
-      return make_float4((float)(v.x & 0xFFFFu) * fac, (float)(v.x >> 16) * fac, (float)(v.y & 0xFFFFu) * fac, (float)(v.y >> 16) * fac);
-    };
-    if (MODE != 0) {
-#pragma unroll
-      for (int a = 0; a < kAhead; ++a) { const int j = lane + 32 * a; zq[a] = j < nq ? load_depth(j) : make_float4(0.f, 0.f, 0.f, 0.f); }
-    }
-    // the cell's first kLocal planes (ascending plane number; a border cell rarely sees more than two) come into
-    // registers with independent loads before the pixel loop; whatever is left stays in `bits` for the generic loop
-    constexpr int kLocal = 4;
-    float4 peq[kLocal];
-    float pmd[kLocal];
-    int pid[kLocal], nloc = 0;
-    uint32_t any_rest = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      while (bits[k] && nloc < kLocal) {
-        const int p = k * 32 + __ffs(bits[k]);
-        bits[k] &= bits[k] - 1;
-#pragma unroll
-        for (int i = 0; i < kLocal; ++i)
-          if (i == nloc) { pid[i] = p; peq[i] = eq[p]; pmd[i] = maxd[p]; }
-        ++nloc;
-      }
-      any_rest |= bits[k];
-    }
-#pragma unroll 1
-    for (int j0 = lane; j0 < nq; j0 += 32 * kAhead) {
-#pragma unroll
-     for (int a = 0; a < kAhead; ++a) {
-      const int j = j0 + 32 * a;
-      if (j >= nq) break;
-      const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
-      float xs[4], ys[4], zs[4];
-      if (MODE == 0) {
-        const float4 xv = X4[j], yv = Y4[j], zv = Z4[j];
-        xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w; ys[0] = yv.x; ys[1] = yv.y; ys[2] = yv.z; ys[3] = yv.w;
-        zs[0] = zv.x; zs[1] = zv.y; zs[2] = zv.z; zs[3] = zv.w;
-      } else {
-        const float4 zv = j0 == lane ? zq[a] : load_depth(j);   // cells of more than 512 pixels: later rounds load on the spot
-        zs[0] = zv.x; zs[1] = zv.y; zs[2] = zv.z; zs[3] = zv.w;
-        const double drow = row0 + (double)lr, dcol = col0 + (double)(4 * c4);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xy_from_depth(C, zs[u], dcol + (double)u, drow, xs[u], ys[u]);
-      }
-      float best[4];
-      uint32_t lab = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) best[u] = __uint_as_float(0x64646464u);
-#pragma unroll
-      for (int i = 0; i < kLocal; ++i) {
-        if (i < nloc) {
-          const float4 e = peq[i];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float v = xs[u] * e.x + ys[u] * e.y + zs[u] * e.z + e.w;
-            const float dist = v * v;
-            if (dist < pmd[i] && dist < best[u]) { best[u] = dist; lab = (lab & ~(0xFFu << (8 * u))) | ((uint32_t)pid[i] << (8 * u)); }
-          }
+      cbits[m] = 0;
+      if (m > 0) {
+        bits[m] = 0;
+        if (32 * m < npl) {                                        // warp-uniform
+          const int p = 32 * m + lane + 1;
+          const bool in = p <= npl && ((bvec[(long long)p * nw] >> (cell & 31)) & 1u);
+          bits[m] = __ballot_sync(0xFFFFFFFFu, in);
         }
       }
-      if (any_rest) {
+    }
+    if (CYL) {
+      const int ncf = P.ncyl_final[f];
+      const uint32_t* cvec = bvec + (long long)(kMaxPlanes + 1) * nw;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          uint32_t b = bits[k];
-          while (b) {
-            const int p = k * 32 + __ffs(b);
-            b &= b - 1;
-            const float4 e = eq[p];
-            const float md = maxd[p];
-#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        if (32 * m < ncf) {
+          const int p = 32 * m + lane + 1;
+          const bool in = p <= ncf && ((cvec[(long long)p * nw] >> (cell & 31)) & 1u);
+          cbits[m] = __ballot_sync(0xFFFFFFFFu, in);
+          anyc |= cbits[m];
+        }
+      }
+    }
+    const float* CX = MODE == 0 ? P.cloud + (long long)f * 3 * N + (long long)cell * npc : nullptr;
+    const float* CY = CX + N;
+    const float* CZ = CY + N;
+    const double col0 = (double)(cc * cw) - C.cx, row0 = (double)(cr * P.ch) - C.cy;
+    const long long dbase = (long long)f * P.depth_fs + (long long)(cr * P.ch) * P.depth_rs + cc * cw;   // the cell's first depth element
+    const float4* eq = P.plane_eq + (long long)f * (kMaxPlanes + 1);
+    const float* maxd = P.plane_maxd + (long long)f * (kMaxPlanes + 1);
+    if (!CYL && vec4 && (npc & 3) == 0 && npc < 8192 &&
+        (MODE == 0 || (((P.depth_rs | P.depth_fs) & 3) == 0 && (reinterpret_cast<uintptr_t>(MODE == 1 ? (const void*)P.depth : (const void*)P.depth16) & (MODE == 1 ? 15 : 7)) == 0))) {
+      // planes only: 4 pixels per lane (float4 loads of the cell-major cloud, or one aligned 4-pixel depth load), one word store
+      const float4* X4 = reinterpret_cast<const float4*>(CX);
+      const float4* Y4 = reinterpret_cast<const float4*>(CY);
+      const float4* Z4 = reinterpret_cast<const float4*>(CZ);
+      // the depth of every quad this lane will handle is requested before any of it is used (a border cell is a few
+      // dependent iterations per lane: one load latency per iteration was a quarter of the kernel's stall samples)
+      constexpr int kAhead = 4;                                   // 4 x 32 quads = cells of up to 512 pixels in one go
+      const int nq = npc >> 2;
+      float4 zq[kAhead];
+      auto load_depth = [&](int j) -> float4 {
+        const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
+        if (MODE == 1) return __ldg(reinterpret_cast<const float4*>(P.depth + dbase + (long long)lr * P.depth_rs + 4 * c4));
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(P.depth16 + dbase + (long long)lr * P.depth_rs + 4 * c4));
+        const float fac = P.depth_factor;
+        return make_float4((float)(v.x & 0xFFFFu) * fac, (float)(v.x >> 16) * fac, (float)(v.y & 0xFFFFu) * fac, (float)(v.y >> 16) * fac);
+      };
+      if (MODE != 0) {
+  #pragma unroll
+        for (int a = 0; a < kAhead; ++a) { const int j = lane + 32 * a; zq[a] = j < nq ? load_depth(j) : make_float4(0.f, 0.f, 0.f, 0.f); }
+      }
+      // the cell's first kLocal planes (ascending plane number; a border cell rarely sees more than two) come into
+      // registers with independent loads before the pixel loop; whatever is left stays in `bits` for the generic loop
+      constexpr int kLocal = 4;
+      float4 peq[kLocal];
+      float pmd[kLocal];
+      int pid[kLocal], nloc = 0;
+      uint32_t any_rest = 0;
+  #pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        while (bits[k] && nloc < kLocal) {
+          const int p = k * 32 + __ffs(bits[k]);
+          bits[k] &= bits[k] - 1;
+  #pragma unroll
+          for (int i = 0; i < kLocal; ++i)
+            if (i == nloc) { pid[i] = p; peq[i] = eq[p]; pmd[i] = maxd[p]; }
+          ++nloc;
+        }
+        any_rest |= bits[k];
+      }
+  #pragma unroll 1
+      for (int j0 = lane; j0 < nq; j0 += 32 * kAhead) {
+  #pragma unroll
+       for (int a = 0; a < kAhead; ++a) {
+        const int j = j0 + 32 * a;
+        if (j >= nq) break;
+        const int lr = (int)(((uint32_t)j * q4_magic) >> 16), c4 = j - lr * q4;
+        float xs[4], ys[4], zs[4];
+        if (MODE == 0) {
+          const float4 xv = X4[j], yv = Y4[j], zv = Z4[j];
+          xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w; ys[0] = yv.x; ys[1] = yv.y; ys[2] = yv.z; ys[3] = yv.w;
+          zs[0] = zv.x; zs[1] = zv.y; zs[2] = zv.z; zs[3] = zv.w;
+        } else {
+          const float4 zv = j0 == lane ? zq[a] : load_depth(j);   // cells of more than 512 pixels: later rounds load on the spot
+          zs[0] = zv.x; zs[1] = zv.y; zs[2] = zv.z; zs[3] = zv.w;
+          const double drow = row0 + (double)lr, dcol = col0 + (double)(4 * c4);
+          const double ky = drow * C.rfy;
+          double qx[4], qy[4];
+          bool exact = !C.sane;
+  #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double zd = (double)zs[u];
+            qx[u] = zd * ((dcol + (double)u) * C.rfx); qy[u] = zd * ky;
+            exact |= xy_needs_exact(zs[u], qx[u], qy[u]);
+          }
+          if (exact) {                                              // rare: all four the slow way
+  #pragma unroll
+            for (int u = 0; u < 4; ++u) xy_exact(zs[u], dcol + (double)u, drow, C.fx, C.fy, xs[u], ys[u]);
+          } else {
+  #pragma unroll
+            for (int u = 0; u < 4; ++u) { xs[u] = (float)qx[u]; ys[u] = (float)qy[u]; }
+          }
+        }
+        float best[4];
+        int labs[4];
+  #pragma unroll
+        for (int u = 0; u < 4; ++u) { best[u] = __uint_as_float(0x64646464u); labs[u] = 0; }
+  #pragma unroll
+        for (int i = 0; i < kLocal; ++i) {
+          if (i < nloc) {
+            const float4 e = peq[i];
+  #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float v = xs[u] * e.x + ys[u] * e.y + zs[u] * e.z + e.w;
               const float dist = v * v;
-              if (dist < md && dist < best[u]) { best[u] = dist; lab = (lab & ~(0xFFu << (8 * u))) | ((uint32_t)p << (8 * u)); }
+              if (dist < fminf(pmd[i], best[u])) { best[u] = dist; labs[u] = pid[i]; }
             }
           }
         }
+        if (any_rest) {
+  #pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t b = bits[k];
+            while (b) {
+              const int p = k * 32 + __ffs(b);
+              b &= b - 1;
+              const float4 e = eq[p];
+              const float md = maxd[p];
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float v = xs[u] * e.x + ys[u] * e.y + zs[u] * e.z + e.w;
+                const float dist = v * v;
+                if (dist < fminf(md, best[u])) { best[u] = dist; labs[u] = p; }
+              }
+            }
+          }
+        }
+        *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) =
+            (uint32_t)labs[0] | ((uint32_t)labs[1] << 8) | ((uint32_t)labs[2] << 16) | ((uint32_t)labs[3] << 24);
+       }
       }
-      *reinterpret_cast<uint32_t*>(out + (long long)lr * P.W + 4 * c4) = lab;
-     }
+      continue;
     }
-    return;
-  }
-  for (int i = lane; i < npc; i += 32) {
-    const int lr = i / cw, lc = i - lr * cw;
-    float x, y, z;
-    if (MODE == 0) { x = CX[i]; y = CY[i]; z = CZ[i]; }
-    else {
-      if (MODE == 1) z = __ldg(P.depth + dbase + (long long)lr * P.depth_rs + lc);
-      else z = (float)__ldg(P.depth16 + dbase + (long long)lr * P.depth_rs + lc) * P.depth_factor;
-      xy_from_depth(C, z, col0 + (double)lc, row0 + (double)lr, x, y);
-    }
-    float best = __uint_as_float(0x64646464u);
-    int lab = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      uint32_t b = bits[k];
-      while (b) {
-        const int p = k * 32 + __ffs(b);
-        b &= b - 1;
-        const float4 e = eq[p];
-        const float v = x * e.x + y * e.y + z * e.z + e.w;
-        const float dist = v * v;
-        if (dist < maxd[p] && dist < best) { best = dist; lab = p; }
+    for (int i = lane; i < npc; i += 32) {
+      const int lr = i / cw, lc = i - lr * cw;
+      float x, y, z;
+      if (MODE == 0) { x = CX[i]; y = CY[i]; z = CZ[i]; }
+      else {
+        if (MODE == 1) z = __ldg(P.depth + dbase + (long long)lr * P.depth_rs + lc);
+        else z = (float)__ldg(P.depth16 + dbase + (long long)lr * P.depth_rs + lc) * P.depth_factor;
+        xy_from_depth(C, z, col0 + (double)lc, row0 + (double)lr, x, y);
       }
-    }
-    if (CYL && anyc && z > 0.f) {
-      // point-to-axis distance minus radius (CAPE.cpp:375-385): float cross / norm, double divide
-      const CylEq* ceq = P.cyl_eq + (long long)f * (kMaxPlanes + 1);
-#pragma unroll
+      float best = __uint_as_float(0x64646464u);
+      int lab = 0;
+  #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        uint32_t b = cbits[k];
+        uint32_t b = bits[k];
         while (b) {
           const int p = k * 32 + __ffs(b);
           b &= b - 1;
-          const CylEq& e = ceq[p];
-          const float q0 = x - e.p2[0], q1 = y - e.p2[1], q2 = z - e.p2[2];
-          const float c0 = e.dir[1] * q2 - e.dir[2] * q1, c1 = e.dir[2] * q0 - e.dir[0] * q2, c2 = e.dir[0] * q1 - e.dir[1] * q0;
-          const float nrm = sqrtf(c0 * c0 + (c1 * c1 + c2 * c2));
-          float dist = (float)((double)nrm / e.n12 - e.radius);
-          dist = dist * dist;
-          if (dist < e.maxd && dist < best) { best = dist; lab = 50 + p; }
+          const float4 e = eq[p];
+          const float v = x * e.x + y * e.y + z * e.z + e.w;
+          const float dist = v * v;
+          if (dist < maxd[p] && dist < best) { best = dist; lab = p; }
         }
       }
+      if (CYL && anyc && z > 0.f) {
+        // point-to-axis distance minus radius (CAPE.cpp:375-385): float cross / norm, double divide
+        const CylEq* ceq = P.cyl_eq + (long long)f * (kMaxPlanes + 1);
+  #pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint32_t b = cbits[k];
+          while (b) {
+            const int p = k * 32 + __ffs(b);
+            b &= b - 1;
+            const CylEq& e = ceq[p];
+            const float q0 = x - e.p2[0], q1 = y - e.p2[1], q2 = z - e.p2[2];
+            const float c0 = e.dir[1] * q2 - e.dir[2] * q1, c1 = e.dir[2] * q0 - e.dir[0] * q2, c2 = e.dir[0] * q1 - e.dir[1] * q0;
+            const float nrm = sqrtf(c0 * c0 + (c1 * c1 + c2 * c2));
+            float dist = (float)((double)nrm / e.n12 - e.radius);
+            dist = dist * dist;
+            if (dist < e.maxd && dist < best) { best = dist; lab = 50 + p; }
+          }
+        }
+      }
+      out[(long long)lr * P.W + lc] = (uint8_t)lab;
     }
-    out[(long long)lr * P.W + lc] = (uint8_t)lab;
   }
 }
 
-__global__ void k_cape_clear_margin(const CapeDev* __restrict__ Pp, int f0, int nframes) {
-  // pixels outside the last full cell row/column are never labelled
-  const CapeDev& P = *Pp;
-  const long long N = (long long)P.H * P.W;
-  const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx0 >= N * nframes) return;
-  const long long idx = idx0 + (long long)f0 * N;
-  const int p = (int)(idx % N);
-  const int r = p / P.W, c = p - r * P.W;
-  if (r >= P.ncy * P.ch || c >= P.ncx * P.cw) P.seg[idx] = 0;
-}
 
 }  // namespace drfe
 
@@ -1781,7 +1842,8 @@ struct drfe_cape {
   float* d_depth = nullptr;   // staging for host depth
   size_t grid_smem = 0;
   int last_frames = 0;
-  bool pending = false, margin = false;
+  bool pending = false;
+  int sm_count = 148;
   bool cloud_valid = false;      // hd.cloud holds the cell-major cloud of the last enqueue (given by the caller, or materialised on demand)
   StageTimer timer;
   ChunkPipe pipe;
@@ -1853,7 +1915,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   D.H = pr->depth_height; D.W = pr->depth_width; D.cw = pr->cell_width; D.ch = pr->cell_height;
   D.ncx = D.W / D.cw; D.ncy = D.H / D.ch; D.ncells = D.ncx * D.ncy; D.npc = D.cw * D.ch; D.B = max_batch;
   D.min_cos = pr->min_cos_angle_4_merge; D.max_merge_dist = pr->max_merge_dist;
-  h->margin = (D.ncx * D.cw != D.W) || (D.ncy * D.ch != D.H);
+  { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount; }
   const size_t N = (size_t)D.H * D.W, B = max_batch, nc = D.ncells;
   int rc = DRFE_OK;
   auto fail = [&](int code) { drfe_cape_destroy(h); return code; };
@@ -1898,6 +1960,9 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   rc |= cape_alloc(h, &D.plane_maxd, (size_t)(kMaxPlanes + 1) * B);
   rc |= cape_alloc(h, &D.nplanes, B);
   rc |= cape_alloc(h, &D.seg, N * B);
+  rc |= cape_alloc(h, &D.cell_label, nc * B);
+  rc |= cape_alloc(h, &D.border_list, nc * B);
+  rc |= cape_alloc(h, &D.border_count, 1);
   rc |= cape_alloc(h, &D.status, 1);
   rc |= cape_alloc(h, &h->d_depth, N * B);
   rc |= cape_alloc(h, &h->dd, 1);
@@ -1982,15 +2047,22 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   if (h->hd.cyl) DRFE_LAUNCH((k_cape_grid<128, true>), n, 128, h->grid_smem, st, h->dd, f0);
   else DRFE_LAUNCH((k_cape_grid<128, false>), n, 128, h->grid_smem, st, h->dd, f0);
   if (timed) h->timer.mark("grid", st);
-  if (h->margin) {
-    const long long tot = (long long)h->hd.H * h->hd.W * n;
-    DRFE_LAUNCH(k_cape_clear_margin, (unsigned)((tot + 255) / 256), 256, 0, st, h->dd, f0, n);
-  }
-#define DRFE_REFINE(CYL, M) DRFE_LAUNCH((k_cape_refine<CYL, M>), (ncell_total * 32 + 255) / 256, 256, 0, st, h->dd, f0, n)
+  {
+    DRFE_CUDA(cudaMemsetAsync(h->hd.border_count, 0, sizeof(int), st));
+    if (h->hd.cyl) DRFE_LAUNCH(k_cape_refine_plan<true>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
+    else DRFE_LAUNCH(k_cape_refine_plan<false>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
+    auto magic = [](unsigned d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };
+    const unsigned q = (unsigned)(h->hd.W + 3) / 4;
+    DRFE_LAUNCH(k_cape_paint, dim3((q + 63) / 64, (unsigned)(h->hd.H + 3) / 4, (unsigned)n), dim3(64, 4), 0, st, h->dd, f0, magic((unsigned)h->hd.cw),
+                magic((unsigned)h->hd.ch));
+    // warps loop over the list of border cells (its length is only known on the device): enough blocks to fill the GPU
+    const int blocks = std::min((ncell_total + kBorderWarps - 1) / kBorderWarps, h->sm_count * 10);
+#define DRFE_REFINE(CYL, M) DRFE_LAUNCH((k_cape_refine_border<CYL, M>), blocks, kBorderWarps * 32, 0, st, h->dd)
 #define DRFE_REFINE_MODE(CYL) do { if (mode == 2) DRFE_REFINE(CYL, 2); else if (mode == 1) DRFE_REFINE(CYL, 1); else DRFE_REFINE(CYL, 0); } while (0)
-  if (h->hd.cyl) DRFE_REFINE_MODE(true); else DRFE_REFINE_MODE(false);
+    if (h->hd.cyl) DRFE_REFINE_MODE(true); else DRFE_REFINE_MODE(false);
 #undef DRFE_REFINE_MODE
 #undef DRFE_REFINE
+  }
   if (timed) h->timer.mark("refine", st);
   return DRFE_OK;
 }
