@@ -82,6 +82,7 @@ SYMBOLS = [
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
     "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
+    "drfe_resizer_create", "drfe_resizer_destroy", "drfe_resizer_stream", "drfe_resizer_sync", "drfe_resize",
     "drfe_pool_create", "drfe_pool_destroy", "drfe_pool_num_devices", "drfe_pool_max_keypoints", "drfe_pool_extract_batch",
     "drfe_pool_device_times", "drfe_host_alloc", "drfe_host_free", "drfe_host_register", "drfe_host_unregister",
 ]
@@ -171,6 +172,12 @@ def lib():
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
     L.drfe_cape_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
+    L.drfe_resizer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.drfe_resizer_destroy.argtypes = [vp]
+    L.drfe_resizer_stream.argtypes = [vp]
+    L.drfe_resizer_stream.restype = vp
+    L.drfe_resizer_sync.argtypes = [vp]
+    L.drfe_resize.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, sz, sz, C.c_int, vp, sz, sz, C.c_int]
     L.drfe_pool_create.argtypes = [C.POINTER(PoolParams), vp, C.c_int, C.POINTER(vp)]
     L.drfe_pool_destroy.argtypes = [vp]
     L.drfe_pool_num_devices.argtypes = [vp]
@@ -277,6 +284,34 @@ def host_array(shape, dtype, write_combined=False):
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
     buf._owner = _Owner(p)
     return np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+
+
+class Resizer:
+    """cv::resize(src, dst, Size(w, h)) (INTER_LINEAR) of System::TrackRGBD (System.cc:325-329), batched"""
+    PIX = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 2, np.dtype(np.float32): 5}
+
+    def __init__(self, src_w, src_h, dst_w, dst_h, max_batch=1, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.src, self.dst = (src_w, src_h), (dst_w, dst_h)
+        _check(self.L.drfe_resizer_create(src_w, src_h, dst_w, dst_h, max_batch, device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drfe_resizer_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __call__(self, images):
+        """images: (B, H, W) or (B, H, W, C) host array of uint8 / uint16 / float32 -> resized array of the same kind"""
+        a = np.ascontiguousarray(images)
+        ch = a.shape[3] if a.ndim == 4 else 1
+        out = np.empty((a.shape[0], self.dst[1], self.dst[0]) + ((ch,) if a.ndim == 4 else ()), a.dtype)
+        es = a.itemsize
+        _check(self.L.drfe_resize(self.h, a.shape[0], _ptr(a), self.PIX[a.dtype], ch, a.shape[2] * ch * es, a.shape[1] * a.shape[2] * ch * es, MEM_HOST,
+                                  _ptr(out), self.dst[0] * ch * es, self.dst[0] * self.dst[1] * ch * es, MEM_HOST))
+        return out
 
 
 class Pool:

@@ -434,6 +434,24 @@ int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16);
 int drfe_cape_set_profiling(drfe_cape* h, int on);
 int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages);
 
+/* ------------------------------------------------------------------ input resize (next-4 of SURVEY.md 8f)
+ * cv::resize(im, IM, Size(640,480)) and cv::resize(depthmap, Depthmap, Size(640,480)) of System::TrackRGBD (reference
+ * src/System.cc:325-329; default INTER_LINEAR), batched: OpenCV's own arithmetic — 11-bit fixed point for 8U (1, 3 or 4
+ * channels), separately rounded float products for 16U (saturate_cast of cvRound) and 32F.  Source and destination may each be
+ * host or device memory; with a device destination the call is asynchronous on the resizer's stream (drfe_resizer_sync, or
+ * drfe_stream_wait_event on drfe_resizer_stream, before another handle consumes it — e.g. drfe_orb_enqueue_color or
+ * drfe_cape_enqueue_depth_u16 with DRFE_MEM_DEVICE).  Strides are in BYTES. */
+#define DRFE_PIX_U8 0
+#define DRFE_PIX_U16 2
+#define DRFE_PIX_F32 5
+typedef struct drfe_resizer drfe_resizer;
+int drfe_resizer_create(int src_width, int src_height, int dst_width, int dst_height, int max_batch, int device, drfe_resizer** out);
+int drfe_resizer_destroy(drfe_resizer* h);
+void* drfe_resizer_stream(drfe_resizer* h);
+int drfe_resizer_sync(drfe_resizer* h);
+int drfe_resize(drfe_resizer* h, int nframes, const void* src, int pixel_type, int channels, size_t src_row_stride, size_t src_frame_stride,
+                int src_mem_kind, void* dst, size_t dst_row_stride, size_t dst_frame_stride, int dst_mem_kind);
+
 /* ------------------------------------------------------------------ several devices
  * Frames are independent (ORBextractor keeps no state across frames, Frame.cc:124-134 builds a fresh
  * PlaneDetection per frame), so a pool cuts a batch of host frames into contiguous blocks, one per device; every

@@ -190,6 +190,56 @@ def resize_linear(src, dw, dh):
     return dst
 
 
+def _resize_tabs(ssize, dsize, vertical=False):
+    """OpenCV resize.cpp (INTER_LINEAR): fx = (float)((dx + 0.5) * scale - 0.5), sx = floor(fx), fx -= sx.  Horizontally an
+    index outside the image is clamped AND its fraction set to 0 (xofs / alpha); vertically only the two ROW indices are
+    clipped (clip(sy0 - ksize2 + 1 + k, 0, ssize.height)) while beta keeps the fraction — which differs when upscaling."""
+    scale = 1.0 / (dsize / ssize)
+    d = np.arange(dsize)
+    fx = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    sx = np.floor(fx).astype(np.int64)
+    fx = (fx - sx.astype(np.float32)).astype(np.float32)
+    if vertical:
+        return np.clip(sx, 0, ssize - 1), np.clip(sx + 1, 0, ssize - 1), (np.float32(1) - fx).astype(np.float32), fx
+    lo = sx < 0
+    fx[lo] = 0; sx[lo] = 0
+    hi = sx >= ssize - 1
+    fx[hi] = 0; sx[hi] = ssize - 1
+    return sx, np.minimum(sx + 1, ssize - 1), (np.float32(1) - fx).astype(np.float32), fx
+
+
+def resize_input(src, dw, dh):
+    """cv::resize(src, dst, Size(dw, dh)) with the default INTER_LINEAR as System::TrackRGBD applies it to the colour image
+    and the depth map (reference src/System.cc:325-329) — numpy restatement of OpenCV's resizeGeneric_ (HResizeLinear /
+    VResizeLinear): 8U with 11-bit fixed-point coefficients, 16U / 32F with separately rounded float products, 16U stored
+    through saturate_cast<ushort>(cvRound).  An exact 2 x 2 reduction is switched to INTER_AREA by cv::resize (resize.cpp:
+    "if (interpolation == INTER_LINEAR && is_area_fast && iscale_x == 2 && iscale_y == 2) interpolation = INTER_AREA"): the
+    rounded integer mean (a + b + c + d + 2) >> 2 for 16U; for 8U and 32F the bilinear expressions give the same values.
+    src: (H, W) or (H, W, C) of uint8 / uint16 / float32."""
+    src = np.asarray(src)
+    sh, sw = src.shape[:2]
+    if src.dtype == np.uint16 and sw == 2 * dw and sh == 2 * dh:
+        q = src.astype(np.int64)
+        return ((q[0::2, 0::2] + q[0::2, 1::2] + q[1::2, 0::2] + q[1::2, 1::2] + 2) >> 2).astype(np.uint16)
+    x0, x1, a0, a1 = _resize_tabs(sw, dw)
+    y0, y1, b0, b1 = _resize_tabs(sh, dh, vertical=True)
+    s = src if src.ndim == 3 else src[:, :, None]
+    if src.dtype == np.uint8:
+        f32 = np.float32
+        c0, c1 = np.rint(a0 * f32(2048)).astype(np.int64), np.rint(a1 * f32(2048)).astype(np.int64)
+        e0, e1 = np.rint(b0 * f32(2048)).astype(np.int64), np.rint(b1 * f32(2048)).astype(np.int64)
+        s = s.astype(np.int64)
+        T = s[:, x0] * c0[None, :, None] + s[:, x1] * c1[None, :, None]
+        D = (((e0[:, None, None] * (T[y0] >> 4)) >> 16) + ((e1[:, None, None] * (T[y1] >> 4)) >> 16) + 2) >> 2
+        out = D.astype(np.uint8)
+    else:
+        s = s.astype(np.float32)
+        T = ((s[:, x0] * a0[None, :, None]).astype(np.float32) + (s[:, x1] * a1[None, :, None]).astype(np.float32)).astype(np.float32)
+        D = ((T[y0] * b0[:, None, None]).astype(np.float32) + (T[y1] * b1[:, None, None]).astype(np.float32)).astype(np.float32)
+        out = np.clip(np.rint(D), 0, 65535).astype(np.uint16) if src.dtype == np.uint16 else D
+    return out if src.ndim == 3 else out[:, :, 0]
+
+
 def border101(src, b):
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.empty((src.shape[0] + 2 * b, src.shape[1] + 2 * b), np.uint8)
