@@ -549,7 +549,13 @@ def main():
                 del rig.d_gray, rig.d_depth
                 pool = drfe.Pool(list(range(ndev)), nfeatures=wl.nfeat, width=W, height=H, cell=wl.cell, cylinder_detection=wl.cyl,
                                  min_cos=MIN_COS, max_merge_dist=wl.max_merge, max_batch=B * ndev, chunk_frames=args.chunk)
-                reps = lambda a: a if ndev == 1 else pin(np.concatenate([a] * ndev))   # noqa: E731  (rank 0's frames, once per device)
+                def reps(a):                                       # rank 0's frames once per device, in pinned memory of the same dtype
+                    if ndev == 1:
+                        return a
+                    out = drfe.host_array((a.shape[0] * ndev,) + a.shape[1:], a.dtype)
+                    for i in range(ndev):
+                        out[i * a.shape[0]:(i + 1) * a.shape[0]] = a
+                    return out
                 pg, pd = reps(h_gray), reps(h_depth16)
                 out = {"kps": reps(h_kps), "desc": reps(h_desc), "counts": reps(h_cnt), "seg": reps(h_seg), "planes": reps(h_planes),
                        "nplanes": reps(h_npl)}

@@ -13,6 +13,7 @@
 //   k_cape_refine  one warp per cell: per-pixel boundary refinement + seg_output in image
 //                  layout (CAPE.cpp:294-319, 395-432)
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -1833,6 +1834,201 @@ static __global__ void __launch_bounds__(kPtsWarps * 32) k_cape_plane_points(con
   }
 }
 
+
+// ------------------------------------------------------------------ 5 cm voxel filter of the per-plane point lists
+// pcl::VoxelGrid<PointT>::applyFilter (PCL 1.9, pcl/filters/impl/voxel_grid.hpp) as Frame::ComputePlanes_CAPE runs it on
+// every plane_cloud[i] (reference src/Frame.cc:1121-1125: setLeafSize(0.05, 0.05, 0.05), default downsample_all_data): bounding
+// box, leaf index per point, points ordered by leaf, one centroid per leaf (float sum / float count, AccumulatorXYZ), leaves in
+// ascending index order.  Declared: a leaf's points are summed in ascending input order (PCL's std::sort leaves that order to
+// the library).  One segment = one plane of one frame; a CTA works on one segment at a time:
+//   k_voxel_sort       bounds (min / max reduction), leaf index of every point, stable LSD radix sort of (leaf, point) by 8-bit
+//                      digits — only as many passes as the box's leaf count needs —, then the leaf heads are counted and listed;
+//   k_voxel_centroids  one thread per leaf adds its points in order and writes the centroid at the plane's offset in the frame.
+struct VoxSeg { int nvox, unfiltered, sorted_in_b, pad; };
+static const int kVoxThreads = 1024;
+
+__global__ void __launch_bounds__(kVoxThreads) k_voxel_sort(const float* __restrict__ pts, const int* __restrict__ offs, const int* __restrict__ nplanes, int N,
+                                                            float inv_leaf, uint32_t* __restrict__ keyA, uint32_t* __restrict__ valA,
+                                                            uint32_t* __restrict__ keyB, uint32_t* __restrict__ valB, VoxSeg* __restrict__ segs) {
+  __shared__ uint32_t s_cnt[32][256];                           // per warp and digit: count, then output position
+  __shared__ uint32_t s_base[256];
+  __shared__ float s_red[6][32];
+  __shared__ int s_i[8];
+  const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int np = min(nplanes[f], kMaxPlanes);
+  const int* fo = offs + (long long)f * (kMaxPlanes + 1);
+  for (int p = blockIdx.x; p < np; p += gridDim.x) {
+    const int s0 = fo[p], n = fo[p + 1] - s0;
+    VoxSeg* seg = segs + (long long)f * kMaxPlanes + p;
+    const float* P3 = pts + ((long long)f * N + s0) * 3;
+    uint32_t* kA = keyA + (long long)f * N + s0; uint32_t* vA = valA + (long long)f * N + s0;
+    uint32_t* kB = keyB + (long long)f * N + s0; uint32_t* vB = valB + (long long)f * N + s0;
+    if (n <= 0) { if (tid == 0) { seg->nvox = 0; seg->unfiltered = 0; seg->sorted_in_b = 0; } continue; }
+    // ---- getMinMax3D
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = tid; i < n; i += kVoxThreads)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const float v = P3[3 * i + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xFFFFFFFFu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xFFFFFFFFu, mx[k], o)); }
+      if (lane == 0) { s_red[k][wid] = mn[k]; s_red[3 + k][wid] = mx[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      mn[k] = s_red[k][0]; mx[k] = s_red[3 + k][0];
+      for (int w = 1; w < 32; ++w) { mn[k] = fminf(mn[k], s_red[k][w]); mx[k] = fmaxf(mx[k], s_red[3 + k][w]); }
+    }
+    // "Leaf size is too small for the input dataset": more than INT32_MAX leaves in the box -> the input is returned as it is
+    const long long d0 = (long long)(__fmul_rn(__fsub_rn(mx[0], mn[0]), inv_leaf)) + 1, d1 = (long long)(__fmul_rn(__fsub_rn(mx[1], mn[1]), inv_leaf)) + 1,
+                    d2 = (long long)(__fmul_rn(__fsub_rn(mx[2], mn[2]), inv_leaf)) + 1;
+    const bool unfiltered = (double)d0 * (double)d1 * (double)d2 > 2147483647.0;
+    if (unfiltered) {
+      if (tid == 0) { seg->nvox = n; seg->unfiltered = 1; seg->sorted_in_b = 0; }
+      __syncthreads();
+      continue;
+    }
+    int min_b[3], mul[3];
+    {
+      int div_b[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        min_b[k] = (int)floorf(__fmul_rn(mn[k], inv_leaf));
+        div_b[k] = (int)floorf(__fmul_rn(mx[k], inv_leaf)) - min_b[k] + 1;
+      }
+      mul[0] = 1; mul[1] = div_b[0]; mul[2] = div_b[0] * div_b[1];
+      const uint32_t total = (uint32_t)(div_b[0] * div_b[1] * div_b[2]);
+      if (tid == 0) s_i[0] = total > 1 ? 32 - __clz(total - 1) : 0;   // bits a leaf index needs
+    }
+    // ---- leaf index of every point
+    for (int i = tid; i < n; i += kVoxThreads) {
+      int idx = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) idx += (int)__fsub_rn(floorf(__fmul_rn(P3[3 * i + k], inv_leaf)), (float)min_b[k]) * mul[k];
+      kA[i] = (uint32_t)idx; vA[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    const int passes = (s_i[0] + 7) >> 3;
+    uint32_t* ki = kA; uint32_t* vi = vA; uint32_t* ko = kB; uint32_t* vo = vB;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int shift = 8 * pass;
+      if (tid < 256) s_base[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kVoxThreads) atomicAdd(&s_base[(ki[i] >> shift) & 255u], 1u);
+      __syncthreads();
+      if (wid == 0) {                                            // exclusive scan of the 256 digit counts
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = s_base[lane * 8 + j]; sum += c[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s_base[lane * 8 + j] = run; run += c[j]; }
+      }
+      __syncthreads();
+      for (int t0 = 0; t0 < n; t0 += kVoxThreads) {
+        for (int j = tid; j < 32 * 256; j += kVoxThreads) (&s_cnt[0][0])[j] = 0;
+        __syncthreads();
+        const int i = t0 + tid;
+        const bool act = i < n;
+        const uint32_t key = act ? ki[i] : 0u, val = act ? vi[i] : 0u;
+        const uint32_t dgt = act ? ((key >> shift) & 255u) : 256u;
+        const unsigned m = __match_any_sync(0xFFFFFFFFu, dgt);
+        const int lower = __popc(m & lt);
+        if (act && lower == 0) s_cnt[wid][dgt] = (uint32_t)__popc(m);
+        __syncthreads();
+        if (tid < 256) {                                         // digit tid: positions of the warps' groups, in warp order (stable)
+          uint32_t run = s_base[tid];
+          for (int w = 0; w < 32; ++w) { const uint32_t c = s_cnt[w][tid]; s_cnt[w][tid] = run; run += c; }
+          s_base[tid] = run;
+        }
+        __syncthreads();
+        if (act) { const uint32_t pos = s_cnt[wid][dgt] + (uint32_t)lower; ko[pos] = key; vo[pos] = val; }
+        __syncthreads();
+      }
+      uint32_t* t = ki; ki = ko; ko = t; t = vi; vi = vo; vo = t;
+    }
+    // ---- leaf heads: count them and list their positions in the other key buffer
+    int nv = 0;
+    for (int t0 = 0; t0 < n; t0 += kVoxThreads) {
+      const int i = t0 + tid;
+      const bool head = i < n && (i == 0 || ki[i] != ki[i - 1]);
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, head);
+      if (lane == 0) s_cnt[0][wid] = (uint32_t)__popc(b);
+      __syncthreads();
+      int before = 0, tot = 0;
+      for (int w = 0; w < 32; ++w) { const int c = (int)s_cnt[0][w]; if (w < wid) before += c; tot += c; }
+      if (head) ko[nv + before + __popc(b & lt)] = (uint32_t)i;
+      nv += tot;
+      __syncthreads();
+    }
+    if (tid == 0) { seg->nvox = nv; seg->unfiltered = 0; seg->sorted_in_b = (ki == kB) ? 1 : 0; }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_voxel_centroids(const float* __restrict__ pts, const int* __restrict__ offs, const int* __restrict__ nplanes, int N,
+                                                         const uint32_t* __restrict__ keyA, const uint32_t* __restrict__ valA, const uint32_t* __restrict__ keyB,
+                                                         const uint32_t* __restrict__ valB, const VoxSeg* __restrict__ segs, float* __restrict__ out,
+                                                         int* __restrict__ out_offs) {
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const int np = min(nplanes[f], kMaxPlanes);
+  const int* fo = offs + (long long)f * (kMaxPlanes + 1);
+  const VoxSeg* fs = segs + (long long)f * kMaxPlanes;
+  int* oo = out_offs + (long long)f * (kMaxPlanes + 1);
+  for (int p = blockIdx.x; p < np; p += gridDim.x) {
+    int start = 0;
+    for (int q = 0; q < p; ++q) start += fs[q].nvox;             // (a few planes per frame)
+    const VoxSeg sg = fs[p];
+    if (tid == 0) { oo[p] = start; if (p == np - 1) oo[np] = start + sg.nvox; }
+    const int s0 = fo[p], n = fo[p + 1] - s0;
+    const float* P3 = pts + ((long long)f * N + s0) * 3;
+    float* O = out + ((long long)f * N + start) * 3;
+    if (sg.unfiltered) {
+      for (int i = tid; i < 3 * n; i += 256) O[i] = P3[i];
+      continue;
+    }
+    const uint32_t* vals = (sg.sorted_in_b ? valB : valA) + (long long)f * N + s0;
+    const uint32_t* heads = (sg.sorted_in_b ? keyA : keyB) + (long long)f * N + s0;
+    for (int j = tid; j < sg.nvox; j += 256) {
+      const int a = (int)heads[j], b = j + 1 < sg.nvox ? (int)heads[j + 1] : n;
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      for (int i = a; i < b; ++i) { const float* q = P3 + 3 * vals[i]; sx = sx + q[0]; sy = sy + q[1]; sz = sz + q[2]; }
+      const float cnt = (float)(b - a);
+      O[3 * j] = __fdiv_rn(sx, cnt); O[3 * j + 1] = __fdiv_rn(sy, cnt); O[3 * j + 2] = __fdiv_rn(sz, cnt);
+    }
+  }
+  if (np == 0 && blockIdx.x == 0 && tid == 0) oo[0] = 0;
+}
+
+// ------------------------------------------------------------------ the 1/3-resolution cloud of Frame::ComputePlanes_CAPE
+// (reference src/Frame.cc:1153-1172): every third pixel of every third row, z = d > max_point_dist ? 0 : d,
+// x = (n - cx) * z / fx in float arithmetic; out [frames][ceil(H/3)][ceil(W/3)][3]
+template <int MODE>
+__global__ void __launch_bounds__(256) k_cape_third_cloud(const CapeDev* __restrict__ Pp, int nframes, float max_point_dist, float* __restrict__ out) {
+  const CapeDev& P = *Pp;
+  const int w3 = (P.W + 2) / 3, h3 = (P.H + 2) / 3;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)nframes * w3 * h3) return;
+  const int f = (int)(t / (w3 * h3));
+  const int rem = (int)(t - (long long)f * w3 * h3);
+  const int r = rem / w3, c = rem - r * w3;
+  const int m = 3 * r, n = 3 * c;
+  float d;
+  if (MODE == 1) d = __ldg(P.depth + (long long)f * P.depth_fs + (long long)m * P.depth_rs + n);
+  else d = (float)__ldg(P.depth16 + (long long)f * P.depth_fs + (long long)m * P.depth_rs + n) * P.depth_factor;
+  const float z = d > max_point_dist ? 0.f : d;
+  float* o = out + 3 * t;
+  o[0] = __fdiv_rn(__fmul_rn(__fsub_rn((float)n, P.cx), z), P.fx);
+  o[1] = __fdiv_rn(__fmul_rn(__fsub_rn((float)m, P.cy), z), P.fy);
+  o[2] = z;
+}
+
 struct drfe_cape {
   int device = 0, max_batch = 0;
   drfe_cape_params prm{};
@@ -1851,6 +2047,9 @@ struct drfe_cape {
   float* d_plane_pts = nullptr;  // [B][H*W][3] per-plane point lists (allocated by the first drfe_cape_plane_points)
   int* d_plane_offs = nullptr;   // [B][kMaxPlanes+1]
   std::vector<int> h_plane_offs;
+  uint32_t* d_vox_key[2] = {nullptr, nullptr}; uint32_t* d_vox_val[2] = {nullptr, nullptr};   // drfe_cape_plane_points_voxel: sort buffers [B][H*W]
+  VoxSeg* d_vox_seg = nullptr; float* d_vox_out = nullptr; int* d_vox_offs = nullptr;          // per (frame, plane) records; centroids [B][H*W][3]; offsets
+  float* d_third = nullptr;      // drfe_cape_third_cloud
   int batch_plane_cap = 0;
   std::vector<void*> allocs;
 };
@@ -2316,16 +2515,12 @@ int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int p
   return DRFE_OK;
 }
 
-int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
-  NvtxRange nvtx_("drfe_cape_plane_points");
-  if (!h || !points || !offsets || plane_cap < 1) { set_error("drfe_cape_plane_points: bad argument"); return DRFE_ERR_ARG; }
-  if (!h->pending) { set_error("drfe_cape_plane_points: nothing enqueued"); return DRFE_ERR_STATE; }
-  DeviceScope ds(h->device);
-  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+// the per-plane point lists of the last batch on the device (h->d_plane_pts / d_plane_offs), no copy out
+static int cape_plane_points_device(drfe_cape* h) {
   cudaStream_t st = h->stream;
   const int nf = h->last_frames;
   const size_t N = (size_t)h->hd.H * h->hd.W;
-  if (h->pipe.active) { set_error("drfe_cape_plane_points: a batch call is in flight (drfe_cape_finish_batch first)"); return DRFE_ERR_STATE; }
+  if (h->pipe.active) { set_error("a batch call is in flight (drfe_cape_finish_batch first)"); return DRFE_ERR_STATE; }
   { const int rc = cape_materialize_cloud(h); if (rc != DRFE_OK) return rc; }
   if (!h->d_plane_pts) {
     if (cape_alloc(h, &h->d_plane_pts, (size_t)h->max_batch * N * 3)) return DRFE_ERR_CUDA;
@@ -2336,23 +2531,86 @@ int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, in
   auto magic = [](unsigned d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };
   DRFE_LAUNCH(k_cape_plane_points, nf, kPtsWarps * 32, kPtsWarps * (kMaxPlanes + 1) * sizeof(int), st, h->dd, 0, h->d_plane_pts, h->d_plane_offs,
               magic((unsigned)h->hd.W), magic((unsigned)h->hd.cw), magic((unsigned)h->hd.ch));
+  return DRFE_OK;
+}
+
+// offsets [nf][256] and points [nf][N][3] on the device -> the caller's arrays
+static int cape_points_out(drfe_cape* h, const char* who, const float* d_pts, const int* d_offs, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  const size_t N = (size_t)h->hd.H * h->hd.W;
   int* ho = h->h_plane_offs.data();
-  DRFE_CUDA(cudaMemcpyAsync(ho, h->d_plane_offs, (size_t)nf * (kMaxPlanes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaMemcpyAsync(ho, d_offs, (size_t)nf * (kMaxPlanes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   std::vector<int> np(nf);
   DRFE_CUDA(cudaMemcpyAsync(np.data(), h->hd.nplanes, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   for (int f = 0; f < nf; ++f) {
     const int n = std::min(np[f], kMaxPlanes);
-    if (n > plane_cap) { set_error("drfe_cape_plane_points: frame %d has %d planes, plane_cap is %d", f, n, plane_cap); return DRFE_ERR_CAPACITY; }
+    if (n > plane_cap) { set_error("%s: frame %d has %d planes, plane_cap is %d", who, f, n, plane_cap); return DRFE_ERR_CAPACITY; }
     const int* src = ho + (size_t)f * (kMaxPlanes + 1);
     int* dst = offsets + (size_t)f * (plane_cap + 1);
     for (int i = 0; i <= n; ++i) dst[i] = src[i];
     for (int i = n + 1; i <= plane_cap; ++i) dst[i] = src[n];
-    if ((size_t)src[n] > cap_per_frame) { set_error("drfe_cape_plane_points: frame %d has %d plane points, cap_per_frame is %zu", f, src[n], cap_per_frame); return DRFE_ERR_CAPACITY; }
+    if ((size_t)src[n] > cap_per_frame) { set_error("%s: frame %d has %d plane points, cap_per_frame is %zu", who, f, src[n], cap_per_frame); return DRFE_ERR_CAPACITY; }
     if (src[n] > 0)
-      DRFE_CUDA(cudaMemcpyAsync(points + (size_t)f * cap_per_frame * 3, h->d_plane_pts + (size_t)f * N * 3, (size_t)src[n] * 3 * sizeof(float),
+      DRFE_CUDA(cudaMemcpyAsync(points + (size_t)f * cap_per_frame * 3, d_pts + (size_t)f * N * 3, (size_t)src[n] * 3 * sizeof(float),
                                 cudaMemcpyDeviceToHost, st));
   }
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
+  NvtxRange nvtx_("drfe_cape_plane_points");
+  if (!h || !points || !offsets || plane_cap < 1) { set_error("drfe_cape_plane_points: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_cape_plane_points: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  const int rc = cape_plane_points_device(h);
+  if (rc != DRFE_OK) return rc;
+  return cape_points_out(h, "drfe_cape_plane_points", h->d_plane_pts, h->d_plane_offs, points, cap_per_frame, offsets, plane_cap);
+}
+
+int drfe_cape_plane_points_voxel(drfe_cape* h, float leaf_size, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
+  NvtxRange nvtx_("drfe_cape_plane_points_voxel");
+  if (!h || !points || !offsets || plane_cap < 1 || !(leaf_size > 0.f)) { set_error("drfe_cape_plane_points_voxel: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_cape_plane_points_voxel: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  int rc = cape_plane_points_device(h);
+  if (rc != DRFE_OK) return rc;
+  const size_t N = (size_t)h->hd.H * h->hd.W, B = h->max_batch;
+  if (!h->d_vox_out) {
+    if (cape_alloc(h, &h->d_vox_key[0], B * N) || cape_alloc(h, &h->d_vox_key[1], B * N) || cape_alloc(h, &h->d_vox_val[0], B * N) ||
+        cape_alloc(h, &h->d_vox_val[1], B * N) || cape_alloc(h, &h->d_vox_seg, B * kMaxPlanes) || cape_alloc(h, &h->d_vox_offs, B * (kMaxPlanes + 1)) ||
+        cape_alloc(h, &h->d_vox_out, B * N * 3)) return DRFE_ERR_CUDA;
+  }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  const float inv_leaf = 1.0f / leaf_size;                        // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+  const dim3 grid(8, nf);                                         // up to 8 CTAs share a frame's planes
+  DRFE_LAUNCH(k_voxel_sort, grid, kVoxThreads, 0, st, h->d_plane_pts, h->d_plane_offs, h->hd.nplanes, (int)N, inv_leaf, h->d_vox_key[0], h->d_vox_val[0],
+              h->d_vox_key[1], h->d_vox_val[1], h->d_vox_seg);
+  DRFE_LAUNCH(k_voxel_centroids, grid, 256, 0, st, h->d_plane_pts, h->d_plane_offs, h->hd.nplanes, (int)N, h->d_vox_key[0], h->d_vox_val[0], h->d_vox_key[1],
+              h->d_vox_val[1], h->d_vox_seg, h->d_vox_out, h->d_vox_offs);
+  return cape_points_out(h, "drfe_cape_plane_points_voxel", h->d_vox_out, h->d_vox_offs, points, cap_per_frame, offsets, plane_cap);
+}
+
+int drfe_cape_third_cloud(drfe_cape* h, float max_point_dist, float* cloud) {
+  NvtxRange nvtx_("drfe_cape_third_cloud");
+  if (!h || !cloud) { set_error("drfe_cape_third_cloud: null argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || (!h->hd.depth && !h->hd.depth16)) { set_error("drfe_cape_third_cloud: no depth image enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  const size_t w3 = (h->hd.W + 2) / 3, h3 = (h->hd.H + 2) / 3, per = w3 * h3 * 3;
+  if (!h->d_third && cape_alloc(h, &h->d_third, per * h->max_batch)) return DRFE_ERR_CUDA;
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
+  const unsigned blocks = (unsigned)((w3 * h3 * nf + 255) / 256);
+  if (h->hd.depth16) DRFE_LAUNCH(k_cape_third_cloud<2>, blocks, 256, 0, st, h->dd, nf, max_point_dist, h->d_third);
+  else DRFE_LAUNCH(k_cape_third_cloud<1>, blocks, 256, 0, st, h->dd, nf, max_point_dist, h->d_third);
+  DRFE_CUDA(cudaMemcpyAsync(cloud, h->d_third, per * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }

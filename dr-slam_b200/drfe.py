@@ -81,7 +81,7 @@ SYMBOLS = [
     "drfe_cape_enqueue_depth_u16", "drfe_cape_process_depth_batch", "drfe_cape_finish_batch",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
-    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
+    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_plane_points_voxel", "drfe_cape_third_cloud", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
     "drfe_resizer_create", "drfe_resizer_destroy", "drfe_resizer_stream", "drfe_resizer_sync", "drfe_resize",
     "drfe_pool_create", "drfe_pool_destroy", "drfe_pool_num_devices", "drfe_pool_max_keypoints", "drfe_pool_extract_batch",
     "drfe_pool_device_times", "drfe_host_alloc", "drfe_host_free", "drfe_host_register", "drfe_host_unregister",
@@ -168,6 +168,8 @@ def lib():
     L.drfe_cape_get_grid_maps.argtypes = [vp, C.c_int, vp, vp]
     L.drfe_cape_cylinders_found.argtypes = [vp, vp]
     L.drfe_cape_plane_points.argtypes = [vp, vp, sz, vp, C.c_int]
+    L.drfe_cape_plane_points_voxel.argtypes = [vp, C.c_float, vp, sz, vp, C.c_int]
+    L.drfe_cape_third_cloud.argtypes = [vp, C.c_float, vp]
     L.drfe_cape_get_cyl_maps.argtypes = [vp, C.c_int, vp, vp]
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
@@ -749,6 +751,22 @@ class CAPE:
         offs = np.zeros((nf, plane_cap + 1), np.int32)
         _check(self.L.drfe_cape_plane_points(self.h, _ptr(pts), N, _ptr(offs), plane_cap))
         return pts, offs
+
+    def plane_points_voxel(self, leaf=0.05, nframes=None, plane_cap=255, cap_per_frame=None):
+        """pcl::VoxelGrid (leaf^3) of every plane's point list (Frame.cc:1121-1125): same layout as plane_points"""
+        nf = nframes or max(getattr(self, "_nframes", 1) or 1, 1)
+        N = cap_per_frame or self.H * self.W
+        pts = np.zeros((nf, N, 3), np.float32)
+        offs = np.zeros((nf, plane_cap + 1), np.int32)
+        _check(self.L.drfe_cape_plane_points_voxel(self.h, leaf, _ptr(pts), N, _ptr(offs), plane_cap))
+        return pts, offs
+
+    def third_cloud(self, max_point_dist, nframes=None):
+        """the 1/3-resolution cloud of Frame::ComputePlanes_CAPE (Frame.cc:1153-1172) of the last batch's depth"""
+        nf = nframes or max(getattr(self, "_nframes", 1) or 1, 1)
+        out = np.empty((nf, (self.H + 2) // 3, (self.W + 2) // 3, 3), np.float32)
+        _check(self.L.drfe_cape_third_cloud(self.h, max_point_dist, _ptr(out)))
+        return out
 
     def cylinders_found(self):
         """length of cylinder_segments_final per frame of the last call (CAPE.cpp:434-445)"""

@@ -404,6 +404,17 @@ int drfe_cape_download(drfe_cape* h, uint8_t* seg_out, drfe_plane* planes, int p
  * (cylinder labels) are not gathered: the reference indexes plane_cloud out of range for them. */
 int drfe_cape_plane_points(drfe_cape* h, float* points, size_t cap_per_frame, int* offsets,
                            int plane_cap);
+/* pcl::VoxelGrid<PointT> voxel; voxel.setLeafSize(l, l, l); voxel.filter(*coarseCloud) on every plane_cloud[i], as
+ * Frame::ComputePlanes_CAPE does with l = 0.05 right after the plane extraction (reference src/Frame.cc:1121-1125; PCL 1.9
+ * voxel_grid.hpp: one centroid per occupied leaf, leaves in ascending index order; a leaf's points are summed in input order —
+ * PCL's std::sort leaves that order open).  Runs on the point lists drfe_cape_plane_points builds, without moving them to the
+ * host: a 640x480 frame's 1.2 MB of plane points become a few thousand centroids.  Same output layout as drfe_cape_plane_points.
+ * A plane whose bounding box has more than INT32_MAX leaves comes back unfiltered, as in PCL. */
+int drfe_cape_plane_points_voxel(drfe_cape* h, float leaf_size, float* points, size_t cap_per_frame, int* offsets, int plane_cap);
+/* The 1/3-resolution cloud Frame::ComputePlanes_CAPE builds for its surface normals (reference src/Frame.cc:1153-1172) from the
+ * depth of the last batch: cloud [nframes][ceil(H/3)][ceil(W/3)][3], z = d > max_point_dist ? 0 : d, x = (n - cx) * z / fx in
+ * float.  (The normal estimation itself — pcl::IntegralImageNormalEstimation — is not part of this library.) */
+int drfe_cape_third_cloud(drfe_cape* h, float max_point_dist, float* cloud);
 int drfe_cape_cylinders_found(drfe_cape* h, int* counts); /* counts[f] = cylinder_segments_final.size() */
 int drfe_cape_sync(drfe_cape* h);
 void* drfe_cape_stream(drfe_cape* h);

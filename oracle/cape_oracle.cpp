@@ -31,6 +31,8 @@
 #include <algorithm>
 #include <array>
 #include <climits>
+#include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -738,6 +740,74 @@ int orc_cape_get_cyl_maps(void* h, int32_t* cyl_map, uint8_t* cyl_eroded_map) {
   memcpy(cyl_eroded_map, o->cyl_eroded_map.data(), o->ncells);
   return o->ncells;
 }
+// ---- pcl::VoxelGrid<PointT>::applyFilter on one plane_cloud (reference src/Frame.cc:1121-1125: leaf 0.05, default
+// downsample_all_data, min_points_per_voxel 0).  PCL is a third-party dependency that is not vendored in the reference
+// (CMakeLists.txt:59 asks for PCL 1.9); this restates the published algorithm of pcl/filters/impl/voxel_grid.hpp (1.9):
+//   getMinMax3D -> min_b / max_b = floor(min|max * inverse_leaf) per axis, div_b = max_b - min_b + 1;
+//   if the box has more than INT32_MAX leaves the input is returned unfiltered ("Leaf size is too small");
+//   leaf index of a point = sum_k (int)(floor(p_k * inverse_leaf_k) - (float)min_b_k) * divb_mul_k;
+//   points sorted by leaf index; per leaf the centroid = float sum of its points / (float)count (AccumulatorXYZ),
+//   leaves in ascending index order.
+// Declared: PCL sorts with std::sort, which leaves the order of the points INSIDE a leaf (and so the last bits of the
+// float sum) to the library's introsort; here a leaf's points are summed in ascending input index (a stable sort).
+// Returns the number of output points (n when unfiltered, *unfiltered = 1).
+int orc_voxel_grid(const float* xyz, int n, float leaf, float* out, int* unfiltered) {
+  *unfiltered = 0;
+  if (n <= 0) return 0;
+  const float inv = 1.0f / leaf;                                  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], xyz[3 * i + k]); mx[k] = std::max(mx[k], xyz[3 * i + k]); }
+  long long d[3];
+  for (int k = 0; k < 3; ++k) d[k] = (long long)((mx[k] - mn[k]) * inv) + 1;
+  if (d[0] * d[1] * d[2] > (long long)INT32_MAX) {
+    std::memcpy(out, xyz, (size_t)n * 3 * sizeof(float));
+    *unfiltered = 1;
+    return n;
+  }
+  int min_b[3], div_b[3];
+  for (int k = 0; k < 3; ++k) {
+    min_b[k] = (int)std::floor(mn[k] * inv);
+    div_b[k] = (int)std::floor(mx[k] * inv) - min_b[k] + 1;
+  }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  std::vector<std::pair<unsigned, int>> iv((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    int idx = 0;
+    for (int k = 0; k < 3; ++k) idx += (int)(std::floor(xyz[3 * i + k] * inv) - (float)min_b[k]) * mul[k];
+    iv[i] = std::make_pair((unsigned)idx, i);
+  }
+  std::stable_sort(iv.begin(), iv.end(), [](const std::pair<unsigned, int>& a, const std::pair<unsigned, int>& b) { return a.first < b.first; });
+  int total = 0;
+  for (size_t a = 0; a < iv.size();) {
+    size_t b = a + 1;
+    while (b < iv.size() && iv[b].first == iv[a].first) ++b;
+    float sx = 0.f, sy = 0.f, sz = 0.f;                            // AccumulatorXYZ: xyz starts at zero, += every point
+    for (size_t i = a; i < b; ++i) { sx += xyz[3 * iv[i].second]; sy += xyz[3 * iv[i].second + 1]; sz += xyz[3 * iv[i].second + 2]; }
+    const float cnt = (float)(b - a);
+    out[3 * total] = sx / cnt; out[3 * total + 1] = sy / cnt; out[3 * total + 2] = sz / cnt;
+    ++total;
+    a = b;
+  }
+  return total;
+}
+
+// ---- the 1/3-resolution cloud Frame::ComputePlanes_CAPE builds for the surface normals (reference src/Frame.cc:1153-1172):
+// every third pixel of every third row, p.z = d > max_point_dist ? 0 : d, p.x = (n - cx) * p.z / fx in FLOAT arithmetic
+// (int n converted to float; cx, fx are the Frame's float members).  out: ceil(H/3) x ceil(W/3) x 3.
+void orc_third_cloud(const float* depth, int width, int height, int row_stride, float fx, float fy, float cx, float cy, float max_point_dist,
+                     float* out) {
+  size_t o = 0;
+  for (int m = 0; m < height; m += 3)
+    for (int n = 0; n < width; n += 3) {
+      const float dd = depth[(size_t)m * row_stride + n];
+      const float z = dd > max_point_dist ? 0.f : dd;
+      out[o++] = ((float)n - cx) * z / fx;
+      out[o++] = ((float)m - cy) * z / fy;
+      out[o++] = z;
+    }
+}
+
 int orc_glibc_rand(uint32_t seed, int n, int32_t* out) {
   GlibcRand g(seed);
   for (int i = 0; i < n; ++i) out[i] = g.next();

@@ -100,6 +100,8 @@ def lib():
         L.orc_cape_cylinders_found.argtypes = [C.c_void_p]
         L.orc_cape_get_cyl_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_voxel_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, i32p]
+        L.orc_third_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         _lib = L
     return _lib
 
@@ -842,6 +844,26 @@ def search_by_bow_cpp(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv,
     nm = f(_p(kd), _p(ka), _p(kv), len(kd), len(kf_fv), _p(kn) if len(kn) else None, _p(ks), _p(kf), _p(fd), _p(fa), len(fd), len(f_fv),
            _p(fn) if len(fn) else None, _p(fs), _p(ff), float(nnratio), int(check_orientation), _p(km), _p(fm))
     return km, fm, nm
+
+
+def voxel_grid(xyz, leaf=0.05):
+    """pcl::VoxelGrid<PointT>::filter with setLeafSize(leaf, leaf, leaf) on an (n, 3) float32 point list (reference
+    src/Frame.cc:1121-1125) -> ((m, 3) centroids in ascending leaf order, unfiltered flag)"""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    out = np.empty_like(xyz)
+    flag = C.c_int32(0)
+    m = lib().orc_voxel_grid(_p(xyz), len(xyz), leaf, _p(out), C.byref(flag))
+    return out[:m].copy(), bool(flag.value)
+
+
+def third_cloud(depth, fx, fy, cx, cy, max_point_dist):
+    """the 1/3-resolution cloud of Frame::ComputePlanes_CAPE (reference src/Frame.cc:1153-1172) -> (ceil(H/3), ceil(W/3), 3)"""
+    depth = np.asarray(depth, np.float32)
+    assert depth.strides[1] == 4
+    H, W = depth.shape
+    out = np.empty(((H + 2) // 3, (W + 2) // 3, 3), np.float32)
+    lib().orc_third_cloud(_p(depth), W, H, depth.strides[0] // 4, fx, fy, cx, cy, max_point_dist, _p(out))
+    return out
 
 
 def glibc_rand(seed, n):
