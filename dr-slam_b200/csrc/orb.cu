@@ -1744,6 +1744,10 @@ struct drfe_orb {
   cudaStream_t stream = nullptr;
   uint8_t* d_gray = nullptr;   // staging for host inputs [B][H][W]
   cudaEvent_t ev_shared = nullptr;   // drfe_orb_frame_post_shared_depth
+  static const int kMaxSplit = 4;
+  int split = 1;                     // parts a long batch's kernel chains are cut into (orb_launch)
+  cudaStream_t aux[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
   void* d_rtab = nullptr; void* d_strips = nullptr;
   int nstrips = 0, blur_blocks = 0, max_node_cap = 0, max_lkp = 0;
@@ -1990,6 +1994,15 @@ static int orb_build(drfe_orb* h) {
   // ---- device memory
   const int B = h->max_batch;
   DRFE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    const char* e = getenv("DRFE_ORB_SPLIT");
+    h->split = e ? std::min(std::max(atoi(e), 1), (int)drfe_orb::kMaxSplit) : 1;
+    DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int p = 0; p + 1 < h->split; ++p) {
+      DRFE_CUDA(cudaStreamCreateWithFlags(&h->aux[p], cudaStreamNonBlocking));
+      DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming));
+    }
+  }
   if (dev_alloc(h, &D.pyr, (size_t)img_total + 256)) return DRFE_ERR_CUDA;
   if (dev_alloc(h, &D.blur, (size_t)blur_total + 256)) return DRFE_ERR_CUDA;
   if (dev_alloc(h, &D.cand, (size_t)cand_total * B)) return DRFE_ERR_CUDA;
@@ -2084,6 +2097,11 @@ int drfe_orb_destroy(drfe_orb* h) {
   for (void* p : h->allocs) cudaFree(p);
   h->timer.destroy();
   if (h->ev_shared) cudaEventDestroy(h->ev_shared);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int p = 0; p < drfe_orb::kMaxSplit - 1; ++p) {
+    if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]);
+    if (h->aux[p]) { cudaStreamSynchronize(h->aux[p]); cudaStreamDestroy(h->aux[p]); }
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DRFE_OK;
@@ -2120,9 +2138,8 @@ int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, in
 }
 
 // all kernels of frames [f0, f0 + n) on the handle's stream; src/rs/fs address frame 0 of the batch
-static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
+static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
   NvtxRange nvtx_("orb_launch");
-  cudaStream_t st = h->stream;
   h->post_valid = false;         // the keypoints drfe_orb_frame_post worked on are being replaced
   const OrbDev& D = h->hd;
   const int nl = D.nlevels;
@@ -2158,6 +2175,29 @@ static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long 
   if (timed) h->timer.mark("blur", st);
   DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kOdWarps * kOdG - 1) / (kOdWarps * kOdG), nl, n), kOdWarps * 32, 0, st, h->dd, f0);
   if (timed) h->timer.mark("orient_describe", st);
+  return DRFE_OK;
+}
+
+// A long batch is cut into `split` parts whose kernel chains run on separate streams (forked from and joined back into the
+// handle's stream): the latency-bound stages of one part (the quadtree's serial passes, 45 % of the SMs busy) then overlap the
+// issue-bound stages of the others.  DRFE_ORB_SPLIT sets the number of parts (default in orb_build).
+static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
+  const int parts = std::min(h->split, n / 32);
+  if (parts <= 1) return orb_launch_on(h, h->stream, f0, n, src, rs, fs, timed);
+  DRFE_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+  const int base = n / parts, extra = n % parts;
+  int first = f0 + base + (extra > 0 ? 1 : 0);
+  for (int p = 1; p < parts; ++p) {
+    const int np = base + (p < extra ? 1 : 0);
+    DRFE_CUDA(cudaStreamWaitEvent(h->aux[p - 1], h->ev_fork, 0));
+    const int rc = orb_launch_on(h, h->aux[p - 1], first, np, src, rs, fs, false);
+    if (rc != DRFE_OK) return rc;
+    DRFE_CUDA(cudaEventRecord(h->ev_join[p - 1], h->aux[p - 1]));
+    first += np;
+  }
+  const int rc = orb_launch_on(h, h->stream, f0, base + (extra > 0 ? 1 : 0), src, rs, fs, timed);
+  if (rc != DRFE_OK) return rc;
+  for (int p = 1; p < parts; ++p) DRFE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[p - 1], 0));
   return DRFE_OK;
 }
 

@@ -19,6 +19,7 @@ KEYS = [
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
     ("l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex%"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),

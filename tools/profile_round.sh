@@ -7,10 +7,11 @@ mkdir -p gpurun_out
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/${tag}_launches.log 2>&1
-# 13 ORB + 5 CAPE launches per step in prof_step (ORB first, then CAPE): skip the 2 warm-up steps of each
-ncu --set full --clock-control none --import-source on -k regex:'k_pyr_stream|k_pyr_level0|k_fast|k_quadtree|k_blur|k_orient' -s 26 -c 13 -f \
+# per step in prof_step: 12 ORB kernels matching the regex (level 0 + 7 resizes + FAST + quadtree + blur + orient/describe) and 7 CAPE
+# kernels (sums, fit, edges, grid, refine plan / paint / border); skip the 2 warm-up steps of each
+ncu --set full --clock-control none --import-source on -k regex:'k_pyr_stream|k_pyr_level0|k_fast|k_quadtree|k_blur|k_orient' -s 24 -c 12 -f \
     -o gpurun_out/${tag}_full_orb python tools/prof_step.py --steps 1 --only orb > gpurun_out/${tag}_full_orb.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_cape' -s 10 -c 5 -f \
+ncu --set full --clock-control none --import-source on -k regex:'k_cape' -s 14 -c 7 -f \
     -o gpurun_out/${tag}_full_cape python tools/prof_step.py --steps 1 --only cape > gpurun_out/${tag}_full_cape.log 2>&1
 python tools/prof_step.py > gpurun_out/${tag}_stages.txt 2>&1
 tail -n 2 gpurun_out/${tag}_stages.txt
