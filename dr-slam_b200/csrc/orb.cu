@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include "drfe_internal.h"
 
 namespace drfe {
@@ -92,6 +94,7 @@ struct OrbDev {
   int kp_cap;
   int* status;                      // bit 0: candidate overflow, bit 1: node overflow
   int fast_tp, fast_rows, fast_list_off, fast_list_cap;
+  int fast_tma2d;                   // the FAST tile comes by one tensor-map TMA load per strip
   int blur_blk_off[DRFE_MAX_LEVELS + 1];   // first k_blur block of each level
 };
 
@@ -369,6 +372,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// one 3-D tensor-map TMA load (cp.async.bulk.tensor, SASS UTMALDG): box of the level image {columns as 32-bit words, rows, 1 frame}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+// the per-level tensor maps of k_fast_strips: level image as {pitch / 4 words, rows, frames}, box {fast_tp / 4, hCell + 6, 1}
+struct FastMaps { CUtensorMap m[DRFE_MAX_LEVELS]; };
+
 // Full threshold-free score of the 4 pixels of quad g in interior row ry: returns the packed bytes
 // e = max(q + 1 - minTh, 0) of pixels 0..3.  tile32: strip rows as words, TP4 words per row.
 __device__ __forceinline__ uint32_t fast_eval_quad(const uint32_t* __restrict__ tile32, int TP4, int ry, int g, uint32_t kmin8) {
@@ -448,7 +460,7 @@ __device__ __forceinline__ uint32_t fast_compass_group(const uint32_t* __restric
 //      nothing (the minThFAST fallback, ORBextractor.cc:812-816), in arbitrary order (the
 //      quadtree orders by a key)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp, int f0) {
+__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp, int f0, const __grid_constant__ FastMaps maps) {
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const StripDev strip = P.strips[blockIdx.x];
@@ -468,8 +480,15 @@ __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restric
   if (tid == 0) { s_n = 0; s_nq = 0; mbar_init(&s_bar, 1); }
   for (int i = tid; i < kMaxStripCells; i += THREADS) s_ini[i] = 0;
   __syncthreads();
-  // ---- 1. TMA: one bulk copy per image row
-  {
+  // ---- 1. TMA: the strip's rows Y0-3 .. Y1+2 as ONE tensor-map load (box = {row pitch of the tile, cell height + 6 rows, this frame};
+  // rows past a short last strip and columns past the image are loaded or zero-filled and never looked at), issued by one thread.
+  // Without tensor maps (driver entry point missing): one bulk copy per row.
+  if (P.fast_tma2d) {
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, (uint32_t)TP * (uint32_t)(L.hCell + 6));
+      tma_load_3d(tile, &maps.m[strip.level], (kXOff + strip.x0) >> 2, kEdge + strip.y0 - 3, f, &s_bar);
+    }
+  } else {
     const uint32_t row_bytes = (uint32_t)((min(strip.xw + 2 * kEdge, L.w - strip.x0) + 15) & ~15);
     const uint8_t* src = roi_ptr(P, L, f) + (long long)(strip.y0 - 3) * L.pitch + strip.x0;
     if (tid == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nrows + 6));
@@ -1750,6 +1769,7 @@ struct drfe_orb {
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
   void* d_rtab = nullptr; void* d_strips = nullptr;
+  FastMaps fast_maps{};
   int nstrips = 0, blur_blocks = 0, max_node_cap = 0, max_lkp = 0;
   size_t fast_smem = 0, quad_smem = 0, pyr_smem = 0;
   int last_frames = 0;
@@ -2038,6 +2058,26 @@ static int orb_build(drfe_orb* h) {
   D.rtab = d_rtab; D.strips = d_strips;
   DRFE_CUDA(cudaMemset(D.pyr, 0, (size_t)img_total + 256));
   DRFE_CUDA(cudaMemset(D.status, 0, sizeof(int)));
+  // tensor maps of the level images for k_fast_strips (32-bit elements: a box may be at most 256 elements wide)
+  {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    bool ok = getenv("DRFE_FAST_NO_TMA2D") == nullptr && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+              fn != nullptr && qres == cudaDriverEntryPointSuccess && (D.fast_tp & 15) == 0 && D.fast_tp / 4 <= 256;
+    for (int l = 0; ok && l < nl; ++l) {
+      const LevelDev& L = D.lv[l];
+      const cuuint64_t dims[3] = {(cuuint64_t)(L.pitch / 4), (cuuint64_t)(L.rows + 1), (cuuint64_t)B};
+      const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.img_fstride};
+      const cuuint32_t box[3] = {(cuuint32_t)(D.fast_tp / 4), (cuuint32_t)(L.hCell + 6), 1u};
+      const cuuint32_t estr[3] = {1u, 1u, 1u};
+      ok = L.hCell + 6 <= 256 && L.hCell <= D.fast_rows &&
+           ((EncodeTiled)fn)(&h->fast_maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, D.pyr + L.img_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    D.fast_tma2d = ok ? 1 : 0;
+  }
   if (dev_alloc(h, &h->dd, 1)) return DRFE_ERR_CUDA;
   DRFE_CUDA(cudaMemcpy(h->dd, &D, sizeof(D), cudaMemcpyHostToDevice));
   DRFE_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
@@ -2167,7 +2207,7 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
     }
   }
   if (timed) h->timer.mark("pyramid", st);
-  DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0);
+  DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps);
   if (timed) h->timer.mark("fast", st);
   DRFE_LAUNCH(k_quadtree<256>, dim3(nl, n), 256, h->quad_smem, st, h->dd, f0);
   if (timed) h->timer.mark("quadtree", st);
