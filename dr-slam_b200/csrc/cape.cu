@@ -1508,32 +1508,46 @@ __global__ void __launch_bounds__(256) k_cape_refine_plan(const CapeDev* __restr
   if (border) P.border_list[atomicAdd(P.border_count, 1)] = make_int2(gid, (int)first32);
 }
 
-// grid (words of a row / 64, rows / 4, frames), block (64, 4); magic_* = ceil(2^32 / d) for d = cell width, cell height
+// grid (words of a row / 64, rows / (4 * kPaintRows), frames), block (64, 4): a thread owns one word column (4 pixels) of
+// kPaintRows consecutive rows and looks its cells' labels up again only when the cell row changes; magic_* = ceil(2^32 / d)
+// for d = cell width, cell height
+static const int kPaintRows = 5;
 __global__ void __launch_bounds__(256) k_cape_paint(const CapeDev* __restrict__ Pp, int f0, uint32_t magic_cw, uint32_t magic_ch) {
   const CapeDev& P = *Pp;
   const int W = P.W, H = P.H;
-  const int c0 = 4 * (blockIdx.x * 64 + threadIdx.x), r = blockIdx.y * 4 + threadIdx.y;
-  if (c0 >= W || r >= H) return;
+  const int c0 = 4 * (blockIdx.x * 64 + threadIdx.x), r0 = (blockIdx.y * 4 + threadIdx.y) * kPaintRows;
+  if (c0 >= W || r0 >= H) return;
   const int f = blockIdx.z + f0;
   const uint8_t* lab = P.cell_label + (long long)f * P.ncells;
-  const int cell_r = (int)__umulhi((uint32_t)r, magic_ch);
-  uint8_t* out = P.seg + ((long long)f * H + r) * W + c0;
+  const int ca = (int)__umulhi((uint32_t)c0, magic_cw), cb = (int)__umulhi((uint32_t)(c0 + 3), magic_cw);
+  uint8_t* out = P.seg + ((long long)f * H + r0) * W + c0;
+  const bool whole = (W & 3) == 0;
+  int last_cell_r = -1;
   uint32_t word = 0;
-  if (cell_r < P.ncy) {
-    const uint8_t* row = lab + cell_r * P.ncx;
-    const int ca = (int)__umulhi((uint32_t)c0, magic_cw), cb = (int)__umulhi((uint32_t)(c0 + 3), magic_cw);
-    if (ca == cb) word = ca < P.ncx ? (uint32_t)row[ca] * 0x01010101u : 0u;      // the usual case: the 4 pixels share a cell
-    else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int cell_c = (int)__umulhi((uint32_t)(c0 + k), magic_cw);
-        if (cell_c < P.ncx) word |= (uint32_t)row[cell_c] << (8 * k);
+  for (int k = 0; k < kPaintRows; ++k) {
+    const int r = r0 + k;
+    if (r >= H) break;
+    const int cell_r = (int)__umulhi((uint32_t)r, magic_ch);
+    if (cell_r != last_cell_r) {
+      last_cell_r = cell_r;
+      word = 0;
+      if (cell_r < P.ncy) {
+        const uint8_t* row = lab + cell_r * P.ncx;
+        if (ca == cb) word = ca < P.ncx ? (uint32_t)row[ca] * 0x01010101u : 0u;      // the usual case: the 4 pixels share a cell
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cell_c = (int)__umulhi((uint32_t)(c0 + j), magic_cw);
+            if (cell_c < P.ncx) word |= (uint32_t)row[cell_c] << (8 * j);
+          }
+        }
       }
     }
+    if (whole) *reinterpret_cast<uint32_t*>(out + (long long)k * W) = word;
+    else
+      for (int j = 0; j < 4 && c0 + j < W; ++j) out[(long long)k * W + j] = (uint8_t)(word >> (8 * j));
   }
-  if ((W & 3) == 0) *reinterpret_cast<uint32_t*>(out) = word;
-  else
-    for (int k = 0; k < 4 && c0 + k < W; ++k) out[k] = (uint8_t)(word >> (8 * k));
 }
 
 static const int kBorderWarps = 4;     // warps per block of k_cape_refine_border
@@ -2252,7 +2266,7 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
     else DRFE_LAUNCH(k_cape_refine_plan<false>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
     auto magic = [](unsigned d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };
     const unsigned q = (unsigned)(h->hd.W + 3) / 4;
-    DRFE_LAUNCH(k_cape_paint, dim3((q + 63) / 64, (unsigned)(h->hd.H + 3) / 4, (unsigned)n), dim3(64, 4), 0, st, h->dd, f0, magic((unsigned)h->hd.cw),
+    DRFE_LAUNCH(k_cape_paint, dim3((q + 63) / 64, (unsigned)(h->hd.H + 4 * kPaintRows - 1) / (4 * kPaintRows), (unsigned)n), dim3(64, 4), 0, st, h->dd, f0, magic((unsigned)h->hd.cw),
                 magic((unsigned)h->hd.ch));
     // warps loop over the list of border cells (its length is only known on the device): enough blocks to fill the GPU
     const int blocks = std::min((ncell_total + kBorderWarps - 1) / kBorderWarps, h->sm_count * 10);
