@@ -113,6 +113,22 @@ def main():
 
     ms, _ = timed(lambda: orb.frame_post_shared_depth(p, cape))
     print("drfe_orb_frame_post_shared_depth %5.2f ms per %d frames (the depth the CAPE handle uploaded)" % (ms, B))
+    # round 2: the 5 cm voxel filter of the per-plane lists, the 1/3-resolution cloud, the input resize
+    pin_vox = _t.empty((B, N, 3), dtype=_t.float32).pin_memory().numpy()
+
+    def vox():
+        drfe._check(cape.L.drfe_cape_plane_points_voxel(cape.h, 0.05, pin_vox.ctypes.data, N, pin_off.ctypes.data, 255))
+    ms, _ = timed(vox, n=3)
+    nvox = sum(int(pin_off[f, 255]) for f in range(B))
+    print("drfe_cape_plane_points_voxel   %7.2f ms per %d frames (pinned destination; %d centroids = %.1f MB instead of the lists)" % (ms, B, nvox, nvox * 12 / 1e6))
+    ms, _ = timed(lambda: cape.third_cloud(3.0, B), n=3)
+    print("drfe_cape_third_cloud          %7.2f ms per %d frames" % (ms, B))
+    rs = drfe.Resizer(848, 480, 640, 480, max_batch=32)
+    rgb = np.random.default_rng(2).integers(0, 256, (32, 480, 848, 3), dtype=np.uint8)
+    d16 = np.random.default_rng(3).integers(0, 65536, (32, 480, 848), dtype=np.uint16)
+    ms, _ = timed(lambda: rs(rgb), n=5)
+    ms2, _ = timed(lambda: rs(d16), n=5)
+    print("drfe_resize 848x480 -> 640x480  %7.2f ms per 32 RGB frames, %.2f ms per 32 16-bit depth maps (pageable host in / out)" % (ms, ms2))
     # the per-frame sequence Tracking runs after the two extractors, on one frame (latency, host in / host out)
     orb1 = drfe.ORBextractor(1000, 1.2, 8, 20, 7, W, H)
     cape1 = drfe.CAPE(H, W, 20, 20, False, bench.MIN_COS, 50.0)
