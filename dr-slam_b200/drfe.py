@@ -55,6 +55,16 @@ class FrameParams(C.Structure):
                 ("bf", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
 
+class PeacParams(C.Structure):
+    """ahc::ParamSet + the PlaneFitter members DR-SLAM leaves at their defaults"""
+    _fields_ = [(n, C.c_double) for n in ("depthSigma", "stdTol_init", "stdTol_merge", "z_near", "z_far", "angle_near", "angle_far",
+                                          "similarityTh_merge", "similarityTh_refine", "depthAlpha", "depthChangeTol")] + \
+               [("min_support", C.c_int32), ("window_width", C.c_int32), ("window_height", C.c_int32), ("max_depth", C.c_float)]
+
+
+PEAC_PLANE_DTYPE = np.dtype([("normal", "<f8", (3,)), ("center", "<f8", (3,)), ("mse", "<f8"), ("curvature", "<f8"), ("N", "<i4"), ("rid", "<i4")], align=True)
+
+
 class PoolParams(C.Structure):
     _fields_ = [("orb", OrbParams), ("cape", CapeParams), ("width", C.c_int32), ("height", C.c_int32),
                 ("max_batch", C.c_int32), ("chunk_frames", C.c_int32)]
@@ -82,6 +92,8 @@ SYMBOLS = [
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
     "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_plane_points_voxel", "drfe_cape_third_cloud", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
+    "drfe_peac_default_params", "drfe_peac_create", "drfe_peac_destroy", "drfe_peac_stream", "drfe_peac_sync", "drfe_peac_enqueue_depth_u16",
+    "drfe_peac_download", "drfe_peac_plane_vertices", "drfe_peac_debug_counters",
     "drfe_resizer_create", "drfe_resizer_destroy", "drfe_resizer_stream", "drfe_resizer_sync", "drfe_resize",
     "drfe_pool_create", "drfe_pool_destroy", "drfe_pool_num_devices", "drfe_pool_max_keypoints", "drfe_pool_extract_batch",
     "drfe_pool_device_times", "drfe_host_alloc", "drfe_host_free", "drfe_host_register", "drfe_host_unregister",
@@ -174,6 +186,16 @@ def lib():
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
     L.drfe_cape_stage_times.argtypes = [vp, vp, vp, C.c_int, i32p]
+    L.drfe_peac_default_params.argtypes = [C.POINTER(PeacParams)]
+    L.drfe_peac_create.argtypes = [C.c_int, C.c_int, C.POINTER(PeacParams), C.c_int, C.c_int, C.POINTER(vp)]
+    L.drfe_peac_destroy.argtypes = [vp]
+    L.drfe_peac_stream.argtypes = [vp]
+    L.drfe_peac_stream.restype = vp
+    L.drfe_peac_sync.argtypes = [vp]
+    L.drfe_peac_enqueue_depth_u16.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.drfe_peac_download.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.drfe_peac_plane_vertices.argtypes = [vp, vp, vp, sz, vp, C.c_int]
+    L.drfe_peac_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_resizer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.drfe_resizer_destroy.argtypes = [vp]
     L.drfe_resizer_stream.argtypes = [vp]
@@ -286,6 +308,59 @@ def host_array(shape, dtype, write_combined=False):
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
     buf._owner = _Owner(p)
     return np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+
+
+class PEAC:
+    """Planar_SLAM::PlaneDetection on ahc::PlaneFitter (PlaneExtractor.h:61-81): readDepthImage + runPlaneDetection, batched"""
+
+    def __init__(self, width=640, height=480, max_batch=1, device=0, **params):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.W, self.H, self.max_batch = width, height, max_batch
+        self.prm = PeacParams()
+        _check(self.L.drfe_peac_default_params(C.byref(self.prm)))
+        for k, v in params.items():
+            setattr(self.prm, k, v)
+        _check(self.L.drfe_peac_create(width, height, C.byref(self.prm), max_batch, device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drfe_peac_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def params_array(self):
+        return np.array([getattr(self.prm, n) for n, _ in PeacParams._fields_[:11]], np.float64)
+
+    def enqueue(self, depth16, depth_factor, fx, fy, cx, cy):
+        depth16 = np.ascontiguousarray(depth16, np.uint16)
+        assert depth16.ndim == 3 and depth16.shape[1:] == (self.H, self.W)
+        self._keep = depth16
+        self._nframes = depth16.shape[0]
+        _check(self.L.drfe_peac_enqueue_depth_u16(self.h, self._nframes, _ptr(depth16), self.W, self.W * self.H, MEM_HOST, depth_factor, fx, fy, cx, cy))
+
+    def download(self, plane_cap=255):
+        nf = self._nframes
+        seg = np.empty((nf, self.H, self.W), np.uint8)
+        planes = np.zeros((nf, plane_cap), PEAC_PLANE_DTYPE)
+        npl = np.empty(nf, np.int32)
+        _check(self.L.drfe_peac_download(self.h, _ptr(seg), _ptr(planes), plane_cap, _ptr(npl)))
+        return seg, planes, npl
+
+    def plane_vertices(self, plane_cap=255, cap_per_frame=None):
+        nf = self._nframes
+        N = cap_per_frame or self.H * self.W
+        idx = np.zeros((nf, N), np.int32)
+        pts = np.zeros((nf, N, 3), np.float32)
+        offs = np.zeros((nf, plane_cap + 1), np.int32)
+        _check(self.L.drfe_peac_plane_vertices(self.h, _ptr(idx), _ptr(pts), N, _ptr(offs), plane_cap))
+        return idx, pts, offs
+
+    def counters(self, frame=0):
+        out = np.zeros(4, np.int32)
+        _check(self.L.drfe_peac_debug_counters(self.h, frame, _ptr(out)))
+        return out
 
 
 class Resizer:

@@ -445,6 +445,45 @@ int drfe_cape_debug_counters(drfe_cape* h, int frame, long long* out16);
 int drfe_cape_set_profiling(drfe_cape* h, int on);
 int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, int* nstages);
 
+/* ------------------------------------------------------------------ PEAC-AHC plane extraction (next-1 of SURVEY.md 8f)
+ * The plane extractor that is live in Frame::Frame (reference src/Frame.cc:126, :937-949): PlaneDetection::readDepthImage
+ * (src/PlaneExtractor.cpp:28-55: 16-bit depth * factor in double, z > 5 culled, X / Y by true double division) and
+ * ahc::PlaneFitter<ImagePointCloud>::run with its defaults (include/peac/AHCPlaneFitter.hpp:211-259: 10x10 windows, minSupport
+ * 3000, doRefine, ERODE_ALL_BORDER, INIT_STRICT) — block statistics and PCA, graph edges, agglomerative clustering by minimum
+ * MSE, block erosion, pixel-level region growing (floodFill), one more clustering pass over the grown planes, relabelling.
+ * Declared orders where the reference leaves them to a library (oracle/peac_oracle.cpp P.1 - P.5): equal MSE in the priority
+ * queue and equal merge candidates go by creation order, equal plane sizes keep extraction order, Jacobi eigen-solver.
+ * One handle = one PlaneDetection object bound to a device, an image size and a maximum batch (frames are independent). */
+typedef struct drfe_peac_params {   /* ahc::ParamSet (AHCParamSet.hpp:46-78) + the PlaneFitter members DR-SLAM leaves at their defaults */
+  double depthSigma, stdTol_init, stdTol_merge;        /* T_mse = (depthSigma * z^2 + stdTol)^2                                  */
+  double z_near, z_far, angle_near, angle_far;         /* T_ang(P_INIT): linear map of the clipped depth to an angle, its cosine */
+  double similarityTh_merge, similarityTh_refine;      /* cos 60 deg, cos 30 deg                                                 */
+  double depthAlpha, depthChangeTol;                   /* T_dz = depthAlpha * |z| + depthChangeTol                               */
+  int32_t min_support, window_width, window_height;    /* 3000, 10, 10                                                           */
+  float max_depth;                                     /* readDepthImage culls z > 5.0 (PlaneExtractor.cpp:44)                   */
+} drfe_peac_params;
+typedef struct drfe_peac_plane {    /* what Frame::ComputePlanes reads of plane_filter.extractedPlanes[i] (Frame.cc:971-979), and its statistics */
+  double normal[3], center[3], mse, curvature;
+  int32_t N, rid;
+} drfe_peac_plane;
+typedef struct drfe_peac drfe_peac;
+int drfe_peac_default_params(drfe_peac_params* p);
+int drfe_peac_create(int width, int height, const drfe_peac_params* params, int max_batch, int device, drfe_peac** out);
+int drfe_peac_destroy(drfe_peac* h);
+void* drfe_peac_stream(drfe_peac* h);
+int drfe_peac_sync(drfe_peac* h);
+/* planeDetector.readDepthImage(Depth, K, depthFactor); planeDetector.runPlaneDetection(); for every frame of a batch
+ * (asynchronous; depth: [nframes][H][W] uint16, host or device) */
+int drfe_peac_enqueue_depth_u16(drfe_peac* h, int nframes, const uint16_t* depth, size_t row_stride, size_t frame_stride, int mem_kind,
+                                float depth_factor, float fx, float fy, float cx, float cy);
+/* seg_output (plid + 1 per pixel, 0 elsewhere; [nframes][H][W]), extractedPlanes ([nframes][plane_cap]) and plane_num_ */
+int drfe_peac_download(drfe_peac* h, uint8_t* seg_out, drfe_peac_plane* planes, int plane_cap, int* nr_planes);
+/* plane_vertices_ (pixel indices of every plane, in scan order) and the points Frame::ComputePlanes reads for them
+ * (Frame.cc:954-963: (float) of cloud.vertices[j]); layout as drfe_cape_plane_points; indices or points may be null */
+int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size_t cap_per_frame, int* offsets, int plane_cap);
+/* diagnostics: clustering steps (both passes) and flood-fill queue length of a frame */
+int drfe_peac_debug_counters(drfe_peac* h, int frame, int32_t* out4);
+
 /* ------------------------------------------------------------------ input resize (next-4 of SURVEY.md 8f)
  * cv::resize(im, IM, Size(640,480)) and cv::resize(depthmap, Depthmap, Size(640,480)) of System::TrackRGBD (reference
  * src/System.cc:325-329; default INTER_LINEAR), batched: OpenCV's own arithmetic — 11-bit fixed point for 8U (1, 3 or 4

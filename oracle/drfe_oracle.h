@@ -67,6 +67,11 @@ int orc_cape_cylinders_found(void* h);
 int orc_cape_get_cyl_maps(void* h, int32_t* cyl_map, uint8_t* cyl_eroded_map);
 /* the declared rand() stream of CylinderSeg: glibc TYPE_3, srand(seed) */
 int orc_glibc_rand(uint32_t seed, int n, int32_t* out);
+/* PEAC (ahc::PlaneFitter, include/peac/): PlaneDetection::readDepthImage and PlaneFitter::run with doRefine (peac_oracle.cpp) */
+void orc_peac_cloud(const uint16_t* depth, int width, int height, int row_stride, float depth_factor, float fx, float fy, float cx, float cy,
+                    double* cloud);
+int orc_peac_run(const double* cloud, int width, int height, const double* prm11, int minSupport, int windowWidth, int windowHeight, uint8_t* seg_out,
+                 double* planes, int plane_cap, int* member_offsets, int* member_idx, int member_cap, int* steps_out);
 /* pcl::VoxelGrid (Frame.cc:1121-1125) on one point list; the 1/3-resolution cloud of Frame.cc:1153-1172 */
 int orc_voxel_grid(const float* xyz, int n, float leaf, float* out, int* unfiltered);
 void orc_third_cloud(const float* depth, int width, int height, int row_stride, float fx, float fy, float cx, float cy, float max_point_dist,

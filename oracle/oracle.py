@@ -100,6 +100,9 @@ def lib():
         L.orc_cape_cylinders_found.argtypes = [C.c_void_p]
         L.orc_cape_get_cyl_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_peac_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orc_peac_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_int, i32p]
         L.orc_voxel_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, i32p]
         L.orc_third_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         _lib = L
@@ -844,6 +847,43 @@ def search_by_bow_cpp(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv,
     nm = f(_p(kd), _p(ka), _p(kv), len(kd), len(kf_fv), _p(kn) if len(kn) else None, _p(ks), _p(kf), _p(fd), _p(fa), len(fd), len(f_fv),
            _p(fn) if len(fn) else None, _p(fs), _p(ff), float(nnratio), int(check_orientation), _p(km), _p(fm))
     return km, fm, nm
+
+
+def peac_params(**kw):
+    """ahc::ParamSet defaults (AHCParamSet.hpp:68-78; DR-SLAM never changes them) as the 11 doubles orc_peac_run takes"""
+    import math
+    d = dict(depthSigma=1.6e-6, stdTol_init=5.0, stdTol_merge=8.0, z_near=500.0, z_far=4000.0, angle_near=15.0 * math.pi / 180.0,
+             angle_far=90.0 * math.pi / 180.0, similarityTh_merge=math.cos(60.0 * math.pi / 180.0),
+             similarityTh_refine=math.cos(30.0 * math.pi / 180.0), depthAlpha=0.04, depthChangeTol=0.02)
+    d.update(kw)
+    return np.array([d[k] for k in ("depthSigma", "stdTol_init", "stdTol_merge", "z_near", "z_far", "angle_near", "angle_far",
+                                    "similarityTh_merge", "similarityTh_refine", "depthAlpha", "depthChangeTol")], np.float64)
+
+
+def peac_cloud(depth16, depth_factor, fx, fy, cx, cy):
+    """PlaneDetection::readDepthImage (PlaneExtractor.cpp:28-55): (H, W) uint16 -> (H*W, 3) float64, z > 5 culled"""
+    depth16 = np.ascontiguousarray(depth16, np.uint16)
+    H, W = depth16.shape
+    out = np.empty((H * W, 3), np.float64)
+    lib().orc_peac_cloud(_p(depth16), W, H, W, depth_factor, fx, fy, cx, cy, _p(out))
+    return out
+
+
+def peac_run(cloud, width, height, params=None, min_support=3000, window=10, plane_cap=256):
+    """ahc::PlaneFitter::run (doRefine) -> (seg_output (H, W) uint8, planes (n, 12) float64 [normal, center, mse, curvature, N, rid],
+    list of pixel-index arrays (plane_vertices_), cluster steps)"""
+    cloud = np.ascontiguousarray(cloud, np.float64)
+    prm = peac_params() if params is None else np.ascontiguousarray(params, np.float64)
+    seg = np.zeros((height, width), np.uint8)
+    planes = np.zeros((plane_cap, 12), np.float64)
+    offs = np.zeros(plane_cap + 1, np.int32)
+    idx = np.zeros(width * height, np.int32)
+    steps = C.c_int32(0)
+    n = lib().orc_peac_run(_p(cloud), width, height, _p(prm), min_support, window, window, _p(seg), _p(planes), plane_cap, _p(offs), _p(idx),
+                           len(idx), C.byref(steps))
+    if n < 0:
+        raise RuntimeError("orc_peac_run: capacity")
+    return seg, planes[:n].copy(), [idx[offs[p]:offs[p + 1]].copy() for p in range(n)], steps.value
 
 
 def voxel_grid(xyz, leaf=0.05):

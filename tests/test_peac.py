@@ -1,0 +1,103 @@
+"""PEAC-AHC, the plane extractor that is live in Frame::Frame (reference src/Frame.cc:126, :937-949; include/peac/*.hpp).
+CPU: invariants of the restatement (oracle/peac_oracle.cpp).  GPU: drfe_peac_* against the restatement — seg_output, plane
+order, plane_vertices_ and member points bit for bit, plane parameters bit for bit (same Jacobi solver, same operation order)."""
+import numpy as np
+import pytest
+
+
+def clean_depth(depth, holes=()):
+    """the synthetic generator drops 2 % of the pixels independently; with INIT_STRICT (no missing pixel allowed in a 10x10 window,
+    the reference's default) that leaves almost no window, so the dropouts are filled from a neighbour and coherent holes are cut
+    instead, like a real sensor's"""
+    d = depth.copy()
+    for _ in range(4):
+        z = d == 0
+        if not z.any():
+            break
+        p = np.pad(d, 1, mode="edge")
+        nb = np.max(np.stack([p[1:-1, :-2], p[1:-1, 2:], p[:-2, 1:-1], p[2:, 1:-1]]), 0)
+        d[z] = nb[z]
+    for (y0, y1, x0, x1) in holes:
+        d[y0:y1, x0:x1] = 0
+    return d
+
+
+def frame(drfe, scene, seed, holes=((100, 140, 300, 420),)):
+    _, depth, K = drfe.synth_frame(640, 480, scene, seed)
+    return np.rint(clean_depth(depth, holes) * 5000).astype(np.uint16), K
+
+
+FAC = float(np.float32(1.0 / 5000.0))
+
+
+def test_peac_restatement_invariants(drfe, orc):
+    q, K = frame(drfe, 1, 20260012)
+    cloud = orc.peac_cloud(q, FAC, *K)
+    assert cloud.shape == (640 * 480, 3) and (cloud[:, 2] <= 5.0).all()
+    z = q.astype(np.float64).ravel() * np.float64(np.float32(FAC))
+    assert np.array_equal(cloud[:, 2], np.where(z > 5.0, 0.0, z))
+    seg, planes, members, steps = orc.peac_run(cloud, 640, 480)
+    n = len(planes)
+    assert n >= 3 and steps > 500 and seg.max() == n
+    assert np.all(np.diff(planes[:, 8]) <= 0)                                  # sorted by N, decreasing
+    assert np.allclose((planes[:, :3] ** 2).sum(1), 1, atol=1e-12)
+    assert np.all((planes[:, :3] * planes[:, 3:6]).sum(1) <= 0)                # normals point towards the camera
+    for p in range(n):
+        idx = members[p]
+        assert np.all(np.diff(idx) > 0) and np.all(seg.ravel()[idx] == p + 1)  # scan order, consistent with seg_output
+    assert sum(len(m) for m in members) == int((seg > 0).sum())
+    assert (seg[100:140, 300:420] == 0).all()                                   # nothing grows into a hole (no depth there)
+    # every member lies close to its plane (region growing accepts within 3 sigma of the block-level fit)
+    for p in range(n):
+        pts = cloud[members[p]]
+        d = np.abs((pts - planes[p, 3:6]) @ planes[p, :3])
+        assert np.median(d) < 0.02
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,seed,holes", [
+    (0, 20260000, ((100, 140, 300, 420),)),
+    (1, 20260012, ((100, 140, 300, 420),)),
+    (2, 20260100, ((0, 60, 0, 640), (200, 260, 100, 180))),
+    (1, 20260042, ()),
+])
+def test_gpu_peac_parity(drfe, orc, scene, seed, holes):
+    q, K = frame(drfe, scene, seed, holes)
+    pe = drfe.PEAC(640, 480)
+    pe.enqueue(q[None], FAC, *K)
+    seg, planes, npl = pe.download()
+    idx, pts, offs = pe.plane_vertices()
+    cloud = orc.peac_cloud(q, FAC, *K)
+    oseg, oplanes, omem, osteps = orc.peac_run(cloud, 640, 480, params=pe.params_array())
+    cnt = pe.counters(0)
+    assert cnt[0] == osteps, (cnt, osteps)
+    assert npl[0] == len(oplanes)
+    n = int(npl[0])
+    assert np.array_equal(planes[0, :n]["N"], oplanes[:, 8].astype(np.int32)) and np.array_equal(planes[0, :n]["rid"], oplanes[:, 9].astype(np.int32))
+    assert np.array_equal(planes[0, :n]["normal"], oplanes[:, :3]) and np.array_equal(planes[0, :n]["center"], oplanes[:, 3:6])
+    assert np.array_equal(planes[0, :n]["mse"], oplanes[:, 6]) and np.array_equal(planes[0, :n]["curvature"], oplanes[:, 7])
+    assert np.array_equal(seg[0], oseg)
+    for p in range(n):
+        got = idx[0, offs[0, p]:offs[0, p + 1]]
+        assert np.array_equal(got, omem[p]), p
+        assert np.array_equal(pts[0, offs[0, p]:offs[0, p + 1]], cloud[omem[p]].astype(np.float32)), p
+
+
+@pytest.mark.gpu
+def test_gpu_peac_batch(drfe, orc):
+    B = 10
+    fr = [frame(drfe, i % 3, 20260600 + 3 * i, ((40 * (i % 5), 40 * (i % 5) + 50, 50 * i, 50 * i + 90),)) for i in range(B)]
+    q = np.stack([f[0] for f in fr]); K = fr[0][1]
+    pe = drfe.PEAC(640, 480, max_batch=B)
+    pe.enqueue(q, FAC, *K)
+    seg, planes, npl = pe.download()
+    for f in range(B):
+        oseg, oplanes, omem, _ = orc.peac_run(orc.peac_cloud(q[f], FAC, *K), 640, 480)
+        assert npl[f] == len(oplanes) and np.array_equal(seg[f], oseg), f
+        assert np.array_equal(planes[f, :npl[f]]["normal"], oplanes[:, :3]), f
+    pe1 = drfe.PEAC(640, 480)                                   # a frame alone = the same frame in a batch
+    pe1.enqueue(q[7:8], FAC, *K)
+    s1, p1, n1 = pe1.download()
+    assert n1[0] == npl[7] and np.array_equal(s1[0], seg[7])
+    with pytest.raises(drfe.DrfeError):
+        pe1.download(plane_cap=1)
