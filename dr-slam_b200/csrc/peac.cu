@@ -59,11 +59,12 @@ struct PeacDev {
   uint8_t* seg;             // [B][H*W]
   drfe_peac_plane* planes;  // [B][kPeacMaxPlanes]
   int* nplanes;             // [B]
-  int* counters;            // [B][4] cluster steps, queue length, first-pass planes, -
+  int* counters;            // [B][12] cluster steps, queue length, first-pass planes, -, then kilocycles at the end of each stage
   int* status;              // 1: more than 255 planes, 2: flood-fill queue overflow, 4: too many merge candidates
 };
 
-// ---- cyclic Jacobi, operation for operation the oracle's eig3_sym
+// ---- cyclic Jacobi, operation for operation the oracle's eig3_sym (peac_oracle.cpp; a pivot that no longer changes the
+// diagonal is zeroed from the fourth sweep on)
 __device__ void peac_eig3(const double in[6], double w[3], double v[3][3]) {
   double a[3][3] = {{in[0], in[1], in[2]}, {in[1], in[3], in[4]}, {in[2], in[4], in[5]}};
   for (int i = 0; i < 3; ++i)
@@ -77,7 +78,7 @@ __device__ void peac_eig3(const double in[6], double w[3], double v[3][3]) {
       if (apq == 0.0) continue;
       const double app = a[p][p], aqq = a[q][q];
       const double g = 100.0 * fabs(apq);
-      if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
+      if (sweep > 2 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
         a[p][q] = a[q][p] = 0.0;
         continue;
       }
@@ -219,38 +220,67 @@ __device__ __forceinline__ void ds_union(int* parent, int* dsize, int x, int y) 
   else { parent[yr] = xr; dsize[xr] += dsize[yr]; }
 }
 
+// a double's place in the order of doubles as a signed 64-bit integer (NaNs sort after +inf: never popped, like `nan < x`)
+__device__ __forceinline__ long long peac_key(double m) {
+  const long long b = __double_as_longlong(m + 0.0);
+  return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFFLL);
+}
+
 // The clustering loop (ahCluster, AHCPlaneFitter.hpp:976-1190) over the slots that are queued in S.qmse.  Whole CTA.
 // Returns the number of steps; extracted planes are appended to S.extracted (n_ext) in extraction order.
 __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, PeacShared& S, int& next_seq, int& n_ext, int* s_tmp, double* s_dtmp) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int NB = P.NB, nw = P.nwords;
   int steps = 0;
+  bool dirty = true;
+  const long long kInfKey = 0x7FF0000000000000LL;
+  long long own_k = kInfKey;
+  int own_s = -1, own_q = 0x7FFFFFFF;
+  long long* s_ktmp = reinterpret_cast<long long*>(s_dtmp);
+#ifdef PEAC_PHASE_PROFILE
+  long long ph[6] = {0, 0, 0, 0, 0, 0}, tph = clock64();
+#define PH(i) { const long long t_ = clock64(); ph[i] += t_ - tph; tph = t_; }
+#else
+#define PH(i)
+#endif
   for (;;) {
-    // ---- pop: argmin of (mse, creation number) over the queued slots
-    double bm = INFINITY;
-    int bs = -1, bq = 0x7FFFFFFF;
-    for (int i = tid; i < NB; i += kPeacThreads) {
-      const double m = S.qmse[i];
-      if (m < bm || (m == bm && m < INFINITY && S.qseq[i] < bq)) { bm = m; bs = i; bq = S.qseq[i]; }
+    // ---- pop: argmin of (mse, creation number) over the queued slots.  A thread keeps the minimum of its own slots
+    // (i = tid mod kPeacThreads) and scans them again only after one of them changed.
+    // The order of doubles is taken on their bit patterns (signed 64-bit after folding the negatives; -0.0 is made +0.0 first):
+    // integer compares instead of the FP64 pipe's.
+    if (dirty) {
+      own_k = kInfKey; own_s = -1; own_q = 0x7FFFFFFF;
+#pragma unroll 8
+      for (int i = tid; i < NB; i += kPeacThreads) {              // branch-free, so that the loads of an unrolled group go out together
+        const long long k = peac_key(S.qmse[i]);
+        const int sq = S.qseq[i];
+        const bool better = k < own_k || (k == own_k && sq < own_q);
+        own_k = better ? k : own_k; own_s = better ? i : own_s; own_q = better ? sq : own_q;
+      }
+      if (own_k >= kInfKey) { own_k = kInfKey; own_s = -1; own_q = 0x7FFFFFFF; }
+      dirty = false;
     }
+    long long bk = own_k;
+    int bs = own_s, bq = own_q;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const double om = __shfl_xor_sync(0xFFFFFFFFu, bm, o);
+      const long long ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
       const int os = __shfl_xor_sync(0xFFFFFFFFu, bs, o), oq = __shfl_xor_sync(0xFFFFFFFFu, bq, o);
-      if (os >= 0 && (bs < 0 || om < bm || (om == bm && oq < bq))) { bm = om; bs = os; bq = oq; }
+      if (os >= 0 && (bs < 0 || ok < bk || (ok == bk && oq < bq))) { bk = ok; bs = os; bq = oq; }
     }
-    if (lane == 0) { s_dtmp[wid] = bm; s_tmp[wid] = bs; s_tmp[4 + wid] = bq; }
+    if (lane == 0) { s_ktmp[wid] = bk; s_tmp[wid] = bs; s_tmp[4 + wid] = bq; }
     __syncthreads();
-    bm = s_dtmp[0]; bs = s_tmp[0]; bq = s_tmp[4];
+    bk = s_ktmp[0]; bs = s_tmp[0]; bq = s_tmp[4];
     for (int w = 1; w < kPeacThreads / 32; ++w) {
-      const double om = s_dtmp[w];
+      const long long ok = s_ktmp[w];
       const int os = s_tmp[w], oq = s_tmp[4 + w];
-      if (os >= 0 && (bs < 0 || om < bm || (om == bm && oq < bq))) { bm = om; bs = os; bq = oq; }
+      if (os >= 0 && (bs < 0 || ok < bk || (ok == bk && oq < bq))) { bk = ok; bs = os; bq = oq; }
     }
     __syncthreads();
     if (bs < 0) break;                                           // queue empty
+    PH(0)
     const int p = bs;
-    if (tid == 0) S.qmse[p] = INFINITY;                          // popped
+    if (tid == p % kPeacThreads) { S.qmse[p] = INFINITY; dirty = true; }   // popped
     // ---- the popped node's live neighbours, in ascending slot order
     uint32_t* row_p = adj + (long long)p * nw;
     int mycnt = 0;
@@ -274,68 +304,86 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
       }
     }
     if (ncand > kPeacCand) { if (tid == 0) atomicOr(P.status, 4); ncand = kPeacCand; }
+#ifdef PEAC_PHASE_PROFILE
+    ph[5] += ncand;
+#endif
     __syncthreads();
-    // ---- fit the merge with every similar neighbour, one thread per candidate
+    PH(1)
+    // ---- fit the merge with every similar neighbour, one thread per candidate; the fit stays in the thread's registers, the
+    // thread that fitted the chosen candidate finishes the step (a fit is ~12 k cycles of dependent double div / sqrt)
     const PeacNode& np = nodes[p];
+    int my_c = -1, my_N = 0;
+    double my_s[9], my_ctr[3], my_nrm[3], my_curv = 0, my_m = 0;
     for (int c = tid; c < ncand; c += kPeacThreads) {
       const PeacNode& nb = nodes[S.cand[c]];
       double m = INFINITY;
       if (!(peac_sim(np, nb) < P.sim_merge)) {
-        double s[9], ctr[3], nrm[3], curv;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s[k] = np.s[k] + nb.s[k];
-        peac_compute(s, np.N + nb.N, ctr, nrm, m, curv);
+        for (int k = 0; k < 9; ++k) my_s[k] = np.s[k] + nb.s[k];
+        my_N = np.N + nb.N;
+        peac_compute(my_s, my_N, my_ctr, my_nrm, my_m, my_curv);
+        my_c = c;
+        m = my_m;
         if (!(m < INFINITY)) m = DBL_MAX;                         // (a NaN would never be chosen after another candidate; keep it last)
       }
       S.cmse[c] = m;
     }
     __syncthreads();
-    // ---- the candidate the reference's scan keeps (ascending creation number; :1040-1051).  Thread 0: the lists are short.
-    if (tid == 0) {
-      int best = -1;
-      double best_m = 0;
-      int best_N = 0;
-      // The scan `cand == 0 || cand.mse > m.mse || (cand.mse == m.mse && cand.N < m.mse)` visits the candidates in creation order;
-      // replay it on the candidates ordered by creation number: repeatedly take the smallest unvisited creation number.
-      // (Done as: find the minimum mse; among exact ties the rule needs the visiting order, resolved below.)
+    PH(2)
+    // ---- the candidate the reference's scan keeps (ascending creation number; :1040-1051): the minimum mse; among exact ties
+    // the scan `cand == 0 || cand.mse > m.mse || (cand.mse == m.mse && cand.N < m.mse)` depends on the visiting order and is
+    // replayed literally over the tied candidates (earlier non-tied ones cannot survive a tie with the minimum, later ones cannot
+    // replace it).  Warp 0.
+    if (wid == 0) {
       double mn = INFINITY;
-      for (int c = 0; c < ncand; ++c) mn = fmin(mn, S.cmse[c]);
-      if (mn < INFINITY) {
-        int ties = 0;
-        for (int c = 0; c < ncand; ++c) ties += (S.cmse[c] == mn);
-        if (ties == 1) {
-          for (int c = 0; c < ncand; ++c) if (S.cmse[c] == mn) best = c;
-        } else {
-          // exact ties: replay the scan over the tied candidates in creation order (earlier non-tied candidates cannot survive a tie
-          // with the minimum, later ones cannot replace it)
-          int last_q = -1;
-          for (int round = 0; round < ties; ++round) {
-            int c_next = -1, q_next = 0x7FFFFFFF;
-            for (int c = 0; c < ncand; ++c)
-              if (S.cmse[c] == mn) { const int q = S.qseq[S.cand[c]]; if (q > last_q && q < q_next) { q_next = q; c_next = c; } }
-            last_q = q_next;
-            const int Nm = np.N + nodes[S.cand[c_next]].N;
-            if (best < 0 || best_m > mn || (best_m == mn && (double)best_N < mn)) { best = c_next; best_m = mn; best_N = Nm; }
-          }
+      for (int c = lane; c < ncand; c += 32) mn = fmin(mn, S.cmse[c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+      int ties = 0, mine_c = -1;
+      if (mn < INFINITY)
+        for (int c = lane; c < ncand; c += 32) if (S.cmse[c] == mn) { ++ties; mine_c = c; }
+      const unsigned has = __ballot_sync(0xFFFFFFFFu, ties > 0);
+      int tot = ties;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+      if (tot <= 1) {
+        if (tot == 0) { if (lane == 0) s_tmp[16] = -1; }
+        else if (lane == __ffs(has) - 1) s_tmp[16] = mine_c;
+      } else if (lane == 0) {
+        int best = -1, best_N = 0, last_q = -1;
+        double best_m = 0;
+        for (int round = 0; round < tot; ++round) {
+          int c_next = -1, q_next = 0x7FFFFFFF;
+          for (int c = 0; c < ncand; ++c)
+            if (S.cmse[c] == mn) { const int q = S.qseq[S.cand[c]]; if (q > last_q && q < q_next) { q_next = q; c_next = c; } }
+          last_q = q_next;
+          const int Nm = np.N + nodes[S.cand[c_next]].N;
+          if (best < 0 || best_m > mn || (best_m == mn && (double)best_N < mn)) { best = c_next; best_m = mn; best_N = Nm; }
         }
+        s_tmp[16] = best;
       }
-      s_tmp[16] = best;
     }
     __syncthreads();
     const int best = s_tmp[16];
+    PH(3)
     bool merged = false;
     if (best >= 0) {
       const int q = S.cand[best];
-      // the accepted candidate once more, by every thread (registers instead of a broadcast of 20 doubles)
       const PeacNode& nb = nodes[q];
-      double s[9], ctr[3], nrm[3], curv, m;
+      const bool owner = tid == best % kPeacThreads;
+      if (owner) {
+        if (my_c != best) {                                       // more than kPeacThreads candidates and a later fit took the registers
 #pragma unroll
-      for (int k = 0; k < 9; ++k) s[k] = np.s[k] + nb.s[k];
-      const int Nm = np.N + nb.N;
-      peac_compute(s, Nm, ctr, nrm, m, curv);
-      const double t = P.depthSigma * ctr[2] * ctr[2] + P.stdTol_merge;                 // T_mse(P_MERGING)
-      if (m < t * t) {
-        merged = true;
+          for (int k = 0; k < 9; ++k) my_s[k] = np.s[k] + nb.s[k];
+          my_N = np.N + nb.N;
+          peac_compute(my_s, my_N, my_ctr, my_nrm, my_m, my_curv);
+        }
+        const double t = P.depthSigma * my_ctr[2] * my_ctr[2] + P.stdTol_merge;         // T_mse(P_MERGING)
+        s_tmp[17] = my_m < t * t;
+      }
+      __syncthreads();
+      merged = s_tmp[17] != 0;
+      if (merged) {
         const int rid_p = np.rid, rid_q = nb.rid;
         const int new_rid = np.N >= nb.N ? rid_p : rid_q;
         uint32_t* row_q = adj + (long long)q * nw;
@@ -354,20 +402,21 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
             atomicOr(adj + (long long)(tid * 32 + b) * nw + (p >> 5), 1u << (p & 31));
           }
         }
-        __syncthreads();                                          // every thread has read nodes[p] / nodes[q]
-        if (tid == 0) {
+        __syncthreads();                                          // every thread has read nodes[p] / nodes[q] / alive
+        if (owner) {
           PeacNode nn;
-          for (int k = 0; k < 9; ++k) nn.s[k] = s[k];
-          nn.mse = m; nn.curvature = curv; nn.th_init = 0;
-          for (int k = 0; k < 3; ++k) { nn.center[k] = ctr[k]; nn.normal[k] = nrm[k]; }
-          nn.N = Nm; nn.rid = new_rid; nn.seq = next_seq; nn.ok = 1;
+          for (int k = 0; k < 9; ++k) nn.s[k] = my_s[k];
+          nn.mse = my_m; nn.curvature = my_curv; nn.th_init = 0;
+          for (int k = 0; k < 3; ++k) { nn.center[k] = my_ctr[k]; nn.normal[k] = my_nrm[k]; }
+          nn.N = my_N; nn.rid = new_rid; nn.seq = next_seq; nn.ok = 1;
           nodes[p] = nn;
           ds_union(S.parent, S.dsize, rid_p, rid_q);
           S.alive[q >> 5] &= ~(1u << (q & 31));
           S.qmse[q] = INFINITY;
-          S.qmse[p] = m;
+          S.qmse[p] = my_m;
           S.qseq[p] = next_seq;
         }
+        if (tid == p % kPeacThreads || tid == q % kPeacThreads) dirty = true;
         ++next_seq;
       }
     }
@@ -382,7 +431,11 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
     }
     ++steps;
     __syncthreads();
+    PH(4)
   }
+#ifdef PEAC_PHASE_PROFILE
+  if (tid == 0 && steps > 100) { for (int i = 0; i < 5; ++i) P.counters[12 * blockIdx.x + 4 + i] = (int)(ph[i] >> 10); P.counters[12 * blockIdx.x + 11] = (int)(ph[5]); }
+#endif
   // ---- std::sort(extractedPlanes, N decreasing), declared stable (P.4): insertion sort by thread 0
   if (tid == 0) {
     for (int i = 1; i < n_ext; ++i) {
@@ -426,6 +479,12 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
   int2* queue = P.queue + (long long)slot * P.qcap;
   for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
     PeacNode* nodes = P.nodes + (long long)f * NB;
+    const long long t_begin = clock64();
+    #ifdef PEAC_PHASE_PROFILE
+    auto stamp = [&](int i) { if (tid == 0 && i >= 5) P.counters[12 * f + 4 + i] = (int)((clock64() - t_begin) >> 10); };
+#else
+    auto stamp = [&](int i) { if (tid == 0) P.counters[12 * f + 4 + i] = (int)((clock64() - t_begin) >> 10); };
+#endif
     // ---- reset
     for (long long i = tid; i < (long long)NB * nw; i += kPeacThreads) adj[i] = 0;
     for (int i = tid; i < NB; i += kPeacThreads) {
@@ -441,6 +500,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
     for (int i = tid; i < NB; i += kPeacThreads)
       if (nodes[i].ok) atomicOr(&S.alive[i >> 5], 1u << (i & 31));
     __syncthreads();
+    stamp(0);
     // ---- edges (AHCPlaneFitter.hpp:901-965): the loops skip and step back, so one thread walks one block row / column
     auto G = [&](int idx) { return nodes[idx].ok != 0; };
     auto connect = [&](int a, int b) {
@@ -479,9 +539,11 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
       }
     }
     __syncthreads();
+    stamp(1);
     // ---- first clustering
     int next_seq = NB, n_ext = 0;
     int steps = peac_cluster(P, nodes, adj, S, next_seq, n_ext, s_tmp, s_dtmp);
+    stamp(2);
     const int n_old = n_ext;
     // ---- findBlockMembership (:494-600, ERODE_ALL_BORDER): rid2plid as an array in S.qseq (free now), blkMap in S.cand? no: NB entries -> reuse S.qmse as ints
     int* rid2plid = S.qseq;
@@ -558,6 +620,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
         for (int b = b0; b < b1; ++b) off += seeds_of(b, queue + off);
     }
     __syncthreads();
+    stamp(3);
     // ---- floodFill (:434-488), kPeacThreads queue entries per chunk
     const double sim_refine = P.sim_refine;
     const int chunk = P.flood_chunk;
@@ -662,6 +725,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
     // ---- one more clustering over the planes the region growing connected (:318-327)
     // planes keep their slots; adjacency rows of those slots are rebuilt from s_padj; only valid planes are queued
     __syncthreads();
+    stamp(4);
     for (int i = tid; i < NB; i += kPeacThreads) { S.qmse[i] = INFINITY; S.qseq[i] = nodes[i].seq; }   // (blkMap / rid2plid are done)
     for (int i = tid; i < nw; i += kPeacThreads) S.alive[i] = 0;
     __syncthreads();
@@ -681,6 +745,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
     __syncthreads();
     n_ext = 0;
     steps += peac_cluster(P, nodes, adj, S, next_seq, n_ext, s_tmp, s_dtmp);
+    stamp(5);
     // ---- plane numbering (:329-343) and the outputs
     for (int i = tid; i <= kPeacMaxPlanes; i += kPeacThreads) {
       int m = -1;
@@ -701,7 +766,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
     }
     if (tid == 0) {
       P.nplanes[f] = n_ext;
-      P.counters[4 * f] = steps; P.counters[4 * f + 1] = qlen; P.counters[4 * f + 2] = n_old; P.counters[4 * f + 3] = 0;
+      P.counters[12 * f] = steps; P.counters[12 * f + 1] = qlen; P.counters[12 * f + 2] = n_old; P.counters[12 * f + 3] = 0;
     }
     uint8_t* seg = P.seg + (long long)f * W * H;
     for (int i = tid; i < (W * H) / 4; i += kPeacThreads) {
@@ -718,6 +783,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
       seg[i] = (v >= 0 && s_plidmap[v] >= 0) ? (uint8_t)(s_plidmap[v] + 1) : 0;
     }
     __syncthreads();
+    stamp(6);
   }
 }
 
@@ -878,7 +944,7 @@ int drfe_peac_create(int width, int height, const drfe_peac_params* params, int 
   rc |= peac_alloc(h, &D.seg, N * B);
   rc |= peac_alloc(h, &D.planes, (size_t)kPeacMaxPlanes * B);
   rc |= peac_alloc(h, &D.nplanes, B);
-  rc |= peac_alloc(h, &D.counters, 4 * B);
+  rc |= peac_alloc(h, &D.counters, 12 * B);
   rc |= peac_alloc(h, &D.status, 1);
   rc |= peac_alloc(h, &h->d_depth, N * B);
   rc |= peac_alloc(h, &h->dd, 1);
@@ -1004,12 +1070,12 @@ int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size
   return DRFE_OK;
 }
 
-int drfe_peac_debug_counters(drfe_peac* h, int frame, int32_t* out4) {
-  if (!h || !out4) { set_error("drfe_peac_debug_counters: null argument"); return DRFE_ERR_ARG; }
+int drfe_peac_debug_counters(drfe_peac* h, int frame, int32_t* out12) {
+  if (!h || !out12) { set_error("drfe_peac_debug_counters: null argument"); return DRFE_ERR_ARG; }
   if (!h->pending || frame < 0 || frame >= h->last_frames) { set_error("drfe_peac_debug_counters: bad frame"); return DRFE_ERR_STATE; }
   DeviceScope ds(h->device);
   DRFE_CUDA(cudaStreamSynchronize(h->stream));
-  DRFE_CUDA(cudaMemcpy(out4, h->hd.counters + 4 * frame, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  DRFE_CUDA(cudaMemcpy(out12, h->hd.counters + 12 * frame, 12 * sizeof(int), cudaMemcpyDeviceToHost));
   return DRFE_OK;
 }
 

@@ -333,12 +333,20 @@ class PEAC:
     def params_array(self):
         return np.array([getattr(self.prm, n) for n, _ in PeacParams._fields_[:11]], np.float64)
 
-    def enqueue(self, depth16, depth_factor, fx, fy, cx, cy):
-        depth16 = np.ascontiguousarray(depth16, np.uint16)
-        assert depth16.ndim == 3 and depth16.shape[1:] == (self.H, self.W)
-        self._keep = depth16
-        self._nframes = depth16.shape[0]
-        _check(self.L.drfe_peac_enqueue_depth_u16(self.h, self._nframes, _ptr(depth16), self.W, self.W * self.H, MEM_HOST, depth_factor, fx, fy, cx, cy))
+    def enqueue(self, depth16, depth_factor, fx, fy, cx, cy, nframes=None, mem_kind=MEM_HOST):
+        """depth16: [n, H, W] uint16 array on the host, or (with mem_kind=MEM_DEVICE and nframes) a device pointer to that layout"""
+        if mem_kind == MEM_HOST:
+            depth16 = np.ascontiguousarray(depth16, np.uint16)
+            assert depth16.ndim == 3 and depth16.shape[1:] == (self.H, self.W)
+            self._keep = depth16
+            self._nframes = depth16.shape[0]
+            ptr = _ptr(depth16)
+        else:
+            self._nframes, ptr = int(nframes), C.c_void_p(int(depth16))
+        _check(self.L.drfe_peac_enqueue_depth_u16(self.h, self._nframes, ptr, self.W, self.W * self.H, mem_kind, depth_factor, fx, fy, cx, cy))
+
+    def sync(self):
+        _check(self.L.drfe_peac_sync(self.h))
 
     def download(self, plane_cap=255):
         nf = self._nframes
@@ -358,7 +366,7 @@ class PEAC:
         return idx, pts, offs
 
     def counters(self, frame=0):
-        out = np.zeros(4, np.int32)
+        out = np.zeros(12, np.int32)
         _check(self.L.drfe_peac_debug_counters(self.h, frame, _ptr(out)))
         return out
 

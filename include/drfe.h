@@ -481,8 +481,10 @@ int drfe_peac_download(drfe_peac* h, uint8_t* seg_out, drfe_peac_plane* planes, 
 /* plane_vertices_ (pixel indices of every plane, in scan order) and the points Frame::ComputePlanes reads for them
  * (Frame.cc:954-963: (float) of cloud.vertices[j]); layout as drfe_cape_plane_points; indices or points may be null */
 int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size_t cap_per_frame, int* offsets, int plane_cap);
-/* diagnostics: clustering steps (both passes) and flood-fill queue length of a frame */
-int drfe_peac_debug_counters(drfe_peac* h, int frame, int32_t* out4);
+/* diagnostics of a frame: [0] clustering steps (both passes), [1] region-growing queue length, [2] planes of the first pass,
+ * [4..10] kilocycles from the frame's start to the end of: reset, edges, first clustering, block membership + seeds, region
+ * growing, second clustering, outputs */
+int drfe_peac_debug_counters(drfe_peac* h, int frame, int32_t* out12);
 
 /* ------------------------------------------------------------------ input resize (next-4 of SURVEY.md 8f)
  * cv::resize(im, IM, Size(640,480)) and cv::resize(depthmap, Depthmap, Size(640,480)) of System::TrackRGBD (reference

@@ -129,6 +129,44 @@ def main():
     ms, _ = timed(lambda: rs(rgb), n=5)
     ms2, _ = timed(lambda: rs(d16), n=5)
     print("drfe_resize 848x480 -> 640x480  %7.2f ms per 32 RGB frames, %.2f ms per 32 16-bit depth maps (pageable host in / out)" % (ms, ms2))
+    # PEAC-AHC (the plane extractor of Frame::Frame): one CTA per frame, so the batch is what fills the GPU
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_peac import clean_depth
+    from oracle import oracle as orc
+    fac = float(np.float32(1.0 / 5000.0))
+    q8 = np.stack([np.rint(clean_depth(data[i][1], ((100, 140, 300, 420),)) * 5000).astype(np.uint16) for i in range(0, 32, 4)])
+    qB = np.ascontiguousarray(q8[np.arange(B) % 8])
+    pe = drfe.PEAC(W, H, max_batch=B)
+
+    def peac_run():
+        pe.enqueue(qB, fac, *K)
+        return pe.download()
+    ms, (seg, planes, npl) = timed(peac_run, n=3)
+    print("drfe_peac (enqueue + download)  %7.2f ms per %d frames = %.3f ms per frame (%.1f planes per frame; pageable host in / out)" % (ms, B, ms / B, npl.mean()))
+    d_q = _t.from_numpy(qB.view(np.int16)).cuda()
+
+    def peac_dev():
+        pe.enqueue(d_q.data_ptr(), fac, *K, nframes=B, mem_kind=drfe.MEM_DEVICE)
+        pe.sync()
+    msd, _ = timed(peac_dev, n=3)
+    tot = np.array([pe.counters(f)[10] for f in range(B)])
+    print("drfe_peac, depth on the device, no download: %7.2f ms per %d frames = %.3f ms per frame; k_peac_frame kilocycles per frame min %d median %d max %d"
+          % (msd, B, msd / B, tot.min(), np.median(tot), tot.max()))
+    pe1 = drfe.PEAC(W, H)
+
+    def peac_one():
+        pe1.enqueue(qB[:1], fac, *K)
+        return pe1.download()
+    ms1, _ = timed(peac_one, n=10)
+    c = pe1.counters(0)
+    names = ["reset", "edges", "cluster 1", "membership + seeds", "region growing", "cluster 2", "outputs"]
+    kc = np.diff(np.concatenate([[0], c[4:11]]))
+    print("   k_peac_frame stages (kilocycles): " + ", ".join("%s %d" % (n, v) for n, v in zip(names, kc)) + "; steps %d, queue %d" % (c[0], c[1]))
+    t0 = time.perf_counter()
+    for i in range(4):
+        orc.peac_run(orc.peac_cloud(q8[i], fac, *K), W, H)
+    cpu = (time.perf_counter() - t0) / 4 * 1e3
+    print("drfe_peac one frame             %7.2f ms (latency);  CPU restatement, one core: %.2f ms per frame" % (ms1, cpu))
     # the per-frame sequence Tracking runs after the two extractors, on one frame (latency, host in / host out)
     orb1 = drfe.ORBextractor(1000, 1.2, 8, 20, 7, W, H)
     cape1 = drfe.CAPE(H, W, 20, 20, False, bench.MIN_COS, 50.0)
