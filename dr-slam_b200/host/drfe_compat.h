@@ -49,6 +49,16 @@ struct Mat32f {
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
 };
 
+// 16-bit image (cv::Mat CV_16UC1: the raw depth map), view only
+struct Mat16u {
+  int rows = 0, cols = 0;
+  size_t step = 0;              // bytes
+  const uint16_t* data = nullptr;
+  Mat16u() = default;
+  Mat16u(int r, int c, const uint16_t* d, size_t step_bytes) : rows(r), cols(c), step(step_bytes), data(d) {}
+  bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+};
+
 // column-major N x 3 float matrix (the role of Eigen::MatrixXf in CAPE::process)
 struct MatrixXf {
   int nrows = 0, ncols = 0;

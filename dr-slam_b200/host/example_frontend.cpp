@@ -5,6 +5,7 @@
 // like Tracking does: the per-frame steps on the keypoints, Frame::ComputeBoW, and the two whole-function matchers with
 // the frame matched against itself (identity pose / itself as the keyframe).
 //   build:  g++ -std=c++17 -O2 example_frontend.cpp -o example_frontend -L.. -ldrfe -Wl,-rpath,'$ORIGIN/..' -lpthread
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
@@ -12,6 +13,7 @@
 #include "CAPE.h"
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include "PlaneExtractor.h"
 #include "drfe_synth.h"   // tools/synth: the tests' input generator, compiled into this example, not part of libdrfe
 
 static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
@@ -90,6 +92,39 @@ int main(int argc, char** argv) {
       printf("words %u bow %zu bow_hash %016llx fv %zu fv_hash %016llx proj %d proj_hash %016llx bowmatch %d bowmatch_hash %016llx\n", voc.size(),
              bow.size(), (unsigned long long)hb, fv.size(), (unsigned long long)hf, nproj, (unsigned long long)fnv1a(mp.data(), (size_t)n * 4), nbow,
              (unsigned long long)fnv1a(mb.data(), (size_t)n * 4));
+    }
+    // the plane extractor Frame::Frame runs (Frame.cc:126 -> ComputePlanes :937-949) on the 16-bit depth map; the synthetic
+    // sensor's isolated dropouts are filled from the left first (INIT_STRICT drops every window with a missing pixel)
+    {
+      std::vector<uint16_t> d16((size_t)W * H);
+      for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+          uint16_t v = (uint16_t)lrintf(depth[(size_t)r * W + c] * 5000.f);
+          if (v == 0 && c > 0) v = d16[(size_t)r * W + c - 1];
+          d16[(size_t)r * W + c] = v;
+        }
+      Planar_SLAM::PlaneDetection planeDetector;
+      planeDetector.readDepthImage(drfe_compat::Mat16u(H, W, d16.data(), (size_t)W * sizeof(uint16_t)), K, 1.0f / 5000.0f);
+      planeDetector.runPlaneDetection();
+      uint64_t hv = 1469598103934665603ull, hp = hv;
+      size_t nv = 0;
+      for (int i = 0; i < planeDetector.plane_num_; ++i) {
+        auto& indices = planeDetector.plane_vertices_[i];
+        nv += indices.size();
+        hv = fnv1a(indices.data(), indices.size() * sizeof(int), hv);
+        for (int j : indices) {                                          // Frame.cc:958-963
+          const float p[3] = {(float)planeDetector.cloud.vertices[j][0], (float)planeDetector.cloud.vertices[j][1], (float)planeDetector.cloud.vertices[j][2]};
+          hp = fnv1a(p, sizeof(p), hp);
+        }
+      }
+      printf("peac planes %d seg_hash %016llx vertices %zu index_hash %016llx point_hash %016llx", planeDetector.plane_num_,
+             (unsigned long long)fnv1a(planeDetector.seg_output.data, (size_t)W * H), nv, (unsigned long long)hv, (unsigned long long)hp);
+      for (int i = 0; i < planeDetector.plane_num_; ++i) {
+        auto pl = planeDetector.plane_filter.extractedPlanes[i];
+        printf(" | %.17g %.17g %.17g %.17g", pl->normal[0], pl->normal[1], pl->normal[2],
+               -(pl->normal[0] * pl->center[0] + pl->normal[1] * pl->center[1] + pl->normal[2] * pl->center[2]));
+      }
+      printf("\n");
     }
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());

@@ -6,12 +6,14 @@
 //                                                                                        PlaneExtractor.cpp:149-154
 // Prints the same digest line as dr-slam_b200/host/example_frontend (tests/test_gpu_adapters.py compares the two and
 // the oracle).  Test infrastructure; build: see tests/test_host_adapters_opencv.py.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
 
 #include "CAPE.h"
 #include "ORBextractor.h"
+#include "PlaneExtractor.h"
 #include "drfe_synth.h"
 
 static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
@@ -83,6 +85,41 @@ int main(int argc, char** argv) {
     cv::Mat d2;
     orb(cv::Mat(), cv::Mat(), untouched, d2);
     printf("empty_image keeps %zu\n", untouched.size());
+    // planeDetector.readDepthImage(Depth, K, depthFactor); planeDetector.runPlaneDetection()   Frame.cc:940-942
+    {
+      cv::Mat Depth(H, W, CV_16UC1);
+      for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+          unsigned short v = (unsigned short)lrintf(imDepth.at<float>(r, c) * 5000.f);
+          if (v == 0 && c > 0) v = Depth.at<unsigned short>(r, c - 1);
+          Depth.at<unsigned short>(r, c) = v;
+        }
+      Planar_SLAM::PlaneDetection planeDetector;
+      planeDetector.readColorImage(im);
+      planeDetector.readDepthImage(Depth, K, 1.0f / 5000.0f);
+      planeDetector.runPlaneDetection();
+      uint64_t hv = 1469598103934665603ull, hp = hv, hs = hv;
+      size_t nv = 0;
+      for (int i = 0; i < planeDetector.plane_num_; ++i) {
+        auto& indices = planeDetector.plane_vertices_[i];
+        nv += indices.size();
+        hv = fnv1a(indices.data(), indices.size() * sizeof(int), hv);
+        for (int j : indices) {
+          const float p[3] = {(float)planeDetector.cloud.vertices[j][0], (float)planeDetector.cloud.vertices[j][1], (float)planeDetector.cloud.vertices[j][2]};
+          hp = fnv1a(p, sizeof(p), hp);
+        }
+      }
+      for (int r = 0; r < H; ++r) hs = fnv1a(planeDetector.seg_output.ptr(r), (size_t)W, hs);
+      printf("peac planes %d seg_hash %016llx vertices %zu index_hash %016llx point_hash %016llx", planeDetector.plane_num_, (unsigned long long)hs, nv,
+             (unsigned long long)hv, (unsigned long long)hp);
+      for (int i = 0; i < planeDetector.plane_num_; ++i) {
+        auto extractedPlane = planeDetector.plane_filter.extractedPlanes[i];
+        printf(" | %.17g %.17g %.17g %.17g", extractedPlane->normal[0], extractedPlane->normal[1], extractedPlane->normal[2],
+               -(extractedPlane->normal[0] * extractedPlane->center[0] + extractedPlane->normal[1] * extractedPlane->center[1] +
+                 extractedPlane->normal[2] * extractedPlane->center[2]));
+      }
+      printf("\n");
+    }
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -11,10 +11,12 @@
 #include <vector>
 
 #define CV_8U 0
+#define CV_16U 2
 #define CV_32F 5
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_Assert(expr) assert(expr)
 
@@ -58,7 +60,7 @@ class Mat {
   int type() const { return type_; }
   int depth() const { return type_ & 7; }
   int channels() const { return (type_ >> 3) + 1; }
-  size_t elemSize() const { return (size_t)channels() * (depth() == CV_32F ? 4 : 1); }
+  size_t elemSize() const { return (size_t)channels() * (depth() == CV_32F ? 4 : depth() == CV_16U ? 2 : 1); }
   uchar* ptr(int r = 0) { return data + (size_t)r * step.p; }
   const uchar* ptr(int r = 0) const { return data + (size_t)r * step.p; }
   template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step.p); }

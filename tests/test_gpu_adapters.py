@@ -41,9 +41,28 @@ def test_cpp_adapters_match_oracle(drfe, orc, scene, seed):
     assert int(m.group(4)) == len(oplanes)
     assert int(m.group(5), 16) == fnv1a(oseg.tobytes())
     assert int(m.group(6)) == int((oseg > 0).sum())
-    for i, line in enumerate(out.stdout.splitlines()[1:]):
+    for i, line in enumerate(out.stdout.splitlines()[1:1 + len(oplanes)]):
         v = [float(x) for x in re.findall(r"-?\d+\.\d+", line)]
         assert np.allclose(v[:3], oplanes["normal"][i], atol=1e-5) and abs(v[3] - oplanes["d"][i]) < 1e-5
+    # Planar_SLAM::PlaneDetection (host/PlaneExtractor.h) the way Frame::ComputePlanes reads it, against the PEAC restatement
+    last = out.stdout.splitlines()[-1]
+    m = re.match(r"peac planes (\d+) seg_hash (\w+) vertices (\d+) index_hash (\w+) point_hash (\w+)(.*)", last)
+    assert m, last
+    q = np.rint(depth * 5000).astype(np.uint16)
+    col = np.where(q > 0, np.arange(640)[None, :], 0)                 # dropouts take the value to their left (as the example does)
+    q = np.take_along_axis(q, np.maximum.accumulate(col, axis=1), axis=1)
+    fac = float(np.float32(1.0) / np.float32(5000.0))
+    cloud = orc.peac_cloud(q, fac, *K)
+    pseg, pplanes, pmem, _ = orc.peac_run(cloud, 640, 480)
+    assert int(m.group(1)) == len(pplanes) and int(m.group(2), 16) == fnv1a(pseg.tobytes())
+    assert int(m.group(3)) == sum(len(x) for x in pmem)
+    if len(pmem):
+        assert int(m.group(4), 16) == fnv1a(np.concatenate(pmem).astype(np.int32).tobytes())
+        assert int(m.group(5), 16) == fnv1a(np.concatenate([cloud[x] for x in pmem]).astype(np.float32).tobytes())
+    vals = [[float(x) for x in part.split()] for part in m.group(6).split("|")[1:]]
+    for i, v in enumerate(vals):
+        assert np.array_equal(v[:3], pplanes[i, :3]) and abs(v[3] + float(pplanes[i, :3] @ pplanes[i, 3:6])) < 1e-12
+    assert len(vals) == len(pplanes)
 
 
 def test_handles_are_usable_from_fresh_host_threads(drfe, orc):

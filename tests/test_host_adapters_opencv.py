@@ -27,7 +27,7 @@ def test_opencv_and_eigen_branches_compile():
     # the matcher / vocabulary adapters sit on top of ORBextractor.h: type-check them in the same configuration
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-DDRFE_WITH_OPENCV", "-DDRFE_WITH_EIGEN",
                         "-I" + os.path.join(ROOT, "tests", "host", "mock"), "-I" + HOST, "-x", "c++", "-"],
-                       input='#include "ORBmatcher.h"\n#include "CAPE.h"\nint main() { return 0; }\n', capture_output=True, text=True, timeout=300)
+                       input='#include "ORBmatcher.h"\n#include "CAPE.h"\n#include "PlaneExtractor.h"\nint main() { return 0; }\n', capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
 
 
@@ -46,3 +46,4 @@ def test_opencv_branch_reports_what_the_standin_build_reports(scene, seed):
     # CAPE::process on an Eigen::MatrixXf cloud = the fused depth path; plane_segments_final is appended to
     assert la[1 + nplanes] == "process planes %d cylinders 0 seg_hash %s appended %d" % (nplanes, seg_hash, nplanes)
     assert la[2 + nplanes] == "empty_image keeps 3"
+    assert la[-1].startswith("peac planes") and la[-1] == lb[-1]     # Planar_SLAM::PlaneDetection (PlaneExtractor.h), cv::Mat in / out
