@@ -635,6 +635,43 @@ def main():
                 "stage_ms": {k: round(v, 4) for k, v in st7.items()}}
         del rig7
 
+    # ---- PEAC-AHC (the plane extractor that is live in Frame::Frame) on the same depth maps: an extra key
+    peac = None
+    if world == 1 and args.workload == "c640" and not args.no_extras:
+        q16 = np.rint(depth * np.float32(5000.0)).astype(np.uint16)
+        col = np.where(q16 > 0, np.arange(W)[None, None, :], 0)      # isolated dropouts take the value to their left: INIT_STRICT
+        q16 = np.take_along_axis(q16, np.maximum.accumulate(col, axis=2), axis=2)   # rejects every window with a missing pixel
+        fac = float(np.float32(1.0) / np.float32(5000.0))
+        pe = drfe.PEAC(W, H, max_batch=B, device=local_rank)
+        d_q = torch.from_numpy(q16.view(np.int16)).cuda(local_rank)
+
+        def peac_step():
+            pe.enqueue(d_q.data_ptr(), fac, *K, nframes=B, mem_kind=drfe.MEM_DEVICE)
+            pe.sync()
+        peac_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            peac_step()
+        ms_p = (time.perf_counter() - t0) / 3 * 1e3
+        npl_p = pe.download()[2]
+        pe1 = drfe.PEAC(W, H, device=local_rank)
+
+        def peac_one(i):
+            pe1.enqueue(q16[i % B][None], fac, *K)
+            pe1.download()
+        lat = median_ms(peac_one, 10)
+        from oracle import oracle as _orc
+        t0 = time.perf_counter()
+        for i in range(4):
+            _orc.peac_run(_orc.peac_cloud(q16[i * 8], fac, *K), W, H)
+        cpu_ms = (time.perf_counter() - t0) / 4 * 1e3
+        peac = {"metric": "PEAC-AHC plane extraction frames/sec (PlaneDetection::readDepthImage + runPlaneDetection)", "value": B / (ms_p * 1e-3),
+                "unit": "frames/s", "ms_per_batch": ms_p, "frames": B, "planes_per_frame": float(npl_p.mean()),
+                "single_frame_ms": lat, "cpu_port_ms_per_frame": cpu_ms, "cpu_cores": 1, "bound": "latency",
+                "note": "one CTA per frame (the clustering and the region growing are sequential in the reference); depth resident on the "
+                        "device, wall clock around enqueue + sync; CPU = oracle/peac_oracle.cpp on one core, 4 frames"}
+        del pe, pe1, d_q
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -711,6 +748,7 @@ def main():
                                 "note": "same call fed float depth (what PlaneDetection_CAPE::readDepthImage takes)"}},
         "strong": strong,
         "c720": c720,
+        "peac": peac,
         "single_frame": single,
         "gpu_launches": int(launches),
         "clocks": clocks,
