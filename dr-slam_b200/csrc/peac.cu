@@ -34,6 +34,7 @@
 namespace drfe {
 
 static const int kPeacThreads = 128;
+static const int kFloodPer = 2;            // queue entries a thread takes per chunk of the region growing
 static const int kPeacMaxPlanes = 255;     // seg_output is uchar (plid + 1)
 static const int kPeacCand = 1024;         // merge candidates of one step
 
@@ -46,7 +47,7 @@ struct PeacNode {
 
 struct PeacDev {
   int W, H, winW, winH, Nw, Nh, NB, nwords, B, nslots, min_support, qcap;
-  int flood_chunk;          // queue entries the region growing takes at a time (kPeacThreads; 1 = the sequential loop, for checks)
+  int flood_chunk;          // queue entries the region growing takes at a time (kFloodPer * kPeacThreads; 1 = the sequential loop, for checks)
   double depthSigma, stdTol_init, stdTol_merge, z_near, z_far, angle_near, angle_far, sim_merge, sim_refine, depthAlpha, depthChangeTol;
   float max_depth, depth_factor, fx, fy, cx, cy;
   const uint16_t* depth; long long depth_rs, depth_fs;
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
   __shared__ int s_old[kPeacMaxPlanes + 1], s_plidmap[kPeacMaxPlanes + 1], s_valid[kPeacMaxPlanes + 1];
   __shared__ uint32_t s_padj[kPeacMaxPlanes + 1][8];            // plane adjacency found by the region growing (bit = plid)
   __shared__ int s_scan[kPeacThreads];
+  __shared__ double s_pl[kPeacMaxPlanes + 1][7];            // normal, centre, mse of the first-pass planes (region growing)
   const int slot = blockIdx.x;
   uint32_t* adj = P.adj + (long long)slot * NB * nw;
   int* trail = P.trail + (long long)slot * W * H;
@@ -621,103 +623,148 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
     }
     __syncthreads();
     stamp(3);
-    // ---- floodFill (:434-488), kPeacThreads queue entries per chunk
+    // ---- floodFill (:434-488), kFloodPer * kPeacThreads queue entries per chunk.  Everything about a visit that does not depend
+    // on mutable state is computed before the rounds (the vertex of the visited pixel, its distance to the visiting plane, the
+    // 3-sigma test); a round then costs one trip to the L2 (first / trail / dist of every pending visit are requested together).
+    for (int i = tid; i < n_old; i += kPeacThreads) {
+      const PeacNode& pl = nodes[s_old[i]];
+      s_pl[i][0] = pl.normal[0]; s_pl[i][1] = pl.normal[1]; s_pl[i][2] = pl.normal[2];
+      s_pl[i][3] = pl.center[0]; s_pl[i][4] = pl.center[1]; s_pl[i][5] = pl.center[2];
+      s_pl[i][6] = pl.mse;
+    }
+    __syncthreads();
     const double sim_refine = P.sim_refine;
-    const int chunk = P.flood_chunk;
+    const int chunk = min(P.flood_chunk, kFloodPer * kPeacThreads);
     for (int q0 = 0, q1; q0 < qlen; q0 = q1) {
       q1 = min(q0 + chunk, qlen);                                   // the entries queued when the chunk starts
-      const int k = q0 + tid;
-      const bool have = k < q1;
-      int tgt[4] = {-1, -1, -1, -1};
-      int plid = 0;
-      double pn[3] = {0, 0, 0}, pc[3] = {0, 0, 0}, pmse = 0;
-      if (have) {
+      int tgt[kFloodPer][4], plid[kFloodPer];
+      float cd[kFloodPer][4];
+      uint32_t pending = 0, pushed = 0, okv = 0;                    // bit 4 * j + it
+#pragma unroll
+      for (int j = 0; j < kFloodPer; ++j) {
+        const int k = q0 + j * kPeacThreads + tid;
+        plid[j] = 0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) { tgt[j][it] = -1; cd[j][it] = -1.f; }
+        if (k >= q1) continue;
         const int2 e = queue[k];
-        plid = e.y;
+        plid[j] = e.y;
         const int sy = e.x / W, sx = e.x - sy * W;
-        const PeacNode& pl = nodes[s_old[plid]];
-        pn[0] = pl.normal[0]; pn[1] = pl.normal[1]; pn[2] = pl.normal[2];
-        pc[0] = pl.center[0]; pc[1] = pl.center[1]; pc[2] = pl.center[2];
-        pmse = pl.mse;
-        // getValid4Neighbor order: left, right, up, down; the early `continue`s that do not depend on mutable state are taken here
+        // getValid4Neighbor order: left, right, up, down; only pixels outside the kept blocks change (inside, trail stays the block's plane)
         const int nbp[4] = {sx > 0 ? e.x - 1 : -1, sx < W - 1 ? e.x + 1 : -1, sy > 0 ? e.x - W : -1, sy < H - 1 ? e.x + W : -1};
+        double z[4];
+        bool has[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int c = nbp[it];
+          has[it] = false; z[it] = 0;
           if (c < 0) continue;
           const int cy = c / W, cx = c - cy * W;
           const int by = cy / winH, bx = cx / winW;
           const int blk = (by < Nh && bx < Nw) ? by * Nw + bx : -1;
-          if (blk >= 0 && blkMap[blk] >= 0) continue;             // only pixels outside the kept blocks change (their trail stays the block's plane)
-          tgt[it] = c;
+          if (blk >= 0 && blkMap[blk] >= 0) continue;
+          tgt[j][it] = c;
+          pending |= 1u << (4 * j + it);
+          has[it] = peac_z(P, f, cy, cx, z[it]);
         }
-      }
-      uint32_t pending = 0, pushed = 0;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) if (tgt[it] >= 0) pending |= 1u << it;
-      // rounds: every pixel serves the earliest of its pending visits (visit number = 4 * entry + neighbour slot)
-      for (;;) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) if (pending >> it & 1u) atomicMin(&first[tgt[it]], 4 * tid + it);
-        const int any = __syncthreads_or(pending != 0);
-        if (!any) break;
+        const double* pl = s_pl[plid[j]];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          if (!(pending >> it & 1u)) continue;
-          const int c = tgt[it];
-          // (first / trail / dist are written by other threads of the CTA, first by atomics that live in L2: read and
-          // write them past the L1 with ld.cg / st.cg so that no stale line is seen)
-          if (__ldcg(&first[c]) != 4 * tid + it) continue;
-          pending &= ~(1u << it);
-          __stcg(&first[c], 0x7FFFFFFF);
-          const int tr = __ldcg(&trail[c]);
-          if (tr <= -6) continue;
-          if (tr >= 0 && tr == plid) continue;
+          if (!has[it]) continue;
+          const int c = tgt[j][it];
           const int cy = c / W, cx = c - cy * W;
-          double pt[3];
-          bool ok = peac_get(P, f, cy, cx, pt[0], pt[1], pt[2]);
-          float cdist = -1.f;
-          if (ok) {
-            const double sd = pn[0] * (pt[0] - pc[0]) + pn[1] * (pt[1] - pc[1]) + pn[2] * (pt[2] - pc[2]);
-            cdist = (float)fabs(sd);
-            ok = (double)cdist * (double)cdist < 9 * pmse + 1e-5;
-          }
-          if (ok) {
-            if (tr >= 0) {
-              const PeacNode& npl = nodes[s_old[tr]];
-              const double sim = fabs(pn[0] * npl.normal[0] + pn[1] * npl.normal[1] + pn[2] * npl.normal[2]);
-              if (sim >= sim_refine) {
-                atomicOr(&s_padj[tr][plid >> 5], 1u << (plid & 31));
-                atomicOr(&s_padj[plid][tr >> 5], 1u << (tr & 31));
-              }
-            }
-            if (cdist < __ldcg(&dist[c])) {
-              __stcg(&trail[c], plid);
-              __stcg(&dist[c], cdist);
-              pushed |= 1u << it;
-            } else if (tr < 0) {
-              __stcg(&trail[c], tr - 1);
-            }
-          } else {
-            if (tr < 0) __stcg(&trail[c], tr - 1);
-          }
+          const double x = ((double)cx - (double)P.cx) * z[it] / (double)P.fx;
+          const double y = ((double)cy - (double)P.cy) * z[it] / (double)P.fy;
+          const double sd = pl[0] * (x - pl[3]) + pl[1] * (y - pl[4]) + pl[2] * (z[it] - pl[5]);
+          const float cdist = (float)fabs(sd);
+          cd[j][it] = cdist;
+          if ((double)cdist * (double)cdist < 9 * pl[6] + 1e-5) okv |= 1u << (4 * j + it);
         }
+      }
+      // rounds: every pixel serves the earliest of its pending visits (visit number = 4 * entry of the chunk + neighbour slot)
+      for (;;) {
+#pragma unroll
+        for (int j = 0; j < kFloodPer; ++j)
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (pending >> (4 * j + it) & 1u) atomicMin(&first[tgt[j][it]], 4 * (j * kPeacThreads + tid) + it);
+        const int any = __syncthreads_or(pending != 0);
+        if (!any) break;
+        // (first / trail / dist are written by other threads of the CTA, first by atomics that live in L2: read and write them
+        // past the L1 with ld.cg / st.cg.  trail and dist are read before it is known whether the visit is served this round:
+        // the values are used by the winner only, and nobody else writes that pixel in this round.)
+        int fv[kFloodPer][4], trv[kFloodPer][4];
+        float dv[kFloodPer][4];
+#pragma unroll
+        for (int j = 0; j < kFloodPer; ++j)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            fv[j][it] = -1; trv[j][it] = 0; dv[j][it] = 0.f;
+            if (pending >> (4 * j + it) & 1u) {
+              const int c = tgt[j][it];
+              fv[j][it] = __ldcg(&first[c]); trv[j][it] = __ldcg(&trail[c]); dv[j][it] = __ldcg(&dist[c]);
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < kFloodPer; ++j)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const uint32_t bit = 1u << (4 * j + it);
+            if (!(pending & bit)) continue;
+            if (fv[j][it] != 4 * (j * kPeacThreads + tid) + it) continue;
+            const int c = tgt[j][it];
+            pending &= ~bit;
+            __stcg(&first[c], 0x7FFFFFFF);
+            const int tr = trv[j][it];
+            if (tr <= -6) continue;
+            if (tr >= 0 && tr == plid[j]) continue;
+            if (okv & bit) {
+              if (tr >= 0) {
+                const double* pl = s_pl[plid[j]];
+                const double* npl = s_pl[tr];
+                const double sim = fabs(pl[0] * npl[0] + pl[1] * npl[1] + pl[2] * npl[2]);
+                if (sim >= sim_refine) {
+                  atomicOr(&s_padj[tr][plid[j] >> 5], 1u << (plid[j] & 31));
+                  atomicOr(&s_padj[plid[j]][tr >> 5], 1u << (tr & 31));
+                }
+              }
+              if (cd[j][it] < dv[j][it]) {
+                __stcg(&trail[c], plid[j]);
+                __stcg(&dist[c], cd[j][it]);
+                pushed |= bit;
+              } else if (tr < 0) {
+                __stcg(&trail[c], tr - 1);
+              }
+            } else {
+              if (tr < 0) __stcg(&trail[c], tr - 1);
+            }
+          }
         __syncthreads();
       }
-      // append the claimed pixels in visit order
-      const int mine = __popc(pushed);
-      int inc = mine;
+      // append the claimed pixels in visit order: all entries j = 0 of the chunk, then j = 1 (counts packed 16 bits each)
+      uint32_t mine = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-      if (lane == 31) s_tmp[20 + wid] = inc;
+      for (int j = 0; j < kFloodPer; ++j) mine |= (uint32_t)__popc((pushed >> (4 * j)) & 15u) << (16 * j);
+      uint32_t inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_tmp[20 + wid] = (int)inc;
       __syncthreads();
-      int basep = 0, tot = 0;
-      for (int w = 0; w < kPeacThreads / 32; ++w) { if (w < wid) basep += s_tmp[20 + w]; tot += s_tmp[20 + w]; }
+      uint32_t basep = 0, totp = 0;
+      for (int w = 0; w < kPeacThreads / 32; ++w) { if (w < wid) basep += (uint32_t)s_tmp[20 + w]; totp += (uint32_t)s_tmp[20 + w]; }
+      int tot = 0;
+#pragma unroll
+      for (int j = 0; j < kFloodPer; ++j) tot += (int)((totp >> (16 * j)) & 0xFFFFu);
       if (qlen + tot > P.qcap) { if (tid == 0) atomicOr(P.status, 2); tot = 0; }
       else {
-        int at = qlen + basep + inc - mine;
+        int before = 0;                                             // pushes of the earlier j
 #pragma unroll
-        for (int it = 0; it < 4; ++it) if (pushed >> it & 1u) queue[at++] = make_int2(tgt[it], plid);
+        for (int j = 0; j < kFloodPer; ++j) {
+          int at = qlen + before + (int)(((basep + inc - mine) >> (16 * j)) & 0xFFFFu);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) if (pushed >> (4 * j + it) & 1u) queue[at++] = make_int2(tgt[j][it], plid[j]);
+          before += (int)((totp >> (16 * j)) & 0xFFFFu);
+        }
       }
       qlen += tot;
       __syncthreads();
@@ -919,7 +966,7 @@ int drfe_peac_create(int width, int height, const drfe_peac_params* params, int 
   D.W = width; D.H = height; D.winW = prm.window_width; D.winH = prm.window_height;
   D.Nw = width / D.winW; D.Nh = height / D.winH; D.NB = D.Nw * D.Nh; D.nwords = (D.NB + 31) / 32; D.B = max_batch;
   D.min_support = prm.min_support;
-  { const char* e = getenv("DRFE_PEAC_FLOOD_CHUNK"); D.flood_chunk = e ? std::min(std::max(atoi(e), 1), kPeacThreads) : kPeacThreads; }
+  { const char* e = getenv("DRFE_PEAC_FLOOD_CHUNK"); D.flood_chunk = e ? std::min(std::max(atoi(e), 1), kFloodPer * kPeacThreads) : kFloodPer * kPeacThreads; }
   D.depthSigma = prm.depthSigma; D.stdTol_init = prm.stdTol_init; D.stdTol_merge = prm.stdTol_merge; D.z_near = prm.z_near; D.z_far = prm.z_far;
   D.angle_near = prm.angle_near; D.angle_far = prm.angle_far; D.sim_merge = prm.similarityTh_merge; D.sim_refine = prm.similarityTh_refine;
   D.depthAlpha = prm.depthAlpha; D.depthChangeTol = prm.depthChangeTol; D.max_depth = prm.max_depth;
