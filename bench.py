@@ -507,6 +507,45 @@ def main():
     assert np.array_equal(q16.astype(np.float32) * fac, depth)
     h_depth16 = pin(q16)
     e2e_u16 = world * B * e2e_steps / time_loop(lambda: step_e2e(h_depth16, float(fac)))
+    # ---- the same calls with TWO batches in flight: a second handle pair and a second set of result buffers, used alternately
+    # (step s is issued before step s-1 is finished), so that the copy-in of a batch starts while the previous batch's last
+    # chunks are still in their kernels and copying out.  Every step still moves all of its inputs and results.
+    e2e_two = None
+    if not args.no_extras:
+        orb_b = drfe.ORBextractor(wl.nfeat, 1.2, 8, 20, 7, W, H, max_batch=B, device=local_rank)
+        cape_b = drfe.CAPE(H, W, wl.cell, wl.cell, wl.cyl, MIN_COS, wl.max_merge, max_batch=B, device=local_rank)
+        pinned_like = lambda a: torch.empty(a.nbytes, dtype=torch.uint8).pin_memory().numpy().view(a.dtype).reshape(a.shape)  # noqa: E731
+        outs = [(h_kps, h_desc, h_cnt, h_seg, h_planes, h_npl), tuple(pinned_like(a) for a in (h_kps, h_desc, h_cnt, h_seg, h_planes, h_npl))]
+        pairs = [(orb, cape), (orb_b, cape_b)]
+
+        def issue(i):
+            o, c = pairs[i]
+            kp, de, cn, sg, pl, npl_ = outs[i]
+            o.extract_batch(h_gray, kp, de, cn, chunk_frames=args.chunk)
+            c.process_depth_batch(h_depth16, *K, depth_factor=float(fac), seg=sg, planes=pl, nplanes=npl_, chunk_frames=args.chunk)
+
+        def finish(i):
+            pairs[i][0].finish_batch(); pairs[i][1].finish_batch()
+
+        def run_two(n):
+            issue(0)
+            for s_ in range(1, n):
+                issue(s_ % 2)
+                finish((s_ - 1) % 2)
+            finish((n - 1) % 2)
+        run_two(3)
+        barrier()
+        n_two = 2 * e2e_steps
+        t0 = time.perf_counter()
+        run_two(n_two)
+        orb_b.sync(); cape_b.sync()
+        barrier()
+        e2e_two = {"value": world * B * n_two / max_over_ranks(time.perf_counter() - t0), "unit": "frames/s", "steps": n_two,
+                   "same_results": bool(np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+                                        and np.array_equal(outs[0][1], outs[1][1])),
+                   "note": "two handle pairs used alternately: step s is issued (drfe_orb_extract_batch + drfe_cape_process_depth_batch) before "
+                           "step s-1 is finished (drfe_*_finish_batch); all of every step's H2D and D2H bytes inside the timed region"}
+        del orb_b, cape_b
     h2d_u16 = int(h_gray.nbytes + h_depth16.nbytes)
     h2d_f32 = int(h_gray.nbytes + h_depth.nbytes)
     d2h = int(h_kps.nbytes + h_desc.nbytes + h_cnt.nbytes + h_seg.nbytes + h_planes.nbytes + h_npl.nbytes)
@@ -741,6 +780,7 @@ def main():
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "pcie": pcie, "pcie_frac": e2e_u16 / pcie["ceiling_fps"],
                 "pool": pool_res,
+                "two_in_flight": e2e_two,
                 "api": "drfe_orb_extract_batch + drfe_cape_process_depth_batch (gray u8 + raw u16 depth as Frame::Frame gets "
                        "them, depth scaled on the device as Frame.cc:113-115 does; pinned host buffers, 32-frame chunks "
                        "(8/16-frame chunks at both ends) pipelined H2D | kernels | D2H; one process per GPU, its host threads pinned to their own cores)",
