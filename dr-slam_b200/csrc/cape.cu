@@ -245,6 +245,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // k_cape_cloud materialises the cell-major cloud when a caller asks for it (drfe_cape_get_cloud / plane_points).
 template <int MODE, int CELL>
 __global__ void __launch_bounds__(kSumsThreads, 6) k_cape_sums(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  DRFE_GRID_DEP();
   constexpr bool FROM_DEPTH = MODE != 0;
   extern __shared__ __align__(16) float s_zall[];           // [8 groups][2 slots][npc]
   const CapeDev& P = *Pp;
@@ -539,6 +540,7 @@ __global__ void __launch_bounds__(256) k_cape_cloud(const CapeDev* __restrict__ 
 // widened to double, fitPlane, the depth-dependent MSE test, and the cell's merge tolerance
 // (CAPE.cpp:69-73).
 __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  DRFE_GRID_DEP();
   // the 152-byte PlaneSeg records of the block's 128 cells leave through shared memory as full 16-byte words of
   // consecutive addresses (a struct store per thread touched 32 lines per instruction)
   __shared__ __align__(16) drfe_plane s_out[128];
@@ -593,6 +595,7 @@ __global__ void __launch_bounds__(128) k_cape_fit(const CapeDev* __restrict__ Pp
 // RegionGrowing (CAPE.cpp:485-506) would activate the cell from each of its four neighbours.  Both depend on the
 // cell and its neighbours only, so they are computed here by 196 k threads instead of by the grid stage's 128.
 __global__ void __launch_bounds__(128) k_cape_edges(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  DRFE_GRID_DEP();
   const CapeDev& P = *Pp;
   const int gid0 = blockIdx.x * 128 + threadIdx.x;
   if (gid0 >= nframes * P.ncells) return;
@@ -929,6 +932,7 @@ enum { BV_FL = 0, BV_FR, BV_FU, BV_FD, BV_U, BV_A, BV_B, BV_M, BV_H, BV_C0, BV_C
 // CYL: compiled with the cylinder stages (cylinder_detection); the plain instantiation carries none of that code
 template <int THREADS, bool CYL>
 __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict__ Pp, int f0) {
+  DRFE_GRID_DEP();
   extern __shared__ __align__(16) uint8_t smem[];
   const CapeDev& P = *Pp;
   const int f = blockIdx.x + f0, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1482,6 +1486,7 @@ __global__ void __launch_bounds__(THREADS) k_cape_grid(const CapeDev* __restrict
 //                         longer writes.
 template <bool CYL>
 __global__ void __launch_bounds__(256) k_cape_refine_plan(const CapeDev* __restrict__ Pp, int f0, int nframes) {
+  DRFE_GRID_DEP();
   const CapeDev& P = *Pp;
   const int gid0 = blockIdx.x * 256 + threadIdx.x;
   if (gid0 >= nframes * P.ncells) return;
@@ -1513,6 +1518,7 @@ __global__ void __launch_bounds__(256) k_cape_refine_plan(const CapeDev* __restr
 // for d = cell width, cell height
 static const int kPaintRows = 5;
 __global__ void __launch_bounds__(256) k_cape_paint(const CapeDev* __restrict__ Pp, int f0, uint32_t magic_cw, uint32_t magic_ch) {
+  DRFE_GRID_DEP();
   const CapeDev& P = *Pp;
   const int W = P.W, H = P.H;
   const int c0 = 4 * (blockIdx.x * 64 + threadIdx.x), r0 = (blockIdx.y * 4 + threadIdx.y) * kPaintRows;
@@ -1553,6 +1559,7 @@ __global__ void __launch_bounds__(256) k_cape_paint(const CapeDev* __restrict__ 
 static const int kBorderWarps = 4;     // warps per block of k_cape_refine_border
 template <bool CYL, int MODE>
 __global__ void __launch_bounds__(kBorderWarps * 32, CYL ? 4 : 5) k_cape_refine_border(const CapeDev* __restrict__ Pp) {
+  DRFE_GRID_DEP();
   const CapeDev& P = *Pp;
   const int lane = threadIdx.x & 31;
   const int nlist = *P.border_count;
@@ -2241,6 +2248,7 @@ int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, 
 // all kernels of frames [f0, f0 + n) on the handle's stream (the device descriptor must be current)
 static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   NvtxRange nvtx_("cape_launch");
+  const bool drfe_pdl_ = pdl_enabled() && n <= kPdlMaxFrames;
   cudaStream_t st = h->stream;
   const int ncell_total = n * h->hd.ncells;
   const size_t sums_smem = (size_t)(kSumsThreads / 16) * 2 * h->hd.npc * sizeof(float);
@@ -2248,29 +2256,29 @@ static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   const int sums_grid = (sums_groups * 16 + kSumsThreads - 1) / kSumsThreads;
   const int mode = h->hd.depth16 ? 2 : (h->hd.depth ? 1 : 0);
   const int cell = (h->hd.cw == h->hd.ch && (h->hd.cw == 20 || h->hd.cw == 10)) ? h->hd.cw : 0;
-#define DRFE_SUMS(M, C) DRFE_LAUNCH((k_cape_sums<M, C>), sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n)
+#define DRFE_SUMS(M, C) DRFE_LAUNCH_PDL((k_cape_sums<M, C>), sums_grid, kSumsThreads, sums_smem, st, h->dd, f0, n)
 #define DRFE_SUMS_MODE(C) do { if (mode == 2) DRFE_SUMS(2, C); else if (mode == 1) DRFE_SUMS(1, C); else DRFE_SUMS(0, C); } while (0)
   if (cell == 20) DRFE_SUMS_MODE(20); else if (cell == 10) DRFE_SUMS_MODE(10); else DRFE_SUMS_MODE(0);
 #undef DRFE_SUMS_MODE
 #undef DRFE_SUMS
   if (timed) h->timer.mark("cells", st);
-  DRFE_LAUNCH(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
-  DRFE_LAUNCH(k_cape_edges, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
+  DRFE_LAUNCH_PDL(k_cape_fit, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
+  DRFE_LAUNCH_PDL(k_cape_edges, (ncell_total + 127) / 128, 128, 0, st, h->dd, f0, n);
   if (timed) h->timer.mark("fit", st);
-  if (h->hd.cyl) DRFE_LAUNCH((k_cape_grid<128, true>), n, 128, h->grid_smem, st, h->dd, f0);
-  else DRFE_LAUNCH((k_cape_grid<128, false>), n, 128, h->grid_smem, st, h->dd, f0);
+  if (h->hd.cyl) DRFE_LAUNCH_PDL((k_cape_grid<128, true>), n, 128, h->grid_smem, st, h->dd, f0);
+  else DRFE_LAUNCH_PDL((k_cape_grid<128, false>), n, 128, h->grid_smem, st, h->dd, f0);
   if (timed) h->timer.mark("grid", st);
   {
     DRFE_CUDA(cudaMemsetAsync(h->hd.border_count, 0, sizeof(int), st));
-    if (h->hd.cyl) DRFE_LAUNCH(k_cape_refine_plan<true>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
-    else DRFE_LAUNCH(k_cape_refine_plan<false>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
+    if (h->hd.cyl) DRFE_LAUNCH_PDL(k_cape_refine_plan<true>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
+    else DRFE_LAUNCH_PDL(k_cape_refine_plan<false>, (ncell_total + 255) / 256, 256, 0, st, h->dd, f0, n);
     auto magic = [](unsigned d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };
     const unsigned q = (unsigned)(h->hd.W + 3) / 4;
-    DRFE_LAUNCH(k_cape_paint, dim3((q + 63) / 64, (unsigned)(h->hd.H + 4 * kPaintRows - 1) / (4 * kPaintRows), (unsigned)n), dim3(64, 4), 0, st, h->dd, f0, magic((unsigned)h->hd.cw),
+    DRFE_LAUNCH_PDL(k_cape_paint, dim3((q + 63) / 64, (unsigned)(h->hd.H + 4 * kPaintRows - 1) / (4 * kPaintRows), (unsigned)n), dim3(64, 4), 0, st, h->dd, f0, magic((unsigned)h->hd.cw),
                 magic((unsigned)h->hd.ch));
     // warps loop over the list of border cells (its length is only known on the device): enough blocks to fill the GPU
     const int blocks = std::min((ncell_total + kBorderWarps - 1) / kBorderWarps, h->sm_count * 10);
-#define DRFE_REFINE(CYL, M) DRFE_LAUNCH((k_cape_refine_border<CYL, M>), blocks, kBorderWarps * 32, 0, st, h->dd)
+#define DRFE_REFINE(CYL, M) DRFE_LAUNCH_PDL((k_cape_refine_border<CYL, M>), blocks, kBorderWarps * 32, 0, st, h->dd)
 #define DRFE_REFINE_MODE(CYL) do { if (mode == 2) DRFE_REFINE(CYL, 2); else if (mode == 1) DRFE_REFINE(CYL, 1); else DRFE_REFINE(CYL, 0); } while (0)
     if (h->hd.cyl) DRFE_REFINE_MODE(true); else DRFE_REFINE_MODE(false);
 #undef DRFE_REFINE_MODE

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const OrbDev* __restrict__ P
                                                      const uint8_t* __restrict__ src,
                                                      long long row_stride, long long frame_stride, int f0,
                                                      int ci, uint32_t ci_magic, int cb, uint32_t cb_magic) {
+  DRFE_GRID_DEP();
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[0];
   const int f = blockIdx.y + f0;
@@ -163,6 +164,7 @@ static const int kPyrTW = 128, kPyrTH = 32;
 struct PyrTile { short g0, by0, sx0, sw4, sy0, nsy, pad0, pad1; };   // first 4-px group, first bordered row, source window
 
 __global__ void __launch_bounds__(256) k_pyr_resize(const OrbDev* __restrict__ Pp, int level, int f0) {
+  DRFE_GRID_DEP();
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[level];
@@ -256,6 +258,7 @@ __device__ __forceinline__ void pyr_hfilter(const PyrRow& r, int al, uint32_t sh
 }
 
 __global__ void __launch_bounds__(128, 10) k_pyr_stream(const OrbDev* __restrict__ Pp, int level, int f0, int R) {
+  DRFE_GRID_DEP();
   const OrbDev& P = *Pp;
   const LevelDev& L = P.lv[level];
   const LevelDev& S = P.lv[level - 1];
@@ -461,6 +464,7 @@ __device__ __forceinline__ uint32_t fast_compass_group(const uint32_t* __restric
 //      quadtree orders by a key)
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp, int f0, const __grid_constant__ FastMaps maps) {
+  DRFE_GRID_DEP();
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const StripDev strip = P.strips[blockIdx.x];
@@ -780,6 +784,7 @@ __device__ __forceinline__ void child_mid(const QBox& b, int& mx, int& my) {
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__ Pp, int f0) {
+  DRFE_GRID_DEP();
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
   const int level = blockIdx.x, f = blockIdx.y + f0;
@@ -1019,6 +1024,7 @@ __device__ __forceinline__ void blur_hfilter(const BlurRow& w, int (&h)[4]) {
 __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int (&h)[4]) { blur_hfilter(blur_load(row), h); }
 
 __global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp, int f0) {
+  DRFE_GRID_DEP();
   const OrbDev& P = *Pp;
   int level = 0;
   while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blur_blk_off[level + 1]) ++level;
@@ -1114,6 +1120,7 @@ __device__ __forceinline__ int dp4a_su(uint32_t w_s8, uint32_t d_u8, int acc) { 
 }
 
 __global__ void __launch_bounds__(kOdWarps * 32, 8) k_orient_describe(const OrbDev* __restrict__ Pp, int f0) {
+  DRFE_GRID_DEP();
   __shared__ __align__(16) uint8_t s_ring[kOdWarps][kOdWarpBytes];
   const OrbDev& P = *Pp;
   const int level = blockIdx.y, f = blockIdx.z + f0;
@@ -1741,6 +1748,7 @@ __global__ void __launch_bounds__(kTrackThreads) k_search_local_points(const Orb
 }
 
 __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes) {
+  DRFE_GRID_DEP();
   const OrbDev& P = *Pp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nframes * P.nlevels) { P.cand_cnt[f0 * P.nlevels + i] = 0; P.lkp_cnt[f0 * P.nlevels + i] = 0; }
@@ -2180,10 +2188,11 @@ int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, in
 // all kernels of frames [f0, f0 + n) on the handle's stream; src/rs/fs address frame 0 of the batch
 static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
   NvtxRange nvtx_("orb_launch");
+  const bool drfe_pdl_ = pdl_enabled() && n <= kPdlMaxFrames;
   h->post_valid = false;         // the keypoints drfe_orb_frame_post worked on are being replaced
   const OrbDev& D = h->hd;
   const int nl = D.nlevels;
-  DRFE_LAUNCH(k_zero_counts, (n * nl + 255) / 256, 256, 0, st, h->dd, f0, n);
+  DRFE_LAUNCH_PDL(k_zero_counts, (n * nl + 255) / 256, 256, 0, st, h->dd, f0, n);
   {
     const LevelDev& L = D.lv[0];
     const int chunks = (kXOff + L.w + 20 + 15) / 16;
@@ -2191,7 +2200,7 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
     const int ci = vec_ok ? L.w / 16 : 0, cb = chunks - ci;
     const uint32_t ci_magic = ci ? (uint32_t)(((1ull << 32) + ci - 1) / ci) : 0, cb_magic = (uint32_t)(((1ull << 32) + cb - 1) / cb);
     const long long threads = (long long)L.rows * (ci + cb);
-    DRFE_LAUNCH(k_pyr_level0, dim3((unsigned)((threads + 255) / 256), n), 256, 0, st, h->dd, src, rs, fs, f0, ci, ci_magic, cb, cb_magic);
+    DRFE_LAUNCH_PDL(k_pyr_level0, dim3((unsigned)((threads + 255) / 256), n), 256, 0, st, h->dd, src, rs, fs, f0, ci, ci_magic, cb, cb_magic);
   }
   for (int l = 1; l < nl; ++l) {
     const LevelDev& L = D.lv[l];
@@ -2201,19 +2210,19 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
       const long long px = (long long)L.w * L.h * n;
       const int R = px >= (24 << 20) ? kPyrR : (px >= (8 << 20) ? 8 : 4);
       const int strips = (L.h + R - 1) / R;
-      DRFE_LAUNCH(k_pyr_stream, dim3((L.pcol_groups + 31) / 32, (strips + 3) / 4, n), dim3(32, 4), 0, st, h->dd, l, f0, R);
+      DRFE_LAUNCH_PDL(k_pyr_stream, dim3((L.pcol_groups + 31) / 32, (strips + 3) / 4, n), dim3(32, 4), 0, st, h->dd, l, f0, R);
     } else {
-      DRFE_LAUNCH(k_pyr_resize, dim3(L.ptile_cnt, n), 256, h->pyr_smem, st, h->dd, l, f0);
+      DRFE_LAUNCH_PDL(k_pyr_resize, dim3(L.ptile_cnt, n), 256, h->pyr_smem, st, h->dd, l, f0);
     }
   }
   if (timed) h->timer.mark("pyramid", st);
-  DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps);
+  DRFE_LAUNCH_PDL(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps);
   if (timed) h->timer.mark("fast", st);
-  DRFE_LAUNCH(k_quadtree<256>, dim3(nl, n), 256, h->quad_smem, st, h->dd, f0);
+  DRFE_LAUNCH_PDL(k_quadtree<256>, dim3(nl, n), 256, h->quad_smem, st, h->dd, f0);
   if (timed) h->timer.mark("quadtree", st);
-  DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, n), 256, 0, st, h->dd, f0);
+  DRFE_LAUNCH_PDL(k_blur, dim3(h->blur_blocks, n), 256, 0, st, h->dd, f0);
   if (timed) h->timer.mark("blur", st);
-  DRFE_LAUNCH(k_orient_describe, dim3((h->max_lkp + kOdWarps * kOdG - 1) / (kOdWarps * kOdG), nl, n), kOdWarps * 32, 0, st, h->dd, f0);
+  DRFE_LAUNCH_PDL(k_orient_describe, dim3((h->max_lkp + kOdWarps * kOdG - 1) / (kOdWarps * kOdG), nl, n), kOdWarps * 32, 0, st, h->dd, f0);
   if (timed) h->timer.mark("orient_describe", st);
   return DRFE_OK;
 }
