@@ -782,6 +782,7 @@ __device__ __forceinline__ void child_mid(const QBox& b, int& mx, int& my) {
   mx = b.x0 + hx; my = b.y0 + hy;
 }
 
+static const int kQuadStage = 6144;       // candidate keys of one (frame, level) list held in shared memory by k_quadtree
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__ Pp, int f0) {
   DRFE_GRID_DEP();
@@ -813,6 +814,22 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
   uint16_t* node_of = P.node_of + (long long)f * P.cand_fstride + L.cand_off;
   int* out_cnt = P.lkp_cnt + f * P.nlevels + level;
   if (n == 0) { if (tid == 0) *out_cnt = 0; return; }
+  // every pass walks all keys (packed position + response, and the node each key sits in): up to kQuadStage of them live in shared
+  // memory for the whole kernel — from global memory each pass paid an L2 round trip per key (node_of is rewritten every pass,
+  // so the L1 never holds it); the kernel is a chain of such passes (58 -> ~25 us for one 640x480 level-0 list)
+  if (n <= kQuadStage) {
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(remap_keep + NC) + 15) & ~(uintptr_t)15);
+    for (int k0 = tid; k0 < n; k0 += 4 * THREADS) {
+      uint32_t e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = (k0 + u * THREADS < n) ? keys[k0 + u * THREADS] : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (k0 + u * THREADS < n) s_keys[k0 + u * THREADS] = e[u];
+    }
+    keys = s_keys;
+    node_of = reinterpret_cast<uint16_t*>(s_keys + kQuadStage);
+    __syncthreads();
+  }
 
   QBox* box = boxA; QBox* nbox = boxB;
   int* cnt = cntA; int* ncnt = cntB;
@@ -820,12 +837,16 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
   // ---- roots (ORBextractor.cc:543-592): key -> root by int(x / hX); empty roots dropped
   for (int i = tid; i < NC; i += THREADS) { cnt[i] = 0; }
   __syncthreads();
-  for (int k = tid; k < n; k += THREADS) {
-    const int x = keys[k] & 0xFFF;
-    int r = (int)__fdiv_rn((float)x, L.hX);
-    r = min(r, L.nIni - 1);
-    node_of[k] = (uint16_t)r;
-    atomicAdd(&cnt[r], 1);
+  for (int k0 = tid; k0 < n; k0 += 4 * THREADS) {
+    int r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = (k0 + u * THREADS < n) ? (int)(keys[k0 + u * THREADS] & 0xFFF) : 0;
+      r[u] = min((int)__fdiv_rn((float)x, L.hX), L.nIni - 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u * THREADS < n) { node_of[k0 + u * THREADS] = (uint16_t)r[u]; atomicAdd(&cnt[r[u]], 1); }
   }
   __syncthreads();
   int S = 0;
@@ -865,16 +886,29 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
     const int V = block_excl_scan<THREADS>(a_rank, S, warp_tot);   // a_rank[p] = compact idx
     if (V == 0) break;                                             // nothing to split: size unchanged
     // 2. classify the keys of candidate nodes into their 4 children (DivideNode :515-531)
-    for (int k = tid; k < n; k += THREADS) {
-      const int nd = node_of[k] & 0x3FFF;
-      if (!a_tmp[nd]) continue;
-      const uint32_t e = keys[k];
-      const int x = e & 0xFFF, y = (e >> 12) & 0xFFF;
-      int mx, my;
-      child_mid(box[nd], mx, my);
-      const int c = (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
-      atomicAdd(&ccnt[4 * nd + c], 1);
-      node_of[k] = (uint16_t)(nd | (c << 14));
+    for (int k0 = tid; k0 < n; k0 += 4 * THREADS) {              // four keys per trip: the loads of all four go out first
+      int nd[4];
+      uint32_t e[4];
+      bool act[4];
+      QBox bx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * THREADS;
+        nd[u] = (k < n) ? (node_of[k] & 0x3FFF) : 0;
+        e[u] = (k < n) ? keys[k] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { act[u] = (k0 + u * THREADS < n) && a_tmp[nd[u]]; bx[u] = box[nd[u]]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!act[u]) continue;
+        const int x = e[u] & 0xFFF, y = (e[u] >> 12) & 0xFFF;
+        int mx, my;
+        child_mid(bx[u], mx, my);
+        const int c = (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
+        atomicAdd(&ccnt[4 * nd[u] + c], 1);
+        node_of[k0 + u * THREADS] = (uint16_t)(nd[u] | (c << 14));
+      }
     }
     // 3. split order.  coarse: list order.  fine: sort by (nKeys, creation seq) ascending and
     //    walk from the back (:684-686) == (nKeys desc, list position asc).
@@ -960,9 +994,18 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
       remap_keep[p] = (unsigned short)np;
     }
     __syncthreads();
-    for (int k = tid; k < n; k += THREADS) {
-      const int v = node_of[k], nd = v & 0x3FFF;
-      node_of[k] = (a_tmp[nd] && a_rank[nd] < nsplit) ? remap[4 * nd + (v >> 14)] : remap_keep[nd];
+    for (int k0 = tid; k0 < n; k0 += 4 * THREADS) {
+      int v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (k0 + u * THREADS < n) ? node_of[k0 + u * THREADS] : 0;
+      bool sp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int nd = v[u] & 0x3FFF; sp[u] = a_tmp[nd] && a_rank[nd] < nsplit; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int nd = v[u] & 0x3FFF;
+        if (k0 + u * THREADS < n) node_of[k0 + u * THREADS] = sp[u] ? remap[4 * nd + (v[u] >> 14)] : remap_keep[nd];
+      }
     }
     const int nexpand = s_expand;
     __syncthreads();
@@ -977,13 +1020,22 @@ __global__ void __launch_bounds__(THREADS) k_quadtree(const OrbDev* __restrict__
   // (cell row-major, then pixel row-major) on ties (:741-760).
   for (int p = tid; p < S; p += THREADS) best[p] = 0ull;
   __syncthreads();
-  for (int k = tid; k < n; k += THREADS) {
-    const uint32_t e = keys[k];
-    const int x = e & 0xFFF, y = (e >> 12) & 0xFFF;
-    const unsigned cellid = (unsigned)(((y - 3) / L.hCell) * L.nCols + (x - 3) / L.wCell);
-    const unsigned long long ord = ((unsigned long long)cellid << 24) | ((unsigned long long)y << 12) | x;
-    const unsigned long long val = ((unsigned long long)(e >> 24) << 40) | (0xFFFFFFFFFFull - ord);
-    atomicMax(&best[node_of[k] & 0x3FFF], val);
+  for (int k0 = tid; k0 < n; k0 += 4 * THREADS) {
+    unsigned long long val[4];
+    int nd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = min(k0 + u * THREADS, n - 1);
+      const uint32_t e = keys[k];
+      nd[u] = node_of[k] & 0x3FFF;
+      const int x = e & 0xFFF, y = (e >> 12) & 0xFFF;
+      const unsigned cellid = (unsigned)(((y - 3) / L.hCell) * L.nCols + (x - 3) / L.wCell);
+      const unsigned long long ord = ((unsigned long long)cellid << 24) | ((unsigned long long)y << 12) | x;
+      val[u] = ((unsigned long long)(e >> 24) << 40) | (0xFFFFFFFFFFull - ord);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u * THREADS < n) atomicMax(&best[nd[u]], val[u]);
   }
   __syncthreads();
   uint32_t* out = P.lkp + (long long)f * P.lkp_fstride + L.kp_off;
@@ -2017,7 +2069,7 @@ static int orb_build(drfe_orb* h) {
   }
   if (h->fast_smem > 220 * 1024) { set_error("image too wide for the FAST strip kernel (%zu B of shared memory)", h->fast_smem); return DRFE_ERR_ARG; }
   const int NC = h->max_node_cap;
-  h->quad_smem = (size_t)NC * (8 + 8 + 8 + 4 + 4 + 16 + 5 * 4 + 8 + 2) + 64;
+  h->quad_smem = (size_t)NC * (8 + 8 + 8 + 4 + 4 + 16 + 5 * 4 + 8 + 2) + 64 + 16 + (size_t)kQuadStage * 6;
 
   // ---- device memory
   const int B = h->max_batch;
