@@ -1815,6 +1815,7 @@ static __global__ void __launch_bounds__(kPtsWarps * 32) k_cape_plane_points(con
     if (key > np) key = 0;
     const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
     if (key && (m & lt) == 0) mine[key] += __popc(m);         // the group's lowest lane adds its size
+    __syncwarp();                                              // the next trip's leader for this key may be another lane
   }
   __syncthreads();
   if (tid < np) {                                              // total of label tid + 1

@@ -859,6 +859,7 @@ __global__ void __launch_bounds__(kMemWarps * 32) k_peac_members(const PeacDev* 
     const int key = p < p1 ? seg[p] : 0;
     const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
     if (key && (m & lt) == 0) mine[key] += __popc(m);
+    __syncwarp();                                                  // the next trip's leader for this key may be another lane
   }
   __syncthreads();
   if (tid < np) {

@@ -13,6 +13,12 @@ ncu --set full --clock-control none --import-source on -k regex:'k_pyr_stream|k_
     -o gpurun_out/${tag}_full_orb python tools/prof_step.py --steps 1 --only orb > gpurun_out/${tag}_full_orb.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_cape' -s 14 -c 7 -f \
     -o gpurun_out/${tag}_full_cape python tools/prof_step.py --steps 1 --only cape > gpurun_out/${tag}_full_cape.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_peac' -c 3 -f \
+    -o gpurun_out/${tag}_full_peac python tools/prof_peac.py --frames 64 --steps 0 > gpurun_out/${tag}_full_peac.log 2>&1
 python tools/prof_step.py > gpurun_out/${tag}_stages.txt 2>&1
+for n in 32 1; do python tools/prof_step.py --frames $n --steps 20 2>&1 | grep "stage ms" >> gpurun_out/${tag}_stages.txt; done
+python tools/prof_peac.py --cpu 4 > gpurun_out/${tag}_peac.txt 2>&1
+for n in 32 1; do python tools/prof_peac.py --frames $n >> gpurun_out/${tag}_peac.txt 2>&1; done
+python tools/prof_extras.py > gpurun_out/${tag}_extras.txt 2>&1
 tail -n 2 gpurun_out/${tag}_stages.txt
 head -c 300 gpurun_out/${tag}_bench.json
