@@ -879,7 +879,8 @@ def peac_run(cloud, width, height, params=None, min_support=3000, window=10, pla
     offs = np.zeros(plane_cap + 1, np.int32)
     idx = np.zeros(width * height, np.int32)
     steps = C.c_int32(0)
-    n = lib().orc_peac_run(_p(cloud), width, height, _p(prm), min_support, window, window, _p(seg), _p(planes), plane_cap, _p(offs), _p(idx),
+    ww, wh = (window, window) if np.isscalar(window) else window
+    n = lib().orc_peac_run(_p(cloud), width, height, _p(prm), min_support, ww, wh, _p(seg), _p(planes), plane_cap, _p(offs), _p(idx),
                            len(idx), C.byref(steps))
     if n < 0:
         raise RuntimeError("orc_peac_run: capacity")

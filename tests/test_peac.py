@@ -101,3 +101,51 @@ def test_gpu_peac_batch(drfe, orc):
     assert n1[0] == npl[7] and np.array_equal(s1[0], seg[7])
     with pytest.raises(drfe.DrfeError):
         pe1.download(plane_cap=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [
+    dict(window_width=16, window_height=12, min_support=1500),                     # non-square windows (40 x 40 grid), smaller planes kept
+    dict(window_width=20, window_height=20, min_support=5000),                     # the AHC paper's coarse setting
+    dict(similarityTh_merge=float(np.cos(np.pi / 12)), similarityTh_refine=float(np.cos(np.pi / 18)), stdTol_merge=0.004, depthAlpha=0.02),
+    dict(max_depth=2.5),                                                            # a tighter readDepthImage cull: more of the frame is empty
+])
+def test_gpu_peac_other_parameters(drfe, orc, kw):
+    """ahc::ParamSet / PlaneFitter members other than DR-SLAM's defaults: same parity"""
+    q, K = frame(drfe, 1, 20260777, ((200, 260, 100, 180),))
+    pe = drfe.PEAC(640, 480, **kw)
+    pe.enqueue(q[None], FAC, *K)
+    seg, planes, npl = pe.download()
+    idx, pts, offs = pe.plane_vertices()
+    cloud = orc.peac_cloud(q, FAC, *K)
+    if "max_depth" in kw:                                                          # the oracle's cloud culls at 5.0 (PlaneExtractor.cpp:44): cull again
+        cloud = cloud.copy(); cloud[cloud[:, 2] > kw["max_depth"]] = 0.0
+    oseg, oplanes, omem, osteps = orc.peac_run(cloud, 640, 480, params=pe.params_array(), min_support=kw.get("min_support", 3000),
+                                               window=(kw.get("window_width", 10), kw.get("window_height", 10)))
+    assert pe.counters(0)[0] == osteps and npl[0] == len(oplanes) and len(oplanes) >= 1
+    n = int(npl[0])
+    assert np.array_equal(seg[0], oseg)
+    assert np.array_equal(planes[0, :n]["normal"], oplanes[:, :3]) and np.array_equal(planes[0, :n]["mse"], oplanes[:, 6])
+    for p in range(n):
+        assert np.array_equal(idx[0, offs[0, p]:offs[0, p + 1]], omem[p]), p
+
+
+@pytest.mark.gpu
+def test_gpu_peac_small_image_and_empty_frames(drfe, orc):
+    """320 x 240 with its own intrinsics; a frame without depth and a frame of pure noise give no plane and an all-zero seg_output"""
+    _, depth, K = drfe.synth_frame(320, 240, 2, 20260801)
+    q = np.rint(clean_depth(depth) * 5000).astype(np.uint16)
+    rng = np.random.default_rng(5)
+    batch = np.stack([q, np.zeros_like(q), rng.integers(500, 20000, q.shape).astype(np.uint16)])
+    pe = drfe.PEAC(320, 240, max_batch=3, min_support=800)
+    pe.enqueue(batch, FAC, *K)
+    seg, planes, npl = pe.download()
+    idx, pts, offs = pe.plane_vertices()
+    for f in range(3):
+        oseg, oplanes, omem, _ = orc.peac_run(orc.peac_cloud(batch[f], FAC, *K), 320, 240, params=pe.params_array(), min_support=800)
+        assert npl[f] == len(oplanes) and np.array_equal(seg[f], oseg), f
+        for p in range(len(oplanes)):
+            assert np.array_equal(idx[f, offs[f, p]:offs[f, p + 1]], omem[p])
+    assert npl[0] >= 1 and npl[1] == 0 and not seg[1].any() and offs[1].max() == 0
+    with pytest.raises(drfe.DrfeError):                                            # 80 x 60 windows: more than the clustering kernel's 4096
+        drfe.PEAC(640, 480, window_width=8, window_height=8)
