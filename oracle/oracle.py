@@ -100,6 +100,7 @@ def lib():
         L.orc_cape_cylinders_found.argtypes = [C.c_void_p]
         L.orc_cape_get_cyl_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_peac_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_peac_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_peac_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, i32p]
@@ -867,6 +868,14 @@ def peac_cloud(depth16, depth_factor, fx, fy, cx, cy):
     out = np.empty((H * W, 3), np.float64)
     lib().orc_peac_cloud(_p(depth16), W, H, W, depth_factor, fx, fy, cx, cy, _p(out))
     return out
+
+
+def peac_fit(sums9, n):
+    """ahc::PlaneSeg::Stats::compute (AHCPlaneSeg.hpp:128-162) on {sx, sy, sz, sxx, syy, szz, sxy, syz, sxz}, N -> center, normal, mse, curvature"""
+    s = np.ascontiguousarray(sums9, np.float64)
+    out = np.zeros(8, np.float64)
+    lib().orc_peac_fit(_p(s), int(n), _p(out))
+    return out[:3].copy(), out[3:6].copy(), float(out[6]), float(out[7])
 
 
 def peac_run(cloud, width, height, params=None, min_support=3000, window=10, plane_cap=256):

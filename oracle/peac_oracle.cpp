@@ -36,7 +36,7 @@
 namespace {
 
 // cyclic Jacobi (cape_oracle.cpp's eig3_sym, except that a pivot too small to change the diagonal is zeroed from the fourth sweep on
-// instead of the fifth: three rotations less per fit, the same eigenpairs): in a = {xx,xy,xz,yy,yz,zz}; w ascending, v[k][i] = component k of evec i
+// instead of the fifth: three rotations less per fit, the same eigenpairs; tests/test_peac.py pins them to LAPACK): in a = {xx,xy,xz,yy,yz,zz}; w ascending, v[k][i] = component k of evec i
 void eig3_sym(const double in[6], double w[3], double v[3][3]) {
   double a[3][3] = {{in[0], in[1], in[2]}, {in[1], in[3], in[4]}, {in[2], in[4], in[5]}};
   for (int i = 0; i < 3; ++i)
@@ -446,6 +446,15 @@ struct Fitter {
 }  // namespace
 
 extern "C" {
+
+// Stats::compute on nine sums {sx, sy, sz, sxx, syy, szz, sxy, syz, sxz} and N -> out = center[3], normal[3], mse, curvature (for the tests
+// that pin the solver to LAPACK)
+void orc_peac_fit(const double* s9, int N, double* out8) {
+  Stats st;
+  st.sx = s9[0]; st.sy = s9[1]; st.sz = s9[2]; st.sxx = s9[3]; st.syy = s9[4]; st.szz = s9[5]; st.sxy = s9[6]; st.syz = s9[7]; st.sxz = s9[8];
+  st.N = N;
+  st.compute(out8, out8 + 3, out8[6], out8[7]);
+}
 
 // PlaneDetection::readDepthImage (PlaneExtractor.cpp:28-55): cloud [H*W][3] doubles from a 16-bit depth image
 void orc_peac_cloud(const uint16_t* depth, int width, int height, int row_stride, float depth_factor, float fx, float fy, float cx, float cy,

@@ -54,6 +54,30 @@ def test_peac_restatement_invariants(drfe, orc):
         assert np.median(d) < 0.02
 
 
+def test_peac_fit_is_pinned_to_lapack(orc):
+    """Stats::compute (AHCPlaneSeg.hpp:128-162) with the restatement's Jacobi solver in place of Eigen's SelfAdjointEigenSolver (P.1):
+    smallest eigenvalue, its vector and the curvature agree with numpy.linalg.eigh (LAPACK dsyevd) on the same scatter matrix to a
+    few ulps of the LARGEST eigenvalue — what any backward-stable solver, Eigen's included, delivers"""
+    rng = np.random.default_rng(0)
+    worst = np.zeros(3)
+    for trial in range(1500):
+        N = int(rng.integers(50, 60000)); ext = rng.uniform(0.02, 1.5); sig = 10 ** rng.uniform(-4, -1.5)
+        R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        pts = np.c_[rng.uniform(-ext, ext, N), rng.uniform(-ext * rng.uniform(0.1, 1), ext, N), rng.normal(0, sig, N)] @ R.T
+        pts += rng.uniform(-1, 1, 3) * np.array([1, 1, 0]) + np.array([0, 0, rng.uniform(0.5, 4)])
+        s = pts.sum(0); sq = (pts * pts).sum(0)
+        sxy, syz, sxz = (pts[:, 0] * pts[:, 1]).sum(), (pts[:, 1] * pts[:, 2]).sum(), (pts[:, 0] * pts[:, 2]).sum()
+        ctr, nrm, mse, curv = orc.peac_fit([s[0], s[1], s[2], sq[0], sq[1], sq[2], sxy, syz, sxz], N)
+        sc = 1.0 / N
+        K = np.array([[sq[0] - s[0] * s[0] * sc, sxy - s[0] * s[1] * sc, sxz - s[0] * s[2] * sc],
+                      [0, sq[1] - s[1] * s[1] * sc, syz - s[1] * s[2] * sc], [0, 0, sq[2] - s[2] * s[2] * sc]])
+        K = K + np.triu(K, 1).T
+        w, V = np.linalg.eigh(K)
+        assert np.array_equal(ctr, s * sc) and nrm @ ctr <= 0                     # the normal points towards the camera
+        worst = np.maximum(worst, [abs(mse / sc - w[0]) / w[2], 1 - abs(nrm @ V[:, 0]), abs(curv - w[0] / w.sum())])
+    assert worst[0] < 4e-15 and worst[1] < 1e-14 and worst[2] < 4e-15, worst
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene,seed,holes", [
     (0, 20260000, ((100, 140, 300, 420),)),
