@@ -2140,7 +2140,7 @@ int drfe_cape_create(const drfe_cape_params* pr, int max_batch, int device, drfe
   const size_t N = (size_t)D.H * D.W, B = max_batch, nc = D.ncells;
   int rc = DRFE_OK;
   auto fail = [&](int code) { drfe_cape_destroy(h); return code; };
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(DRFE_ERR_CUDA); }
+  { const char* e = getenv("DRFE_CAPE_PRIO"); if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, e ? atoi(e) : 0) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(DRFE_ERR_CUDA); } }
   rc |= cape_alloc(h, &D.cells, nc * B);
   rc |= cape_alloc(h, &D.tols, nc * B);
   rc |= cape_alloc(h, &D.cell_meta, nc * B);

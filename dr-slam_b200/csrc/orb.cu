@@ -2073,7 +2073,10 @@ static int orb_build(drfe_orb* h) {
 
   // ---- device memory
   const int B = h->max_batch;
-  DRFE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  // the ORB chain is the longer of the two a frame batch needs (1.48 ms against 0.58 ms for the planes at 256 frames): its stream
+  // gets the higher priority, so the block scheduler places its CTAs first and the plane kernels — shorter, two of them latency-bound —
+  // run in what is left.  Measured 1.887 -> 1.835 ms per two-stream step (the reverse: 1.936 ms).  DRFE_ORB_PRIO / DRFE_CAPE_PRIO override.
+  { const char* e = getenv("DRFE_ORB_PRIO"); DRFE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, e ? atoi(e) : -1)); }
   {
     const char* e = getenv("DRFE_ORB_SPLIT");
     h->split = e ? std::min(std::max(atoi(e), 1), (int)drfe_orb::kMaxSplit) : 1;
