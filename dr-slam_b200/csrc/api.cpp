@@ -22,6 +22,10 @@ cudaError_t raise_dyn_smem_impl(const void* func, int device, size_t bytes) {
 
 static thread_local char t_err[512] = "";
 std::atomic<long long> g_launches{0};
+int pdl_max_frames() {
+  static const int v = [] { const char* e = getenv("DRFE_PDL_MAX_FRAMES"); return e ? atoi(e) : kPdlMaxFrames; }();
+  return v;
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("DRFE_NO_PDL"); return !(e && e[0] == '1'); }();
   return on;

@@ -2249,7 +2249,7 @@ int drfe_cape_stage_times(drfe_cape* h, float* ms, const char** names, int cap, 
 // all kernels of frames [f0, f0 + n) on the handle's stream (the device descriptor must be current)
 static int cape_launch(drfe_cape* h, int f0, int n, bool timed) {
   NvtxRange nvtx_("cape_launch");
-  const bool drfe_pdl_ = pdl_enabled() && n <= kPdlMaxFrames;
+  const bool drfe_pdl_ = pdl_enabled() && n <= pdl_max_frames();
   cudaStream_t st = h->stream;
   const int ncell_total = n * h->hd.ncells;
   const size_t sums_smem = (size_t)(kSumsThreads / 16) * 2 * h->hd.npc * sizeof(float);

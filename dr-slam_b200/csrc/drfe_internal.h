@@ -16,7 +16,8 @@ namespace drfe {
 void set_error(const char* fmt, ...);          // thread-local message for drfe_last_error()
 extern std::atomic<long long> g_launches;      // counted by DRFE_LAUNCH
 static const int kPdlMaxFrames = 64;
-bool pdl_enabled();                            // programmatic dependent launch in the batch chains (off with DRFE_NO_PDL=1)
+bool pdl_enabled();
+int pdl_max_frames();                          // kPdlMaxFrames, or DRFE_PDL_MAX_FRAMES                            // programmatic dependent launch in the batch chains (off with DRFE_NO_PDL=1)
 
 #define DRFE_CUDA(expr)                                                                   \
   do {                                                                                    \
@@ -47,7 +48,8 @@ bool pdl_enabled();                            // programmatic dependent launch 
 // has completed and its writes are visible.  That hides the launch latency and the ramp-up of each of the chain's 13 + 7
 // kernel boundaries.  Measured: pyramid (8 launches) 0.087 -> 0.072 ms at 32 frames, 0.052 -> 0.033 ms at one frame; at 256
 // frames the waiting CTAs take SM slots from the OTHER handle's stream and the two-stream step gets 1.5 % slower — so the
-// caller sets `drfe_pdl_` (a local the macro reads) only for launches of at most kPdlMaxFrames frames.  DRFE_NO_PDL=1: never.
+// caller sets `drfe_pdl_` (a local the macro reads) only for launches of at most kPdlMaxFrames frames (DRFE_PDL_MAX_FRAMES overrides;
+// with it on at 256 frames and the ORB stream prioritised: 1.84 -> 1.97 ms).  DRFE_NO_PDL=1: never.
 #define DRFE_LAUNCH_PDL(kernel, grid_, block_, smem_, strm_, ...)                           \
   do {                                                                                    \
     cudaLaunchConfig_t cfg__ = {};                                                        \

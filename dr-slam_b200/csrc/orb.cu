@@ -2243,7 +2243,7 @@ int drfe_orb_stage_times(drfe_orb* h, float* ms, const char** names, int cap, in
 // all kernels of frames [f0, f0 + n) on the handle's stream; src/rs/fs address frame 0 of the batch
 static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
   NvtxRange nvtx_("orb_launch");
-  const bool drfe_pdl_ = pdl_enabled() && n <= kPdlMaxFrames;
+  const bool drfe_pdl_ = pdl_enabled() && n <= pdl_max_frames();
   h->post_valid = false;         // the keypoints drfe_orb_frame_post worked on are being replaced
   const OrbDev& D = h->hd;
   const int nl = D.nlevels;
