@@ -1812,6 +1812,7 @@ __global__ void k_zero_counts(const OrbDev* __restrict__ Pp, int f0, int nframes
 // ====================================================================== host side
 using namespace drfe;
 
+static const int kHiPrioMinFrames = 128;   // launches of at least this many frames run on the handle's high-priority stream
 struct drfe_orb {
   int device = 0, width = 0, height = 0, max_batch = 0;
   drfe_orb_params prm{};
@@ -1827,6 +1828,9 @@ struct drfe_orb {
   int split = 1;                     // parts a long batch's kernel chains are cut into (orb_launch)
   cudaStream_t aux[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
+  cudaStream_t hi = nullptr;             // one priority level above `stream`, for launches of many frames
+  cudaEvent_t ev_hi = nullptr;
+  int hi_min_frames = 0;
   uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
   void* d_rtab = nullptr; void* d_strips = nullptr;
   FastMaps fast_maps{};
@@ -2073,10 +2077,22 @@ static int orb_build(drfe_orb* h) {
 
   // ---- device memory
   const int B = h->max_batch;
-  // the ORB chain is the longer of the two a frame batch needs (1.48 ms against 0.58 ms for the planes at 256 frames): its stream
-  // gets the higher priority, so the block scheduler places its CTAs first and the plane kernels — shorter, two of them latency-bound —
-  // run in what is left.  Measured 1.887 -> 1.835 ms per two-stream step (the reverse: 1.936 ms).  DRFE_ORB_PRIO / DRFE_CAPE_PRIO override.
-  { const char* e = getenv("DRFE_ORB_PRIO"); DRFE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, e ? atoi(e) : -1)); }
+  // The handle's stream has the default priority; launches of at least kHiPrioMinFrames frames are forked onto `hi`, a stream one
+  // priority level up, and joined back.  The ORB chain is the longer of the two a frame batch needs (1.48 ms against 0.58 ms for
+  // the planes at 256 frames): with the higher priority the block scheduler places its CTAs first and the plane kernels — shorter,
+  // two of them latency-bound — run in what is left: 1.87 -> 1.83 ms per two-stream step (the reverse: 1.94 ms).  Small launches
+  // stay on the default priority: there the chains are latency-bound, and a prioritised ORB chain that also launches dependents early
+  // (DRFE_LAUNCH_PDL) keeps the plane kernels off the SMs (32 frames: 0.326 ms -> 0.370 ms; 64: 0.532 -> 0.613).
+  // DRFE_ORB_PRIO / DRFE_CAPE_PRIO set the handle streams' own priority, DRFE_ORB_HI_MIN_FRAMES the threshold (0: never).
+  { const char* e = getenv("DRFE_ORB_PRIO"); DRFE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, e ? atoi(e) : 0)); }
+  {
+    const char* e = getenv("DRFE_ORB_HI_MIN_FRAMES");
+    h->hi_min_frames = e ? atoi(e) : kHiPrioMinFrames;
+    if (h->hi_min_frames > 0) {
+      DRFE_CUDA(cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, -1));
+      DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_hi, cudaEventDisableTiming));
+    }
+  }
   {
     const char* e = getenv("DRFE_ORB_SPLIT");
     h->split = e ? std::min(std::max(atoi(e), 1), (int)drfe_orb::kMaxSplit) : 1;
@@ -2201,6 +2217,8 @@ int drfe_orb_destroy(drfe_orb* h) {
   h->timer.destroy();
   if (h->ev_shared) cudaEventDestroy(h->ev_shared);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_hi) cudaEventDestroy(h->ev_hi);
+  if (h->hi) { cudaStreamSynchronize(h->hi); cudaStreamDestroy(h->hi); }
   for (int p = 0; p < drfe_orb::kMaxSplit - 1; ++p) {
     if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]);
     if (h->aux[p]) { cudaStreamSynchronize(h->aux[p]); cudaStreamDestroy(h->aux[p]); }
@@ -2287,7 +2305,16 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
 // issue-bound stages of the others.  DRFE_ORB_SPLIT sets the number of parts (default in orb_build).
 static int orb_launch(drfe_orb* h, int f0, int n, const uint8_t* src, long long rs, long long fs, bool timed) {
   const int parts = std::min(h->split, n / 32);
-  if (parts <= 1) return orb_launch_on(h, h->stream, f0, n, src, rs, fs, timed);
+  if (parts <= 1) {
+    if (!h->hi || n < h->hi_min_frames) return orb_launch_on(h, h->stream, f0, n, src, rs, fs, timed);
+    DRFE_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    DRFE_CUDA(cudaStreamWaitEvent(h->hi, h->ev_fork, 0));
+    const int rc = orb_launch_on(h, h->hi, f0, n, src, rs, fs, timed);
+    if (rc != DRFE_OK) return rc;
+    DRFE_CUDA(cudaEventRecord(h->ev_hi, h->hi));
+    DRFE_CUDA(cudaStreamWaitEvent(h->stream, h->ev_hi, 0));
+    return DRFE_OK;
+  }
   DRFE_CUDA(cudaEventRecord(h->ev_fork, h->stream));
   const int base = n / parts, extra = n % parts;
   int first = f0 + base + (extra > 0 ? 1 : 0);
