@@ -762,8 +762,8 @@ def main():
                         "bytes against the HBM copy peak, as the contract asks" if bound != "hbm" else None,
                 "alg_bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms,
                 "whole_step": {"alg_bytes_per_frame": alg["total"],
-                               "achieved": alg["total"] * B * args.steps / (ms * 1e-3) / 1e9 / world,
-                               "frac": alg["total"] * B * args.steps / (ms * 1e-3) / 1e9 / world / peak,
+                               "achieved": alg["total"] * B * args.steps / (ms * 1e-3) / 1e9,
+                               "frac": alg["total"] * B * args.steps / (ms * 1e-3) / 1e9 / peak,
                                "note": "per GPU: all stages' algorithmic bytes / the step's device time, against the HBM copy peak"},
                 "stage_ms": {k: round(v, 4) for k, v in stages.items()},
                 "stage_ms_in_step": {k: round(v, 4) for k, v in stages_in_step.items()},
