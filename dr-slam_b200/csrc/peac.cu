@@ -208,6 +208,7 @@ struct PeacShared {
   int* cand;         // [kPeacCand] neighbour slots of the popped node
   double* cmse;      // [kPeacCand] mse of the merge with that neighbour (+inf: not similar enough)
   int* extracted;    // [kPeacMaxPlanes + 1]
+  uint8_t* cpass;    // [kPeacCand] the merge with that neighbour passes T_mse(P_MERGING)
 };
 
 __device__ __forceinline__ int ds_find(const int* parent, int x) {      // no path compression: the root is the same
@@ -238,6 +239,7 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
   long long own_k = kInfKey;
   int own_s = -1, own_q = 0x7FFFFFFF;
   long long* s_ktmp = reinterpret_cast<long long*>(s_dtmp);
+  long long* s_minkey = s_ktmp + 6;                             // smallest candidate key of the running step
 #ifdef PEAC_PHASE_PROFILE
   long long ph[6] = {0, 0, 0, 0, 0, 0}, tph = clock64();
 #define PH(i) { const long long t_ = clock64(); ph[i] += t_ - tph; tph = t_; }
@@ -282,6 +284,7 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
     PH(0)
     const int p = bs;
     if (tid == p % kPeacThreads) { S.qmse[p] = INFINITY; dirty = true; }   // popped
+    if (tid == 0) { *s_minkey = kInfKey; s_tmp[16] = 0x7FFFFFFF; s_tmp[18] = 0; }
     // ---- the popped node's live neighbours, in ascending slot order
     uint32_t* row_p = adj + (long long)p * nw;
     int mycnt = 0;
@@ -311,13 +314,15 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
     __syncthreads();
     PH(1)
     // ---- fit the merge with every similar neighbour, one thread per candidate; the fit stays in the thread's registers, the
-    // thread that fitted the chosen candidate finishes the step (a fit is ~12 k cycles of dependent double div / sqrt)
+    // thread that fitted the chosen candidate finishes the step (a fit is ~8 k cycles of dependent FP64 operations).  Each fit leaves
+    // its mse, whether it passes T_mse(P_MERGING), and takes part in a shared-memory minimum over the ordered bit patterns.
     const PeacNode& np = nodes[p];
     int my_c = -1, my_N = 0;
     double my_s[9], my_ctr[3], my_nrm[3], my_curv = 0, my_m = 0;
     for (int c = tid; c < ncand; c += kPeacThreads) {
       const PeacNode& nb = nodes[S.cand[c]];
       double m = INFINITY;
+      bool pass = false;
       if (!(peac_sim(np, nb) < P.sim_merge)) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) my_s[k] = np.s[k] + nb.s[k];
@@ -325,33 +330,34 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
         peac_compute(my_s, my_N, my_ctr, my_nrm, my_m, my_curv);
         my_c = c;
         m = my_m;
+        const double t = P.depthSigma * my_ctr[2] * my_ctr[2] + P.stdTol_merge;         // T_mse(P_MERGING)
+        pass = my_m < t * t;
         if (!(m < INFINITY)) m = DBL_MAX;                         // (a NaN would never be chosen after another candidate; keep it last)
+        atomicMin(s_minkey, peac_key(m));
       }
       S.cmse[c] = m;
+      S.cpass[c] = pass ? 1 : 0;
     }
     __syncthreads();
     PH(2)
     // ---- the candidate the reference's scan keeps (ascending creation number; :1040-1051): the minimum mse; among exact ties
     // the scan `cand == 0 || cand.mse > m.mse || (cand.mse == m.mse && cand.N < m.mse)` depends on the visiting order and is
     // replayed literally over the tied candidates (earlier non-tied ones cannot survive a tie with the minimum, later ones cannot
-    // replace it).  Warp 0.
-    if (wid == 0) {
-      double mn = INFINITY;
-      for (int c = lane; c < ncand; c += 32) mn = fmin(mn, S.cmse[c]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
-      int ties = 0, mine_c = -1;
-      if (mn < INFINITY)
-        for (int c = lane; c < ncand; c += 32) if (S.cmse[c] == mn) { ++ties; mine_c = c; }
-      const unsigned has = __ballot_sync(0xFFFFFFFFu, ties > 0);
-      int tot = ties;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
-      if (tot <= 1) {
-        if (tot == 0) { if (lane == 0) s_tmp[16] = -1; }
-        else if (lane == __ffs(has) - 1) s_tmp[16] = mine_c;
-      } else if (lane == 0) {
-        int best = -1, best_N = 0, last_q = -1;
+    // replace it).
+    {
+      const long long mk = *s_minkey;
+      if (mk < kInfKey)
+        for (int c = tid; c < ncand; c += kPeacThreads)
+          if (S.cmse[c] < INFINITY && peac_key(S.cmse[c]) == mk) { atomicAdd(&s_tmp[18], 1); atomicMin(&s_tmp[16], c); }
+    }
+    __syncthreads();
+    int best = s_tmp[18] ? s_tmp[16] : -1;
+    if (s_tmp[18] > 1) {                                          // exact ties (uniform branch): thread 0 replays the scan
+      __syncthreads();
+      if (tid == 0) {
+        const double mn = S.cmse[best];
+        const int tot = s_tmp[18];
+        int bst = -1, best_N = 0, last_q = -1;
         double best_m = 0;
         for (int round = 0; round < tot; ++round) {
           int c_next = -1, q_next = 0x7FFFFFFF;
@@ -359,31 +365,20 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
             if (S.cmse[c] == mn) { const int q = S.qseq[S.cand[c]]; if (q > last_q && q < q_next) { q_next = q; c_next = c; } }
           last_q = q_next;
           const int Nm = np.N + nodes[S.cand[c_next]].N;
-          if (best < 0 || best_m > mn || (best_m == mn && (double)best_N < mn)) { best = c_next; best_m = mn; best_N = Nm; }
+          if (bst < 0 || best_m > mn || (best_m == mn && (double)best_N < mn)) { bst = c_next; best_m = mn; best_N = Nm; }
         }
-        s_tmp[16] = best;
+        s_tmp[16] = bst;
       }
+      __syncthreads();
+      best = s_tmp[16];
     }
-    __syncthreads();
-    const int best = s_tmp[16];
     PH(3)
     bool merged = false;
     if (best >= 0) {
       const int q = S.cand[best];
       const PeacNode& nb = nodes[q];
       const bool owner = tid == best % kPeacThreads;
-      if (owner) {
-        if (my_c != best) {                                       // more than kPeacThreads candidates and a later fit took the registers
-#pragma unroll
-          for (int k = 0; k < 9; ++k) my_s[k] = np.s[k] + nb.s[k];
-          my_N = np.N + nb.N;
-          peac_compute(my_s, my_N, my_ctr, my_nrm, my_m, my_curv);
-        }
-        const double t = P.depthSigma * my_ctr[2] * my_ctr[2] + P.stdTol_merge;         // T_mse(P_MERGING)
-        s_tmp[17] = my_m < t * t;
-      }
-      __syncthreads();
-      merged = s_tmp[17] != 0;
+      merged = S.cpass[best] != 0;
       if (merged) {
         const int rid_p = np.rid, rid_q = nb.rid;
         const int new_rid = np.N >= nb.N ? rid_p : rid_q;
@@ -405,6 +400,12 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
         }
         __syncthreads();                                          // every thread has read nodes[p] / nodes[q] / alive
         if (owner) {
+          if (my_c != best) {                                     // more than kPeacThreads candidates and a later fit took the registers
+#pragma unroll
+            for (int k = 0; k < 9; ++k) my_s[k] = np.s[k] + nb.s[k];
+            my_N = np.N + nb.N;
+            peac_compute(my_s, my_N, my_ctr, my_nrm, my_m, my_curv);
+          }
           PeacNode nn;
           for (int k = 0; k < 9; ++k) nn.s[k] = my_s[k];
           nn.mse = my_m; nn.curvature = my_curv; nn.th_init = 0;
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
     S.cand = (int*)q; q += sizeof(int) * kPeacCand;
     S.alive = (uint32_t*)q; q += sizeof(uint32_t) * nw;
     S.extracted = (int*)q; q += sizeof(int) * (kPeacMaxPlanes + 1);
+    S.cpass = q; q += kPeacCand;
   }
   __shared__ int s_tmp[32];
   __shared__ double s_dtmp[8];
@@ -974,7 +976,7 @@ int drfe_peac_create(int width, int height, const drfe_peac_params* params, int 
   auto fail = [&](int code) { drfe_peac_destroy(h); return code; };
   if (D.nwords > kPeacThreads) { set_error("drfe_peac_create: %d windows are too many for the clustering kernel (at most %d)", D.NB, 32 * kPeacThreads); return fail(DRFE_ERR_ARG); }
   h->frame_smem = sizeof(double) * D.NB + sizeof(double) * kPeacCand + sizeof(int) * 3 * D.NB + sizeof(int) * kPeacCand + sizeof(uint32_t) * D.nwords +
-                  sizeof(int) * (kPeacMaxPlanes + 1) + 64;
+                  sizeof(int) * (kPeacMaxPlanes + 1) + kPeacCand + 64;
   if (h->frame_smem > 200 * 1024) { set_error("drfe_peac_create: %d windows need %zu bytes of shared memory", D.NB, h->frame_smem); return fail(DRFE_ERR_ARG); }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
