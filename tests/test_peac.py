@@ -173,3 +173,37 @@ def test_gpu_peac_small_image_and_empty_frames(drfe, orc):
     assert npl[0] >= 1 and npl[1] == 0 and not seg[1].any() and offs[1].max() == 0
     with pytest.raises(drfe.DrfeError):                                            # 80 x 60 windows: more than the clustering kernel's 4096
         drfe.PEAC(640, 480, window_width=8, window_height=8)
+
+
+def _golden_frames():
+    from conftest import load_golden
+    G = load_golden("peac_640x480.npz")
+    for i in range(2):
+        offs = G["member_offsets%d" % i]
+        yield (G["depth%d" % i], [float(v) for v in G["K%d" % i]], float(G["depth_factor"]), G["seg%d" % i], G["planes%d" % i],
+               [G["member_idx%d" % i][offs[p]:offs[p + 1]] for p in range(len(offs) - 1)], int(G["steps%d" % i]))
+
+
+def test_oracle_reproduces_peac_golden(orc):
+    """tests/golden/peac_640x480.npz (made by tests/golden/make_golden_peac.py): the restatement must not drift"""
+    for q, K, fac, seg, planes, members, steps in _golden_frames():
+        oseg, oplanes, omem, osteps = orc.peac_run(orc.peac_cloud(q, fac, *K), 640, 480)
+        assert osteps == steps and np.array_equal(oseg, seg) and oplanes.tobytes() == planes.tobytes()
+        assert len(omem) == len(members) and all(np.array_equal(a, b) for a, b in zip(omem, members))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_peac_golden(drfe):
+    for q, K, fac, seg, planes, members, steps in _golden_frames():
+        pe = drfe.PEAC(640, 480)
+        pe.enqueue(q[None], fac, *K)
+        gseg, gplanes, npl = pe.download()
+        idx, pts, offs = pe.plane_vertices()
+        n = int(npl[0])
+        assert n == len(planes) and pe.counters(0)[0] == steps and np.array_equal(gseg[0], seg)
+        for name, cols in (("normal", slice(0, 3)), ("center", slice(3, 6))):
+            assert np.array_equal(gplanes[0, :n][name], planes[:, cols]), name
+        assert np.array_equal(gplanes[0, :n]["mse"], planes[:, 6]) and np.array_equal(gplanes[0, :n]["curvature"], planes[:, 7])
+        assert np.array_equal(gplanes[0, :n]["N"], planes[:, 8].astype(np.int32)) and np.array_equal(gplanes[0, :n]["rid"], planes[:, 9].astype(np.int32))
+        for p in range(n):
+            assert np.array_equal(idx[0, offs[0, p]:offs[0, p + 1]], members[p]), p
