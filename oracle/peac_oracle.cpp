@@ -21,6 +21,8 @@
 //        insertion sort, hence stable, up to 16 elements anyway).
 //   P.5  no FMA contraction in Stats::push / compute (the reference's -O3 -march=native build may contract).
 // PARITY STATUS: "parity unpinned" by the reference (no tests / fixtures; it cannot be built here: the headers include OpenCV).
+// Pinned by: oracle/peac_py.py (an independent Python restatement: equal value for value, and decision for decision with LAPACK as the
+// solver), numpy.linalg.eigh for the plane fit, tests/golden/peac_640x480.npz against drift (tests/test_peac.py).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -78,6 +78,33 @@ def test_peac_fit_is_pinned_to_lapack(orc):
     assert worst[0] < 4e-15 and worst[1] < 1e-14 and worst[2] < 4e-15, worst
 
 
+@pytest.mark.parametrize("scene,seed,holes,kw", [
+    (0, 20260000, ((100, 140, 300, 420),), {}),
+    (2, 20260100, ((0, 60, 0, 640), (200, 260, 100, 180)), {}),
+    (1, 20260777, ((200, 260, 100, 180),), dict(min_support=1500, win_w=16, win_h=12)),
+])
+def test_two_independent_restatements_agree(drfe, orc, scene, seed, holes, kw):
+    """oracle/peac_py.py (plain Python, heapq / set / list, written from the reference headers) against oracle/peac_oracle.cpp:
+    with the declared Jacobi solver every value is equal, the doubles bit for bit; with LAPACK (numpy.linalg.eigh) in the place where
+    the reference has Eigen's SelfAdjointEigenSolver, the decisions are the same — same number of clustering steps, same seg_output,
+    same plane order and members — and the plane parameters agree to 1e-12: the solver substitution P.1 changes nothing that is extracted"""
+    from oracle import peac_py
+    q, K = frame(drfe, scene, seed, holes)
+    cloud = orc.peac_cloud(q, FAC, *K)
+    assert np.array_equal(cloud, peac_py.cloud_from_depth(q, FAC, *K))
+    ms, ww, wh = kw.get("min_support", 3000), kw.get("win_w", 10), kw.get("win_h", 10)
+    oseg, oplanes, omem, osteps = orc.peac_run(cloud, 640, 480, min_support=ms, window=(ww, wh))
+    assert len(oplanes) >= 3
+    for solver in ("jacobi", "lapack"):
+        seg, planes, mem, steps = peac_py.run(cloud, 640, 480, min_support=ms, win_w=ww, win_h=wh, solver=solver)
+        assert steps == osteps and np.array_equal(seg, oseg) and len(planes) == len(oplanes), solver
+        assert all(np.array_equal(a, b) for a, b in zip(mem, omem)), solver
+        if solver == "jacobi":
+            assert planes.tobytes() == oplanes[:, :10].tobytes()
+        else:
+            assert np.array_equal(planes[:, 8:], oplanes[:, 8:10]) and np.abs(planes[:, :8] - oplanes[:, :8]).max() < 1e-12
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene,seed,holes", [
     (0, 20260000, ((100, 140, 300, 420),)),
