@@ -69,7 +69,8 @@ typedef struct drfe_orb_params {
   int32_t min_th_fast;
 } drfe_orb_params;
 
-/* Mirror of the public data members of PlaneSeg (src/CAPE/PlaneSeg.h:15-28). */
+/* Mirror of the public data members of PlaneSeg (src/CAPE/PlaneSeg.h:15-28).  (The 4 padding bytes after `planar` are not written:
+ * compare records field by field, not with memcmp.) */
 typedef struct drfe_plane {
   int32_t nr_pts, min_nr_pts;
   double x_acc, y_acc, z_acc, xx_acc, yy_acc, zz_acc, xy_acc, xz_acc, yz_acc;
