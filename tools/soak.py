@@ -61,6 +61,28 @@ def main():
                 print("MISMATCH: ORB + CAPE, %d frames, iteration %d" % (n, it))
                 break
         print("ORB + CAPE, %3d frames per step: %d identical downloads" % (n, a.iters if bad == 0 else it))
+    # the chunk-pipelined batch calls (host buffers in and out, three streams per handle), against the resident path's result
+    B, W, H = wl.batch, wl.W, wl.H
+    rig.step_resident(B)
+    kps0, desc0, cnt0 = rig.orb.download()
+    seg0, planes0, npl0 = rig.cape.download()
+    hk = drfe.host_array(kps0.shape, kps0.dtype); hd = drfe.host_array(desc0.shape, desc0.dtype); hc = drfe.host_array(cnt0.shape, cnt0.dtype)
+    hs = drfe.host_array(seg0.shape, seg0.dtype); hp = drfe.host_array(planes0.shape, planes0.dtype); hn = drfe.host_array(npl0.shape, npl0.dtype)
+    hg = drfe.host_array(gray.shape, gray.dtype); hg[...] = gray
+    hz = drfe.host_array(depth.shape, depth.dtype); hz[...] = depth
+    valid0 = np.arange(kps0.shape[1])[None, :] < cnt0[:, None]
+    iters = max(5, a.iters // 3)
+    for it in range(iters):
+        rig.orb.extract_batch(hg, hk, hd, hc)
+        rig.cape.process_depth_batch(hz, *K, seg=hs, planes=hp, nplanes=hn)
+        rig.orb.finish_batch(); rig.cape.finish_batch()
+        same = (np.array_equal(hc, cnt0) and hk[valid0].tobytes() == kps0[valid0].tobytes() and np.array_equal(hd[valid0], desc0[valid0])
+                and np.array_equal(hs, seg0) and np.array_equal(hn, npl0))
+        if not same:
+            bad += 1
+            print("MISMATCH: batch calls, iteration %d" % it)
+            break
+    print("batch calls (drfe_orb_extract_batch + drfe_cape_process_depth_batch), %d frames: %d results identical to the resident path's" % (B, iters))
     q = np.rint(depth[:64] * np.float32(5000.0)).astype(np.uint16)
     col = np.where(q > 0, np.arange(wl.W)[None, None, :], 0)
     q = np.take_along_axis(q, np.maximum.accumulate(col, axis=2), axis=2)
