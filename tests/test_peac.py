@@ -234,3 +234,28 @@ def test_gpu_reproduces_peac_golden(drfe):
         assert np.array_equal(gplanes[0, :n]["N"], planes[:, 8].astype(np.int32)) and np.array_equal(gplanes[0, :n]["rid"], planes[:, 9].astype(np.int32))
         for p in range(n):
             assert np.array_equal(idx[0, offs[0, p]:offs[0, p + 1]], members[p]), p
+
+
+@pytest.mark.gpu
+def test_gpu_peac_argument_and_state_errors(drfe):
+    """the C ABI's error behaviour: every misuse comes back as a status with a text, nothing is launched"""
+    import ctypes as C
+    L = drfe.lib()
+    pe = drfe.PEAC(640, 480, max_batch=2)
+    seg = np.zeros((1, 480, 640), np.uint8); planes = np.zeros((1, 255), drfe.PEAC_PLANE_DTYPE); npl = np.zeros(1, np.int32)
+    assert L.drfe_peac_download(pe.h, seg.ctypes.data, planes.ctypes.data, 255, npl.ctypes.data) == drfe.ERR_STATE      # nothing enqueued
+    q = np.zeros((3, 480, 640), np.uint16)
+    for nframes, rs, kind in ((3, 640, drfe.MEM_HOST), (0, 640, drfe.MEM_HOST), (1, 600, drfe.MEM_HOST), (1, 640, 7)):
+        rc = L.drfe_peac_enqueue_depth_u16(pe.h, nframes, q.ctypes.data, rs, rs * 480, kind, C.c_float(2e-4), C.c_float(525), C.c_float(525),
+                                           C.c_float(320), C.c_float(240))
+        assert rc == drfe.ERR_ARG and len(L.drfe_last_error()) > 10, (nframes, rs, kind)
+    assert L.drfe_peac_enqueue_depth_u16(None, 1, q.ctypes.data, 640, 640 * 480, drfe.MEM_HOST, C.c_float(2e-4), C.c_float(525), C.c_float(525),
+                                         C.c_float(320), C.c_float(240)) == drfe.ERR_ARG
+    prm = drfe.PeacParams()
+    L.drfe_peac_default_params(C.byref(prm))
+    h = C.c_void_p()
+    assert L.drfe_peac_create(640, 480, C.byref(prm), 0, 0, C.byref(h)) == drfe.ERR_ARG                                   # max_batch 0
+    prm.window_width = 0
+    assert L.drfe_peac_create(640, 480, C.byref(prm), 1, 0, C.byref(h)) == drfe.ERR_ARG
+    pe.enqueue(q[:2], 2e-4, 525.0, 525.0, 320.0, 240.0)                                                                    # still usable
+    assert pe.download()[2].tolist() == [0, 0]
