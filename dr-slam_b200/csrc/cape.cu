@@ -2069,8 +2069,7 @@ struct drfe_cape {
   float* d_plane_pts = nullptr;  // [B][H*W][3] per-plane point lists (allocated by the first drfe_cape_plane_points)
   int* d_plane_offs = nullptr;   // [B][kMaxPlanes+1]
   std::vector<int> h_plane_offs;
-  uint32_t* d_vox_key[2] = {nullptr, nullptr}; uint32_t* d_vox_val[2] = {nullptr, nullptr};   // drfe_cape_plane_points_voxel: sort buffers [B][H*W]
-  VoxSeg* d_vox_seg = nullptr; float* d_vox_out = nullptr; int* d_vox_offs = nullptr;          // per (frame, plane) records; centroids [B][H*W][3]; offsets
+  VoxelScratch vox;                      // drfe_cape_plane_points_voxel: sort buffers, per (frame, plane) records, centroids, offsets
   float* d_third = nullptr;      // drfe_cape_third_cloud
   int batch_plane_cap = 0;
   std::vector<void*> allocs;
@@ -2110,6 +2109,28 @@ int drfe::cape_depth_view(drfe_cape* h, CapeDepthView* v) {
   v->depth = h->hd.depth; v->depth16 = h->hd.depth16; v->factor = h->hd.depth_factor; v->row_stride = h->hd.depth_rs; v->frame_stride = h->hd.depth_fs;
   return DRFE_OK;
 }
+
+// ---- the voxel filter for handles that hold per-plane point lists on the device (drfe_internal.h)
+int drfe::voxel_scratch_alloc(VoxelScratch& s, size_t B, size_t N) {
+  void** slots[7] = {(void**)&s.key[0], (void**)&s.key[1], (void**)&s.val[0], (void**)&s.val[1], &s.seg, (void**)&s.out, (void**)&s.out_offs};
+  const size_t bytes[7] = {B * N * 4, B * N * 4, B * N * 4, B * N * 4, B * kMaxPlanes * sizeof(VoxSeg), B * N * 3 * sizeof(float), B * (kMaxPlanes + 1) * sizeof(int)};
+  for (int i = 0; i < 7; ++i)
+    if (cudaMalloc(slots[i], bytes[i]) != cudaSuccess) { voxel_scratch_free(s); return 1; }
+  return 0;
+}
+void drfe::voxel_scratch_free(VoxelScratch& s) {
+  void** slots[7] = {(void**)&s.key[0], (void**)&s.key[1], (void**)&s.val[0], (void**)&s.val[1], &s.seg, (void**)&s.out, (void**)&s.out_offs};
+  for (int i = 0; i < 7; ++i) { if (*slots[i]) cudaFree(*slots[i]); *slots[i] = nullptr; }
+}
+int drfe::voxel_filter_launch(cudaStream_t st, int nf, const float* pts, const int* offs, const int* nplanes, int N, float leaf_size, const VoxelScratch& s) {
+  const float inv_leaf = 1.0f / leaf_size;                        // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+  const dim3 grid(8, nf);                                         // up to 8 CTAs share a frame's planes
+  VoxSeg* seg = static_cast<VoxSeg*>(s.seg);
+  DRFE_LAUNCH(k_voxel_sort, grid, kVoxThreads, 0, st, pts, offs, nplanes, N, inv_leaf, s.key[0], s.val[0], s.key[1], s.val[1], seg);
+  DRFE_LAUNCH(k_voxel_centroids, grid, 256, 0, st, pts, offs, nplanes, N, s.key[0], s.val[0], s.key[1], s.val[1], seg, s.out, s.out_offs);
+  return DRFE_OK;
+}
+
 
 extern "C" {
 
@@ -2226,6 +2247,7 @@ int drfe_cape_destroy(drfe_cape* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->pipe.destroy();
   for (void* p : h->allocs) cudaFree(p);
+  voxel_scratch_free(h->vox);
   h->timer.destroy();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -2602,21 +2624,13 @@ int drfe_cape_plane_points_voxel(drfe_cape* h, float leaf_size, float* points, s
   if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
   int rc = cape_plane_points_device(h);
   if (rc != DRFE_OK) return rc;
-  const size_t N = (size_t)h->hd.H * h->hd.W, B = h->max_batch;
-  if (!h->d_vox_out) {
-    if (cape_alloc(h, &h->d_vox_key[0], B * N) || cape_alloc(h, &h->d_vox_key[1], B * N) || cape_alloc(h, &h->d_vox_val[0], B * N) ||
-        cape_alloc(h, &h->d_vox_val[1], B * N) || cape_alloc(h, &h->d_vox_seg, B * kMaxPlanes) || cape_alloc(h, &h->d_vox_offs, B * (kMaxPlanes + 1)) ||
-        cape_alloc(h, &h->d_vox_out, B * N * 3)) return DRFE_ERR_CUDA;
+  const size_t N = (size_t)h->hd.H * h->hd.W;
+  if (!h->vox.out) {
+    if (voxel_scratch_alloc(h->vox, (size_t)h->max_batch, N)) { set_error("drfe_cape_plane_points_voxel: cudaMalloc failed"); return DRFE_ERR_CUDA; }
   }
-  cudaStream_t st = h->stream;
-  const int nf = h->last_frames;
-  const float inv_leaf = 1.0f / leaf_size;                        // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
-  const dim3 grid(8, nf);                                         // up to 8 CTAs share a frame's planes
-  DRFE_LAUNCH(k_voxel_sort, grid, kVoxThreads, 0, st, h->d_plane_pts, h->d_plane_offs, h->hd.nplanes, (int)N, inv_leaf, h->d_vox_key[0], h->d_vox_val[0],
-              h->d_vox_key[1], h->d_vox_val[1], h->d_vox_seg);
-  DRFE_LAUNCH(k_voxel_centroids, grid, 256, 0, st, h->d_plane_pts, h->d_plane_offs, h->hd.nplanes, (int)N, h->d_vox_key[0], h->d_vox_val[0], h->d_vox_key[1],
-              h->d_vox_val[1], h->d_vox_seg, h->d_vox_out, h->d_vox_offs);
-  return cape_points_out(h, "drfe_cape_plane_points_voxel", h->d_vox_out, h->d_vox_offs, points, cap_per_frame, offsets, plane_cap);
+  rc = voxel_filter_launch(h->stream, h->last_frames, h->d_plane_pts, h->d_plane_offs, h->hd.nplanes, (int)N, leaf_size, h->vox);
+  if (rc != DRFE_OK) return rc;
+  return cape_points_out(h, "drfe_cape_plane_points_voxel", h->vox.out, h->vox.out_offs, points, cap_per_frame, offsets, plane_cap);
 }
 
 int drfe_cape_third_cloud(drfe_cape* h, float max_point_dist, float* cloud) {

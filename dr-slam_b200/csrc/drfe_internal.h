@@ -76,6 +76,20 @@ int pdl_max_frames();                          // kPdlMaxFrames, or DRFE_PDL_MAX
   } while (0)
 #endif
 
+// pcl::VoxelGrid::applyFilter on per-(frame, plane) point lists that are already on the device (k_voxel_sort / k_voxel_centroids in
+// cape.cu), for the handles that produce such lists (CAPE's plane_cloud, PEAC's plane vertices): pts [nf][N][3], offs [nf][256]
+// (first point of plane p; offs[np] = total), nplanes [nf].  The scratch holds the centroids (out, [nf][N][3]) and their offsets.
+struct VoxelScratch {
+  uint32_t* key[2] = {nullptr, nullptr};
+  uint32_t* val[2] = {nullptr, nullptr};
+  void* seg = nullptr;
+  float* out = nullptr;
+  int* out_offs = nullptr;
+};
+int voxel_scratch_alloc(VoxelScratch& s, size_t max_frames, size_t N);    // cudaMalloc on the current device; 0 on success
+void voxel_scratch_free(VoxelScratch& s);
+int voxel_filter_launch(cudaStream_t st, int nf, const float* pts, const int* offs, const int* nplanes, int N, float leaf_size, const VoxelScratch& s);
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (kernel, device), not to a handle, and the last setter
 // wins: two live handles of different geometry would shrink each other's limit.  raise_dyn_smem keeps a
 // process-wide high-water mark per (kernel, device) under a mutex and only ever raises the attribute.  The

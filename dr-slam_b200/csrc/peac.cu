@@ -836,10 +836,21 @@ __global__ void __launch_bounds__(kPeacThreads) k_peac_frame(const PeacDev* __re
   }
 }
 
+// the plane a pixel is listed under: its label, or none when the caller culls far points (Frame::ComputePlanes drops the points
+// with (float) z > mMax_point_dist before the voxel filter, Frame.cc:960-963)
+__device__ __forceinline__ int member_key(const PeacDev& P, int f, const uint8_t* __restrict__ seg, int p, float max_z) {
+  const int key = seg[p];
+  if (key == 0 || max_z == FLT_MAX) return key;
+  const int i = p / P.W, j = p - i * P.W;
+  double z;
+  peac_z(P, f, i, j, z);
+  return (float)z > max_z ? 0 : key;
+}
+
 // plane_vertices_ and the member points, like k_cape_plane_points: count per (plane, warp run), scan, stable scatter
 static const int kMemWarps = 32;
 __global__ void __launch_bounds__(kMemWarps * 32) k_peac_members(const PeacDev* __restrict__ Pp, int* __restrict__ out_idx, float* __restrict__ out_pts,
-                                                                  int* __restrict__ offsets) {
+                                                                  int* __restrict__ offsets, float max_z) {
   extern __shared__ int s_pos[];                              // [kMemWarps][np + 1]
   __shared__ int s_start[kPeacMaxPlanes + 2];
   const PeacDev& P = *Pp;
@@ -858,7 +869,7 @@ __global__ void __launch_bounds__(kMemWarps * 32) k_peac_members(const PeacDev* 
   const int p0 = w * run, p1 = min(p0 + run, N);
   int* mine = s_pos + w * stride;
   for (int p = p0 + lane; p - lane < p1; p += 32) {
-    const int key = p < p1 ? seg[p] : 0;
+    const int key = p < p1 ? member_key(P, f, seg, p, max_z) : 0;
     const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
     if (key && (m & lt) == 0) mine[key] += __popc(m);
     __syncwarp();                                                  // the next trip's leader for this key may be another lane
@@ -884,7 +895,7 @@ __global__ void __launch_bounds__(kMemWarps * 32) k_peac_members(const PeacDev* 
   int* oi = out_idx ? out_idx + (long long)f * N : nullptr;
   float* op = out_pts ? out_pts + (long long)f * N * 3 : nullptr;
   for (int p = p0 + lane; p - lane < p1; p += 32) {
-    const int key = p < p1 ? seg[p] : 0;
+    const int key = p < p1 ? member_key(P, f, seg, p, max_z) : 0;
     const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
     const int leader = __ffs(m) - 1;
     int base = 0;
@@ -916,6 +927,7 @@ struct drfe_peac {
   cudaStream_t stream = nullptr;
   uint16_t* d_depth = nullptr;
   int* d_mem_idx = nullptr; float* d_mem_pts = nullptr; int* d_mem_offs = nullptr;
+  VoxelScratch vox;
   std::vector<int> h_offs;
   size_t frame_smem = 0;
   int last_frames = 0;
@@ -1010,6 +1022,7 @@ int drfe_peac_destroy(drfe_peac* h) {
   DeviceScope ds(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  voxel_scratch_free(h->vox);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DRFE_OK;
@@ -1097,7 +1110,7 @@ int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size
     DRFE_CUDA(raise_dyn_smem(k_peac_members, h->device, (size_t)kMemWarps * (kPeacMaxPlanes + 1) * sizeof(int)));
   }
   DRFE_LAUNCH(k_peac_members, nf, kMemWarps * 32, kMemWarps * (kPeacMaxPlanes + 1) * sizeof(int), st, h->dd, indices ? h->d_mem_idx : nullptr,
-              points ? h->d_mem_pts : nullptr, h->d_mem_offs);
+              points ? h->d_mem_pts : nullptr, h->d_mem_offs, FLT_MAX);
   int* ho = h->h_offs.data();
   DRFE_CUDA(cudaMemcpyAsync(ho, h->d_mem_offs, (size_t)nf * (kPeacMaxPlanes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   std::vector<int> np(nf);
@@ -1115,6 +1128,48 @@ int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size
       if (indices) DRFE_CUDA(cudaMemcpyAsync(indices + (size_t)f * cap_per_frame, h->d_mem_idx + (size_t)f * N, (size_t)src[n] * sizeof(int), cudaMemcpyDeviceToHost, st));
       if (points) DRFE_CUDA(cudaMemcpyAsync(points + (size_t)f * cap_per_frame * 3, h->d_mem_pts + (size_t)f * N * 3, (size_t)src[n] * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+  }
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+// Frame::ComputePlanes' per-plane clouds (Frame.cc:954-990): the vertices of every plane with (float) z <= max_point_dist, through
+// pcl::VoxelGrid with a cubic leaf — the lists never leave the device, the centroids do
+int drfe_peac_plane_points_voxel(drfe_peac* h, float max_point_dist, float leaf_size, float* points, size_t cap_per_frame, int* offsets, int plane_cap) {
+  NvtxRange nvtx_("drfe_peac_plane_points_voxel");
+  if (!h || !points || !offsets || plane_cap < 1 || !(leaf_size > 0.f)) { set_error("drfe_peac_plane_points_voxel: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_peac_plane_points_voxel: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  const size_t N = (size_t)h->width * h->height;
+  if (!h->d_mem_offs) {
+    if (peac_alloc(h, &h->d_mem_idx, (size_t)h->max_batch * N) || peac_alloc(h, &h->d_mem_pts, (size_t)h->max_batch * N * 3) ||
+        peac_alloc(h, &h->d_mem_offs, (size_t)h->max_batch * (kPeacMaxPlanes + 1))) return DRFE_ERR_CUDA;
+    h->h_offs.resize((size_t)h->max_batch * (kPeacMaxPlanes + 1));
+    DRFE_CUDA(raise_dyn_smem(k_peac_members, h->device, (size_t)kMemWarps * (kPeacMaxPlanes + 1) * sizeof(int)));
+  }
+  if (!h->vox.out && voxel_scratch_alloc(h->vox, (size_t)h->max_batch, N)) { set_error("drfe_peac_plane_points_voxel: cudaMalloc failed"); return DRFE_ERR_CUDA; }
+  DRFE_LAUNCH(k_peac_members, nf, kMemWarps * 32, kMemWarps * (kPeacMaxPlanes + 1) * sizeof(int), st, h->dd, (int*)nullptr, h->d_mem_pts, h->d_mem_offs,
+              max_point_dist);
+  int rc = voxel_filter_launch(st, nf, h->d_mem_pts, h->d_mem_offs, h->hd.nplanes, (int)N, leaf_size, h->vox);
+  if (rc != DRFE_OK) return rc;
+  int* ho = h->h_offs.data();
+  DRFE_CUDA(cudaMemcpyAsync(ho, h->vox.out_offs, (size_t)nf * (kPeacMaxPlanes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  std::vector<int> np(nf);
+  DRFE_CUDA(cudaMemcpyAsync(np.data(), h->hd.nplanes, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  for (int f = 0; f < nf; ++f) {
+    const int n = std::min(np[f], kPeacMaxPlanes);
+    if (n > plane_cap) { set_error("drfe_peac_plane_points_voxel: frame %d has %d planes, plane_cap is %d", f, n, plane_cap); return DRFE_ERR_CAPACITY; }
+    const int* src = ho + (size_t)f * (kPeacMaxPlanes + 1);
+    int* dst = offsets + (size_t)f * (plane_cap + 1);
+    for (int i = 0; i <= n; ++i) dst[i] = src[i];
+    for (int i = n + 1; i <= plane_cap; ++i) dst[i] = src[n];
+    if ((size_t)src[n] > cap_per_frame) { set_error("drfe_peac_plane_points_voxel: frame %d has %d centroids, cap_per_frame is %zu", f, src[n], cap_per_frame); return DRFE_ERR_CAPACITY; }
+    if (src[n] > 0)
+      DRFE_CUDA(cudaMemcpyAsync(points + (size_t)f * cap_per_frame * 3, h->vox.out + (size_t)f * N * 3, (size_t)src[n] * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;

@@ -93,7 +93,7 @@ SYMBOLS = [
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
     "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_plane_points_voxel", "drfe_cape_third_cloud", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
     "drfe_peac_default_params", "drfe_peac_create", "drfe_peac_destroy", "drfe_peac_stream", "drfe_peac_sync", "drfe_peac_enqueue_depth_u16",
-    "drfe_peac_download", "drfe_peac_plane_vertices", "drfe_peac_debug_counters",
+    "drfe_peac_download", "drfe_peac_plane_vertices", "drfe_peac_plane_points_voxel", "drfe_peac_debug_counters",
     "drfe_resizer_create", "drfe_resizer_destroy", "drfe_resizer_stream", "drfe_resizer_sync", "drfe_resize",
     "drfe_pool_create", "drfe_pool_destroy", "drfe_pool_num_devices", "drfe_pool_max_keypoints", "drfe_pool_extract_batch",
     "drfe_pool_device_times", "drfe_host_alloc", "drfe_host_free", "drfe_host_register", "drfe_host_unregister",
@@ -195,6 +195,7 @@ def lib():
     L.drfe_peac_enqueue_depth_u16.argtypes = [vp, C.c_int, vp, sz, sz, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
     L.drfe_peac_download.argtypes = [vp, vp, vp, C.c_int, vp]
     L.drfe_peac_plane_vertices.argtypes = [vp, vp, vp, sz, vp, C.c_int]
+    L.drfe_peac_plane_points_voxel.argtypes = [vp, C.c_float, C.c_float, vp, sz, vp, C.c_int]
     L.drfe_peac_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_resizer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.drfe_resizer_destroy.argtypes = [vp]
@@ -364,6 +365,15 @@ class PEAC:
         offs = np.zeros((nf, plane_cap + 1), np.int32)
         _check(self.L.drfe_peac_plane_vertices(self.h, _ptr(idx), _ptr(pts), N, _ptr(offs), plane_cap))
         return idx, pts, offs
+
+    def plane_points_voxel(self, max_point_dist=float(np.finfo(np.float32).max), leaf=0.05, plane_cap=255, cap_per_frame=None):
+        """Frame::ComputePlanes' coarseCloud of every plane: z <= max_point_dist, pcl::VoxelGrid(leaf) -> (points, offsets)"""
+        nf = self._nframes
+        N = cap_per_frame or self.H * self.W
+        pts = np.zeros((nf, N, 3), np.float32)
+        offs = np.zeros((nf, plane_cap + 1), np.int32)
+        _check(self.L.drfe_peac_plane_points_voxel(self.h, max_point_dist, leaf, _ptr(pts), N, _ptr(offs), plane_cap))
+        return pts, offs
 
     def counters(self, frame=0):
         out = np.zeros(12, np.int32)

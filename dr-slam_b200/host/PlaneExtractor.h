@@ -136,6 +136,22 @@ class PlaneDetection {
     }
   }
 
+  // What Frame::ComputePlanes does with every plane next (Frame.cc:954-990): the vertices with (float) z <= max_point_dist through
+  // pcl::VoxelGrid(leaf, leaf, leaf), on the device — coarse[i] is `coarseCloud` of plane i (x, y, z triples).  Call after
+  // runPlaneDetection(); the per-plane lists do not have to come to the host for it.
+  void planeCloudsVoxel(float max_point_dist, float leaf, std::vector<std::vector<std::array<float, 3>>>& coarse) {
+    if (!h_) throw std::runtime_error("PlaneDetection::planeCloudsVoxel: runPlaneDetection first");
+    const size_t N = (size_t)cloud.w * cloud.h;
+    pts_.resize(N * 3);
+    offs_.assign(256, 0);
+    check(drfe_peac_plane_points_voxel(h_, max_point_dist, leaf, pts_.data(), N, offs_.data(), 255), "drfe_peac_plane_points_voxel");
+    coarse.assign(plane_num_, std::vector<std::array<float, 3>>());
+    for (int p = 0; p < plane_num_; ++p) {
+      const std::array<float, 3>* first = reinterpret_cast<const std::array<float, 3>*>(pts_.data()) + offs_[p];
+      coarse[p].assign(first, first + (offs_[p + 1] - offs_[p]));
+    }
+  }
+
  private:
   static void check(int rc, const char* what) {
     if (rc != DRFE_OK) throw std::runtime_error(std::string(what) + ": " + drfe_last_error());

@@ -124,6 +124,12 @@ int main(int argc, char** argv) {
         printf(" | %.17g %.17g %.17g %.17g", pl->normal[0], pl->normal[1], pl->normal[2],
                -(pl->normal[0] * pl->center[0] + pl->normal[1] * pl->center[1] + pl->normal[2] * pl->center[2]));
       }
+      std::vector<std::vector<std::array<float, 3>>> coarse;          // voxel.filter(*coarseCloud) of every plane, Frame.cc:981-985
+      planeDetector.planeCloudsVoxel(3.0f, 0.05f, coarse);
+      size_t nc = 0;
+      uint64_t hc = 1469598103934665603ull;
+      for (auto& c : coarse) { nc += c.size(); hc = fnv1a(c.data(), c.size() * sizeof(c[0]), hc); }
+      printf(" | coarse %zu %016llx", nc, (unsigned long long)hc);
       printf("\n");
     }
   } catch (const std::exception& e) {

@@ -482,6 +482,11 @@ int drfe_peac_download(drfe_peac* h, uint8_t* seg_out, drfe_peac_plane* planes, 
 /* plane_vertices_ (pixel indices of every plane, in scan order) and the points Frame::ComputePlanes reads for them
  * (Frame.cc:954-963: (float) of cloud.vertices[j]); layout as drfe_cape_plane_points; indices or points may be null */
 int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size_t cap_per_frame, int* offsets, int plane_cap);
+/* What Frame::ComputePlanes does with every plane right after the extraction (Frame.cc:954-990): the vertices with
+ * (float) z <= max_point_dist (mMax_point_dist; FLT_MAX keeps all), through pcl::VoxelGrid with setLeafSize(leaf, leaf, leaf) —
+ * the declared summation order of drfe_cape_plane_points_voxel applies.  The lists stay on the device, the centroids come back:
+ * points [nframes][cap_per_frame][3], offsets as drfe_peac_plane_vertices */
+int drfe_peac_plane_points_voxel(drfe_peac* h, float max_point_dist, float leaf_size, float* points, size_t cap_per_frame, int* offsets, int plane_cap);
 /* diagnostics of a frame: [0] clustering steps (both passes), [1] region-growing queue length, [2] planes of the first pass,
  * [4..10] kilocycles from the frame's start to the end of: reset, edges, first clustering, block membership + seeds, region
  * growing, second clustering, outputs */

@@ -118,6 +118,12 @@ int main(int argc, char** argv) {
                -(extractedPlane->normal[0] * extractedPlane->center[0] + extractedPlane->normal[1] * extractedPlane->center[1] +
                  extractedPlane->normal[2] * extractedPlane->center[2]));
       }
+      std::vector<std::vector<std::array<float, 3>>> coarse;          // voxel.filter(*coarseCloud) of every plane, Frame.cc:981-985
+      planeDetector.planeCloudsVoxel(3.0f, 0.05f, coarse);
+      size_t nc = 0;
+      uint64_t hc = 1469598103934665603ull;
+      for (auto& c : coarse) { nc += c.size(); hc = fnv1a(c.data(), c.size() * sizeof(c[0]), hc); }
+      printf(" | coarse %zu %016llx", nc, (unsigned long long)hc);
       printf("\n");
     }
   } catch (const std::exception& e) {

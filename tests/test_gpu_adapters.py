@@ -59,7 +59,13 @@ def test_cpp_adapters_match_oracle(drfe, orc, scene, seed):
     if len(pmem):
         assert int(m.group(4), 16) == fnv1a(np.concatenate(pmem).astype(np.int32).tobytes())
         assert int(m.group(5), 16) == fnv1a(np.concatenate([cloud[x] for x in pmem]).astype(np.float32).tobytes())
-    vals = [[float(x) for x in part.split()] for part in m.group(6).split("|")[1:]]
+    parts = [part.split() for part in m.group(6).split("|")[1:]]
+    coarse = [pt for pt in parts if pt and pt[0] == "coarse"]
+    vals = [[float(x) for x in pt] for pt in parts if pt and pt[0] != "coarse"]
+    # planeCloudsVoxel(3 m, 5 cm): the member lists of the restatement, culled and voxel-filtered by the voxel-grid restatement
+    want = [orc.voxel_grid(x[~(x[:, 2] > np.float32(3.0))], 0.05)[0] for x in (cloud[mm].astype(np.float32) for mm in pmem)]
+    assert len(coarse) == 1 and int(coarse[0][1]) == sum(len(w) for w in want)
+    assert int(coarse[0][2], 16) == fnv1a(b"".join(w.tobytes() for w in want))
     for i, v in enumerate(vals):
         assert np.array_equal(v[:3], pplanes[i, :3]) and abs(v[3] + float(pplanes[i, :3] @ pplanes[i, 3:6])) < 1e-12
     assert len(vals) == len(pplanes)

@@ -259,3 +259,29 @@ def test_gpu_peac_argument_and_state_errors(drfe):
     assert L.drfe_peac_create(640, 480, C.byref(prm), 1, 0, C.byref(h)) == drfe.ERR_ARG
     pe.enqueue(q[:2], 2e-4, 525.0, 525.0, 320.0, 240.0)                                                                    # still usable
     assert pe.download()[2].tolist() == [0, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_dist", [3.0, float(np.finfo(np.float32).max)])
+def test_gpu_peac_plane_points_voxel(drfe, orc, max_dist):
+    """Frame::ComputePlanes' per-plane clouds (Frame.cc:954-990): vertices with (float) z <= mMax_point_dist, then the 5 cm pcl::VoxelGrid —
+    drfe_peac_plane_points_voxel against the member lists of the PEAC restatement pushed through the voxel-grid restatement"""
+    fr = [frame(drfe, s, seed, holes) for s, seed, holes in ((1, 20260012, ((100, 140, 300, 420),)), (2, 20260100, ((200, 260, 100, 180),)))]
+    q = np.stack([f[0] for f in fr]); K = fr[0][1]
+    pe = drfe.PEAC(640, 480, max_batch=2)
+    pe.enqueue(q, FAC, *K)
+    seg, planes, npl = pe.download()
+    pts, offs = pe.plane_points_voxel(max_dist, 0.05)
+    for f in range(2):
+        cloud = orc.peac_cloud(q[f], FAC, *K)
+        _, oplanes, omem, _ = orc.peac_run(cloud, 640, 480)
+        assert npl[f] == len(oplanes) and len(oplanes) >= 3
+        culled = 0
+        for p in range(len(oplanes)):
+            xyz = cloud[omem[p]].astype(np.float32)
+            keep = ~(xyz[:, 2] > np.float32(max_dist))
+            culled += int((~keep).sum())
+            want, unfiltered = orc.voxel_grid(xyz[keep], 0.05)
+            got = pts[f, offs[f, p]:offs[f, p + 1]]
+            assert not unfiltered and got.shape == want.shape and got.tobytes() == want.tobytes(), (f, p)
+        assert (culled > 0) == (max_dist < 100)                   # the 3 m cull removes something on these scenes

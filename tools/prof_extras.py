@@ -152,6 +152,14 @@ def main():
     tot = np.array([pe.counters(f)[10] for f in range(B)])
     print("drfe_peac, depth on the device, no download: %7.2f ms per %d frames = %.3f ms per frame; k_peac_frame kilocycles per frame min %d median %d max %d"
           % (msd, B, msd / B, tot.min(), np.median(tot), tot.max()))
+    pin_pv = _t.empty((B, N, 3), dtype=_t.float32).pin_memory().numpy()
+    pin_po = _t.empty((B, 256), dtype=_t.int32).pin_memory().numpy()
+
+    def peac_vox():
+        drfe._check(pe.L.drfe_peac_plane_points_voxel(pe.h, 3.0, 0.05, pin_pv.ctypes.data, N, pin_po.ctypes.data, 255))
+    msv, _ = timed(peac_vox, n=3)
+    print("drfe_peac_plane_points_voxel   %7.2f ms per %d frames (z <= 3 m, 5 cm leaf, pinned destination; %d centroids)"
+          % (msv, B, sum(int(pin_po[f, 255]) for f in range(B))))
     pe1 = drfe.PEAC(W, H)
 
     def peac_one():
