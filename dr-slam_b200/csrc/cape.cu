@@ -2071,6 +2071,7 @@ struct drfe_cape {
   std::vector<int> h_plane_offs;
   VoxelScratch vox;                      // drfe_cape_plane_points_voxel: sort buffers, per (frame, plane) records, centroids, offsets
   float* d_third = nullptr;      // drfe_cape_third_cloud
+  NormalsScratch nrm;            // drfe_cape_third_cloud_normals
   int batch_plane_cap = 0;
   std::vector<void*> allocs;
 };
@@ -2248,6 +2249,7 @@ int drfe_cape_destroy(drfe_cape* h) {
   h->pipe.destroy();
   for (void* p : h->allocs) cudaFree(p);
   voxel_scratch_free(h->vox);
+  normals_scratch_free(h->nrm);
   h->timer.destroy();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -2648,6 +2650,32 @@ int drfe_cape_third_cloud(drfe_cape* h, float max_point_dist, float* cloud) {
   if (h->hd.depth16) DRFE_LAUNCH(k_cape_third_cloud<2>, blocks, 256, 0, st, h->dd, nf, max_point_dist, h->d_third);
   else DRFE_LAUNCH(k_cape_third_cloud<1>, blocks, 256, 0, st, h->dd, nf, max_point_dist, h->d_third);
   DRFE_CUDA(cudaMemcpyAsync(cloud, h->d_third, per * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+// the surface normals Frame::ComputePlanes(_CAPE) takes from pcl::IntegralImageNormalEstimation on that cloud (Frame.cc:1174-1216)
+int drfe_cape_third_cloud_normals(drfe_cape* h, float max_point_dist, float max_depth_change_factor, float normal_smoothing_size, float* cloud, float* normals) {
+  NvtxRange nvtx_("drfe_cape_third_cloud_normals");
+  if (!h || !normals || !(normal_smoothing_size >= 1.f)) { set_error("drfe_cape_third_cloud_normals: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending || (!h->hd.depth && !h->hd.depth16)) { set_error("drfe_cape_third_cloud_normals: no depth image enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  const int w3 = (h->hd.W + 2) / 3, h3 = (h->hd.H + 2) / 3;
+  const size_t per = (size_t)w3 * h3 * 3;
+  if (2 * (int)normal_smoothing_size >= std::min(w3, h3)) { set_error("drfe_cape_third_cloud_normals: smoothing size %g leaves no interior", (double)normal_smoothing_size); return DRFE_ERR_ARG; }
+  if (!h->d_third && cape_alloc(h, &h->d_third, per * h->max_batch)) return DRFE_ERR_CUDA;
+  if (!h->nrm.normals && normals_scratch_alloc(h->nrm, (size_t)h->max_batch, w3, h3)) { set_error("drfe_cape_third_cloud_normals: cudaMalloc failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  DRFE_CUDA(cudaMemcpyAsync(h->dd, &h->hd, sizeof(CapeDev), cudaMemcpyHostToDevice, st));
+  const unsigned blocks = (unsigned)(((size_t)w3 * h3 * nf + 255) / 256);
+  if (h->hd.depth16) DRFE_LAUNCH(k_cape_third_cloud<2>, blocks, 256, 0, st, h->dd, nf, max_point_dist, h->d_third);
+  else DRFE_LAUNCH(k_cape_third_cloud<1>, blocks, 256, 0, st, h->dd, nf, max_point_dist, h->d_third);
+  int rc = normals_launch(st, h->device, nf, h->d_third, w3, h3, max_depth_change_factor, normal_smoothing_size, h->nrm);
+  if (rc != DRFE_OK) return rc;
+  if (cloud) DRFE_CUDA(cudaMemcpyAsync(cloud, h->d_third, per * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaMemcpyAsync(normals, h->nrm.normals, per * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }

@@ -90,6 +90,19 @@ int voxel_scratch_alloc(VoxelScratch& s, size_t max_frames, size_t N);    // cud
 void voxel_scratch_free(VoxelScratch& s);
 int voxel_filter_launch(cudaStream_t st, int nf, const float* pts, const int* offs, const int* nplanes, int N, float leaf_size, const VoxelScratch& s);
 
+// pcl::IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT) on organized device clouds [nf][h][w][3] (normals.cu)
+struct NormalsScratch {
+  float* dist = nullptr;        // [nf][h][w] distance map
+  double* I = nullptr;          // [nf][2][h + 1][w + 1][3] integral images of the x- and y-differences
+  unsigned* Cn = nullptr;       // [nf][2][h + 1][w + 1] finite counts
+  float* normals = nullptr;     // [nf][h][w][3]
+};
+int normals_scratch_alloc(NormalsScratch& s, size_t max_frames, int w, int h);
+void normals_scratch_free(NormalsScratch& s);
+int third_cloud_u16_launch(cudaStream_t st, int nf, const uint16_t* depth, long long rs, long long fs, float factor, float fx, float fy, float cx, float cy, int W, int H,
+                           float max_point_dist, float* out);
+int normals_launch(cudaStream_t st, int device, int nf, const float* cloud, int w, int h, float max_depth_change_factor, float smoothing_size, const NormalsScratch& s);
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (kernel, device), not to a handle, and the last setter
 // wins: two live handles of different geometry would shrink each other's limit.  raise_dyn_smem keeps a
 // process-wide high-water mark per (kernel, device) under a mutex and only ever raises the attribute.  The

@@ -928,6 +928,8 @@ struct drfe_peac {
   uint16_t* d_depth = nullptr;
   int* d_mem_idx = nullptr; float* d_mem_pts = nullptr; int* d_mem_offs = nullptr;
   VoxelScratch vox;
+  float* d_third = nullptr;
+  NormalsScratch nrm;
   std::vector<int> h_offs;
   size_t frame_smem = 0;
   int last_frames = 0;
@@ -1023,6 +1025,7 @@ int drfe_peac_destroy(drfe_peac* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   voxel_scratch_free(h->vox);
+  normals_scratch_free(h->nrm);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DRFE_OK;
@@ -1171,6 +1174,32 @@ int drfe_peac_plane_points_voxel(drfe_peac* h, float max_point_dist, float leaf_
     if (src[n] > 0)
       DRFE_CUDA(cudaMemcpyAsync(points + (size_t)f * cap_per_frame * 3, h->vox.out + (size_t)f * N * 3, (size_t)src[n] * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
+  DRFE_CUDA(cudaStreamSynchronize(st));
+  return DRFE_OK;
+}
+
+// the 1/3-resolution cloud of Frame::ComputePlanes (Frame.cc:1044-1066) and PCL's integral-image normals on it (:1068-1100), from the
+// depth batch the handle was given (imDepth = float(raw) * depth factor)
+int drfe_peac_third_cloud_normals(drfe_peac* h, float max_point_dist, float max_depth_change_factor, float normal_smoothing_size, float* cloud, float* normals) {
+  NvtxRange nvtx_("drfe_peac_third_cloud_normals");
+  if (!h || !normals || !(normal_smoothing_size >= 1.f)) { set_error("drfe_peac_third_cloud_normals: bad argument"); return DRFE_ERR_ARG; }
+  if (!h->pending) { set_error("drfe_peac_third_cloud_normals: nothing enqueued"); return DRFE_ERR_STATE; }
+  DeviceScope ds(h->device);
+  if (!ds.ok) { set_error("cudaSetDevice failed"); return DRFE_ERR_CUDA; }
+  const int w3 = (h->width + 2) / 3, h3 = (h->height + 2) / 3;
+  const size_t per = (size_t)w3 * h3 * 3;
+  if (2 * (int)normal_smoothing_size >= std::min(w3, h3)) { set_error("drfe_peac_third_cloud_normals: smoothing size %g leaves no interior", (double)normal_smoothing_size); return DRFE_ERR_ARG; }
+  if (!h->d_third && peac_alloc(h, &h->d_third, per * h->max_batch)) return DRFE_ERR_CUDA;
+  if (!h->nrm.normals && normals_scratch_alloc(h->nrm, (size_t)h->max_batch, w3, h3)) { set_error("drfe_peac_third_cloud_normals: cudaMalloc failed"); return DRFE_ERR_CUDA; }
+  cudaStream_t st = h->stream;
+  const int nf = h->last_frames;
+  int rc = third_cloud_u16_launch(st, nf, h->hd.depth, h->hd.depth_rs, h->hd.depth_fs, h->hd.depth_factor, h->hd.fx, h->hd.fy, h->hd.cx, h->hd.cy, h->width, h->height,
+                                  max_point_dist, h->d_third);
+  if (rc != DRFE_OK) return rc;
+  rc = normals_launch(st, h->device, nf, h->d_third, w3, h3, max_depth_change_factor, normal_smoothing_size, h->nrm);
+  if (rc != DRFE_OK) return rc;
+  if (cloud) DRFE_CUDA(cudaMemcpyAsync(cloud, h->d_third, per * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DRFE_CUDA(cudaMemcpyAsync(normals, h->nrm.normals, per * nf * sizeof(float), cudaMemcpyDeviceToHost, st));
   DRFE_CUDA(cudaStreamSynchronize(st));
   return DRFE_OK;
 }

@@ -91,9 +91,9 @@ SYMBOLS = [
     "drfe_cape_enqueue_depth_u16", "drfe_cape_process_depth_batch", "drfe_cape_finish_batch",
     "drfe_cape_download", "drfe_cape_sync", "drfe_cape_stream", "drfe_cape_process",
     "drfe_cape_process_depth", "drfe_cape_num_cells", "drfe_cape_get_cloud", "drfe_cape_get_cells",
-    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_plane_points_voxel", "drfe_cape_third_cloud", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
+    "drfe_cape_get_grid_maps", "drfe_cape_plane_points", "drfe_cape_plane_points_voxel", "drfe_cape_third_cloud", "drfe_cape_third_cloud_normals", "drfe_cape_cylinders_found", "drfe_cape_get_cyl_maps", "drfe_cape_debug_counters", "drfe_cape_set_profiling", "drfe_cape_stage_times",
     "drfe_peac_default_params", "drfe_peac_create", "drfe_peac_destroy", "drfe_peac_stream", "drfe_peac_sync", "drfe_peac_enqueue_depth_u16",
-    "drfe_peac_download", "drfe_peac_plane_vertices", "drfe_peac_plane_points_voxel", "drfe_peac_debug_counters",
+    "drfe_peac_download", "drfe_peac_plane_vertices", "drfe_peac_plane_points_voxel", "drfe_peac_third_cloud_normals", "drfe_peac_debug_counters",
     "drfe_resizer_create", "drfe_resizer_destroy", "drfe_resizer_stream", "drfe_resizer_sync", "drfe_resize",
     "drfe_pool_create", "drfe_pool_destroy", "drfe_pool_num_devices", "drfe_pool_max_keypoints", "drfe_pool_extract_batch",
     "drfe_pool_device_times", "drfe_host_alloc", "drfe_host_free", "drfe_host_register", "drfe_host_unregister",
@@ -182,6 +182,7 @@ def lib():
     L.drfe_cape_plane_points.argtypes = [vp, vp, sz, vp, C.c_int]
     L.drfe_cape_plane_points_voxel.argtypes = [vp, C.c_float, vp, sz, vp, C.c_int]
     L.drfe_cape_third_cloud.argtypes = [vp, C.c_float, vp]
+    L.drfe_cape_third_cloud_normals.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp, vp]
     L.drfe_cape_get_cyl_maps.argtypes = [vp, C.c_int, vp, vp]
     L.drfe_cape_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_cape_set_profiling.argtypes = [vp, C.c_int]
@@ -196,6 +197,7 @@ def lib():
     L.drfe_peac_download.argtypes = [vp, vp, vp, C.c_int, vp]
     L.drfe_peac_plane_vertices.argtypes = [vp, vp, vp, sz, vp, C.c_int]
     L.drfe_peac_plane_points_voxel.argtypes = [vp, C.c_float, C.c_float, vp, sz, vp, C.c_int]
+    L.drfe_peac_third_cloud_normals.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp, vp]
     L.drfe_peac_debug_counters.argtypes = [vp, C.c_int, vp]
     L.drfe_resizer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.drfe_resizer_destroy.argtypes = [vp]
@@ -374,6 +376,14 @@ class PEAC:
         offs = np.zeros((nf, plane_cap + 1), np.int32)
         _check(self.L.drfe_peac_plane_points_voxel(self.h, max_point_dist, leaf, _ptr(pts), N, _ptr(offs), plane_cap))
         return pts, offs
+
+    def third_cloud_normals(self, max_point_dist, max_depth_change_factor=0.05, smoothing_size=10.0):
+        """Frame::ComputePlanes' 1/3-resolution cloud and PCL's integral-image normals on it (Frame.cc:1044-1100) -> (cloud, normals)"""
+        nf = self._nframes
+        cloud = np.empty((nf, (self.H + 2) // 3, (self.W + 2) // 3, 3), np.float32)
+        normals = np.empty_like(cloud)
+        _check(self.L.drfe_peac_third_cloud_normals(self.h, max_point_dist, max_depth_change_factor, smoothing_size, _ptr(cloud), _ptr(normals)))
+        return cloud, normals
 
     def counters(self, frame=0):
         out = np.zeros(12, np.int32)
@@ -860,6 +870,14 @@ class CAPE:
         out = np.empty((nf, (self.H + 2) // 3, (self.W + 2) // 3, 3), np.float32)
         _check(self.L.drfe_cape_third_cloud(self.h, max_point_dist, _ptr(out)))
         return out
+
+    def third_cloud_normals(self, max_point_dist, max_depth_change_factor=0.05, smoothing_size=10.0, nframes=None):
+        """the 1/3-resolution cloud and PCL's integral-image normals on it (Frame.cc:1153-1216) -> (cloud, normals), NaN where PCL has NaN"""
+        nf = nframes or max(getattr(self, "_nframes", 1) or 1, 1)
+        cloud = np.empty((nf, (self.H + 2) // 3, (self.W + 2) // 3, 3), np.float32)
+        normals = np.empty_like(cloud)
+        _check(self.L.drfe_cape_third_cloud_normals(self.h, max_point_dist, max_depth_change_factor, smoothing_size, _ptr(cloud), _ptr(normals)))
+        return cloud, normals
 
     def cylinders_found(self):
         """length of cylinder_segments_final per frame of the last call (CAPE.cpp:434-445)"""

@@ -416,6 +416,12 @@ int drfe_cape_plane_points_voxel(drfe_cape* h, float leaf_size, float* points, s
  * depth of the last batch: cloud [nframes][ceil(H/3)][ceil(W/3)][3], z = d > max_point_dist ? 0 : d, x = (n - cx) * z / fx in
  * float.  (The normal estimation itself — pcl::IntegralImageNormalEstimation — is not part of this library.) */
 int drfe_cape_third_cloud(drfe_cape* h, float max_point_dist, float* cloud);
+/* ... and the surface normals DR-SLAM takes from PCL on that cloud (Frame.cc:1174-1216, :1057-1100: pcl::IntegralImageNormalEstimation,
+ * AVERAGE_3D_GRADIENT, setMaxDepthChangeFactor(0.05f), setNormalSmoothingSize(10.0f), border policy and viewpoint at their defaults):
+ * normals [nframes][ceil(H/3)][ceil(W/3)][3], NaN where PCL leaves NaN (the border of int(smoothing) points, depth discontinuities,
+ * empty windows); cloud as drfe_cape_third_cloud, may be NULL.  PCL is not vendored in the reference: this is its published algorithm
+ * (PCL 1.9 integral_image_normal.hpp / integral_image2D.hpp) as restated in oracle/normals_oracle.cpp — parity unpinned by PCL itself. */
+int drfe_cape_third_cloud_normals(drfe_cape* h, float max_point_dist, float max_depth_change_factor, float normal_smoothing_size, float* cloud, float* normals);
 int drfe_cape_cylinders_found(drfe_cape* h, int* counts); /* counts[f] = cylinder_segments_final.size() */
 int drfe_cape_sync(drfe_cape* h);
 void* drfe_cape_stream(drfe_cape* h);
@@ -487,6 +493,10 @@ int drfe_peac_plane_vertices(drfe_peac* h, int32_t* indices, float* points, size
  * the declared summation order of drfe_cape_plane_points_voxel applies.  The lists stay on the device, the centroids come back:
  * points [nframes][cap_per_frame][3], offsets as drfe_peac_plane_vertices */
 int drfe_peac_plane_points_voxel(drfe_peac* h, float max_point_dist, float leaf_size, float* points, size_t cap_per_frame, int* offsets, int plane_cap);
+/* the 1/3-resolution cloud Frame::ComputePlanes builds from imDepth (Frame.cc:1044-1066) and the surface normals it takes from
+ * pcl::IntegralImageNormalEstimation on it (:1068-1100) — as drfe_cape_third_cloud / drfe_cape_third_cloud_normals, from the depth batch
+ * this handle was given; cloud may be NULL */
+int drfe_peac_third_cloud_normals(drfe_peac* h, float max_point_dist, float max_depth_change_factor, float normal_smoothing_size, float* cloud, float* normals);
 /* diagnostics of a frame: [0] clustering steps (both passes), [1] region-growing queue length, [2] planes of the first pass,
  * [4..10] kilocycles from the frame's start to the end of: reset, edges, first clustering, block membership + seeds, region
  * growing, second clustering, outputs */

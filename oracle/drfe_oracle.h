@@ -68,6 +68,7 @@ int orc_cape_get_cyl_maps(void* h, int32_t* cyl_map, uint8_t* cyl_eroded_map);
 /* the declared rand() stream of CylinderSeg: glibc TYPE_3, srand(seed) */
 int orc_glibc_rand(uint32_t seed, int n, int32_t* out);
 /* PEAC (ahc::PlaneFitter, include/peac/): PlaneDetection::readDepthImage and PlaneFitter::run with doRefine (peac_oracle.cpp) */
+void orc_integral_normals(const float* cloud, int w, int h, float max_depth_change_factor, float smoothing_size, float* normals, float* distance_map);
 void orc_peac_fit(const double* s9, int N, double* out8);
 void orc_peac_cloud(const uint16_t* depth, int width, int height, int row_stride, float depth_factor, float fx, float fy, float cx, float cy,
                     double* cloud);

@@ -100,6 +100,7 @@ def lib():
         L.orc_cape_cylinders_found.argtypes = [C.c_void_p]
         L.orc_cape_get_cyl_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_integral_normals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_peac_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_peac_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_peac_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
@@ -914,6 +915,17 @@ def third_cloud(depth, fx, fy, cx, cy, max_point_dist):
     out = np.empty(((H + 2) // 3, (W + 2) // 3, 3), np.float32)
     lib().orc_third_cloud(_p(depth), W, H, depth.strides[0] // 4, fx, fy, cx, cy, max_point_dist, _p(out))
     return out
+
+
+def integral_normals(cloud, max_depth_change_factor=0.05, smoothing_size=10.0, with_distance_map=False):
+    """pcl::IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT) as DR-SLAM configures it (reference src/Frame.cc:1174-1187) on an
+    organized (h, w, 3) float cloud -> (h, w, 3) normals, NaN where PCL leaves NaN [, the distance map]"""
+    cloud = np.ascontiguousarray(cloud, np.float32)
+    h, w, _ = cloud.shape
+    out = np.empty((h, w, 3), np.float32)
+    dm = np.empty((h, w), np.float32) if with_distance_map else None
+    lib().orc_integral_normals(_p(cloud), w, h, max_depth_change_factor, smoothing_size, _p(out), _p(dm) if with_distance_map else None)
+    return (out, dm) if with_distance_map else out
 
 
 def glibc_rand(seed, n):

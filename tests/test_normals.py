@@ -1,0 +1,91 @@
+"""The surface normals DR-SLAM takes from pcl::IntegralImageNormalEstimation on the 1/3-resolution cloud (reference src/Frame.cc:1174-1216).
+PCL is not vendored in the reference and not installed here: oracle/normals_oracle.cpp restates PCL 1.9's published algorithm (parity
+unpinned by PCL).  CPU: properties of the restatement — exact normals on planes seen in perspective, PCL's NaN pattern, the window rule,
+depth discontinuities.  GPU: drfe_cape_third_cloud_normals is bit-identical to the restatement, NaN for NaN."""
+import numpy as np
+import pytest
+
+MC = float(np.float32(np.cos(np.pi / 12)))
+
+
+def plane_cloud(w, h, n, d, fx, fy, cx, cy):
+    jj, ii = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    z = d / (n[0] * (jj - cx) / fx + n[1] * (ii - cy) / fy + n[2])
+    return np.stack([(jj - cx) / fx * z, (ii - cy) / fy * z, z], -1).astype(np.float32)
+
+
+def test_normals_of_planes_and_the_nan_border(orc):
+    w, h = 214, 160
+    for n, d in (((0.3, -0.2, 1.0), 2.0), ((0.0, 0.0, 1.0), 1.5), ((-0.5, 0.1, 0.8), 3.0)):
+        cloud = plane_cloud(w, h, n, d, 175.0, 175.0, 106.5, 79.5)
+        nr, dm = orc.integral_normals(cloud, with_distance_map=True)
+        want = -np.array(n) / np.linalg.norm(n)                     # flipped towards the camera at the origin
+        assert np.isnan(nr[:10]).all() and np.isnan(nr[-10:]).all() and np.isnan(nr[:, :10]).all() and np.isnan(nr[:, -10:]).all()
+        assert not np.isnan(nr[10:-10, 10:-10]).any() and np.abs(nr[10:-10, 10:-10] - want).max() < 2e-6
+        assert (dm == w + h).all()                                  # no depth discontinuity anywhere
+
+
+def test_depth_discontinuity_and_window_rule(orc):
+    w, h = 214, 160
+    cloud = plane_cloud(w, h, (0.0, 0.0, 1.0), 2.0, 175.0, 175.0, 106.5, 79.5)
+    near = plane_cloud(w, h, (0.2, 0.0, 1.0), 1.0, 175.0, 175.0, 106.5, 79.5)
+    cloud[40:120, 60:150] = near[40:120, 60:150]                    # a box in front of the wall: jumps of ~1 m along its outline
+    nr, dm = orc.integral_normals(cloud, with_distance_map=True)
+    assert dm[40, 100] == 0 and dm[39, 100] == 0 and dm[80, 60] == 0 and dm[80, 59] == 0       # both sides of the jump are marked
+    assert dm[80, 100] > 10 and dm[20, 30] > 10
+    # chamfer distances: 1.0 per axial step, 1.4f per diagonal step, float additions in scan order
+    assert dm[41, 100] == np.float32(1.0) and dm[42, 100] == np.float32(2.0) and dm[80, 63] == np.float32(3.0)
+    inside = nr[60:100, 80:130]
+    assert np.abs(inside - (-np.array([0.2, 0, 1.0]) / np.linalg.norm([0.2, 0, 1.0]))).max() < 2e-6
+    # smoothing = min(distance, 10) > 2 is needed: next to the jump (distance <= 2) the normal is NaN, three steps away it is not
+    assert np.isnan(nr[41, 100]).all() and np.isnan(nr[42, 100]).all() and not np.isnan(nr[43, 100]).any()
+    # a zero-depth region (the far cull writes x = y = z = 0) is finite: PCL estimates there too; |n|^2 == 0 gives NaN
+    cloud2 = cloud.copy(); cloud2[130:150, 20:200] = 0
+    nr2 = orc.integral_normals(cloud2)
+    assert np.isnan(nr2[138:142, 60:160]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,seed,u16,clean", [(1, 20260042, False, True), (2, 20260100, False, False), (0, 20260007, True, True)])
+def test_gpu_third_cloud_normals_equal_the_restatement(drfe, orc, scene, seed, u16, clean):
+    from test_peac import clean_depth
+    frames = [drfe.synth_frame(640, 480, scene, seed + i) for i in range(3)]
+    K = frames[0][2]
+    # the synthetic sensor drops 2 % of the pixels independently: every dropout is a depth jump, and with them almost every window is
+    # rejected (the NaN pattern is then most of the result); the cleaned variant keeps coherent holes only, like a real sensor
+    depth = np.stack([clean_depth(f[1], ((100, 140, 300, 420),)) if clean else f[1] for f in frames])
+    cp = drfe.CAPE(480, 640, 20, 20, False, MC, 50.0, max_batch=3)
+    if u16:
+        q = np.rint(depth * 5000).astype(np.uint16)
+        fac = float(np.float32(1.0 / 5000.0))
+        cp.enqueue_depth_u16(q, fac, *K)
+        depth = q.astype(np.float32) * np.float32(fac)
+    else:
+        cp.enqueue_depth(depth, *K)
+    cp.download()
+    dist_max = 10.0 if clean else 3.0                              # mMax_point_dist: with 3 m most of these rooms is culled to (0, 0, 0)
+    cloud, normals = cp.third_cloud_normals(dist_max)
+    for f in range(3):
+        want_cloud = orc.third_cloud(depth[f], *K, dist_max)
+        assert cloud[f].tobytes() == want_cloud.tobytes()
+        want = orc.integral_normals(want_cloud, 0.05, 10.0)
+        assert np.array_equal(np.isnan(normals[f]), np.isnan(want)), f
+        ok = ~np.isnan(want)
+        assert ok.mean() > (0.5 if clean else 0.01) and normals[f][ok].tobytes() == want[ok].tobytes(), f
+
+
+@pytest.mark.gpu
+def test_gpu_peac_handle_gives_the_same_cloud_and_normals(drfe, orc):
+    """Frame::ComputePlanes (the PEAC path, Frame.cc:1044-1100) builds the same 1/3 cloud from imDepth = float(raw) * factor"""
+    from test_peac import FAC, frame
+    q, K = frame(drfe, 1, 20260012, ((100, 140, 300, 420),))
+    pe = drfe.PEAC(640, 480)
+    pe.enqueue(q[None], FAC, *K)
+    pe.download()
+    cloud, normals = pe.third_cloud_normals(10.0)
+    depth = q.astype(np.float32) * np.float32(FAC)
+    want_cloud = orc.third_cloud(depth, *K, 10.0)
+    assert cloud[0].tobytes() == want_cloud.tobytes()
+    want = orc.integral_normals(want_cloud)
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(normals[0]), ~ok) and ok.mean() > 0.5 and normals[0][ok].tobytes() == want[ok].tobytes()
