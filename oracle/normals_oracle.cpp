@@ -24,6 +24,10 @@
 //      0 on the image border; integral images of both in DOUBLE by I(r+1, c+1) = I(r, c+1) + I(r+1, c) - I(r, c) (+ the element if its
 //      x + y + z is finite, which also counts it); the window [c - s/2, r - s/2] of s x s elements: NaN when either finite count is 0;
 //      n = gy x gx (double), NaN when |n|^2 == 0, n / sqrt(|n|^2), cast to float, flipped so that (0 - P) . n >= 0; curvature is NaN.
+// Details a maintainer with PCL 1.9 at hand should check first (they decide last bits and the NaN outline, not the normals of smooth
+// surfaces): U.1 the bounds of the two raster passes (rows 1..H-1 / cols 1..W-1, then rows H-2..0 / cols W-2..0) and so which reads fall
+// one element outside the row; U.2 the threshold's trailing `* 2.0f`; U.3 the window origin `pos - rect/2` with rect = int(smoothing)
+// for both axes; U.4 the association (previous[c+1] + current[c]) - previous[c] in the integral-image recurrence.
 // PARITY STATUS: "parity unpinned" — no PCL here to run, the reference has no fixture; the restatement is pinned only by its own
 // properties (tests/test_normals.py: exact normals on synthetic planes, NaN pattern, the window rule).  The GPU path
 // (drfe_cape_third_cloud_normals) is bit-identical to THIS restatement.
