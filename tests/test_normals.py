@@ -89,3 +89,77 @@ def test_gpu_peac_handle_gives_the_same_cloud_and_normals(drfe, orc):
     want = orc.integral_normals(want_cloud)
     ok = ~np.isnan(want)
     assert np.array_equal(np.isnan(normals[0]), ~ok) and ok.mean() > 0.5 and normals[0][ok].tobytes() == want[ok].tobytes()
+
+
+def brute_force_normals(cloud, factor=0.05, smoothing=10.0):
+    """an independent formulation of the same published algorithm: scatter-form change map, the raster passes as plain Python loops over a
+    flat list (so the one-past-the-row reads are literal), window sums by numpy's own 2-D cumulative sums in float64"""
+    h, w, _ = cloud.shape
+    z = cloud[:, :, 2].astype(np.float32)
+    change = np.full(h * w, 255, np.uint8)
+    th = (np.float32(factor) * (np.abs(z) + np.float32(1.0)) * np.float32(2.0)).astype(np.float32)
+    for r in range(h - 1):
+        for c in range(w - 1):
+            i = r * w + c
+            if abs(float(z[r, c] - z[r, c + 1])) > th[r, c] or not np.isfinite(z[r, c]) or not np.isfinite(z[r, c + 1]):
+                change[i] = change[i + 1] = 0
+            if abs(float(z[r, c] - z[r + 1, c])) > th[r, c] or not np.isfinite(z[r, c]) or not np.isfinite(z[r + 1, c]):
+                change[i] = change[i + w] = 0
+    f32 = np.float32
+    d = [f32(0.0) if v == 0 else f32(w + h) for v in change]
+    one, diag = f32(1.0), f32(1.4)
+    for r in range(1, h):
+        pr, cu = (r - 1) * w, r * w
+        for c in range(1, w):
+            m = min(min(d[pr + c - 1] + diag, d[pr + c] + one), min(d[cu + c - 1] + one, d[pr + c + 1] + diag))
+            if m < d[cu + c]:
+                d[cu + c] = m
+    for r in range(h - 2, -1, -1):
+        nx, cu = (r + 1) * w, r * w
+        for c in range(w - 2, -1, -1):
+            m = min(min(d[nx + c - 1] + diag, d[nx + c] + one), min(d[cu + c + 1] + one, d[nx + c + 1] + diag))
+            if m < d[cu + c]:
+                d[cu + c] = m
+    dm = np.array(d, np.float32).reshape(h, w)
+    P = cloud.astype(np.float32)
+    dx = np.zeros((h, w, 3), np.float32); dy = np.zeros((h, w, 3), np.float32)
+    dx[1:-1, 1:-1] = P[1:-1, 2:] - P[1:-1, :-2]
+    dy[1:-1, 1:-1] = P[2:, 1:-1] - P[:-2, 1:-1]
+    Ix = np.zeros((h + 1, w + 1, 3)); Iy = np.zeros((h + 1, w + 1, 3))
+    Ix[1:, 1:] = dx.astype(np.float64).cumsum(0).cumsum(1)
+    Iy[1:, 1:] = dy.astype(np.float64).cumsum(0).cumsum(1)
+    out = np.full((h, w, 3), np.nan, np.float32)
+    b = int(smoothing)
+    for r in range(b, h - b):
+        for c in range(b, w - b):
+            sm = min(dm[r, c], np.float32(smoothing))
+            if not (np.isfinite(z[r, c]) and sm > 2.0):
+                continue
+            s = int(sm)
+            x0, y0 = c - s // 2, r - s // 2
+            gx = Ix[y0 + s, x0 + s] + Ix[y0, x0] - Ix[y0, x0 + s] - Ix[y0 + s, x0]
+            gy = Iy[y0 + s, x0 + s] + Iy[y0, x0] - Iy[y0, x0 + s] - Iy[y0 + s, x0]
+            n = np.cross(gy, gx)
+            l2 = float(n @ n)
+            if l2 == 0.0:
+                continue
+            n = (n / np.sqrt(l2)).astype(np.float32)
+            if float(-(P[r, c] @ n)) < 0:
+                n = -n
+            out[r, c] = n
+    return out, dm
+
+
+def test_restatement_agrees_with_an_independent_formulation(drfe, orc):
+    """the C++ restatement against brute_force_normals on a real-looking cloud (depth jumps, culled far points, a hole): identical
+    distance map (float for float) and NaN pattern, normals equal to 1e-5 (the window sums are associated differently)"""
+    from test_peac import clean_depth
+    _, depth, K = drfe.synth_frame(640, 480, 2, 20260100)
+    cloud = orc.third_cloud(clean_depth(depth, ((200, 260, 100, 180),)), *K, 4.0)
+    nr, dm = orc.integral_normals(cloud, with_distance_map=True)
+    bn, bdm = brute_force_normals(cloud)
+    assert np.array_equal(dm, bdm)
+    # a window whose gradients cancel to exactly 0 in one association may leave 1e-17 in the other: compare where both are finite
+    both = ~np.isnan(nr[..., 0]) & ~np.isnan(bn[..., 0])
+    assert (np.isnan(nr[..., 0]) != np.isnan(bn[..., 0])).mean() < 1e-3 and both.mean() > 0.2
+    assert np.abs(nr[both] - bn[both]).max() < 1e-5
