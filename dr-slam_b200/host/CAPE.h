@@ -202,6 +202,17 @@ class PlaneDetection_CAPE {
     }
   }
 
+  // What Frame::ComputePlanes_CAPE computes next on the depth image (Frame.cc:1153-1216): the 1/3-resolution cloud (far points zeroed)
+  // and PCL's integral-image surface normals on it (AVERAGE_3D_GRADIENT, depth-change factor 0.05, smoothing 10).  cloud3 / normals3:
+  // [h3][w3][3] floats, inputCloud->at(n, m) = cloud3[(m * w3 + n) * 3 ..], NaN where PCL leaves NaN.  Call after runPlaneDetection().
+  void thirdCloudNormals(float max_point_dist, std::vector<float>& cloud3, std::vector<float>& normals3, int& w3, int& h3) {
+    if (!plane_detector) throw std::runtime_error("PlaneDetection_CAPE::thirdCloudNormals: runPlaneDetection first");
+    w3 = (depth_img.cols + 2) / 3; h3 = (depth_img.rows + 2) / 3;
+    cloud3.resize((size_t)w3 * h3 * 3); normals3.resize((size_t)w3 * h3 * 3);
+    if (drfe_cape_third_cloud_normals(plane_detector->handle(), max_point_dist, 0.05f, 10.0f, cloud3.data(), normals3.data()) != DRFE_OK)
+      throw std::runtime_error(std::string("drfe_cape_third_cloud_normals: ") + drfe_last_error());
+  }
+
   std::vector<PointCloud> plane_cloud;
   std::vector<PlaneSeg> plane_params;
   std::vector<CylinderSeg> cylinder_params;

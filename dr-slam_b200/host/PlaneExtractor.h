@@ -152,6 +152,15 @@ class PlaneDetection {
     }
   }
 
+  // ... and on the depth image (Frame.cc:1044-1100): the 1/3-resolution cloud (far points zeroed) and PCL's integral-image surface
+  // normals on it.  cloud3 / normals3: [h3][w3][3] floats, inputCloud->at(n, m) = cloud3[(m * w3 + n) * 3 ..], NaN where PCL leaves NaN
+  void thirdCloudNormals(float max_point_dist, std::vector<float>& cloud3, std::vector<float>& normals3, int& w3, int& h3) {
+    if (!h_) throw std::runtime_error("PlaneDetection::thirdCloudNormals: runPlaneDetection first");
+    w3 = (cloud.w + 2) / 3; h3 = (cloud.h + 2) / 3;
+    cloud3.resize((size_t)w3 * h3 * 3); normals3.resize((size_t)w3 * h3 * 3);
+    check(drfe_peac_third_cloud_normals(h_, max_point_dist, 0.05f, 10.0f, cloud3.data(), normals3.data()), "drfe_peac_third_cloud_normals");
+  }
+
  private:
   static void check(int rc, const char* what) {
     if (rc != DRFE_OK) throw std::runtime_error(std::string(what) + ": " + drfe_last_error());

@@ -130,6 +130,14 @@ int main(int argc, char** argv) {
       uint64_t hc = 1469598103934665603ull;
       for (auto& c : coarse) { nc += c.size(); hc = fnv1a(c.data(), c.size() * sizeof(c[0]), hc); }
       printf(" | coarse %zu %016llx", nc, (unsigned long long)hc);
+      std::vector<float> cloud3, normals3;                            // Frame.cc:1044-1100: the 1/3 cloud and PCL's normals on it
+      int w3 = 0, h3 = 0;
+      planeDetector.thirdCloudNormals(10.0f, cloud3, normals3, w3, h3);
+      size_t nn = 0;
+      uint64_t hn = 1469598103934665603ull;
+      for (size_t i = 0; i < normals3.size(); i += 3)
+        if (normals3[i] == normals3[i]) { ++nn; hn = fnv1a(&normals3[i], 3 * sizeof(float), hn); }
+      printf(" | normals %d %d %zu %016llx", w3, h3, nn, (unsigned long long)hn);
       printf("\n");
     }
   } catch (const std::exception& e) {

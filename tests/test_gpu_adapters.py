@@ -61,7 +61,13 @@ def test_cpp_adapters_match_oracle(drfe, orc, scene, seed):
         assert int(m.group(5), 16) == fnv1a(np.concatenate([cloud[x] for x in pmem]).astype(np.float32).tobytes())
     parts = [part.split() for part in m.group(6).split("|")[1:]]
     coarse = [pt for pt in parts if pt and pt[0] == "coarse"]
-    vals = [[float(x) for x in pt] for pt in parts if pt and pt[0] != "coarse"]
+    nrm = [pt for pt in parts if pt and pt[0] == "normals"]
+    vals = [[float(x) for x in pt] for pt in parts if pt and pt[0] not in ("coarse", "normals")]
+    # thirdCloudNormals(10 m): the 1/3 cloud of imDepth = float(raw) * factor and the restated PCL normals on it
+    wn = orc.integral_normals(orc.third_cloud(q.astype(np.float32) * np.float32(fac), *K, 10.0))
+    okn = ~np.isnan(wn[..., 0])
+    assert len(nrm) == 1 and [int(x) for x in nrm[0][1:4]] == [214, 160, int(okn.sum())]
+    assert int(nrm[0][4], 16) == fnv1a(wn[okn].tobytes())
     # planeCloudsVoxel(3 m, 5 cm): the member lists of the restatement, culled and voxel-filtered by the voxel-grid restatement
     want = [orc.voxel_grid(x[~(x[:, 2] > np.float32(3.0))], 0.05)[0] for x in (cloud[mm].astype(np.float32) for mm in pmem)]
     assert len(coarse) == 1 and int(coarse[0][1]) == sum(len(w) for w in want)
