@@ -14,14 +14,19 @@
 //       cluster       the pop-min / best-neighbour / merge loop.  The queue is an argmin over (mse, creation number) of the queued
 //                     nodes (a total order, so any priority structure pops the same sequence); a merged node takes over the slot
 //                     of the popped one, whose neighbours are its neighbours anyway, adjacency is a bit matrix over slots with
-//                     dead slots skipped; the merge candidates of a step are fitted in parallel, one thread each
+//                     dead slots skipped; the merge candidates of a step are fitted in parallel, one thread each, the best one is
+//                     found by shared-memory atomics on the ordered bit patterns of the mse, and the thread that fitted it — the fit
+//                     is still in its registers — writes the merged node.  Every thread caches the minimum of its own queue slots
 //       membership    block erosion (ERODE_ALL_BORDER) and the seed pixels of the region growing, in the reference's order by a scan
-//       floodFill     the FIFO region grower, 128 queue entries at a time.  Its result depends on the visiting order only through
-//                     the state of the visited pixel, so the 512 visits of a chunk run in rounds: in each round every pixel takes
-//                     the earliest of its pending visits (atomicMin of the visit number), which keeps the per-pixel order of the
-//                     sequential loop; the pixels claimed by a chunk are appended to the queue in visit order by a scan
+//       floodFill     the FIFO region grower, 256 queue entries at a time (two per thread).  Its result depends on the visiting order
+//                     only through the state of the visited pixel, so the 1024 visits of a chunk run in rounds: in each round every
+//                     pixel takes the earliest of its pending visits (atomicMin of the visit number), which keeps the per-pixel order
+//                     of the sequential loop; what a visit computes without that state (vertex, distance, 3-sigma test) is done before
+//                     the rounds; the pixels claimed by a chunk are appended to the queue in visit order by a scan.  A chunk ends at
+//                     the queue length it started with
 //       cluster again on the planes the region growing connected, plane numbering, seg_output
-//   k_peac_members    plane_vertices_ and the member points as Frame::ComputePlanes reads them
+//   k_peac_members    plane_vertices_ and the member points as Frame::ComputePlanes reads them (optionally without the points
+//                     beyond mMax_point_dist: the lists drfe_peac_plane_points_voxel filters)
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
