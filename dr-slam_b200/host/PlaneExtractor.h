@@ -42,18 +42,18 @@ typedef std::array<double, 3> VertexType;
 const int kDepthWidth = 640;
 const int kDepthHeight = 480;
 
-struct ImagePointCloud {                                           // PlaneExtractor.h:40-58
+// the organized cloud as the reference exposes it (include/PlaneExtractor.h:40-58): row-major vertices, get() refuses points without depth
+struct ImagePointCloud {
   std::vector<VertexType> vertices;
   int w = 0, h = 0;
   int width() const { return w; }
   int height() const { return h; }
   bool get(const int row, const int col, double& x, double& y, double& z) const {
-    const int pixIdx = row * w + col;
-    z = vertices[pixIdx][2];
-    if (z == 0 || z != z) return false;
-    x = vertices[pixIdx][0];
-    y = vertices[pixIdx][1];
-    return true;
+    const VertexType& v = vertices[(size_t)row * w + col];
+    z = v[2];
+    const bool has_depth = z != 0 && z == z;                       // 0 or NaN: not a point
+    if (has_depth) { x = v[0]; y = v[1]; }
+    return has_depth;
   }
 };
 
