@@ -501,7 +501,7 @@ def main():
         orb.finish_batch()
         cape.finish_batch()
 
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(2 * args.steps, 40))                    # ~5 ms each: 40 of them, so that one slow copy does not move the figure
 
     def time_loop(fn):
         for _ in range(2):
@@ -551,7 +551,7 @@ def main():
             finish((n - 1) % 2)
         run_two(3)
         barrier()
-        n_two = 2 * e2e_steps
+        n_two = e2e_steps
         t0 = time.perf_counter()
         run_two(n_two)
         orb_b.sync(); cape_b.sync()
