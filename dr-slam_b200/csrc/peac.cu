@@ -268,13 +268,22 @@ __device__ int peac_cluster(const PeacDev& P, PeacNode* nodes, uint32_t* adj, Pe
       if (own_k >= kInfKey) { own_k = kInfKey; own_s = -1; own_q = 0x7FFFFFFF; }
       dirty = false;
     }
+    // the warp's minimum of (key, creation number) by three redux.sync steps: high word, low word among the lanes that hold the
+    // minimal high word, creation number among those that hold the minimal key (creation numbers are unique)
     long long bk = own_k;
     int bs = own_s, bq = own_q;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const long long ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
-      const int os = __shfl_xor_sync(0xFFFFFFFFu, bs, o), oq = __shfl_xor_sync(0xFFFFFFFFu, bq, o);
-      if (os >= 0 && (bs < 0 || ok < bk || (ok == bk && oq < bq))) { bk = ok; bs = os; bq = oq; }
+    {
+      const uint32_t hi = (uint32_t)((unsigned long long)own_k >> 32) ^ 0x80000000u;     // signed order as unsigned order
+      const uint32_t mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
+      const uint32_t lo = hi == mhi ? (uint32_t)own_k : 0xFFFFFFFFu;
+      const uint32_t mlo = __reduce_min_sync(0xFFFFFFFFu, lo);
+      const bool tie = hi == mhi && (uint32_t)own_k == mlo;
+      const uint32_t mq = __reduce_min_sync(0xFFFFFFFFu, tie ? (uint32_t)own_q : 0xFFFFFFFFu);
+      const unsigned win = __ballot_sync(0xFFFFFFFFu, tie && (uint32_t)own_q == mq);
+      const int src = __ffs(win) - 1;
+      bk = __shfl_sync(0xFFFFFFFFu, own_k, src);
+      bs = __shfl_sync(0xFFFFFFFFu, own_s, src);
+      bq = __shfl_sync(0xFFFFFFFFu, own_q, src);
     }
     if (lane == 0) { s_ktmp[wid] = bk; s_tmp[wid] = bs; s_tmp[4 + wid] = bq; }
     __syncthreads();
