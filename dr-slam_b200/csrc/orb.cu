@@ -1075,14 +1075,16 @@ __device__ __forceinline__ void blur_hfilter(const BlurRow& w, int (&h)[4]) {
 }
 __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int (&h)[4]) { blur_hfilter(blur_load(row), h); }
 
-__global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp, int f0) {
+__global__ void __launch_bounds__(256) k_blur(const OrbDev* __restrict__ Pp, int f0, int check_counts) {
   DRFE_GRID_DEP();
   const OrbDev& P = *Pp;
   int level = 0;
   while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blur_blk_off[level + 1]) ++level;
   const LevelDev& L = P.lv[level];
   const int f = blockIdx.y + f0;
-  if (P.lkp_cnt[f * P.nlevels + level] == 0) return;  // reference skips levels without keypoints (:1081)
+  // the reference skips levels without keypoints (:1081); when the blur runs beside FAST and the quadtree the counts are not there yet
+  // and every level is blurred (a blurred level without keypoints is never read)
+  if (check_counts && P.lkp_cnt[f * P.nlevels + level] == 0) return;
   // flattened (row group, 4-pixel column) index, columns fastest
   const int t = ((int)blockIdx.x - P.blur_blk_off[level]) * 256 + threadIdx.x;
   const int rg = (int)__umulhi((uint32_t)t, L.blur_magic);
@@ -1829,6 +1831,8 @@ struct drfe_orb {
   cudaStream_t aux[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {nullptr, nullptr, nullptr};
   cudaStream_t hi = nullptr;             // one priority level above `stream`, for launches of many frames
+  cudaStream_t blur_stream = nullptr;    // small launches: the blur beside FAST and the quadtree
+  cudaEvent_t ev_blur_fork = nullptr, ev_blur_join = nullptr;
   cudaEvent_t ev_hi = nullptr;
   int hi_min_frames = 0;
   uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
@@ -2085,6 +2089,11 @@ static int orb_build(drfe_orb* h) {
   // (DRFE_LAUNCH_PDL) keeps the plane kernels off the SMs (32 frames: 0.326 ms -> 0.370 ms; 64: 0.532 -> 0.613).
   // DRFE_ORB_PRIO / DRFE_CAPE_PRIO set the handle streams' own priority, DRFE_ORB_HI_MIN_FRAMES the threshold (0: never).
   { const char* e = getenv("DRFE_ORB_PRIO"); DRFE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, e ? atoi(e) : 0)); }
+  if (!(getenv("DRFE_ORB_NO_BLUR_FORK") && getenv("DRFE_ORB_NO_BLUR_FORK")[0] == '1')) {
+    DRFE_CUDA(cudaStreamCreateWithFlags(&h->blur_stream, cudaStreamNonBlocking));
+    DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_blur_fork, cudaEventDisableTiming));
+    DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_blur_join, cudaEventDisableTiming));
+  }
   {
     const char* e = getenv("DRFE_ORB_HI_MIN_FRAMES");
     h->hi_min_frames = e ? atoi(e) : kHiPrioMinFrames;
@@ -2218,6 +2227,9 @@ int drfe_orb_destroy(drfe_orb* h) {
   if (h->ev_shared) cudaEventDestroy(h->ev_shared);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_hi) cudaEventDestroy(h->ev_hi);
+  if (h->ev_blur_fork) cudaEventDestroy(h->ev_blur_fork);
+  if (h->ev_blur_join) cudaEventDestroy(h->ev_blur_join);
+  if (h->blur_stream) { cudaStreamSynchronize(h->blur_stream); cudaStreamDestroy(h->blur_stream); }
   if (h->hi) { cudaStreamSynchronize(h->hi); cudaStreamDestroy(h->hi); }
   for (int p = 0; p < drfe_orb::kMaxSplit - 1; ++p) {
     if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]);
@@ -2289,11 +2301,22 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
     }
   }
   if (timed) h->timer.mark("pyramid", st);
+  // small launches are a chain of latencies: the blur needs the pyramid only, so it runs on a second stream beside FAST and the quadtree
+  // and is joined in front of the descriptors (32 frames: ORB chain 0.29 -> 0.26 ms).  Large launches fill the GPU kernel by kernel
+  // (there the fork gained nothing), timed launches keep the stages one after the other.
+  const bool fork_blur = !(timed && h->timer.enabled) && n <= kPdlMaxFrames && h->blur_stream != nullptr;
+  if (fork_blur) {
+    DRFE_CUDA(cudaEventRecord(h->ev_blur_fork, st));
+    DRFE_CUDA(cudaStreamWaitEvent(h->blur_stream, h->ev_blur_fork, 0));
+    DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, n), 256, 0, h->blur_stream, h->dd, f0, 0);
+    DRFE_CUDA(cudaEventRecord(h->ev_blur_join, h->blur_stream));
+  }
   DRFE_LAUNCH_PDL(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps);
   if (timed) h->timer.mark("fast", st);
   DRFE_LAUNCH_PDL(k_quadtree<256>, dim3(nl, n), 256, h->quad_smem, st, h->dd, f0);
   if (timed) h->timer.mark("quadtree", st);
-  DRFE_LAUNCH_PDL(k_blur, dim3(h->blur_blocks, n), 256, 0, st, h->dd, f0);
+  if (fork_blur) DRFE_CUDA(cudaStreamWaitEvent(st, h->ev_blur_join, 0));
+  else DRFE_LAUNCH_PDL(k_blur, dim3(h->blur_blocks, n), 256, 0, st, h->dd, f0, 1);
   if (timed) h->timer.mark("blur", st);
   DRFE_LAUNCH_PDL(k_orient_describe, dim3((h->max_lkp + kOdWarps * kOdG - 1) / (kOdWarps * kOdG), nl, n), kOdWarps * 32, 0, st, h->dd, f0);
   if (timed) h->timer.mark("orient_describe", st);
