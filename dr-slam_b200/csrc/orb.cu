@@ -463,11 +463,11 @@ __device__ __forceinline__ uint32_t fast_compass_group(const uint32_t* __restric
 //      nothing (the minThFAST fallback, ORBextractor.cc:812-816), in arbitrary order (the
 //      quadtree orders by a key)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp, int f0, const __grid_constant__ FastMaps maps) {
+__global__ void __launch_bounds__(THREADS) k_fast_strips(const OrbDev* __restrict__ Pp, int f0, const __grid_constant__ FastMaps maps, int strip0) {
   DRFE_GRID_DEP();
   extern __shared__ __align__(128) uint8_t smem[];
   const OrbDev& P = *Pp;
-  const StripDev strip = P.strips[blockIdx.x];
+  const StripDev strip = P.strips[blockIdx.x + strip0];
   const int f = blockIdx.y + f0;
   const LevelDev& L = P.lv[strip.level];
   const int TP = P.fast_tp;                  // smem row pitch (multiple of 16)
@@ -1833,6 +1833,9 @@ struct drfe_orb {
   cudaStream_t hi = nullptr;             // one priority level above `stream`, for launches of many frames
   cudaStream_t blur_stream = nullptr;    // small launches: the blur beside FAST and the quadtree
   cudaEvent_t ev_blur_fork = nullptr, ev_blur_join = nullptr;
+  cudaStream_t fast0_stream = nullptr;   // small launches: FAST on level 0 beside the resizes of levels 1..
+  cudaEvent_t ev_l0 = nullptr, ev_fast0 = nullptr;
+  int nstrips_l0 = 0;
   cudaEvent_t ev_hi = nullptr;
   int hi_min_frames = 0;
   uint8_t* d_color = nullptr; size_t color_bytes = 0; bool gray_valid = false;   // drfe_orb_enqueue_color
@@ -2059,6 +2062,8 @@ static int orb_build(drfe_orb* h) {
     if (L.w > 4000 || L.h > 4000) { set_error("image too large (12-bit packed coordinates)"); return DRFE_ERR_ARG; }
   }
   h->nstrips = (int)strips.size();
+  h->nstrips_l0 = 0;
+  for (const StripDev& sd : strips) h->nstrips_l0 += sd.level == 0;
   D.cand_fstride = cand_total; D.lkp_fstride = lkp_total; D.kp_cap = kp_cap; h->max_lkp = 0;
   for (int l = 0; l < nl; ++l) h->max_lkp = std::max(h->max_lkp, D.lv[l].node_cap);
   D.fast_tp = max_strip_tp;                       // smem row pitch of a FAST strip (TMA rows are 16 B multiples)
@@ -2093,6 +2098,9 @@ static int orb_build(drfe_orb* h) {
     DRFE_CUDA(cudaStreamCreateWithFlags(&h->blur_stream, cudaStreamNonBlocking));
     DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_blur_fork, cudaEventDisableTiming));
     DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_blur_join, cudaEventDisableTiming));
+    DRFE_CUDA(cudaStreamCreateWithFlags(&h->fast0_stream, cudaStreamNonBlocking));
+    DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_l0, cudaEventDisableTiming));
+    DRFE_CUDA(cudaEventCreateWithFlags(&h->ev_fast0, cudaEventDisableTiming));
   }
   {
     const char* e = getenv("DRFE_ORB_HI_MIN_FRAMES");
@@ -2230,6 +2238,9 @@ int drfe_orb_destroy(drfe_orb* h) {
   if (h->ev_blur_fork) cudaEventDestroy(h->ev_blur_fork);
   if (h->ev_blur_join) cudaEventDestroy(h->ev_blur_join);
   if (h->blur_stream) { cudaStreamSynchronize(h->blur_stream); cudaStreamDestroy(h->blur_stream); }
+  if (h->ev_l0) cudaEventDestroy(h->ev_l0);
+  if (h->ev_fast0) cudaEventDestroy(h->ev_fast0);
+  if (h->fast0_stream) { cudaStreamSynchronize(h->fast0_stream); cudaStreamDestroy(h->fast0_stream); }
   if (h->hi) { cudaStreamSynchronize(h->hi); cudaStreamDestroy(h->hi); }
   for (int p = 0; p < drfe_orb::kMaxSplit - 1; ++p) {
     if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]);
@@ -2287,6 +2298,15 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
     const long long threads = (long long)L.rows * (ci + cb);
     DRFE_LAUNCH_PDL(k_pyr_level0, dim3((unsigned)((threads + 255) / 256), n), 256, 0, st, h->dd, src, rs, fs, f0, ci, ci_magic, cb, cb_magic);
   }
+  // small launches: FAST on level 0 (a third of its work) needs level 0 only and runs on another stream beside the seven resizes
+  const bool fork_small = !(timed && h->timer.enabled) && n <= kPdlMaxFrames && h->blur_stream != nullptr;
+  const bool fork_fast0 = fork_small && nl > 1 && h->nstrips_l0 > 0 && h->nstrips_l0 < h->nstrips;
+  if (fork_fast0) {
+    DRFE_CUDA(cudaEventRecord(h->ev_l0, st));
+    DRFE_CUDA(cudaStreamWaitEvent(h->fast0_stream, h->ev_l0, 0));
+    DRFE_LAUNCH(k_fast_strips<256>, dim3(h->nstrips_l0, n), 256, h->fast_smem, h->fast0_stream, h->dd, f0, h->fast_maps, 0);
+    DRFE_CUDA(cudaEventRecord(h->ev_fast0, h->fast0_stream));
+  }
   for (int l = 1; l < nl; ++l) {
     const LevelDev& L = D.lv[l];
     if (D.pcols) {
@@ -2304,14 +2324,19 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
   // small launches are a chain of latencies: the blur needs the pyramid only, so it runs on a second stream beside FAST and the quadtree
   // and is joined in front of the descriptors (32 frames: ORB chain 0.29 -> 0.26 ms).  Large launches fill the GPU kernel by kernel
   // (there the fork gained nothing), timed launches keep the stages one after the other.
-  const bool fork_blur = !(timed && h->timer.enabled) && n <= kPdlMaxFrames && h->blur_stream != nullptr;
+  const bool fork_blur = fork_small;
   if (fork_blur) {
     DRFE_CUDA(cudaEventRecord(h->ev_blur_fork, st));
     DRFE_CUDA(cudaStreamWaitEvent(h->blur_stream, h->ev_blur_fork, 0));
     DRFE_LAUNCH(k_blur, dim3(h->blur_blocks, n), 256, 0, h->blur_stream, h->dd, f0, 0);
     DRFE_CUDA(cudaEventRecord(h->ev_blur_join, h->blur_stream));
   }
-  DRFE_LAUNCH_PDL(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps);
+  if (fork_fast0) {
+    DRFE_LAUNCH_PDL(k_fast_strips<256>, dim3(h->nstrips - h->nstrips_l0, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps, h->nstrips_l0);
+    DRFE_CUDA(cudaStreamWaitEvent(st, h->ev_fast0, 0));
+  } else {
+    DRFE_LAUNCH_PDL(k_fast_strips<256>, dim3(h->nstrips, n), 256, h->fast_smem, st, h->dd, f0, h->fast_maps, 0);
+  }
   if (timed) h->timer.mark("fast", st);
   DRFE_LAUNCH_PDL(k_quadtree<256>, dim3(nl, n), 256, h->quad_smem, st, h->dd, f0);
   if (timed) h->timer.mark("quadtree", st);
