@@ -2299,7 +2299,9 @@ static int orb_launch_on(drfe_orb* h, cudaStream_t st, int f0, int n, const uint
     DRFE_LAUNCH_PDL(k_pyr_level0, dim3((unsigned)((threads + 255) / 256), n), 256, 0, st, h->dd, src, rs, fs, f0, ci, ci_magic, cb, cb_magic);
   }
   // small launches: FAST on level 0 (a third of its work) needs level 0 only and runs on another stream beside the seven resizes
-  const bool fork_small = !(timed && h->timer.enabled) && n <= kPdlMaxFrames && h->blur_stream != nullptr;
+  // (only for drfe_orb_enqueue — `timed` — with the stage timers off: the chunks of the pipelined batch calls are bound by the host link, and
+  // the extra event calls per chunk cost the issuing thread more than the kernels gain: e2e 50.1 k -> 49.3 k frames/s with the forks there)
+  const bool fork_small = timed && !h->timer.enabled && n <= kPdlMaxFrames && h->blur_stream != nullptr;
   const bool fork_fast0 = fork_small && nl > 1 && h->nstrips_l0 > 0 && h->nstrips_l0 < h->nstrips;
   if (fork_fast0) {
     DRFE_CUDA(cudaEventRecord(h->ev_l0, st));
